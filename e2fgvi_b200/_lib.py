@@ -1,0 +1,58 @@
+"""ctypes binding of ``libe2fgvi_b200.so`` (declared in ``include/e2fgvi_b200.h``).
+
+There is NO fallback: if the library is missing or a call fails the caller gets an exception.
+"""
+import ctypes
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libe2fgvi_b200.so")
+
+_c = ctypes
+_vp, _fp, _i, _f = _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_float
+
+# name -> (restype, argtypes); kept in the same order as the header so tests can diff them.
+SIGNATURES = {
+    "e2f_version": (_c.c_char_p, []),
+    "e2f_last_error": (_c.c_char_p, []),
+    "e2f_flow_warp": (_i, [_vp, _fp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    "e2f_flow_warp_nchw": (_i, [_fp, _fp, _fp, _i, _i, _i, _i, _i, _vp]),
+    "e2f_dcn_pack_weight": (_i, [_fp, _vp, _i, _i, _i, _vp]),
+    "e2f_modulated_deform_conv2d": (_i, [_vp, _fp, _fp, _vp, _fp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "e2f_deform_align_fused": (_i, [_vp, _fp, _fp, _fp, _vp, _fp, _vp, _i, _i, _i, _i, _i, _i, _f, _i, _vp]),
+    "e2f_focal_window_attention": (_i, [_vp, _vp, _vp] + [_i] * 13 + [_f, _i, _vp]),
+    "e2f_launch_count": (_c.c_int64, []),
+}
+
+_lib = None
+
+
+class ExtensionMissing(RuntimeError):
+    pass
+
+
+def load():
+    """Load (once) and return the ctypes library. Raises ExtensionMissing if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ExtensionMissing(
+            f"{LIB_PATH} not found: build it with `python -m e2fgvi_b200.build` "
+            "(there is no CPU or PyTorch fallback for the hot-path kernels)")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(status, what):
+    if status == 0:
+        return
+    msg = load().e2f_last_error().decode("utf-8", "replace")
+    if status == -1:
+        raise ValueError(f"{what}: {msg}")
+    raise RuntimeError(f"{what} failed (status {status}): {msg}")

@@ -1,0 +1,89 @@
+"""Flow completion on the hot path: SPyNet and ``flow_warp`` (reference: model/modules/flow_comp.py:49-226,345-383).
+
+State-dict layout (must stay byte-compatible with released checkpoints):
+``basic_module.{0..5}.basic_module.{0..4}.conv.{weight,bias}`` + buffers ``mean``/``std`` [1,3,1,1].
+The ``.conv.`` level exists in the reference because it wraps each conv in ``mmcv.cnn.ConvModule``
+(flow_comp.py:181-215); here a tiny holder module provides the same key path with no mmcv dependency.
+The constructor never touches the network (the reference downloads pretrained weights, flow_comp.py:59-72;
+E2FGVI checkpoints carry ``update_spynet.*`` anyway).
+"""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from ... import ops
+
+# (cin, cout) of the five 7x7 convs of one pyramid level, ReLU after all but the last (flow_comp.py:181-215)
+_LEVEL_CONVS = ((8, 32), (32, 64), (64, 32), (32, 16), (16, 2))
+_NUM_LEVELS = 6
+
+
+def flow_warp(x, flow, interpolation="bilinear", padding_mode="zeros", align_corners=True):
+    """Same signature and error behaviour as the reference ``flow_warp`` (flow_comp.py:345-383); CUDA kernel."""
+    return ops.flow_warp(x, flow, interpolation, padding_mode, align_corners)
+
+
+class _ConvHolder(nn.Module):
+    """Gives a conv the ``<idx>.conv.{weight,bias}`` key path of mmcv's ConvModule."""
+
+    def __init__(self, cin, cout):
+        super().__init__()
+        self.conv = nn.Conv2d(cin, cout, kernel_size=7, stride=1, padding=3)
+
+
+class SPyNetBasicModule(nn.Module):
+    """One pyramid level: 5 x (7x7 conv), ReLU between (flow_comp.py:172-226)."""
+
+    def __init__(self):
+        super().__init__()
+        self.basic_module = nn.Sequential(*[_ConvHolder(ci, co) for ci, co in _LEVEL_CONVS])
+
+    def forward(self, tensor_input):
+        y = tensor_input
+        last = len(self.basic_module) - 1
+        for i, holder in enumerate(self.basic_module):
+            y = holder.conv(y)
+            if i != last:
+                y = F.relu(y, inplace=True)
+        return y
+
+
+class SPyNet(nn.Module):
+    """6-level coarse-to-fine flow estimator (flow_comp.py:49-169). ``forward(ref, supp) -> flow (n,2,h,w)``."""
+
+    def __init__(self, use_pretrain=False, pretrained=None):
+        super().__init__()
+        del use_pretrain, pretrained  # accepted for signature compatibility; never fetched
+        self.basic_module = nn.ModuleList([SPyNetBasicModule() for _ in range(_NUM_LEVELS)])
+        self.register_buffer("mean", torch.tensor([0.485, 0.456, 0.406]).view(1, 3, 1, 1))
+        self.register_buffer("std", torch.tensor([0.229, 0.224, 0.225]).view(1, 3, 1, 1))
+
+    def compute_flow(self, ref, supp):
+        """ref/supp (n,3,h,w) with h,w multiples of 32 (flow_comp.py:84-134)."""
+        n, _, h, w = ref.shape
+        pyr_ref = [(ref - self.mean) / self.std]
+        pyr_supp = [(supp - self.mean) / self.std]
+        for _ in range(_NUM_LEVELS - 1):
+            pyr_ref.append(F.avg_pool2d(pyr_ref[-1], kernel_size=2, stride=2, count_include_pad=False))
+            pyr_supp.append(F.avg_pool2d(pyr_supp[-1], kernel_size=2, stride=2, count_include_pad=False))
+        flow = ref.new_zeros(n, 2, h >> (_NUM_LEVELS - 1), w >> (_NUM_LEVELS - 1))
+        for level in range(_NUM_LEVELS):
+            r, s = pyr_ref[_NUM_LEVELS - 1 - level], pyr_supp[_NUM_LEVELS - 1 - level]
+            if level == 0:
+                flow_up = flow
+            else:
+                flow_up = F.interpolate(flow, scale_factor=2, mode="bilinear", align_corners=True) * 2.0
+            warped = flow_warp(s, flow_up.permute(0, 2, 3, 1), padding_mode="border")
+            flow = flow_up + self.basic_module[level](torch.cat([r, warped, flow_up], 1))
+        return flow
+
+    def forward(self, ref, supp):
+        h, w = ref.shape[2:4]
+        w_up = w if w % 32 == 0 else 32 * (w // 32 + 1)
+        h_up = h if h % 32 == 0 else 32 * (h // 32 + 1)
+        ref = F.interpolate(ref, size=(h_up, w_up), mode="bilinear", align_corners=False)
+        supp = F.interpolate(supp, size=(h_up, w_up), mode="bilinear", align_corners=False)
+        flow = F.interpolate(self.compute_flow(ref, supp), size=(h, w), mode="bilinear", align_corners=False)
+        # rescale u by w/w_up and v by h/h_up (flow_comp.py:164-167)
+        scale = flow.new_tensor([float(w) / float(w_up), float(h) / float(h_up)]).view(1, 2, 1, 1)
+        return flow * scale

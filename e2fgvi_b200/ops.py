@@ -1,0 +1,180 @@
+"""Operator-level mirror of the three reference boundaries the CUDA kernels sit behind:
+
+* ``flow_warp``                   — model/modules/flow_comp.py:345-383
+* ``modulated_deform_conv2d``     — mmcv.ops.modulated_deform_conv2d as called at model/modules/feat_prop.py:55-58
+* ``deform_align_fused``          — the tail of SecondOrderDeformableAlignment.forward, feat_prop.py:41-58
+* ``focal_window_attention``      — WindowAttention.forward between qkv and proj, tfocal_transformer.py:226-396
+
+Same names / argument meaning / error behaviour as the reference operators; every call goes through the C ABI of
+``libe2fgvi_b200.so`` on the current CUDA stream.  There is no CPU path: CPU tensors raise.
+"""
+import torch
+
+from . import _lib
+
+_PAD = {"zeros": 0, "border": 1}
+_DT = {torch.float32: 0, torch.float16: 1}
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("e2fgvi_b200 kernels need CUDA tensors on a B200 (sm_100a); there is no CPU fallback")
+
+
+def _is_cl(x):
+    """True if the 4-D tensor is dense NHWC in memory (channels_last or a permuted NHWC view)."""
+    n, c, h, w = x.shape
+    return x.stride() == (h * w * c, 1, w * c, c)
+
+
+def flow_warp(x, flow, interpolation="bilinear", padding_mode="zeros", align_corners=True):
+    """Warp ``x`` (n,c,h,w) with ``flow`` (n,h,w,2; pixel units, [...,0] = x-displacement).
+
+    Mirrors flow_comp.py:345-383, including the ValueError on a spatial mismatch (:364-366).  Output keeps the
+    memory format of ``x`` (NCHW-contiguous or channels_last) and its dtype (fp32 / fp16).
+    """
+    if x.size()[-2:] != flow.size()[1:3]:
+        raise ValueError(f"The spatial sizes of input ({x.size()[-2:]}) and "
+                         f"flow ({flow.size()[1:3]}) are not the same.")
+    if interpolation != "bilinear" or not align_corners:
+        raise NotImplementedError("only bilinear / align_corners=True is on the E2FGVI path")
+    if padding_mode not in _PAD:
+        raise NotImplementedError(f"padding_mode={padding_mode!r} is not on the E2FGVI path")
+    _need_cuda(x, flow)
+    lib = _lib.load()
+    n, c, h, w = x.shape
+    flow = flow.contiguous().float()
+    vec = 8 if x.dtype == torch.float16 else 4
+    if x.dtype in _DT and _is_cl(x) and c % vec == 0:
+        out = torch.empty_like(x)  # preserves strides (dense)
+        st = lib.e2f_flow_warp(x.data_ptr(), flow.data_ptr(), out.data_ptr(), n, h, w, c, _DT[x.dtype],
+                               _PAD[padding_mode], _stream())
+        _lib.check(st, "e2f_flow_warp")
+        return out
+    xc = x.contiguous()
+    if xc.dtype != torch.float32:
+        xc = xc.float()
+    out = torch.empty_like(xc)
+    st = lib.e2f_flow_warp_nchw(xc.data_ptr(), flow.data_ptr(), out.data_ptr(), n, c, h, w, _PAD[padding_mode],
+                                _stream())
+    _lib.check(st, "e2f_flow_warp_nchw")
+    return out if out.dtype == x.dtype else out.to(x.dtype)
+
+
+_PACK_CACHE = {}
+
+
+def pack_dcn_weight(weight, deform_groups):
+    """fp32 [Cout,Cin,3,3] -> fp16 [Cout, 9*Cin] GEMM operand in sampler K-order (cached per weight version)."""
+    _need_cuda(weight)
+    key = (weight.data_ptr(), weight._version, tuple(weight.shape), deform_groups, weight.device.index)
+    hit = _PACK_CACHE.get(key)
+    if hit is not None:
+        return hit
+    cout, cin, kh, kw = weight.shape
+    if (kh, kw) != (3, 3):
+        raise ValueError("only 3x3 deformable kernels are on the E2FGVI path")
+    w32 = weight.detach().contiguous().float()
+    packed = torch.empty(cout, 9 * cin, dtype=torch.float16, device=weight.device)
+    st = _lib.load().e2f_dcn_pack_weight(w32.data_ptr(), packed.data_ptr(), cout, cin, deform_groups, _stream())
+    _lib.check(st, "e2f_dcn_pack_weight")
+    if len(_PACK_CACHE) > 64:
+        _PACK_CACHE.clear()
+    _PACK_CACHE[key] = packed
+    return packed
+
+
+def _pair(v):
+    return tuple(v) if isinstance(v, (tuple, list)) else (v, v)
+
+
+def modulated_deform_conv2d(x, offset, mask, weight, bias=None, stride=1, padding=0, dilation=1, groups=1,
+                            deform_groups=1, out_dtype=torch.float32):
+    """Drop-in for ``mmcv.ops.modulated_deform_conv2d`` (call site feat_prop.py:55-58).
+
+    x (n,cin,h,w), offset (n,2*9*dg,h,w) with channel (g*9+tap)*2+{dy,dx}, mask (n,9*dg,h,w), weight
+    (cout,cin,3,3).  Returns (n,cout,h,w) in channels_last memory format.
+    """
+    if _pair(stride) != (1, 1) or _pair(padding) != (1, 1) or _pair(dilation) != (1, 1) or groups != 1:
+        raise NotImplementedError("E2FGVI uses 3x3 / stride 1 / padding 1 / dilation 1 / groups 1 only")
+    _need_cuda(x, offset, mask, weight, bias)
+    n, cin, h, w = x.shape
+    cout = weight.shape[0]
+    if offset.shape != (n, 18 * deform_groups, h, w) or mask.shape != (n, 9 * deform_groups, h, w):
+        raise ValueError(f"offset/mask shapes {tuple(offset.shape)}/{tuple(mask.shape)} do not match x {tuple(x.shape)}")
+    wp = pack_dcn_weight(weight, deform_groups)
+    x_cl = x.to(dtype=torch.float16, memory_format=torch.channels_last)
+    off_cl = offset.to(dtype=torch.float32, memory_format=torch.channels_last)
+    msk_cl = mask.to(dtype=torch.float32, memory_format=torch.channels_last)
+    b32 = None if bias is None else bias.detach().float().contiguous()
+    out = torch.empty((n, cout, h, w), dtype=out_dtype, device=x.device, memory_format=torch.channels_last)
+    st = _lib.load().e2f_modulated_deform_conv2d(
+        x_cl.data_ptr(), off_cl.data_ptr(), msk_cl.data_ptr(), wp.data_ptr(),
+        None if b32 is None else b32.data_ptr(), out.data_ptr(), n, h, w, cin, cout, deform_groups,
+        _DT[out_dtype], _stream())
+    _lib.check(st, "e2f_modulated_deform_conv2d")
+    return out
+
+
+def deform_align_fused(x, head, flow_1, flow_2, w_packed, bias, deform_groups, max_residue_magnitude=10.0,
+                       out_dtype=torch.float32):
+    """feat_prop.py:41-58 in one kernel: 10*tanh + flow.flip(1) add, sigmoid, deformable sampling, GEMM, bias.
+
+    x (n,cin,h,w) fp16 channels_last; head (n,27*dg,h,w) fp32 channels_last (raw conv_offset output);
+    flow_k (n,2,h,w) any layout (converted to (n,h,w,2) fp32).  Returns (n,cout,h,w) channels_last.
+    """
+    _need_cuda(x, head, flow_1, flow_2, w_packed, bias)
+    n, cin, h, w = x.shape
+    cout = w_packed.shape[0]
+    if x.dtype != torch.float16 or not _is_cl(x):
+        x = x.to(dtype=torch.float16, memory_format=torch.channels_last)
+    if head.dtype != torch.float32 or not _is_cl(head):
+        head = head.to(dtype=torch.float32, memory_format=torch.channels_last)
+    f1 = flow_1.permute(0, 2, 3, 1).contiguous().float()
+    f2 = flow_2.permute(0, 2, 3, 1).contiguous().float()
+    b32 = None if bias is None else bias.detach().float().contiguous()
+    out = torch.empty((n, cout, h, w), dtype=out_dtype, device=x.device, memory_format=torch.channels_last)
+    st = _lib.load().e2f_deform_align_fused(
+        x.data_ptr(), head.data_ptr(), f1.data_ptr(), f2.data_ptr(), w_packed.data_ptr(),
+        None if b32 is None else b32.data_ptr(), out.data_ptr(), n, h, w, cin, cout, deform_groups,
+        float(max_residue_magnitude), _DT[out_dtype], _stream())
+    _lib.check(st, "e2f_deform_align_fused")
+    return out
+
+
+def focal_window_attention(qkv, qkv_pooled, num_heads, window_size, expand_size, focal_window, scale,
+                           out_dtype=torch.float16):
+    """softmax(q k_all^T) v_all of tfocal_transformer.py:226-396, un-partitioned output.
+
+    qkv (B,T,H,W,3C) fp16, qkv_pooled (B,T,nWh,nWw,3C) fp16 or None (focal_level 1) -> (B,T,H,W,C).
+    """
+    _need_cuda(qkv, qkv_pooled)
+    B, T, H, W, C3 = qkv.shape
+    C = C3 // 3
+    wh, ww = window_size
+    if H % wh or W % ww:
+        raise ValueError(f"token grid {H}x{W} is not a multiple of the window {wh}x{ww}")
+    if qkv.dtype != torch.float16 or not qkv.is_contiguous():
+        qkv = qkv.contiguous().half()
+    use_pooled = qkv_pooled is not None
+    if use_pooled:
+        if qkv_pooled.shape != (B, T, H // wh, W // ww, C3):
+            raise ValueError(f"qkv_pooled shape {tuple(qkv_pooled.shape)} != {(B, T, H // wh, W // ww, C3)}")
+        if qkv_pooled.dtype != torch.float16 or not qkv_pooled.is_contiguous():
+            qkv_pooled = qkv_pooled.contiguous().half()
+    out = torch.empty((B, T, H, W, C), dtype=out_dtype, device=qkv.device)
+    st = _lib.load().e2f_focal_window_attention(
+        qkv.data_ptr(), qkv_pooled.data_ptr() if use_pooled else None, out.data_ptr(), B, T, H, W, num_heads,
+        C // num_heads, wh, ww, expand_size[0], expand_size[1], focal_window[0], focal_window[1],
+        1 if use_pooled else 0, float(scale), _DT[out_dtype], _stream())
+    _lib.check(st, "e2f_focal_window_attention")
+    return out
+
+
+def launch_count():
+    return int(_lib.load().e2f_launch_count())

@@ -1,0 +1,102 @@
+/* e2fgvi_b200 — C ABI of the sm_100a hot-path kernels behind E2FGVI's InpaintGenerator.forward.
+ *
+ * The reference (MCG-NKU/E2FGVI) is pure Python and has no C ABI of its own; each entry point below replaces
+ * one operator boundary of the reference and cites it.  A reference maintainer binds these with ctypes (see
+ * INTEGRATION.md).  Conventions:
+ *   - every pointer is a DEVICE pointer owned by the caller; the library never allocates or frees caller memory
+ *     and keeps no persistent device state (TMA descriptors are built per call on the host);
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream); calls are asynchronous on it and
+ *     re-entrant across streams;
+ *   - return value: 0 = OK, negative = argument error (E2F_ERR_*), positive = cudaError_t of the launch;
+ *     e2f_last_error() returns a thread-local human-readable message for the last non-zero return;
+ *   - activation layout is NHWC ("channels last"), i.e. [N][H][W][C] contiguous; token tensors are
+ *     [B][T][H][W][C] contiguous.
+ */
+#ifndef E2FGVI_B200_H_
+#define E2FGVI_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define E2F_OK 0
+#define E2F_ERR_BAD_ARG (-1)
+#define E2F_ERR_UNSUPPORTED (-2)
+#define E2F_ERR_ALIGNMENT (-3)
+#define E2F_ERR_DRIVER (-4)
+
+/* element types */
+#define E2F_F32 0
+#define E2F_F16 1
+
+/* padding modes of e2f_flow_warp (reference: F.grid_sample padding_mode) */
+#define E2F_PAD_ZEROS 0
+#define E2F_PAD_BORDER 1
+
+/* Library / build identification: "e2fgvi_b200 <version> sm_100a". */
+const char* e2f_version(void);
+/* Thread-local message describing the last failing call on this thread ("" if none). */
+const char* e2f_last_error(void);
+
+/* flow_warp — replaces model/modules/flow_comp.py:345-383 (bilinear grid_sample at pixel+flow,
+ * align_corners=True, so the normalise/denormalise round trip cancels: sample at (x+flow[...,0], y+flow[...,1])).
+ *   x    [N][H][W][C]  (dtype: E2F_F32 or E2F_F16)        flow [N][H][W][2] fp32 (u = x-displacement first)
+ *   out  [N][H][W][C]  (same dtype as x)
+ * C must be a multiple of 4 (fp32) / 8 (fp16), or C <= 4 for the small-channel path (flows, RGB). */
+int e2f_flow_warp(const void* x, const float* flow, void* out, int n, int h, int w, int c, int dtype,
+                  int pad_mode, void* stream);
+
+/* flow_warp on NCHW fp32 tensors (the reference's native layout), used for few-channel inputs
+ * (2-channel flows in feat_prop.py:120, 3-channel images in flow_comp.py:127). */
+int e2f_flow_warp_nchw(const float* x, const float* flow, float* out, int n, int c, int h, int w, int pad_mode,
+                       void* stream);
+
+/* Pack a DCN weight [Cout][Cin][3][3] fp32 (mmcv / torch layout, feat_prop.py:13 via ModulatedDeformConv2d)
+ * into the fp16 GEMM operand [Cout][K], K = 9*Cin, k = (g*9 + tap)*cpg + c_in_group with cpg = Cin/deform_groups.
+ * This K order makes one 64-wide K block = 64/cpg consecutive sample points of the sampler. */
+int e2f_dcn_pack_weight(const float* w, void* w_packed_f16, int cout, int cin, int deform_groups, void* stream);
+
+/* modulated_deform_conv2d — replaces mmcv.ops.modulated_deform_conv2d as called at feat_prop.py:55-58
+ * (3x3, stride 1, padding 1, dilation 1, groups 1).  Sampling + im2col are fused into the tcgen05 GEMM; no
+ * column buffer is materialised.
+ *   x        [N][H][W][Cin] fp16           offset [N][H][W][2*9*dg] fp32, channel (g*9+tap)*2 + {0:dy, 1:dx}
+ *   mask     [N][H][W][9*dg] fp32 (already sigmoid-ed), channel g*9+tap
+ *   w_packed [Cout][9*Cin] fp16 from e2f_dcn_pack_weight      bias [Cout] fp32 or NULL
+ *   out      [N][H][W][Cout] (out_dtype E2F_F32 or E2F_F16)
+ * Supported: Cin = 256, Cout = 128, dg = 16 (the only instance on the path). */
+int e2f_modulated_deform_conv2d(const void* x, const float* offset, const float* mask, const void* w_packed,
+                                const float* bias, void* out, int n, int h, int w, int cin, int cout,
+                                int deform_groups, int out_dtype, void* stream);
+
+/* Fused SecondOrderDeformableAlignment tail — replaces feat_prop.py:41-58: takes the raw 27*dg-channel output of
+ * conv_offset (`head`, [N][H][W][27*dg] fp32: o1 | o2 | mask), applies offset = max_residue * tanh(o) +
+ * flow_k.flip(1) (first half of the groups uses flow_1, second half flow_2), mask = sigmoid(.), then the DCN.
+ *   flow1, flow2 [N][H][W][2] fp32 (u, v). */
+int e2f_deform_align_fused(const void* x, const float* head, const float* flow1, const float* flow2,
+                           const void* w_packed, const float* bias, void* out, int n, int h, int w, int cin,
+                           int cout, int deform_groups, float max_residue, int out_dtype, void* stream);
+
+/* Temporal focal window attention core — replaces model/modules/tfocal_transformer.py:226-396 (everything in
+ * WindowAttention.forward between the qkv Linear and the proj Linear): window partition of q, the own-window keys,
+ * the 4 circularly rolled ring key sets (with their duplicated tokens), the pooled-window keys with the -100
+ * logit on zero-padded neighbours, softmax and P*V, written back un-partitioned (fuses window_reverse :528).
+ *   qkv        [B][T][H][W][3*C] fp16  (q | k | v, each C = heads*head_dim, head-major inside C)
+ *   qkv_pooled [B][T][nWh][nWw][3*C] fp16 (the same Linear applied to the pooled window tokens; q part unused)
+ *   out        [B][T][H][W][C] (out_dtype)
+ *   window (wh, ww); expand (eh, ew) = window//2; focal window (fh, fw) (pooled neighbourhood, odd sizes);
+ *   nWh = H/wh, nWw = W/ww.  scale multiplies q.k (head_dim^-0.5).  head_dim must be 128.
+ *   use_pooled = 0 runs focal_level 1 (no pooled keys). */
+int e2f_focal_window_attention(const void* qkv, const void* qkv_pooled, void* out, int b, int t, int h, int w,
+                               int heads, int head_dim, int wh, int ww, int eh, int ew, int fh, int fw,
+                               int use_pooled, float scale, int out_dtype, void* stream);
+
+/* Number of kernel launches issued through this library since load (all threads); used by bench.py's
+ * "gpu_launches" accounting. */
+int64_t e2f_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* E2FGVI_B200_H_ */
