@@ -1,0 +1,154 @@
+"""InpaintGenerator — the drop-in boundary (reference: model/e2fgvi.py:71-263, model/e2fgvi_hq.py).
+
+Contract kept: ``InpaintGenerator()`` takes no required args, ``load_state_dict`` of a reference
+checkpoint is strict-compatible (243 entries base / 244 HQ), and
+``forward(masked_frames[b,t,3,H,W], num_local_frames) -> (pred[b*t,3,H,W], (flows_fwd, flows_bwd))``.
+The constructor never downloads SPyNet weights.
+"""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .modules.flow_comp import SPyNet
+from .modules.feat_prop import BidirectionalPropagation, SecondOrderDeformableAlignment
+from .modules.tfocal_transformer import SoftComp, SoftSplit, TemporalFocalTransformerBlock
+
+# Encoder convs: (cin, cout, stride, groups); LeakyReLU(0.2) after each (e2fgvi.py:75-94).
+# From the 6th conv on, the input is the 256-ch tensor x0 (input of conv 5) concatenated group-wise with the
+# previous output (e2fgvi.py:96-109).
+_ENC = ((3, 64, 2, 1), (64, 64, 1, 1), (64, 128, 2, 1), (128, 256, 1, 1), (256, 384, 1, 1),
+        (640, 512, 1, 2), (768, 384, 1, 4), (640, 256, 1, 8), (512, 128, 1, 1))
+
+
+class BaseNetwork(nn.Module):
+    def print_network(self):
+        n = sum(p.numel() for p in self.parameters())
+        print(f"Network [{type(self).__name__}] was created. Total number of parameters: {n / 1e6:.1f} million.")
+
+    def init_weights(self, init_type="normal", gain=0.02):
+        """N(0, gain) on every Conv*/Linear weight, zero bias (e2fgvi.py:29-68, 'normal' branch only)."""
+        if init_type != "normal":
+            raise NotImplementedError("only the reference default init_type='normal' is provided")
+        for m in self.modules():
+            cls = type(m).__name__
+            if hasattr(m, "weight") and ("Conv" in cls or "Linear" in cls) and isinstance(m.weight, torch.Tensor):
+                nn.init.normal_(m.weight.data, 0.0, gain)
+                if getattr(m, "bias", None) is not None:
+                    nn.init.constant_(m.bias.data, 0.0)
+
+
+class Encoder(nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.group = [1, 2, 4, 8, 1]
+        layers = []
+        for cin, cout, stride, groups in _ENC:
+            layers += [nn.Conv2d(cin, cout, 3, stride, 1, groups=groups), nn.LeakyReLU(0.2, inplace=True)]
+        self.layers = nn.ModuleList(layers)
+
+    def forward(self, x):
+        bt = x.size(0)
+        out = x
+        x0 = None
+        for k in range(len(_ENC)):
+            conv, act = self.layers[2 * k], self.layers[2 * k + 1]
+            if k == 4:
+                x0 = out
+            if k > 4:
+                g = self.group[k - 4]
+                h, w = x0.shape[-2:]
+                out = torch.cat([x0.reshape(bt, g, -1, h, w), out.reshape(bt, g, -1, h, w)], 2).reshape(bt, -1, h, w)
+            out = act(conv(out))
+        return out
+
+
+class deconv(nn.Module):
+    """x2 bilinear upsample (align_corners=True) + conv (e2fgvi.py:112-130)."""
+
+    def __init__(self, input_channel, output_channel, kernel_size=3, padding=0):
+        super().__init__()
+        self.conv = nn.Conv2d(input_channel, output_channel, kernel_size=kernel_size, stride=1, padding=padding)
+
+    def forward(self, x):
+        return self.conv(F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=True))
+
+
+class InpaintGenerator(BaseNetwork):
+    HQ = False
+
+    def __init__(self, init_weights=True):
+        super().__init__()
+        channel, hidden = 256, 512
+        self.encoder = Encoder()
+        self.decoder = nn.Sequential(
+            deconv(channel // 2, 128, kernel_size=3, padding=1), nn.LeakyReLU(0.2, inplace=True),
+            nn.Conv2d(128, 64, kernel_size=3, stride=1, padding=1), nn.LeakyReLU(0.2, inplace=True),
+            deconv(64, 64, kernel_size=3, padding=1), nn.LeakyReLU(0.2, inplace=True),
+            nn.Conv2d(64, 3, kernel_size=3, stride=1, padding=1))
+        self.feat_prop_module = BidirectionalPropagation(channel // 2)
+
+        kernel_size, padding, stride, output_size = (7, 7), (3, 3), (3, 3), (60, 108)
+        t2t_params = {"kernel_size": kernel_size, "stride": stride, "padding": padding}
+        if not self.HQ:
+            t2t_params["output_size"] = output_size
+        self.ss = SoftSplit(channel // 2, hidden, kernel_size, stride, padding, t2t_param=t2t_params)
+        self.sc = SoftComp(channel // 2, hidden, None if self.HQ else output_size, kernel_size, stride, padding,
+                           hq=self.HQ)
+        n_vecs = 1
+        for i, d in enumerate(kernel_size):
+            n_vecs *= int((output_size[i] + 2 * padding[i] - (d - 1) - 1) / stride[i] + 1)
+        depths = 8
+        self.transformer = nn.Sequential(*[
+            TemporalFocalTransformerBlock(dim=hidden, num_heads=4, window_size=(5, 9), focal_level=2,
+                                          focal_window=(5, 9), n_vecs=n_vecs, t2t_params=t2t_params,
+                                          pool_method="fc", hq=self.HQ) for _ in range(depths)])
+        if init_weights:
+            self.init_weights()
+            for m in self.modules():
+                if isinstance(m, SecondOrderDeformableAlignment):
+                    m.init_offset()
+        # built after init_weights, like the reference (e2fgvi.py:208): keeps its own default init
+        self.update_spynet = SPyNet()
+
+    def forward_bidirect_flow(self, masked_local_frames):
+        """1/4 bilinear downsample then SPyNet in both directions (e2fgvi.py:210-234); both directions run as
+        one batched SPyNet call (every op inside is batch-independent)."""
+        b, l_t, c, h, w = masked_local_frames.size()
+        small = F.interpolate(masked_local_frames.reshape(-1, c, h, w), scale_factor=1 / 4, mode="bilinear",
+                              align_corners=True, recompute_scale_factor=True)
+        small = small.view(b, l_t, c, h // 4, w // 4)
+        a = small[:, :-1].reshape(-1, c, h // 4, w // 4)
+        z = small[:, 1:].reshape(-1, c, h // 4, w // 4)
+        n = a.size(0)
+        both = self.update_spynet(torch.cat([a, z]), torch.cat([z, a]))
+        fwd = both[:n].reshape(b, l_t - 1, 2, h // 4, w // 4)
+        bwd = both[n:].reshape(b, l_t - 1, 2, h // 4, w // 4)
+        return fwd, bwd
+
+    def forward(self, masked_frames, num_local_frames):
+        l_t = num_local_frames
+        b, t, ori_c, ori_h, ori_w = masked_frames.size()
+        pred_flows = self.forward_bidirect_flow((masked_frames[:, :l_t] + 1) / 2)
+
+        enc_feat = self.encoder(masked_frames.reshape(b * t, ori_c, ori_h, ori_w))
+        _, c, h, w = enc_feat.size()
+        enc_feat = enc_feat.view(b, t, c, h, w)
+        # NB: (forward, backward) flows go to (flows_backward, flows_forward) exactly as e2fgvi.py:249-250 does
+        local_feat = self.feat_prop_module(enc_feat[:, :l_t], pred_flows[0], pred_flows[1])
+        enc_feat = torch.cat((local_feat, enc_feat[:, l_t:]), dim=1)
+
+        fold_size = (h, w)
+        tokens = self.ss(enc_feat.reshape(-1, c, h, w), b, fold_size if self.HQ else None)
+        if self.HQ:
+            tokens = self.transformer([tokens, fold_size])[0]
+        else:
+            tokens = self.transformer(tokens)
+        trans_feat = self.sc(tokens, t, fold_size if self.HQ else None).view(b, t, -1, h, w)
+        enc_feat = enc_feat + trans_feat
+
+        output = torch.tanh(self.decoder(enc_feat.reshape(b * t, c, h, w)))
+        return output, pred_flows
+
+
+class InpaintGeneratorHQ(InpaintGenerator):
+    HQ = True

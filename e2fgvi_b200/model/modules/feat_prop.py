@@ -1,0 +1,122 @@
+"""Flow-guided feature propagation (reference: model/modules/feat_prop.py:13-149).
+
+``SecondOrderDeformableAlignment`` keeps the reference's parameter names (``weight``, ``bias``,
+``conv_offset.{0,2,4,6}``) and attributes (stride/padding/dilation/groups/deform_groups) but its DCN is the
+fused sm_100a kernel (``ops.deform_align_fused``): 10*tanh + flow add + sigmoid + bilinear sampling + im2col +
+tcgen05 GEMM + bias in one launch, no column buffer.  ``BidirectionalPropagation`` restates the recurrence,
+including the two reference quirks that trained weights depend on: the flow index is ``i-1`` for BOTH
+sweep directions (feat_prop.py:94-103) and the caller passes (forward, backward) flows into
+(flows_backward, flows_forward) (e2fgvi.py:249-250).
+"""
+import math
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from ... import ops
+from .flow_comp import flow_warp
+
+
+class SecondOrderDeformableAlignment(nn.Module):
+    """Second-order deformable alignment: offset head (4 convs) + modulated deformable 3x3 conv, 16 groups."""
+
+    def __init__(self, in_channels, out_channels, kernel_size=3, stride=1, padding=1, dilation=1, groups=1,
+                 deform_groups=16, max_residue_magnitude=10):
+        super().__init__()
+        if kernel_size != 3:
+            raise ValueError("E2FGVI uses a 3x3 deformable kernel")
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.kernel_size = (3, 3)
+        self.stride, self.padding, self.dilation = (stride,) * 2, (padding,) * 2, (dilation,) * 2
+        self.groups, self.deform_groups = groups, deform_groups
+        self.max_residue_magnitude = max_residue_magnitude
+        # same init family as mmcv's ModulatedDeformConv2d (uniform +-1/sqrt(fan_in), zero bias)
+        self.weight = nn.Parameter(torch.empty(out_channels, in_channels // groups, 3, 3))
+        self.bias = nn.Parameter(torch.zeros(out_channels))
+        bound = 1.0 / math.sqrt(in_channels * 9)
+        nn.init.uniform_(self.weight, -bound, bound)
+        co = out_channels
+        self.conv_offset = nn.Sequential(
+            nn.Conv2d(3 * co + 4, co, 3, 1, 1), nn.LeakyReLU(0.1, inplace=True),
+            nn.Conv2d(co, co, 3, 1, 1), nn.LeakyReLU(0.1, inplace=True),
+            nn.Conv2d(co, co, 3, 1, 1), nn.LeakyReLU(0.1, inplace=True),
+            nn.Conv2d(co, 27 * deform_groups, 3, 1, 1))
+        self.fused = True  # False: torch epilogue + ops.modulated_deform_conv2d (the reference's operator split)
+        self.init_offset()
+
+    def init_offset(self):
+        """Zero the last offset conv (feat_prop.py:32-33)."""
+        nn.init.zeros_(self.conv_offset[-1].weight)
+        nn.init.zeros_(self.conv_offset[-1].bias)
+
+    def forward(self, x, extra_feat, flow_1, flow_2):
+        head = self.conv_offset(torch.cat([extra_feat, flow_1, flow_2], dim=1))
+        if self.fused:
+            wp = ops.pack_dcn_weight(self.weight, self.deform_groups)
+            return ops.deform_align_fused(x, head, flow_1, flow_2, wp, self.bias, self.deform_groups,
+                                          self.max_residue_magnitude)
+        # operator-level path, identical maths to feat_prop.py:41-58
+        o1, o2, mask = torch.chunk(head, 3, dim=1)
+        offset = self.max_residue_magnitude * torch.tanh(torch.cat((o1, o2), dim=1))
+        off1, off2 = torch.chunk(offset, 2, dim=1)
+        off1 = off1 + flow_1.flip(1).repeat(1, off1.size(1) // 2, 1, 1)
+        off2 = off2 + flow_2.flip(1).repeat(1, off2.size(1) // 2, 1, 1)
+        return ops.modulated_deform_conv2d(x, torch.cat([off1, off2], dim=1), torch.sigmoid(mask), self.weight,
+                                           self.bias, self.stride, self.padding, self.dilation, self.groups,
+                                           self.deform_groups)
+
+
+class BidirectionalPropagation(nn.Module):
+    """Backward then forward recurrent sweep with second-order alignment, 1x1 fusion and residual."""
+
+    DIRECTIONS = ("backward_", "forward_")
+
+    def __init__(self, channel):
+        super().__init__()
+        self.channel = channel
+        self.deform_align = nn.ModuleDict()
+        self.backbone = nn.ModuleDict()
+        for i, name in enumerate(self.DIRECTIONS):
+            self.deform_align[name] = SecondOrderDeformableAlignment(2 * channel, channel, 3, padding=1,
+                                                                    deform_groups=16)
+            self.backbone[name] = nn.Sequential(
+                nn.Conv2d((2 + i) * channel, channel, 3, 1, 1), nn.LeakyReLU(0.1, inplace=True),
+                nn.Conv2d(channel, channel, 3, 1, 1))
+        self.fusion = nn.Conv2d(2 * channel, channel, 1, 1, 0)
+
+    def forward(self, x, flows_backward, flows_forward):
+        """x (b,t,c,h,w); flows_* (b,t-1,2,h,w) -> (b,t,c,h,w)."""
+        b, t, c, h, w = x.shape
+        frames = [x[:, i].contiguous(memory_format=torch.channels_last) for i in range(t)]
+        swept = {}
+        for name in self.DIRECTIONS:
+            backward = name == "backward_"
+            order = list(range(t - 1, -1, -1)) if backward else list(range(t))
+            flows = flows_backward if backward else flows_forward
+            align, backbone = self.deform_align[name], self.backbone[name]
+            prop = torch.zeros_like(frames[0])
+            hist = []
+            for i, idx in enumerate(order):
+                cur = frames[idx]
+                if i > 0:
+                    flow_n1 = flows[:, i - 1]
+                    grid_n1 = flow_n1.permute(0, 2, 3, 1)
+                    cond_n1 = flow_warp(prop, grid_n1)
+                    if i > 1:
+                        feat_n2 = hist[-2]
+                        flow_n2 = flow_n1 + flow_warp(flows[:, i - 2], grid_n1)
+                        cond_n2 = flow_warp(feat_n2, flow_n2.permute(0, 2, 3, 1))
+                    else:
+                        feat_n2 = torch.zeros_like(prop)
+                        flow_n2 = torch.zeros_like(flow_n1)
+                        cond_n2 = torch.zeros_like(cond_n1)
+                    cond = torch.cat([cond_n1, cur, cond_n2], dim=1)
+                    prop = align(torch.cat([prop, feat_n2], dim=1), cond, flow_n1, flow_n2)
+                parts = [cur, prop] if backward else [cur, swept["backward_"][idx], prop]
+                prop = prop + backbone(torch.cat(parts, dim=1))
+                hist.append(prop)
+            swept[name] = hist[::-1] if backward else hist
+        both = torch.stack([torch.cat([swept["backward_"][i], swept["forward_"][i]], dim=1) for i in range(t)], 1)
+        fused = self.fusion(both.view(b * t, 2 * c, h, w)).view(b, t, c, h, w)
+        return fused + x

@@ -1,0 +1,236 @@
+"""Temporal focal transformer (reference: model/modules/tfocal_transformer.py:19-536 and _hq.py).
+
+One implementation serves both variants: the base model fixes ``output_size`` at construction
+(tfocal_transformer.py:30-37,56-59,83-87), the HQ model threads it through at run time (_hq.py:32-46,92-119).
+Parameter / buffer names follow the reference so released ``state_dict``s load strictly.
+
+The attention core (window partition, 4 rolled ring key sets, pooled-window keys with the -100 mask, softmax,
+P·V, window reverse) is ONE kernel, ``ops.focal_window_attention``; rolled K/V copies and the logits matrix are
+never materialised.
+"""
+import math
+from functools import reduce
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from ... import ops
+
+
+def _token_grid(output_size, kernel_size, stride, padding):
+    return tuple((output_size[i] + 2 * padding[i] - (kernel_size[i] - 1) - 1) // stride[i] + 1 for i in range(2))
+
+
+class SoftSplit(nn.Module):
+    """unfold(7x7, s3, p3) + Linear(49*C -> hidden) (tfocal_transformer.py:19-46)."""
+
+    def __init__(self, channel, hidden, kernel_size, stride, padding, t2t_param=None):
+        super().__init__()
+        self.kernel_size, self.stride, self.padding = tuple(kernel_size), tuple(stride), tuple(padding)
+        self.embedding = nn.Linear(reduce(lambda a, b: a * b, kernel_size) * channel, hidden)
+        self.t2t_param = t2t_param
+        self.output_size = None if t2t_param is None else t2t_param.get("output_size")
+
+    def forward(self, x, b, output_size=None):
+        output_size = output_size or self.output_size
+        f_h, f_w = _token_grid(output_size, self.kernel_size, self.stride, self.padding)
+        feat = F.unfold(x, self.kernel_size, padding=self.padding, stride=self.stride).permute(0, 2, 1)
+        feat = self.embedding(feat)
+        return feat.view(b, -1, f_h, f_w, feat.size(2))
+
+
+class SoftComp(nn.Module):
+    """Linear(hidden -> 49*C) + fold + bias map (base, tfocal_transformer.py:49-72) or 3x3 conv (HQ, _hq.py:49-79)."""
+
+    def __init__(self, channel, hidden, output_size=None, kernel_size=(7, 7), stride=(3, 3), padding=(3, 3), hq=False):
+        super().__init__()
+        self.kernel_size, self.stride, self.padding = tuple(kernel_size), tuple(stride), tuple(padding)
+        self.embedding = nn.Linear(hidden, reduce(lambda a, b: a * b, kernel_size) * channel)
+        self.output_size = output_size
+        self.hq = hq
+        if hq:
+            self.bias_conv = nn.Conv2d(channel, channel, kernel_size=3, stride=1, padding=1)
+        else:
+            self.bias = nn.Parameter(torch.zeros((channel, output_size[0], output_size[1]), dtype=torch.float32))
+
+    def forward(self, x, t, output_size=None):
+        output_size = output_size or self.output_size
+        b_, _, _, _, c_ = x.shape
+        feat = self.embedding(x.view(b_, -1, c_))
+        b, _, c = feat.size()
+        feat = feat.view(b * t, -1, c).permute(0, 2, 1)
+        feat = F.fold(feat, output_size, self.kernel_size, padding=self.padding, stride=self.stride)
+        return self.bias_conv(feat) if self.hq else feat + self.bias[None]
+
+
+class FusionFeedForward(nn.Module):
+    """Linear(512->1960), overlap-average through fold/normalise/unfold, GELU, Linear(1960->512)
+    (tfocal_transformer.py:75-98; _hq.py:82-119)."""
+
+    def __init__(self, d_model, n_vecs=None, t2t_params=None):
+        super().__init__()
+        hd = 1960
+        self.conv1 = nn.Sequential(nn.Linear(d_model, hd))
+        self.conv2 = nn.Sequential(nn.GELU(), nn.Linear(hd, d_model))
+        assert t2t_params is not None
+        self.t2t_params = dict(t2t_params)
+        self.n_vecs = n_vecs
+        self._normalizer = {}
+
+    def _fold_normalizer(self, output_size, like):
+        """fold(ones): how many 7x7 patches cover each pixel; a constant map per output size."""
+        key = (tuple(output_size), like.device, like.dtype)
+        m = self._normalizer.get(key)
+        if m is None:
+            p = self.t2t_params
+            f_h, f_w = _token_grid(output_size, p["kernel_size"], p["stride"], p["padding"])
+            ones = torch.ones(1, 49, f_h * f_w, device=like.device, dtype=like.dtype)
+            m = F.fold(ones, output_size, p["kernel_size"], padding=p["padding"], stride=p["stride"])
+            self._normalizer[key] = m
+        return m
+
+    def forward(self, x, output_size=None):
+        p = self.t2t_params
+        output_size = output_size or p.get("output_size")
+        f_h, f_w = _token_grid(output_size, p["kernel_size"], p["stride"], p["padding"])
+        n_vecs = f_h * f_w
+        x = self.conv1(x)
+        b, n, c = x.size()
+        y = F.fold(x.view(-1, n_vecs, c).permute(0, 2, 1), output_size, p["kernel_size"], padding=p["padding"],
+                   stride=p["stride"])
+        y = y / self._fold_normalizer(output_size, y)
+        y = F.unfold(y, p["kernel_size"], padding=p["padding"], stride=p["stride"])
+        x = y.permute(0, 2, 1).contiguous().view(b, n, c)
+        return self.conv2(x)
+
+
+def window_partition(x, window_size):
+    """(B,T,H,W,C) -> (B*nW, T*wh*ww, C) (tfocal_transformer.py:101-114)."""
+    B, T, H, W, C = x.shape
+    wh, ww = window_size
+    x = x.view(B, T, H // wh, wh, W // ww, ww, C)
+    return x.permute(0, 2, 4, 1, 3, 5, 6).reshape(-1, T * wh * ww, C)
+
+
+def window_partition_noreshape(x, window_size):
+    """(B,T,H,W,C) -> (B, nWh, nWw, T, wh, ww, C) (tfocal_transformer.py:117-129)."""
+    B, T, H, W, C = x.shape
+    wh, ww = window_size
+    return x.view(B, T, H // wh, wh, W // ww, ww, C).permute(0, 2, 4, 1, 3, 5, 6).contiguous()
+
+
+def window_reverse(windows, window_size, T, H, W):
+    """(B*nW, T, wh, ww, C) -> (B,T,H,W,C) (tfocal_transformer.py:132-147)."""
+    wh, ww = window_size
+    B = windows.shape[0] // ((H // wh) * (W // ww))
+    x = windows.view(B, H // wh, W // ww, T, wh, ww, -1)
+    return x.permute(0, 3, 1, 4, 2, 5, 6).reshape(B, T, H, W, -1)
+
+
+def rolled_valid_indices(window_size, expand_size):
+    """Flat indices kept from the 4 rolled window copies (tfocal_transformer.py:166-179): positions of the
+    (tl, tr, bl, br) rolled windows that fall OUTSIDE the query window."""
+    wh, ww = window_size
+    eh, ew = expand_size
+    keep = []
+    for quad, (row_from_end, col_from_end) in enumerate(((True, True), (True, False), (False, True), (False, False))):
+        for r in range(wh):
+            for c in range(ww):
+                row_ok = r >= wh - eh if row_from_end else r < eh
+                col_ok = c >= ww - ew if col_from_end else c < ew
+                if row_ok or col_ok:
+                    keep.append(quad * wh * ww + r * ww + c)
+    return torch.tensor(keep, dtype=torch.int64)
+
+
+class WindowAttention(nn.Module):
+    """Temporal focal window attention (tfocal_transformer.py:150-399)."""
+
+    def __init__(self, dim, expand_size, window_size, focal_window, focal_level, num_heads, qkv_bias, pool_method):
+        super().__init__()
+        self.dim, self.num_heads = dim, num_heads
+        self.expand_size, self.window_size = tuple(expand_size), tuple(window_size)
+        self.focal_window, self.focal_level, self.pool_method = tuple(focal_window), focal_level, pool_method
+        self.scale = (dim // num_heads) ** -0.5
+        if focal_level > 2:
+            raise NotImplementedError("E2FGVI uses focal_level=2 (one pooled level)")
+        if any(i > 0 for i in self.expand_size) and focal_level > 0:
+            self.register_buffer("valid_ind_rolled", rolled_valid_indices(self.window_size, self.expand_size))
+        self.qkv = nn.Linear(dim, dim * 3, bias=qkv_bias)
+        self.proj = nn.Linear(dim, dim)
+
+    @property
+    def uses_pooled(self):
+        return self.pool_method != "none" and self.focal_level > 1
+
+    def pooled_kernel(self):
+        """Neighbourhood of pooled windows each query window attends (unfold kernel, tfocal_transformer.py:186-196)."""
+        return tuple(2 * (i // 2) + 1 for i in self.focal_window)
+
+    def attend(self, x, pooled):
+        """x (B,T,H,W,C) normed tokens, pooled (B,nWh,nWw,T,C) -> (B,T,H,W,C) after proj."""
+        qkv = self.qkv(x)
+        qkv_pooled = self.qkv(pooled.permute(0, 3, 1, 2, 4)) if self.uses_pooled else None
+        out = ops.focal_window_attention(qkv, qkv_pooled, self.num_heads, self.window_size, self.expand_size,
+                                         self.pooled_kernel(), self.scale, out_dtype=x.dtype)
+        return self.proj(out)
+
+    def forward(self, x_all, mask_all=None):
+        """Reference boundary: x_all = [x (B,T,H,W,C), pooled (B,nWh,nWw,T,C)] -> (B*nW, T*wh*ww, C)."""
+        del mask_all  # always [None, None] on the path (tfocal_transformer.py:475)
+        out = self.attend(x_all[0], x_all[1] if len(x_all) > 1 else None)
+        return window_partition(out, self.window_size)
+
+
+class TemporalFocalTransformerBlock(nn.Module):
+    """LN -> window pool -> focal attention -> +res -> LN -> fusion FFN -> +res (tfocal_transformer.py:402-536)."""
+
+    def __init__(self, dim, num_heads, window_size=(5, 9), mlp_ratio=4., qkv_bias=True, pool_method="fc",
+                 focal_level=2, focal_window=(5, 9), norm_layer=nn.LayerNorm, n_vecs=None, t2t_params=None,
+                 hq=False):
+        super().__init__()
+        self.dim, self.num_heads, self.window_size = dim, num_heads, tuple(window_size)
+        self.expand_size = tuple(i // 2 for i in window_size)
+        self.mlp_ratio, self.pool_method = mlp_ratio, pool_method
+        self.focal_level, self.focal_window = focal_level, tuple(focal_window)
+        self.hq = hq
+        self.pool_layers = nn.ModuleList()
+        if pool_method != "none":
+            for k in range(focal_level - 1):
+                ws = tuple(math.floor(i / (2 ** k)) for i in self.window_size)
+                layer = nn.Linear(ws[0] * ws[1], 1)
+                layer.weight.data.fill_(1.0 / (ws[0] * ws[1]))
+                layer.bias.data.fill_(0)
+                self.pool_layers.append(layer)
+        self.norm1 = norm_layer(dim)
+        self.attn = WindowAttention(dim, self.expand_size, self.window_size, focal_window, focal_level, num_heads,
+                                    qkv_bias, pool_method)
+        self.norm2 = norm_layer(dim)
+        self.mlp = FusionFeedForward(dim, n_vecs=n_vecs, t2t_params=t2t_params)
+
+    def _pool_windows(self, x):
+        """Linear(wh*ww -> 1) over each window's tokens, per channel (tfocal_transformer.py:508-516)."""
+        B, T, H, W, C = x.shape
+        wh, ww = self.window_size
+        if H % wh or W % ww:
+            raise ValueError(f"token grid {H}x{W} must be a multiple of the window {wh}x{ww}")
+        lin = self.pool_layers[0]
+        xw = x.view(B, T, H // wh, wh, W // ww, ww, C)
+        pooled = torch.einsum("bthrwqc,rq->bhwtc", xw, lin.weight.view(wh, ww).to(x.dtype))
+        return pooled + lin.bias.to(x.dtype)
+
+    def _forward(self, x, output_size):
+        shortcut = x
+        xn = self.norm1(x)
+        pooled = self._pool_windows(xn) if self.attn.uses_pooled else None
+        x = shortcut + self.attn.attend(xn, pooled).to(shortcut.dtype)
+        B, T, H, W, C = x.shape
+        y = self.norm2(x)
+        return x + self.mlp(y.view(B, T * H * W, C), output_size).view(B, T, H, W, C)
+
+    def forward(self, x):
+        if self.hq:  # x = [tokens, (h, w)] -> (tokens, (h, w))   (_hq.py:492-495,562-565)
+            tokens, output_size = x[0], x[1]
+            return self._forward(tokens, output_size), output_size
+        return self._forward(x, None)

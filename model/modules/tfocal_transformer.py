@@ -1,0 +1,1 @@
+from e2fgvi_b200.model.modules.tfocal_transformer import *  # noqa: F401,F403
