@@ -17,7 +17,6 @@ SOURCES = ["api.cu", "flow_warp.cu", "dcn.cu", "focal_attn.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
-    "--use_fast_math",
     "-Xcompiler", "-fPIC",
     "-Xptxas", "-v",
     "-I", os.path.join(os.path.dirname(HERE), "include"),

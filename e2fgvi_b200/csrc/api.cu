@@ -1,0 +1,119 @@
+// extern "C" boundary of libe2fgvi_b200.so (declared in include/e2fgvi_b200.h): argument validation, error
+// strings, launch accounting.  No torch types, no allocation, no global device state.
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "e2fgvi_b200.h"
+#include "launch.h"
+
+namespace e2f {
+
+static thread_local char g_err[512] = {0};
+static std::atomic<long long> g_launches{0};
+
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+static int finish(int status, const char* what) {
+  if (status > 0) set_error("%s: CUDA error %d (%s)", what, status, cudaGetErrorString(static_cast<cudaError_t>(status)));
+  return status;
+}
+
+static bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; }
+
+}  // namespace e2f
+
+using namespace e2f;
+
+extern "C" {
+
+const char* e2f_version(void) { return "e2fgvi_b200 0.1.0 sm_100a"; }
+
+const char* e2f_last_error(void) { return g_err; }
+
+int64_t e2f_launch_count(void) { return static_cast<int64_t>(g_launches.load(std::memory_order_relaxed)); }
+
+int e2f_flow_warp(const void* x, const float* flow, void* out, int n, int h, int w, int c, int dtype, int pad_mode,
+                  void* stream) {
+  if (!x || !flow || !out) { set_error("e2f_flow_warp: null pointer"); return E2F_ERR_BAD_ARG; }
+  if (n < 0 || h <= 0 || w <= 0 || c <= 0) { set_error("e2f_flow_warp: bad shape n=%d h=%d w=%d c=%d", n, h, w, c); return E2F_ERR_BAD_ARG; }
+  if (dtype != E2F_F32 && dtype != E2F_F16) { set_error("e2f_flow_warp: dtype %d", dtype); return E2F_ERR_BAD_ARG; }
+  if (pad_mode != E2F_PAD_ZEROS && pad_mode != E2F_PAD_BORDER) { set_error("e2f_flow_warp: pad_mode %d", pad_mode); return E2F_ERR_BAD_ARG; }
+  const int vec = dtype == E2F_F16 ? 8 : 4;
+  if (c % vec) { set_error("e2f_flow_warp: C=%d must be a multiple of %d for the NHWC kernel (use e2f_flow_warp_nchw)", c, vec); return E2F_ERR_UNSUPPORTED; }
+  if (!aligned(x, 16) || !aligned(out, 16) || !aligned(flow, 8)) { set_error("e2f_flow_warp: x/out need 16-byte, flow 8-byte alignment"); return E2F_ERR_ALIGNMENT; }
+  return finish(launch_flow_warp_nhwc(x, flow, out, n, h, w, c, dtype, pad_mode, static_cast<cudaStream_t>(stream)), "e2f_flow_warp");
+}
+
+int e2f_flow_warp_nchw(const float* x, const float* flow, float* out, int n, int c, int h, int w, int pad_mode,
+                       void* stream) {
+  if (!x || !flow || !out) { set_error("e2f_flow_warp_nchw: null pointer"); return E2F_ERR_BAD_ARG; }
+  if (n < 0 || h <= 0 || w <= 0 || c <= 0) { set_error("e2f_flow_warp_nchw: bad shape"); return E2F_ERR_BAD_ARG; }
+  if (pad_mode != E2F_PAD_ZEROS && pad_mode != E2F_PAD_BORDER) { set_error("e2f_flow_warp_nchw: pad_mode %d", pad_mode); return E2F_ERR_BAD_ARG; }
+  if (!aligned(flow, 8)) { set_error("e2f_flow_warp_nchw: flow needs 8-byte alignment"); return E2F_ERR_ALIGNMENT; }
+  return finish(launch_flow_warp_nchw(x, flow, out, n, c, h, w, pad_mode, static_cast<cudaStream_t>(stream)), "e2f_flow_warp_nchw");
+}
+
+int e2f_dcn_pack_weight(const float* w, void* w_packed_f16, int cout, int cin, int deform_groups, void* stream) {
+  if (!w || !w_packed_f16) { set_error("e2f_dcn_pack_weight: null pointer"); return E2F_ERR_BAD_ARG; }
+  if (cout <= 0 || cin <= 0 || deform_groups <= 0 || cin % deform_groups) { set_error("e2f_dcn_pack_weight: bad shape"); return E2F_ERR_BAD_ARG; }
+  return finish(launch_dcn_pack_weight(w, w_packed_f16, cout, cin, deform_groups, static_cast<cudaStream_t>(stream)), "e2f_dcn_pack_weight");
+}
+
+static int dcn_common_checks(const char* who, const void* x, const void* w_packed, const void* out, int n, int h, int w,
+                             int out_dtype) {
+  if (!x || !w_packed || !out) { set_error("%s: null pointer", who); return E2F_ERR_BAD_ARG; }
+  if (n < 0 || h <= 0 || w <= 0) { set_error("%s: bad shape n=%d h=%d w=%d", who, n, h, w); return E2F_ERR_BAD_ARG; }
+  if (out_dtype != E2F_F32 && out_dtype != E2F_F16) { set_error("%s: out_dtype %d", who, out_dtype); return E2F_ERR_BAD_ARG; }
+  if (!aligned(x, 32) || !aligned(w_packed, 128) || !aligned(out, 16)) { set_error("%s: x needs 32-byte, w_packed 128-byte, out 16-byte alignment", who); return E2F_ERR_ALIGNMENT; }
+  return 0;
+}
+
+int e2f_modulated_deform_conv2d(const void* x, const float* offset, const float* mask, const void* w_packed,
+                                const float* bias, void* out, int n, int h, int w, int cin, int cout,
+                                int deform_groups, int out_dtype, void* stream) {
+  int st = dcn_common_checks("e2f_modulated_deform_conv2d", x, w_packed, out, n, h, w, out_dtype);
+  if (st) return st;
+  if (!offset || !mask) { set_error("e2f_modulated_deform_conv2d: null offset/mask"); return E2F_ERR_BAD_ARG; }
+  if (!aligned(offset, 8)) { set_error("e2f_modulated_deform_conv2d: offset needs 8-byte alignment"); return E2F_ERR_ALIGNMENT; }
+  return finish(launch_dcn(x, offset, mask, nullptr, nullptr, nullptr, w_packed, bias, out, n, h, w, cin, cout,
+                           deform_groups, 0.f, out_dtype, static_cast<cudaStream_t>(stream)),
+                "e2f_modulated_deform_conv2d");
+}
+
+int e2f_deform_align_fused(const void* x, const float* head, const float* flow1, const float* flow2,
+                           const void* w_packed, const float* bias, void* out, int n, int h, int w, int cin, int cout,
+                           int deform_groups, float max_residue, int out_dtype, void* stream) {
+  int st = dcn_common_checks("e2f_deform_align_fused", x, w_packed, out, n, h, w, out_dtype);
+  if (st) return st;
+  if (!head || !flow1 || !flow2) { set_error("e2f_deform_align_fused: null head/flow"); return E2F_ERR_BAD_ARG; }
+  if (!aligned(head, 8) || !aligned(flow1, 8) || !aligned(flow2, 8)) { set_error("e2f_deform_align_fused: head/flow need 8-byte alignment"); return E2F_ERR_ALIGNMENT; }
+  return finish(launch_dcn(x, nullptr, nullptr, head, flow1, flow2, w_packed, bias, out, n, h, w, cin, cout,
+                           deform_groups, max_residue, out_dtype, static_cast<cudaStream_t>(stream)),
+                "e2f_deform_align_fused");
+}
+
+int e2f_focal_window_attention(const void* qkv, const void* qkv_pooled, void* out, int b, int t, int h, int w,
+                               int heads, int head_dim, int wh, int ww, int eh, int ew, int fh, int fw,
+                               int use_pooled, float scale, int out_dtype, void* stream) {
+  if (!qkv || !out || (use_pooled && !qkv_pooled)) { set_error("e2f_focal_window_attention: null pointer"); return E2F_ERR_BAD_ARG; }
+  if (b < 0 || t <= 0 || h <= 0 || w <= 0 || heads <= 0 || wh <= 0 || ww <= 0 || eh < 0 || ew < 0) { set_error("e2f_focal_window_attention: bad shape"); return E2F_ERR_BAD_ARG; }
+  if (h % wh || w % ww) { set_error("e2f_focal_window_attention: token grid %dx%d is not a multiple of the window %dx%d", h, w, wh, ww); return E2F_ERR_BAD_ARG; }
+  if (use_pooled && (fh <= 0 || fw <= 0 || !(fh & 1) || !(fw & 1))) { set_error("e2f_focal_window_attention: pooled neighbourhood %dx%d must be odd", fh, fw); return E2F_ERR_BAD_ARG; }
+  if (out_dtype != E2F_F32 && out_dtype != E2F_F16) { set_error("e2f_focal_window_attention: out_dtype %d", out_dtype); return E2F_ERR_BAD_ARG; }
+  if (head_dim != 128) { set_error("e2f_focal_window_attention: head_dim %d unsupported (128 only)", head_dim); return E2F_ERR_UNSUPPORTED; }
+  if (!aligned(qkv, 16) || !aligned(out, 16) || (use_pooled && !aligned(qkv_pooled, 16))) { set_error("e2f_focal_window_attention: 16-byte alignment required"); return E2F_ERR_ALIGNMENT; }
+  return finish(launch_focal_attention(qkv, qkv_pooled, out, b, t, h, w, heads, head_dim, wh, ww, eh, ew, fh, fw,
+                                       use_pooled, scale, out_dtype, static_cast<cudaStream_t>(stream)),
+                "e2f_focal_window_attention");
+}
+
+}  // extern "C"

@@ -1,0 +1,26 @@
+// Internal host-side launcher declarations shared by api.cu and the kernel translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+
+namespace e2f {
+
+void count_launch();                       // api.cu: atomic launch counter behind e2f_launch_count()
+void set_error(const char* fmt, ...);      // api.cu: thread-local message behind e2f_last_error()
+
+int launch_flow_warp_nhwc(const void* x, const float* flow, void* out, int n, int h, int w, int c, int dtype,
+                          int pad_mode, cudaStream_t stream);
+int launch_flow_warp_nchw(const float* x, const float* flow, float* out, int n, int c, int h, int w, int pad_mode,
+                          cudaStream_t stream);
+
+int launch_dcn_pack_weight(const float* w, void* w_packed, int cout, int cin, int dg, cudaStream_t stream);
+// head != nullptr selects the fused (tanh / flow / sigmoid) prologue; otherwise offset+mask are final values.
+int launch_dcn(const void* x, const float* offset, const float* mask, const float* head, const float* flow1,
+               const float* flow2, const void* w_packed, const float* bias, void* out, int n, int h, int w, int cin,
+               int cout, int dg, float max_residue, int out_dtype, cudaStream_t stream);
+
+int launch_focal_attention(const void* qkv, const void* qkv_pooled, void* out, int b, int t, int h, int w, int heads,
+                           int head_dim, int wh, int ww, int eh, int ew, int fh, int fw, int use_pooled, float scale,
+                           int out_dtype, cudaStream_t stream);
+
+}  // namespace e2f

@@ -43,7 +43,16 @@ class SecondOrderDeformableAlignment(nn.Module):
             nn.Conv2d(co, co, 3, 1, 1), nn.LeakyReLU(0.1, inplace=True),
             nn.Conv2d(co, 27 * deform_groups, 3, 1, 1))
         self.fused = True  # False: torch epilogue + ops.modulated_deform_conv2d (the reference's operator split)
+        self._packed = None  # (weight version, data_ptr, fp16 GEMM operand)
         self.init_offset()
+
+    def packed_weight(self):
+        """fp16 [Cout, 9*Cin] operand of the DCN GEMM, re-packed whenever the parameter changes or moves."""
+        w = self.weight
+        tag = (w._version, w.data_ptr(), w.device)
+        if self._packed is None or self._packed[0] != tag:
+            self._packed = (tag, ops.pack_dcn_weight(w, self.deform_groups))
+        return self._packed[1]
 
     def init_offset(self):
         """Zero the last offset conv (feat_prop.py:32-33)."""
@@ -53,8 +62,7 @@ class SecondOrderDeformableAlignment(nn.Module):
     def forward(self, x, extra_feat, flow_1, flow_2):
         head = self.conv_offset(torch.cat([extra_feat, flow_1, flow_2], dim=1))
         if self.fused:
-            wp = ops.pack_dcn_weight(self.weight, self.deform_groups)
-            return ops.deform_align_fused(x, head, flow_1, flow_2, wp, self.bias, self.deform_groups,
+            return ops.deform_align_fused(x, head, flow_1, flow_2, self.packed_weight(), self.bias, self.deform_groups,
                                           self.max_residue_magnitude)
         # operator-level path, identical maths to feat_prop.py:41-58
         o1, o2, mask = torch.chunk(head, 3, dim=1)
@@ -118,5 +126,5 @@ class BidirectionalPropagation(nn.Module):
                 hist.append(prop)
             swept[name] = hist[::-1] if backward else hist
         both = torch.stack([torch.cat([swept["backward_"][i], swept["forward_"][i]], dim=1) for i in range(t)], 1)
-        fused = self.fusion(both.view(b * t, 2 * c, h, w)).view(b, t, c, h, w)
+        fused = self.fusion(both.reshape(b * t, 2 * c, h, w)).view(b, t, c, h, w)
         return fused + x

@@ -66,16 +66,12 @@ def flow_warp(x, flow, interpolation="bilinear", padding_mode="zeros", align_cor
     return out if out.dtype == x.dtype else out.to(x.dtype)
 
 
-_PACK_CACHE = {}
-
-
 def pack_dcn_weight(weight, deform_groups):
-    """fp32 [Cout,Cin,3,3] -> fp16 [Cout, 9*Cin] GEMM operand in sampler K-order (cached per weight version)."""
+    """fp32 [Cout,Cin,3,3] -> fp16 [Cout, 9*Cin] GEMM operand in sampler K-order (k = (g*9+tap)*cpg + c).
+
+    Not cached here (a data_ptr-keyed cache is unsound once the allocator reuses addresses); modules that own a
+    long-lived weight cache the result themselves (see SecondOrderDeformableAlignment.packed_weight)."""
     _need_cuda(weight)
-    key = (weight.data_ptr(), weight._version, tuple(weight.shape), deform_groups, weight.device.index)
-    hit = _PACK_CACHE.get(key)
-    if hit is not None:
-        return hit
     cout, cin, kh, kw = weight.shape
     if (kh, kw) != (3, 3):
         raise ValueError("only 3x3 deformable kernels are on the E2FGVI path")
@@ -83,9 +79,6 @@ def pack_dcn_weight(weight, deform_groups):
     packed = torch.empty(cout, 9 * cin, dtype=torch.float16, device=weight.device)
     st = _lib.load().e2f_dcn_pack_weight(w32.data_ptr(), packed.data_ptr(), cout, cin, deform_groups, _stream())
     _lib.check(st, "e2f_dcn_pack_weight")
-    if len(_PACK_CACHE) > 64:
-        _PACK_CACHE.clear()
-    _PACK_CACHE[key] = packed
     return packed
 
 

@@ -1,0 +1,192 @@
+"""GPU parity of the three C-ABI kernels against the CPU oracle (bit-level semantics, fp tolerances stated)."""
+import math
+
+import pytest
+import torch
+
+from e2fgvi_b200 import ops
+from oracle import restate
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(a, b):
+    return ((a.double() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-30)).item()
+
+
+# ------------------------------------------------------------------------------------------ flow_warp
+@pytest.mark.parametrize("pad", ["zeros", "border"])
+@pytest.mark.parametrize("shape", [(1, 128, 60, 108), (2, 128, 17, 23), (3, 8, 5, 7)])
+def test_flow_warp_nhwc_fp32(cuda, pad, shape):
+    g = torch.Generator().manual_seed(7)
+    n, c, h, w = shape
+    x = torch.randn(n, c, h, w, generator=g)
+    flow = torch.randn(n, h, w, 2, generator=g) * 6.0          # includes far out-of-bounds samples
+    flow[0, 0, 0] = torch.tensor([1e6, -1e6])
+    flow[0, h - 1, w - 1] = torch.tensor([0.0, 0.0])            # exact corner
+    want = restate.flow_warp(x, flow, padding_mode=pad)
+    got = ops.flow_warp(x.to(cuda).contiguous(memory_format=torch.channels_last), flow.to(cuda), padding_mode=pad)
+    assert got.shape == want.shape
+    # fp32 bilinear blend: only the association order differs -> 1e-5 abs on O(1) data
+    assert (got.cpu() - want).abs().max().item() < 1e-5
+
+
+def test_flow_warp_nhwc_fp16(cuda):
+    g = torch.Generator().manual_seed(8)
+    x = torch.randn(2, 128, 30, 54, generator=g).half()
+    flow = torch.randn(2, 30, 54, 2, generator=g) * 3.0
+    want = restate.flow_warp(x.float(), flow)
+    got = ops.flow_warp(x.to(cuda).contiguous(memory_format=torch.channels_last), flow.to(cuda))
+    assert got.dtype == torch.float16
+    assert (got.float().cpu() - want).abs().max().item() < 4e-3   # one fp16 rounding of an O(4) value
+
+
+@pytest.mark.parametrize("pad", ["zeros", "border"])
+@pytest.mark.parametrize("c", [2, 3])
+def test_flow_warp_nchw_small_channels(cuda, pad, c):
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn(4, c, 64, 128, generator=g)
+    flow = torch.randn(4, 64, 128, 2, generator=g) * 5.0
+    want = restate.flow_warp(x, flow, padding_mode=pad)
+    got = ops.flow_warp(x.to(cuda), flow.to(cuda), padding_mode=pad)
+    assert got.is_contiguous()
+    assert (got.cpu() - want).abs().max().item() < 1e-5
+
+
+def test_flow_warp_errors(cuda):
+    x = torch.zeros(1, 8, 4, 4, device=cuda)
+    with pytest.raises(ValueError):
+        ops.flow_warp(x, torch.zeros(1, 4, 5, 2, device=cuda))
+    with pytest.raises(RuntimeError):
+        ops.flow_warp(x.cpu(), torch.zeros(1, 4, 4, 2))
+
+
+# ------------------------------------------------------------------------------------------ DCN
+def _dcn_inputs(n, h, w, seed, off_scale=3.0):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(n, 256, h, w, generator=g)
+    offset = torch.randn(n, 288, h, w, generator=g) * off_scale
+    mask = torch.rand(n, 144, h, w, generator=g)
+    weight = torch.randn(128, 256, 3, 3, generator=g) / math.sqrt(2304.0)
+    bias = torch.randn(128, generator=g) * 0.1
+    return x, offset, mask, weight, bias
+
+
+@pytest.mark.parametrize("shape", [(1, 60, 108), (2, 9, 11), (1, 16, 8), (3, 5, 7)])
+def test_modulated_deform_conv2d(cuda, shape):
+    n, h, w = shape
+    x, offset, mask, weight, bias = _dcn_inputs(n, h, w, seed=11)
+    # the kernel multiplies fp16 operands: feed the oracle the same fp16-rounded x and weight so the comparison
+    # isolates the kernel's own arithmetic (fp32 interpolation, one fp16 rounding of the sampled value, fp32 accum)
+    xq, wq = x.half().float(), weight.half().float()
+    want = restate.modulated_deform_conv2d(xq.double(), offset.double(), mask.double(), wq.double(), bias.double(),
+                                           1, 1, 1, 1, 16).float()
+    got = ops.modulated_deform_conv2d(x.to(cuda), offset.to(cuda), mask.to(cuda), weight.to(cuda), bias.to(cuda),
+                                      1, 1, 1, 1, 16)
+    assert got.shape == want.shape
+    rel = _rel(got.cpu(), want)
+    # A-operand rounding to fp16 (2^-11 relative per element) averaged over K=2304 products: << 1e-3 of max
+    assert rel < 1.5e-3, rel
+
+
+def test_modulated_deform_conv2d_border_cases(cuda):
+    """Offsets that land exactly on -1, H, integer grid points and far outside (zero-padding rule)."""
+    n, h, w = 1, 6, 10
+    x, offset, mask, weight, bias = _dcn_inputs(n, h, w, seed=12, off_scale=0.0)
+    offset[:, 0::2, 0, :] = -1.0     # dy pushes row 0 samples to y = -2..0
+    offset[:, 1::2, :, 0] = -1.0
+    offset[:, 0::2, h - 1, :] = 1.0
+    offset[:, :, 2, 3] = 1e5
+    offset[:, :, 3, 4] = -1e5
+    xq, wq = x.half().float(), weight.half().float()
+    want = restate.modulated_deform_conv2d(xq.double(), offset.double(), mask.double(), wq.double(), bias.double(),
+                                           1, 1, 1, 1, 16).float()
+    got = ops.modulated_deform_conv2d(x.to(cuda), offset.to(cuda), mask.to(cuda), weight.to(cuda), bias.to(cuda),
+                                      1, 1, 1, 1, 16)
+    assert _rel(got.cpu(), want) < 1.5e-3
+
+
+def test_deform_align_fused_matches_unfused(cuda):
+    """Fused tanh/flow/sigmoid prologue == torch epilogue + plain DCN (feat_prop.py:41-58)."""
+    g = torch.Generator().manual_seed(13)
+    n, h, w = 2, 12, 20
+    x = torch.randn(n, 256, h, w, generator=g)
+    head = torch.randn(n, 432, h, w, generator=g) * 1.5
+    f1 = torch.randn(n, 2, h, w, generator=g) * 2
+    f2 = torch.randn(n, 2, h, w, generator=g) * 2
+    weight = torch.randn(128, 256, 3, 3, generator=g) / 48.0
+    bias = torch.randn(128, generator=g) * 0.1
+    o1, o2, m = torch.chunk(head, 3, dim=1)
+    off = 10.0 * torch.tanh(torch.cat((o1, o2), 1))
+    a, b = torch.chunk(off, 2, dim=1)
+    off = torch.cat([a + f1.flip(1).repeat(1, 72, 1, 1), b + f2.flip(1).repeat(1, 72, 1, 1)], 1)
+    want = restate.modulated_deform_conv2d(x.half().double(), off.double(), torch.sigmoid(m).double(),
+                                           weight.half().double(), bias.double(), 1, 1, 1, 1, 16).float()
+    wp = ops.pack_dcn_weight(weight.to(cuda), 16)
+    got = ops.deform_align_fused(x.to(cuda), head.to(cuda), f1.to(cuda), f2.to(cuda), wp, bias.to(cuda), 16, 10.0)
+    assert _rel(got.cpu(), want) < 1.5e-3
+    got16 = ops.deform_align_fused(x.to(cuda), head.to(cuda), f1.to(cuda), f2.to(cuda), wp, bias.to(cuda), 16, 10.0,
+                                   out_dtype=torch.float16)
+    assert _rel(got16.float().cpu(), want) < 3e-3
+
+
+def test_dcn_linearity_full_size(cuda):
+    """Size-independent property at the BASELINE shape (60x108, batch 8): DCN is linear in x for fixed offsets."""
+    n, h, w = 8, 60, 108
+    x1, offset, mask, weight, bias = _dcn_inputs(n, h, w, seed=14)
+    x2 = torch.randn(n, 256, h, w, generator=torch.Generator().manual_seed(15))
+    d = lambda t: ops.modulated_deform_conv2d(t.to(cuda), offset.to(cuda), mask.to(cuda), weight.to(cuda), None,  # noqa
+                                              1, 1, 1, 1, 16)
+    y1, y2, y12 = d(x1), d(x2), d(x1 + x2)
+    assert _rel(y12, y1 + y2) < 3e-3
+
+
+# ------------------------------------------------------------------------------------------ focal attention
+def _attn_case(cuda, B, T, H, W, seed, gain=1.0, use_pooled=True, heads=4, window=(5, 9), out_dtype=torch.float32):
+    from e2fgvi_b200.model.modules.tfocal_transformer import rolled_valid_indices
+    g = torch.Generator().manual_seed(seed)
+    C = heads * 128
+    wh, ww = window
+    expand = (wh // 2, ww // 2)
+    qkv = (torch.randn(B, T, H, W, 3 * C, generator=g) * gain).half()
+    pooled = (torch.randn(B, T, H // wh, W // ww, 3 * C, generator=g) * gain).half() if use_pooled else None
+    scale = 128 ** -0.5
+    fk = (2 * (wh // 2) + 1, 2 * (ww // 2) + 1)
+    want = restate.focal_window_attention(qkv.float(), None if pooled is None else pooled.float(), heads, window,
+                                          expand, fk, scale, rolled_valid_indices(window, expand))
+    got = ops.focal_window_attention(qkv.to(cuda), None if pooled is None else pooled.to(cuda), heads, window,
+                                     expand, fk, scale, out_dtype=out_dtype)
+    return got.float().cpu(), want
+
+
+@pytest.mark.parametrize("case", [
+    dict(B=1, T=2, H=10, W=18, seed=21),            # 2x2 windows: every ring wraps around the token grid
+    dict(B=2, T=3, H=20, W=36, seed=22),            # base token grid, 4x4 windows, partial last q-tile
+    dict(B=1, T=1, H=5, W=9, seed=23),              # a single window: the ring wraps onto the window itself
+    dict(B=1, T=3, H=15, W=27, seed=24, use_pooled=False),
+    dict(B=1, T=2, H=10, W=18, seed=25, gain=4.0),  # logits spread over >> 2^8: exercises the O rescale path
+])
+def test_focal_window_attention(cuda, case):
+    got, want = _attn_case(cuda, **case)
+    assert got.shape == want.shape
+    # P is rounded to fp16 before P.V (2^-11 relative per weight), everything else is fp32
+    assert _rel(got, want) < 2e-3, _rel(got, want)
+
+
+def test_focal_window_attention_base_size_fp16_out(cuda):
+    got, want = _attn_case(cuda, B=1, T=8, H=20, W=36, seed=26, out_dtype=torch.float16)
+    assert _rel(got, want) < 3e-3
+
+
+def test_focal_attention_rows_sum_property(cuda):
+    """Size-independent property at a large size (B=8 clips): with v == 1 the output must be exactly
+    (sum_j p_j) / (sum_j p_j + n_masked * exp(-100 - m)) ~= 1 for every token, whatever q and k are."""
+    B, T, H, W, C = 8, 8, 20, 36, 512
+    g = torch.Generator().manual_seed(27)
+    qkv = torch.randn(B, T, H, W, 3 * C, generator=g).half()
+    qkv[..., 2 * C:] = 1.0
+    pooled = torch.randn(B, T, 4, 4, 3 * C, generator=g).half()
+    pooled[..., 2 * C:] = 1.0
+    got = ops.focal_window_attention(qkv.to(cuda), pooled.to(cuda), 4, (5, 9), (2, 4), (5, 9), 128 ** -0.5,
+                                     out_dtype=torch.float32)
+    assert (got - 1.0).abs().max().item() < 2e-3
