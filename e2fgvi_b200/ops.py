@@ -20,6 +20,36 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+# Optional live kernel timing for bench.py's roofline block: name -> [(start_event, end_event, work)], recorded on
+# the launching stream around the C-ABI call (the call is one kernel launch).
+_PROFILE = None
+
+
+def profile_kernels(enable=True):
+    """Start (returns the live dict) or stop (enable=False) recording CUDA events around kernel launches."""
+    global _PROFILE
+    _PROFILE = {} if enable else None
+    return _PROFILE
+
+
+class _timed:
+    def __init__(self, name, work=0.0):
+        self.name, self.work = name, work
+
+    def __enter__(self):
+        if _PROFILE is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e1 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if _PROFILE is not None:
+            self.e1.record()
+            _PROFILE.setdefault(self.name, []).append((self.e0, self.e1, self.work))
+        return False
+
+
 def _need_cuda(*ts):
     for t in ts:
         if t is not None and not t.is_cuda:
@@ -132,10 +162,11 @@ def deform_align_fused(x, head, flow_1, flow_2, w_packed, bias, deform_groups, m
     f2 = flow_2.permute(0, 2, 3, 1).contiguous().float()
     b32 = None if bias is None else bias.detach().float().contiguous()
     out = torch.empty((n, cout, h, w), dtype=out_dtype, device=x.device, memory_format=torch.channels_last)
-    st = _lib.load().e2f_deform_align_fused(
-        x.data_ptr(), head.data_ptr(), f1.data_ptr(), f2.data_ptr(), w_packed.data_ptr(),
-        None if b32 is None else b32.data_ptr(), out.data_ptr(), n, h, w, cin, cout, deform_groups,
-        float(max_residue_magnitude), _DT[out_dtype], _stream())
+    with _timed("deform_align_fused", 2.0 * cout * cin * 9 * n * h * w):
+        st = _lib.load().e2f_deform_align_fused(
+            x.data_ptr(), head.data_ptr(), f1.data_ptr(), f2.data_ptr(), w_packed.data_ptr(),
+            None if b32 is None else b32.data_ptr(), out.data_ptr(), n, h, w, cin, cout, deform_groups,
+            float(max_residue_magnitude), _DT[out_dtype], _stream())
     _lib.check(st, "e2f_deform_align_fused")
     return out
 
@@ -161,12 +192,24 @@ def focal_window_attention(qkv, qkv_pooled, num_heads, window_size, expand_size,
         if qkv_pooled.dtype != torch.float16 or not qkv_pooled.is_contiguous():
             qkv_pooled = qkv_pooled.contiguous().half()
     out = torch.empty((B, T, H, W, C), dtype=out_dtype, device=qkv.device)
-    st = _lib.load().e2f_focal_window_attention(
-        qkv.data_ptr(), qkv_pooled.data_ptr() if use_pooled else None, out.data_ptr(), B, T, H, W, num_heads,
-        C // num_heads, wh, ww, expand_size[0], expand_size[1], focal_window[0], focal_window[1],
-        1 if use_pooled else 0, float(scale), _DT[out_dtype], _stream())
+    with _timed("focal_window_attention", attention_flops(B, T, H, W, C, window_size, expand_size, focal_window,
+                                                            use_pooled)):
+        st = _lib.load().e2f_focal_window_attention(
+            qkv.data_ptr(), qkv_pooled.data_ptr() if use_pooled else None, out.data_ptr(), B, T, H, W, num_heads,
+            C // num_heads, wh, ww, expand_size[0], expand_size[1], focal_window[0], focal_window[1],
+            1 if use_pooled else 0, float(scale), _DT[out_dtype], _stream())
     _lib.check(st, "e2f_focal_window_attention")
     return out
+
+
+def attention_flops(B, T, H, W, C, window_size, expand_size, focal_window, use_pooled=True):
+    """Algorithmic FLOPs of one attention launch as the REFERENCE counts keys: QK^T + PV over
+    T*(own window + listed ring keys incl. duplicates + fh*fw pooled keys incl. masked ones) keys per query."""
+    wh, ww = window_size
+    eh, ew = expand_size
+    ring = 4 * (wh * ww - (wh - eh) * (ww - ew)) if (eh or ew) else 0
+    keys = T * (wh * ww + ring + (focal_window[0] * focal_window[1] if use_pooled else 0))
+    return 4.0 * B * T * H * W * keys * C
 
 
 def launch_count():

@@ -1,0 +1,52 @@
+"""TEST helper: route the three kernel entry points of ``e2fgvi_b200.ops`` to the CPU oracle so the model's HOST
+logic (orchestration, state-dict plumbing, layouts) can be checked on a CPU-only box.  Never used by the product."""
+import contextlib
+
+import torch
+
+from e2fgvi_b200 import ops
+from e2fgvi_b200.model.modules.tfocal_transformer import rolled_valid_indices
+from oracle import restate
+
+
+def _flow_warp(x, flow, interpolation="bilinear", padding_mode="zeros", align_corners=True):
+    return restate.flow_warp(x.contiguous(), flow, interpolation, padding_mode, align_corners)
+
+
+def _pack(weight, deform_groups):
+    return weight.detach()  # the oracle consumes the unpacked weight
+
+
+def _fused(x, head, flow_1, flow_2, w_packed, bias, deform_groups, max_residue_magnitude=10.0,
+           out_dtype=torch.float32):
+    o1, o2, mask = torch.chunk(head, 3, dim=1)
+    off = max_residue_magnitude * torch.tanh(torch.cat((o1, o2), 1))
+    a, b = torch.chunk(off, 2, dim=1)
+    half = a.size(1) // 2
+    off = torch.cat([a + flow_1.flip(1).repeat(1, half, 1, 1), b + flow_2.flip(1).repeat(1, half, 1, 1)], 1)
+    return restate.modulated_deform_conv2d(x.contiguous(), off, torch.sigmoid(mask), w_packed, bias, 1, 1, 1, 1,
+                                           deform_groups).to(out_dtype)
+
+
+def _mdcn(x, offset, mask, weight, bias=None, stride=1, padding=0, dilation=1, groups=1, deform_groups=1,
+          out_dtype=torch.float32):
+    return restate.modulated_deform_conv2d(x, offset, mask, weight, bias, 1, 1, 1, 1, deform_groups).to(out_dtype)
+
+
+def _attention(qkv, qkv_pooled, num_heads, window_size, expand_size, focal_window, scale, out_dtype=torch.float32):
+    return restate.focal_window_attention(qkv.float(), None if qkv_pooled is None else qkv_pooled.float(), num_heads,
+                                          window_size, expand_size, focal_window, scale,
+                                          rolled_valid_indices(window_size, expand_size)).to(out_dtype)
+
+
+@contextlib.contextmanager
+def oracle_ops():
+    saved = {n: getattr(ops, n) for n in ("flow_warp", "pack_dcn_weight", "deform_align_fused",
+                                          "modulated_deform_conv2d", "focal_window_attention")}
+    ops.flow_warp, ops.pack_dcn_weight, ops.deform_align_fused = _flow_warp, _pack, _fused
+    ops.modulated_deform_conv2d, ops.focal_window_attention = _mdcn, _attention
+    try:
+        yield
+    finally:
+        for n, f in saved.items():
+            setattr(ops, n, f)

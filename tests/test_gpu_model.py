@@ -1,0 +1,71 @@
+"""GPU: InpaintGenerator.forward (CUDA kernels through the C ABI) against goldens made by the REAL reference.
+Tolerance is north_star's: 1e-3 max-abs on the fp32 output."""
+import importlib
+import os
+
+import pytest
+import torch
+
+from e2fgvi_b200.synth import synth_frames, synth_state_dict
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+TOL = 1e-3
+
+
+def _model(hq, family, seed, device):
+    net = importlib.import_module("model." + ("e2fgvi_hq" if hq else "e2fgvi"))
+    m = net.InpaintGenerator().eval()
+    m.load_state_dict(synth_state_dict(m, family, seed), strict=True)
+    return m.to(device)
+
+
+@pytest.mark.parametrize("name", ["e2e_hq_tiny_stress", "e2e_hq_small_stress", "e2e_base_stress", "e2e_base_default"])
+def test_forward_matches_reference_golden(cuda, name):
+    g = torch.load(os.path.join(GOLDEN, name + ".pt"))
+    c = g["case"]
+    model = _model(c["hq"], c["family"], c["weight_seed"], cuda)
+    x = synth_frames(1, c["T"], c["H"], c["W"], seed=c["frame_seed"]).to(cuda)
+    with torch.no_grad():
+        pred, (ff, fb) = model(x, c["l_t"])
+    assert pred.dtype == torch.float32 and pred.shape == (c["T"], 3, c["H"], c["W"])
+    s = g["subsample"]
+    err = (pred[:, :, ::s, ::s].cpu() - g["pred"]).abs().max().item()
+    assert err < TOL, f"{name}: max abs err {err:.3e}"
+    # flows are O(1..90) pixels and come out of a 30-conv fp32 pyramid: compare relative to their range
+    for got, want in ((ff, g["flows_forward"]), (fb, g["flows_backward"])):
+        assert (got.cpu() - want).abs().max().item() < 2e-3 * max(1.0, want.abs().max().item())
+
+
+def test_batch_independence(cuda):
+    """Clips are independent units: clip 0 of a b=2 batch equals the b=1 result."""
+    model = _model(True, "stress", 0, cuda)
+    x = torch.cat([synth_frames(1, 4, 120, 216, seed=5), synth_frames(1, 4, 120, 216, seed=6)]).to(cuda)
+    with torch.no_grad():
+        both, _ = model(x, 3)
+        one, _ = model(x[:1], 3)
+    assert (both[:4] - one).abs().max().item() < 2e-4
+
+
+def test_reference_operator_goldens(cuda):
+    g = torch.load(os.path.join(GOLDEN, "ops.pt"))
+    from model.modules.flow_comp import flow_warp
+    fw = g["flow_warp"]
+    for pad in ("zeros", "border"):
+        got = flow_warp(fw["x"].to(cuda), fw["flow"].to(cuda), padding_mode=pad)
+        assert (got.cpu() - fw[pad]).abs().max().item() < 1e-5
+    model = _model(False, "stress", 0, cuda)
+    da = g["deform_align"]
+    align = model.feat_prop_module.deform_align["backward_"]
+    with torch.no_grad():
+        for fused in (True, False):
+            align.fused = fused
+            got = align(da["x"].to(cuda), da["extra"].to(cuda), da["flow_1"].to(cuda), da["flow_2"].to(cuda))
+            rel = (got.cpu() - da["out"]).abs().max().item() / da["out"].abs().max().item()
+            assert rel < 2e-3, (fused, rel)      # fp16 operands in the deformable GEMM
+    wa = g["window_attention"]
+    attn = model.transformer[0].attn
+    with torch.no_grad():
+        got = attn([wa["x"].to(cuda), wa["pooled"].to(cuda)], [None, None])
+    rel = (got.cpu() - wa["out"]).abs().max().item() / wa["out"].abs().max().item()
+    assert got.shape == wa["out"].shape and rel < 2e-3, rel

@@ -1,0 +1,70 @@
+"""CPU: the drop-in boundary and the model's host logic (kernels replaced by the oracle, in tests only)."""
+import importlib
+import json
+import os
+
+import pytest
+import torch
+
+from e2fgvi_b200.synth import synth_frames, synth_state_dict
+from oracle_backend import oracle_ops
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.mark.parametrize("name", ["e2fgvi", "e2fgvi_hq"])
+def test_state_dict_layout_matches_reference(name):
+    """Keys, order, shapes and dtypes equal the reference generator's (strict checkpoint compatibility)."""
+    layout = json.load(open(os.path.join(GOLDEN, "state_dict_layout.json")))[name]
+    net = importlib.import_module("model." + name)          # the reference's import path (test.py:117)
+    sd = net.InpaintGenerator().state_dict()
+    assert [[k, list(v.shape), str(v.dtype)] for k, v in sd.items()] == layout
+
+
+def test_constructor_is_offline_and_default_init():
+    net = importlib.import_module("model.e2fgvi")
+    g = net.InpaintGenerator()
+    for m in g.feat_prop_module.deform_align.values():       # init_offset (feat_prop.py:32-33)
+        assert float(m.conv_offset[-1].weight.abs().max()) == 0.0
+    assert abs(float(g.encoder.layers[0].weight.std()) - 0.02) < 0.005
+    assert g.transformer[0].attn.valid_ind_rolled.numel() == 120
+
+
+@pytest.mark.parametrize("name", ["e2e_hq_tiny_stress"])
+def test_host_logic_against_golden(name):
+    g = torch.load(os.path.join(GOLDEN, name + ".pt"))
+    c = g["case"]
+    net = importlib.import_module("model." + ("e2fgvi_hq" if c["hq"] else "e2fgvi"))
+    model = net.InpaintGenerator().eval()
+    model.load_state_dict(synth_state_dict(model, c["family"], c["weight_seed"]), strict=True)
+    x = synth_frames(1, c["T"], c["H"], c["W"], seed=c["frame_seed"])
+    with torch.no_grad(), oracle_ops():
+        pred, (ff, fb) = model(x, c["l_t"])
+    assert pred.shape == (c["T"], 3, c["H"], c["W"])
+    assert (pred - g["pred"]).abs().max() < 5e-5
+    assert (ff - g["flows_forward"]).abs().max() < 1e-3 and (fb - g["flows_backward"]).abs().max() < 1e-3
+
+
+def test_reference_module_boundaries():
+    """The inner operator boundaries keep the reference's call shapes."""
+    from model.modules.tfocal_transformer import WindowAttention
+    from model.modules.feat_prop import SecondOrderDeformableAlignment
+    attn = WindowAttention(512, (2, 4), (5, 9), (5, 9), 2, 4, True, "fc").eval()
+    x = torch.randn(1, 2, 10, 18, 512)
+    pooled = torch.randn(1, 2, 2, 2, 512)
+    with torch.no_grad(), oracle_ops():
+        out = attn([x, pooled], [None, None])
+    assert out.shape == (4, 90, 512)
+    align = SecondOrderDeformableAlignment(256, 128, 3, padding=1, deform_groups=16).eval()
+    with torch.no_grad(), oracle_ops():
+        y = align(torch.randn(1, 256, 6, 8), torch.randn(1, 384, 6, 8), torch.randn(1, 2, 6, 8), torch.randn(1, 2, 6, 8))
+        align.fused = False
+        y2 = align(torch.randn(1, 256, 6, 8), torch.randn(1, 384, 6, 8), torch.randn(1, 2, 6, 8), torch.randn(1, 2, 6, 8))
+    assert y.shape == y2.shape == (1, 128, 6, 8)
+
+
+def test_forward_fails_loudly_without_gpu():
+    net = importlib.import_module("model.e2fgvi_hq")
+    model = net.InpaintGenerator().eval()
+    with torch.no_grad(), pytest.raises(RuntimeError, match="no CPU fallback"):
+        model(synth_frames(1, 3, 60, 108), 2)
