@@ -26,6 +26,23 @@ H, W, T, L_T = 240, 432, 8, 5
 METRIC = "frames/sec InpaintGenerator.forward 432x240x(5+3)"
 
 
+def log(msg):
+    print(f"[bench {time.strftime('%H:%M:%S')}] {msg}", file=sys.stderr, flush=True)
+
+
+def host_cores():
+    """CPU threads this process may really use: min(affinity mask, cgroup cpu quota) — os.cpu_count() alone
+    reports the host's cores inside a quota-limited container and oversubscribes the oracle by 10-100x."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()
+        if quota != "max":
+            n = min(n, max(1, int(int(quota) / int(period))))
+    except (OSError, ValueError):
+        pass
+    return max(1, n)
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -89,7 +106,7 @@ def cpu_oracle_fps(sd, steps=1, warmup=0):
     one 5+3 clip per step (the reference itself is single-process, b=1: test.py:108,152-166)."""
     from e2fgvi_b200.synth import synth_frames
     from oracle import restate
-    torch.set_num_threads(os.cpu_count() or 1)
+    torch.set_num_threads(host_cores())
     x = synth_frames(1, T, H, W, seed=3)
     with torch.no_grad():
         for _ in range(warmup):
@@ -131,6 +148,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--clips-per-gpu", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--precision", default="strict", choices=["strict", "tf32"],
+                    help="library conv/linear precision: strict = fp32 (TF32 off), tf32 = PyTorch GPU defaults")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
 
@@ -148,6 +167,8 @@ def main():
     from e2fgvi_b200.synth import synth_frames
     _build.build()
     model, sd = make_model(dev)
+    model.precision = args.precision
+    log(f"rank {rank}/{world}: model ready, precision={args.precision}, host cores={host_cores()}")
     B = args.clips_per_gpu
     num_clips = B * world
 
@@ -170,6 +191,7 @@ def main():
         for i in range(args.warmup):
             step(i)
         sync()
+        log("warm-up done")
         # ---------------- device-resident timing (value) + live kernel timing for the roofline
         prof = ops.profile_kernels(True)
         sampler = ClockSampler(local_rank) if rank == 0 else None
@@ -185,6 +207,7 @@ def main():
         clocks = sampler.stop() if sampler else None
         ops.profile_kernels(False)
         ms = e0.elapsed_time(e1)
+        log(f"timed region: {ms / args.steps:.2f} ms/step")
         # ---------------- end-to-end through the public API with HOST buffers (pinned H2D in, D2H of the result)
         for i in range(2):
             pred, _ = model(host_sets[i].to(dev, non_blocking=True), L_T)
@@ -201,6 +224,7 @@ def main():
         f1.record()
         sync()
         ms_e2e = f0.elapsed_time(f1)
+        log(f"e2e: {ms_e2e / args.steps:.2f} ms/step")
         # single-clip latency (BASELINE configs[1] shape, b=1)
         one = dev_sets[0][:1]
         for _ in range(3):
@@ -247,18 +271,23 @@ def main():
                         "launches_timed": len(durs), "share_of_step": sum(durs) / ms}
         cpu = None
         if not args.no_cpu_baseline:
+            log("timing the CPU oracle (1 warm-up + 2 clips) ...")
             fps, s_per, cores = cpu_oracle_fps(sd, steps=2, warmup=1)
+            log(f"CPU oracle: {s_per:.2f} s/clip on {cores} threads")
             cpu = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
                    "sample": "2 x one 5+3 clip forward after 1 warm-up (oracle/restate.py, torch CPU fp32)"}
         line = {
             "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f16 operands / f32 accumulate (DCN, attention); f32 elsewhere",
+            "vs_baseline": None,
+            "dtype": "f16 operands / f32 accumulate (DCN, attention kernels); library convs/linears "
+                     + ("f32" if args.precision == "strict" else "tf32"),
             "data": "synthetic",
             "config": {"workload": f"e2fgvi 432x240, 5 local + 3 ref frames, {B} clips per GPU per step "
                                    "(BASELINE configs[3] per-GPU share)",
                        "global_batch_clips": num_clips, "frames_per_clip": T, "parallelism": f"clip-dp{world}",
                        "l2": f"inputs rotate over {n_sets} sets x {B * T * 3 * H * W * 4 / 1e6:.0f} MB (> 126 MB L2)",
+                       "precision": args.precision,
                        "weights": "random-init, reference default family (e2fgvi_b200.synth 'default', seed 0)"},
             "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": B * T * 3 * H * W * 4 * world,
                     "d2h_bytes_per_step": B * T * 3 * H * W * 4 * world, "ms_per_step": ms_e2e / args.steps},
