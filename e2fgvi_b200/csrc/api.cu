@@ -116,4 +116,47 @@ int e2f_focal_window_attention(const void* qkv, const void* qkv_pooled, void* ou
                 "e2f_focal_window_attention");
 }
 
+static int t2t_checks(const char* who, const void* a, const void* b, int bt, int c, int h, int w, int k, int s, int p) {
+  if (!a || !b) { set_error("%s: null pointer", who); return E2F_ERR_BAD_ARG; }
+  if (bt < 0 || c <= 0 || h <= 0 || w <= 0 || k <= 0 || s <= 0 || p < 0 || h + 2 * p < k || w + 2 * p < k) { set_error("%s: bad shape", who); return E2F_ERR_BAD_ARG; }
+  if ((c * k * k) % 4) { set_error("%s: C*k*k=%d must be a multiple of 4", who, c * k * k); return E2F_ERR_UNSUPPORTED; }
+  if (!aligned(a, 16) || !aligned(b, 16)) { set_error("%s: 16-byte alignment required", who); return E2F_ERR_ALIGNMENT; }
+  return 0;
+}
+
+int e2f_t2t_unfold(const float* img, float* tokens, int bt, int c, int h, int w, int k, int stride, int pad, int gelu,
+                   void* stream) {
+  int st = t2t_checks("e2f_t2t_unfold", img, tokens, bt, c, h, w, k, stride, pad);
+  if (st) return st;
+  return finish(launch_t2t_unfold(img, tokens, bt, c, h, w, k, stride, pad, gelu, static_cast<cudaStream_t>(stream)), "e2f_t2t_unfold");
+}
+
+int e2f_t2t_fold(const float* tokens, const float* bias, float* img, int bt, int c, int h, int w, int k, int stride,
+                 int pad, int normalize, void* stream) {
+  int st = t2t_checks("e2f_t2t_fold", tokens, img, bt, c, h, w, k, stride, pad);
+  if (st) return st;
+  return finish(launch_t2t_fold(tokens, bias, img, bt, c, h, w, k, stride, pad, normalize, static_cast<cudaStream_t>(stream)), "e2f_t2t_fold");
+}
+
+int e2f_split_bf16(const float* x, void* hi_bf16, void* lo_bf16, int64_t n, void* stream) {
+  if (!x || !hi_bf16 || !lo_bf16) { set_error("e2f_split_bf16: null pointer"); return E2F_ERR_BAD_ARG; }
+  if (n < 0 || n % 8) { set_error("e2f_split_bf16: n=%lld must be a non-negative multiple of 8", static_cast<long long>(n)); return E2F_ERR_BAD_ARG; }
+  if (!aligned(x, 16) || !aligned(hi_bf16, 16) || !aligned(lo_bf16, 16)) { set_error("e2f_split_bf16: 16-byte alignment required"); return E2F_ERR_ALIGNMENT; }
+  return finish(launch_split_bf16(x, hi_bf16, lo_bf16, n, static_cast<cudaStream_t>(stream)), "e2f_split_bf16");
+}
+
+int e2f_linear_bf16x3(const void* a_hi, const void* a_lo, const void* w_hi, const void* w_lo, const float* bias,
+                      const float* residual, void* out, int m, int n, int k, int out_dtype, int tile_hint,
+                      void* stream) {
+  if (!a_hi || !a_lo || !w_hi || !w_lo || !out) { set_error("e2f_linear_bf16x3: null pointer"); return E2F_ERR_BAD_ARG; }
+  if (m < 0 || n <= 0 || k <= 0) { set_error("e2f_linear_bf16x3: bad shape m=%d n=%d k=%d", m, n, k); return E2F_ERR_BAD_ARG; }
+  if (out_dtype != E2F_F32 && out_dtype != E2F_F16) { set_error("e2f_linear_bf16x3: out_dtype %d", out_dtype); return E2F_ERR_BAD_ARG; }
+  if (tile_hint != 0 && tile_hint != 128 && tile_hint != 256) { set_error("e2f_linear_bf16x3: tile_hint %d", tile_hint); return E2F_ERR_BAD_ARG; }
+  if (k % 8 || n % (out_dtype == E2F_F16 ? 8 : 4)) { set_error("e2f_linear_bf16x3: K %% 8 and N %% %d must be 0 (k=%d n=%d)", out_dtype == E2F_F16 ? 8 : 4, k, n); return E2F_ERR_UNSUPPORTED; }
+  if (!aligned(a_hi, 16) || !aligned(a_lo, 16) || !aligned(w_hi, 16) || !aligned(w_lo, 16) || !aligned(out, 16) || (residual && !aligned(residual, 16))) { set_error("e2f_linear_bf16x3: 16-byte alignment required"); return E2F_ERR_ALIGNMENT; }
+  int bn = tile_hint;
+  if (bn == 0) bn = (n >= 1024 && n % 256 <= 128 && n % 256 != 0) ? 128 : (n >= 512 ? 256 : 128);
+  return finish(launch_linear_bf16x3(a_hi, a_lo, w_hi, w_lo, bias, residual, out, m, n, k, out_dtype, bn, static_cast<cudaStream_t>(stream)), "e2f_linear_bf16x3");
+}
+
 }  // extern "C"

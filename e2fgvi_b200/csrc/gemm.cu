@@ -1,0 +1,312 @@
+// Linear layers of the transformer path (nn.Linear at tfocal_transformer.py:44 ss.embedding, :68 sc.embedding,
+// :221 attn.qkv, :398 attn.proj, :89/:97 mlp.conv1/conv2) as ONE persistent tcgen05 GEMM with fp32-level accuracy:
+//     out[M,N] = A[M,K] . W[N,K]^T + bias[N] (+ residual[M,N])
+// fp32 operands are split into two bf16 terms (x = hi + lo, |lo| <= 2^-9 |x|) and the product is evaluated as
+//     Ah.Wh + Ah.Wl + Al.Wh      (the dropped Al.Wl term is ~2^-18 relative)
+// on the bf16 tensor pipe with fp32 accumulation in TMEM — bf16 keeps the full fp32 exponent range, so no scaling
+// is needed.  Relative error per output ~2^-17, versus 2^-11 for TF32; the SIMT fp32 cuBLAS path it replaces
+// runs at ~60 TFLOP/s.
+//
+// Structure (canonical Blackwell GEMM): persistent CTAs over a static tile schedule (n fastest, so concurrently
+// running CTAs share A row-panels in L2); warp 0 = TMA producer (4 tensor maps: Ah, Al, Wh, Wl, SWIZZLE_128B,
+// K tail / row tails zero-filled by TMA), warp 1 = MMA issuer (12 tcgen05.mma per 64-wide K block), warps 2-5 =
+// epilogue (tcgen05.ld -> +bias (+residual) -> fp32/fp16 global store) on a double-buffered TMEM accumulator, so
+// tile i's epilogue overlaps tile i+1's main loop.  smem ring: STAGES x (Ah 16K + Al 16K + Wh + Wl).
+// Roofline: tensor-bound, 3 x 2*M*N*K bf16 FLOP of tensor work per 2*M*N*K algorithmic fp32 FLOP.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include "common.cuh"
+#include "launch.h"
+
+namespace e2f {
+namespace gemm {
+
+constexpr int BM = 128, BK = 64;
+constexpr int A_TILE = BM * BK * 2;                // 16 KB (one bf16 term)
+constexpr int EPI_WARPS = 4;
+constexpr int THREADS = (2 + EPI_WARPS) * 32;      // 192
+
+template <int BN>
+struct Cfg {
+  static constexpr int W_TILE = BN * BK * 2;
+  static constexpr int STAGE = 2 * A_TILE + 2 * W_TILE;
+  static constexpr int STAGES = (BN == 128) ? 3 : 2;
+  static constexpr int TMEM_COLS = 2 * BN;          // double-buffered accumulator (256 or 512 columns)
+  static constexpr int SMEM = STAGES * STAGE + 256 + 1024;
+};
+
+// kind::f16 instruction descriptor with BF16 operands (a_format = b_format = 1), fp32 accumulate, K-major A and B
+__host__ __device__ constexpr uint32_t idesc_bf16(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(N >> 3) << 17) |
+         (static_cast<uint32_t>(M >> 4) << 24);
+}
+
+template <int BN, typename OutT>
+__global__ void __launch_bounds__(THREADS, 1)
+linear_kernel(const __grid_constant__ CUtensorMap tm_ah, const __grid_constant__ CUtensorMap tm_al,
+              const __grid_constant__ CUtensorMap tm_wh, const __grid_constant__ CUtensorMap tm_wl,
+              const float* __restrict__ bias, const float* __restrict__ residual, OutT* __restrict__ out, int M,
+              int N, int K) {
+  using C = Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE);
+  uint64_t* empty = full + C::STAGES;
+  uint64_t* acc_full = empty + C::STAGES;     // [2]
+  uint64_t* acc_empty = acc_full + 2;         // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tiles_m = (M + BM - 1) / BM, tiles_n = (N + BN - 1) / BN;
+  const int num_tiles = tiles_m * tiles_n;
+  const int num_kb = (K + BK - 1) / BK;
+
+  if (warp == 1) tmem_alloc(tmem_slot, C::TMEM_COLS);
+  if (tid == 0) {
+    for (int s = 0; s < C::STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&acc_full[s], 1);
+      mbar_init(&acc_empty[s], EPI_WARPS);
+    }
+    fence_barrier_init();
+    tma_prefetch_desc(&tm_ah);
+    tma_prefetch_desc(&tm_al);
+    tma_prefetch_desc(&tm_wh);
+    tma_prefetch_desc(&tm_wl);
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tbase = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int stage = it % C::STAGES;
+          mbar_wait(&empty[stage], ((it / C::STAGES) & 1) ^ 1);
+          mbar_arrive_expect_tx(&full[stage], C::STAGE);
+          const uint32_t s0 = smem_u32(smem + stage * C::STAGE);
+          tma_load_2d(s0, &tm_ah, &full[stage], kb * BK, m0);
+          tma_load_2d(s0 + A_TILE, &tm_al, &full[stage], kb * BK, m0);
+          tma_load_2d(s0 + 2 * A_TILE, &tm_wh, &full[stage], kb * BK, n0);
+          tma_load_2d(s0 + 2 * A_TILE + C::W_TILE, &tm_wl, &full[stage], kb * BK, n0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = idesc_bf16(BM, BN);
+      uint32_t it = 0, local = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+        const int buf = local & 1;
+        mbar_wait(&acc_empty[buf], ((local >> 1) & 1) ^ 1);
+        tc_fence_after_sync();
+        const uint32_t d = tbase + buf * BN;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int stage = it % C::STAGES;
+          mbar_wait(&full[stage], (it / C::STAGES) & 1);
+          tc_fence_after_sync();
+          const uint32_t s0 = smem_u32(smem + stage * C::STAGE);
+          const uint32_t ah = s0, al = s0 + A_TILE, wh = s0 + 2 * A_TILE, wl = wh + C::W_TILE;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t dah = umma_desc_sw128(ah + k * 32, 16, 1024), dal = umma_desc_sw128(al + k * 32, 16, 1024);
+            const uint64_t dwh = umma_desc_sw128(wh + k * 32, 16, 1024), dwl = umma_desc_sw128(wl + k * 32, 16, 1024);
+            umma_f16(d, dal, dwh, idesc, (kb | k) != 0);   // small terms first
+            umma_f16(d, dah, dwl, idesc, 1);
+            umma_f16(d, dah, dwh, idesc, 1);
+          }
+          umma_commit(&empty[stage]);
+        }
+        umma_commit(&acc_full[buf]);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (TMEM lanes by warp id % 4)
+    const int q = warp & 3;
+    uint32_t local = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+      const int buf = local & 1;
+      const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
+      mbar_wait(&acc_full[buf], (local >> 1) & 1);
+      tc_fence_after_sync();
+      const int row = m0 + q * 32 + lane;
+      const uint32_t taddr = tbase + (static_cast<uint32_t>(q * 32) << 16) + buf * BN;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld32(taddr + c * 32, v);
+        tmem_ld_wait();
+        const int col0 = n0 + c * 32;
+        if (row < M && col0 < N) {
+          const bool full_chunk = col0 + 32 <= N;
+          float f[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            float b = 0.f;
+            if (bias && (full_chunk || col0 + i < N)) b = __ldg(bias + col0 + i);
+            f[i] = __uint_as_float(v[i]) + b;
+          }
+          const size_t o = static_cast<size_t>(row) * N + col0;
+          if (full_chunk) {
+            if (residual) {
+              const float4* r4 = reinterpret_cast<const float4*>(residual + o);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float4 r = __ldg(r4 + i);
+                f[4 * i] += r.x; f[4 * i + 1] += r.y; f[4 * i + 2] += r.z; f[4 * i + 3] += r.w;
+              }
+            }
+            if constexpr (sizeof(OutT) == 4) {
+              float4* d4 = reinterpret_cast<float4*>(out + o);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) d4[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+            } else {
+              uint4* d4 = reinterpret_cast<uint4*>(out + o);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                uint4 u;
+                u.x = pack_half2(f[8 * i], f[8 * i + 1]);     u.y = pack_half2(f[8 * i + 2], f[8 * i + 3]);
+                u.z = pack_half2(f[8 * i + 4], f[8 * i + 5]); u.w = pack_half2(f[8 * i + 6], f[8 * i + 7]);
+                d4[i] = u;
+              }
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {     // static indexing keeps f[] in registers
+              if (col0 + i < N) {
+                const float val = f[i] + (residual ? __ldg(residual + o + i) : 0.f);
+                if constexpr (sizeof(OutT) == 4) out[o + i] = val;
+                else out[o + i] = __float2half_rn(val);
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[buf]);
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tbase, C::TMEM_COLS);
+}
+
+// x = hi + lo with hi = bf16(x), lo = bf16(x - hi); 8 elements per thread
+__global__ void __launch_bounds__(256) split_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ hi,
+                                                         __nv_bfloat16* __restrict__ lo, long long n8) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n8) return;
+  const float4 a = __ldg(reinterpret_cast<const float4*>(x) + 2 * i);
+  const float4 b = __ldg(reinterpret_cast<const float4*>(x) + 2 * i + 1);
+  const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+  __align__(16) __nv_bfloat16 h[8], l[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    h[e] = __float2bfloat16_rn(v[e]);
+    l[e] = __float2bfloat16_rn(v[e] - __bfloat162float(h[e]));
+  }
+  reinterpret_cast<uint4*>(hi)[i] = *reinterpret_cast<const uint4*>(h);
+  reinterpret_cast<uint4*>(lo)[i] = *reinterpret_cast<const uint4*>(l);
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess) p = nullptr;
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  return fn;
+}
+
+static int make_map(CUtensorMap* tm, const void* base, int rows, int k, int box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled is not available from the driver");
+    return -4;
+  }
+  const cuuint64_t dims[2] = {static_cast<cuuint64_t>(k), static_cast<cuuint64_t>(rows)};
+  const cuuint64_t strides[1] = {static_cast<cuuint64_t>(k) * 2};
+  const cuuint32_t box[2] = {BK, static_cast<cuuint32_t>(box_rows)};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows=%d k=%d)", static_cast<int>(r), rows, k);
+    return -4;
+  }
+  return 0;
+}
+
+static int num_sms() {
+  static int n = [] {
+    int dev = 0, v = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    return v;
+  }();
+  return n;
+}
+
+template <int BN, typename OutT>
+static int launch_variant(const void* ah, const void* al, const void* wh, const void* wl, const float* bias,
+                          const float* residual, void* out, int m, int n, int k, cudaStream_t stream) {
+  CUtensorMap tah, tal, twh, twl;
+  int st;
+  if ((st = make_map(&tah, ah, m, k, BM))) return st;
+  if ((st = make_map(&tal, al, m, k, BM))) return st;
+  if ((st = make_map(&twh, wh, n, k, BN))) return st;
+  if ((st = make_map(&twl, wl, n, k, BN))) return st;
+  auto kern = linear_kernel<BN, OutT>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    configured = true;
+  }
+  const int tiles = ((m + BM - 1) / BM) * ((n + BN - 1) / BN);
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  kern<<<grid, THREADS, Cfg<BN>::SMEM, stream>>>(tah, tal, twh, twl, bias, residual, static_cast<OutT*>(out), m, n, k);
+  count_launch();
+  return static_cast<int>(cudaGetLastError());
+}
+
+}  // namespace gemm
+
+int launch_split_bf16(const float* x, void* hi, void* lo, long long n, cudaStream_t stream) {
+  const long long n8 = n / 8;
+  if (n8 == 0) return 0;
+  const int threads = 256;
+  gemm::split_bf16_kernel<<<static_cast<unsigned>((n8 + threads - 1) / threads), threads, 0, stream>>>(
+      x, static_cast<__nv_bfloat16*>(hi), static_cast<__nv_bfloat16*>(lo), n8);
+  count_launch();
+  return static_cast<int>(cudaGetLastError());
+}
+
+int launch_linear_bf16x3(const void* a_hi, const void* a_lo, const void* w_hi, const void* w_lo, const float* bias,
+                         const float* residual, void* out, int m, int n, int k, int out_dtype, int block_n,
+                         cudaStream_t stream) {
+  using namespace gemm;
+  if (m == 0 || n == 0) return 0;
+  if (block_n == 256)
+    return out_dtype == 1 ? launch_variant<256, __half>(a_hi, a_lo, w_hi, w_lo, bias, residual, out, m, n, k, stream)
+                          : launch_variant<256, float>(a_hi, a_lo, w_hi, w_lo, bias, residual, out, m, n, k, stream);
+  return out_dtype == 1 ? launch_variant<128, __half>(a_hi, a_lo, w_hi, w_lo, bias, residual, out, m, n, k, stream)
+                        : launch_variant<128, float>(a_hi, a_lo, w_hi, w_lo, bias, residual, out, m, n, k, stream);
+}
+
+}  // namespace e2f

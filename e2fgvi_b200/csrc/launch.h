@@ -23,4 +23,14 @@ int launch_focal_attention(const void* qkv, const void* qkv_pooled, void* out, i
                            int head_dim, int wh, int ww, int eh, int ew, int fh, int fw, int use_pooled, float scale,
                            int out_dtype, cudaStream_t stream);
 
+int launch_t2t_unfold(const float* img, float* tok, int bt, int c, int h, int w, int k, int s, int p, int gelu,
+                      cudaStream_t stream);
+int launch_t2t_fold(const float* tok, const float* bias, float* img, int bt, int c, int h, int w, int k, int s,
+                    int p, int normalize, cudaStream_t stream);
+
+int launch_split_bf16(const float* x, void* hi, void* lo, long long n, cudaStream_t stream);
+int launch_linear_bf16x3(const void* a_hi, const void* a_lo, const void* w_hi, const void* w_lo, const float* bias,
+                         const float* residual, void* out, int m, int n, int k, int out_dtype, int block_n,
+                         cudaStream_t stream);
+
 }  // namespace e2f

@@ -1,0 +1,107 @@
+// Token <-> image transforms of the T2T path ("soft split" / "soft composition" / fusion feed-forward):
+//   t2t_unfold : img [BT][C][H][W] -> tokens [BT][L][C*k*k]   == F.unfold(k, stride, pad).permute(0,2,1)
+//                (tfocal_transformer.py:39-43 SoftSplit; :94-96 FusionFeedForward), optional exact GELU fused
+//   t2t_fold   : tokens [BT][L][C*k*k] -> img [BT][C][H][W]   == F.fold(x.permute(0,2,1), ...) (+ optional
+//                division by fold(ones), + optional bias map)  (tfocal_transformer.py:65-72 SoftComp; :89-96 FFN)
+// Both work directly on the token-major layout the Linears produce/consume, so the two 361 MB transposes, the
+// normaliser divide and the GELU pass of the reference formulation disappear.  Pure HBM/L2-bound gathers:
+// algorithmic bytes = tokens (BT*L*C*k*k*4) + image (BT*C*H*W*4) per call.
+#include "common.cuh"
+#include "launch.h"
+
+namespace e2f {
+
+__device__ __forceinline__ float gelu_exact(float v) { return 0.5f * v * (1.0f + erff(v * 0.70710678118654752f)); }
+
+// one thread per 4 consecutive token channels (float4 store); channel = c*k*k + ky*k + kx
+template <bool GELU>
+__global__ void __launch_bounds__(256) t2t_unfold_kernel(const float* __restrict__ img, float* __restrict__ tok,
+                                                         int BT, int C, int H, int W, int K, int S, int P, int FH,
+                                                         int FW) {
+  const int CK = C * K * K;                    // multiple of 4 is required by the launcher
+  const long long total4 = static_cast<long long>(BT) * FH * FW * (CK / 4);
+  const long long i4 = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i4 >= total4) return;
+  const int ch0 = static_cast<int>(i4 % (CK / 4)) * 4;
+  const long long t = i4 / (CK / 4);
+  const int tx = static_cast<int>(t % FW);
+  const int ty = static_cast<int>((t / FW) % FH);
+  const long long bt = t / (static_cast<long long>(FW) * FH);
+  const float* plane0 = img + bt * C * H * W;
+  float v[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const int ch = ch0 + e;
+    const int c = ch / (K * K), kk = ch - c * K * K;
+    const int ky = kk / K, kx = kk - ky * K;
+    const int y = ty * S - P + ky, x = tx * S - P + kx;
+    float val = 0.f;
+    if (y >= 0 && y < H && x >= 0 && x < W) val = __ldg(plane0 + (static_cast<long long>(c) * H + y) * W + x);
+    v[e] = GELU ? gelu_exact(val) : val;
+  }
+  *reinterpret_cast<float4*>(tok + t * CK + ch0) = make_float4(v[0], v[1], v[2], v[3]);
+}
+
+// one thread per image element (c, y, x): sums the <= ceil(K/S)^2 patch entries that cover it
+__global__ void __launch_bounds__(256) t2t_fold_kernel(const float* __restrict__ tok, const float* __restrict__ bias,
+                                                       float* __restrict__ img, int BT, int C, int H, int W, int K,
+                                                       int S, int P, int FH, int FW, int normalize) {
+  const long long total = static_cast<long long>(BT) * C * H * W;
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int x = static_cast<int>(i % W);
+  const int y = static_cast<int>((i / W) % H);
+  const int c = static_cast<int>((i / (static_cast<long long>(W) * H)) % C);
+  const long long bt = i / (static_cast<long long>(W) * H * C);
+  const int CK = C * K * K;
+  // patches (ty, ky) with ty*S - P + ky == y, 0 <= ky < K
+  const int ty_hi = min(FH - 1, (y + P) / S);
+  const int ty_lo = max(0, (y + P - K + S) / S);     // ceil((y + P - K + 1) / S) for non-negative numerators
+  const int tx_hi = min(FW - 1, (x + P) / S);
+  const int tx_lo = max(0, (x + P - K + S) / S);
+  float acc = 0.f;
+  int count = 0;
+  const float* base = tok + bt * FH * FW * CK + c * K * K;
+  for (int ty = ty_lo; ty <= ty_hi; ++ty) {
+    const int ky = y + P - ty * S;
+    if (ky < 0 || ky >= K) continue;
+    for (int tx = tx_lo; tx <= tx_hi; ++tx) {
+      const int kx = x + P - tx * S;
+      if (kx < 0 || kx >= K) continue;
+      acc += __ldg(base + static_cast<long long>(ty * FW + tx) * CK + ky * K + kx);
+      ++count;
+    }
+  }
+  if (normalize) acc = acc / static_cast<float>(count);   // == / fold(ones); count >= 1 whenever P <= K-S... checked on host
+  if (bias) acc += __ldg(bias + (static_cast<long long>(c) * H + y) * W + x);
+  img[i] = acc;
+}
+
+int launch_t2t_unfold(const float* img, float* tok, int bt, int c, int h, int w, int k, int s, int p, int gelu,
+                      cudaStream_t stream) {
+  const int fh = (h + 2 * p - k) / s + 1, fw = (w + 2 * p - k) / s + 1;
+  const long long total4 = static_cast<long long>(bt) * fh * fw * (c * k * k / 4);
+  if (total4 == 0) return 0;
+  const int threads = 256;
+  const unsigned blocks = static_cast<unsigned>((total4 + threads - 1) / threads);
+  if (gelu)
+    t2t_unfold_kernel<true><<<blocks, threads, 0, stream>>>(img, tok, bt, c, h, w, k, s, p, fh, fw);
+  else
+    t2t_unfold_kernel<false><<<blocks, threads, 0, stream>>>(img, tok, bt, c, h, w, k, s, p, fh, fw);
+  count_launch();
+  return static_cast<int>(cudaGetLastError());
+}
+
+int launch_t2t_fold(const float* tok, const float* bias, float* img, int bt, int c, int h, int w, int k, int s,
+                    int p, int normalize, cudaStream_t stream) {
+  const int fh = (h + 2 * p - k) / s + 1, fw = (w + 2 * p - k) / s + 1;
+  const long long total = static_cast<long long>(bt) * c * h * w;
+  if (total == 0) return 0;
+  const int threads = 256;
+  const unsigned blocks = static_cast<unsigned>((total + threads - 1) / threads);
+  t2t_fold_kernel<<<blocks, threads, 0, stream>>>(tok, bias, img, bt, c, h, w, k, s, p, fh, fw, normalize);
+  count_launch();
+  return static_cast<int>(cudaGetLastError());
+}
+
+}  // namespace e2f

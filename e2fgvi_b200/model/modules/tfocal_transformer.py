@@ -35,8 +35,8 @@ class SoftSplit(nn.Module):
     def forward(self, x, b, output_size=None):
         output_size = output_size or self.output_size
         f_h, f_w = _token_grid(output_size, self.kernel_size, self.stride, self.padding)
-        feat = F.unfold(x, self.kernel_size, padding=self.padding, stride=self.stride).permute(0, 2, 1)
-        feat = self.embedding(feat)
+        feat = ops.linear(ops.t2t_unfold(x, self.kernel_size, self.stride, self.padding), self.embedding.weight,
+                          self.embedding.bias)
         return feat.view(b, -1, f_h, f_w, feat.size(2))
 
 
@@ -57,11 +57,11 @@ class SoftComp(nn.Module):
     def forward(self, x, t, output_size=None):
         output_size = output_size or self.output_size
         b_, _, _, _, c_ = x.shape
-        feat = self.embedding(x.view(b_, -1, c_))
+        feat = ops.linear(x.view(b_, -1, c_), self.embedding.weight, self.embedding.bias)
         b, _, c = feat.size()
-        feat = feat.view(b * t, -1, c).permute(0, 2, 1)
-        feat = F.fold(feat, output_size, self.kernel_size, padding=self.padding, stride=self.stride)
-        return self.bias_conv(feat) if self.hq else feat + self.bias[None]
+        feat = ops.t2t_fold(feat.view(b * t, -1, c), output_size, self.kernel_size, self.stride, self.padding,
+                            bias=None if self.hq else self.bias)
+        return self.bias_conv(feat) if self.hq else feat
 
 
 class FusionFeedForward(nn.Module):
@@ -76,33 +76,21 @@ class FusionFeedForward(nn.Module):
         assert t2t_params is not None
         self.t2t_params = dict(t2t_params)
         self.n_vecs = n_vecs
-        self._normalizer = {}
 
-    def _fold_normalizer(self, output_size, like):
-        """fold(ones): how many 7x7 patches cover each pixel; a constant map per output size."""
-        key = (tuple(output_size), like.device, like.dtype)
-        m = self._normalizer.get(key)
-        if m is None:
-            p = self.t2t_params
-            f_h, f_w = _token_grid(output_size, p["kernel_size"], p["stride"], p["padding"])
-            ones = torch.ones(1, 49, f_h * f_w, device=like.device, dtype=like.dtype)
-            m = F.fold(ones, output_size, p["kernel_size"], padding=p["padding"], stride=p["stride"])
-            self._normalizer[key] = m
-        return m
-
-    def forward(self, x, output_size=None):
+    def forward(self, x, output_size=None, residual=None):
+        """conv1 -> [fold / fold(ones) -> unfold -> GELU] (two fused gather kernels on the token-major layout) -> conv2
+        (+ residual, fused into the GEMM epilogue)."""
         p = self.t2t_params
         output_size = output_size or p.get("output_size")
         f_h, f_w = _token_grid(output_size, p["kernel_size"], p["stride"], p["padding"])
         n_vecs = f_h * f_w
-        x = self.conv1(x)
+        x = ops.linear(x, self.conv1[0].weight, self.conv1[0].bias)
         b, n, c = x.size()
-        y = F.fold(x.view(-1, n_vecs, c).permute(0, 2, 1), output_size, p["kernel_size"], padding=p["padding"],
-                   stride=p["stride"])
-        y = y / self._fold_normalizer(output_size, y)
-        y = F.unfold(y, p["kernel_size"], padding=p["padding"], stride=p["stride"])
-        x = y.permute(0, 2, 1).contiguous().view(b, n, c)
-        return self.conv2(x)
+        img = ops.t2t_fold(x.view(-1, n_vecs, c), output_size, p["kernel_size"], p["stride"], p["padding"],
+                           normalize=True)
+        x = ops.t2t_unfold(img, p["kernel_size"], p["stride"], p["padding"], gelu=True).view(b, n, c)
+        # conv2[0] (GELU) is fused into the unfold kernel
+        return ops.linear(x, self.conv2[1].weight, self.conv2[1].bias, residual=residual)
 
 
 def window_partition(x, window_size):
@@ -168,13 +156,16 @@ class WindowAttention(nn.Module):
         """Neighbourhood of pooled windows each query window attends (unfold kernel, tfocal_transformer.py:186-196)."""
         return tuple(2 * (i // 2) + 1 for i in self.focal_window)
 
-    def attend(self, x, pooled):
-        """x (B,T,H,W,C) normed tokens, pooled (B,nWh,nWw,T,C) -> (B,T,H,W,C) after proj."""
-        qkv = self.qkv(x)
-        qkv_pooled = self.qkv(pooled.permute(0, 3, 1, 2, 4)) if self.uses_pooled else None
+    def attend(self, x, pooled, residual=None):
+        """x (B,T,H,W,C) normed tokens, pooled (B,nWh,nWw,T,C) -> (B,T,H,W,C) after proj (+ residual)."""
+        qkv = ops.linear(x, self.qkv.weight, self.qkv.bias, out_dtype=torch.float16)
+        qkv_pooled = None
+        if self.uses_pooled:
+            qkv_pooled = ops.linear(pooled.permute(0, 3, 1, 2, 4).contiguous(), self.qkv.weight, self.qkv.bias,
+                                    out_dtype=torch.float16)
         out = ops.focal_window_attention(qkv, qkv_pooled, self.num_heads, self.window_size, self.expand_size,
-                                         self.pooled_kernel(), self.scale, out_dtype=x.dtype)
-        return self.proj(out)
+                                         self.pooled_kernel(), self.scale, out_dtype=torch.float32)
+        return ops.linear(out, self.proj.weight, self.proj.bias, residual=residual)
 
     def forward(self, x_all, mask_all=None):
         """Reference boundary: x_all = [x (B,T,H,W,C), pooled (B,nWh,nWw,T,C)] -> (B*nW, T*wh*ww, C)."""
@@ -224,10 +215,10 @@ class TemporalFocalTransformerBlock(nn.Module):
         shortcut = x
         xn = self.norm1(x)
         pooled = self._pool_windows(xn) if self.attn.uses_pooled else None
-        x = shortcut + self.attn.attend(xn, pooled).to(shortcut.dtype)
+        x = self.attn.attend(xn, pooled, residual=shortcut)
         B, T, H, W, C = x.shape
         y = self.norm2(x)
-        return x + self.mlp(y.view(B, T * H * W, C), output_size).view(B, T, H, W, C)
+        return self.mlp(y.view(B, T * H * W, C), output_size, residual=x.view(B, T * H * W, C)).view(B, T, H, W, C)
 
     def forward(self, x):
         if self.hq:  # x = [tokens, (h, w)] -> (tokens, (h, w))   (_hq.py:492-495,562-565)

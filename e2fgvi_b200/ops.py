@@ -8,6 +8,8 @@
 Same names / argument meaning / error behaviour as the reference operators; every call goes through the C ABI of
 ``libe2fgvi_b200.so`` on the current CUDA stream.  There is no CPU path: CPU tensors raise.
 """
+import weakref
+
 import torch
 
 from . import _lib
@@ -200,6 +202,101 @@ def focal_window_attention(qkv, qkv_pooled, num_heads, window_size, expand_size,
             1 if use_pooled else 0, float(scale), _DT[out_dtype], _stream())
     _lib.check(st, "e2f_focal_window_attention")
     return out
+
+
+def t2t_unfold(img, kernel_size, stride, padding, gelu=False):
+    """``F.unfold(img, k, padding=p, stride=s).permute(0, 2, 1)`` (tfocal_transformer.py:39-43, :94-96) in one
+    gather kernel, optionally followed by the exact GELU.  img (BT,C,H,W) fp32 -> tokens (BT, L, C*k*k) fp32."""
+    _need_cuda(img)
+    (k, k2), (s, s2), (p, p2) = _pair(kernel_size), _pair(stride), _pair(padding)
+    if k != k2 or s != s2 or p != p2:
+        raise NotImplementedError("square kernel / stride / padding only (E2FGVI uses 7 / 3 / 3)")
+    img = img.contiguous().float()
+    bt, c, h, w = img.shape
+    fh, fw = (h + 2 * p - k) // s + 1, (w + 2 * p - k) // s + 1
+    tok = torch.empty((bt, fh * fw, c * k * k), dtype=torch.float32, device=img.device)
+    with _timed("t2t_unfold", float(tok.numel() * 4 + img.numel() * 4)):
+        st = _lib.load().e2f_t2t_unfold(img.data_ptr(), tok.data_ptr(), bt, c, h, w, k, s, p, 1 if gelu else 0,
+                                        _stream())
+    _lib.check(st, "e2f_t2t_unfold")
+    return tok
+
+
+def t2t_fold(tokens, output_size, kernel_size, stride, padding, normalize=False, bias=None):
+    """``F.fold(tokens.permute(0, 2, 1), output_size, k, padding=p, stride=s)`` (tfocal_transformer.py:65-72,
+    :89-96), optionally divided by fold(ones) and/or with a (C,H,W) bias map added.
+    tokens (BT, L, C*k*k) fp32 -> img (BT, C, H, W) fp32."""
+    _need_cuda(tokens, bias)
+    (k, k2), (s, s2), (p, p2) = _pair(kernel_size), _pair(stride), _pair(padding)
+    if k != k2 or s != s2 or p != p2:
+        raise NotImplementedError("square kernel / stride / padding only (E2FGVI uses 7 / 3 / 3)")
+    tokens = tokens.contiguous().float()
+    bt, L, ck = tokens.shape
+    h, w = output_size
+    fh, fw = (h + 2 * p - k) // s + 1, (w + 2 * p - k) // s + 1
+    if L != fh * fw or ck % (k * k):
+        raise ValueError(f"tokens {tuple(tokens.shape)} do not match output_size {output_size} with k={k}, s={s}, p={p}")
+    c = ck // (k * k)
+    if bias is not None:
+        if tuple(bias.shape) != (c, h, w):
+            raise ValueError(f"bias {tuple(bias.shape)} != {(c, h, w)}")
+        bias = bias.detach().contiguous().float()
+    img = torch.empty((bt, c, h, w), dtype=torch.float32, device=tokens.device)
+    with _timed("t2t_fold", float(tokens.numel() * 4 + img.numel() * 4)):
+        st = _lib.load().e2f_t2t_fold(tokens.data_ptr(), None if bias is None else bias.data_ptr(), img.data_ptr(), bt,
+                                      c, h, w, k, s, p, 1 if normalize else 0, _stream())
+    _lib.check(st, "e2f_t2t_fold")
+    return img
+
+
+def split_bf16(x):
+    """fp32 tensor -> (hi, lo) bf16 tensors with x ~= hi + lo to 2^-17 relative (numel % 8 == 0)."""
+    _need_cuda(x)
+    x = x.contiguous().float()
+    hi = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    lo = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    st = _lib.load().e2f_split_bf16(x.data_ptr(), hi.data_ptr(), lo.data_ptr(), x.numel(), _stream())
+    _lib.check(st, "e2f_split_bf16")
+    return hi, lo
+
+
+_WEIGHT_SPLITS = weakref.WeakKeyDictionary()  # Parameter object -> ((version, data_ptr), hi, lo)
+
+
+def _split_weight(weight):
+    tag = (weight._version, weight.data_ptr())
+    hit = _WEIGHT_SPLITS.get(weight)
+    if hit is None or hit[0] != tag:
+        hi, lo = split_bf16(weight.detach())
+        hit = (tag, hi, lo)
+        _WEIGHT_SPLITS[weight] = hit
+    return hit[1], hit[2]
+
+
+def linear(x, weight, bias=None, residual=None, out_dtype=torch.float32, tile_hint=0):
+    """``F.linear(x, weight, bias) (+ residual)`` on the bf16 tensor pipe with a 3-term split (fp32-level accuracy).
+
+    x (..., K) fp32, weight (N, K) fp32 nn.Parameter (its bf16 split is cached per parameter object and refreshed
+    when the parameter changes), bias (N,), residual (..., N) fp32 -> (..., N) ``out_dtype``."""
+    _need_cuda(x, weight, bias, residual)
+    n, k = weight.shape
+    lead = x.shape[:-1]
+    x2 = x.reshape(-1, k)
+    m = x2.shape[0]
+    a_hi, a_lo = split_bf16(x2)
+    w_hi, w_lo = _split_weight(weight)
+    b32 = None if bias is None else bias.detach().float().contiguous()
+    res = None
+    if residual is not None:
+        res = residual.reshape(m, n).contiguous().float()
+    out = torch.empty((m, n), dtype=out_dtype, device=x.device)
+    with _timed("linear_bf16x3", 2.0 * m * n * k):
+        st = _lib.load().e2f_linear_bf16x3(a_hi.data_ptr(), a_lo.data_ptr(), w_hi.data_ptr(), w_lo.data_ptr(),
+                                           None if b32 is None else b32.data_ptr(),
+                                           None if res is None else res.data_ptr(), out.data_ptr(), m, n, k,
+                                           _DT[out_dtype], tile_hint, _stream())
+    _lib.check(st, "e2f_linear_bf16x3")
+    return out.view(*lead, n)
 
 
 def attention_flops(B, T, H, W, C, window_size, expand_size, focal_window, use_pooled=True):

@@ -92,6 +92,31 @@ int e2f_focal_window_attention(const void* qkv, const void* qkv_pooled, void* ou
                                int heads, int head_dim, int wh, int ww, int eh, int ew, int fh, int fw,
                                int use_pooled, float scale, int out_dtype, void* stream);
 
+/* T2T token <-> image transforms, replacing F.unfold / F.fold as used by SoftSplit (tfocal_transformer.py:39-43),
+ * SoftComp (:65-72) and FusionFeedForward (:89-96).  img [BT][C][H][W] fp32 (NCHW), tokens [BT][L][C*k*k] fp32 with
+ * L = fh*fw, fh = (H+2p-k)/s+1, channel = c*k*k + ky*k + kx (torch.nn.Unfold order), i.e. the token-major layout
+ * the Linears produce / consume (no transposes).
+ *   e2f_t2t_unfold: tokens = unfold(img); gelu != 0 applies the exact (erf) GELU of FusionFeedForward.conv2[0].
+ *   e2f_t2t_fold  : img = fold(tokens); normalize != 0 divides by fold(ones) (the overlap count, :92-96);
+ *                   bias (NULL or [C][H][W]) is added after (SoftComp.bias, :60-63,71). */
+int e2f_t2t_unfold(const float* img, float* tokens, int bt, int c, int h, int w, int k, int stride, int pad,
+                   int gelu, void* stream);
+int e2f_t2t_fold(const float* tokens, const float* bias, float* img, int bt, int c, int h, int w, int k, int stride,
+                 int pad, int normalize, void* stream);
+
+/* fp32 -> two-term bf16 split (x = hi + lo, hi = bf16(x), lo = bf16(x - hi)); n must be a multiple of 8. */
+int e2f_split_bf16(const float* x, void* hi_bf16, void* lo_bf16, int64_t n, void* stream);
+
+/* nn.Linear replacement (tfocal_transformer.py:44, :68, :89, :97, :221, :398) with fp32-level accuracy on the bf16
+ * tensor pipe:  out[M][N] = A[M][K] . W[N][K]^T + bias[N] (+ residual[M][N]),  evaluated as Ah.Wh + Ah.Wl + Al.Wh
+ * with fp32 accumulation (relative error ~2^-17; TF32 would be 2^-11).
+ *   a_hi/a_lo [M][K] bf16, w_hi/w_lo [N][K] bf16 (from e2f_split_bf16), bias [N] fp32 or NULL,
+ *   residual [M][N] fp32 or NULL, out [M][N] fp32 (E2F_F32) or fp16 (E2F_F16).
+ *   K % 8 == 0; N % 4 == 0 (fp32 out) / N % 8 == 0 (fp16 out).  tile_hint: 0 = auto, 128 or 256 = N tile. */
+int e2f_linear_bf16x3(const void* a_hi, const void* a_lo, const void* w_hi, const void* w_lo, const float* bias,
+                      const float* residual, void* out, int m, int n, int k, int out_dtype, int tile_hint,
+                      void* stream);
+
 /* Number of kernel launches issued through this library since load (all threads); used by bench.py's
  * "gpu_launches" accounting. */
 int64_t e2f_launch_count(void);

@@ -39,12 +39,33 @@ def _attention(qkv, qkv_pooled, num_heads, window_size, expand_size, focal_windo
                                           rolled_valid_indices(window_size, expand_size)).to(out_dtype)
 
 
+def _unfold(img, kernel_size, stride, padding, gelu=False):
+    t = torch.nn.functional.unfold(img, kernel_size, padding=padding, stride=stride).permute(0, 2, 1).contiguous()
+    return torch.nn.functional.gelu(t) if gelu else t
+
+
+def _fold(tokens, output_size, kernel_size, stride, padding, normalize=False, bias=None):
+    F = torch.nn.functional
+    img = F.fold(tokens.permute(0, 2, 1), output_size, kernel_size, padding=padding, stride=stride)
+    if normalize:
+        ones = torch.ones(1, kernel_size[0] * kernel_size[1], tokens.shape[1], dtype=tokens.dtype)
+        img = img / F.fold(ones, output_size, kernel_size, padding=padding, stride=stride)
+    return img if bias is None else img + bias[None]
+
+
+def _linear(x, weight, bias=None, residual=None, out_dtype=torch.float32, tile_hint=0):
+    y = torch.nn.functional.linear(x, weight, bias)
+    return (y if residual is None else y + residual.reshape(y.shape)).to(out_dtype if x.is_cuda else torch.float32)
+
+
 @contextlib.contextmanager
 def oracle_ops():
     saved = {n: getattr(ops, n) for n in ("flow_warp", "pack_dcn_weight", "deform_align_fused",
-                                          "modulated_deform_conv2d", "focal_window_attention")}
+                                          "modulated_deform_conv2d", "focal_window_attention", "t2t_unfold",
+                                          "t2t_fold", "linear")}
     ops.flow_warp, ops.pack_dcn_weight, ops.deform_align_fused = _flow_warp, _pack, _fused
     ops.modulated_deform_conv2d, ops.focal_window_attention = _mdcn, _attention
+    ops.t2t_unfold, ops.t2t_fold, ops.linear = _unfold, _fold, _linear
     try:
         yield
     finally:

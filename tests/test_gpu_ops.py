@@ -190,3 +190,65 @@ def test_focal_attention_rows_sum_property(cuda):
     got = ops.focal_window_attention(qkv.to(cuda), pooled.to(cuda), 4, (5, 9), (2, 4), (5, 9), 128 ** -0.5,
                                      out_dtype=torch.float32)
     assert (got - 1.0).abs().max().item() < 2e-3
+
+
+# ------------------------------------------------------------------------------------------ T2T fold / unfold
+@pytest.mark.parametrize("shape", [(3, 40, 60, 108), (2, 128, 30, 54), (1, 4, 7, 7), (2, 8, 61, 110)])
+def test_t2t_unfold_fold(cuda, shape):
+    F = torch.nn.functional
+    bt, c, h, w = shape
+    g = torch.Generator().manual_seed(31)
+    img = torch.randn(bt, c, h, w, generator=g)
+    want = F.unfold(img, (7, 7), padding=(3, 3), stride=(3, 3)).permute(0, 2, 1)
+    got = ops.t2t_unfold(img.to(cuda), (7, 7), (3, 3), (3, 3))
+    assert torch.equal(got.cpu(), want)                               # pure data movement: bit-exact
+    got_g = ops.t2t_unfold(img.to(cuda), (7, 7), (3, 3), (3, 3), gelu=True)
+    assert (got_g.cpu() - F.gelu(want)).abs().max().item() < 2e-6
+    tok = torch.randn(bt, want.shape[1], c * 49, generator=g)
+    folded = F.fold(tok.permute(0, 2, 1), (h, w), (7, 7), padding=(3, 3), stride=(3, 3))
+    got_f = ops.t2t_fold(tok.to(cuda), (h, w), (7, 7), (3, 3), (3, 3))
+    assert (got_f.cpu() - folded).abs().max().item() < 1e-5         # <= 9 fp32 adds in a different order
+    ones = F.fold(torch.ones(1, 49, want.shape[1]), (h, w), (7, 7), padding=(3, 3), stride=(3, 3))
+    bias = torch.randn(c, h, w, generator=g)
+    got_n = ops.t2t_fold(tok.to(cuda), (h, w), (7, 7), (3, 3), (3, 3), normalize=True, bias=bias.to(cuda))
+    want_n = folded / ones + bias[None]
+    ok = torch.isfinite(want_n)
+    assert (got_n.cpu()[ok] - want_n[ok]).abs().max().item() < 1e-5
+
+
+# ------------------------------------------------------------------------------------------ bf16x3 linear
+@pytest.mark.parametrize("case", [
+    dict(m=5760, k=512, n=1536, out=torch.float16),               # attn.qkv of one clip
+    dict(m=300, k=1960, n=512, residual=True),                    # mlp.conv2: K tail (1960 = 30.6 x 64), M tail
+    dict(m=720, k=512, n=1960, tile=128),                         # mlp.conv1: N tail with 128-wide tiles
+    dict(m=720, k=512, n=1960, tile=256),                         # ... and 256-wide tiles
+    dict(m=257, k=6272, n=512),                                   # ss.embedding: long K
+    dict(m=129, k=512, n=6272, residual=True),                    # sc.embedding: wide N
+    dict(m=1, k=8, n=4),                                          # degenerate
+])
+def test_linear_bf16x3(cuda, case):
+    g = torch.Generator().manual_seed(41)
+    m, k, n = case["m"], case["k"], case["n"]
+    x = torch.randn(m, k, generator=g) * 2.0
+    w = torch.nn.Parameter(torch.randn(n, k, generator=g) / (k ** 0.5))
+    b = torch.randn(n, generator=g)
+    r = torch.randn(m, n, generator=g) if case.get("residual") else None
+    want = torch.nn.functional.linear(x.double(), w.detach().double(), b.double())
+    if r is not None:
+        want = want + r.double()
+    wd = torch.nn.Parameter(w.detach().to(cuda))
+    got = ops.linear(x.to(cuda), wd, b.to(cuda), None if r is None else r.to(cuda),
+                     out_dtype=case.get("out", torch.float32), tile_hint=case.get("tile", 0))
+    assert got.shape == (m, n)
+    tol = 1.5e-3 if case.get("out") is torch.float16 else 2e-5    # fp16 store rounding vs 3-term bf16 split (~2^-17)
+    assert _rel(got.cpu(), want) < tol, _rel(got.cpu(), want)
+
+
+def test_linear_weight_cache_tracks_updates(cuda):
+    w = torch.nn.Parameter(torch.randn(64, 64, device=cuda))
+    x = torch.randn(16, 64, device=cuda)
+    y1 = ops.linear(x, w)
+    with torch.no_grad():
+        w.mul_(2.0)
+    y2 = ops.linear(x, w)
+    assert _rel(y2, 2.0 * y1) < 1e-5
