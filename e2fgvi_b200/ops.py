@@ -260,17 +260,20 @@ def split_bf16(x):
     return hi, lo
 
 
-_WEIGHT_SPLITS = weakref.WeakKeyDictionary()  # Parameter object -> ((version, data_ptr), hi, lo)
+_WEIGHT_SPLITS = {}  # id(Parameter) -> (weakref to it, (version, data_ptr), hi, lo); dropped when the parameter dies
 
 
 def _split_weight(weight):
+    key = id(weight)
     tag = (weight._version, weight.data_ptr())
-    hit = _WEIGHT_SPLITS.get(weight)
-    if hit is None or hit[0] != tag:
+    hit = _WEIGHT_SPLITS.get(key)
+    if hit is None or hit[0]() is not weight or hit[1] != tag:
         hi, lo = split_bf16(weight.detach())
-        hit = (tag, hi, lo)
-        _WEIGHT_SPLITS[weight] = hit
-    return hit[1], hit[2]
+        if hit is None or hit[0]() is not weight:
+            weakref.finalize(weight, _WEIGHT_SPLITS.pop, key, None)
+        hit = (weakref.ref(weight), tag, hi, lo)
+        _WEIGHT_SPLITS[key] = hit
+    return hit[2], hit[3]
 
 
 def linear(x, weight, bias=None, residual=None, out_dtype=torch.float32, tile_hint=0):
