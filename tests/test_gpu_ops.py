@@ -240,7 +240,7 @@ def test_linear_bf16x3(cuda, case):
     got = ops.linear(x.to(cuda), wd, b.to(cuda), None if r is None else r.to(cuda),
                      out_dtype=case.get("out", torch.float32), tile_hint=case.get("tile", 0))
     assert got.shape == (m, n)
-    tol = 1.5e-3 if case.get("out") is torch.float16 else 2e-5    # fp16 store rounding vs 3-term bf16 split (~2^-17)
+    tol = 1.5e-3 if case.get("out") is torch.float16 else 5e-5    # fp16 store rounding vs 3-term bf16 split (~2^-16 of max|out|)
     assert _rel(got.cpu(), want) < tol, _rel(got.cpu(), want)
 
 
