@@ -33,4 +33,8 @@ int launch_linear_bf16x3(const void* a_hi, const void* a_lo, const void* w_hi, c
                          const float* residual, void* out, int m, int n, int k, int out_dtype, int block_n,
                          cudaStream_t stream);
 
+int launch_conv3x3(int nsrc, const void* const* src_hi, const void* const* src_lo, const int* src_channels,
+                   const void* w_hi, const void* w_lo, const float* bias, const float* residual, float* out, int n,
+                   int h, int w, int cout, int groups, float slope, cudaStream_t stream);
+
 }  // namespace e2f

@@ -11,6 +11,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from .. import ops
 from .modules.flow_comp import SPyNet
 from .modules.feat_prop import BidirectionalPropagation, SecondOrderDeformableAlignment
 from .modules.tfocal_transformer import SoftComp, SoftSplit, TemporalFocalTransformerBlock
@@ -67,18 +68,21 @@ class Encoder(nn.Module):
         self.layers = nn.ModuleList(layers)
 
     def forward(self, x):
-        bt = x.size(0)
-        out = x
+        """Stride-1 convs run on the tcgen05 implicit-GEMM kernel with LeakyReLU fused; the group-wise
+        concatenation of e2fgvi.py:103-108 is expressed as two TMA sources, never materialised.  The two stride-2
+        convs (1.8 % of the encoder FLOPs) stay on cuDNN."""
+        out = x.contiguous(memory_format=torch.channels_last)
         x0 = None
-        for k in range(len(_ENC)):
-            conv, act = self.layers[2 * k], self.layers[2 * k + 1]
+        for k, (_, _, stride, _) in enumerate(_ENC):
+            conv = self.layers[2 * k]
             if k == 4:
-                x0 = out
-            if k > 4:
-                g = self.group[k - 4]
-                h, w = x0.shape[-2:]
-                out = torch.cat([x0.reshape(bt, g, -1, h, w), out.reshape(bt, g, -1, h, w)], 2).reshape(bt, -1, h, w)
-            out = act(conv(out))
+                x0 = ops.split_nhwc(out)
+            if stride != 1:
+                out = F.leaky_relu(conv(out), 0.2)
+            elif k > 4:
+                out = ops.conv3x3([x0, out], conv.weight, conv.bias, groups=self.group[k - 4], negative_slope=0.2)
+            else:
+                out = ops.conv3x3([x0 if k == 4 else out], conv.weight, conv.bias, negative_slope=0.2)
         return out
 
 
@@ -172,8 +176,18 @@ class InpaintGenerator(BaseNetwork):
         trans_feat = self.sc(tokens, t, fold_size if self.HQ else None).view(b, t, -1, h, w)
         enc_feat = enc_feat + trans_feat
 
-        output = torch.tanh(self.decoder(enc_feat.reshape(b * t, c, h, w)))
-        return output, pred_flows
+        output = torch.tanh(self._decode(enc_feat.reshape(b * t, c, h, w)))
+        return output.contiguous(), pred_flows
+
+    def _decode(self, x):
+        """self.decoder (e2fgvi.py:143-150) with the convs on the tcgen05 kernel and LeakyReLU(0.2) fused."""
+        d = self.decoder
+        up = lambda t: F.interpolate(t, scale_factor=2, mode="bilinear", align_corners=True)  # noqa: E731
+        y = ops.conv3x3([up(x.contiguous(memory_format=torch.channels_last))], d[0].conv.weight, d[0].conv.bias,
+                        negative_slope=0.2)
+        y = ops.conv3x3([y], d[2].weight, d[2].bias, negative_slope=0.2)
+        y = ops.conv3x3([up(y)], d[4].conv.weight, d[4].conv.bias, negative_slope=0.2)
+        return ops.conv3x3([y], d[6].weight, d[6].bias)
 
 
 class InpaintGeneratorHQ(InpaintGenerator):

@@ -59,8 +59,19 @@ class SecondOrderDeformableAlignment(nn.Module):
         nn.init.zeros_(self.conv_offset[-1].weight)
         nn.init.zeros_(self.conv_offset[-1].bias)
 
-    def forward(self, x, extra_feat, flow_1, flow_2):
-        head = self.conv_offset(torch.cat([extra_feat, flow_1, flow_2], dim=1))
+    def offset_head(self, cond_sources, flow_1, flow_2):
+        """conv_offset on cat[cond..., flow_1, flow_2] (feat_prop.py:36-37) without building the cat: each tensor is
+        one TMA source of the first conv; LeakyReLU(0.1) is fused into the conv epilogues.  Returns the raw
+        27*dg-channel head, fp32, channels_last."""
+        co = self.conv_offset
+        flows = torch.cat([flow_1, flow_2], dim=1)
+        y = ops.conv3x3(list(cond_sources) + [flows], co[0].weight, co[0].bias, negative_slope=0.1)
+        y = ops.conv3x3([y], co[2].weight, co[2].bias, negative_slope=0.1)
+        y = ops.conv3x3([y], co[4].weight, co[4].bias, negative_slope=0.1)
+        return ops.conv3x3([y], co[6].weight, co[6].bias)
+
+    def align(self, x, cond_sources, flow_1, flow_2):
+        head = self.offset_head(cond_sources, flow_1, flow_2)
         if self.fused:
             return ops.deform_align_fused(x, head, flow_1, flow_2, self.packed_weight(), self.bias, self.deform_groups,
                                           self.max_residue_magnitude)
@@ -73,6 +84,10 @@ class SecondOrderDeformableAlignment(nn.Module):
         return ops.modulated_deform_conv2d(x, torch.cat([off1, off2], dim=1), torch.sigmoid(mask), self.weight,
                                            self.bias, self.stride, self.padding, self.dilation, self.groups,
                                            self.deform_groups)
+
+    def forward(self, x, extra_feat, flow_1, flow_2):
+        """Reference boundary (feat_prop.py:35): extra_feat is the already concatenated condition tensor."""
+        return self.align(x, [extra_feat], flow_1, flow_2)
 
 
 class BidirectionalPropagation(nn.Module):
@@ -119,12 +134,15 @@ class BidirectionalPropagation(nn.Module):
                         feat_n2 = torch.zeros_like(prop)
                         flow_n2 = torch.zeros_like(flow_n1)
                         cond_n2 = torch.zeros_like(cond_n1)
-                    cond = torch.cat([cond_n1, cur, cond_n2], dim=1)
-                    prop = align(torch.cat([prop, feat_n2], dim=1), cond, flow_n1, flow_n2)
+                    prop = align.align(torch.cat([prop, feat_n2], dim=1), [cond_n1, cur, cond_n2], flow_n1, flow_n2)
                 parts = [cur, prop] if backward else [cur, swept["backward_"][idx], prop]
-                prop = prop + backbone(torch.cat(parts, dim=1))
+                # feat_prop + backbone(cat(parts)): conv+LeakyReLU(0.1), then conv with the residual add fused
+                y = ops.conv3x3(parts, backbone[0].weight, backbone[0].bias, negative_slope=0.1)
+                prop = ops.conv3x3([y], backbone[2].weight, backbone[2].bias, residual=prop)
                 hist.append(prop)
             swept[name] = hist[::-1] if backward else hist
+        # 1x1 fusion conv == a Linear over pixels; "+ x" is its fused residual (feat_prop.py:143-149)
         both = torch.stack([torch.cat([swept["backward_"][i], swept["forward_"][i]], dim=1) for i in range(t)], 1)
-        fused = self.fusion(both.reshape(b * t, 2 * c, h, w)).view(b, t, c, h, w)
-        return fused + x
+        tokens = both.permute(0, 1, 3, 4, 2)                               # (b,t,h,w,2c)
+        out = ops.linear(tokens, self.fusion.weight, self.fusion.bias, residual=x.permute(0, 1, 3, 4, 2))
+        return out.permute(0, 1, 4, 2, 3)

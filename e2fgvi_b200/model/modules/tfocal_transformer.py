@@ -61,7 +61,7 @@ class SoftComp(nn.Module):
         b, _, c = feat.size()
         feat = ops.t2t_fold(feat.view(b * t, -1, c), output_size, self.kernel_size, self.stride, self.padding,
                             bias=None if self.hq else self.bias)
-        return self.bias_conv(feat) if self.hq else feat
+        return ops.conv3x3([feat], self.bias_conv.weight, self.bias_conv.bias) if self.hq else feat
 
 
 class FusionFeedForward(nn.Module):

@@ -268,7 +268,7 @@ def _split_weight(weight):
     tag = (weight._version, weight.data_ptr())
     hit = _WEIGHT_SPLITS.get(key)
     if hit is None or hit[0]() is not weight or hit[1] != tag:
-        hi, lo = split_bf16(weight.detach())
+        hi, lo = split_bf16(weight.detach().reshape(weight.shape[0], -1))
         if hit is None or hit[0]() is not weight:
             weakref.finalize(weight, _WEIGHT_SPLITS.pop, key, None)
         hit = (weakref.ref(weight), tag, hi, lo)
@@ -282,7 +282,7 @@ def linear(x, weight, bias=None, residual=None, out_dtype=torch.float32, tile_hi
     x (..., K) fp32, weight (N, K) fp32 nn.Parameter (its bf16 split is cached per parameter object and refreshed
     when the parameter changes), bias (N,), residual (..., N) fp32 -> (..., N) ``out_dtype``."""
     _need_cuda(x, weight, bias, residual)
-    n, k = weight.shape
+    n, k = weight.shape[:2]            # (N, K) Linear weight or (N, K, 1, 1) 1x1-conv weight
     lead = x.shape[:-1]
     x2 = x.reshape(-1, k)
     m = x2.shape[0]
@@ -300,6 +300,102 @@ def linear(x, weight, bias=None, residual=None, out_dtype=torch.float32, tile_hi
                                            _DT[out_dtype], tile_hint, _stream())
     _lib.check(st, "e2f_linear_bf16x3")
     return out.view(*lead, n)
+
+
+class SplitNHWC:
+    """An NHWC activation as two bf16 terms (hi + lo) — the operand format of ``conv3x3``. Reusable across convs."""
+
+    __slots__ = ("hi", "lo", "shape")
+
+    def __init__(self, hi, lo, shape):
+        self.hi, self.lo, self.shape = hi, lo, shape   # hi/lo: (N,H,W,Cpad) bf16; shape: logical (N,C,H,W)
+
+
+def split_nhwc(x):
+    """(N,C,H,W) fp32 (any memory format) -> SplitNHWC with channels zero-padded to a multiple of 8."""
+    if isinstance(x, SplitNHWC):
+        return x
+    _need_cuda(x)
+    n, c, h, w = x.shape
+    nhwc = x.permute(0, 2, 3, 1)
+    if c % 8:
+        nhwc = torch.nn.functional.pad(nhwc, (0, 8 - c % 8))
+    hi, lo = split_bf16(nhwc)            # .contiguous() inside is a no-op for channels_last inputs
+    return SplitNHWC(hi, lo, (n, c, h, w))
+
+
+def pack_conv3x3_weight(weight, src_channels, groups=1):
+    """fp32 (Cout, Cin/G, 3, 3) -> (hi, lo) bf16 (Cout, 9*T*64) in the K order of ``e2f_conv3x3_bf16x3``:
+    tap-major, then source, then 64-channel chunk; the group-local input channel axis is the concatenation of the
+    sources' per-group slices (exactly the channel order of the torch.cat the reference performs)."""
+    cout, cin_g, kh, kw = weight.shape
+    assert (kh, kw) == (3, 3)
+    cig = [c // groups for c in src_channels]
+    assert sum(cig) == cin_g, (src_channels, groups, cin_g)
+    chunks = [(c + 63) // 64 for c in cig]
+    T = sum(chunks)
+    w = weight.detach().float()
+    packed = torch.zeros((cout, 9, T, 64), dtype=torch.float32, device=weight.device)
+    off, base = 0, 0
+    for c, nch in zip(cig, chunks):
+        for j in range(nch):
+            cc = min(64, c - 64 * j)
+            packed[:, :, base + j, :cc] = w[:, off + 64 * j: off + 64 * j + cc].reshape(cout, cc, 9).transpose(1, 2)
+        off += c
+        base += nch
+    return split_bf16(packed.view(cout, 9 * T * 64))
+
+
+_CONV_PACKS = {}  # (id(Parameter), src channels, groups) -> (weakref, tag, hi, lo)
+
+
+def _packed_conv_weight(weight, src_channels, groups):
+    key = (id(weight), tuple(src_channels), groups)
+    tag = (weight._version, weight.data_ptr())
+    hit = _CONV_PACKS.get(key)
+    if hit is None or hit[0]() is not weight or hit[1] != tag:
+        hi, lo = pack_conv3x3_weight(weight, src_channels, groups)
+        if hit is None or hit[0]() is not weight:
+            weakref.finalize(weight, _CONV_PACKS.pop, key, None)
+        hit = (weakref.ref(weight), tag, hi, lo)
+        _CONV_PACKS[key] = hit
+    return hit[2], hit[3]
+
+
+def conv3x3(sources, weight, bias=None, groups=1, negative_slope=1.0, residual=None):
+    """``leaky_relu(F.conv2d(torch.cat(sources, 1) [group-wise for groups > 1], weight, bias, 1, 1, 1, groups),
+    negative_slope) (+ residual)`` as one tcgen05 implicit-GEMM launch; the cat is never built.
+
+    sources: list of (N,C_i,H,W) fp32 tensors or ``SplitNHWC``; weight: the nn.Conv2d parameter (Cout, sum C_i / G,
+    3, 3); returns (N,Cout,H,W) fp32 in channels_last memory format."""
+    splits = [split_nhwc(s) for s in (sources if isinstance(sources, (list, tuple)) else [sources])]
+    _need_cuda(weight, bias, residual)
+    n, _, h, w = splits[0].shape
+    for s in splits:
+        if (s.shape[0], s.shape[2], s.shape[3]) != (n, h, w):
+            raise ValueError("conv3x3 sources must share N, H, W")
+    true_channels = [s.shape[1] for s in splits]
+    padded_channels = [s.hi.shape[-1] for s in splits]
+    if groups != 1 and true_channels != padded_channels:
+        raise NotImplementedError("grouped conv3x3 needs channel counts that are multiples of 8")
+    cout = weight.shape[0]
+    w_hi, w_lo = _packed_conv_weight(weight, true_channels, groups)
+    b32 = None if bias is None else bias.detach().float().contiguous()
+    res = None
+    if residual is not None:
+        res = residual.permute(0, 2, 3, 1).contiguous().float()
+    out = torch.empty((n, h, w, cout), dtype=torch.float32, device=weight.device)
+    k = len(splits)
+    hi_arr = (_lib._vp * k)(*[s.hi.data_ptr() for s in splits])
+    lo_arr = (_lib._vp * k)(*[s.lo.data_ptr() for s in splits])
+    ch_arr = (_lib._i * k)(*padded_channels)
+    with _timed("conv3x3_bf16x3", 2.0 * n * h * w * cout * weight.shape[1] * 9):
+        st = _lib.load().e2f_conv3x3_bf16x3(k, hi_arr, lo_arr, ch_arr, w_hi.data_ptr(), w_lo.data_ptr(),
+                                            None if b32 is None else b32.data_ptr(),
+                                            None if res is None else res.data_ptr(), out.data_ptr(), n, h, w, cout,
+                                            groups, float(negative_slope), _stream())
+    _lib.check(st, "e2f_conv3x3_bf16x3")
+    return out.permute(0, 3, 1, 2)
 
 
 def attention_flops(B, T, H, W, C, window_size, expand_size, focal_window, use_pooled=True):

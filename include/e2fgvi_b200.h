@@ -117,6 +117,21 @@ int e2f_linear_bf16x3(const void* a_hi, const void* a_lo, const void* w_hi, cons
                       const float* residual, void* out, int m, int n, int k, int out_dtype, int tile_hint,
                       void* stream);
 
+/* 3x3 / stride 1 / pad 1 convolution (nn.Conv2d at e2fgvi.py:75-94,143-150; feat_prop.py:20-28,73-77) as a tcgen05
+ * implicit GEMM with fp32-level accuracy (bf16 3-term split, like e2f_linear_bf16x3):
+ *   out = leaky_relu(conv(cat(src_0 .. src_{nsrc-1}, channel dim), W) + bias, slope) (+ residual)
+ * without materialising the concatenation or an im2col buffer (TMA boxes with zero-filled out-of-bounds = padding).
+ *   src_hi[i], src_lo[i]  [N][H][W][C_i] bf16 (e2f_split_bf16 of the NHWC fp32 activation), C_i % 8 == 0, nsrc <= 4
+ *   groups G: group g convolves channels [g*C_i/G, (g+1)*C_i/G) of every source (in source order) into output
+ *             channels [g*Cout/G, (g+1)*Cout/G)   (== nn.Conv2d(groups=G) on the group-wise concatenation of
+ *             e2fgvi.py:103-108)
+ *   w_hi, w_lo [Cout][9 * T * 64] bf16 with T = sum_i ceil((C_i/G)/64): k = ((tap*T + chunk_base_i + j)*64 + c),
+ *             zero where c >= C_i/G - 64 j (see e2fgvi_b200.ops.pack_conv3x3_weight)
+ *   bias [Cout] fp32 or NULL; residual / out [N][H][W][Cout] fp32; leaky_slope = 1 disables the activation. */
+int e2f_conv3x3_bf16x3(int nsrc, const void* const* src_hi, const void* const* src_lo, const int* src_channels,
+                       const void* w_hi, const void* w_lo, const float* bias, const float* residual, float* out,
+                       int n, int h, int w, int cout, int groups, float leaky_slope, void* stream);
+
 /* Number of kernel launches issued through this library since load (all threads); used by bench.py's
  * "gpu_launches" accounting. */
 int64_t e2f_launch_count(void);

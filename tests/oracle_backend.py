@@ -53,8 +53,24 @@ def _fold(tokens, output_size, kernel_size, stride, padding, normalize=False, bi
     return img if bias is None else img + bias[None]
 
 
+def _conv3x3(sources, weight, bias=None, groups=1, negative_slope=1.0, residual=None):
+    F = torch.nn.functional
+    srcs = sources if isinstance(sources, (list, tuple)) else [sources]
+    if groups == 1:
+        x = torch.cat(srcs, 1)
+    else:  # group-wise concatenation (e2fgvi.py:103-108)
+        n, _, h, w = srcs[0].shape
+        x = torch.cat([s.reshape(n, groups, -1, h, w) for s in srcs], 2).reshape(n, -1, h, w)
+    y = F.leaky_relu(F.conv2d(x, weight, bias, 1, 1, 1, groups), negative_slope)
+    return y if residual is None else y + residual
+
+
+def _split_nhwc(x):
+    return x
+
+
 def _linear(x, weight, bias=None, residual=None, out_dtype=torch.float32, tile_hint=0):
-    y = torch.nn.functional.linear(x, weight, bias)
+    y = torch.nn.functional.linear(x, weight.reshape(weight.shape[0], -1), bias)
     return (y if residual is None else y + residual.reshape(y.shape)).to(out_dtype if x.is_cuda else torch.float32)
 
 
@@ -62,10 +78,11 @@ def _linear(x, weight, bias=None, residual=None, out_dtype=torch.float32, tile_h
 def oracle_ops():
     saved = {n: getattr(ops, n) for n in ("flow_warp", "pack_dcn_weight", "deform_align_fused",
                                           "modulated_deform_conv2d", "focal_window_attention", "t2t_unfold",
-                                          "t2t_fold", "linear")}
+                                          "t2t_fold", "linear", "conv3x3", "split_nhwc")}
     ops.flow_warp, ops.pack_dcn_weight, ops.deform_align_fused = _flow_warp, _pack, _fused
     ops.modulated_deform_conv2d, ops.focal_window_attention = _mdcn, _attention
     ops.t2t_unfold, ops.t2t_fold, ops.linear = _unfold, _fold, _linear
+    ops.conv3x3, ops.split_nhwc = _conv3x3, _split_nhwc
     try:
         yield
     finally:

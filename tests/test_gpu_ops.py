@@ -252,3 +252,40 @@ def test_linear_weight_cache_tracks_updates(cuda):
         w.mul_(2.0)
     y2 = ops.linear(x, w)
     assert _rel(y2, 2.0 * y1) < 1e-5
+
+
+# ------------------------------------------------------------------------------------------ conv3x3 (bf16x3 implicit GEMM)
+@pytest.mark.parametrize("case", [
+    dict(n=2, h=60, w=108, src=[256], cout=384, slope=0.2),                     # encoder conv 4
+    dict(n=1, h=30, w=54, src=[128, 128, 128, 4], cout=128, slope=0.1),         # offset-head conv 0 (4 sources, 4-ch flows)
+    dict(n=2, h=20, w=36, src=[256, 384], cout=512, groups=2, slope=0.2),       # encoder conv 5 (grouped concat)
+    dict(n=1, h=17, w=23, src=[256, 512], cout=384, groups=4, slope=0.2),       # encoder conv 6: 96 out ch / group
+    dict(n=1, h=9, w=19, src=[256, 384], cout=256, groups=8, slope=0.2),        # conv 7: 32+48 ch / group (chunk spill)
+    dict(n=1, h=12, w=20, src=[128], cout=128, residual=True),                  # backbone conv 2 (+ residual)
+    dict(n=1, h=24, w=40, src=[64], cout=3),                                    # last decoder conv (3 output channels)
+    dict(n=1, h=10, w=14, src=[128], cout=432),                                 # offset-head conv 6
+    dict(n=1, h=7, w=5, src=[8], cout=16),                                      # tiny
+])
+def test_conv3x3_bf16x3(cuda, case):
+    F = torch.nn.functional
+    g = torch.Generator().manual_seed(51)
+    n, h, w, groups = case["n"], case["h"], case["w"], case.get("groups", 1)
+    srcs = [torch.randn(n, c, h, w, generator=g) for c in case["src"]]
+    cin = sum(case["src"])
+    weight = torch.nn.Parameter(torch.randn(case["cout"], cin // groups, 3, 3, generator=g) / (9 * cin / groups) ** 0.5)
+    bias = torch.randn(case["cout"], generator=g) * 0.1
+    res = torch.randn(n, case["cout"], h, w, generator=g) if case.get("residual") else None
+    if groups == 1:
+        x = torch.cat(srcs, 1)
+    else:
+        x = torch.cat([s.reshape(n, groups, -1, h, w) for s in srcs], 2).reshape(n, -1, h, w)
+    want = F.leaky_relu(F.conv2d(x.double(), weight.detach().double(), bias.double(), 1, 1, 1, groups),
+                        case.get("slope", 1.0))
+    if res is not None:
+        want = want + res.double()
+    wd = torch.nn.Parameter(weight.detach().to(cuda))
+    got = ops.conv3x3([s.to(cuda).contiguous(memory_format=torch.channels_last) for s in srcs], wd, bias.to(cuda),
+                      groups=groups, negative_slope=case.get("slope", 1.0),
+                      residual=None if res is None else res.to(cuda))
+    assert got.shape == want.shape
+    assert _rel(got.cpu(), want) < 5e-5, _rel(got.cpu(), want)
