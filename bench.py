@@ -248,27 +248,43 @@ def main():
 
     if rank == 0:
         hbm, tf_burst, tf_sust, src = peaks()
-        roof = None
-        ev = prof.get("focal_window_attention", [])
-        if ev:
+        # per-kernel live timing (CUDA events around each launch inside the timed region)
+        kinds = {"focal_window_attention": ("focal_attn_kernel", "tensor", 1.0),
+                 "deform_align_fused": ("dcn_kernel", "tensor", 1.0),
+                 # bf16x3 kernels: algorithmic fp32 FLOPs; each costs 3 bf16 MMAs, so <= 1/3 of the bf16 peak
+                 "conv3x3_bf16x3": ("conv3x3_kernel", "tensor", 3.0),
+                 "linear_bf16x3": ("linear_kernel", "tensor", 3.0),
+                 "t2t_fold": ("t2t_fold_kernel", "hbm", 1.0), "t2t_unfold": ("t2t_unfold_kernel", "hbm", 1.0)}
+        traffic = {}
+        tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")   # dram bytes / launch from `ncu --set full`
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath))
+        kernels = {}
+        for key, (kname, bound, mult) in kinds.items():
+            ev = prof.get(key, [])
+            if not ev:
+                continue
             durs = [a.elapsed_time(b) for a, b, _ in ev]
-            flops = ev[0][2]
-            avg_ms = sum(durs) / len(durs)
-            ach = flops / (avg_ms * 1e-3) / 1e12
-            roof = {"kernel": "focal_attn_kernel", "bound": "tensor", "achieved": ach, "peak": tf_sust,
-                    "unit": "TFLOP/s", "frac": ach / tf_sust, "peak_source": f"{src} bf16_tflops_sustained",
-                    "traffic": None, "launches_timed": len(durs), "avg_launch_ms": avg_ms,
-                    "flop_per_launch": flops,
-                    "share_of_step": sum(durs) / ms}
-        dcn = prof.get("deform_align_fused", [])
-        roof_dcn = None
-        if dcn:
-            durs = [a.elapsed_time(b) for a, b, _ in dcn]
-            avg_ms = sum(durs) / len(durs)
-            ach = dcn[0][2] / (avg_ms * 1e-3) / 1e12
-            roof_dcn = {"kernel": "dcn_kernel", "bound": "tensor", "achieved": ach, "peak": tf_sust,
-                        "unit": "TFLOP/s", "frac": ach / tf_sust, "avg_launch_ms": avg_ms,
-                        "launches_timed": len(durs), "share_of_step": sum(durs) / ms}
+            work = sum(w for _, _, w in ev)
+            tot_ms = sum(durs)
+            if bound == "tensor":
+                ach = work / (tot_ms * 1e-3) / 1e12
+                peak, unit = tf_sust, "TFLOP/s"
+            else:
+                ach = work / (tot_ms * 1e-3) / 1e9
+                peak, unit = hbm, "GB/s"
+            kernels[kname] = {"bound": bound, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak,
+                              "launches_timed": len(durs), "avg_launch_ms": tot_ms / len(durs),
+                              "share_of_step": tot_ms / ms, "traffic": traffic.get(kname)}
+            if mult != 1.0:
+                kernels[kname]["tensor_work_multiplier"] = mult
+                kernels[kname]["tensor_pipe_frac"] = mult * ach / peak
+        roof = None
+        if kernels:
+            dom = max(kernels, key=lambda k: kernels[k]["share_of_step"])
+            roof = dict(kernels[dom], kernel=dom,
+                        peak_source=f"{src} " + ("bf16_tflops_sustained" if kernels[dom]["bound"] == "tensor" else "hbm_gbs"),
+                        note="achieved = algorithmic work (SURVEY 8d) / live CUDA-event launch time inside the timed region")
         cpu = None
         if not args.no_cpu_baseline:
             log("timing the CPU oracle (1 warm-up + 2 clips) ...")
@@ -291,7 +307,7 @@ def main():
                        "weights": "random-init, reference default family (e2fgvi_b200.synth 'default', seed 0)"},
             "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": B * T * 3 * H * W * 4 * world,
                     "d2h_bytes_per_step": B * T * 3 * H * W * 4 * world, "ms_per_step": ms_e2e / args.steps},
-            "gpu_launches": launches, "clocks": clocks, "roofline": roof, "roofline_dcn": roof_dcn,
+            "gpu_launches": launches, "clocks": clocks, "roofline": roof, "roofline_kernels": kernels,
             "cpu_baseline": cpu, "latency_b1_ms": ms_b1, "fps_b1": T / (ms_b1 * 1e-3),
         }
         print(json.dumps(line), flush=True)
