@@ -14,10 +14,13 @@ namespace e2f {
 __device__ __forceinline__ float gelu_exact(float v) { return 0.5f * v * (1.0f + erff(v * 0.70710678118654752f)); }
 
 // one thread per 4 consecutive token channels (float4 store); channel = c*k*k + ky*k + kx
-template <bool GELU>
+// KC/SC/PC: compile-time kernel / stride / padding (the div/mod by 49 and 7 become multiply-shifts); KC = 0 selects
+// the run-time geometry.
+template <bool GELU, int KC, int SC, int PC>
 __global__ void __launch_bounds__(256) t2t_unfold_kernel(const float* __restrict__ img, float* __restrict__ tok,
-                                                         int BT, int C, int H, int W, int K, int S, int P, int FH,
+                                                         int BT, int C, int H, int W, int Kr, int Sr, int Pr, int FH,
                                                          int FW) {
+  const int K = KC ? KC : Kr, S = KC ? SC : Sr, P = KC ? PC : Pr;
   const int CK = C * K * K;                    // multiple of 4 is required by the launcher
   const long long total4 = static_cast<long long>(BT) * FH * FW * (CK / 4);
   const long long i4 = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -43,9 +46,11 @@ __global__ void __launch_bounds__(256) t2t_unfold_kernel(const float* __restrict
 }
 
 // one thread per image element (c, y, x): sums the <= ceil(K/S)^2 patch entries that cover it
+template <int KC, int SC, int PC>
 __global__ void __launch_bounds__(256) t2t_fold_kernel(const float* __restrict__ tok, const float* __restrict__ bias,
-                                                       float* __restrict__ img, int BT, int C, int H, int W, int K,
-                                                       int S, int P, int FH, int FW, int normalize) {
+                                                       float* __restrict__ img, int BT, int C, int H, int W, int Kr,
+                                                       int Sr, int Pr, int FH, int FW, int normalize) {
+  const int K = KC ? KC : Kr, S = KC ? SC : Sr, P = KC ? PC : Pr;
   const long long total = static_cast<long long>(BT) * C * H * W;
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= total) return;
@@ -84,10 +89,15 @@ int launch_t2t_unfold(const float* img, float* tok, int bt, int c, int h, int w,
   if (total4 == 0) return 0;
   const int threads = 256;
   const unsigned blocks = static_cast<unsigned>((total4 + threads - 1) / threads);
-  if (gelu)
-    t2t_unfold_kernel<true><<<blocks, threads, 0, stream>>>(img, tok, bt, c, h, w, k, s, p, fh, fw);
+  const bool fast = (k == 7 && s == 3 && p == 3);
+  if (gelu && fast)
+    t2t_unfold_kernel<true, 7, 3, 3><<<blocks, threads, 0, stream>>>(img, tok, bt, c, h, w, k, s, p, fh, fw);
+  else if (fast)
+    t2t_unfold_kernel<false, 7, 3, 3><<<blocks, threads, 0, stream>>>(img, tok, bt, c, h, w, k, s, p, fh, fw);
+  else if (gelu)
+    t2t_unfold_kernel<true, 0, 0, 0><<<blocks, threads, 0, stream>>>(img, tok, bt, c, h, w, k, s, p, fh, fw);
   else
-    t2t_unfold_kernel<false><<<blocks, threads, 0, stream>>>(img, tok, bt, c, h, w, k, s, p, fh, fw);
+    t2t_unfold_kernel<false, 0, 0, 0><<<blocks, threads, 0, stream>>>(img, tok, bt, c, h, w, k, s, p, fh, fw);
   count_launch();
   return static_cast<int>(cudaGetLastError());
 }
@@ -99,7 +109,10 @@ int launch_t2t_fold(const float* tok, const float* bias, float* img, int bt, int
   if (total == 0) return 0;
   const int threads = 256;
   const unsigned blocks = static_cast<unsigned>((total + threads - 1) / threads);
-  t2t_fold_kernel<<<blocks, threads, 0, stream>>>(tok, bias, img, bt, c, h, w, k, s, p, fh, fw, normalize);
+  if (k == 7 && s == 3 && p == 3)
+    t2t_fold_kernel<7, 3, 3><<<blocks, threads, 0, stream>>>(tok, bias, img, bt, c, h, w, k, s, p, fh, fw, normalize);
+  else
+    t2t_fold_kernel<0, 0, 0><<<blocks, threads, 0, stream>>>(tok, bias, img, bt, c, h, w, k, s, p, fh, fw, normalize);
   count_launch();
   return static_cast<int>(cudaGetLastError());
 }
