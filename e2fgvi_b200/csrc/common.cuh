@@ -11,9 +11,10 @@
 
 namespace e2f {
 
-#ifndef E2F_SPIN_LIMIT_CYCLES
-// A lost arrive must end in a trap (launch failure), never in a hung GPU.
-#define E2F_SPIN_LIMIT_CYCLES (4000000000LL)
+#ifndef E2F_SPIN_LIMIT
+// A lost arrive must end in a trap (launch failure), never in a hung GPU: bounded number of try_wait polls
+// (each poll suspends in hardware for up to the try_wait time limit, so this is seconds, not microseconds).
+#define E2F_SPIN_LIMIT (1u << 24)
 #endif
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -48,14 +49,10 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
+  // bare poll loop: waiting warps share an SM sub-partition with working warps, so the loop body must stay tiny
+  uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > E2F_SPIN_LIMIT_CYCLES) {
-      printf("e2f: mbarrier timeout block=(%d,%d,%d) thread=%d bar=%u parity=%u\n", blockIdx.x, blockIdx.y,
-             blockIdx.z, threadIdx.x, smem_u32(bar), parity);
-      asm volatile("trap;");
-    }
+    if (++spins > E2F_SPIN_LIMIT) asm volatile("trap;");
   }
 }
 
