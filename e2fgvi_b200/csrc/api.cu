@@ -124,11 +124,30 @@ static int t2t_checks(const char* who, const void* a, const void* b, int bt, int
   return 0;
 }
 
-int e2f_t2t_unfold(const float* img, float* tokens, int bt, int c, int h, int w, int k, int stride, int pad, int gelu,
-                   void* stream) {
-  int st = t2t_checks("e2f_t2t_unfold", img, tokens, bt, c, h, w, k, stride, pad);
+int e2f_t2t_unfold(const float* img, float* tokens, void* tokens_hi, void* tokens_lo, int bt, int c, int h, int w, int k,
+                   int stride, int pad, int gelu, void* stream) {
+  if ((!tokens && !tokens_hi) || (!tokens_hi) != (!tokens_lo)) { set_error("e2f_t2t_unfold: need tokens and/or both of tokens_hi/tokens_lo"); return E2F_ERR_BAD_ARG; }
+  int st = t2t_checks("e2f_t2t_unfold", img, tokens ? static_cast<const void*>(tokens) : tokens_hi, bt, c, h, w, k, stride, pad);
   if (st) return st;
-  return finish(launch_t2t_unfold(img, tokens, bt, c, h, w, k, stride, pad, gelu, static_cast<cudaStream_t>(stream)), "e2f_t2t_unfold");
+  if (tokens_hi && (!aligned(tokens_hi, 16) || !aligned(tokens_lo, 16))) { set_error("e2f_t2t_unfold: 16-byte alignment required"); return E2F_ERR_ALIGNMENT; }
+  return finish(launch_t2t_unfold(img, tokens, tokens_hi, tokens_lo, bt, c, h, w, k, stride, pad, gelu, static_cast<cudaStream_t>(stream)), "e2f_t2t_unfold");
+}
+
+int e2f_upsample2x_split(const float* x, void* out_hi, void* out_lo, int n, int h, int w, int c, void* stream) {
+  if (!x || !out_hi || !out_lo) { set_error("e2f_upsample2x_split: null pointer"); return E2F_ERR_BAD_ARG; }
+  if (n < 0 || h <= 0 || w <= 0 || c <= 0) { set_error("e2f_upsample2x_split: bad shape"); return E2F_ERR_BAD_ARG; }
+  if (c % 8) { set_error("e2f_upsample2x_split: C=%d must be a multiple of 8", c); return E2F_ERR_UNSUPPORTED; }
+  if (!aligned(x, 16) || !aligned(out_hi, 16) || !aligned(out_lo, 16)) { set_error("e2f_upsample2x_split: 16-byte alignment required"); return E2F_ERR_ALIGNMENT; }
+  return finish(launch_upsample2x_split(x, out_hi, out_lo, n, h, w, c, static_cast<cudaStream_t>(stream)), "e2f_upsample2x_split");
+}
+
+int e2f_layernorm_split(const float* x, const float* gamma, const float* beta, float* out, void* out_hi, void* out_lo,
+                        int64_t rows, int c, float eps, void* stream) {
+  if (!x || !gamma || !beta) { set_error("e2f_layernorm_split: null pointer"); return E2F_ERR_BAD_ARG; }
+  if ((!out && !out_hi) || (!out_hi) != (!out_lo)) { set_error("e2f_layernorm_split: need out and/or both of out_hi/out_lo"); return E2F_ERR_BAD_ARG; }
+  if (rows < 0 || c <= 0) { set_error("e2f_layernorm_split: bad shape"); return E2F_ERR_BAD_ARG; }
+  if (!aligned(x, 16) || (out && !aligned(out, 16)) || (out_hi && (!aligned(out_hi, 16) || !aligned(out_lo, 16)))) { set_error("e2f_layernorm_split: 16-byte alignment required"); return E2F_ERR_ALIGNMENT; }
+  return finish(launch_layernorm_split(x, gamma, beta, out, out_hi, out_lo, rows, c, eps, static_cast<cudaStream_t>(stream)), "e2f_layernorm_split");
 }
 
 int e2f_t2t_fold(const float* tokens, const float* bias, float* img, int bt, int c, int h, int w, int k, int stride,
@@ -160,9 +179,12 @@ int e2f_linear_bf16x3(const void* a_hi, const void* a_lo, const void* w_hi, cons
 }
 
 int e2f_conv3x3_bf16x3(int nsrc, const void* const* src_hi, const void* const* src_lo, const int* src_channels,
-                       const void* w_hi, const void* w_lo, const float* bias, const float* residual, float* out, int n,
-                       int h, int w, int cout, int groups, float leaky_slope, void* stream) {
-  if (!src_hi || !src_lo || !src_channels || !w_hi || !w_lo || !out) { set_error("e2f_conv3x3_bf16x3: null pointer"); return E2F_ERR_BAD_ARG; }
+                       const void* w_hi, const void* w_lo, const float* bias, const float* residual, float* out,
+                       void* out_hi, void* out_lo, int n, int h, int w, int cout, int groups, float leaky_slope,
+                       void* stream) {
+  if (!src_hi || !src_lo || !src_channels || !w_hi || !w_lo) { set_error("e2f_conv3x3_bf16x3: null pointer"); return E2F_ERR_BAD_ARG; }
+  if ((!out && !out_hi) || (!out_hi) != (!out_lo)) { set_error("e2f_conv3x3_bf16x3: need out and/or both of out_hi/out_lo"); return E2F_ERR_BAD_ARG; }
+  if (out_hi && cout % 8) { set_error("e2f_conv3x3_bf16x3: split output needs Cout %% 8 == 0"); return E2F_ERR_UNSUPPORTED; }
   if (nsrc < 1 || nsrc > 4) { set_error("e2f_conv3x3_bf16x3: nsrc=%d (1..4 supported)", nsrc); return E2F_ERR_UNSUPPORTED; }
   if (n < 0 || h <= 0 || w <= 0 || cout <= 0 || groups <= 0 || cout % groups) { set_error("e2f_conv3x3_bf16x3: bad shape n=%d h=%d w=%d cout=%d groups=%d", n, h, w, cout, groups); return E2F_ERR_BAD_ARG; }
   for (int i = 0; i < nsrc; ++i) {
@@ -170,9 +192,9 @@ int e2f_conv3x3_bf16x3(int nsrc, const void* const* src_hi, const void* const* s
     if (src_channels[i] <= 0 || src_channels[i] % 8 || src_channels[i] % groups) { set_error("e2f_conv3x3_bf16x3: source %d has %d channels (needs a multiple of 8 and of groups)", i, src_channels[i]); return E2F_ERR_UNSUPPORTED; }
     if (!aligned(src_hi[i], 16) || !aligned(src_lo[i], 16)) { set_error("e2f_conv3x3_bf16x3: 16-byte alignment required"); return E2F_ERR_ALIGNMENT; }
   }
-  if (!aligned(w_hi, 16) || !aligned(w_lo, 16) || !aligned(out, 16) || (residual && !aligned(residual, 16))) { set_error("e2f_conv3x3_bf16x3: 16-byte alignment required"); return E2F_ERR_ALIGNMENT; }
+  if (!aligned(w_hi, 16) || !aligned(w_lo, 16) || (out && !aligned(out, 16)) || (out_hi && (!aligned(out_hi, 16) || !aligned(out_lo, 16))) || (residual && !aligned(residual, 16))) { set_error("e2f_conv3x3_bf16x3: 16-byte alignment required"); return E2F_ERR_ALIGNMENT; }
   if (n == 0) return 0;
-  return finish(launch_conv3x3(nsrc, src_hi, src_lo, src_channels, w_hi, w_lo, bias, residual, out, n, h, w, cout, groups, leaky_slope, static_cast<cudaStream_t>(stream)), "e2f_conv3x3_bf16x3");
+  return finish(launch_conv3x3(nsrc, src_hi, src_lo, src_channels, w_hi, w_lo, bias, residual, out, out_hi, out_lo, n, h, w, cout, groups, leaky_slope, static_cast<cudaStream_t>(stream)), "e2f_conv3x3_bf16x3");
 }
 
 }  // extern "C"

@@ -43,7 +43,9 @@ struct Params {
   float slope;             // LeakyReLU negative slope (1 = identity)
   const float* bias;
   const float* residual;   // NHWC fp32 [N][H][W][Cout] or null
-  float* out;              // NHWC fp32
+  float* out;              // NHWC fp32 or null
+  __nv_bfloat16* out_hi;   // NHWC bf16 split of the result (operand format of the next conv) or null
+  __nv_bfloat16* out_lo;
 };
 
 __host__ __device__ constexpr uint32_t idesc_bf16(int M, int N) {
@@ -79,7 +81,7 @@ __device__ __forceinline__ TileCoord decode_tile(int tile, const Params& p, int 
   return t;
 }
 
-__global__ void __launch_bounds__(THREADS, 1) conv3x3_kernel(const __grid_constant__ Maps maps, const Params p) {
+__global__ void __launch_bounds__(THREADS, 1) conv3x3_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Params p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE);
@@ -210,9 +212,29 @@ __global__ void __launch_bounds__(THREADS, 1) conv3x3_kernel(const __grid_consta
                 f[4 * i] += rr.x; f[4 * i + 1] += rr.y; f[4 * i + 2] += rr.z; f[4 * i + 3] += rr.w;
               }
             }
-            float4* d4 = reinterpret_cast<float4*>(p.out + o);
+            if (p.out) {
+              float4* d4 = reinterpret_cast<float4*>(p.out + o);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) d4[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+              for (int i = 0; i < 8; ++i) d4[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+            }
+            if (p.out_hi) {
+              uint32_t hp[16], lp[16];       // packed bf16 pairs, kept in registers
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const __nv_bfloat162 hb = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+                const float2 hf = __bfloat1622float2(hb);
+                const __nv_bfloat162 lb = __floats2bfloat162_rn(f[2 * i] - hf.x, f[2 * i + 1] - hf.y);
+                hp[i] = *reinterpret_cast<const uint32_t*>(&hb);
+                lp[i] = *reinterpret_cast<const uint32_t*>(&lb);
+              }
+              uint4* dh = reinterpret_cast<uint4*>(p.out_hi + o);
+              uint4* dl = reinterpret_cast<uint4*>(p.out_lo + o);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                dh[i] = make_uint4(hp[4 * i], hp[4 * i + 1], hp[4 * i + 2], hp[4 * i + 3]);
+                dl[i] = make_uint4(lp[4 * i], lp[4 * i + 1], lp[4 * i + 2], lp[4 * i + 3]);
+              }
+            }
           } else {
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
@@ -220,7 +242,12 @@ __global__ void __launch_bounds__(THREADS, 1) conv3x3_kernel(const __grid_consta
                 float a = __uint_as_float(v[i]) + (p.bias ? __ldg(p.bias + co + i) : 0.f);
                 a = a > 0.f ? a : a * p.slope;
                 if (p.residual) a += __ldg(p.residual + o + i);
-                p.out[o + i] = a;
+                if (p.out) p.out[o + i] = a;
+                if (p.out_hi) {
+                  const __nv_bfloat16 hb = __float2bfloat16_rn(a);
+                  p.out_hi[o + i] = hb;
+                  p.out_lo[o + i] = __float2bfloat16_rn(a - __bfloat162float(hb));
+                }
               }
             }
           }
@@ -262,8 +289,9 @@ static int num_sms() {
 }  // namespace conv
 
 int launch_conv3x3(int nsrc, const void* const* src_hi, const void* const* src_lo, const int* src_channels,
-                   const void* w_hi, const void* w_lo, const float* bias, const float* residual, float* out, int n,
-                   int h, int w, int cout, int groups, float slope, cudaStream_t stream) {
+                   const void* w_hi, const void* w_lo, const float* bias, const float* residual, float* out,
+                   void* out_hi, void* out_lo, int n, int h, int w, int cout, int groups, float slope,
+                   cudaStream_t stream) {
   using namespace conv;
   EncodeTiledFn enc = get_encode();
   if (!enc) {
@@ -274,6 +302,7 @@ int launch_conv3x3(int nsrc, const void* const* src_hi, const void* const* src_l
   Params p;
   p.N = n; p.H = h; p.W = w; p.Cout = cout; p.groups = groups; p.nsrc = nsrc;
   p.slope = slope; p.bias = bias; p.residual = residual; p.out = out;
+  p.out_hi = static_cast<__nv_bfloat16*>(out_hi); p.out_lo = static_cast<__nv_bfloat16*>(out_lo);
   p.chunks_total = 0;
   for (int i = 0; i < MAX_SRC; ++i) p.cig[i] = p.chunks[i] = 0;
   const cuuint32_t estr4[4] = {1, 1, 1, 1};

@@ -1,0 +1,135 @@
+// Producer-side fusions that emit the bf16 (hi, lo) operand pairs of the bf16x3 GEMM / conv kernels directly:
+//   upsample2x_split : F.interpolate(scale_factor=2, bilinear, align_corners=True) of e2fgvi.py:125-129 on NHWC fp32,
+//                      written as the split operand of the following conv (the 4x larger fp32 tensor never exists)
+//   layernorm_split  : nn.LayerNorm over the last dim (tfocal_transformer.py:470,533) -> fp32 and/or split output
+// HBM-bound elementwise kernels; algorithmic bytes = input read + outputs written.
+#include <cuda_bf16.h>
+#include "common.cuh"
+#include "launch.h"
+
+namespace e2f {
+
+__device__ __forceinline__ void split_store8(const float (&f)[8], __nv_bfloat16* hi, __nv_bfloat16* lo) {
+  uint32_t hp[4], lp[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const __nv_bfloat162 hb = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+    const float2 hf = __bfloat1622float2(hb);
+    const __nv_bfloat162 lb = __floats2bfloat162_rn(f[2 * i] - hf.x, f[2 * i + 1] - hf.y);
+    hp[i] = *reinterpret_cast<const uint32_t*>(&hb);
+    lp[i] = *reinterpret_cast<const uint32_t*>(&lb);
+  }
+  *reinterpret_cast<uint4*>(hi) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
+  *reinterpret_cast<uint4*>(lo) = make_uint4(lp[0], lp[1], lp[2], lp[3]);
+}
+
+// one thread per (output pixel, 8 channels); source index arithmetic mirrors ATen's upsample_bilinear2d
+__global__ void __launch_bounds__(256) upsample2x_split_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ hi,
+                                                               __nv_bfloat16* __restrict__ lo, int N, int H, int W, int C) {
+  const int OH = 2 * H, OW = 2 * W, V = C / 8;
+  const long long total = static_cast<long long>(N) * OH * OW * V;
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int v = static_cast<int>(i % V);
+  const long long pix = i / V;
+  const int ox = static_cast<int>(pix % OW);
+  const int oy = static_cast<int>((pix / OW) % OH);
+  const long long n = pix / (static_cast<long long>(OW) * OH);
+  const float rh = (OH > 1) ? static_cast<float>(H - 1) / static_cast<float>(OH - 1) : 0.f;
+  const float rw = (OW > 1) ? static_cast<float>(W - 1) / static_cast<float>(OW - 1) : 0.f;
+  const float sy = rh * oy, sx = rw * ox;
+  const int y0 = static_cast<int>(sy), x0 = static_cast<int>(sx);
+  const int y1 = y0 + ((y0 < H - 1) ? 1 : 0), x1 = x0 + ((x0 < W - 1) ? 1 : 0);
+  const float ly = sy - y0, lx = sx - x0, hy = 1.f - ly, hx = 1.f - lx;
+  const float* base = x + n * H * W * C + v * 8;
+  const float4* p00 = reinterpret_cast<const float4*>(base + (static_cast<long long>(y0) * W + x0) * C);
+  const float4* p01 = reinterpret_cast<const float4*>(base + (static_cast<long long>(y0) * W + x1) * C);
+  const float4* p10 = reinterpret_cast<const float4*>(base + (static_cast<long long>(y1) * W + x0) * C);
+  const float4* p11 = reinterpret_cast<const float4*>(base + (static_cast<long long>(y1) * W + x1) * C);
+  float f[8];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const float4 a = __ldg(p00 + h), b = __ldg(p01 + h), c = __ldg(p10 + h), d = __ldg(p11 + h);
+    f[4 * h + 0] = hy * (hx * a.x + lx * b.x) + ly * (hx * c.x + lx * d.x);
+    f[4 * h + 1] = hy * (hx * a.y + lx * b.y) + ly * (hx * c.y + lx * d.y);
+    f[4 * h + 2] = hy * (hx * a.z + lx * b.z) + ly * (hx * c.z + lx * d.z);
+    f[4 * h + 3] = hy * (hx * a.w + lx * b.w) + ly * (hx * c.w + lx * d.w);
+  }
+  const long long o = pix * C + v * 8;
+  split_store8(f, hi + o, lo + o);
+}
+
+// one warp per row of C = 32 * PER_LANE floats (C = 512 -> 16 per lane); two-pass mean / variance in registers
+template <int PER_LANE>
+__global__ void __launch_bounds__(256) layernorm_split_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                              const float* __restrict__ beta, float* __restrict__ out,
+                                                              __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
+                                                              long long rows, float eps) {
+  constexpr int C = 32 * PER_LANE;
+  const long long row = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const float* xr = x + row * C;
+  float v[PER_LANE];
+  float sum = 0.f;
+#pragma unroll
+  for (int j = 0; j < PER_LANE / 8; ++j) {        // lane owns 8 consecutive floats per 256-float segment
+    const float4 a = __ldg(reinterpret_cast<const float4*>(xr + j * 256 + lane * 8));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(xr + j * 256 + lane * 8) + 1);
+    v[8 * j + 0] = a.x; v[8 * j + 1] = a.y; v[8 * j + 2] = a.z; v[8 * j + 3] = a.w;
+    v[8 * j + 4] = b.x; v[8 * j + 5] = b.y; v[8 * j + 6] = b.z; v[8 * j + 7] = b.w;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) sum += v[8 * j + e];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float mean = sum * (1.0f / C);
+  float sq = 0.f;
+#pragma unroll
+  for (int e = 0; e < PER_LANE; ++e) {
+    const float d = v[e] - mean;
+    sq = fmaf(d, d, sq);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+  const float rstd = rsqrtf(sq * (1.0f / C) + eps);
+#pragma unroll
+  for (int j = 0; j < PER_LANE / 8; ++j) {
+    const int c0 = j * 256 + lane * 8;
+    float f[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) f[e] = (v[8 * j + e] - mean) * rstd * __ldg(gamma + c0 + e) + __ldg(beta + c0 + e);
+    if (out) {
+      float4* d4 = reinterpret_cast<float4*>(out + row * C + c0);
+      d4[0] = make_float4(f[0], f[1], f[2], f[3]);
+      d4[1] = make_float4(f[4], f[5], f[6], f[7]);
+    }
+    if (hi) split_store8(f, hi + row * C + c0, lo + row * C + c0);
+  }
+}
+
+int launch_upsample2x_split(const float* x, void* hi, void* lo, int n, int h, int w, int c, cudaStream_t stream) {
+  const long long total = static_cast<long long>(n) * 4 * h * w * (c / 8);
+  if (total == 0) return 0;
+  const int threads = 256;
+  upsample2x_split_kernel<<<static_cast<unsigned>((total + threads - 1) / threads), threads, 0, stream>>>(
+      x, static_cast<__nv_bfloat16*>(hi), static_cast<__nv_bfloat16*>(lo), n, h, w, c);
+  count_launch();
+  return static_cast<int>(cudaGetLastError());
+}
+
+int launch_layernorm_split(const float* x, const float* gamma, const float* beta, float* out, void* hi, void* lo,
+                           long long rows, int c, float eps, cudaStream_t stream) {
+  if (rows == 0) return 0;
+  if (c != 512) {
+    set_error("layernorm_split is specialised for 512 channels (got %d)", c);
+    return -2;
+  }
+  const int threads = 256, rows_per_block = threads / 32;
+  layernorm_split_kernel<16><<<static_cast<unsigned>((rows + rows_per_block - 1) / rows_per_block), threads, 0, stream>>>(
+      x, gamma, beta, out, static_cast<__nv_bfloat16*>(hi), static_cast<__nv_bfloat16*>(lo), rows, eps);
+  count_launch();
+  return static_cast<int>(cudaGetLastError());
+}
+
+}  // namespace e2f

@@ -23,8 +23,11 @@ int launch_focal_attention(const void* qkv, const void* qkv_pooled, void* out, i
                            int head_dim, int wh, int ww, int eh, int ew, int fh, int fw, int use_pooled, float scale,
                            int out_dtype, cudaStream_t stream);
 
-int launch_t2t_unfold(const float* img, float* tok, int bt, int c, int h, int w, int k, int s, int p, int gelu,
-                      cudaStream_t stream);
+int launch_t2t_unfold(const float* img, float* tok, void* tok_hi, void* tok_lo, int bt, int c, int h, int w, int k,
+                      int s, int p, int gelu, cudaStream_t stream);
+int launch_upsample2x_split(const float* x, void* hi, void* lo, int n, int h, int w, int c, cudaStream_t stream);
+int launch_layernorm_split(const float* x, const float* gamma, const float* beta, float* out, void* hi, void* lo,
+                           long long rows, int c, float eps, cudaStream_t stream);
 int launch_t2t_fold(const float* tok, const float* bias, float* img, int bt, int c, int h, int w, int k, int s,
                     int p, int normalize, cudaStream_t stream);
 
@@ -34,7 +37,8 @@ int launch_linear_bf16x3(const void* a_hi, const void* a_lo, const void* w_hi, c
                          cudaStream_t stream);
 
 int launch_conv3x3(int nsrc, const void* const* src_hi, const void* const* src_lo, const int* src_channels,
-                   const void* w_hi, const void* w_lo, const float* bias, const float* residual, float* out, int n,
-                   int h, int w, int cout, int groups, float slope, cudaStream_t stream);
+                   const void* w_hi, const void* w_lo, const float* bias, const float* residual, float* out,
+                   void* out_hi, void* out_lo, int n, int h, int w, int cout, int groups, float slope,
+                   cudaStream_t stream);
 
 }  // namespace e2f

@@ -6,6 +6,7 @@
 // Both work directly on the token-major layout the Linears produce/consume, so the two 361 MB transposes, the
 // normaliser divide and the GELU pass of the reference formulation disappear.  Pure HBM/L2-bound gathers:
 // algorithmic bytes = tokens (BT*L*C*k*k*4) + image (BT*C*H*W*4) per call.
+#include <cuda_bf16.h>
 #include "common.cuh"
 #include "launch.h"
 
@@ -18,8 +19,9 @@ __device__ __forceinline__ float gelu_exact(float v) { return 0.5f * v * (1.0f +
 // the run-time geometry.
 template <bool GELU, int KC, int SC, int PC>
 __global__ void __launch_bounds__(256) t2t_unfold_kernel(const float* __restrict__ img, float* __restrict__ tok,
-                                                         int BT, int C, int H, int W, int Kr, int Sr, int Pr, int FH,
-                                                         int FW) {
+                                                         __nv_bfloat16* __restrict__ tok_hi,
+                                                         __nv_bfloat16* __restrict__ tok_lo, int BT, int C, int H,
+                                                         int W, int Kr, int Sr, int Pr, int FH, int FW) {
   const int K = KC ? KC : Kr, S = KC ? SC : Sr, P = KC ? PC : Pr;
   const int CK = C * K * K;                    // multiple of 4 is required by the launcher
   const long long total4 = static_cast<long long>(BT) * FH * FW * (CK / 4);
@@ -42,7 +44,14 @@ __global__ void __launch_bounds__(256) t2t_unfold_kernel(const float* __restrict
     if (y >= 0 && y < H && x >= 0 && x < W) val = __ldg(plane0 + (static_cast<long long>(c) * H + y) * W + x);
     v[e] = GELU ? gelu_exact(val) : val;
   }
-  *reinterpret_cast<float4*>(tok + t * CK + ch0) = make_float4(v[0], v[1], v[2], v[3]);
+  if (tok) *reinterpret_cast<float4*>(tok + t * CK + ch0) = make_float4(v[0], v[1], v[2], v[3]);
+  if (tok_hi) {   // bf16 (hi, lo) operand pair of the following Linear, written instead of / next to the fp32 tokens
+    const __nv_bfloat162 h0 = __floats2bfloat162_rn(v[0], v[1]), h1 = __floats2bfloat162_rn(v[2], v[3]);
+    const float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
+    const __nv_bfloat162 l0 = __floats2bfloat162_rn(v[0] - f0.x, v[1] - f0.y), l1 = __floats2bfloat162_rn(v[2] - f1.x, v[3] - f1.y);
+    *reinterpret_cast<uint2*>(tok_hi + t * CK + ch0) = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
+    *reinterpret_cast<uint2*>(tok_lo + t * CK + ch0) = make_uint2(*reinterpret_cast<const uint32_t*>(&l0), *reinterpret_cast<const uint32_t*>(&l1));
+  }
 }
 
 // one thread per image element (c, y, x): sums the <= ceil(K/S)^2 patch entries that cover it
@@ -82,8 +91,10 @@ __global__ void __launch_bounds__(256) t2t_fold_kernel(const float* __restrict__
   img[i] = acc;
 }
 
-int launch_t2t_unfold(const float* img, float* tok, int bt, int c, int h, int w, int k, int s, int p, int gelu,
-                      cudaStream_t stream) {
+int launch_t2t_unfold(const float* img, float* tok, void* tok_hi_v, void* tok_lo_v, int bt, int c, int h, int w, int k,
+                      int s, int p, int gelu, cudaStream_t stream) {
+  __nv_bfloat16* tok_hi = static_cast<__nv_bfloat16*>(tok_hi_v);
+  __nv_bfloat16* tok_lo = static_cast<__nv_bfloat16*>(tok_lo_v);
   const int fh = (h + 2 * p - k) / s + 1, fw = (w + 2 * p - k) / s + 1;
   const long long total4 = static_cast<long long>(bt) * fh * fw * (c * k * k / 4);
   if (total4 == 0) return 0;
@@ -91,13 +102,13 @@ int launch_t2t_unfold(const float* img, float* tok, int bt, int c, int h, int w,
   const unsigned blocks = static_cast<unsigned>((total4 + threads - 1) / threads);
   const bool fast = (k == 7 && s == 3 && p == 3);
   if (gelu && fast)
-    t2t_unfold_kernel<true, 7, 3, 3><<<blocks, threads, 0, stream>>>(img, tok, bt, c, h, w, k, s, p, fh, fw);
+    t2t_unfold_kernel<true, 7, 3, 3><<<blocks, threads, 0, stream>>>(img, tok, tok_hi, tok_lo, bt, c, h, w, k, s, p, fh, fw);
   else if (fast)
-    t2t_unfold_kernel<false, 7, 3, 3><<<blocks, threads, 0, stream>>>(img, tok, bt, c, h, w, k, s, p, fh, fw);
+    t2t_unfold_kernel<false, 7, 3, 3><<<blocks, threads, 0, stream>>>(img, tok, tok_hi, tok_lo, bt, c, h, w, k, s, p, fh, fw);
   else if (gelu)
-    t2t_unfold_kernel<true, 0, 0, 0><<<blocks, threads, 0, stream>>>(img, tok, bt, c, h, w, k, s, p, fh, fw);
+    t2t_unfold_kernel<true, 0, 0, 0><<<blocks, threads, 0, stream>>>(img, tok, tok_hi, tok_lo, bt, c, h, w, k, s, p, fh, fw);
   else
-    t2t_unfold_kernel<false, 0, 0, 0><<<blocks, threads, 0, stream>>>(img, tok, bt, c, h, w, k, s, p, fh, fw);
+    t2t_unfold_kernel<false, 0, 0, 0><<<blocks, threads, 0, stream>>>(img, tok, tok_hi, tok_lo, bt, c, h, w, k, s, p, fh, fw);
   count_launch();
   return static_cast<int>(cudaGetLastError());
 }

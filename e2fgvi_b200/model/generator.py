@@ -73,16 +73,22 @@ class Encoder(nn.Module):
         convs (1.8 % of the encoder FLOPs) stay on cuDNN."""
         out = x.contiguous(memory_format=torch.channels_last)
         x0 = None
+        last = len(_ENC) - 1
         for k, (_, _, stride, _) in enumerate(_ENC):
             conv = self.layers[2 * k]
-            if k == 4:
-                x0 = ops.split_nhwc(out)
             if stride != 1:
                 out = F.leaky_relu(conv(out), 0.2)
-            elif k > 4:
-                out = ops.conv3x3([x0, out], conv.weight, conv.bias, groups=self.group[k - 4], negative_slope=0.2)
+                continue
+            # conv -> conv chains hand over the bf16 split operand written by the epilogue ("split"); fp32 is only
+            # materialised where a non-conv consumer needs it (the stride-2 cuDNN conv after k=1, the final features)
+            mode = "f32" if (k == last or _ENC[k + 1][2] != 1) else "split"
+            if k == 4:
+                x0 = out
+            if k > 4:
+                out = ops.conv3x3([x0, out], conv.weight, conv.bias, groups=self.group[k - 4], negative_slope=0.2,
+                                  out=mode)
             else:
-                out = ops.conv3x3([x0 if k == 4 else out], conv.weight, conv.bias, negative_slope=0.2)
+                out = ops.conv3x3([out], conv.weight, conv.bias, negative_slope=0.2, out=mode)
         return out
 
 
@@ -182,11 +188,9 @@ class InpaintGenerator(BaseNetwork):
     def _decode(self, x):
         """self.decoder (e2fgvi.py:143-150) with the convs on the tcgen05 kernel and LeakyReLU(0.2) fused."""
         d = self.decoder
-        up = lambda t: F.interpolate(t, scale_factor=2, mode="bilinear", align_corners=True)  # noqa: E731
-        y = ops.conv3x3([up(x.contiguous(memory_format=torch.channels_last))], d[0].conv.weight, d[0].conv.bias,
-                        negative_slope=0.2)
+        y = ops.conv3x3([ops.upsample2x_split(x)], d[0].conv.weight, d[0].conv.bias, negative_slope=0.2, out="split")
         y = ops.conv3x3([y], d[2].weight, d[2].bias, negative_slope=0.2)
-        y = ops.conv3x3([up(y)], d[4].conv.weight, d[4].conv.bias, negative_slope=0.2)
+        y = ops.conv3x3([ops.upsample2x_split(y)], d[4].conv.weight, d[4].conv.bias, negative_slope=0.2, out="split")
         return ops.conv3x3([y], d[6].weight, d[6].bias)
 
 

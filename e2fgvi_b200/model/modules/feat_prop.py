@@ -65,9 +65,9 @@ class SecondOrderDeformableAlignment(nn.Module):
         27*dg-channel head, fp32, channels_last."""
         co = self.conv_offset
         flows = torch.cat([flow_1, flow_2], dim=1)
-        y = ops.conv3x3(list(cond_sources) + [flows], co[0].weight, co[0].bias, negative_slope=0.1)
-        y = ops.conv3x3([y], co[2].weight, co[2].bias, negative_slope=0.1)
-        y = ops.conv3x3([y], co[4].weight, co[4].bias, negative_slope=0.1)
+        y = ops.conv3x3(list(cond_sources) + [flows], co[0].weight, co[0].bias, negative_slope=0.1, out="split")
+        y = ops.conv3x3([y], co[2].weight, co[2].bias, negative_slope=0.1, out="split")
+        y = ops.conv3x3([y], co[4].weight, co[4].bias, negative_slope=0.1, out="split")
         return ops.conv3x3([y], co[6].weight, co[6].bias)
 
     def align(self, x, cond_sources, flow_1, flow_2):
@@ -137,7 +137,7 @@ class BidirectionalPropagation(nn.Module):
                     prop = align.align(torch.cat([prop, feat_n2], dim=1), [cond_n1, cur, cond_n2], flow_n1, flow_n2)
                 parts = [cur, prop] if backward else [cur, swept["backward_"][idx], prop]
                 # feat_prop + backbone(cat(parts)): conv+LeakyReLU(0.1), then conv with the residual add fused
-                y = ops.conv3x3(parts, backbone[0].weight, backbone[0].bias, negative_slope=0.1)
+                y = ops.conv3x3(parts, backbone[0].weight, backbone[0].bias, negative_slope=0.1, out="split")
                 prop = ops.conv3x3([y], backbone[2].weight, backbone[2].bias, residual=prop)
                 hist.append(prop)
             swept[name] = hist[::-1] if backward else hist

@@ -88,7 +88,7 @@ class FusionFeedForward(nn.Module):
         b, n, c = x.size()
         img = ops.t2t_fold(x.view(-1, n_vecs, c), output_size, p["kernel_size"], p["stride"], p["padding"],
                            normalize=True)
-        x = ops.t2t_unfold(img, p["kernel_size"], p["stride"], p["padding"], gelu=True).view(b, n, c)
+        x = ops.t2t_unfold(img, p["kernel_size"], p["stride"], p["padding"], gelu=True, out="split").view(b, n, c)
         # conv2[0] (GELU) is fused into the unfold kernel
         return ops.linear(x, self.conv2[1].weight, self.conv2[1].bias, residual=residual)
 
@@ -157,7 +157,8 @@ class WindowAttention(nn.Module):
         return tuple(2 * (i // 2) + 1 for i in self.focal_window)
 
     def attend(self, x, pooled, residual=None):
-        """x (B,T,H,W,C) normed tokens, pooled (B,nWh,nWw,T,C) -> (B,T,H,W,C) after proj (+ residual)."""
+        """x (B,T,H,W,C) normed tokens (tensor or ops.SplitMat), pooled (B,nWh,nWw,T,C) -> (B,T,H,W,C) after proj
+        (+ residual)."""
         qkv = ops.linear(x, self.qkv.weight, self.qkv.bias, out_dtype=torch.float16)
         qkv_pooled = None
         if self.uses_pooled:
@@ -213,11 +214,12 @@ class TemporalFocalTransformerBlock(nn.Module):
 
     def _forward(self, x, output_size):
         shortcut = x
-        xn = self.norm1(x)
-        pooled = self._pool_windows(xn) if self.attn.uses_pooled else None
-        x = self.attn.attend(xn, pooled, residual=shortcut)
         B, T, H, W, C = x.shape
-        y = self.norm2(x)
+        # LayerNorm writes fp32 (for the window pooling) and the bf16 split operand of the qkv Linear in one pass
+        xn, xn_split = ops.layer_norm(x, self.norm1.weight, self.norm1.bias, self.norm1.eps, out="both")
+        pooled = self._pool_windows(xn) if self.attn.uses_pooled else None
+        x = self.attn.attend(xn_split, pooled, residual=shortcut)
+        y = ops.layer_norm(x, self.norm2.weight, self.norm2.bias, self.norm2.eps, out="split")
         return self.mlp(y.view(B, T * H * W, C), output_size, residual=x.view(B, T * H * W, C)).view(B, T, H, W, C)
 
     def forward(self, x):

@@ -204,9 +204,27 @@ def focal_window_attention(qkv, qkv_pooled, num_heads, window_size, expand_size,
     return out
 
 
-def t2t_unfold(img, kernel_size, stride, padding, gelu=False):
+class SplitMat:
+    """A (..., K) activation as two bf16 terms (hi + lo): the A operand of ``linear`` produced directly by a fused
+    producer (LayerNorm, unfold+GELU), so no fp32 round trip and no standalone split launch."""
+
+    __slots__ = ("hi", "lo")
+
+    def __init__(self, hi, lo):
+        self.hi, self.lo = hi, lo
+
+    @property
+    def shape(self):
+        return self.hi.shape
+
+    def view(self, *shape):
+        return SplitMat(self.hi.view(*shape), self.lo.view(*shape))
+
+
+def t2t_unfold(img, kernel_size, stride, padding, gelu=False, out="f32"):
     """``F.unfold(img, k, padding=p, stride=s).permute(0, 2, 1)`` (tfocal_transformer.py:39-43, :94-96) in one
-    gather kernel, optionally followed by the exact GELU.  img (BT,C,H,W) fp32 -> tokens (BT, L, C*k*k) fp32."""
+    gather kernel, optionally followed by the exact GELU.  img (BT,C,H,W) fp32 -> tokens (BT, L, C*k*k): fp32
+    tensor (out="f32") or a ``SplitMat`` (out="split")."""
     _need_cuda(img)
     (k, k2), (s, s2), (p, p2) = _pair(kernel_size), _pair(stride), _pair(padding)
     if k != k2 or s != s2 or p != p2:
@@ -214,12 +232,62 @@ def t2t_unfold(img, kernel_size, stride, padding, gelu=False):
     img = img.contiguous().float()
     bt, c, h, w = img.shape
     fh, fw = (h + 2 * p - k) // s + 1, (w + 2 * p - k) // s + 1
-    tok = torch.empty((bt, fh * fw, c * k * k), dtype=torch.float32, device=img.device)
-    with _timed("t2t_unfold", float(tok.numel() * 4 + img.numel() * 4)):
-        st = _lib.load().e2f_t2t_unfold(img.data_ptr(), tok.data_ptr(), bt, c, h, w, k, s, p, 1 if gelu else 0,
-                                        _stream())
+    shape = (bt, fh * fw, c * k * k)
+    tok = hi = lo = None
+    if out == "f32":
+        tok = torch.empty(shape, dtype=torch.float32, device=img.device)
+    elif out == "split":
+        hi = torch.empty(shape, dtype=torch.bfloat16, device=img.device)
+        lo = torch.empty(shape, dtype=torch.bfloat16, device=img.device)
+    else:
+        raise ValueError("out must be 'f32' or 'split'")
+    numel = shape[0] * shape[1] * shape[2]
+    with _timed("t2t_unfold", float(numel * 4 + img.numel() * 4)):
+        st = _lib.load().e2f_t2t_unfold(img.data_ptr(), None if tok is None else tok.data_ptr(),
+                                        None if hi is None else hi.data_ptr(), None if lo is None else lo.data_ptr(),
+                                        bt, c, h, w, k, s, p, 1 if gelu else 0, _stream())
     _lib.check(st, "e2f_t2t_unfold")
-    return tok
+    return tok if out == "f32" else SplitMat(hi, lo)
+
+
+def upsample2x_split(x):
+    """``F.interpolate(x, scale_factor=2, mode='bilinear', align_corners=True)`` (deconv.forward, e2fgvi.py:125-129)
+    fused with the bf16 split: (N,C,H,W) fp32 -> ``SplitNHWC`` of (N,C,2H,2W); the upsampled fp32 tensor never exists."""
+    _need_cuda(x)
+    n, c, h, w = x.shape
+    if c % 8:
+        raise ValueError("upsample2x_split needs C % 8 == 0")
+    xcl = x.permute(0, 2, 3, 1).contiguous().float()      # no-op for channels_last inputs
+    hi = torch.empty((n, 2 * h, 2 * w, c), dtype=torch.bfloat16, device=x.device)
+    lo = torch.empty((n, 2 * h, 2 * w, c), dtype=torch.bfloat16, device=x.device)
+    with _timed("upsample2x_split", float(xcl.numel() * 4 + hi.numel() * 4)):
+        st = _lib.load().e2f_upsample2x_split(xcl.data_ptr(), hi.data_ptr(), lo.data_ptr(), n, h, w, c, _stream())
+    _lib.check(st, "e2f_upsample2x_split")
+    return SplitNHWC(hi, lo, (n, c, 2 * h, 2 * w))
+
+
+def layer_norm(x, weight, bias, eps=1e-5, out="f32"):
+    """``F.layer_norm(x, (C,), weight, bias, eps)`` over the last dim (C = 512).  out = "f32": tensor; "split": a
+    ``SplitMat`` (operand of the following ``linear``); "both": (tensor, SplitMat)."""
+    _need_cuda(x, weight, bias)
+    c = x.shape[-1]
+    xc = x.contiguous().float()
+    rows = xc.numel() // c
+    want_f32, want_split = out in ("f32", "both"), out in ("split", "both")
+    if not (want_f32 or want_split):
+        raise ValueError("out must be 'f32', 'split' or 'both'")
+    o32 = torch.empty_like(xc) if want_f32 else None
+    hi = torch.empty(xc.shape, dtype=torch.bfloat16, device=x.device) if want_split else None
+    lo = torch.empty(xc.shape, dtype=torch.bfloat16, device=x.device) if want_split else None
+    g32, b32 = weight.detach().float().contiguous(), bias.detach().float().contiguous()
+    with _timed("layernorm_split", float(xc.numel() * 4 * (1 + want_f32 + want_split))):
+        st = _lib.load().e2f_layernorm_split(xc.data_ptr(), g32.data_ptr(), b32.data_ptr(),
+                                             None if o32 is None else o32.data_ptr(),
+                                             None if hi is None else hi.data_ptr(),
+                                             None if lo is None else lo.data_ptr(), rows, c, float(eps), _stream())
+    _lib.check(st, "e2f_layernorm_split")
+    sp = SplitMat(hi, lo) if want_split else None
+    return o32 if out == "f32" else sp if out == "split" else (o32, sp)
 
 
 def t2t_fold(tokens, output_size, kernel_size, stride, padding, normalize=False, bias=None):
@@ -281,18 +349,23 @@ def linear(x, weight, bias=None, residual=None, out_dtype=torch.float32, tile_hi
 
     x (..., K) fp32, weight (N, K) fp32 nn.Parameter (its bf16 split is cached per parameter object and refreshed
     when the parameter changes), bias (N,), residual (..., N) fp32 -> (..., N) ``out_dtype``."""
-    _need_cuda(x, weight, bias, residual)
     n, k = weight.shape[:2]            # (N, K) Linear weight or (N, K, 1, 1) 1x1-conv weight
     lead = x.shape[:-1]
-    x2 = x.reshape(-1, k)
-    m = x2.shape[0]
-    a_hi, a_lo = split_bf16(x2)
+    if isinstance(x, SplitMat):         # operand pair written by a fused producer
+        _need_cuda(weight, bias, residual)
+        a_hi, a_lo = x.hi.reshape(-1, k), x.lo.reshape(-1, k)
+        m = a_hi.shape[0]
+    else:
+        _need_cuda(x, weight, bias, residual)
+        x2 = x.reshape(-1, k)
+        m = x2.shape[0]
+        a_hi, a_lo = split_bf16(x2)
     w_hi, w_lo = _split_weight(weight)
     b32 = None if bias is None else bias.detach().float().contiguous()
     res = None
     if residual is not None:
         res = residual.reshape(m, n).contiguous().float()
-    out = torch.empty((m, n), dtype=out_dtype, device=x.device)
+    out = torch.empty((m, n), dtype=out_dtype, device=weight.device)
     with _timed("linear_bf16x3", 2.0 * m * n * k):
         st = _lib.load().e2f_linear_bf16x3(a_hi.data_ptr(), a_lo.data_ptr(), w_hi.data_ptr(), w_lo.data_ptr(),
                                            None if b32 is None else b32.data_ptr(),
@@ -362,12 +435,13 @@ def _packed_conv_weight(weight, src_channels, groups):
     return hit[2], hit[3]
 
 
-def conv3x3(sources, weight, bias=None, groups=1, negative_slope=1.0, residual=None):
+def conv3x3(sources, weight, bias=None, groups=1, negative_slope=1.0, residual=None, out="f32"):
     """``leaky_relu(F.conv2d(torch.cat(sources, 1) [group-wise for groups > 1], weight, bias, 1, 1, 1, groups),
     negative_slope) (+ residual)`` as one tcgen05 implicit-GEMM launch; the cat is never built.
 
     sources: list of (N,C_i,H,W) fp32 tensors or ``SplitNHWC``; weight: the nn.Conv2d parameter (Cout, sum C_i / G,
-    3, 3); returns (N,Cout,H,W) fp32 in channels_last memory format."""
+    3, 3).  out = "f32": (N,Cout,H,W) fp32 channels_last tensor; "split": a ``SplitNHWC`` (the bf16 operand pair of a
+    following conv3x3, written by the epilogue, no fp32 round trip); "both": (tensor, SplitNHWC)."""
     splits = [split_nhwc(s) for s in (sources if isinstance(sources, (list, tuple)) else [sources])]
     _need_cuda(weight, bias, residual)
     n, _, h, w = splits[0].shape
@@ -384,7 +458,13 @@ def conv3x3(sources, weight, bias=None, groups=1, negative_slope=1.0, residual=N
     res = None
     if residual is not None:
         res = residual.permute(0, 2, 3, 1).contiguous().float()
-    out = torch.empty((n, h, w, cout), dtype=torch.float32, device=weight.device)
+    want_f32, want_split = out in ("f32", "both"), out in ("split", "both")
+    if not (want_f32 or want_split):
+        raise ValueError("out must be 'f32', 'split' or 'both'")
+    dev = weight.device
+    o32 = torch.empty((n, h, w, cout), dtype=torch.float32, device=dev) if want_f32 else None
+    ohi = torch.empty((n, h, w, cout), dtype=torch.bfloat16, device=dev) if want_split else None
+    olo = torch.empty((n, h, w, cout), dtype=torch.bfloat16, device=dev) if want_split else None
     k = len(splits)
     hi_arr = (_lib._vp * k)(*[s.hi.data_ptr() for s in splits])
     lo_arr = (_lib._vp * k)(*[s.lo.data_ptr() for s in splits])
@@ -392,10 +472,15 @@ def conv3x3(sources, weight, bias=None, groups=1, negative_slope=1.0, residual=N
     with _timed("conv3x3_bf16x3", 2.0 * n * h * w * cout * weight.shape[1] * 9):
         st = _lib.load().e2f_conv3x3_bf16x3(k, hi_arr, lo_arr, ch_arr, w_hi.data_ptr(), w_lo.data_ptr(),
                                             None if b32 is None else b32.data_ptr(),
-                                            None if res is None else res.data_ptr(), out.data_ptr(), n, h, w, cout,
+                                            None if res is None else res.data_ptr(),
+                                            None if o32 is None else o32.data_ptr(),
+                                            None if ohi is None else ohi.data_ptr(),
+                                            None if olo is None else olo.data_ptr(), n, h, w, cout,
                                             groups, float(negative_slope), _stream())
     _lib.check(st, "e2f_conv3x3_bf16x3")
-    return out.permute(0, 3, 1, 2)
+    t32 = o32.permute(0, 3, 1, 2) if want_f32 else None
+    sp = SplitNHWC(ohi, olo, (n, cout, h, w)) if want_split else None
+    return t32 if out == "f32" else sp if out == "split" else (t32, sp)
 
 
 def attention_flops(B, T, H, W, C, window_size, expand_size, focal_window, use_pooled=True):

@@ -97,12 +97,25 @@ int e2f_focal_window_attention(const void* qkv, const void* qkv_pooled, void* ou
  * L = fh*fw, fh = (H+2p-k)/s+1, channel = c*k*k + ky*k + kx (torch.nn.Unfold order), i.e. the token-major layout
  * the Linears produce / consume (no transposes).
  *   e2f_t2t_unfold: tokens = unfold(img); gelu != 0 applies the exact (erf) GELU of FusionFeedForward.conv2[0].
+ *                   Outputs (at least one): tokens fp32 and/or tokens_hi, tokens_lo bf16 (the split operand pair of
+ *                   the following e2f_linear_bf16x3).
  *   e2f_t2t_fold  : img = fold(tokens); normalize != 0 divides by fold(ones) (the overlap count, :92-96);
  *                   bias (NULL or [C][H][W]) is added after (SoftComp.bias, :60-63,71). */
-int e2f_t2t_unfold(const float* img, float* tokens, int bt, int c, int h, int w, int k, int stride, int pad,
-                   int gelu, void* stream);
+int e2f_t2t_unfold(const float* img, float* tokens, void* tokens_hi, void* tokens_lo, int bt, int c, int h, int w,
+                   int k, int stride, int pad, int gelu, void* stream);
 int e2f_t2t_fold(const float* tokens, const float* bias, float* img, int bt, int c, int h, int w, int k, int stride,
                  int pad, int normalize, void* stream);
+
+/* x2 bilinear upsample, align_corners=True (F.interpolate in deconv.forward, e2fgvi.py:125-129) of an NHWC fp32
+ * tensor [N][H][W][C] (C % 8 == 0), written directly as the bf16 (hi, lo) split [N][2H][2W][C] consumed by
+ * e2f_conv3x3_bf16x3 — the 4x larger fp32 intermediate is never materialised. */
+int e2f_upsample2x_split(const float* x, void* out_hi, void* out_lo, int n, int h, int w, int c, void* stream);
+
+/* nn.LayerNorm over the last dimension (tfocal_transformer.py:470 norm1, :533 norm2; C = 512):
+ * y = (x - mean) / sqrt(var + eps) * gamma + beta, biased variance.  Outputs (at least one): out fp32 [rows][C]
+ * and/or out_hi, out_lo bf16 (split operand pair of the following e2f_linear_bf16x3). */
+int e2f_layernorm_split(const float* x, const float* gamma, const float* beta, float* out, void* out_hi, void* out_lo,
+                        int64_t rows, int c, float eps, void* stream);
 
 /* fp32 -> two-term bf16 split (x = hi + lo, hi = bf16(x), lo = bf16(x - hi)); n must be a multiple of 8. */
 int e2f_split_bf16(const float* x, void* hi_bf16, void* lo_bf16, int64_t n, void* stream);
@@ -127,10 +140,13 @@ int e2f_linear_bf16x3(const void* a_hi, const void* a_lo, const void* w_hi, cons
  *             e2fgvi.py:103-108)
  *   w_hi, w_lo [Cout][9 * T * 64] bf16 with T = sum_i ceil((C_i/G)/64): k = ((tap*T + chunk_base_i + j)*64 + c),
  *             zero where c >= C_i/G - 64 j (see e2fgvi_b200.ops.pack_conv3x3_weight)
- *   bias [Cout] fp32 or NULL; residual / out [N][H][W][Cout] fp32; leaky_slope = 1 disables the activation. */
+ *   bias [Cout] fp32 or NULL; residual [N][H][W][Cout] fp32 or NULL; leaky_slope = 1 disables the activation.
+ *   Outputs (at least one): out [N][H][W][Cout] fp32 and/or out_hi, out_lo [N][H][W][Cout] bf16 = the two-term
+ *   split of the result, i.e. directly the operand format of a following e2f_conv3x3_bf16x3 (Cout % 8 == 0). */
 int e2f_conv3x3_bf16x3(int nsrc, const void* const* src_hi, const void* const* src_lo, const int* src_channels,
                        const void* w_hi, const void* w_lo, const float* bias, const float* residual, float* out,
-                       int n, int h, int w, int cout, int groups, float leaky_slope, void* stream);
+                       void* out_hi, void* out_lo, int n, int h, int w, int cout, int groups, float leaky_slope,
+                       void* stream);
 
 /* Number of kernel launches issued through this library since load (all threads); used by bench.py's
  * "gpu_launches" accounting. */

@@ -39,7 +39,7 @@ def _attention(qkv, qkv_pooled, num_heads, window_size, expand_size, focal_windo
                                           rolled_valid_indices(window_size, expand_size)).to(out_dtype)
 
 
-def _unfold(img, kernel_size, stride, padding, gelu=False):
+def _unfold(img, kernel_size, stride, padding, gelu=False, out="f32"):
     t = torch.nn.functional.unfold(img, kernel_size, padding=padding, stride=stride).permute(0, 2, 1).contiguous()
     return torch.nn.functional.gelu(t) if gelu else t
 
@@ -53,7 +53,16 @@ def _fold(tokens, output_size, kernel_size, stride, padding, normalize=False, bi
     return img if bias is None else img + bias[None]
 
 
-def _conv3x3(sources, weight, bias=None, groups=1, negative_slope=1.0, residual=None):
+def _upsample(x):
+    return torch.nn.functional.interpolate(x, scale_factor=2, mode="bilinear", align_corners=True)
+
+
+def _layer_norm(x, weight, bias, eps=1e-5, out="f32"):
+    y = torch.nn.functional.layer_norm(x, (x.shape[-1],), weight, bias, eps)
+    return (y, y) if out == "both" else y
+
+
+def _conv3x3(sources, weight, bias=None, groups=1, negative_slope=1.0, residual=None, out="f32"):
     F = torch.nn.functional
     srcs = sources if isinstance(sources, (list, tuple)) else [sources]
     if groups == 1:
@@ -62,7 +71,8 @@ def _conv3x3(sources, weight, bias=None, groups=1, negative_slope=1.0, residual=
         n, _, h, w = srcs[0].shape
         x = torch.cat([s.reshape(n, groups, -1, h, w) for s in srcs], 2).reshape(n, -1, h, w)
     y = F.leaky_relu(F.conv2d(x, weight, bias, 1, 1, 1, groups), negative_slope)
-    return y if residual is None else y + residual
+    y = y if residual is None else y + residual
+    return (y, y) if out == "both" else y
 
 
 def _split_nhwc(x):
@@ -78,11 +88,13 @@ def _linear(x, weight, bias=None, residual=None, out_dtype=torch.float32, tile_h
 def oracle_ops():
     saved = {n: getattr(ops, n) for n in ("flow_warp", "pack_dcn_weight", "deform_align_fused",
                                           "modulated_deform_conv2d", "focal_window_attention", "t2t_unfold",
-                                          "t2t_fold", "linear", "conv3x3", "split_nhwc")}
+                                          "t2t_fold", "linear", "conv3x3", "split_nhwc", "upsample2x_split",
+                                          "layer_norm")}
     ops.flow_warp, ops.pack_dcn_weight, ops.deform_align_fused = _flow_warp, _pack, _fused
     ops.modulated_deform_conv2d, ops.focal_window_attention = _mdcn, _attention
     ops.t2t_unfold, ops.t2t_fold, ops.linear = _unfold, _fold, _linear
     ops.conv3x3, ops.split_nhwc = _conv3x3, _split_nhwc
+    ops.upsample2x_split, ops.layer_norm = _upsample, _layer_norm
     try:
         yield
     finally:

@@ -289,3 +289,58 @@ def test_conv3x3_bf16x3(cuda, case):
                       residual=None if res is None else res.to(cuda))
     assert got.shape == want.shape
     assert _rel(got.cpu(), want) < 5e-5, _rel(got.cpu(), want)
+
+
+# ------------------------------------------------------------------------------------------ fused producers
+def _join(sp):
+    return sp.hi.float() + sp.lo.float()
+
+
+def test_upsample2x_split(cuda):
+    F = torch.nn.functional
+    g = torch.Generator().manual_seed(61)
+    for shape in [(2, 64, 30, 54), (1, 128, 7, 9), (3, 8, 1, 5)]:
+        x = torch.randn(*shape, generator=g)
+        want = F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=True)
+        got = ops.upsample2x_split(x.to(cuda).contiguous(memory_format=torch.channels_last))
+        assert got.shape == tuple(want.shape)
+        back = _join(got).permute(0, 3, 1, 2).cpu()
+        # bf16 two-term split keeps ~2^-17 relative; interpolation weights differ by fp32 rounding only
+        assert (back - want).abs().max().item() < 5e-5
+
+
+def test_layer_norm_split(cuda):
+    F = torch.nn.functional
+    g = torch.Generator().manual_seed(62)
+    x = torch.randn(3, 5, 7, 512, generator=g) * 3 + 0.5
+    w, b = torch.randn(512, generator=g), torch.randn(512, generator=g)
+    want = F.layer_norm(x.double(), (512,), w.double(), b.double(), 1e-5)
+    y32, ysp = ops.layer_norm(x.to(cuda), w.to(cuda), b.to(cuda), 1e-5, out="both")
+    assert (y32.cpu() - want).abs().max().item() < 2e-5
+    assert (_join(ysp).cpu() - want).abs().max().item() < 1e-4
+    only = ops.layer_norm(x.to(cuda), w.to(cuda), b.to(cuda), 1e-5, out="split")
+    assert torch.equal(only.hi, ysp.hi) and torch.equal(only.lo, ysp.lo)
+
+
+def test_t2t_unfold_split_and_conv_split_outputs(cuda):
+    F = torch.nn.functional
+    g = torch.Generator().manual_seed(63)
+    img = torch.randn(2, 40, 30, 54, generator=g)
+    want = F.gelu(F.unfold(img, (7, 7), padding=(3, 3), stride=(3, 3)).permute(0, 2, 1))
+    sp = ops.t2t_unfold(img.to(cuda), (7, 7), (3, 3), (3, 3), gelu=True, out="split")
+    assert (_join(sp).cpu() - want).abs().max().item() < 5e-5
+    # a Linear fed by the split equals the Linear fed by the fp32 tensor
+    w = torch.nn.Parameter(torch.randn(64, 1960, generator=g).to(cuda) / 44.0)
+    a = ops.linear(sp, w)
+    b = ops.linear(want.to(cuda), w)
+    assert _rel(a, b) < 2e-5
+    # conv3x3 split / both outputs
+    x = torch.randn(1, 64, 12, 20, generator=g).to(cuda).contiguous(memory_format=torch.channels_last)
+    cw = torch.nn.Parameter(torch.randn(128, 64, 3, 3, generator=g).to(cuda) / 24.0)
+    f32, both_sp = ops.conv3x3([x], cw, None, negative_slope=0.2, out="both")
+    only_sp = ops.conv3x3([x], cw, None, negative_slope=0.2, out="split")
+    assert torch.equal(both_sp.hi, only_sp.hi) and torch.equal(both_sp.lo, only_sp.lo)
+    assert (_join(only_sp).permute(0, 3, 1, 2) - f32).abs().max().item() < 5e-5 * f32.abs().max().item() + 1e-6
+    chained = ops.conv3x3([only_sp], torch.nn.Parameter(torch.randn(8, 128, 3, 3, generator=g).to(cuda) / 34.0))
+    ref = ops.conv3x3([f32], torch.nn.Parameter(torch.randn(8, 128, 3, 3, generator=torch.Generator().manual_seed(63)).to(cuda)))
+    assert chained.shape == ref.shape == (1, 8, 12, 20)
