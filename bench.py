@@ -24,6 +24,13 @@ import torch  # noqa: E402
 
 H, W, T, L_T = 240, 432, 8, 5
 METRIC = "frames/sec InpaintGenerator.forward 432x240x(5+3)"
+# other BASELINE.json configs, selectable with --workload (the default "base" is the headline one):
+#   name -> (model module, H, W (mirror-padded to multiples of 60 / 108 like test.py:156-165), T, l_t, clips per GPU)
+WORKLOADS = {
+    "base": ("model.e2fgvi", 240, 432, 8, 5, 8),
+    "hq720": ("model.e2fgvi_hq", 720, 1296, 8, 5, 1),       # configs[2]: 720x1280, 5+3
+    "hq1080": ("model.e2fgvi_hq", 1080, 1944, 16, 10, 1),   # configs[4]: 1080x1920, 10+6, one clip per GPU
+}
 
 
 def log(msg):
@@ -92,8 +99,8 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def make_model(device):
-    net = importlib.import_module("model.e2fgvi")
+def make_model(device, module="model.e2fgvi"):
+    net = importlib.import_module(module)
     from e2fgvi_b200.synth import synth_state_dict
     model = net.InpaintGenerator().eval()
     sd = synth_state_dict(model, "default", 0)          # the reference's own init family (BASELINE config)
@@ -146,12 +153,19 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--clips-per-gpu", type=int, default=8)
+    ap.add_argument("--clips-per-gpu", type=int, default=None)
+    ap.add_argument("--workload", default="base", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--precision", default="strict", choices=["strict", "tf32"],
                     help="library conv/linear precision: strict = fp32 (TF32 off), tf32 = PyTorch GPU defaults")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
+    global H, W, T, L_T, METRIC
+    module, H, W, T, L_T, default_b = WORKLOADS[args.workload]
+    if args.clips_per_gpu is None:
+        args.clips_per_gpu = default_b
+    if args.workload != "base":
+        METRIC = f"frames/sec InpaintGenerator.forward {W}x{H}x({L_T}+{T - L_T}) [{args.workload}]"
 
     from e2fgvi_b200 import clips as C
     if args.impl == "reference":
@@ -166,7 +180,7 @@ def main():
     from e2fgvi_b200 import ops
     from e2fgvi_b200.synth import synth_frames
     _build.build()
-    model, sd = make_model(dev)
+    model, sd = make_model(dev, module)
     model.precision = args.precision
     log(f"rank {rank}/{world}: model ready, precision={args.precision}, host cores={host_cores()}")
     B = args.clips_per_gpu
@@ -227,6 +241,7 @@ def main():
         log(f"e2e: {ms_e2e / args.steps:.2f} ms/step")
         # single-clip latency (BASELINE configs[1] shape, b=1)
         one = dev_sets[0][:1]
+        n_sets_b1 = 1
         for _ in range(3):
             model(one, L_T)
         sync()
@@ -286,7 +301,7 @@ def main():
                         peak_source=f"{src} " + ("bf16_tflops_sustained" if kernels[dom]["bound"] == "tensor" else "hbm_gbs"),
                         note="achieved = algorithmic work (SURVEY 8d) / live CUDA-event launch time inside the timed region")
         cpu = None
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and args.workload == "base":
             log("timing the CPU oracle (1 warm-up + 2 clips) ...")
             fps, s_per, cores = cpu_oracle_fps(sd, steps=2, warmup=1)
             log(f"CPU oracle: {s_per:.2f} s/clip on {cores} threads")
@@ -299,8 +314,10 @@ def main():
             "dtype": "f16 operands / f32 accumulate (DCN, attention kernels); library convs/linears "
                      + ("f32" if args.precision == "strict" else "tf32"),
             "data": "synthetic",
-            "config": {"workload": f"e2fgvi 432x240, 5 local + 3 ref frames, {B} clips per GPU per step "
-                                   "(BASELINE configs[3] per-GPU share)",
+            "config": {"workload": (f"e2fgvi 432x240, 5 local + 3 ref frames, {B} clips per GPU per step "
+                                    "(BASELINE configs[3] per-GPU share)") if args.workload == "base" else
+                                   f"{module.split('.')[-1]} {W}x{H} (mirror-padded), {L_T} local + {T - L_T} ref frames, "
+                                   f"{B} clip(s) per GPU per step",
                        "global_batch_clips": num_clips, "frames_per_clip": T, "parallelism": f"clip-dp{world}",
                        "l2": f"inputs rotate over {n_sets} sets x {B * T * 3 * H * W * 4 / 1e6:.0f} MB (> 126 MB L2)",
                        "precision": args.precision,
