@@ -12,14 +12,18 @@
 //   Keys are ordered [multiplicity-1 ring keys | pooled keys | multiplicity>=2 ring keys | padding], so only the
 //   last key tile(s) carry a non-zero logit bias and every other tile takes a bias-free fast path.
 //
-// One CTA = one (128-query tile, head, window).  Warp roles (416 threads):
-//   warps 0-7   softmax: two warps per SM sub-partition; thread (q, lane, hh) owns HALF of query row q*32+lane
-//               (64 of the 128 keys of a tile): S -> registers, row max exchanged through smem, online softmax with
-//               lazy rescale, P -> fp16 128B-swizzled smem, final O / l -> global (un-partitioned layout).
-//               (r01 v1 had one softmax warp per sub-partition and was issue-bound: tensor pipe 16 %.)
-//   warps 8-11  loaders: per-key source addresses (wrap / pooled / padding) then coalesced 16-byte cp.async gathers
-//               of K and V rows (256 B each) into swizzled smem, 2-stage ring
-//   warp  12    tcgen05 issuer: S = Q K^T (K-major operands), O += P V (V as MN-major B operand), fp32 in TMEM
+// One CTA = one (128-query tile, head, window), TWO CTAs co-resident per SM (98 KB smem, 256 TMEM columns each) so
+// one CTA's hand-off bubbles (barrier round trips, gather latency, prologue / epilogue) are filled by the other —
+// the r01 ablation showed those bubbles were > 50 % of the v1-v3 kernels at one CTA per SM.
+// Warp roles (288 threads):
+//   warps 0-3  softmax: thread r owns query row r (= TMEM lane r): S (64 keys) -> registers, online softmax with lazy
+//              rescale, P packed to fp16 and written BACK INTO THE S TILE'S TMEM COLUMNS (tcgen05.st) — no P tile in
+//              shared memory, no stores / proxy fences on this path; final O / l -> global (un-partitioned layout)
+//   warps 4-7  loaders: per-key source addresses (wrap / pooled / padding) then coalesced 16-byte cp.async gathers of
+//              K and V rows (256 B each) into swizzled smem, 2-stage ring of 64-key tiles
+//   warp  8    tcgen05 issuer: S = Q K^T (A, B K-major in smem), O += P V with P as the A operand FROM TENSOR MEMORY
+//              and V as an MN-major B operand; issue order S0 S1 PV0 S2 PV1 S3 ... so S(kt+2) may overwrite the
+//              buffer that held P(kt) without any extra barrier (the tensor pipe executes in order)
 // Roofline: 4*B*nW*heads*(T*wh*ww)*(T*(wh*ww+ring+fh*fw))*128 FLOP on the tensor pipe.
 #include <cstdlib>
 #include "common.cuh"
@@ -29,30 +33,33 @@ namespace e2f {
 namespace attn {
 
 constexpr int HD = 128;                    // head dim
-constexpr int BM = 128, BN = 128;          // query tile, key tile
-constexpr int ATOM = 16384;                // one [128 rows][64 halfs] swizzled sub-tile
-constexpr int TILE = 2 * ATOM;             // [128][128] fp16
+constexpr int BM = 128, BN = 64;           // query tile, key tile
+constexpr int QATOM = BM * 128;            // [128 rows][64 halfs] swizzled sub-tile of Q
+constexpr int KATOM = BN * 128;            // [64 keys][64 halfs] swizzled sub-tile of K / V
+constexpr int QTILE = 2 * QATOM;           // 32 KB
+constexpr int KTILE = 2 * KATOM;           // 16 KB
 constexpr int KV_STAGES = 2;
-constexpr int SOFTMAX_WARPS = 8, LOADER_WARPS = 4;
+constexpr int SOFTMAX_WARPS = 4, LOADER_WARPS = 4;
 constexpr int SOFTMAX_THREADS = SOFTMAX_WARPS * 32;
 constexpr int MMA_WARP = SOFTMAX_WARPS + LOADER_WARPS;
-constexpr int THREADS = (MMA_WARP + 1) * 32;   // 416
-constexpr int TMEM_COLS = 512;                 // S0 [0,128) S1 [128,256) O [256,384)
-constexpr uint32_t COL_S = 0, COL_O = 256;
+constexpr int THREADS = (MMA_WARP + 1) * 32;   // 288
+constexpr int CTAS_PER_SM = 2;
+constexpr int TMEM_COLS = 256;                 // S0/P0 [0,64) S1/P1 [64,128) O [128,256)
+constexpr uint32_t COL_S = 0, COL_O = 128;
 constexpr float LOG2E = 1.4426950408889634f;
 constexpr float RESCALE_THRESHOLD = 8.0f;      // log2 domain: P stays <= 2^8
 constexpr int MAX_RING = 256;                  // expanded-window positions (153 for the 5x9 window)
+constexpr int MAX_FRAME_KEYS = 384;            // ring + pooled keys of one frame (198 for 5x9 / 5x9)
 
 struct Smem {
   static constexpr int Q = 0;
-  static constexpr int K = Q + TILE;
-  static constexpr int V = K + KV_STAGES * TILE;
-  static constexpr int P = V + KV_STAGES * TILE;
-  static constexpr int KEYPTR = P + TILE;                       // [stages][128] uint64
-  static constexpr int BIAS = KEYPTR + KV_STAGES * BN * 8;      // [stages][128] float
-  static constexpr int XCHG = BIAS + KV_STAGES * BN * 4;        // [2 parity][2 halves][128 rows] float (row max)
-  static constexpr int XSUM = XCHG + 2 * 2 * BM * 4;            // [2 halves][128 rows] float (row sum)
-  static constexpr int BARS = XSUM + 2 * BM * 4;
+  static constexpr int K = Q + QTILE;
+  static constexpr int V = K + KV_STAGES * KTILE;
+  static constexpr int KEYPTR = V + KV_STAGES * KTILE;          // [128] uint64 (Q rows at start, then [stages][64])
+  static constexpr int BIAS = KEYPTR + BM * 8;                  // [stages][64] float
+  static constexpr int FTAB = BIAS + KV_STAGES * BN * 4;        // [MAX_FRAME_KEYS] int32: key offset inside its frame
+  static constexpr int FBIAS = FTAB + MAX_FRAME_KEYS * 4;       // [MAX_FRAME_KEYS] float: logit bias (log2 multiplicity)
+  static constexpr int BARS = FBIAS + MAX_FRAME_KEYS * 4;
   static constexpr int NUM_BARS = 1 + 3 * KV_STAGES + 2 + 2 + 2;
   static constexpr int TMEM_SLOT = BARS + NUM_BARS * 8;
   static constexpr int BYTES = TMEM_SLOT + 16;
@@ -69,6 +76,7 @@ struct Params {
   int use_pooled;
   float scale_log2;               // scale * log2(e)
   int debug;                      // perf-experiment bits (E2F_ATTN_DEBUG): 1 skip softmax math, 2 skip gathers, 4 skip MMAs
+  long long* trace;               // optional [3 roles][64 events] clock64 stamps of CTA (0,0,0) (E2F_ATTN_TRACE)
   int n1, n2;                     // expanded-window positions listed once / more than once by the reference
   uint8_t ring_pos[MAX_RING];     // positions (er*EW + ec): the n1 single ones first, then the n2 multiple ones
   uint8_t ring_mult[MAX_RING];    // multiplicity of each entry
@@ -100,41 +108,99 @@ __host__ __device__ inline int key_multiplicity(int er, int ec, int wh, int ww, 
 __device__ __forceinline__ void loader_barrier() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 __device__ __forceinline__ void softmax_barrier() { asm volatile("bar.sync 2, 256;" ::: "memory"); }
 
-// coalesced gather of 128 rows x 256 B (two 64-half atoms) into a swizzled tile; 16 lanes cover one row.
+// coalesced gather of ROWS rows x 256 B (two 64-half atoms of ROWS*128 B) into a swizzled tile; 16 lanes cover one
+// row, the 4 loader warps split the rows.
+template <int ROWS>
 __device__ __forceinline__ void gather_rows(uint32_t tile_smem, const uint64_t* row_ptr, int lwarp, int lane,
                                             int half_offset) {
   const int chunk = lane & 15;
-  const uint32_t atom_off = (chunk >> 3) * ATOM;
+  const uint32_t atom_off = (chunk >> 3) * (ROWS * 128);
 #pragma unroll 4
-  for (int it = 0; it < 16; ++it) {
-    const int row = lwarp * 32 + it * 2 + (lane >> 4);
-    const uint64_t p = row_ptr[row];
+  for (int it = 0; it < ROWS / 8; ++it) {
+    const int row = lwarp * (ROWS / 4) + it * 2 + (lane >> 4);
+    uint64_t p;
+    asm volatile("ld.shared.u64 %0, [%1];" : "=l"(p) : "r"(smem_u32(row_ptr + row)));
     const uint32_t dst = tile_smem + atom_off + sw128_offset(row, chunk & 7);
     const __half* src = reinterpret_cast<const __half*>(p) + half_offset + chunk * 8;
     cp_async16_zfill(dst, p ? static_cast<const void*>(src) : static_cast<const void*>(row_ptr), p ? 16u : 0u);
   }
 }
 
+// One 32-logit chunk of a query row: p = exp2(s * scale [+ bias] - m) as 16 packed fp16 pairs + 4 partial row sums.
+// MODE is a compile-time constant so the 32 exps form one branch-free block the scheduler can pipeline
+// (a per-element mode test serialised every 4-element group on the MUFU latency: 3.3k cycles per 64 keys, r01 trace).
+enum { MODE_FAST = 0, MODE_BIASED = 1, MODE_NOEXP = 2 };
+template <int MODE>
+__device__ __forceinline__ void softmax_chunk(const uint32_t (&sv)[32], const float4* __restrict__ bias4, float sc,
+                                              float neg_m, uint32_t (&pk)[16], float& l0, float& l1, float& l2,
+                                              float& l3) {
+  float p[32];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    float a0 = __uint_as_float(sv[4 * i]), a1 = __uint_as_float(sv[4 * i + 1]);
+    float a2 = __uint_as_float(sv[4 * i + 2]), a3 = __uint_as_float(sv[4 * i + 3]);
+    if (MODE == MODE_BIASED) {
+      const float4 bb = bias4[i];
+      a0 = fmaf(a0, sc, bb.x) + neg_m; a1 = fmaf(a1, sc, bb.y) + neg_m;
+      a2 = fmaf(a2, sc, bb.z) + neg_m; a3 = fmaf(a3, sc, bb.w) + neg_m;
+    } else if (MODE == MODE_FAST) {
+      a0 = fmaf(a0, sc, neg_m); a1 = fmaf(a1, sc, neg_m); a2 = fmaf(a2, sc, neg_m); a3 = fmaf(a3, sc, neg_m);
+    }
+    if (MODE == MODE_NOEXP) {
+      p[4 * i] = a0 * 1e-3f; p[4 * i + 1] = a1 * 1e-3f; p[4 * i + 2] = a2 * 1e-3f; p[4 * i + 3] = a3 * 1e-3f;
+    } else {
+      p[4 * i] = fast_exp2(a0); p[4 * i + 1] = fast_exp2(a1); p[4 * i + 2] = fast_exp2(a2); p[4 * i + 3] = fast_exp2(a3);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    l0 += p[4 * i]; l1 += p[4 * i + 1]; l2 += p[4 * i + 2]; l3 += p[4 * i + 3];
+    pk[2 * i] = pack_half2(p[4 * i], p[4 * i + 1]);
+    pk[2 * i + 1] = pack_half2(p[4 * i + 2], p[4 * i + 3]);
+  }
+}
+
+template <int MODE>
+__device__ __forceinline__ float max_chunk(const uint32_t (&sv)[32], const float4* __restrict__ bias4, float sc) {
+  float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;   // 4 independent chains
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    float a0 = __uint_as_float(sv[4 * i]), a1 = __uint_as_float(sv[4 * i + 1]);
+    float a2 = __uint_as_float(sv[4 * i + 2]), a3 = __uint_as_float(sv[4 * i + 3]);
+    if (MODE == MODE_BIASED) {
+      const float4 bb = bias4[i];
+      a0 = fmaf(a0, sc, bb.x); a1 = fmaf(a1, sc, bb.y); a2 = fmaf(a2, sc, bb.z); a3 = fmaf(a3, sc, bb.w);
+    }
+    m0 = fmaxf(m0, a0); m1 = fmaxf(m1, a1); m2 = fmaxf(m2, a2); m3 = fmaxf(m3, a3);
+  }
+  const float m = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+  return MODE == MODE_BIASED ? m : m * sc;      // scale > 0: max commutes with the scaling
+}
+
 template <typename OutT>
-__global__ void __launch_bounds__(THREADS, 1) focal_attn_kernel(const __grid_constant__ Params prm) {
+__global__ void __launch_bounds__(THREADS, CTAS_PER_SM) focal_attn_kernel(const __grid_constant__ Params prm) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* key_ptr = reinterpret_cast<uint64_t*>(smem + Smem::KEYPTR);
   float* key_bias = reinterpret_cast<float*>(smem + Smem::BIAS);
-  float* xchg = reinterpret_cast<float*>(smem + Smem::XCHG);
-  float* xsum = reinterpret_cast<float*>(smem + Smem::XSUM);
+  int* ftab = reinterpret_cast<int*>(smem + Smem::FTAB);
+  float* fbias = reinterpret_cast<float*>(smem + Smem::FBIAS);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Smem::BARS);
   uint64_t* q_full = bars;
   uint64_t* k_full = bars + 1;
   uint64_t* v_full = k_full + KV_STAGES;
   uint64_t* kv_empty = v_full + KV_STAGES;
-  uint64_t* s_full = kv_empty + KV_STAGES;      // [2]
-  uint64_t* s_free = s_full + 2;                // [2]
-  uint64_t* p_full = s_free + 2;
-  uint64_t* o_done = p_full + 1;
+  uint64_t* s_full = kv_empty + KV_STAGES;      // [2] S tile written by the MMA
+  uint64_t* p_full = s_full + 2;                // [2] P written into the S tile's columns by the softmax warps
+  uint64_t* pv_done = p_full + 2;               // [2] PV MMA of that buffer complete (O updated, buffer reusable)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + Smem::TMEM_SLOT);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool tracing = prm.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+  int tr_n = 0;
+  auto stamp = [&](int role) {     // role 0 softmax (warp 0 lane 0), 1 loader (warp 4 lane 0), 2 MMA thread
+    if (tracing && tr_n < 64) prm.trace[role * 64 + tr_n++] = clock64();
+  };
 
   // ---- problem geometry (uniform per CTA)
   const int area = prm.wh * prm.ww;
@@ -170,10 +236,9 @@ __global__ void __launch_bounds__(THREADS, 1) focal_attn_kernel(const __grid_con
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&s_full[s], 1);
-      mbar_init(&s_free[s], SOFTMAX_WARPS);
+      mbar_init(&p_full[s], SOFTMAX_WARPS);
+      mbar_init(&pv_done[s], 1);
     }
-    mbar_init(p_full, SOFTMAX_WARPS);
-    mbar_init(o_done, 1);
     fence_barrier_init();
   }
   tc_fence_before_sync();
@@ -183,66 +248,38 @@ __global__ void __launch_bounds__(THREADS, 1) focal_attn_kernel(const __grid_con
 
   if (warp < SOFTMAX_WARPS) {
     // =================================================================== softmax + epilogue
-    const int q = warp & 3, hh = warp >> 2;             // TMEM lane quarter, key/column half
-    const int r = q * 32 + lane;                        // query row in the tile == TMEM lane
-    const uint32_t lane_addr = tbase + (static_cast<uint32_t>(q * 32) << 16);
+    const int r = tid;                                  // query row in the tile == TMEM lane
+    const uint32_t lane_addr = tbase + (static_cast<uint32_t>(warp * 32) << 16);
     float m_used = n_masked > 0 ? -100.0f * LOG2E : -INFINITY;
-    float l = (hh == 0) ? static_cast<float>(n_masked) : 0.f;     // partial row sum of this thread's columns
-    uint8_t* sP = smem + Smem::P + hh * ATOM;
+    float l = static_cast<float>(n_masked);
     const float sc = prm.scale_log2;
 
     for (int kt = 0; kt < num_kt; ++kt) {
       const int sb = kt & 1, stage = kt % KV_STAGES;
       const bool biased = kt >= bias_kt;                // uniform over the CTA
       if (biased) mbar_wait(&k_full[stage], (kt / KV_STAGES) & 1);   // acquire the loaders' bias writes
+      if (tid == 0 && kt < 10) stamp(0);                 // [6kt+0] start of tile
       mbar_wait(&s_full[sb], (kt >> 1) & 1);
+      if (tid == 0 && kt < 10) stamp(0);                 // [6kt+1] S ready
       tc_fence_after_sync();
-      uint32_t sv[2][32];
-      tmem_ld32(lane_addr + COL_S + sb * BN + hh * 64, sv[0]);
-      tmem_ld32(lane_addr + COL_S + sb * BN + hh * 64 + 32, sv[1]);
-      tmem_ld_wait();
-      tc_fence_before_sync();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&s_free[sb]);
-
+      // Two passes over the S tile in 32-column chunks (TMEM re-reads are cheap; holding all 64 logits plus the 32
+      // packed outputs in registers does not fit the 96-register budget of 2 CTAs/SM and went to local memory).
+      const uint32_t s_addr = lane_addr + COL_S + sb * BN;
+      const float4* bias4 = reinterpret_cast<const float4*>(key_bias + stage * BN);
       float mx = -INFINITY;
       if (prm.debug & 1) {
         mx = 0.f;
-      } else if (biased) {
-        const float4* bias4 = reinterpret_cast<const float4*>(key_bias + stage * BN + hh * 64);
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float4 bb = bias4[c * 8 + i];
-            const float s0 = fmaf(__uint_as_float(sv[c][4 * i + 0]), sc, bb.x);
-            const float s1 = fmaf(__uint_as_float(sv[c][4 * i + 1]), sc, bb.y);
-            const float s2 = fmaf(__uint_as_float(sv[c][4 * i + 2]), sc, bb.z);
-            const float s3 = fmaf(__uint_as_float(sv[c][4 * i + 3]), sc, bb.w);
-            sv[c][4 * i + 0] = __float_as_uint(s0);
-            sv[c][4 * i + 1] = __float_as_uint(s1);
-            sv[c][4 * i + 2] = __float_as_uint(s2);
-            sv[c][4 * i + 3] = __float_as_uint(s3);
-            mx = fmaxf(mx, fmaxf(fmaxf(s0, s1), fmaxf(s2, s3)));
-          }
-        }
       } else {
-#pragma unroll
+#pragma unroll 1
         for (int c = 0; c < 2; ++c) {
-#pragma unroll
-          for (int i = 0; i < 32; i += 4)
-            mx = fmaxf(mx, fmaxf(fmaxf(__uint_as_float(sv[c][i]), __uint_as_float(sv[c][i + 1])),
-                                 fmaxf(__uint_as_float(sv[c][i + 2]), __uint_as_float(sv[c][i + 3]))));
+          uint32_t sv[32];
+          tmem_ld32(s_addr + c * 32, sv);
+          tmem_ld_wait();
+          mx = fmaxf(mx, biased ? max_chunk<MODE_BIASED>(sv, bias4 + c * 8, sc) : max_chunk<MODE_FAST>(sv, bias4, sc));
         }
-        mx *= sc;                                       // scale > 0: max commutes with the scaling
       }
-      // full-row max: exchange the two half-row maxima through smem (buffer alternates with the tile parity)
-      float* xm = xchg + (kt & 1) * (2 * BM);
-      xm[hh * BM + r] = mx;
-      softmax_barrier();
-      mx = fmaxf(mx, xm[(hh ^ 1) * BM + r]);
-
-      // lazy rescale: only move the reference max when it grew by more than 2^8 (both half-row threads agree)
+      if (tid == 0 && kt < 10 && (prm.debug & 8)) stamp(0);   // (fine trace) max done
+      // lazy rescale: only move the reference max when it grew by more than 2^8
       float alpha = 1.0f;
       bool need = false;
       if (m_used == -INFINITY) {
@@ -252,70 +289,67 @@ __global__ void __launch_bounds__(THREADS, 1) focal_attn_kernel(const __grid_con
         m_used = mx;
         need = true;
       }
-      if (kt > 0) {                        // PV(kt-1) must be complete before P is overwritten / O is rescaled
-        mbar_wait(o_done, (kt - 1) & 1);
-        tc_fence_after_sync();
-      }
-      if (__any_sync(0xffffffffu, need)) {
+      const bool any_need = __any_sync(0xffffffffu, need);
+      if (tid == 0 && kt < 10 && (prm.debug & 8)) stamp(0);   // (fine trace) rescale decided
+      if (any_need) {
         l *= alpha;
-        if (kt > 0) {
+        if (kt > 0) {                      // O holds PV(0..kt-1): wait for PV(kt-1), then scale the row in TMEM
+          mbar_wait(&pv_done[(kt - 1) & 1], ((kt - 1) >> 1) & 1);
+          tc_fence_after_sync();
 #pragma unroll 1
-          for (int c = 0; c < 2; ++c) {
+          for (int c = 0; c < 4; ++c) {
             uint32_t ov[32];
-            tmem_ld32(lane_addr + COL_O + hh * 64 + c * 32, ov);
+            tmem_ld32(lane_addr + COL_O + c * 32, ov);
             tmem_ld_wait();
 #pragma unroll
             for (int i = 0; i < 32; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * alpha);
-            tmem_st32(lane_addr + COL_O + hh * 64 + c * 32, ov);
+            tmem_st32(lane_addr + COL_O + c * 32, ov);
           }
           tmem_st_wait();
         }
       }
-      float lsum = 0.f;
+      // P = exp2(s - m) as packed fp16 pairs, written over the first 32 columns of the S tile just consumed: chunk c
+      // (logit columns [32c, 32c+32)) becomes packed columns [16c, 16c+16).  Chunk 1's logits are still intact when
+      // chunk 0's P lands in columns [0,16).  S(kt) complete => PV(kt-2), the previous reader of this buffer, is too.
+      float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
       const float neg_m = -m_used;
-#pragma unroll
+#pragma unroll 1
       for (int c = 0; c < 2; ++c) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {       // 8 probabilities -> one 16-byte chunk of the P row
-          float p[8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const float sval = __uint_as_float(sv[c][8 * i + e]);
-            if (prm.debug & 1) p[e] = sval * 1e-3f;
-            else p[e] = biased ? fast_exp2(sval + neg_m) : fast_exp2(fmaf(sval, sc, neg_m));
-            lsum += p[e];
-          }
-          uint4 u;
-          u.x = pack_half2(p[0], p[1]); u.y = pack_half2(p[2], p[3]);
-          u.z = pack_half2(p[4], p[5]); u.w = pack_half2(p[6], p[7]);
-          *reinterpret_cast<uint4*>(sP + sw128_offset(r, c * 4 + i)) = u;
-        }
+        uint32_t sv[32];
+        tmem_ld32(s_addr + c * 32, sv);
+        tmem_ld_wait();
+        uint32_t pk[16];
+        if (prm.debug & 1) softmax_chunk<MODE_NOEXP>(sv, bias4, sc, neg_m, pk, l0, l1, l2, l3);
+        else if (biased) softmax_chunk<MODE_BIASED>(sv, bias4 + c * 8, sc, neg_m, pk, l0, l1, l2, l3);
+        else softmax_chunk<MODE_FAST>(sv, bias4, sc, neg_m, pk, l0, l1, l2, l3);
+        tmem_st16(s_addr + c * 16, pk);
       }
-      l += lsum;
-      fence_proxy_async_smem();
+      l += (l0 + l1) + (l2 + l3);
+      if (tid == 0 && kt < 10) stamp(0);                 // math done
+      tmem_st_wait();
+      if (tid == 0 && kt < 10) stamp(0);                 // P stored
       tc_fence_before_sync();
       __syncwarp();
-      if (lane == 0) mbar_arrive(p_full);
+      if (lane == 0) mbar_arrive(&p_full[sb]);
+      if (tid == 0 && kt < 10) stamp(0);                 // [6kt+5] arrived
     }
 
-    // ---- epilogue: O / l -> out[b, t, y, x, head*128 + hh*64 ..]
-    xsum[hh * BM + r] = l;
-    softmax_barrier();
-    const float inv_l = 1.0f / (l + xsum[(hh ^ 1) * BM + r]);
-    mbar_wait(o_done, (num_kt - 1) & 1);
+    // ---- epilogue: O / l -> out[b, t, y, x, head*128 ..]
+    mbar_wait(&pv_done[(num_kt - 1) & 1], ((num_kt - 1) >> 1) & 1);
     tc_fence_after_sync();
     const int qi = qt * BM + r;
+    const float inv_l = 1.0f / l;
     OutT* dst = nullptr;
     if (qi < nq) {
       const int t = qi / area, p = qi - t * area;
       const int y = wi * prm.wh + p / prm.ww, x = wj * prm.ww + p % prm.ww;
       const size_t tok = ((static_cast<size_t>(b) * prm.T + t) * prm.H + y) * prm.W + x;
-      dst = static_cast<OutT*>(prm.out) + tok * prm.C + head * HD + hh * 64;
+      dst = static_cast<OutT*>(prm.out) + tok * prm.C + head * HD;
     }
 #pragma unroll 1
-    for (int c = 0; c < 2; ++c) {
+    for (int c = 0; c < 4; ++c) {
       uint32_t ov[32];
-      tmem_ld32(lane_addr + COL_O + hh * 64 + c * 32, ov);
+      tmem_ld32(lane_addr + COL_O + c * 32, ov);
       tmem_ld_wait();
       if (dst) {
         if constexpr (sizeof(OutT) == 4) {
@@ -342,7 +376,7 @@ __global__ void __launch_bounds__(THREADS, 1) focal_attn_kernel(const __grid_con
     // =================================================================== loaders
     const int lt = tid - SOFTMAX_THREADS;               // 0..127
     const int lwarp = lt >> 5;
-    // Q tile: row lt's source address (key_ptr stage 0 is borrowed as scratch before the first K tile)
+    // Q tile: row lt's source address (key_ptr is borrowed as scratch before the first K tile)
     {
       const int qi = qt * BM + lt;
       uint64_t p = 0;
@@ -354,7 +388,7 @@ __global__ void __launch_bounds__(THREADS, 1) focal_attn_kernel(const __grid_con
       }
       key_ptr[lt] = p;
       loader_barrier();
-      gather_rows(smem_u32(smem + Smem::Q), key_ptr, lwarp, lane, 0);
+      gather_rows<BM>(smem_u32(smem + Smem::Q), key_ptr, lwarp, lane, 0);
       cp_async_commit();
       cp_async_wait<0>();
       fence_proxy_async_smem();
@@ -362,92 +396,135 @@ __global__ void __launch_bounds__(THREADS, 1) focal_attn_kernel(const __grid_con
       if (lane == 0) mbar_arrive(q_full);
       loader_barrier();                                 // everyone done reading key_ptr[0..127]
     }
-    for (int kt = 0; kt < num_kt; ++kt) {
-      const int stage = kt % KV_STAGES;
-      mbar_wait(&kv_empty[stage], ((kt / KV_STAGES) & 1) ^ 1);
-      // ---- one key per thread: where does key (kt*128 + lt) live, and what is its logit bias
-      const int idx = kt * BN + lt;
-      uint64_t p = 0;
-      float bias = -INFINITY;
-      if (idx < nB && idx >= nA) {                       // pooled window key
-        const int j = idx - nA;
-        const int t = j / npool, pp = j - t * npool;
-        const int pi = pi0 + pp / PW, pj = pj0 + pp % PW;
-        const size_t tok = ((static_cast<size_t>(b) * prm.T + t) * prm.nWh + pi) * prm.nWw + pj;
-        p = reinterpret_cast<uint64_t>(prm.pooled + tok * C3 + prm.C + head * HD);
-        bias = 0.f;
-      } else if (idx < NK) {                             // ring key (single-listed first, multiply-listed last)
-        int t, e;
-        if (idx < nA) {
-          t = idx / prm.n1;
-          e = idx - t * prm.n1;
-        } else {
-          const int j = idx - nB;
-          t = j / prm.n2;
-          e = prm.n1 + (j - t * prm.n2);
-        }
-        const int pos = prm.ring_pos[e], mult = prm.ring_mult[e];
+    // ---- per-frame key table, built once per CTA: entry e -> offset (in halfs) of that key's token inside its frame
+    //      and its logit bias; entries ordered [n1 single ring | npool pooled | n2 multiple ring]
+    const int nf = prm.n1 + npool + prm.n2;
+    for (int e = lt; e < nf; e += LOADER_WARPS * 32) {
+      int off;
+      float bias = 0.f;
+      if (e >= prm.n1 && e < prm.n1 + npool) {
+        const int pp = e - prm.n1;
+        off = ((pi0 + pp / PW) * prm.nWw + (pj0 + pp % PW)) * static_cast<int>(C3);
+      } else {
+        const int slot = (e < prm.n1) ? e : e - npool;
+        const int pos = prm.ring_pos[slot], mult = prm.ring_mult[slot];
         const int er = pos / EW, ec = pos - er * EW;
         int y = (wi * prm.wh - prm.eh + er) % prm.H;
         int x = (wj * prm.ww - prm.ew + ec) % prm.W;
         y += (y < 0) ? prm.H : 0;
         x += (x < 0) ? prm.W : 0;
-        const size_t tok = ((static_cast<size_t>(b) * prm.T + t) * prm.H + y) * prm.W + x;
-        p = reinterpret_cast<uint64_t>(prm.qkv + tok * C3 + prm.C + head * HD);
+        off = (y * prm.W + x) * static_cast<int>(C3);
         bias = (mult == 1) ? 0.f : log2f(static_cast<float>(mult));
       }
-      key_ptr[stage * BN + lt] = p;
-      key_bias[stage * BN + lt] = bias;
+      ftab[e] = off;
+      fbias[e] = bias;
+    }
+    loader_barrier();
+    const size_t ring_frame = static_cast<size_t>(prm.H) * prm.W * C3;
+    const size_t pool_frame = static_cast<size_t>(prm.nWh) * prm.nWw * C3;
+    const __half* ring_base = prm.qkv + static_cast<size_t>(b) * prm.T * ring_frame + prm.C + head * HD;
+    const __half* pool_base = prm.pooled + static_cast<size_t>(b) * prm.T * pool_frame + prm.C + head * HD;
+    for (int kt = 0; kt < num_kt; ++kt) {
+      const int stage = kt % KV_STAGES;
+      // ---- threads 0..63: address and logit bias of key (kt*64 + lt): (frame, entry) -> table lookup; computed
+      //      BEFORE waiting for the stage to drain, so it is off the critical path
+      uint64_t p = 0;
+      float bias = -INFINITY;
+      if (lt < BN) {
+        const int idx = kt * BN + lt;
+        if (idx < nA) {
+          const int t = idx / prm.n1, e = idx - t * prm.n1;
+          p = reinterpret_cast<uint64_t>(ring_base + t * ring_frame + ftab[e]);
+          bias = 0.f;
+        } else if (idx < nB) {
+          const int j = idx - nA;
+          const int t = j / npool, e = prm.n1 + (j - t * npool);
+          p = reinterpret_cast<uint64_t>(pool_base + t * pool_frame + ftab[e]);
+          bias = 0.f;
+        } else if (idx < NK) {
+          const int j = idx - nB;
+          const int t = j / prm.n2, e = prm.n1 + npool + (j - t * prm.n2);
+          p = reinterpret_cast<uint64_t>(ring_base + t * ring_frame + ftab[e]);
+          bias = fbias[e];
+        }
+      }
+      if (lt == 0 && kt < 12) stamp(1);                  // [5kt+0] index math done
+      mbar_wait(&kv_empty[stage], ((kt / KV_STAGES) & 1) ^ 1);
+      if (lt == 0 && kt < 12) stamp(1);                  // [5kt+1] stage free
+      if (lt < BN) {
+        key_ptr[stage * BN + lt] = p;
+        key_bias[stage * BN + lt] = bias;
+      }
       loader_barrier();
       if (!(prm.debug & 2) || kt < KV_STAGES) {
-        gather_rows(smem_u32(smem + Smem::K + stage * TILE), key_ptr + stage * BN, lwarp, lane, 0);
+        gather_rows<BN>(smem_u32(smem + Smem::K + stage * KTILE), key_ptr + stage * BN, lwarp, lane, 0);
         cp_async_commit();
-        gather_rows(smem_u32(smem + Smem::V + stage * TILE), key_ptr + stage * BN, lwarp, lane, prm.C);
+        gather_rows<BN>(smem_u32(smem + Smem::V + stage * KTILE), key_ptr + stage * BN, lwarp, lane, prm.C);
         cp_async_commit();
       }
+      if (lt == 0 && kt < 12) stamp(1);                  // [5kt+2] gathers issued
       cp_async_wait<1>();                               // K landed
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(&k_full[stage]);
+      if (lt == 0 && kt < 12) stamp(1);                  // [5kt+3] K landed + arrived
       cp_async_wait<0>();                               // V landed
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(&v_full[stage]);
+      if (lt == 0 && kt < 12) stamp(1);                  // [5kt+4] V landed + arrived
     }
   } else {
     // =================================================================== tcgen05 issuer
     if (lane == 0) {
       const uint32_t idesc_s = umma_idesc_f16(BM, BN, 0, 0);   // S = Q K^T, both K-major (d contiguous)
-      const uint32_t idesc_o = umma_idesc_f16(BM, HD, 0, 1);   // O = P V, V is MN-major (d contiguous per key)
+      const uint32_t idesc_o = umma_idesc_f16(BM, HD, 0, 1);   // O = P V: P from TMEM, V MN-major (d contiguous per key)
       const uint32_t sQ = smem_u32(smem + Smem::Q), sK = smem_u32(smem + Smem::K);
-      const uint32_t sV = smem_u32(smem + Smem::V), sPa = smem_u32(smem + Smem::P);
+      const uint32_t sV = smem_u32(smem + Smem::V);
+      const bool run_mma = !(prm.debug & 4);
       auto issue_s = [&](int kt) {
         const int stage = kt % KV_STAGES, sb = kt & 1;
         mbar_wait(&k_full[stage], (kt / KV_STAGES) & 1);
-        mbar_wait(&s_free[sb], ((kt >> 1) & 1) ^ 1);
         tc_fence_after_sync();
-        const uint32_t kb = sK + stage * TILE;
+        const uint32_t kb = sK + stage * KTILE;
 #pragma unroll
         for (int k = 0; k < HD / 16; ++k)
-          if (!(prm.debug & 4) || kt < 2) umma_f16(tbase + COL_S + sb * BN, umma_desc_sw128(sQ + (k >> 2) * ATOM + (k & 3) * 32, 16, 1024),
-                   umma_desc_sw128(kb + (k >> 2) * ATOM + (k & 3) * 32, 16, 1024), idesc_s, k != 0);
+          if (run_mma || kt < 2)
+            umma_f16(tbase + COL_S + sb * BN, umma_desc_sw128(sQ + (k >> 2) * QATOM + (k & 3) * 32, 16, 1024),
+                     umma_desc_sw128(kb + (k >> 2) * KATOM + (k & 3) * 32, 16, 1024), idesc_s, k != 0);
         umma_commit(&s_full[sb]);
       };
       mbar_wait(q_full, 0);
       issue_s(0);
+      if (num_kt > 1) issue_s(1);
       for (int kt = 0; kt < num_kt; ++kt) {
-        const int stage = kt % KV_STAGES;
-        if (kt + 1 < num_kt) issue_s(kt + 1);
-        mbar_wait(p_full, kt & 1);
+        const int stage = kt % KV_STAGES, sb = kt & 1;
+        if (kt < 15) stamp(2);                           // [4kt+0] waiting for P
+        mbar_wait(&p_full[sb], (kt >> 1) & 1);
+        if (kt < 15) stamp(2);                           // [4kt+1] P ready
         mbar_wait(&v_full[stage], (kt / KV_STAGES) & 1);
         tc_fence_after_sync();
-        const uint32_t vb = sV + stage * TILE;
+        const uint32_t vb = sV + stage * KTILE;
+        const uint32_t p_tmem = tbase + COL_S + sb * BN;       // packed fp16 P: 8 columns per 16 keys
 #pragma unroll
-        for (int k = 0; k < BN / 16; ++k)
-          if (!(prm.debug & 4) || kt < 2) umma_f16(tbase + COL_O, umma_desc_sw128(sPa + (k >> 2) * ATOM + (k & 3) * 32, 16, 1024),
-                   umma_desc_sw128(vb + k * 2048, ATOM, 1024), idesc_o, (kt | k) != 0);
+        for (int k = 0; k < BN / 16; ++k) {
+          if (run_mma || kt < 2) {
+            const uint64_t bdesc = umma_desc_sw128(vb + k * 2048, KATOM, 1024);
+            const uint32_t acc = (kt | k) != 0;
+            asm volatile(
+                "{\n"
+                ".reg .pred p;\n"
+                "setp.ne.b32 p, %4, 0;\n"
+                "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
+                "}\n" ::"r"(tbase + COL_O), "r"(p_tmem + k * 8), "l"(bdesc), "r"(idesc_o), "r"(acc)
+                : "memory");
+          }
+        }
         umma_commit(&kv_empty[stage]);
-        umma_commit(o_done);
+        umma_commit(&pv_done[sb]);
+        if (kt < 15) stamp(2);                           // [4kt+2] PV issued
+        if (kt + 2 < num_kt) issue_s(kt + 2);           // tensor pipe order: ... PV(kt), S(kt+2), PV(kt+1), ...
+        if (kt < 15) stamp(2);                           // [4kt+3] S(kt+2) issued
       }
     }
   }
@@ -468,8 +545,12 @@ int launch_focal_attention(const void* qkv, const void* qkv_pooled, void* out, i
   }
   if (b == 0) return 0;
   const int EH = wh + 2 * eh, EW = ww + 2 * ew;
-  if (EH * EW > MAX_RING) {
-    set_error("focal attention: expanded window %dx%d exceeds %d positions", EH, EW, MAX_RING);
+  if (EH * EW > MAX_RING || EH * EW + (use_pooled ? fh * fw : 0) > MAX_FRAME_KEYS) {
+    set_error("focal attention: expanded window %dx%d (+%dx%d pooled) exceeds the per-frame key table", EH, EW, fh, fw);
+    return -2;
+  }
+  if (static_cast<long long>(h) * w * 3 * heads * HD > 0x7FFFFFFFLL) {
+    set_error("focal attention: one frame of qkv exceeds 2^31 elements");
     return -2;
   }
   if (!(scale > 0.f)) {
@@ -488,6 +569,8 @@ int launch_focal_attention(const void* qkv, const void* qkv_pooled, void* out, i
   {
     const char* dbg = getenv("E2F_ATTN_DEBUG");
     prm.debug = dbg ? atoi(dbg) : 0;
+    const char* tr = getenv("E2F_ATTN_TRACE");      // hex device address of a [3][64] int64 buffer (perf experiments)
+    prm.trace = tr ? reinterpret_cast<long long*>(strtoull(tr, nullptr, 16)) : nullptr;
   }
   // order the expanded-window positions: single-listed first, multiply-listed last (positions never listed are dropped)
   prm.n1 = prm.n2 = 0;
@@ -513,6 +596,7 @@ int launch_focal_attention(const void* qkv, const void* qkv_pooled, void* out, i
     if (!cfg) {
       e = cudaFuncSetAttribute(focal_attn_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
       if (e != cudaSuccess) return static_cast<int>(e);
+      cudaFuncSetAttribute(focal_attn_kernel<__half>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
       cfg = true;
     }
     focal_attn_kernel<__half><<<grid, THREADS, SMEM_BYTES, stream>>>(prm);
@@ -521,6 +605,7 @@ int launch_focal_attention(const void* qkv, const void* qkv_pooled, void* out, i
     if (!cfg) {
       e = cudaFuncSetAttribute(focal_attn_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
       if (e != cudaSuccess) return static_cast<int>(e);
+      cudaFuncSetAttribute(focal_attn_kernel<float>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
       cfg = true;
     }
     focal_attn_kernel<float><<<grid, THREADS, SMEM_BYTES, stream>>>(prm);

@@ -7,6 +7,9 @@
 //   mode 2: A K-major                             B MN-major ([k][n] rows, manual swizzle); swap=1 swaps LBO/SBO
 //   mode 3: mode 1 + TMEM round trip (ld, x2, st, ld)
 //   mode 4: mode 1 with N=64 instruction shape (only the first 64 columns are produced)
+//   mode 5: A operand from TENSOR MEMORY (tcgen05.mma [d], [a_tmem], b_desc): A is written to TMEM columns 128.. by
+//           tcgen05.st as packed fp16 pairs (column j of lane m holds A[m][2j] (low half) | A[m][2j+1] (high half));
+//           B K-major in smem.  swap=1 tries the opposite half order.
 #include <cuda.h>
 #include <cstdio>
 #include <cstdlib>
@@ -30,7 +33,7 @@ probe_kernel(const __grid_constant__ CUtensorMap tmapB, const __half* __restrict
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_tma + 2);
 
   const int tid = threadIdx.x, warp = tid >> 5;
-  if (warp == 0) tmem_alloc(tmem_slot, 128);
+  if (warp == 0) tmem_alloc(tmem_slot, 256);
   if (tid == 0) {
     mbar_init(bar_tma, 1);
     mbar_init(bar_mma, 1);
@@ -60,12 +63,43 @@ probe_kernel(const __grid_constant__ CUtensorMap tmapB, const __half* __restrict
   fence_proxy_async_smem();
   __syncthreads();
 
+  if (mode == 5) {
+    // thread m writes its row of A (128 halfs = 64 packed columns) to TMEM lanes [32*warp, +32), columns 128..191
+    const uint32_t lane_base5 = static_cast<uint32_t>(warp * 32) << 16;
+    for (int c = 0; c < 2; ++c) {
+      uint32_t pk[32];
+      for (int j = 0; j < 32; ++j) {
+        const __half lo = A[tid * K + 2 * (c * 32 + j) + (swap ? 1 : 0)];
+        const __half hi = A[tid * K + 2 * (c * 32 + j) + (swap ? 0 : 1)];
+        pk[j] = static_cast<uint32_t>(__half_as_ushort(lo)) | (static_cast<uint32_t>(__half_as_ushort(hi)) << 16);
+      }
+      tmem_st32(tbase + lane_base5 + 128 + c * 32, pk);
+    }
+    tmem_st_wait();
+    tc_fence_before_sync();
+    __syncthreads();
+  }
   if (tid == 0) {
     if (mode == 0) mbar_wait(bar_tma, 0);
     tc_fence_after_sync();
+    if (mode == 5) {
+      const uint32_t idesc5 = umma_idesc_f16(128, 128, 0, 0);
+      for (int k = 0; k < K / 16; ++k) {
+        const uint64_t bd = umma_desc_sw128(smem_u32(sB) + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024);
+        const uint32_t a_tmem = tbase + 128 + k * 8;      // 16 halfs = 8 packed 32-bit columns per K step
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "setp.ne.b32 p, %4, 0;\n"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
+            "}\n" ::"r"(tbase), "r"(a_tmem), "l"(bd), "r"(idesc5), "r"(k > 0 ? 1u : 0u)
+            : "memory");
+      }
+      umma_commit(bar_mma);
+    }
     const int n_inst = (mode == 4) ? 64 : 128;
     const uint32_t idesc = umma_idesc_f16(128, n_inst, 0, mode == 2 ? 1 : 0);
-    for (int k = 0; k < K / 16; ++k) {
+    for (int k = 0; k < (mode == 5 ? 0 : K / 16); ++k) {
       const uint64_t ad = umma_desc_sw128(smem_u32(sA) + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024);
       uint64_t bd;
       if (mode == 2) {
@@ -76,7 +110,7 @@ probe_kernel(const __grid_constant__ CUtensorMap tmapB, const __half* __restrict
       }
       umma_f16(tbase, ad, bd, idesc, k > 0);
     }
-    umma_commit(bar_mma);
+    if (mode != 5) umma_commit(bar_mma);
   }
   mbar_wait(bar_mma, 0);
   tc_fence_after_sync();
@@ -99,7 +133,7 @@ probe_kernel(const __grid_constant__ CUtensorMap tmapB, const __half* __restrict
   }
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tbase, 128);
+  if (warp == 0) tmem_dealloc(tbase, 256);
 }
 
 #define CK(x)                                                                          \
