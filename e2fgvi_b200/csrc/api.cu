@@ -79,25 +79,27 @@ static int dcn_common_checks(const char* who, const void* x, const void* w_packe
 
 int e2f_modulated_deform_conv2d(const void* x, const float* offset, const float* mask, const void* w_packed,
                                 const float* bias, void* out, int n, int h, int w, int cin, int cout,
-                                int deform_groups, int out_dtype, void* stream) {
+                                int deform_groups, int out_dtype, int x_layout, void* stream) {
   int st = dcn_common_checks("e2f_modulated_deform_conv2d", x, w_packed, out, n, h, w, out_dtype);
   if (st) return st;
   if (!offset || !mask) { set_error("e2f_modulated_deform_conv2d: null offset/mask"); return E2F_ERR_BAD_ARG; }
   if (!aligned(offset, 8)) { set_error("e2f_modulated_deform_conv2d: offset needs 8-byte alignment"); return E2F_ERR_ALIGNMENT; }
+  if (x_layout != E2F_X_NHWC && x_layout != E2F_X_GROUPED) { set_error("e2f_modulated_deform_conv2d: x_layout %d", x_layout); return E2F_ERR_BAD_ARG; }
   return finish(launch_dcn(x, offset, mask, nullptr, nullptr, nullptr, w_packed, bias, out, n, h, w, cin, cout,
-                           deform_groups, 0.f, out_dtype, static_cast<cudaStream_t>(stream)),
+                           deform_groups, 0.f, out_dtype, x_layout, static_cast<cudaStream_t>(stream)),
                 "e2f_modulated_deform_conv2d");
 }
 
 int e2f_deform_align_fused(const void* x, const float* head, const float* flow1, const float* flow2,
                            const void* w_packed, const float* bias, void* out, int n, int h, int w, int cin, int cout,
-                           int deform_groups, float max_residue, int out_dtype, void* stream) {
+                           int deform_groups, float max_residue, int out_dtype, int x_layout, void* stream) {
   int st = dcn_common_checks("e2f_deform_align_fused", x, w_packed, out, n, h, w, out_dtype);
   if (st) return st;
   if (!head || !flow1 || !flow2) { set_error("e2f_deform_align_fused: null head/flow"); return E2F_ERR_BAD_ARG; }
   if (!aligned(head, 8) || !aligned(flow1, 8) || !aligned(flow2, 8)) { set_error("e2f_deform_align_fused: head/flow need 8-byte alignment"); return E2F_ERR_ALIGNMENT; }
+  if (x_layout != E2F_X_NHWC && x_layout != E2F_X_GROUPED) { set_error("e2f_deform_align_fused: x_layout %d", x_layout); return E2F_ERR_BAD_ARG; }
   return finish(launch_dcn(x, nullptr, nullptr, head, flow1, flow2, w_packed, bias, out, n, h, w, cin, cout,
-                           deform_groups, max_residue, out_dtype, static_cast<cudaStream_t>(stream)),
+                           deform_groups, max_residue, out_dtype, x_layout, static_cast<cudaStream_t>(stream)),
                 "e2f_deform_align_fused");
 }
 
@@ -114,6 +116,13 @@ int e2f_focal_window_attention(const void* qkv, const void* qkv_pooled, void* ou
   return finish(launch_focal_attention(qkv, qkv_pooled, out, b, t, h, w, heads, head_dim, wh, ww, eh, ew, fh, fw,
                                        use_pooled, scale, out_dtype, static_cast<cudaStream_t>(stream)),
                 "e2f_focal_window_attention");
+}
+
+int e2f_dcn_pack_input(const float* a, const float* b, void* xg, int n, int h, int w, int ca, int cb, void* stream) {
+  if (!a || !b || !xg) { set_error("e2f_dcn_pack_input: null pointer"); return E2F_ERR_BAD_ARG; }
+  if (n < 0 || h <= 0 || w <= 0 || ca <= 0 || cb <= 0 || ca % 16 || cb % 16) { set_error("e2f_dcn_pack_input: bad shape (channels must be multiples of 16)"); return E2F_ERR_BAD_ARG; }
+  if (!aligned(a, 16) || !aligned(b, 16) || !aligned(xg, 16)) { set_error("e2f_dcn_pack_input: 16-byte alignment required"); return E2F_ERR_ALIGNMENT; }
+  return finish(launch_dcn_pack_input(a, b, xg, n, h, w, ca, cb, static_cast<cudaStream_t>(stream)), "e2f_dcn_pack_input");
 }
 
 static int t2t_checks(const char* who, const void* a, const void* b, int bt, int c, int h, int w, int k, int s, int p) {

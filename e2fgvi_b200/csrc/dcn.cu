@@ -40,7 +40,9 @@ __device__ __forceinline__ float fast_tanh(float v) {
 }
 __device__ __forceinline__ float fast_sigmoid(float v) { return __fdividef(1.f, 1.f + __expf(-v)); }
 
-template <bool FUSED, typename OutT>
+// GROUPED: x is [N][G][H][W][16] (group-major; the two horizontally adjacent bilinear corners of a sample are one
+// contiguous 64 B run -> about half the distinct L1 lines per sample of the NHWC layout [N][H][W][256]).
+template <bool FUSED, bool GROUPED, typename OutT>
 __global__ void __launch_bounds__(THREADS, 1)
 dcn_kernel(const __grid_constant__ CUtensorMap tmap_w, const __half* __restrict__ x,
            const float* __restrict__ offset, const float* __restrict__ mask, const float* __restrict__ head,
@@ -84,6 +86,7 @@ dcn_kernel(const __grid_constant__ CUtensorMap tmap_w, const __half* __restrict_
     const int py = static_cast<int>((mm / W) % H);
     const long long n = mm / (static_cast<long long>(W) * H);
     const __half* xn = x + n * H * W * CIN;
+    constexpr int PIX_STRIDE = GROUPED ? CPG : CIN;      // halfs between horizontally adjacent pixels
     const float* off_p = FUSED ? head + mm * (3 * NSP) : offset + mm * (2 * NSP);
     const float* msk_p = FUSED ? head + mm * (3 * NSP) + 2 * NSP : mask + mm * NSP;
     float2 fl1 = make_float2(0.f, 0.f), fl2 = make_float2(0.f, 0.f);
@@ -125,7 +128,7 @@ dcn_kernel(const __grid_constant__ CUtensorMap tmap_w, const __half* __restrict_
         const float fy = floorf(h_im), fx = floorf(w_im);
         const float ly = h_im - fy, lx = w_im - fx;
         const int y0 = static_cast<int>(fy), x0 = static_cast<int>(fx);
-        const __half* xg = xn + g * CPG;
+        const __half* xg = GROUPED ? xn + static_cast<long long>(g) * H * W * CPG : xn + g * CPG;
         uint4 lo[4], hi[4];
         float wgt[4];
 #pragma unroll
@@ -135,7 +138,7 @@ dcn_kernel(const __grid_constant__ CUtensorMap tmap_w, const __half* __restrict_
           const bool in = (yy >= 0) && (yy < H) && (xx >= 0) && (xx < W);
           wgt[k] = in ? (dy ? ly : 1.f - ly) * (dx ? lx : 1.f - lx) * mk : 0.f;
           const int po = min(max(yy, 0), H - 1) * W + min(max(xx, 0), W - 1);
-          const uint4* p = reinterpret_cast<const uint4*>(xg + static_cast<long long>(po) * CIN);
+          const uint4* p = reinterpret_cast<const uint4*>(xg + static_cast<long long>(po) * PIX_STRIDE);
           lo[k] = __ldg(p);
           hi[k] = __ldg(p + 1);
         }
@@ -211,17 +214,16 @@ dcn_kernel(const __grid_constant__ CUtensorMap tmap_w, const __half* __restrict_
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0) {
       const uint32_t idesc = umma_idesc_f16(BLOCK_M, COUT, 0, 0);
+      const uint64_t d_a0 = umma_desc_sw128(smem_u32(sA), 16, 1024), d_b0 = umma_desc_sw128(smem_u32(sB), 16, 1024);
       for (int j = 0; j < NUM_KB; ++j) {
         const int stage = j % STAGES;
         const uint32_t phase = (j / STAGES) & 1;
         mbar_wait(&full_a[stage], phase);
         mbar_wait(&full_b[stage], phase);
         tc_fence_after_sync();
-        const uint32_t a0 = smem_u32(sA + stage * A_BYTES), b0 = smem_u32(sB + stage * B_BYTES);
+        const uint64_t da = d_a0 + ((stage * A_BYTES) >> 4), db = d_b0 + ((stage * B_BYTES) >> 4);
 #pragma unroll
-        for (int k = 0; k < BLOCK_K / 16; ++k)
-          umma_f16(tbase, umma_desc_sw128(a0 + k * 32, 16, 1024), umma_desc_sw128(b0 + k * 32, 16, 1024), idesc,
-                   (j | k) != 0);
+        for (int k = 0; k < BLOCK_K / 16; ++k) umma_f16(tbase, da + 2 * k, db + 2 * k, idesc, (j | k) != 0);
         umma_commit(&empty[stage]);
       }
       umma_commit(accum_bar);
@@ -258,11 +260,36 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 
-template <bool FUSED, typename OutT>
+// fp32 NHWC sources a [N][H][W][Ca], b [N][H][W][Cb] -> fp16 group-major [N][(Ca+Cb)/16][H][W][16]
+// (== torch.cat([a, b], 1).half() of feat_prop.py:126 in the layout the sampler wants); one thread per (group, pixel)
+__global__ void __launch_bounds__(256) pack_input_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                                         __half* __restrict__ xg, int N, int HW, int Ca, int Cb) {
+  const int G = (Ca + Cb) / CPG;
+  const long long total = static_cast<long long>(N) * G * HW;
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int pix = static_cast<int>(i % HW);
+  const int g = static_cast<int>((i / HW) % G);
+  const long long n = i / (static_cast<long long>(HW) * G);
+  const int c0 = g * CPG;
+  const float* src = (c0 < Ca) ? a + (n * HW + pix) * Ca + c0 : b + (n * HW + pix) * Cb + (c0 - Ca);
+  uint32_t o[8];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(src) + j);
+    o[2 * j] = pack_half2(v.x, v.y);
+    o[2 * j + 1] = pack_half2(v.z, v.w);
+  }
+  uint4* dst = reinterpret_cast<uint4*>(xg + i * CPG);
+  dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
+  dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
+}
+
+template <bool FUSED, bool GROUPED, typename OutT>
 static int launch_variant(const CUtensorMap& tmap, const void* x, const float* offset, const float* mask,
                           const float* head, const float* flow1, const float* flow2, const float* bias, void* out,
                           int M, int h, int w, float max_res, cudaStream_t stream) {
-  auto kern = dcn_kernel<FUSED, OutT>;
+  auto kern = dcn_kernel<FUSED, GROUPED, OutT>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
@@ -291,7 +318,7 @@ int launch_dcn_pack_weight(const float* w, void* w_packed, int cout, int cin, in
 
 int launch_dcn(const void* x, const float* offset, const float* mask, const float* head, const float* flow1,
                const float* flow2, const void* w_packed, const float* bias, void* out, int n, int h, int w, int cin,
-               int cout, int dg, float max_residue, int out_dtype, cudaStream_t stream) {
+               int cout, int dg, float max_residue, int out_dtype, int x_grouped, cudaStream_t stream) {
   using namespace dcn;
   if (cin != CIN || cout != COUT || dg != DG) {
     set_error("deformable conv is specialised for Cin=256, Cout=128, deform_groups=16 (got %d, %d, %d)", cin, cout,
@@ -322,18 +349,25 @@ int launch_dcn(const void* x, const float* offset, const float* mask, const floa
     return -4;
   }
   const int Mi = static_cast<int>(M);
+#define E2F_DCN_LAUNCH(F, G, T) launch_variant<F, G, T>(tmap, x, offset, mask, head, flow1, flow2, bias, out, Mi, h, w, max_residue, stream)
   if (head) {
-    return out_dtype == 1
-               ? launch_variant<true, __half>(tmap, x, offset, mask, head, flow1, flow2, bias, out, Mi, h, w,
-                                              max_residue, stream)
-               : launch_variant<true, float>(tmap, x, offset, mask, head, flow1, flow2, bias, out, Mi, h, w,
-                                             max_residue, stream);
+    if (x_grouped) return out_dtype == 1 ? E2F_DCN_LAUNCH(true, true, __half) : E2F_DCN_LAUNCH(true, true, float);
+    return out_dtype == 1 ? E2F_DCN_LAUNCH(true, false, __half) : E2F_DCN_LAUNCH(true, false, float);
   }
-  return out_dtype == 1
-             ? launch_variant<false, __half>(tmap, x, offset, mask, head, flow1, flow2, bias, out, Mi, h, w,
-                                             max_residue, stream)
-             : launch_variant<false, float>(tmap, x, offset, mask, head, flow1, flow2, bias, out, Mi, h, w,
-                                            max_residue, stream);
+  if (x_grouped) return out_dtype == 1 ? E2F_DCN_LAUNCH(false, true, __half) : E2F_DCN_LAUNCH(false, true, float);
+  return out_dtype == 1 ? E2F_DCN_LAUNCH(false, false, __half) : E2F_DCN_LAUNCH(false, false, float);
+#undef E2F_DCN_LAUNCH
+}
+
+int launch_dcn_pack_input(const float* a, const float* b, void* xg, int n, int h, int w, int ca, int cb,
+                          cudaStream_t stream) {
+  const long long total = static_cast<long long>(n) * ((ca + cb) / dcn::CPG) * h * w;
+  if (total == 0) return 0;
+  const int threads = 256;
+  dcn::pack_input_kernel<<<static_cast<unsigned>((total + threads - 1) / threads), threads, 0, stream>>>(
+      a, b, static_cast<__half*>(xg), n, h * w, ca, cb);
+  count_launch();
+  return static_cast<int>(cudaGetLastError());
 }
 
 }  // namespace e2f

@@ -104,6 +104,10 @@ linear_kernel(const __grid_constant__ CUtensorMap tm_ah, const __grid_constant__
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0) {
       const uint32_t idesc = idesc_bf16(BM, BN);
+      // stage-0 descriptors; stage s / K step k are reached with one 64-bit add each
+      const uint64_t d_ah0 = umma_desc_sw128(smem_u32(smem), 16, 1024);
+      const uint64_t d_al0 = umma_desc_adv(d_ah0, A_TILE), d_wh0 = umma_desc_adv(d_ah0, 2 * A_TILE);
+      const uint64_t d_wl0 = umma_desc_adv(d_wh0, C::W_TILE);
       uint32_t it = 0, local = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
         const int buf = local & 1;
@@ -114,12 +118,11 @@ linear_kernel(const __grid_constant__ CUtensorMap tm_ah, const __grid_constant__
           const int stage = it % C::STAGES;
           mbar_wait(&full[stage], (it / C::STAGES) & 1);
           tc_fence_after_sync();
-          const uint32_t s0 = smem_u32(smem + stage * C::STAGE);
-          const uint32_t ah = s0, al = s0 + A_TILE, wh = s0 + 2 * A_TILE, wl = wh + C::W_TILE;
+          const uint32_t soff = (stage * C::STAGE) >> 4;
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
-            const uint64_t dah = umma_desc_sw128(ah + k * 32, 16, 1024), dal = umma_desc_sw128(al + k * 32, 16, 1024);
-            const uint64_t dwh = umma_desc_sw128(wh + k * 32, 16, 1024), dwl = umma_desc_sw128(wl + k * 32, 16, 1024);
+            const uint64_t dah = d_ah0 + soff + 2 * k, dal = d_al0 + soff + 2 * k;
+            const uint64_t dwh = d_wh0 + soff + 2 * k, dwl = d_wl0 + soff + 2 * k;
             umma_f16(d, dal, dwh, idesc, (kb | k) != 0);   // small terms first
             umma_f16(d, dah, dwl, idesc, 1);
             umma_f16(d, dah, dwh, idesc, 1);

@@ -17,7 +17,9 @@ int launch_dcn_pack_weight(const float* w, void* w_packed, int cout, int cin, in
 // head != nullptr selects the fused (tanh / flow / sigmoid) prologue; otherwise offset+mask are final values.
 int launch_dcn(const void* x, const float* offset, const float* mask, const float* head, const float* flow1,
                const float* flow2, const void* w_packed, const float* bias, void* out, int n, int h, int w, int cin,
-               int cout, int dg, float max_residue, int out_dtype, cudaStream_t stream);
+               int cout, int dg, float max_residue, int out_dtype, int x_grouped, cudaStream_t stream);
+int launch_dcn_pack_input(const float* a, const float* b, void* xg, int n, int h, int w, int ca, int cb,
+                          cudaStream_t stream);
 
 int launch_focal_attention(const void* qkv, const void* qkv_pooled, void* out, int b, int t, int h, int w, int heads,
                            int head_dim, int wh, int ww, int eh, int ew, int fh, int fw, int use_pooled, float scale,

@@ -134,7 +134,7 @@ class BidirectionalPropagation(nn.Module):
                         feat_n2 = torch.zeros_like(prop)
                         flow_n2 = torch.zeros_like(flow_n1)
                         cond_n2 = torch.zeros_like(cond_n1)
-                    prop = align.align(torch.cat([prop, feat_n2], dim=1), [cond_n1, cur, cond_n2], flow_n1, flow_n2)
+                    prop = align.align(ops.dcn_pack_input(prop, feat_n2), [cond_n1, cur, cond_n2], flow_n1, flow_n2)
                 parts = [cur, prop] if backward else [cur, swept["backward_"][idx], prop]
                 # feat_prop + backbone(cat(parts)): conv+LeakyReLU(0.1), then conv with the residual add fused
                 y = ops.conv3x3(parts, backbone[0].weight, backbone[0].bias, negative_slope=0.1, out="split")

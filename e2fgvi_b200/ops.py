@@ -141,9 +141,32 @@ def modulated_deform_conv2d(x, offset, mask, weight, bias=None, stride=1, paddin
     st = _lib.load().e2f_modulated_deform_conv2d(
         x_cl.data_ptr(), off_cl.data_ptr(), msk_cl.data_ptr(), wp.data_ptr(),
         None if b32 is None else b32.data_ptr(), out.data_ptr(), n, h, w, cin, cout, deform_groups,
-        _DT[out_dtype], _stream())
+        _DT[out_dtype], 0, _stream())
     _lib.check(st, "e2f_modulated_deform_conv2d")
     return out
+
+
+class GroupedX:
+    """DCN input in the group-major fp16 layout [N][G][H][W][16] (see ``dcn_pack_input``)."""
+
+    __slots__ = ("data", "shape")
+
+    def __init__(self, data, shape):
+        self.data, self.shape = data, shape       # shape: logical (N, Cin, H, W)
+
+
+def dcn_pack_input(a, b):
+    """``torch.cat([a, b], 1)`` (feat_prop.py:126) converted to fp16 in the group-major layout the deformable sampler
+    reads best (adjacent bilinear corners contiguous).  a, b: (N,C,H,W) fp32, C % 16 == 0 -> ``GroupedX``."""
+    _need_cuda(a, b)
+    n, ca, h, w = a.shape
+    cb = b.shape[1]
+    a_cl = a.permute(0, 2, 3, 1).contiguous().float()
+    b_cl = b.permute(0, 2, 3, 1).contiguous().float()
+    xg = torch.empty((n, (ca + cb) // 16, h, w, 16), dtype=torch.float16, device=a.device)
+    st = _lib.load().e2f_dcn_pack_input(a_cl.data_ptr(), b_cl.data_ptr(), xg.data_ptr(), n, h, w, ca, cb, _stream())
+    _lib.check(st, "e2f_dcn_pack_input")
+    return GroupedX(xg, (n, ca + cb, h, w))
 
 
 def deform_align_fused(x, head, flow_1, flow_2, w_packed, bias, deform_groups, max_residue_magnitude=10.0,
@@ -153,22 +176,25 @@ def deform_align_fused(x, head, flow_1, flow_2, w_packed, bias, deform_groups, m
     x (n,cin,h,w) fp16 channels_last; head (n,27*dg,h,w) fp32 channels_last (raw conv_offset output);
     flow_k (n,2,h,w) any layout (converted to (n,h,w,2) fp32).  Returns (n,cout,h,w) channels_last.
     """
-    _need_cuda(x, head, flow_1, flow_2, w_packed, bias)
+    grouped = isinstance(x, GroupedX)
+    _need_cuda(None if grouped else x, head, flow_1, flow_2, w_packed, bias)
     n, cin, h, w = x.shape
     cout = w_packed.shape[0]
-    if x.dtype != torch.float16 or not _is_cl(x):
+    if grouped:
+        x = x.data
+    elif x.dtype != torch.float16 or not _is_cl(x):
         x = x.to(dtype=torch.float16, memory_format=torch.channels_last)
     if head.dtype != torch.float32 or not _is_cl(head):
         head = head.to(dtype=torch.float32, memory_format=torch.channels_last)
     f1 = flow_1.permute(0, 2, 3, 1).contiguous().float()
     f2 = flow_2.permute(0, 2, 3, 1).contiguous().float()
     b32 = None if bias is None else bias.detach().float().contiguous()
-    out = torch.empty((n, cout, h, w), dtype=out_dtype, device=x.device, memory_format=torch.channels_last)
+    out = torch.empty((n, cout, h, w), dtype=out_dtype, device=head.device, memory_format=torch.channels_last)
     with _timed("deform_align_fused", 2.0 * cout * cin * 9 * n * h * w):
         st = _lib.load().e2f_deform_align_fused(
             x.data_ptr(), head.data_ptr(), f1.data_ptr(), f2.data_ptr(), w_packed.data_ptr(),
             None if b32 is None else b32.data_ptr(), out.data_ptr(), n, h, w, cin, cout, deform_groups,
-            float(max_residue_magnitude), _DT[out_dtype], _stream())
+            float(max_residue_magnitude), _DT[out_dtype], 1 if grouped else 0, _stream())
     _lib.check(st, "e2f_deform_align_fused")
     return out
 

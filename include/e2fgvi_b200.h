@@ -27,6 +27,10 @@ extern "C" {
 #define E2F_ERR_ALIGNMENT (-3)
 #define E2F_ERR_DRIVER (-4)
 
+/* layouts of the deformable-conv input x */
+#define E2F_X_NHWC 0     /* [N][H][W][Cin] */
+#define E2F_X_GROUPED 1  /* [N][G][H][W][Cin/G] with G = deform_groups (group-major, see e2f_dcn_pack_input) */
+
 /* element types */
 #define E2F_F32 0
 #define E2F_F16 1
@@ -61,14 +65,19 @@ int e2f_dcn_pack_weight(const float* w, void* w_packed_f16, int cout, int cin, i
 /* modulated_deform_conv2d — replaces mmcv.ops.modulated_deform_conv2d as called at feat_prop.py:55-58
  * (3x3, stride 1, padding 1, dilation 1, groups 1).  Sampling + im2col are fused into the tcgen05 GEMM; no
  * column buffer is materialised.
- *   x        [N][H][W][Cin] fp16           offset [N][H][W][2*9*dg] fp32, channel (g*9+tap)*2 + {0:dy, 1:dx}
+ *   x        fp16, [N][H][W][Cin] (x_layout = E2F_X_NHWC) or group-major (E2F_X_GROUPED)     offset [N][H][W][2*9*dg] fp32, channel (g*9+tap)*2 + {0:dy, 1:dx}
  *   mask     [N][H][W][9*dg] fp32 (already sigmoid-ed), channel g*9+tap
  *   w_packed [Cout][9*Cin] fp16 from e2f_dcn_pack_weight      bias [Cout] fp32 or NULL
  *   out      [N][H][W][Cout] (out_dtype E2F_F32 or E2F_F16)
  * Supported: Cin = 256, Cout = 128, dg = 16 (the only instance on the path). */
 int e2f_modulated_deform_conv2d(const void* x, const float* offset, const float* mask, const void* w_packed,
                                 const float* bias, void* out, int n, int h, int w, int cin, int cout,
-                                int deform_groups, int out_dtype, void* stream);
+                                int deform_groups, int out_dtype, int x_layout, void* stream);
+
+/* cat([a, b], channel).half() in the group-major layout E2F_X_GROUPED (feat_prop.py:126 builds the DCN input as
+ * cat([feat_prop, feat_n2])): a [N][H][W][Ca], b [N][H][W][Cb] fp32 NHWC -> xg [N][(Ca+Cb)/16][H][W][16] fp16.
+ * Ca, Cb multiples of 16. */
+int e2f_dcn_pack_input(const float* a, const float* b, void* xg, int n, int h, int w, int ca, int cb, void* stream);
 
 /* Fused SecondOrderDeformableAlignment tail — replaces feat_prop.py:41-58: takes the raw 27*dg-channel output of
  * conv_offset (`head`, [N][H][W][27*dg] fp32: o1 | o2 | mask), applies offset = max_residue * tanh(o) +
@@ -76,7 +85,8 @@ int e2f_modulated_deform_conv2d(const void* x, const float* offset, const float*
  *   flow1, flow2 [N][H][W][2] fp32 (u, v). */
 int e2f_deform_align_fused(const void* x, const float* head, const float* flow1, const float* flow2,
                            const void* w_packed, const float* bias, void* out, int n, int h, int w, int cin,
-                           int cout, int deform_groups, float max_residue, int out_dtype, void* stream);
+                           int cout, int deform_groups, float max_residue, int out_dtype, int x_layout,
+                           void* stream);
 
 /* Temporal focal window attention core — replaces model/modules/tfocal_transformer.py:226-396 (everything in
  * WindowAttention.forward between the qkv Linear and the proj Linear): window partition of q, the own-window keys,

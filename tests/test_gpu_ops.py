@@ -344,3 +344,19 @@ def test_t2t_unfold_split_and_conv_split_outputs(cuda):
     chained = ops.conv3x3([only_sp], torch.nn.Parameter(torch.randn(8, 128, 3, 3, generator=g).to(cuda) / 34.0))
     ref = ops.conv3x3([f32], torch.nn.Parameter(torch.randn(8, 128, 3, 3, generator=torch.Generator().manual_seed(63)).to(cuda)))
     assert chained.shape == ref.shape == (1, 8, 12, 20)
+
+
+def test_deform_align_fused_grouped_layout(cuda):
+    """The group-major input layout (dcn_pack_input) gives the same result as the NHWC path."""
+    g = torch.Generator().manual_seed(71)
+    n, h, w = 2, 14, 22
+    a = torch.randn(n, 128, h, w, generator=g).to(cuda)
+    b = torch.randn(n, 128, h, w, generator=g).to(cuda)
+    head = (torch.randn(n, 432, h, w, generator=g) * 1.5).to(cuda)
+    f1 = (torch.randn(n, 2, h, w, generator=g) * 2).to(cuda)
+    f2 = (torch.randn(n, 2, h, w, generator=g) * 2).to(cuda)
+    wp = ops.pack_dcn_weight((torch.randn(128, 256, 3, 3, generator=g) / 48.0).to(cuda), 16)
+    bias = (torch.randn(128, generator=g) * 0.1).to(cuda)
+    ref = ops.deform_align_fused(torch.cat([a, b], 1), head, f1, f2, wp, bias, 16, 10.0)
+    got = ops.deform_align_fused(ops.dcn_pack_input(a, b), head, f1, f2, wp, bias, 16, 10.0)
+    assert torch.equal(ref, got)          # identical arithmetic, only the addressing differs
