@@ -19,16 +19,23 @@
 namespace e2f {
 namespace conv {
 
-constexpr int BM = 128, BN = 128, BK = 64;
+constexpr int BM = 128, BK = 64;
 constexpr int TILE_H = 8, TILE_W = 16;                  // 8 x 16 output pixels = 128 GEMM rows
-constexpr int A_TILE = BM * BK * 2, W_TILE = BN * BK * 2;
-constexpr int STAGE = 2 * A_TILE + 2 * W_TILE;          // 64 KB
-constexpr int STAGES = 3;
+constexpr int A_TILE = BM * BK * 2;
 constexpr int EPI_WARPS = 4;
 constexpr int THREADS = (2 + EPI_WARPS) * 32;
-constexpr int TMEM_COLS = 2 * BN;
-constexpr int SMEM = STAGES * STAGE + 256 + 1024;
 constexpr int MAX_SRC = 4;
+
+// N tile: 128 output channels, or 64 for the layers with <= 64 output channels per group (decoder, encoder conv 1,
+// the 3-channel output conv), which would otherwise waste half of every MMA.
+template <int BN>
+struct Cfg {
+  static constexpr int W_TILE = BN * BK * 2;
+  static constexpr int STAGE = 2 * A_TILE + 2 * W_TILE;   // 64 KB (BN=128) / 48 KB (BN=64)
+  static constexpr int STAGES = (BN == 128) ? 3 : 4;
+  static constexpr int TMEM_COLS = 2 * BN;
+  static constexpr int SMEM = STAGES * STAGE + 256 + 1024;
+};
 
 struct Maps {
   CUtensorMap a_hi[MAX_SRC], a_lo[MAX_SRC], w_hi, w_lo;
@@ -65,6 +72,7 @@ struct TileCoord {
   int n, y0, x0, g, co0;   // co0: first output channel of the tile (global index)
 };
 
+template <int BN>
 __device__ __forceinline__ TileCoord decode_tile(int tile, const Params& p, int tiles_y, int tiles_x, int tiles_ng) {
   TileCoord t;
   const int nt = tile % tiles_ng;
@@ -81,7 +89,9 @@ __device__ __forceinline__ TileCoord decode_tile(int tile, const Params& p, int 
   return t;
 }
 
+template <int BN>
 __global__ void __launch_bounds__(THREADS, 1) conv3x3_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Params p) {
+  constexpr int W_TILE = Cfg<BN>::W_TILE, STAGE = Cfg<BN>::STAGE, STAGES = Cfg<BN>::STAGES, TMEM_COLS = Cfg<BN>::TMEM_COLS;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE);
@@ -125,7 +135,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv3x3_kernel(const __grid_consta
     if (lane == 0) {
       uint32_t it = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const TileCoord t = decode_tile(tile, p, tiles_y, tiles_x, tiles_ng);
+        const TileCoord t = decode_tile<BN>(tile, p, tiles_y, tiles_x, tiles_ng);
         int kb = 0;
         for (int tap = 0; tap < 9; ++tap) {
           const int yy = t.y0 + tap / 3 - 1, xx = t.x0 + tap % 3 - 1;
@@ -182,7 +192,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv3x3_kernel(const __grid_consta
     uint32_t local = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
       const int buf = local & 1;
-      const TileCoord t = decode_tile(tile, p, tiles_y, tiles_x, tiles_ng);
+      const TileCoord t = decode_tile<BN>(tile, p, tiles_y, tiles_x, tiles_ng);
       mbar_wait(&acc_full[buf], (local >> 1) & 1);
       tc_fence_after_sync();
       const int r = q * 32 + lane;
@@ -300,6 +310,7 @@ int launch_conv3x3(int nsrc, const void* const* src_hi, const void* const* src_l
     set_error("cuTensorMapEncodeTiled is not available from the driver");
     return -4;
   }
+  const int bn = (cout / groups <= 64) ? 64 : 128;
   Maps maps;
   Params p;
   p.N = n; p.H = h; p.W = w; p.Cout = cout; p.groups = groups; p.nsrc = nsrc;
@@ -334,7 +345,7 @@ int launch_conv3x3(int nsrc, const void* const* src_hi, const void* const* src_l
     const int kpad = 9 * p.chunks_total * BK;
     const cuuint64_t dims[2] = {static_cast<cuuint64_t>(kpad), static_cast<cuuint64_t>(cout)};
     const cuuint64_t strides[1] = {static_cast<cuuint64_t>(kpad) * 2};
-    const cuuint32_t box[2] = {BK, BN};
+    const cuuint32_t box[2] = {BK, static_cast<cuuint32_t>(bn)};
     const cuuint32_t estr[2] = {1, 1};
     for (int part = 0; part < 2; ++part) {
       CUresult r = enc(part ? &maps.w_lo : &maps.w_hi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
@@ -349,12 +360,14 @@ int launch_conv3x3(int nsrc, const void* const* src_hi, const void* const* src_l
   }
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv3x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    cudaError_t e = cudaFuncSetAttribute(conv3x3_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<128>::SMEM);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(conv3x3_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<64>::SMEM);
     if (e != cudaSuccess) return static_cast<int>(e);
     configured = true;
   }
   const int tiles_y = (h + TILE_H - 1) / TILE_H, tiles_x = (w + TILE_W - 1) / TILE_W;
-  const int tiles_ng = (cout / groups + BN - 1) / BN;
+  const int tiles_ng = (cout / groups + bn - 1) / bn;
   const long long tiles = static_cast<long long>(n) * tiles_y * tiles_x * groups * tiles_ng;
   if (tiles == 0) return 0;
   if (tiles > 0x7FFFFFFFLL) {
@@ -362,7 +375,10 @@ int launch_conv3x3(int nsrc, const void* const* src_hi, const void* const* src_l
     return -2;
   }
   const int grid = tiles < num_sms() ? static_cast<int>(tiles) : num_sms();
-  conv3x3_kernel<<<grid, THREADS, SMEM, stream>>>(maps, p);
+  if (bn == 64)
+    conv3x3_kernel<64><<<grid, THREADS, Cfg<64>::SMEM, stream>>>(maps, p);
+  else
+    conv3x3_kernel<128><<<grid, THREADS, Cfg<128>::SMEM, stream>>>(maps, p);
   count_launch();
   return static_cast<int>(cudaGetLastError());
 }

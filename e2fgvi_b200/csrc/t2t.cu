@@ -54,6 +54,55 @@ __global__ void __launch_bounds__(256) t2t_unfold_kernel(const float* __restrict
   }
 }
 
+// Shared-memory staged unfold for the 7/3/3 geometry: one block per (8-channel chunk, token row, image).  The 7 image
+// rows a token row touches are loaded once (coalesced, zero-padded, GELU applied ONCE per pixel instead of once per
+// unfolded copy), then the 36 x (8*49) token values are written as fully coalesced runs (fp32 and/or bf16 split).
+constexpr int U2_CC = 8;
+template <bool GELU>
+__global__ void __launch_bounds__(256) t2t_unfold733_kernel(const float* __restrict__ img, float* __restrict__ tok,
+                                                            __nv_bfloat16* __restrict__ tok_hi,
+                                                            __nv_bfloat16* __restrict__ tok_lo, int C, int H, int W,
+                                                            int FH, int FW) {
+  extern __shared__ float simg[];                 // [U2_CC][7][W + 6]
+  const int WP = W + 6;
+  const int c0 = blockIdx.x * U2_CC, ty = blockIdx.y;
+  const long long bt = blockIdx.z;
+  const float* src = img + (bt * C + c0) * static_cast<long long>(H) * W;
+  for (int i = threadIdx.x; i < U2_CC * 7 * WP; i += blockDim.x) {
+    const int xx = i % WP, r = (i / WP) % 7, cc = i / (7 * WP);
+    const int y = ty * 3 - 3 + r, x = xx - 3;
+    float v = 0.f;
+    if (y >= 0 && y < H && x >= 0 && x < W) {
+      v = __ldg(src + (static_cast<long long>(cc) * H + y) * W + x);
+      if (GELU) v = gelu_exact(v);
+    }
+    simg[i] = v;
+  }
+  __syncthreads();
+  const int CK = C * 49, RUN = U2_CC * 49;         // 392 values per token and chunk (multiple of 4)
+  const long long tok0 = (bt * FH + ty) * static_cast<long long>(FW);
+  for (int o = threadIdx.x * 4; o < FW * RUN; o += blockDim.x * 4) {
+    const int tx = o / RUN, rem = o - tx * RUN;
+    float v[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int q = rem + e;
+      const int cc = q / 49, kk = q - cc * 49;
+      const int ky = kk / 7, kx = kk - ky * 7;
+      v[e] = simg[(cc * 7 + ky) * WP + tx * 3 + kx];
+    }
+    const long long dst = (tok0 + tx) * CK + c0 * 49 + rem;
+    if (tok) *reinterpret_cast<float4*>(tok + dst) = make_float4(v[0], v[1], v[2], v[3]);
+    if (tok_hi) {
+      const __nv_bfloat162 h0 = __floats2bfloat162_rn(v[0], v[1]), h1 = __floats2bfloat162_rn(v[2], v[3]);
+      const float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
+      const __nv_bfloat162 l0 = __floats2bfloat162_rn(v[0] - f0.x, v[1] - f0.y), l1 = __floats2bfloat162_rn(v[2] - f1.x, v[3] - f1.y);
+      *reinterpret_cast<uint2*>(tok_hi + dst) = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
+      *reinterpret_cast<uint2*>(tok_lo + dst) = make_uint2(*reinterpret_cast<const uint32_t*>(&l0), *reinterpret_cast<const uint32_t*>(&l1));
+    }
+  }
+}
+
 // one thread per image element (c, y, x): sums the <= ceil(K/S)^2 patch entries that cover it
 template <int KC, int SC, int PC>
 __global__ void __launch_bounds__(256) t2t_fold_kernel(const float* __restrict__ tok, const float* __restrict__ bias,
@@ -101,6 +150,22 @@ int launch_t2t_unfold(const float* img, float* tok, void* tok_hi_v, void* tok_lo
   const int threads = 256;
   const unsigned blocks = static_cast<unsigned>((total4 + threads - 1) / threads);
   const bool fast = (k == 7 && s == 3 && p == 3);
+  const int smem2 = U2_CC * 7 * (w + 6) * 4;
+  if (fast && c % U2_CC == 0 && smem2 <= 200 * 1024 && fh <= 65535 && bt <= 65535) {
+    static bool cfg = false;
+    if (!cfg) {
+      cudaFuncSetAttribute(t2t_unfold733_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      cudaFuncSetAttribute(t2t_unfold733_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      cfg = true;
+    }
+    const dim3 grid(c / U2_CC, fh, bt);
+    if (gelu)
+      t2t_unfold733_kernel<true><<<grid, threads, smem2, stream>>>(img, tok, tok_hi, tok_lo, c, h, w, fh, fw);
+    else
+      t2t_unfold733_kernel<false><<<grid, threads, smem2, stream>>>(img, tok, tok_hi, tok_lo, c, h, w, fh, fw);
+    count_launch();
+    return static_cast<int>(cudaGetLastError());
+  }
   if (gelu && fast)
     t2t_unfold_kernel<true, 7, 3, 3><<<blocks, threads, 0, stream>>>(img, tok, tok_hi, tok_lo, bt, c, h, w, k, s, p, fh, fw);
   else if (fast)
