@@ -269,7 +269,7 @@ def main():
                  # bf16x3 kernels: algorithmic fp32 FLOPs; each costs 3 bf16 MMAs, so <= 1/3 of the bf16 peak
                  "conv3x3_bf16x3": ("conv3x3_kernel", "tensor", 3.0),
                  "linear_bf16x3": ("linear_kernel", "tensor", 3.0),
-                 "t2t_fold": ("t2t_fold_kernel", "hbm", 1.0), "t2t_unfold": ("t2t_unfold_kernel", "hbm", 1.0)}
+                 "t2t_fold": ("t2t_fold_kernel", "hbm", 1.0), "t2t_unfold": ("t2t_unfold733_kernel", "hbm", 1.0)}
         traffic = {}
         tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")   # dram bytes / launch from `ncu --set full`
         if os.path.exists(tpath):
