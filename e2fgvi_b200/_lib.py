@@ -30,6 +30,8 @@ SIGNATURES = {
     "e2f_linear_bf16x3": (_i, [_vp, _vp, _vp, _vp, _fp, _fp, _vp, _i, _i, _i, _i, _i, _vp]),
     "e2f_conv3x3_bf16x3": (_i, [_i, _c.POINTER(_vp), _c.POINTER(_vp), _c.POINTER(_i), _vp, _vp, _fp, _fp, _fp, _vp, _vp,
                                 _i, _i, _i, _i, _i, _f, _vp]),
+    "e2f_conv2d_bf16x3": (_i, [_i, _c.POINTER(_vp), _c.POINTER(_vp), _c.POINTER(_i), _vp, _vp, _fp, _fp, _fp, _vp, _vp,
+                               _i, _i, _i, _i, _i, _f, _i, _i, _i, _vp]),
     "e2f_launch_count": (_c.c_int64, []),
 }
 

@@ -187,23 +187,32 @@ int e2f_linear_bf16x3(const void* a_hi, const void* a_lo, const void* w_hi, cons
   return finish(launch_linear_bf16x3(a_hi, a_lo, w_hi, w_lo, bias, residual, out, m, n, k, out_dtype, bn, static_cast<cudaStream_t>(stream)), "e2f_linear_bf16x3");
 }
 
+int e2f_conv2d_bf16x3(int nsrc, const void* const* src_hi, const void* const* src_lo, const int* src_channels,
+                      const void* w_hi, const void* w_lo, const float* bias, const float* residual, float* out,
+                      void* out_hi, void* out_lo, int n, int h, int w, int cout, int groups, float leaky_slope, int ksize,
+                      int stride, int pad, void* stream) {
+  if (!src_hi || !src_lo || !src_channels || !w_hi || !w_lo) { set_error("e2f_conv2d_bf16x3: null pointer"); return E2F_ERR_BAD_ARG; }
+  if ((!out && !out_hi) || (!out_hi) != (!out_lo)) { set_error("e2f_conv2d_bf16x3: need out and/or both of out_hi/out_lo"); return E2F_ERR_BAD_ARG; }
+  if (out_hi && cout % 8) { set_error("e2f_conv2d_bf16x3: split output needs Cout %% 8 == 0"); return E2F_ERR_UNSUPPORTED; }
+  if (nsrc < 1 || nsrc > 4) { set_error("e2f_conv2d_bf16x3: nsrc=%d (1..4 supported)", nsrc); return E2F_ERR_UNSUPPORTED; }
+  if (n < 0 || h <= 0 || w <= 0 || cout <= 0 || groups <= 0 || cout % groups) { set_error("e2f_conv2d_bf16x3: bad shape n=%d h=%d w=%d cout=%d groups=%d", n, h, w, cout, groups); return E2F_ERR_BAD_ARG; }
+  if (ksize < 1 || ksize > 7 || (stride != 1 && stride != 2) || pad < 0 || h + 2 * pad < ksize || w + 2 * pad < ksize) { set_error("e2f_conv2d_bf16x3: unsupported geometry k=%d stride=%d pad=%d", ksize, stride, pad); return E2F_ERR_UNSUPPORTED; }
+  for (int i = 0; i < nsrc; ++i) {
+    if (!src_hi[i] || !src_lo[i]) { set_error("e2f_conv2d_bf16x3: null source %d", i); return E2F_ERR_BAD_ARG; }
+    if (src_channels[i] <= 0 || src_channels[i] % 8 || src_channels[i] % groups) { set_error("e2f_conv2d_bf16x3: source %d has %d channels (needs a multiple of 8 and of groups)", i, src_channels[i]); return E2F_ERR_UNSUPPORTED; }
+    if (!aligned(src_hi[i], 16) || !aligned(src_lo[i], 16)) { set_error("e2f_conv2d_bf16x3: 16-byte alignment required"); return E2F_ERR_ALIGNMENT; }
+  }
+  if (!aligned(w_hi, 16) || !aligned(w_lo, 16) || (out && !aligned(out, 16)) || (out_hi && (!aligned(out_hi, 16) || !aligned(out_lo, 16))) || (residual && !aligned(residual, 16))) { set_error("e2f_conv2d_bf16x3: 16-byte alignment required"); return E2F_ERR_ALIGNMENT; }
+  if (n == 0) return 0;
+  return finish(launch_conv3x3(nsrc, src_hi, src_lo, src_channels, w_hi, w_lo, bias, residual, out, out_hi, out_lo, n, h, w, cout, groups, leaky_slope, ksize, stride, pad, static_cast<cudaStream_t>(stream)), "e2f_conv2d_bf16x3");
+}
+
 int e2f_conv3x3_bf16x3(int nsrc, const void* const* src_hi, const void* const* src_lo, const int* src_channels,
                        const void* w_hi, const void* w_lo, const float* bias, const float* residual, float* out,
                        void* out_hi, void* out_lo, int n, int h, int w, int cout, int groups, float leaky_slope,
                        void* stream) {
-  if (!src_hi || !src_lo || !src_channels || !w_hi || !w_lo) { set_error("e2f_conv3x3_bf16x3: null pointer"); return E2F_ERR_BAD_ARG; }
-  if ((!out && !out_hi) || (!out_hi) != (!out_lo)) { set_error("e2f_conv3x3_bf16x3: need out and/or both of out_hi/out_lo"); return E2F_ERR_BAD_ARG; }
-  if (out_hi && cout % 8) { set_error("e2f_conv3x3_bf16x3: split output needs Cout %% 8 == 0"); return E2F_ERR_UNSUPPORTED; }
-  if (nsrc < 1 || nsrc > 4) { set_error("e2f_conv3x3_bf16x3: nsrc=%d (1..4 supported)", nsrc); return E2F_ERR_UNSUPPORTED; }
-  if (n < 0 || h <= 0 || w <= 0 || cout <= 0 || groups <= 0 || cout % groups) { set_error("e2f_conv3x3_bf16x3: bad shape n=%d h=%d w=%d cout=%d groups=%d", n, h, w, cout, groups); return E2F_ERR_BAD_ARG; }
-  for (int i = 0; i < nsrc; ++i) {
-    if (!src_hi[i] || !src_lo[i]) { set_error("e2f_conv3x3_bf16x3: null source %d", i); return E2F_ERR_BAD_ARG; }
-    if (src_channels[i] <= 0 || src_channels[i] % 8 || src_channels[i] % groups) { set_error("e2f_conv3x3_bf16x3: source %d has %d channels (needs a multiple of 8 and of groups)", i, src_channels[i]); return E2F_ERR_UNSUPPORTED; }
-    if (!aligned(src_hi[i], 16) || !aligned(src_lo[i], 16)) { set_error("e2f_conv3x3_bf16x3: 16-byte alignment required"); return E2F_ERR_ALIGNMENT; }
-  }
-  if (!aligned(w_hi, 16) || !aligned(w_lo, 16) || (out && !aligned(out, 16)) || (out_hi && (!aligned(out_hi, 16) || !aligned(out_lo, 16))) || (residual && !aligned(residual, 16))) { set_error("e2f_conv3x3_bf16x3: 16-byte alignment required"); return E2F_ERR_ALIGNMENT; }
-  if (n == 0) return 0;
-  return finish(launch_conv3x3(nsrc, src_hi, src_lo, src_channels, w_hi, w_lo, bias, residual, out, out_hi, out_lo, n, h, w, cout, groups, leaky_slope, static_cast<cudaStream_t>(stream)), "e2f_conv3x3_bf16x3");
+  return e2f_conv2d_bf16x3(nsrc, src_hi, src_lo, src_channels, w_hi, w_lo, bias, residual, out, out_hi, out_lo, n, h, w,
+                           cout, groups, leaky_slope, 3, 1, 1, stream);
 }
 
 }  // extern "C"

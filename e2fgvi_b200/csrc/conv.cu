@@ -42,7 +42,8 @@ struct Maps {
 };
 
 struct Params {
-  int N, H, W, Cout, groups;
+  int N, H, W, Cout, groups;     // H, W: OUTPUT spatial size
+  int ks, stride, pad;           // square kernel size (3 or 7), stride (1 or 2), zero padding
   int nsrc;
   int cig[MAX_SRC];        // channels per group of each source
   int chunks[MAX_SRC];     // ceil(cig / 64)
@@ -105,7 +106,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv3x3_kernel(const __grid_consta
   const int cog = p.Cout / p.groups;
   const int tiles_ng = (cog + BN - 1) / BN;
   const int num_tiles = p.N * tiles_y * tiles_x * p.groups * tiles_ng;
-  const int num_kb = 9 * p.chunks_total;
+  const int num_kb = p.ks * p.ks * p.chunks_total;
 
   if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
   if (tid == 0) {
@@ -137,8 +138,10 @@ __global__ void __launch_bounds__(THREADS, 1) conv3x3_kernel(const __grid_consta
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const TileCoord t = decode_tile<BN>(tile, p, tiles_y, tiles_x, tiles_ng);
         int kb = 0;
-        for (int tap = 0; tap < 9; ++tap) {
-          const int yy = t.y0 + tap / 3 - 1, xx = t.x0 + tap % 3 - 1;
+        const int taps = p.ks * p.ks;
+        for (int tap = 0; tap < taps; ++tap) {
+          // input coordinate of the tile's first output pixel for this tap (TMA steps by `stride` inside the box)
+          const int yy = t.y0 * p.stride - p.pad + tap / p.ks, xx = t.x0 * p.stride - p.pad + tap % p.ks;
           for (int s = 0; s < p.nsrc; ++s) {
             const int c_base = t.g * p.cig[s];
             for (int j = 0; j < p.chunks[s]; ++j, ++kb, ++it) {
@@ -302,9 +305,10 @@ static int num_sms() {
 
 int launch_conv3x3(int nsrc, const void* const* src_hi, const void* const* src_lo, const int* src_channels,
                    const void* w_hi, const void* w_lo, const float* bias, const float* residual, float* out,
-                   void* out_hi, void* out_lo, int n, int h, int w, int cout, int groups, float slope,
-                   cudaStream_t stream) {
+                   void* out_hi, void* out_lo, int n, int h_in, int w_in, int cout, int groups, float slope, int ks,
+                   int stride, int pad, cudaStream_t stream) {
   using namespace conv;
+  const int h = (h_in + 2 * pad - ks) / stride + 1, w = (w_in + 2 * pad - ks) / stride + 1;   // output size
   EncodeTiledFn enc = get_encode();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled is not available from the driver");
@@ -314,35 +318,37 @@ int launch_conv3x3(int nsrc, const void* const* src_hi, const void* const* src_l
   Maps maps;
   Params p;
   p.N = n; p.H = h; p.W = w; p.Cout = cout; p.groups = groups; p.nsrc = nsrc;
+  p.ks = ks; p.stride = stride; p.pad = pad;
   p.slope = slope; p.bias = bias; p.residual = residual; p.out = out;
   p.out_hi = static_cast<__nv_bfloat16*>(out_hi); p.out_lo = static_cast<__nv_bfloat16*>(out_lo);
   p.chunks_total = 0;
   for (int i = 0; i < MAX_SRC; ++i) p.cig[i] = p.chunks[i] = 0;
-  const cuuint32_t estr4[4] = {1, 1, 1, 1};
+  const cuuint32_t estr4[4] = {1, static_cast<cuuint32_t>(stride), static_cast<cuuint32_t>(stride), 1};
   for (int i = 0; i < nsrc; ++i) {
     const int c = src_channels[i];
     p.cig[i] = c / groups;
     p.chunks[i] = (p.cig[i] + BK - 1) / BK;
     p.chunks_total += p.chunks[i];
-    const cuuint64_t dims[4] = {static_cast<cuuint64_t>(c), static_cast<cuuint64_t>(w), static_cast<cuuint64_t>(h),
-                                static_cast<cuuint64_t>(n)};
-    const cuuint64_t strides[3] = {static_cast<cuuint64_t>(c) * 2, static_cast<cuuint64_t>(w) * c * 2,
-                                   static_cast<cuuint64_t>(h) * w * c * 2};
-    const cuuint32_t box[4] = {BK, TILE_W, TILE_H, 1};
+    const cuuint64_t dims[4] = {static_cast<cuuint64_t>(c), static_cast<cuuint64_t>(w_in),
+                                static_cast<cuuint64_t>(h_in), static_cast<cuuint64_t>(n)};
+    const cuuint64_t strides[3] = {static_cast<cuuint64_t>(c) * 2, static_cast<cuuint64_t>(w_in) * c * 2,
+                                   static_cast<cuuint64_t>(h_in) * w_in * c * 2};
+    // the box spans TILE*stride input elements and is traversed with elementStrides = stride: TILE elements land
+    const cuuint32_t box[4] = {BK, static_cast<cuuint32_t>(TILE_W * stride), static_cast<cuuint32_t>(TILE_H * stride), 1};
     for (int part = 0; part < 2; ++part) {
       CUresult r = enc(part ? &maps.a_lo[i] : &maps.a_hi[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4,
                        const_cast<void*>(part ? src_lo[i] : src_hi[i]), dims, strides, box, estr4,
                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       if (r != CUDA_SUCCESS) {
-        set_error("conv3x3: cuTensorMapEncodeTiled(source %d) failed with CUresult %d (c=%d w=%d h=%d n=%d)", i,
-                  static_cast<int>(r), c, w, h, n);
+        set_error("conv2d: cuTensorMapEncodeTiled(source %d) failed with CUresult %d (c=%d w=%d h=%d n=%d)", i,
+                  static_cast<int>(r), c, w_in, h_in, n);
         return -4;
       }
     }
   }
   {
-    const int kpad = 9 * p.chunks_total * BK;
+    const int kpad = ks * ks * p.chunks_total * BK;
     const cuuint64_t dims[2] = {static_cast<cuuint64_t>(kpad), static_cast<cuuint64_t>(cout)};
     const cuuint64_t strides[1] = {static_cast<cuuint64_t>(kpad) * 2};
     const cuuint32_t box[2] = {BK, static_cast<cuuint32_t>(bn)};

@@ -68,27 +68,22 @@ class Encoder(nn.Module):
         self.layers = nn.ModuleList(layers)
 
     def forward(self, x):
-        """Stride-1 convs run on the tcgen05 implicit-GEMM kernel with LeakyReLU fused; the group-wise
-        concatenation of e2fgvi.py:103-108 is expressed as two TMA sources, never materialised.  The two stride-2
-        convs (1.8 % of the encoder FLOPs) stay on cuDNN."""
-        out = x.contiguous(memory_format=torch.channels_last)
+        """All nine convs run on the tcgen05 implicit-GEMM kernel (stride 2 via TMA element strides) with LeakyReLU
+        fused and the bf16 split operand handed from epilogue to the next conv; the group-wise concatenation of
+        e2fgvi.py:103-108 is expressed as two TMA sources, never materialised."""
+        out = x
         x0 = None
         last = len(_ENC) - 1
         for k, (_, _, stride, _) in enumerate(_ENC):
             conv = self.layers[2 * k]
-            if stride != 1:
-                out = F.leaky_relu(conv(out), 0.2)
-                continue
-            # conv -> conv chains hand over the bf16 split operand written by the epilogue ("split"); fp32 is only
-            # materialised where a non-conv consumer needs it (the stride-2 cuDNN conv after k=1, the final features)
-            mode = "f32" if (k == last or _ENC[k + 1][2] != 1) else "split"
+            mode = "f32" if k == last else "split"
             if k == 4:
                 x0 = out
             if k > 4:
                 out = ops.conv3x3([x0, out], conv.weight, conv.bias, groups=self.group[k - 4], negative_slope=0.2,
                                   out=mode)
             else:
-                out = ops.conv3x3([out], conv.weight, conv.bias, negative_slope=0.2, out=mode)
+                out = ops.conv3x3([out], conv.weight, conv.bias, negative_slope=0.2, out=mode, stride=stride)
         return out
 
 

@@ -39,12 +39,13 @@ class SPyNetBasicModule(nn.Module):
         self.basic_module = nn.Sequential(*[_ConvHolder(ci, co) for ci, co in _LEVEL_CONVS])
 
     def forward(self, tensor_input):
+        """Five 7x7 convs on the tcgen05 implicit-GEMM kernel (k x k taps are just more TMA boxes), ReLU fused
+        (LeakyReLU with slope 0), the bf16 split operand handed from conv to conv."""
         y = tensor_input
         last = len(self.basic_module) - 1
         for i, holder in enumerate(self.basic_module):
-            y = holder.conv(y)
-            if i != last:
-                y = F.relu(y, inplace=True)
+            y = ops.conv3x3([y], holder.conv.weight, holder.conv.bias, negative_slope=1.0 if i == last else 0.0,
+                            out="f32" if i == last else "split")
         return y
 
 
@@ -85,5 +86,4 @@ class SPyNet(nn.Module):
         supp = F.interpolate(supp, size=(h_up, w_up), mode="bilinear", align_corners=False)
         flow = F.interpolate(self.compute_flow(ref, supp), size=(h, w), mode="bilinear", align_corners=False)
         # rescale u by w/w_up and v by h/h_up (flow_comp.py:164-167)
-        scale = flow.new_tensor([float(w) / float(w_up), float(h) / float(h_up)]).view(1, 2, 1, 1)
-        return flow * scale
+        return torch.stack((flow[:, 0] * (float(w) / float(w_up)), flow[:, 1] * (float(h) / float(h_up))), dim=1)

@@ -428,21 +428,22 @@ def pack_conv3x3_weight(weight, src_channels, groups=1):
     tap-major, then source, then 64-channel chunk; the group-local input channel axis is the concatenation of the
     sources' per-group slices (exactly the channel order of the torch.cat the reference performs)."""
     cout, cin_g, kh, kw = weight.shape
-    assert (kh, kw) == (3, 3)
+    assert kh == kw
+    taps = kh * kw
     cig = [c // groups for c in src_channels]
     assert sum(cig) == cin_g, (src_channels, groups, cin_g)
     chunks = [(c + 63) // 64 for c in cig]
     T = sum(chunks)
     w = weight.detach().float()
-    packed = torch.zeros((cout, 9, T, 64), dtype=torch.float32, device=weight.device)
+    packed = torch.zeros((cout, taps, T, 64), dtype=torch.float32, device=weight.device)
     off, base = 0, 0
     for c, nch in zip(cig, chunks):
         for j in range(nch):
             cc = min(64, c - 64 * j)
-            packed[:, :, base + j, :cc] = w[:, off + 64 * j: off + 64 * j + cc].reshape(cout, cc, 9).transpose(1, 2)
+            packed[:, :, base + j, :cc] = w[:, off + 64 * j: off + 64 * j + cc].reshape(cout, cc, taps).transpose(1, 2)
         off += c
         base += nch
-    return split_bf16(packed.view(cout, 9 * T * 64))
+    return split_bf16(packed.view(cout, taps * T * 64))
 
 
 _CONV_PACKS = {}  # (id(Parameter), src channels, groups) -> (weakref, tag, hi, lo)
@@ -461,12 +462,16 @@ def _packed_conv_weight(weight, src_channels, groups):
     return hit[2], hit[3]
 
 
-def conv3x3(sources, weight, bias=None, groups=1, negative_slope=1.0, residual=None, out="f32"):
+def conv3x3(sources, weight, bias=None, groups=1, negative_slope=1.0, residual=None, out="f32", stride=1,
+            padding=None):
     """``leaky_relu(F.conv2d(torch.cat(sources, 1) [group-wise for groups > 1], weight, bias, 1, 1, 1, groups),
     negative_slope) (+ residual)`` as one tcgen05 implicit-GEMM launch; the cat is never built.
 
+    Also serves square k x k kernels (k = 3, 7) with stride 1 / 2 (``padding`` defaults to k // 2): the stride-2
+    encoder convs and SPyNet's 7x7 convs (negative_slope = 0 is ReLU).
+
     sources: list of (N,C_i,H,W) fp32 tensors or ``SplitNHWC``; weight: the nn.Conv2d parameter (Cout, sum C_i / G,
-    3, 3).  out = "f32": (N,Cout,H,W) fp32 channels_last tensor; "split": a ``SplitNHWC`` (the bf16 operand pair of a
+    k, k).  out = "f32": (N,Cout,H,W) fp32 channels_last tensor; "split": a ``SplitNHWC`` (the bf16 operand pair of a
     following conv3x3, written by the epilogue, no fp32 round trip); "both": (tensor, SplitNHWC)."""
     splits = [split_nhwc(s) for s in (sources if isinstance(sources, (list, tuple)) else [sources])]
     _need_cuda(weight, bias, residual)
@@ -478,7 +483,10 @@ def conv3x3(sources, weight, bias=None, groups=1, negative_slope=1.0, residual=N
     padded_channels = [s.hi.shape[-1] for s in splits]
     if groups != 1 and true_channels != padded_channels:
         raise NotImplementedError("grouped conv3x3 needs channel counts that are multiples of 8")
-    cout = weight.shape[0]
+    cout, ks = weight.shape[0], weight.shape[2]
+    pad = ks // 2 if padding is None else padding
+    h_in, w_in = h, w
+    h, w = (h_in + 2 * pad - ks) // stride + 1, (w_in + 2 * pad - ks) // stride + 1
     w_hi, w_lo = _packed_conv_weight(weight, true_channels, groups)
     b32 = None if bias is None else bias.detach().float().contiguous()
     res = None
@@ -495,15 +503,15 @@ def conv3x3(sources, weight, bias=None, groups=1, negative_slope=1.0, residual=N
     hi_arr = (_lib._vp * k)(*[s.hi.data_ptr() for s in splits])
     lo_arr = (_lib._vp * k)(*[s.lo.data_ptr() for s in splits])
     ch_arr = (_lib._i * k)(*padded_channels)
-    with _timed("conv3x3_bf16x3", 2.0 * n * h * w * cout * weight.shape[1] * 9):
-        st = _lib.load().e2f_conv3x3_bf16x3(k, hi_arr, lo_arr, ch_arr, w_hi.data_ptr(), w_lo.data_ptr(),
-                                            None if b32 is None else b32.data_ptr(),
-                                            None if res is None else res.data_ptr(),
-                                            None if o32 is None else o32.data_ptr(),
-                                            None if ohi is None else ohi.data_ptr(),
-                                            None if olo is None else olo.data_ptr(), n, h, w, cout,
-                                            groups, float(negative_slope), _stream())
-    _lib.check(st, "e2f_conv3x3_bf16x3")
+    with _timed("conv3x3_bf16x3", 2.0 * n * h * w * cout * weight.shape[1] * ks * ks):
+        st = _lib.load().e2f_conv2d_bf16x3(k, hi_arr, lo_arr, ch_arr, w_hi.data_ptr(), w_lo.data_ptr(),
+                                           None if b32 is None else b32.data_ptr(),
+                                           None if res is None else res.data_ptr(),
+                                           None if o32 is None else o32.data_ptr(),
+                                           None if ohi is None else ohi.data_ptr(),
+                                           None if olo is None else olo.data_ptr(), n, h_in, w_in, cout,
+                                           groups, float(negative_slope), ks, stride, pad, _stream())
+    _lib.check(st, "e2f_conv2d_bf16x3")
     t32 = o32.permute(0, 3, 1, 2) if want_f32 else None
     sp = SplitNHWC(ohi, olo, (n, cout, h, w)) if want_split else None
     return t32 if out == "f32" else sp if out == "split" else (t32, sp)

@@ -158,6 +158,15 @@ int e2f_conv3x3_bf16x3(int nsrc, const void* const* src_hi, const void* const* s
                        void* out_hi, void* out_lo, int n, int h, int w, int cout, int groups, float leaky_slope,
                        void* stream);
 
+/* Generalisation of e2f_conv3x3_bf16x3 to square k x k kernels (k = 3, 7), stride 1 or 2 and any zero padding:
+ * the stride-2 encoder convs (e2fgvi.py:76,80) and SPyNet's 7x7 convs (flow_comp.py:181-215; leaky_slope = 0 is
+ * ReLU).  h, w are the INPUT spatial size; outputs are [N][Ho][Wo][Cout] with Ho = (h + 2 pad - k)/stride + 1.
+ * Weights: [Cout][k*k * T * 64] in the same tap-major order. */
+int e2f_conv2d_bf16x3(int nsrc, const void* const* src_hi, const void* const* src_lo, const int* src_channels,
+                      const void* w_hi, const void* w_lo, const float* bias, const float* residual, float* out,
+                      void* out_hi, void* out_lo, int n, int h, int w, int cout, int groups, float leaky_slope,
+                      int ksize, int stride, int pad, void* stream);
+
 /* Number of kernel launches issued through this library since load (all threads); used by bench.py's
  * "gpu_launches" accounting. */
 int64_t e2f_launch_count(void);

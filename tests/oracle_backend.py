@@ -66,7 +66,8 @@ def _layer_norm(x, weight, bias, eps=1e-5, out="f32"):
     return (y, y) if out == "both" else y
 
 
-def _conv3x3(sources, weight, bias=None, groups=1, negative_slope=1.0, residual=None, out="f32"):
+def _conv3x3(sources, weight, bias=None, groups=1, negative_slope=1.0, residual=None, out="f32", stride=1,
+             padding=None):
     F = torch.nn.functional
     srcs = sources if isinstance(sources, (list, tuple)) else [sources]
     if groups == 1:
@@ -74,7 +75,8 @@ def _conv3x3(sources, weight, bias=None, groups=1, negative_slope=1.0, residual=
     else:  # group-wise concatenation (e2fgvi.py:103-108)
         n, _, h, w = srcs[0].shape
         x = torch.cat([s.reshape(n, groups, -1, h, w) for s in srcs], 2).reshape(n, -1, h, w)
-    y = F.leaky_relu(F.conv2d(x, weight, bias, 1, 1, 1, groups), negative_slope)
+    pad = weight.shape[2] // 2 if padding is None else padding
+    y = F.leaky_relu(F.conv2d(x, weight, bias, stride, pad, 1, groups), negative_slope)
     y = y if residual is None else y + residual
     return (y, y) if out == "both" else y
 

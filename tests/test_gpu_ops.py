@@ -360,3 +360,26 @@ def test_deform_align_fused_grouped_layout(cuda):
     ref = ops.deform_align_fused(torch.cat([a, b], 1), head, f1, f2, wp, bias, 16, 10.0)
     got = ops.deform_align_fused(ops.dcn_pack_input(a, b), head, f1, f2, wp, bias, 16, 10.0)
     assert torch.equal(ref, got)          # identical arithmetic, only the addressing differs
+
+
+@pytest.mark.parametrize("case", [
+    dict(n=2, h=60, w=108, cin=64, cout=128, ks=3, stride=2),      # encoder conv 2 (stride 2)
+    dict(n=1, h=48, w=88, cin=3, cout=64, ks=3, stride=2),         # encoder conv 0: 3 input channels, stride 2
+    dict(n=1, h=17, w=23, cin=8, cout=16, ks=3, stride=2),         # odd sizes with stride 2
+    dict(n=2, h=32, w=64, cin=8, cout=32, ks=7, stride=1),         # SPyNet level conv 0 (7x7)
+    dict(n=1, h=4, w=8, cin=32, cout=64, ks=7, stride=1),          # SPyNet coarse level (image smaller than a tile)
+    dict(n=3, h=2, w=4, cin=16, cout=2, ks=7, stride=1),           # SPyNet coarsest level, 2 output channels
+])
+def test_conv2d_kxk_stride(cuda, case):
+    F = torch.nn.functional
+    g = torch.Generator().manual_seed(52)
+    n, h, w, cin, cout, ks, stride = (case[k] for k in ("n", "h", "w", "cin", "cout", "ks", "stride"))
+    x = torch.randn(n, cin, h, w, generator=g)
+    weight = torch.nn.Parameter(torch.randn(cout, cin, ks, ks, generator=g) / (ks * ks * cin) ** 0.5)
+    bias = torch.randn(cout, generator=g) * 0.1
+    want = F.relu(F.conv2d(x.double(), weight.detach().double(), bias.double(), stride, ks // 2))
+    wd = torch.nn.Parameter(weight.detach().to(cuda))
+    got = ops.conv3x3([x.to(cuda).contiguous(memory_format=torch.channels_last)], wd, bias.to(cuda),
+                      negative_slope=0.0, stride=stride)
+    assert got.shape == want.shape, (got.shape, want.shape)
+    assert _rel(got.cpu(), want) < 5e-5, _rel(got.cpu(), want)
