@@ -252,6 +252,23 @@ def main():
         g1.record()
         sync()
         ms_b1 = g0.elapsed_time(g1) / 5
+        # the same single clip replayed from a CUDA graph (launch-bound case)
+        ms_b1_graph = None
+        try:
+            from e2fgvi_b200.graph import GraphedGenerator
+            graphed = GraphedGenerator(model, one, L_T)
+            for _ in range(3):
+                graphed(one)
+            sync()
+            h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            h0.record()
+            for _ in range(10):
+                graphed(one)
+            h1.record()
+            sync()
+            ms_b1_graph = h0.elapsed_time(h1) / 10
+        except Exception as exc:      # reported, never fatal for the headline numbers
+            log(f"CUDA-graph latency run failed: {exc!r}")
 
     t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
     if world > 1:
@@ -326,6 +343,8 @@ def main():
                     "d2h_bytes_per_step": B * T * 3 * H * W * 4 * world, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches, "clocks": clocks, "roofline": roof, "roofline_kernels": kernels,
             "cpu_baseline": cpu, "latency_b1_ms": ms_b1, "fps_b1": T / (ms_b1 * 1e-3),
+            "latency_b1_cuda_graph_ms": ms_b1_graph,
+            "fps_b1_cuda_graph": None if not ms_b1_graph else T / (ms_b1_graph * 1e-3),
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -69,3 +69,15 @@ def test_reference_operator_goldens(cuda):
         got = attn([wa["x"].to(cuda), wa["pooled"].to(cuda)], [None, None])
     rel = (got.cpu() - wa["out"]).abs().max().item() / wa["out"].abs().max().item()
     assert got.shape == wa["out"].shape and rel < 2e-3, rel
+
+
+def test_cuda_graph_replay_matches_eager(cuda):
+    from e2fgvi_b200.graph import GraphedGenerator
+    model = _model(True, "stress", 0, cuda)
+    x1 = synth_frames(1, 4, 120, 216, seed=5).to(cuda)
+    x2 = synth_frames(1, 4, 120, 216, seed=6).to(cuda)
+    g = GraphedGenerator(model, x1, 3)
+    with torch.no_grad():
+        want, _ = model(x2, 3)
+    got, _ = g(x2)
+    assert torch.equal(got, want)          # same kernels, same order: bit-identical
