@@ -103,6 +103,114 @@ __global__ void __launch_bounds__(256) t2t_unfold733_kernel(const float* __restr
   }
 }
 
+// Fused fold -> / fold(ones) -> unfold -> GELU of the fusion feed-forward (tfocal_transformer.py:89-96) for the 7/3/3
+// geometry: the folded image never goes to HBM.  One block per (CC-channel chunk, band of TR token rows, image):
+//   1. the CC*49 values of every token in rows [ty0-2, ty0+TR+1] are read ONCE, fully coalesced (float4), and added
+//      into the band's folded image in shared memory.  Tokens are visited in 9 phases (ty mod 3, tx mod 3): patches
+//      of one phase are disjoint (stride 3 * 3 >= 7), so plain += suffices — no atomics;
+//   2. every pixel is divided by its patch count and passed through GELU once;
+//   3. the TR x FW tokens of the band are written as coalesced runs (bf16 hi/lo operand pair and/or fp32).
+// Algorithmic bytes: tokens in (x (TR+4)/TR halo re-read, served by L2) + tokens out.
+template <bool GELU, int CC>
+__global__ void __launch_bounds__(256) t2t_fold_unfold733_kernel(const float* __restrict__ tin, float* __restrict__ tok,
+                                                                 __nv_bfloat16* __restrict__ tok_hi,
+                                                                 __nv_bfloat16* __restrict__ tok_lo, int C, int H,
+                                                                 int W, int FH, int FW, int TR) {
+  extern __shared__ float simg[];                  // [CC][ROWS][WP], x padded by 3 on both sides
+  constexpr int RUN4 = CC * 49 / 4;
+  const int WP = W + 6, ROWS = 3 * TR + 4;
+  const int c0 = blockIdx.x * CC, ty0 = blockIdx.y * TR;
+  const long long bt = blockIdx.z;
+  const int tr = min(TR, FH - ty0);
+  const int ybase = 3 * ty0 - 3;                   // image row held by smem row 0
+  const int CK = C * 49;
+  for (int i = threadIdx.x; i < CC * ROWS * WP; i += blockDim.x) simg[i] = 0.f;
+  // thread -> fixed float4 slot q4 of a token's CC*49 run, so the (channel, ky, kx) decode happens once per thread:
+  // RUN4 = 49 slots x TSUB tokens in flight per pass (245 of 256 threads active)
+  constexpr int TSUB = 256 / RUN4;
+  const int q4 = threadIdx.x % RUN4, tsub = threadIdx.x / RUN4;
+  const bool active = tsub < TSUB;
+  int off[4], kyv[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const int q = q4 * 4 + e;
+    const int cc = q / 49, kk = q - cc * 49;
+    kyv[e] = kk / 7;
+    off[e] = (cc * ROWS + kyv[e]) * WP + (kk - kyv[e] * 7);
+  }
+  __syncthreads();
+  const int tin_lo = max(0, ty0 - 2), tin_hi = min(FH - 1, ty0 + tr + 1);
+  const float* src = tin + bt * FH * FW * static_cast<long long>(CK) + c0 * 49;
+  for (int phase = 0; phase < 9; ++phase) {
+    const int a = phase / 3, b = phase - 3 * a;
+    const int first_ty = tin_lo + (a - tin_lo % 3 + 3) % 3;
+    const int nty = first_ty <= tin_hi ? (tin_hi - first_ty) / 3 + 1 : 0;
+    const int ntx = b < FW ? (FW - 1 - b) / 3 + 1 : 0;
+    const int ntok = active ? nty * ntx : 0;
+    // U tokens per thread in flight: all global loads of a batch are issued before the first shared-memory update
+    constexpr int U = 6;
+    for (int tt = tsub; tt < ntok; tt += TSUB * U) {
+      float4 v4[U];
+      int base[U], r0[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int t = tt + u * TSUB;
+        if (t < ntok) {
+          const int tyi = t / ntx, txi = t - tyi * ntx;
+          const int ty = first_ty + 3 * tyi, tx = b + 3 * txi;
+          v4[u] = __ldg(reinterpret_cast<const float4*>(src + static_cast<long long>(ty * FW + tx) * CK) + q4);
+          r0[u] = 3 * ty - 3 - ybase;              // smem row of the patch's first row (negative above the band)
+          base[u] = r0[u] * WP + 3 * tx;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (tt + u * TSUB < ntok) {
+          const float v[4] = {v4[u].x, v4[u].y, v4[u].z, v4[u].w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int r = r0[u] + kyv[e];
+            if (r >= 0 && r < ROWS) simg[base[u] + off[e]] += v[e];
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+  // patch count of a pixel = (#token rows covering y) * (#token columns covering x); padding -> 0
+  for (int i = threadIdx.x; i < CC * ROWS * WP; i += blockDim.x) {
+    const int xx = i % WP, r = (i / WP) % ROWS;
+    const int y = ybase + r, x = xx - 3;
+    float v = 0.f;
+    if (y >= 0 && y < H && x >= 0 && x < W) {
+      const int ny = min(FH - 1, (y + 3) / 3) - max(0, (y - 1) / 3) + 1;     // ty in [ceil((y-3)/3), floor((y+3)/3)]
+      const int nx = min(FW - 1, (x + 3) / 3) - max(0, (x - 1) / 3) + 1;
+      v = simg[i] / static_cast<float>(ny * nx);
+      if (GELU) v = gelu_exact(v);
+    }
+    simg[i] = v;
+  }
+  __syncthreads();
+  const long long tok0 = (bt * FH + ty0) * static_cast<long long>(FW);
+  const int nout = active ? tr * FW : 0;
+  for (int t = tsub; t < nout; t += TSUB) {
+    const int tyl = t / FW, tx = t - tyl * FW;
+    const int base = 3 * tyl * WP + 3 * tx, rem = q4 * 4;
+    float v[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) v[e] = simg[base + off[e]];
+    const long long dst = (tok0 + t) * CK + c0 * 49 + rem;
+    if (tok) *reinterpret_cast<float4*>(tok + dst) = make_float4(v[0], v[1], v[2], v[3]);
+    if (tok_hi) {
+      const __nv_bfloat162 h0 = __floats2bfloat162_rn(v[0], v[1]), h1 = __floats2bfloat162_rn(v[2], v[3]);
+      const float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
+      const __nv_bfloat162 l0 = __floats2bfloat162_rn(v[0] - f0.x, v[1] - f0.y), l1 = __floats2bfloat162_rn(v[2] - f1.x, v[3] - f1.y);
+      *reinterpret_cast<uint2*>(tok_hi + dst) = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
+      *reinterpret_cast<uint2*>(tok_lo + dst) = make_uint2(*reinterpret_cast<const uint32_t*>(&l0), *reinterpret_cast<const uint32_t*>(&l1));
+    }
+  }
+}
+
 // one thread per image element (c, y, x): sums the <= ceil(K/S)^2 patch entries that cover it
 template <int KC, int SC, int PC>
 __global__ void __launch_bounds__(256) t2t_fold_kernel(const float* __restrict__ tok, const float* __restrict__ bias,
@@ -174,6 +282,42 @@ int launch_t2t_unfold(const float* img, float* tok, void* tok_hi_v, void* tok_lo
     t2t_unfold_kernel<true, 0, 0, 0><<<blocks, threads, 0, stream>>>(img, tok, tok_hi, tok_lo, bt, c, h, w, k, s, p, fh, fw);
   else
     t2t_unfold_kernel<false, 0, 0, 0><<<blocks, threads, 0, stream>>>(img, tok, tok_hi, tok_lo, bt, c, h, w, k, s, p, fh, fw);
+  count_launch();
+  return static_cast<int>(cudaGetLastError());
+}
+
+// Fused fold/normalise/unfold(/GELU).  Returns -2 (unsupported) when the geometry is not 7/3/3 or no band fits in
+// shared memory; the caller then composes launch_t2t_fold + launch_t2t_unfold.
+int launch_t2t_fold_unfold(const float* tin, float* tok, void* tok_hi, void* tok_lo, int bt, int c, int h, int w, int k,
+                           int s, int p, int gelu, cudaStream_t stream) {
+  constexpr int CC = 4;                            // 4 channels = 784-byte runs per token, 16-byte aligned
+  if (k != 7 || s != 3 || p != 3 || c % CC) return -2;
+  const int fh = (h + 2 * p - k) / s + 1, fw = (w + 2 * p - k) / s + 1;
+  if (bt == 0 || fh <= 0 || fw <= 0) return 0;
+  if (bt > 65535) return -2;
+  // band height: the tallest that keeps 3 blocks per SM; wide images (few rows fit) take up to 200 KB instead
+  const size_t row_bytes = static_cast<size_t>(CC) * (w + 6) * sizeof(float);
+  auto band_rows = [&](size_t budget) { return budget / row_bytes < 7 ? 0 : static_cast<int>((budget / row_bytes - 4) / 3); };
+  int tr = band_rows(72 * 1024);
+  if (tr < 5 && tr < fh) tr = band_rows(200 * 1024);
+  if (tr < 1) return -2;
+  tr = tr < fh ? tr : fh;
+  const int bands = (fh + tr - 1) / tr;
+  tr = (fh + bands - 1) / bands;                   // even out the bands
+  const size_t smem = row_bytes * (3 * tr + 4);
+  auto* hi = static_cast<__nv_bfloat16*>(tok_hi);
+  auto* lo = static_cast<__nv_bfloat16*>(tok_lo);
+  const dim3 grid(c / CC, bands, bt);
+  static bool cfg = false;
+  if (!cfg) {
+    cudaFuncSetAttribute(t2t_fold_unfold733_kernel<true, CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(t2t_fold_unfold733_kernel<false, CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cfg = true;
+  }
+  if (gelu)
+    t2t_fold_unfold733_kernel<true, CC><<<grid, 256, smem, stream>>>(tin, tok, hi, lo, c, h, w, fh, fw, tr);
+  else
+    t2t_fold_unfold733_kernel<false, CC><<<grid, 256, smem, stream>>>(tin, tok, hi, lo, c, h, w, fh, fw, tr);
   count_launch();
   return static_cast<int>(cudaGetLastError());
 }

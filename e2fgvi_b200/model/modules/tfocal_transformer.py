@@ -78,7 +78,7 @@ class FusionFeedForward(nn.Module):
         self.n_vecs = n_vecs
 
     def forward(self, x, output_size=None, residual=None):
-        """conv1 -> [fold / fold(ones) -> unfold -> GELU] (two fused gather kernels on the token-major layout) -> conv2
+        """conv1 -> [fold / fold(ones) -> unfold -> GELU] (one fused kernel on the token-major layout) -> conv2
         (+ residual, fused into the GEMM epilogue)."""
         p = self.t2t_params
         output_size = output_size or p.get("output_size")
@@ -86,10 +86,9 @@ class FusionFeedForward(nn.Module):
         n_vecs = f_h * f_w
         x = ops.linear(x, self.conv1[0].weight, self.conv1[0].bias)
         b, n, c = x.size()
-        img = ops.t2t_fold(x.view(-1, n_vecs, c), output_size, p["kernel_size"], p["stride"], p["padding"],
-                           normalize=True)
-        x = ops.t2t_unfold(img, p["kernel_size"], p["stride"], p["padding"], gelu=True, out="split").view(b, n, c)
-        # conv2[0] (GELU) is fused into the unfold kernel
+        # fold / fold(ones) -> unfold -> conv2[0] (GELU): one kernel, the folded image stays in shared memory
+        x = ops.t2t_fold_unfold(x.view(-1, n_vecs, c), output_size, p["kernel_size"], p["stride"], p["padding"],
+                                gelu=True, out="split").view(b, n, c)
         return ops.linear(x, self.conv2[1].weight, self.conv2[1].bias, residual=residual)
 
 

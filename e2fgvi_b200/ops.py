@@ -276,6 +276,43 @@ def t2t_unfold(img, kernel_size, stride, padding, gelu=False, out="f32"):
     return tok if out == "f32" else SplitMat(hi, lo)
 
 
+def t2t_fold_unfold(tokens, output_size, kernel_size, stride, padding, gelu=False, out="f32"):
+    """``unfold(fold(tokens) / fold(ones))`` (+ exact GELU): the middle of FusionFeedForward.forward
+    (tfocal_transformer.py:89-96) as ONE kernel for the 7/3/3 geometry — the folded image lives in shared memory only.
+    Other geometries compose ``t2t_fold(normalize=True)`` and ``t2t_unfold``.  tokens (BT, L, C*k*k) fp32 -> same
+    shape, fp32 (out="f32") or ``SplitMat`` (out="split")."""
+    _need_cuda(tokens)
+    (k, k2), (s, s2), (p, p2) = _pair(kernel_size), _pair(stride), _pair(padding)
+    if k != k2 or s != s2 or p != p2:
+        raise NotImplementedError("square kernel / stride / padding only (E2FGVI uses 7 / 3 / 3)")
+    h, w = output_size
+    tokens = tokens.contiguous().float()
+    bt, n_tok, ck = tokens.shape
+    c = ck // (k * k)
+    fh, fw = (h + 2 * p - k) // s + 1, (w + 2 * p - k) // s + 1
+    if n_tok != fh * fw or c * k * k != ck:
+        raise ValueError(f"t2t_fold_unfold: tokens {tuple(tokens.shape)} do not match output_size {output_size}")
+    fused = (k, s, p) == (7, 3, 3) and c % 4 == 0 and bt <= 65535 and 16 * (w + 6) * 7 <= 200 * 1024
+    if not fused:
+        img = t2t_fold(tokens, output_size, kernel_size, stride, padding, normalize=True)
+        return t2t_unfold(img, kernel_size, stride, padding, gelu=gelu, out=out)
+    tok = hi = lo = None
+    if out == "f32":
+        tok = torch.empty_like(tokens)
+    elif out == "split":
+        hi = torch.empty(tokens.shape, dtype=torch.bfloat16, device=tokens.device)
+        lo = torch.empty(tokens.shape, dtype=torch.bfloat16, device=tokens.device)
+    else:
+        raise ValueError("out must be 'f32' or 'split'")
+    with _timed("t2t_fold_unfold", float(tokens.numel() * 8)):
+        st = _lib.load().e2f_t2t_fold_unfold(tokens.data_ptr(), None if tok is None else tok.data_ptr(),
+                                             None if hi is None else hi.data_ptr(),
+                                             None if lo is None else lo.data_ptr(), bt, c, h, w, k, s, p,
+                                             1 if gelu else 0, _stream())
+    _lib.check(st, "e2f_t2t_fold_unfold")
+    return tok if out == "f32" else SplitMat(hi, lo)
+
+
 def upsample2x_split(x):
     """``F.interpolate(x, scale_factor=2, mode='bilinear', align_corners=True)`` (deconv.forward, e2fgvi.py:125-129)
     fused with the bf16 split: (N,C,H,W) fp32 -> ``SplitNHWC`` of (N,C,2H,2W); the upsampled fp32 tensor never exists."""
@@ -446,7 +483,32 @@ def pack_conv3x3_weight(weight, src_channels, groups=1):
     return split_bf16(packed.view(cout, taps * T * 64))
 
 
-_CONV_PACKS = {}  # (id(Parameter), src channels, groups) -> (weakref, tag, hi, lo)
+def merge_conv_groups(weight, src_channels, groups):
+    """Rewrite a grouped conv whose groups have few output channels as one with fewer, wider groups and
+    block-diagonal weights: m = largest power of two with m * Cout/G <= 64 and G % m == 0 groups are merged, so a
+    64-wide N tile and the 64-channel K chunks of every source are filled instead of padded (encoder conv 7,
+    e2fgvi.py:97: G=8 with 32 outputs and 32 + 48 inputs per group).  Returns (weight', groups')."""
+    cout, cin_g = weight.shape[0], weight.shape[1]
+    cog = cout // groups
+    m = 1
+    while groups % (2 * m) == 0 and 2 * m * cog <= 64:
+        m *= 2
+    if m == 1:
+        return weight, groups
+    cig = [c // groups for c in src_channels]
+    w = weight.detach().float()
+    merged = torch.zeros((cout, m * cin_g) + tuple(weight.shape[2:]), dtype=torch.float32, device=weight.device)
+    sub = (torch.arange(cout, device=weight.device) % (m * cog)) // cog      # position of o's group in its merge
+    off = 0
+    for c in cig:
+        for j in range(m):
+            rows = (sub == j).nonzero().flatten()
+            merged[rows, m * off + j * c: m * off + (j + 1) * c] = w[rows, off: off + c]
+        off += c
+    return merged, groups // m
+
+
+_CONV_PACKS = {}  # (id(Parameter), src channels, groups) -> (weakref, tag, hi, lo, effective groups)
 
 
 def _packed_conv_weight(weight, src_channels, groups):
@@ -454,12 +516,13 @@ def _packed_conv_weight(weight, src_channels, groups):
     tag = (weight._version, weight.data_ptr())
     hit = _CONV_PACKS.get(key)
     if hit is None or hit[0]() is not weight or hit[1] != tag:
-        hi, lo = pack_conv3x3_weight(weight, src_channels, groups)
+        w_eff, g_eff = merge_conv_groups(weight, src_channels, groups)
+        hi, lo = pack_conv3x3_weight(w_eff, src_channels, g_eff)
         if hit is None or hit[0]() is not weight:
             weakref.finalize(weight, _CONV_PACKS.pop, key, None)
-        hit = (weakref.ref(weight), tag, hi, lo)
+        hit = (weakref.ref(weight), tag, hi, lo, g_eff)
         _CONV_PACKS[key] = hit
-    return hit[2], hit[3]
+    return hit[2], hit[3], hit[4]
 
 
 def conv3x3(sources, weight, bias=None, groups=1, negative_slope=1.0, residual=None, out="f32", stride=1,
@@ -487,7 +550,7 @@ def conv3x3(sources, weight, bias=None, groups=1, negative_slope=1.0, residual=N
     pad = ks // 2 if padding is None else padding
     h_in, w_in = h, w
     h, w = (h_in + 2 * pad - ks) // stride + 1, (w_in + 2 * pad - ks) // stride + 1
-    w_hi, w_lo = _packed_conv_weight(weight, true_channels, groups)
+    w_hi, w_lo, g_eff = _packed_conv_weight(weight, true_channels, groups)
     b32 = None if bias is None else bias.detach().float().contiguous()
     res = None
     if residual is not None:
@@ -510,7 +573,7 @@ def conv3x3(sources, weight, bias=None, groups=1, negative_slope=1.0, residual=N
                                            None if o32 is None else o32.data_ptr(),
                                            None if ohi is None else ohi.data_ptr(),
                                            None if olo is None else olo.data_ptr(), n, h_in, w_in, cout,
-                                           groups, float(negative_slope), ks, stride, pad, _stream())
+                                           g_eff, float(negative_slope), ks, stride, pad, _stream())
     _lib.check(st, "e2f_conv2d_bf16x3")
     t32 = o32.permute(0, 3, 1, 2) if want_f32 else None
     sp = SplitNHWC(ohi, olo, (n, cout, h, w)) if want_split else None

@@ -116,6 +116,14 @@ int e2f_t2t_unfold(const float* img, float* tokens, void* tokens_hi, void* token
 int e2f_t2t_fold(const float* tokens, const float* bias, float* img, int bt, int c, int h, int w, int k, int stride,
                  int pad, int normalize, void* stream);
 
+/* FusionFeedForward's middle (tfocal_transformer.py:89-96) in ONE launch:
+ *   out = gelu?( unfold( fold(tokens_in) / fold(ones) ) ), tokens [BT][L][C*k*k] -> tokens [BT][L][C*k*k];
+ * the folded image stays in shared memory.  Fused for k=7, stride=3, pad=3 (the only geometry on the path); returns
+ * E2F_ERR_UNSUPPORTED otherwise, and the caller composes e2f_t2t_fold(normalize=1) + e2f_t2t_unfold.  Outputs as
+ * e2f_t2t_unfold (fp32 and/or bf16 hi/lo pair). */
+int e2f_t2t_fold_unfold(const float* tokens_in, float* tokens, void* tokens_hi, void* tokens_lo, int bt, int c, int h,
+                        int w, int k, int stride, int pad, int gelu, void* stream);
+
 /* x2 bilinear upsample, align_corners=True (F.interpolate in deconv.forward, e2fgvi.py:125-129) of an NHWC fp32
  * tensor [N][H][W][C] (C % 8 == 0), written directly as the bf16 (hi, lo) split [N][2H][2W][C] consumed by
  * e2f_conv3x3_bf16x3 — the 4x larger fp32 intermediate is never materialised. */

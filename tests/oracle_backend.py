@@ -53,6 +53,11 @@ def _fold(tokens, output_size, kernel_size, stride, padding, normalize=False, bi
     return img if bias is None else img + bias[None]
 
 
+def _fold_unfold(tokens, output_size, kernel_size, stride, padding, gelu=False, out="f32"):
+    return _unfold(_fold(tokens, output_size, kernel_size, stride, padding, normalize=True), kernel_size, stride, padding,
+                   gelu=gelu)
+
+
 def _dcn_pack_input(a, b):
     return torch.cat([a, b], 1)
 
@@ -95,10 +100,10 @@ def oracle_ops():
     saved = {n: getattr(ops, n) for n in ("flow_warp", "pack_dcn_weight", "deform_align_fused",
                                           "modulated_deform_conv2d", "focal_window_attention", "t2t_unfold",
                                           "t2t_fold", "linear", "conv3x3", "split_nhwc", "upsample2x_split",
-                                          "layer_norm", "dcn_pack_input")}
+                                          "layer_norm", "dcn_pack_input", "t2t_fold_unfold")}
     ops.flow_warp, ops.pack_dcn_weight, ops.deform_align_fused = _flow_warp, _pack, _fused
     ops.modulated_deform_conv2d, ops.focal_window_attention = _mdcn, _attention
-    ops.t2t_unfold, ops.t2t_fold, ops.linear = _unfold, _fold, _linear
+    ops.t2t_unfold, ops.t2t_fold, ops.linear, ops.t2t_fold_unfold = _unfold, _fold, _linear, _fold_unfold
     ops.conv3x3, ops.split_nhwc = _conv3x3, _split_nhwc
     ops.upsample2x_split, ops.layer_norm, ops.dcn_pack_input = _upsample, _layer_norm, _dcn_pack_input
     try:

@@ -216,6 +216,35 @@ def test_t2t_unfold_fold(cuda, shape):
     assert (got_n.cpu()[ok] - want_n[ok]).abs().max().item() < 1e-5
 
 
+@pytest.mark.parametrize("shape", [(3, 40, 60, 108), (2, 12, 30, 54), (1, 4, 7, 7), (2, 8, 61, 110), (1, 40, 135, 240),
+                                   (1, 4, 9, 1500), (1, 3, 16, 16)])
+def test_t2t_fold_unfold_fused(cuda, shape):
+    """One-kernel fold / fold(ones) -> unfold (-> GELU) against F.fold / F.unfold (tfocal_transformer.py:89-96):
+    several bands (tall images), the large-shared-memory configuration (very wide image), image sizes that leave a
+    ragged last patch, and the error for a channel count the token layout cannot hold (C*49 % 4 != 0)."""
+    F = torch.nn.functional
+    bt, c, h, w = shape
+    g = torch.Generator().manual_seed(37)
+    fh, fw = (h + 6 - 7) // 3 + 1, (w + 6 - 7) // 3 + 1
+    tok = torch.randn(bt, fh * fw, c * 49, generator=g)
+    folded = F.fold(tok.permute(0, 2, 1), (h, w), (7, 7), padding=(3, 3), stride=(3, 3))
+    ones = F.fold(torch.ones(1, 49, fh * fw), (h, w), (7, 7), padding=(3, 3), stride=(3, 3))
+    norm = torch.nan_to_num(folded / ones, nan=0.0, posinf=0.0, neginf=0.0)     # pixels no patch covers stay 0
+    want = F.unfold(norm, (7, 7), padding=(3, 3), stride=(3, 3)).permute(0, 2, 1)
+    if (c * 49) % 4:
+        with pytest.raises(RuntimeError):
+            ops.t2t_fold_unfold(tok.to(cuda), (h, w), (7, 7), (3, 3), (3, 3))
+        return
+    got = ops.t2t_fold_unfold(tok.to(cuda), (h, w), (7, 7), (3, 3), (3, 3))
+    assert (got.cpu() - want).abs().max().item() < 1e-5
+    sp = ops.t2t_fold_unfold(tok.to(cuda), (h, w), (7, 7), (3, 3), (3, 3), gelu=True, out="split")
+    assert (_join(sp).cpu() - F.gelu(want)).abs().max().item() < 5e-5
+    # agrees with the two-kernel composition it replaces
+    img = ops.t2t_fold(tok.to(cuda), (h, w), (7, 7), (3, 3), (3, 3), normalize=True)
+    two = ops.t2t_unfold(torch.nan_to_num(img, nan=0.0, posinf=0.0, neginf=0.0), (7, 7), (3, 3), (3, 3))
+    assert (got - two).abs().max().item() < 1e-5
+
+
 # ------------------------------------------------------------------------------------------ bf16x3 linear
 @pytest.mark.parametrize("case", [
     dict(m=5760, k=512, n=1536, out=torch.float16),               # attn.qkv of one clip

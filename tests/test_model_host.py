@@ -68,3 +68,29 @@ def test_forward_fails_loudly_without_gpu():
     model = net.InpaintGenerator().eval()
     with torch.no_grad(), pytest.raises(RuntimeError, match="no CPU fallback"):
         model(synth_frames(1, 3, 60, 108), 2)
+
+
+def test_merge_conv_groups_is_equivalent_grouped_conv():
+    """Block-diagonal group merging (ops.merge_conv_groups) leaves the grouped conv unchanged: checked against
+    F.conv2d on the group-wise concatenation the encoder performs (reference e2fgvi.py:103-108)."""
+    import torch.nn.functional as F
+    from e2fgvi_b200 import ops
+    torch.manual_seed(3)
+    groups, c1, c2, cout = 8, 32, 48, 32 * 8 // 8 * 2          # 8 groups, 4+6 inputs and 8 outputs per group
+    x1, x2 = torch.randn(2, c1, 6, 7), torch.randn(2, c2, 6, 7)
+    w = torch.randn(cout, (c1 + c2) // groups, 3, 3)
+
+    def group_cat(g):
+        a = x1.view(2, g, -1, 6, 7)
+        b = x2.view(2, g, -1, 6, 7)
+        return torch.cat([a, b], 2).view(2, -1, 6, 7)
+
+    want = F.conv2d(group_cat(groups), w, None, 1, 1, 1, groups)
+    merged, g2 = ops.merge_conv_groups(w, [c1, c2], groups)
+    assert g2 < groups and merged.shape[1] == w.shape[1] * (groups // g2)
+    got = F.conv2d(group_cat(g2), merged, None, 1, 1, 1, g2)
+    assert torch.allclose(got, want, atol=1e-5)
+    same, g3 = ops.merge_conv_groups(torch.randn(256, 16, 3, 3), [128], 8)   # 32 outputs per group: merge by 2
+    assert g3 == 4 and same.shape == (256, 32, 3, 3)
+    keep, g4 = ops.merge_conv_groups(torch.randn(384, 48, 3, 3), [192], 4)   # 96 per group: untouched
+    assert g4 == 4 and keep.shape == (384, 48, 3, 3)

@@ -10,6 +10,8 @@
 //   mode 5: A operand from TENSOR MEMORY (tcgen05.mma [d], [a_tmem], b_desc): A is written to TMEM columns 128.. by
 //           tcgen05.st as packed fp16 pairs (column j of lane m holds A[m][2j] (low half) | A[m][2j+1] (high half));
 //           B K-major in smem.  swap=1 tries the opposite half order.
+//   mode 6: B rows gathered by TMA tile::gather4 (4 arbitrary rows per instruction, here in bit-reversed order) into
+//           the K-major SWIZZLE_128B tile; tensor-map box {64, 1} (swap=0) or {64, 4} (swap=1).
 #include <cuda.h>
 #include <cstdio>
 #include <cstdlib>
@@ -22,7 +24,8 @@ using namespace e2f;
 constexpr int M = 128, N = 128, K = 128;
 
 __global__ void __launch_bounds__(128, 1)
-probe_kernel(const __grid_constant__ CUtensorMap tmapB, const __half* __restrict__ A,
+probe_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_constant__ CUtensorMap tmapG,
+             const __half* __restrict__ A,
              const __half* __restrict__ B, float* __restrict__ D, int mode, int swap) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -53,6 +56,24 @@ probe_kernel(const __grid_constant__ CUtensorMap tmapB, const __half* __restrict
       tma_load_2d(smem_u32(sB), &tmapB, bar_tma, 0, 0);
       tma_load_2d(smem_u32(sB) + 16384, &tmapB, bar_tma, 64, 0);
     }
+  } else if (mode == 6) {
+    if (tid == 0) {
+      mbar_arrive_expect_tx(bar_tma, 32768);
+      for (int half = 0; half < 2; ++half)
+        for (int i = 0; i < 32; ++i) {            // smem rows 4i..4i+3 <- global rows rev7(4i+j)
+          int r[4];
+          for (int j = 0; j < 4; ++j) {
+            const int n = 4 * i + j;
+            r[j] = ((n & 1) << 6) | ((n & 2) << 4) | ((n & 4) << 2) | (n & 8) | ((n & 16) >> 2) | ((n & 32) >> 4) | ((n & 64) >> 6);
+          }
+          asm volatile(
+              "cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes"
+              " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(smem_u32(sB) + half * 16384 + i * 512),
+              "l"(reinterpret_cast<uint64_t>(&tmapG)), "r"(smem_u32(bar_tma)), "r"(half * 64), "r"(r[0]), "r"(r[1]),
+              "r"(r[2]), "r"(r[3])
+              : "memory");
+        }
+    }
   } else {
     // mode 1/3/4: B is [n][k] row-major, thread n owns row n.  mode 2: B is [k][n] row-major, thread k owns row k.
     for (int c = 0; c < 16; ++c)
@@ -80,7 +101,7 @@ probe_kernel(const __grid_constant__ CUtensorMap tmapB, const __half* __restrict
     __syncthreads();
   }
   if (tid == 0) {
-    if (mode == 0) mbar_wait(bar_tma, 0);
+    if (mode == 0 || mode == 6) mbar_wait(bar_tma, 0);
     tc_fence_after_sync();
     if (mode == 5) {
       const uint32_t idesc5 = umma_idesc_f16(128, 128, 0, 0);
@@ -197,9 +218,28 @@ int main(int argc, char** argv) {
       return 2;
     }
   }
+  CUtensorMap tmapG;
+  memset(&tmapG, 0, sizeof(tmapG));
+  {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    cuuint64_t dims[2] = {K, 128};
+    cuuint64_t strides[1] = {K * 2};
+    cuuint32_t box[2] = {64, swap ? 4u : 1u};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = reinterpret_cast<EncodeTiled>(fn)(&tmapG, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, dB, dims, strides, box,
+                                                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      printf("cuTensorMapEncodeTiled (gather map) failed %d\n", (int)r);
+      return 2;
+    }
+  }
   const int smem_bytes = 65536 + 64 + 1024;
   CK(cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-  probe_kernel<<<1, 128, smem_bytes>>>(tmap, dA, dB, dD, mode, swap);
+  probe_kernel<<<1, 128, smem_bytes>>>(tmap, tmapG, dA, dB, dD, mode, swap);
   CK(cudaGetLastError());
   CK(cudaDeviceSynchronize());
   std::vector<float> hD(M * N);
@@ -210,8 +250,10 @@ int main(int argc, char** argv) {
   for (int m = 0; m < M; ++m)
     for (int n = 0; n < ncols; ++n) {
       double ref = 0;
+      int nn = n;
+      if (mode == 6) nn = ((n & 1) << 6) | ((n & 2) << 4) | ((n & 4) << 2) | (n & 8) | ((n & 16) >> 2) | ((n & 32) >> 4) | ((n & 64) >> 6);
       for (int k = 0; k < K; ++k)
-        ref += (double)fA[m * K + k] * (mode == 2 ? (double)fB[k * 128 + n] : (double)fB[n * K + k]);
+        ref += (double)fA[m * K + k] * (mode == 2 ? (double)fB[k * 128 + n] : (double)fB[nn * K + k]);
       if (mode == 3) ref *= 2.0;
       maxerr = fmax(maxerr, fabs(ref - hD[m * N + n]));
       maxref = fmax(maxref, fabs(ref));
