@@ -198,24 +198,56 @@ int e2f_linear_bf16x3(const void* a_hi, const void* a_lo, const void* w_hi, cons
   return finish(launch_linear_bf16x3(a_hi, a_lo, w_hi, w_lo, bias, residual, out, m, n, k, out_dtype, bn, static_cast<cudaStream_t>(stream)), "e2f_linear_bf16x3");
 }
 
+int e2f_conv2d_rows_bf16x3(int nsrc, const void* const* src_hi, const void* const* src_lo, const int* src_channels,
+                           int in_rows, const void* w_hi, const void* w_lo, const float* bias, const float* residual,
+                           float* out, void* out_hi, void* out_lo, int out_lead, int n, int h, int w, int cout, int groups,
+                           float leaky_slope, int ksize, int stride, int pad, void* stream) {
+  const char* who = "e2f_conv2d_bf16x3";
+  if (!src_hi || !src_lo || !src_channels || !w_hi || !w_lo) { set_error("%s: null pointer", who); return E2F_ERR_BAD_ARG; }
+  if ((!out && !out_hi) || (!out_hi) != (!out_lo)) { set_error("%s: need out and/or both of out_hi/out_lo", who); return E2F_ERR_BAD_ARG; }
+  if (out_hi && cout % 8) { set_error("%s: split output needs Cout %% 8 == 0", who); return E2F_ERR_UNSUPPORTED; }
+  if (nsrc < 1 || nsrc > 4) { set_error("%s: nsrc=%d (1..4 supported)", who, nsrc); return E2F_ERR_UNSUPPORTED; }
+  if (n < 0 || h <= 0 || w <= 0 || cout <= 0 || groups <= 0 || cout % groups) { set_error("%s: bad shape n=%d h=%d w=%d cout=%d groups=%d", who, n, h, w, cout, groups); return E2F_ERR_BAD_ARG; }
+  if (ksize < 1 || ksize > 7 || (stride != 1 && stride != 2) || pad < 0 || h + 2 * pad < ksize || w + 2 * pad < ksize) { set_error("%s: unsupported geometry k=%d stride=%d pad=%d", who, ksize, stride, pad); return E2F_ERR_UNSUPPORTED; }
+  if (out_lead < 0 || out_lead > 8 || (out_lead && !out_hi)) { set_error("%s: out_lead=%d needs a split output and 0..8", who, out_lead); return E2F_ERR_BAD_ARG; }
+  if (out_lead && groups != 1) { set_error("%s: row-gapped output needs groups == 1", who); return E2F_ERR_UNSUPPORTED; }
+  if (in_rows) {
+    const int cin = src_channels[0];
+    const bool pow2 = cin == 4 || cin == 8 || cin == 16 || cin == 32;
+    if (nsrc != 1 || groups != 1 || !pow2 || (stride * cin * 2) % 16 || (ksize > 64 / cin && (64 / cin) % stride)) {
+      set_error("%s: window-packed input needs one source, groups == 1, cin in {4,8,16,32} with stride*cin*2 %% 16 == 0 (nsrc=%d groups=%d cin=%d stride=%d)", who, nsrc, groups, cin, stride);
+      return E2F_ERR_UNSUPPORTED;
+    }
+  }
+  for (int i = 0; i < nsrc; ++i) {
+    if (!src_hi[i] || !src_lo[i]) { set_error("%s: null source %d", who, i); return E2F_ERR_BAD_ARG; }
+    if (!in_rows && (src_channels[i] <= 0 || src_channels[i] % 8 || src_channels[i] % groups)) { set_error("%s: source %d has %d channels (needs a multiple of 8 and of groups)", who, i, src_channels[i]); return E2F_ERR_UNSUPPORTED; }
+    if (!aligned(src_hi[i], 16) || !aligned(src_lo[i], 16)) { set_error("%s: 16-byte alignment required", who); return E2F_ERR_ALIGNMENT; }
+  }
+  if (!aligned(w_hi, 16) || !aligned(w_lo, 16) || (out && !aligned(out, 16)) || (out_hi && (!aligned(out_hi, 16) || !aligned(out_lo, 16))) || (residual && !aligned(residual, 16))) { set_error("%s: 16-byte alignment required", who); return E2F_ERR_ALIGNMENT; }
+  if (n == 0) return 0;
+  return finish(launch_conv3x3(nsrc, src_hi, src_lo, src_channels, w_hi, w_lo, bias, residual, out, out_hi, out_lo, n, h, w, cout, groups, leaky_slope, ksize, stride, pad, in_rows ? 1 : 0, out_lead, static_cast<cudaStream_t>(stream)), who);
+}
+
 int e2f_conv2d_bf16x3(int nsrc, const void* const* src_hi, const void* const* src_lo, const int* src_channels,
                       const void* w_hi, const void* w_lo, const float* bias, const float* residual, float* out,
                       void* out_hi, void* out_lo, int n, int h, int w, int cout, int groups, float leaky_slope, int ksize,
                       int stride, int pad, void* stream) {
-  if (!src_hi || !src_lo || !src_channels || !w_hi || !w_lo) { set_error("e2f_conv2d_bf16x3: null pointer"); return E2F_ERR_BAD_ARG; }
-  if ((!out && !out_hi) || (!out_hi) != (!out_lo)) { set_error("e2f_conv2d_bf16x3: need out and/or both of out_hi/out_lo"); return E2F_ERR_BAD_ARG; }
-  if (out_hi && cout % 8) { set_error("e2f_conv2d_bf16x3: split output needs Cout %% 8 == 0"); return E2F_ERR_UNSUPPORTED; }
-  if (nsrc < 1 || nsrc > 4) { set_error("e2f_conv2d_bf16x3: nsrc=%d (1..4 supported)", nsrc); return E2F_ERR_UNSUPPORTED; }
-  if (n < 0 || h <= 0 || w <= 0 || cout <= 0 || groups <= 0 || cout % groups) { set_error("e2f_conv2d_bf16x3: bad shape n=%d h=%d w=%d cout=%d groups=%d", n, h, w, cout, groups); return E2F_ERR_BAD_ARG; }
-  if (ksize < 1 || ksize > 7 || (stride != 1 && stride != 2) || pad < 0 || h + 2 * pad < ksize || w + 2 * pad < ksize) { set_error("e2f_conv2d_bf16x3: unsupported geometry k=%d stride=%d pad=%d", ksize, stride, pad); return E2F_ERR_UNSUPPORTED; }
-  for (int i = 0; i < nsrc; ++i) {
-    if (!src_hi[i] || !src_lo[i]) { set_error("e2f_conv2d_bf16x3: null source %d", i); return E2F_ERR_BAD_ARG; }
-    if (src_channels[i] <= 0 || src_channels[i] % 8 || src_channels[i] % groups) { set_error("e2f_conv2d_bf16x3: source %d has %d channels (needs a multiple of 8 and of groups)", i, src_channels[i]); return E2F_ERR_UNSUPPORTED; }
-    if (!aligned(src_hi[i], 16) || !aligned(src_lo[i], 16)) { set_error("e2f_conv2d_bf16x3: 16-byte alignment required"); return E2F_ERR_ALIGNMENT; }
-  }
-  if (!aligned(w_hi, 16) || !aligned(w_lo, 16) || (out && !aligned(out, 16)) || (out_hi && (!aligned(out_hi, 16) || !aligned(out_lo, 16))) || (residual && !aligned(residual, 16))) { set_error("e2f_conv2d_bf16x3: 16-byte alignment required"); return E2F_ERR_ALIGNMENT; }
-  if (n == 0) return 0;
-  return finish(launch_conv3x3(nsrc, src_hi, src_lo, src_channels, w_hi, w_lo, bias, residual, out, out_hi, out_lo, n, h, w, cout, groups, leaky_slope, ksize, stride, pad, static_cast<cudaStream_t>(stream)), "e2f_conv2d_bf16x3");
+  return e2f_conv2d_rows_bf16x3(nsrc, src_hi, src_lo, src_channels, 0, w_hi, w_lo, bias, residual, out, out_hi, out_lo, 0, n,
+                                h, w, cout, groups, leaky_slope, ksize, stride, pad, stream);
+}
+
+int e2f_conv_rows_pitch(int w, int lead, int channels) { return (w <= 0 || lead < 0 || channels <= 0) ? E2F_ERR_BAD_ARG : conv_rows_pitch(w, lead, channels); }
+
+int e2f_conv_rows_tail(int lead, int channels) { return (lead < 0 || channels <= 0) ? E2F_ERR_BAD_ARG : conv_rows_tail(lead, channels); }
+
+int e2f_pack_rows_bf16(const float* x, void* out_hi, void* out_lo, int n, int c, int h, int w, int cin, int lead,
+                       void* stream) {
+  if (!x || !out_hi || !out_lo) { set_error("e2f_pack_rows_bf16: null pointer"); return E2F_ERR_BAD_ARG; }
+  if (n < 0 || c <= 0 || h <= 0 || w <= 0 || lead < 0 || lead > 8) { set_error("e2f_pack_rows_bf16: bad shape"); return E2F_ERR_BAD_ARG; }
+  if ((cin != 4 && cin != 8 && cin != 16 && cin != 32) || c > cin) { set_error("e2f_pack_rows_bf16: cin=%d must be 4, 8, 16 or 32 and >= C=%d", cin, c); return E2F_ERR_UNSUPPORTED; }
+  if (!aligned(x, 4) || !aligned(out_hi, 16) || !aligned(out_lo, 16)) { set_error("e2f_pack_rows_bf16: alignment"); return E2F_ERR_ALIGNMENT; }
+  return finish(launch_pack_rows(x, out_hi, out_lo, n, c, h, w, cin, lead, static_cast<cudaStream_t>(stream)), "e2f_pack_rows_bf16");
 }
 
 int e2f_conv3x3_bf16x3(int nsrc, const void* const* src_hi, const void* const* src_lo, const int* src_channels,

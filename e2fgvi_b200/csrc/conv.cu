@@ -9,7 +9,15 @@
 //    feat_prop.py:36,125,131-136) are never built — each concatenated tensor is its own TMA source.
 //  * groups (encoder convs with groups 2/4/8): a tile's N range lives inside one group and its K chunks start at the
 //    group's channel offset of every source; chunks that spill past a group's slice hit zero weights.
-//  * epilogue: + bias, LeakyReLU(slope), optional residual add, fp32 NHWC store.
+//  * small-channel sources (cin = 4 / 8 / 16 / 32: SPyNet's 7x7 convs, the 3-channel stem): "window-packed" K.  The
+//    source is stored row-gapped, [N][H][W + pad][cin] with `pad` zero pixels in front of every row (the gap doubles
+//    as the previous row's right padding).  The tensor map's pixel dimension has a stride of ONE pixel (x conv
+//    stride) but dimension 0 spans 64 elements = 64/cin consecutive pixels, so every TMA row is the sliding window
+//    [x - pad + g*PX, +PX) x cin — a whole slice of the kernel row per 64-wide K chunk instead of one tap padded from
+//    cin to 64 channels (7x fewer K chunks for SPyNet's first conv, 12x for the stem).  Weights for taps past the
+//    kernel width are zero; what those positions read is finite data of the same buffer.
+//  * epilogue: + bias, LeakyReLU(slope), optional residual add, fp32 NHWC store and/or the bf16 (hi, lo) split of
+//    the result — dense NHWC or row-gapped for a following window-packed conv (the zero gaps are written here).
 // Pipeline = gemm.cu: persistent CTAs, TMA warp / MMA warp / 4 epilogue warps, double-buffered TMEM accumulator.
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -26,12 +34,12 @@ constexpr int EPI_WARPS = 4;
 constexpr int THREADS = (2 + EPI_WARPS) * 32;
 constexpr int MAX_SRC = 4;
 
-// N tile: 128 output channels, or 64 for the layers with <= 64 output channels per group (decoder, encoder conv 1,
-// the 3-channel output conv), which would otherwise waste half of every MMA.
+// N tile: 128 output channels; 64 / 32 for the layers with <= 64 / <= 32 output channels per group (decoder, encoder
+// conv 1, SPyNet, the 3-channel output conv), which would otherwise waste most of every MMA.
 template <int BN>
 struct Cfg {
   static constexpr int W_TILE = BN * BK * 2;
-  static constexpr int STAGE = 2 * A_TILE + 2 * W_TILE;   // 64 KB (BN=128) / 48 KB (BN=64)
+  static constexpr int STAGE = 2 * A_TILE + 2 * W_TILE;   // 64 KB (BN=128) / 48 KB (BN=64) / 40 KB (BN=32)
   static constexpr int STAGES = (BN == 128) ? 3 : 4;
   static constexpr int TMEM_COLS = 2 * BN;
   static constexpr int SMEM = STAGES * STAGE + 256 + 1024;
@@ -45,6 +53,10 @@ struct Params {
   int N, H, W, Cout, groups;     // H, W: OUTPUT spatial size
   int ks, stride, pad;           // square kernel size (3 or 7), stride (1 or 2), zero padding
   int nsrc;
+  int rows_px;             // 0: dense NHWC sources.  > 0: window-packed K, 64 / cin pixels per K chunk (one source)
+  int rows_g;              // ... K chunks per kernel row = ceil(ks / rows_px)
+  int out_lead, out_pitch; // split output rows: `out_lead` zero pixels, then W pixels; out_pitch = W + out_lead
+  int out_tail;            // zero pixels after the last row of the split output (0 when dense)
   int cig[MAX_SRC];        // channels per group of each source
   int chunks[MAX_SRC];     // ceil(cig / 64)
   int chunks_total;        // sum of chunks
@@ -106,7 +118,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv3x3_kernel(const __grid_consta
   const int cog = p.Cout / p.groups;
   const int tiles_ng = (cog + BN - 1) / BN;
   const int num_tiles = p.N * tiles_y * tiles_x * p.groups * tiles_ng;
-  const int num_kb = p.ks * p.ks * p.chunks_total;
+  const int num_kb = p.rows_px ? p.ks * p.rows_g : p.ks * p.ks * p.chunks_total;
 
   if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
   if (tid == 0) {
@@ -138,6 +150,24 @@ __global__ void __launch_bounds__(THREADS, 1) conv3x3_kernel(const __grid_consta
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const TileCoord t = decode_tile<BN>(tile, p, tiles_y, tiles_x, tiles_ng);
         int kb = 0;
+        if (p.rows_px) {
+          // window-packed K: chunk (ky, g) = pixels [x*stride - pad + g*PX, +PX) x cin of input row y*stride - pad + ky
+          for (int ky = 0; ky < p.ks; ++ky) {
+            const int yy = t.y0 * p.stride - p.pad + ky;
+            for (int g = 0; g < p.rows_g; ++g, ++kb, ++it) {
+              const int stage = it % STAGES;
+              mbar_wait(&empty[stage], ((it / STAGES) & 1) ^ 1);
+              mbar_arrive_expect_tx(&full[stage], STAGE);
+              const uint32_t s0 = smem_u32(smem + stage * STAGE);
+              const int xi = t.x0 + g * p.rows_px / p.stride;       // window-start index (row gap = left padding)
+              tma_load_4d(s0, &maps.a_hi[0], &full[stage], 0, xi, yy, t.n);
+              tma_load_4d(s0 + A_TILE, &maps.a_lo[0], &full[stage], 0, xi, yy, t.n);
+              tma_load_2d(s0 + 2 * A_TILE, &maps.w_hi, &full[stage], kb * BK, t.co0);
+              tma_load_2d(s0 + 2 * A_TILE + W_TILE, &maps.w_lo, &full[stage], kb * BK, t.co0);
+            }
+          }
+          continue;
+        }
         const int taps = p.ks * p.ks;
         for (int tap = 0; tap < taps; ++tap) {
           // input coordinate of the tile's first output pixel for this tap (TMA steps by `stride` inside the box)
@@ -201,8 +231,10 @@ __global__ void __launch_bounds__(THREADS, 1) conv3x3_kernel(const __grid_consta
       const int r = q * 32 + lane;
       const int y = t.y0 + r / TILE_W, x = t.x0 + r % TILE_W;
       const bool pix_ok = (y < p.H) && (x < p.W);
-      const size_t pix = (static_cast<size_t>(t.n) * p.H + y) * p.W + x;
+      const size_t pix = (static_cast<size_t>(t.n) * p.H + y) * p.W + x;                      // fp32 out, residual
+      const size_t opix = (static_cast<size_t>(t.n) * p.H + y) * p.out_pitch + p.out_lead + x;   // split outputs
       const int co_end = (t.g + 1) * cog;               // exclusive end of this group's output channels
+      const bool vec_ok = (p.Cout & 3) == 0;            // 16-byte aligned channel groups
       const uint32_t taddr = tbase + (static_cast<uint32_t>(q * 32) << 16) + buf * BN;
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
@@ -211,61 +243,72 @@ __global__ void __launch_bounds__(THREADS, 1) conv3x3_kernel(const __grid_consta
         tmem_ld_wait();
         const int co = t.co0 + c * 32;
         if (pix_ok && co < co_end) {
-          const size_t o = pix * p.Cout + co;
-          if (co + 32 <= co_end) {
-            float f[32];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              float a = __uint_as_float(v[i]) + (p.bias ? __ldg(p.bias + co + i) : 0.f);
-              f[i] = a > 0.f ? a : a * p.slope;
-            }
-            if (p.residual) {
-              const float4* r4 = reinterpret_cast<const float4*>(p.residual + o);
+          for (int g8 = 0; g8 < 4; ++g8) {              // 8 output channels at a time
+            const int cb = co + g8 * 8;
+            if (vec_ok && cb + 8 <= co_end) {
+              float f[8];
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
-                const float4 rr = __ldg(r4 + i);
-                f[4 * i] += rr.x; f[4 * i + 1] += rr.y; f[4 * i + 2] += rr.z; f[4 * i + 3] += rr.w;
+                const float a = __uint_as_float(v[g8 * 8 + i]) + (p.bias ? __ldg(p.bias + cb + i) : 0.f);
+                f[i] = a > 0.f ? a : a * p.slope;
               }
-            }
-            if (p.out) {
-              float4* d4 = reinterpret_cast<float4*>(p.out + o);
-#pragma unroll
-              for (int i = 0; i < 8; ++i) d4[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
-            }
-            if (p.out_hi) {
-              uint32_t hp[16], lp[16];       // packed bf16 pairs, kept in registers
-#pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                const __nv_bfloat162 hb = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
-                const float2 hf = __bfloat1622float2(hb);
-                const __nv_bfloat162 lb = __floats2bfloat162_rn(f[2 * i] - hf.x, f[2 * i + 1] - hf.y);
-                hp[i] = *reinterpret_cast<const uint32_t*>(&hb);
-                lp[i] = *reinterpret_cast<const uint32_t*>(&lb);
+              if (p.residual) {
+                const float4* r4 = reinterpret_cast<const float4*>(p.residual + pix * p.Cout + cb);
+                const float4 ra = __ldg(r4), rb = __ldg(r4 + 1);
+                f[0] += ra.x; f[1] += ra.y; f[2] += ra.z; f[3] += ra.w;
+                f[4] += rb.x; f[5] += rb.y; f[6] += rb.z; f[7] += rb.w;
               }
-              uint4* dh = reinterpret_cast<uint4*>(p.out_hi + o);
-              uint4* dl = reinterpret_cast<uint4*>(p.out_lo + o);
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                dh[i] = make_uint4(hp[4 * i], hp[4 * i + 1], hp[4 * i + 2], hp[4 * i + 3]);
-                dl[i] = make_uint4(lp[4 * i], lp[4 * i + 1], lp[4 * i + 2], lp[4 * i + 3]);
+              if (p.out) {
+                float4* d4 = reinterpret_cast<float4*>(p.out + pix * p.Cout + cb);
+                d4[0] = make_float4(f[0], f[1], f[2], f[3]);
+                d4[1] = make_float4(f[4], f[5], f[6], f[7]);
               }
-            }
-          } else {
+              if (p.out_hi) {
+                uint32_t hp[4], lp[4];                  // packed bf16 pairs, kept in registers
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              if (co + i < co_end) {
-                float a = __uint_as_float(v[i]) + (p.bias ? __ldg(p.bias + co + i) : 0.f);
-                a = a > 0.f ? a : a * p.slope;
-                if (p.residual) a += __ldg(p.residual + o + i);
-                if (p.out) p.out[o + i] = a;
-                if (p.out_hi) {
-                  const __nv_bfloat16 hb = __float2bfloat16_rn(a);
-                  p.out_hi[o + i] = hb;
-                  p.out_lo[o + i] = __float2bfloat16_rn(a - __bfloat162float(hb));
+                for (int i = 0; i < 4; ++i) {
+                  const __nv_bfloat162 hb = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+                  const float2 hf = __bfloat1622float2(hb);
+                  const __nv_bfloat162 lb = __floats2bfloat162_rn(f[2 * i] - hf.x, f[2 * i + 1] - hf.y);
+                  hp[i] = *reinterpret_cast<const uint32_t*>(&hb);
+                  lp[i] = *reinterpret_cast<const uint32_t*>(&lb);
+                }
+                *reinterpret_cast<uint4*>(p.out_hi + opix * p.Cout + cb) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
+                *reinterpret_cast<uint4*>(p.out_lo + opix * p.Cout + cb) = make_uint4(lp[0], lp[1], lp[2], lp[3]);
+              }
+            } else if (cb < co_end) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                if (cb + i < co_end) {
+                  float a = __uint_as_float(v[g8 * 8 + i]) + (p.bias ? __ldg(p.bias + cb + i) : 0.f);
+                  a = a > 0.f ? a : a * p.slope;
+                  if (p.residual) a += __ldg(p.residual + pix * p.Cout + cb + i);
+                  if (p.out) p.out[pix * p.Cout + cb + i] = a;
+                  if (p.out_hi) {
+                    const __nv_bfloat16 hb = __float2bfloat16_rn(a);
+                    p.out_hi[opix * p.Cout + cb + i] = hb;
+                    p.out_lo[opix * p.Cout + cb + i] = __float2bfloat16_rn(a - __bfloat162float(hb));
+                  }
                 }
               }
             }
           }
+        }
+      }
+      // row-gapped split output: the pixel at x == 0 also writes the zero gap in front of its row, the very last pixel
+      // the zero tail (once per pixel: only the first N tile of group 0 does it; Cout % 8 == 0 is checked by the API)
+      if (p.out_hi && p.out_lead && pix_ok && t.co0 == 0) {
+        const uint4 z = make_uint4(0, 0, 0, 0);
+        if (x == 0) {
+          uint4* zh = reinterpret_cast<uint4*>(p.out_hi + (opix - p.out_lead) * p.Cout);
+          uint4* zl = reinterpret_cast<uint4*>(p.out_lo + (opix - p.out_lead) * p.Cout);
+          for (int i = 0; i < p.out_lead * p.Cout / 8; ++i) zh[i] = zl[i] = z;
+        }
+        if (x == p.W - 1 && y == p.H - 1 && t.n == p.N - 1) {
+          uint4* zh = reinterpret_cast<uint4*>(p.out_hi + (opix + 1) * p.Cout);
+          uint4* zl = reinterpret_cast<uint4*>(p.out_lo + (opix + 1) * p.Cout);
+          for (int i = 0; i < p.out_tail * p.Cout / 8; ++i) zh[i] = zl[i] = z;
         }
       }
       tc_fence_before_sync();
@@ -301,12 +344,58 @@ static int num_sms() {
   return n;
 }
 
+// NCHW fp32 (C <= cin channels) -> row-gapped NHWC bf16 (hi, lo) [N][H][lead + W][cin] + tail, zeros in the gaps, the
+// tail and channels >= C: the operand layout of the window-packed conv.  One thread per (row pixel incl. gap, n*H+y).
+__global__ void __launch_bounds__(256) pack_rows_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ hi,
+                                                        __nv_bfloat16* __restrict__ lo, int N, int C, int H, int W, int cin,
+                                                        int lead, int pitch, int tail) {
+  const long long total = static_cast<long long>(N) * H * pitch + tail;
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const long long row = i / pitch;
+  const int xp = static_cast<int>(i - row * pitch) - lead;
+  const bool inside = row < static_cast<long long>(N) * H && xp >= 0 && xp < W;
+  const long long n = row / H;
+  const int y = static_cast<int>(row - n * H);
+  for (int c0 = 0; c0 < cin; c0 += 4) {          // cin is a multiple of 4: 8-byte stores
+    float f[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      f[j] = (inside && c0 + j < C) ? __ldg(x + ((n * C + c0 + j) * H + y) * static_cast<long long>(W) + xp) : 0.f;
+    const __nv_bfloat162 h0 = __floats2bfloat162_rn(f[0], f[1]), h1 = __floats2bfloat162_rn(f[2], f[3]);
+    const float2 g0 = __bfloat1622float2(h0), g1 = __bfloat1622float2(h1);
+    const __nv_bfloat162 l0 = __floats2bfloat162_rn(f[0] - g0.x, f[1] - g0.y), l1 = __floats2bfloat162_rn(f[2] - g1.x, f[3] - g1.y);
+    *reinterpret_cast<uint2*>(hi + i * cin + c0) = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
+    *reinterpret_cast<uint2*>(lo + i * cin + c0) = make_uint2(*reinterpret_cast<const uint32_t*>(&l0), *reinterpret_cast<const uint32_t*>(&l1));
+  }
+}
+
 }  // namespace conv
+
+int conv_rows_tail(int lead, int channels) { return lead + (conv::BK + channels - 1) / channels; }
+
+// pixels per row of the row-gapped layout: lead + W, rounded up so that a row is a multiple of 16 bytes (TMA stride
+// rule; only matters for 4 channels); the extra pixel, if any, sits at the END of the row and is zero as well
+int conv_rows_pitch(int w, int lead, int channels) {
+  const int unit = channels >= 8 ? 1 : 8 / channels;
+  return (w + lead + unit - 1) / unit * unit;
+}
+
+int launch_pack_rows(const float* x, void* hi, void* lo, int n, int c, int h, int w, int cin, int lead,
+                     cudaStream_t stream) {
+  const int pitch = conv_rows_pitch(w, lead, cin);
+  const long long total = static_cast<long long>(n) * h * pitch + conv_rows_tail(lead, cin);
+  const unsigned blocks = static_cast<unsigned>((total + 255) / 256);
+  conv::pack_rows_kernel<<<blocks, 256, 0, stream>>>(x, static_cast<__nv_bfloat16*>(hi), static_cast<__nv_bfloat16*>(lo), n, c,
+                                                     h, w, cin, lead, pitch, conv_rows_tail(lead, cin));
+  count_launch();
+  return static_cast<int>(cudaGetLastError());
+}
 
 int launch_conv3x3(int nsrc, const void* const* src_hi, const void* const* src_lo, const int* src_channels,
                    const void* w_hi, const void* w_lo, const float* bias, const float* residual, float* out,
                    void* out_hi, void* out_lo, int n, int h_in, int w_in, int cout, int groups, float slope, int ks,
-                   int stride, int pad, cudaStream_t stream) {
+                   int stride, int pad, int in_rows, int out_lead, cudaStream_t stream) {
   using namespace conv;
   const int h = (h_in + 2 * pad - ks) / stride + 1, w = (w_in + 2 * pad - ks) / stride + 1;   // output size
   EncodeTiledFn enc = get_encode();
@@ -314,7 +403,8 @@ int launch_conv3x3(int nsrc, const void* const* src_hi, const void* const* src_l
     set_error("cuTensorMapEncodeTiled is not available from the driver");
     return -4;
   }
-  const int bn = (cout / groups <= 64) ? 64 : 128;
+  const int cog = cout / groups;
+  const int bn = cog <= 32 ? 32 : (cog <= 64 ? 64 : 128);
   Maps maps;
   Params p;
   p.N = n; p.H = h; p.W = w; p.Cout = cout; p.groups = groups; p.nsrc = nsrc;
@@ -322,9 +412,41 @@ int launch_conv3x3(int nsrc, const void* const* src_hi, const void* const* src_l
   p.slope = slope; p.bias = bias; p.residual = residual; p.out = out;
   p.out_hi = static_cast<__nv_bfloat16*>(out_hi); p.out_lo = static_cast<__nv_bfloat16*>(out_lo);
   p.chunks_total = 0;
+  p.rows_px = p.rows_g = 0;
+  p.out_lead = out_lead;
+  p.out_pitch = conv_rows_pitch(w, out_lead, cout);   // == w + out_lead: split outputs have >= 8 channels
+  p.out_tail = out_lead ? conv_rows_tail(out_lead, cout) : 0;
   for (int i = 0; i < MAX_SRC; ++i) p.cig[i] = p.chunks[i] = 0;
+  if (in_rows) {
+    // ONE row-gapped source [N][H][w_in + pad][cin] (+ tail): dimension 1 steps by `stride` pixels, dimension 0 spans
+    // 64 elements = 64/cin pixels (overlapping windows; validated by tools/tma_window_probe.cu)
+    const int cin = src_channels[0];
+    p.rows_px = BK / cin;
+    p.rows_g = (ks + p.rows_px - 1) / p.rows_px;
+    p.cig[0] = cin;
+    p.chunks[0] = 1;
+    p.chunks_total = 1;
+    const int pitch = conv_rows_pitch(w_in, pad, cin);
+    const cuuint64_t dims[4] = {BK, static_cast<cuuint64_t>((pitch + stride - 1) / stride), static_cast<cuuint64_t>(h_in),
+                                static_cast<cuuint64_t>(n)};
+    const cuuint64_t strides[3] = {static_cast<cuuint64_t>(stride) * cin * 2, static_cast<cuuint64_t>(pitch) * cin * 2,
+                                   static_cast<cuuint64_t>(h_in) * pitch * cin * 2};
+    const cuuint32_t box[4] = {BK, TILE_W, static_cast<cuuint32_t>(TILE_H * stride), 1};
+    const cuuint32_t estr[4] = {1, 1, static_cast<cuuint32_t>(stride), 1};
+    for (int part = 0; part < 2; ++part) {
+      CUresult r = enc(part ? &maps.a_lo[0] : &maps.a_hi[0], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4,
+                       const_cast<void*>(part ? src_lo[0] : src_hi[0]), dims, strides, box, estr,
+                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) {
+        set_error("conv2d: cuTensorMapEncodeTiled(row-gapped source) failed with CUresult %d (cin=%d w=%d h=%d n=%d)",
+                  static_cast<int>(r), cin, w_in, h_in, n);
+        return -4;
+      }
+    }
+  }
   const cuuint32_t estr4[4] = {1, static_cast<cuuint32_t>(stride), static_cast<cuuint32_t>(stride), 1};
-  for (int i = 0; i < nsrc; ++i) {
+  for (int i = 0; i < (in_rows ? 0 : nsrc); ++i) {
     const int c = src_channels[i];
     p.cig[i] = c / groups;
     p.chunks[i] = (p.cig[i] + BK - 1) / BK;
@@ -348,7 +470,7 @@ int launch_conv3x3(int nsrc, const void* const* src_hi, const void* const* src_l
     }
   }
   {
-    const int kpad = ks * ks * p.chunks_total * BK;
+    const int kpad = (in_rows ? ks * p.rows_g : ks * ks * p.chunks_total) * BK;
     const cuuint64_t dims[2] = {static_cast<cuuint64_t>(kpad), static_cast<cuuint64_t>(cout)};
     const cuuint64_t strides[1] = {static_cast<cuuint64_t>(kpad) * 2};
     const cuuint32_t box[2] = {BK, static_cast<cuuint32_t>(bn)};
@@ -369,6 +491,8 @@ int launch_conv3x3(int nsrc, const void* const* src_hi, const void* const* src_l
     cudaError_t e = cudaFuncSetAttribute(conv3x3_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<128>::SMEM);
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(conv3x3_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<64>::SMEM);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(conv3x3_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<32>::SMEM);
     if (e != cudaSuccess) return static_cast<int>(e);
     configured = true;
   }
@@ -381,7 +505,9 @@ int launch_conv3x3(int nsrc, const void* const* src_hi, const void* const* src_l
     return -2;
   }
   const int grid = tiles < num_sms() ? static_cast<int>(tiles) : num_sms();
-  if (bn == 64)
+  if (bn == 32)
+    conv3x3_kernel<32><<<grid, THREADS, Cfg<32>::SMEM, stream>>>(maps, p);
+  else if (bn == 64)
     conv3x3_kernel<64><<<grid, THREADS, Cfg<64>::SMEM, stream>>>(maps, p);
   else
     conv3x3_kernel<128><<<grid, THREADS, Cfg<128>::SMEM, stream>>>(maps, p);

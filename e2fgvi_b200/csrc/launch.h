@@ -43,6 +43,10 @@ int launch_linear_bf16x3(const void* a_hi, const void* a_lo, const void* w_hi, c
 int launch_conv3x3(int nsrc, const void* const* src_hi, const void* const* src_lo, const int* src_channels,
                    const void* w_hi, const void* w_lo, const float* bias, const float* residual, float* out,
                    void* out_hi, void* out_lo, int n, int h_in, int w_in, int cout, int groups, float slope, int ks,
-                   int stride, int pad, cudaStream_t stream);
+                   int stride, int pad, int in_rows, int out_lead, cudaStream_t stream);
+int conv_rows_tail(int lead, int channels);
+int conv_rows_pitch(int w, int lead, int channels);
+int launch_pack_rows(const float* x, void* hi, void* lo, int n, int c, int h, int w, int cin, int lead,
+                     cudaStream_t stream);
 
 }  // namespace e2f

@@ -77,6 +77,10 @@ class Encoder(nn.Module):
         for k, (_, _, stride, _) in enumerate(_ENC):
             conv = self.layers[2 * k]
             mode = "f32" if k == last else "split"
+            if k == 0:
+                # 3-channel stem: row-gapped 4-channel layout, window-packed K (3 K chunks per tile instead of 9
+                # taps zero-padded from 3 to 64 channels)
+                out = ops.pack_rows(out, lead=conv.padding[0])
             if k == 4:
                 x0 = out
             if k > 4:

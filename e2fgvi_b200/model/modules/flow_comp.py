@@ -39,14 +39,21 @@ class SPyNetBasicModule(nn.Module):
         self.basic_module = nn.Sequential(*[_ConvHolder(ci, co) for ci, co in _LEVEL_CONVS])
 
     def forward(self, tensor_input):
-        """Five 7x7 convs on the tcgen05 implicit-GEMM kernel (k x k taps are just more TMA boxes), ReLU fused
-        (LeakyReLU with slope 0), the bf16 split operand handed from conv to conv."""
-        y = tensor_input
-        last = len(self.basic_module) - 1
-        for i, holder in enumerate(self.basic_module):
-            y = ops.conv3x3([y], holder.conv.weight, holder.conv.bias, negative_slope=1.0 if i == last else 0.0,
-                            out="f32" if i == last else "split")
-        return y
+        """Five 7x7 convs on the tcgen05 implicit-GEMM kernel, ReLU fused (LeakyReLU with slope 0), the bf16 split
+        operand handed from conv to conv.  Activations with <= 32 channels (the 8-channel input, the 32- and
+        16-channel intermediates) travel in the row-gapped layout so their convs use window-packed K: 7 / 28 / 14 K
+        chunks per tile instead of 49 taps zero-padded to 64 channels."""
+        convs = [holder.conv for holder in self.basic_module]
+        y = ops.pack_rows(tensor_input, lead=convs[0].padding[0])
+        last = len(convs) - 1
+        for i, conv in enumerate(convs):
+            if i == last:
+                return ops.conv3x3(y, conv.weight, conv.bias, negative_slope=1.0, out="f32")
+            nxt = convs[i + 1]
+            if ops.rows_channels(nxt.in_channels) == nxt.in_channels:      # 8 / 16 / 32 channels: row-gapped hand-off
+                y = ops.conv3x3(y, conv.weight, conv.bias, negative_slope=0.0, out="rows", out_lead=nxt.padding[0])
+            else:
+                y = ops.conv3x3(y, conv.weight, conv.bias, negative_slope=0.0, out="split")
 
 
 class SPyNet(nn.Module):

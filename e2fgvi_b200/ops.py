@@ -460,6 +460,71 @@ def split_nhwc(x):
     return SplitNHWC(hi, lo, (n, c, h, w))
 
 
+class RowsNHWC:
+    """A small-channel activation in the row-gapped layout of the window-packed conv (include/e2fgvi_b200.h,
+    ``e2f_conv2d_rows_bf16x3``): bf16 (hi, lo), flat [N][H][pitch][cin] + tail with pitch = lead + W (+1 rounding
+    pixel for odd rows of 4 channels), zeros in gaps / tail / pad channels."""
+
+    __slots__ = ("hi", "lo", "shape", "lead", "cin", "pitch")
+
+    def __init__(self, hi, lo, shape, lead, cin):
+        self.hi, self.lo, self.shape, self.lead, self.cin = hi, lo, shape, lead, cin   # shape: logical (N,C,H,W)
+        self.pitch = int(_lib.load().e2f_conv_rows_pitch(shape[3], lead, cin))
+
+    def dense(self):
+        """fp32 (N,C,H,W) view of the content (tests / debugging)."""
+        n, c, h, w = self.shape
+        body = (self.hi.float() + self.lo.float())[: n * h * self.pitch * self.cin]
+        return body.view(n, h, self.pitch, self.cin)[:, :, self.lead: self.lead + w, :c].permute(0, 3, 1, 2)
+
+
+def rows_channels(c):
+    """Channel count of the row-gapped layout that holds c channels (4, 8, 16 or 32), or None if c > 32."""
+    for cin in (4, 8, 16, 32):
+        if c <= cin:
+            return cin
+    return None
+
+
+def _rows_numel(n, h, w, lead, cin):
+    lib = _lib.load()
+    return (n * h * int(lib.e2f_conv_rows_pitch(w, lead, cin)) + int(lib.e2f_conv_rows_tail(lead, cin))) * cin
+
+
+def pack_rows(x, lead, cin=None):
+    """(N,C,H,W) fp32 -> ``RowsNHWC`` with ``lead`` zero pixels in front of every row (= the padding of the conv
+    that consumes it) and channels zero-padded to ``cin`` (default: the smallest of 4/8/16/32 that holds C)."""
+    if isinstance(x, RowsNHWC):
+        return x
+    _need_cuda(x)
+    n, c, h, w = x.shape
+    cin = cin or rows_channels(c)
+    if cin is None or c > cin:
+        raise ValueError(f"pack_rows: {c} channels do not fit a row-gapped layout (<= 32)")
+    x = x.contiguous().float()
+    numel = _rows_numel(n, h, w, lead, cin)
+    hi = torch.empty(numel, dtype=torch.bfloat16, device=x.device)
+    lo = torch.empty(numel, dtype=torch.bfloat16, device=x.device)
+    with _timed("pack_rows", float(x.numel() * 4 + numel * 4)):
+        st = _lib.load().e2f_pack_rows_bf16(x.data_ptr(), hi.data_ptr(), lo.data_ptr(), n, c, h, w, cin, lead, _stream())
+    _lib.check(st, "e2f_pack_rows_bf16")
+    return RowsNHWC(hi, lo, (n, c, h, w), lead, cin)
+
+
+def pack_conv_rows_weight(weight, cin):
+    """fp32 (Cout, C, k, k), C <= cin -> (hi, lo) bf16 (Cout, k*G*64) in the window-packed K order of
+    ``e2f_conv2d_rows_bf16x3``: chunk (ky, g) holds taps kx = g*PX .. g*PX+PX-1 (PX = 64/cin) x cin channels, zeros
+    for kx >= k and for channels >= C."""
+    cout, c, kh, kw = weight.shape
+    assert kh == kw and c <= cin
+    px = 64 // cin
+    g = (kw + px - 1) // px
+    w = weight.detach().float()
+    packed = torch.zeros((cout, kh, g * px, cin), dtype=torch.float32, device=weight.device)
+    packed[:, :, :kw, :c] = w.permute(0, 2, 3, 1)          # [co][ky][kx][c]
+    return split_bf16(packed.view(cout, kh * g * 64))
+
+
 def pack_conv3x3_weight(weight, src_channels, groups=1):
     """fp32 (Cout, Cin/G, 3, 3) -> (hi, lo) bf16 (Cout, 9*T*64) in the K order of ``e2f_conv3x3_bf16x3``:
     tap-major, then source, then 64-channel chunk; the group-local input channel axis is the concatenation of the
@@ -511,13 +576,16 @@ def merge_conv_groups(weight, src_channels, groups):
 _CONV_PACKS = {}  # (id(Parameter), src channels, groups) -> (weakref, tag, hi, lo, effective groups)
 
 
-def _packed_conv_weight(weight, src_channels, groups):
-    key = (id(weight), tuple(src_channels), groups)
+def _packed_conv_weight(weight, src_channels, groups, rows_cin=0):
+    key = (id(weight), tuple(src_channels), groups, rows_cin)
     tag = (weight._version, weight.data_ptr())
     hit = _CONV_PACKS.get(key)
     if hit is None or hit[0]() is not weight or hit[1] != tag:
-        w_eff, g_eff = merge_conv_groups(weight, src_channels, groups)
-        hi, lo = pack_conv3x3_weight(w_eff, src_channels, g_eff)
+        if rows_cin:
+            (hi, lo), g_eff = pack_conv_rows_weight(weight, rows_cin), 1
+        else:
+            w_eff, g_eff = merge_conv_groups(weight, src_channels, groups)
+            hi, lo = pack_conv3x3_weight(w_eff, src_channels, g_eff)
         if hit is None or hit[0]() is not weight:
             weakref.finalize(weight, _CONV_PACKS.pop, key, None)
         hit = (weakref.ref(weight), tag, hi, lo, g_eff)
@@ -526,55 +594,79 @@ def _packed_conv_weight(weight, src_channels, groups):
 
 
 def conv3x3(sources, weight, bias=None, groups=1, negative_slope=1.0, residual=None, out="f32", stride=1,
-            padding=None):
+            padding=None, out_lead=0):
     """``leaky_relu(F.conv2d(torch.cat(sources, 1) [group-wise for groups > 1], weight, bias, 1, 1, 1, groups),
     negative_slope) (+ residual)`` as one tcgen05 implicit-GEMM launch; the cat is never built.
 
     Also serves square k x k kernels (k = 3, 7) with stride 1 / 2 (``padding`` defaults to k // 2): the stride-2
     encoder convs and SPyNet's 7x7 convs (negative_slope = 0 is ReLU).
 
-    sources: list of (N,C_i,H,W) fp32 tensors or ``SplitNHWC``; weight: the nn.Conv2d parameter (Cout, sum C_i / G,
-    k, k).  out = "f32": (N,Cout,H,W) fp32 channels_last tensor; "split": a ``SplitNHWC`` (the bf16 operand pair of a
-    following conv3x3, written by the epilogue, no fp32 round trip); "both": (tensor, SplitNHWC)."""
-    splits = [split_nhwc(s) for s in (sources if isinstance(sources, (list, tuple)) else [sources])]
+    sources: list of (N,C_i,H,W) fp32 tensors or ``SplitNHWC``, or ONE ``RowsNHWC`` (small-channel input, window-packed
+    K; its lead must equal the padding); weight: the nn.Conv2d parameter (Cout, sum C_i / G, k, k).
+    out = "f32": (N,Cout,H,W) fp32 channels_last tensor; "split": a ``SplitNHWC`` (the bf16 operand pair of a
+    following conv3x3, written by the epilogue, no fp32 round trip); "both": (tensor, SplitNHWC); "rows": a
+    ``RowsNHWC`` with ``out_lead`` zero pixels per row (operand of a following small-channel conv with that padding)."""
+    cout, ks = weight.shape[0], weight.shape[2]
+    pad = ks // 2 if padding is None else padding
+    rows_in = sources if isinstance(sources, RowsNHWC) else (
+        sources[0] if isinstance(sources, (list, tuple)) and len(sources) == 1 and isinstance(sources[0], RowsNHWC) else None)
     _need_cuda(weight, bias, residual)
+    if rows_in is not None:
+        if rows_in.lead != pad or groups != 1:
+            raise ValueError(f"conv3x3: RowsNHWC source with lead {rows_in.lead} needs padding {rows_in.lead} and groups 1")
+        if rows_in.shape[1] != weight.shape[1]:
+            raise ValueError("conv3x3: weight does not match the source's channel count")
+        splits = [rows_in]
+        true_channels = padded_channels = [rows_in.cin]
+    else:
+        splits = [split_nhwc(s) for s in (sources if isinstance(sources, (list, tuple)) else [sources])]
+        true_channels = [s.shape[1] for s in splits]
+        padded_channels = [s.hi.shape[-1] for s in splits]
     n, _, h, w = splits[0].shape
     for s in splits:
         if (s.shape[0], s.shape[2], s.shape[3]) != (n, h, w):
             raise ValueError("conv3x3 sources must share N, H, W")
-    true_channels = [s.shape[1] for s in splits]
-    padded_channels = [s.hi.shape[-1] for s in splits]
     if groups != 1 and true_channels != padded_channels:
         raise NotImplementedError("grouped conv3x3 needs channel counts that are multiples of 8")
-    cout, ks = weight.shape[0], weight.shape[2]
-    pad = ks // 2 if padding is None else padding
     h_in, w_in = h, w
     h, w = (h_in + 2 * pad - ks) // stride + 1, (w_in + 2 * pad - ks) // stride + 1
-    w_hi, w_lo, g_eff = _packed_conv_weight(weight, true_channels, groups)
+    w_hi, w_lo, g_eff = _packed_conv_weight(weight, true_channels, groups, rows_in.cin if rows_in is not None else 0)
     b32 = None if bias is None else bias.detach().float().contiguous()
     res = None
     if residual is not None:
         res = residual.permute(0, 2, 3, 1).contiguous().float()
-    want_f32, want_split = out in ("f32", "both"), out in ("split", "both")
-    if not (want_f32 or want_split):
-        raise ValueError("out must be 'f32', 'split' or 'both'")
+    want_f32, want_split, want_rows = out in ("f32", "both"), out in ("split", "both"), out == "rows"
+    if not (want_f32 or want_split or want_rows):
+        raise ValueError("out must be 'f32', 'split', 'both' or 'rows'")
+    if want_rows and (out_lead <= 0 or cout not in (8, 16, 32)):
+        raise ValueError("conv3x3: out='rows' needs out_lead > 0 and 8, 16 or 32 output channels")
     dev = weight.device
     o32 = torch.empty((n, h, w, cout), dtype=torch.float32, device=dev) if want_f32 else None
-    ohi = torch.empty((n, h, w, cout), dtype=torch.bfloat16, device=dev) if want_split else None
-    olo = torch.empty((n, h, w, cout), dtype=torch.bfloat16, device=dev) if want_split else None
+    ohi = olo = None
+    if want_split:
+        ohi = torch.empty((n, h, w, cout), dtype=torch.bfloat16, device=dev)
+        olo = torch.empty((n, h, w, cout), dtype=torch.bfloat16, device=dev)
+    elif want_rows:
+        numel = _rows_numel(n, h, w, out_lead, cout)
+        ohi = torch.empty(numel, dtype=torch.bfloat16, device=dev)
+        olo = torch.empty(numel, dtype=torch.bfloat16, device=dev)
     k = len(splits)
     hi_arr = (_lib._vp * k)(*[s.hi.data_ptr() for s in splits])
     lo_arr = (_lib._vp * k)(*[s.lo.data_ptr() for s in splits])
     ch_arr = (_lib._i * k)(*padded_channels)
     with _timed("conv3x3_bf16x3", 2.0 * n * h * w * cout * weight.shape[1] * ks * ks):
-        st = _lib.load().e2f_conv2d_bf16x3(k, hi_arr, lo_arr, ch_arr, w_hi.data_ptr(), w_lo.data_ptr(),
-                                           None if b32 is None else b32.data_ptr(),
-                                           None if res is None else res.data_ptr(),
-                                           None if o32 is None else o32.data_ptr(),
-                                           None if ohi is None else ohi.data_ptr(),
-                                           None if olo is None else olo.data_ptr(), n, h_in, w_in, cout,
-                                           g_eff, float(negative_slope), ks, stride, pad, _stream())
-    _lib.check(st, "e2f_conv2d_bf16x3")
+        st = _lib.load().e2f_conv2d_rows_bf16x3(k, hi_arr, lo_arr, ch_arr, 1 if rows_in is not None else 0,
+                                                w_hi.data_ptr(), w_lo.data_ptr(),
+                                                None if b32 is None else b32.data_ptr(),
+                                                None if res is None else res.data_ptr(),
+                                                None if o32 is None else o32.data_ptr(),
+                                                None if ohi is None else ohi.data_ptr(),
+                                                None if olo is None else olo.data_ptr(),
+                                                out_lead if want_rows else 0, n, h_in, w_in, cout,
+                                                g_eff, float(negative_slope), ks, stride, pad, _stream())
+    _lib.check(st, "e2f_conv2d_rows_bf16x3")
+    if want_rows:
+        return RowsNHWC(ohi, olo, (n, cout, h, w), out_lead, cout)
     t32 = o32.permute(0, 3, 1, 2) if want_f32 else None
     sp = SplitNHWC(ohi, olo, (n, cout, h, w)) if want_split else None
     return t32 if out == "f32" else sp if out == "split" else (t32, sp)

@@ -175,6 +175,36 @@ int e2f_conv2d_bf16x3(int nsrc, const void* const* src_hi, const void* const* sr
                       void* out_hi, void* out_lo, int n, int h, int w, int cout, int groups, float leaky_slope,
                       int ksize, int stride, int pad, void* stream);
 
+/* Small-channel convolutions (SPyNet's 7x7 convs with 8 / 32 / 16 input channels, flow_comp.py:181-215; the 3-channel
+ * stride-2 stem, e2fgvi.py:76) with "window-packed" K, and the row-gapped layout that feeds them.
+ *
+ * Row-gapped NHWC: [N][H][P][C] bf16 (hi, lo) followed by e2f_conv_rows_tail(lead, C) pixels, with the row pitch
+ * P = e2f_conv_rows_pitch(W, lead, C) = lead + W (rounded up to a 16-byte row for C = 4); pixel (y, x) lives at
+ * y*P + lead + x; the `lead` pixels in front of every row, any rounding pixel behind it and the tail are zero.  With lead = the consuming conv's padding the gap is the left
+ * padding of its row and the right padding of the previous one, and 64/C consecutive pixels x C channels form one
+ * contiguous 64-element K chunk — a whole slice of a kernel row — that TMA fetches as a sliding window (tensor-map
+ * pixel stride = one pixel).  A 7x7 conv over 8 channels takes 7 K chunks per tile instead of 49 zero-padded ones.
+ *
+ *   e2f_pack_rows_bf16     : NCHW fp32 [N][C][H][W] (C <= cin, cin in {4, 8, 16, 32}) -> row-gapped (hi, lo) with cin
+ *                            channels (extra channels zero).
+ *   e2f_conv2d_rows_bf16x3 : e2f_conv2d_bf16x3 plus
+ *       in_rows  != 0: src_hi[0] / src_lo[0] is ONE row-gapped source with lead == pad and src_channels[0] = cin
+ *                      (nsrc == 1, groups == 1, stride*cin*2 % 16 == 0).  Weights: [Cout][k * G * 64] with
+ *                      G = ceil(k / PX), PX = 64 / cin:  K index ((ky*G + g)*64 + px*cin + c)  <->  W[co][c][ky][g*PX+px],
+ *                      zero for g*PX + px >= k (see e2fgvi_b200.ops.pack_conv_rows_weight).
+ *       out_lead  > 0: out_hi / out_lo are written row-gapped with this lead ([N][Ho][out_lead + Wo][Cout] + tail, Cout >= 8,
+ *                      gaps and tail zeroed by the kernel) for a following window-packed conv; 0 = dense NHWC.
+ *   e2f_conv_rows_pitch / e2f_conv_rows_tail : row pitch and number of tail pixels of a row-gapped buffer (host
+ *                            arithmetic, no CUDA call). */
+int e2f_conv_rows_pitch(int w, int lead, int channels);
+int e2f_conv_rows_tail(int lead, int channels);
+int e2f_pack_rows_bf16(const float* x, void* out_hi, void* out_lo, int n, int c, int h, int w, int cin, int lead,
+                       void* stream);
+int e2f_conv2d_rows_bf16x3(int nsrc, const void* const* src_hi, const void* const* src_lo, const int* src_channels,
+                           int in_rows, const void* w_hi, const void* w_lo, const float* bias, const float* residual,
+                           float* out, void* out_hi, void* out_lo, int out_lead, int n, int h, int w, int cout, int groups,
+                           float leaky_slope, int ksize, int stride, int pad, void* stream);
+
 /* Number of kernel launches issued through this library since load (all threads); used by bench.py's
  * "gpu_launches" accounting. */
 int64_t e2f_launch_count(void);

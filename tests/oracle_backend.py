@@ -71,8 +71,12 @@ def _layer_norm(x, weight, bias, eps=1e-5, out="f32"):
     return (y, y) if out == "both" else y
 
 
+def _pack_rows(x, lead, cin=None):
+    return x
+
+
 def _conv3x3(sources, weight, bias=None, groups=1, negative_slope=1.0, residual=None, out="f32", stride=1,
-             padding=None):
+             padding=None, out_lead=0):
     F = torch.nn.functional
     srcs = sources if isinstance(sources, (list, tuple)) else [sources]
     if groups == 1:
@@ -100,11 +104,11 @@ def oracle_ops():
     saved = {n: getattr(ops, n) for n in ("flow_warp", "pack_dcn_weight", "deform_align_fused",
                                           "modulated_deform_conv2d", "focal_window_attention", "t2t_unfold",
                                           "t2t_fold", "linear", "conv3x3", "split_nhwc", "upsample2x_split",
-                                          "layer_norm", "dcn_pack_input", "t2t_fold_unfold")}
+                                          "layer_norm", "dcn_pack_input", "t2t_fold_unfold", "pack_rows")}
     ops.flow_warp, ops.pack_dcn_weight, ops.deform_align_fused = _flow_warp, _pack, _fused
     ops.modulated_deform_conv2d, ops.focal_window_attention = _mdcn, _attention
     ops.t2t_unfold, ops.t2t_fold, ops.linear, ops.t2t_fold_unfold = _unfold, _fold, _linear, _fold_unfold
-    ops.conv3x3, ops.split_nhwc = _conv3x3, _split_nhwc
+    ops.conv3x3, ops.split_nhwc, ops.pack_rows = _conv3x3, _split_nhwc, _pack_rows
     ops.upsample2x_split, ops.layer_norm, ops.dcn_pack_input = _upsample, _layer_norm, _dcn_pack_input
     try:
         yield

@@ -412,3 +412,86 @@ def test_conv2d_kxk_stride(cuda, case):
                       negative_slope=0.0, stride=stride)
     assert got.shape == want.shape, (got.shape, want.shape)
     assert _rel(got.cpu(), want) < 5e-5, _rel(got.cpu(), want)
+
+
+# ------------------------------------------------------------------------------------------ window-packed small-channel convs
+@pytest.mark.parametrize("case", [
+    dict(n=2, h=32, w=64, cin=8, cout=32, ks=7, stride=1, out="rows"),      # SPyNet conv 0 -> row-gapped 32 channels
+    dict(n=2, h=13, w=21, cin=32, cout=64, ks=7, stride=1, out="split"),    # SPyNet conv 1, ragged tile, 4 chunks/row
+    dict(n=1, h=4, w=8, cin=32, cout=16, ks=7, stride=1, out="rows"),       # SPyNet conv 3, image smaller than a tile
+    dict(n=3, h=2, w=4, cin=16, cout=2, ks=7, stride=1, out="f32"),         # SPyNet conv 4, coarsest level
+    dict(n=2, h=30, w=54, cin=3, cout=64, ks=3, stride=2, out="split"),     # encoder stem: 3 channels in a 4-channel row
+    dict(n=1, h=17, w=33, cin=3, cout=64, ks=3, stride=2, out="f32"),       # ... odd input size
+    dict(n=1, h=9, w=20, cin=5, cout=8, ks=3, stride=1, out="rows"),        # 5 channels padded to 8, 3x3
+    dict(n=1, h=12, w=40, cin=8, cout=24, ks=5, stride=2, out="f32"),       # 5x5 stride 2, one chunk per kernel row
+    dict(n=1, h=12, w=40, cin=16, cout=8, ks=7, stride=2, out="rows"),      # stride 2, PX=4, 2 chunks per kernel row
+])
+def test_conv_rows_window_packed(cuda, case):
+    """Window-packed K on the row-gapped layout equals F.conv2d (fp64) to bf16x3 accuracy; row-gapped outputs carry
+    zero gaps / tail and the right content."""
+    F = torch.nn.functional
+    g = torch.Generator().manual_seed(77)
+    n, h, w, cin, cout, ks, stride = (case[k] for k in ("n", "h", "w", "cin", "cout", "ks", "stride"))
+    pad = ks // 2
+    x = torch.randn(n, cin, h, w, generator=g)
+    weight = torch.nn.Parameter(torch.randn(cout, cin, ks, ks, generator=g) / (ks * ks * cin) ** 0.5)
+    bias = torch.randn(cout, generator=g) * 0.1
+    want = F.relu(F.conv2d(x.double(), weight.detach().double(), bias.double(), stride, pad))
+    wd = torch.nn.Parameter(weight.detach().to(cuda))
+    rows = ops.pack_rows(x.to(cuda), lead=pad)
+    assert rows.cin == ops.rows_channels(cin) and rows.lead == pad
+    assert (rows.dense().cpu() - x).abs().max().item() < 4e-5           # bf16 two-term split of the input
+    got = ops.conv3x3(rows, wd, bias.to(cuda), negative_slope=0.0, stride=stride, out=case["out"], out_lead=2)
+    if case["out"] == "rows":
+        ho, wo = want.shape[2:]
+        assert got.shape == tuple(want.shape) and got.lead == 2 and got.cin == cout
+        body = (got.hi.float() + got.lo.float())
+        tail = ops._lib.load().e2f_conv_rows_tail(2, cout)
+        assert body.numel() == (n * ho * (wo + 2) + tail) * cout
+        grid = body[: n * ho * (wo + 2) * cout].view(n, ho, wo + 2, cout)
+        assert float(grid[:, :, :2].abs().max()) == 0.0 and float(body[n * ho * (wo + 2) * cout:].abs().max()) == 0.0
+        got = got.dense()
+    elif case["out"] == "split":
+        got = _join(got).permute(0, 3, 1, 2)
+    assert got.shape == want.shape, (got.shape, want.shape)
+    assert _rel(got.cpu(), want) < 5e-5, _rel(got.cpu(), want)
+    # same result as the tap-per-chunk path on the dense layout
+    dense = ops.conv3x3([x.to(cuda)], wd, bias.to(cuda), negative_slope=0.0, stride=stride)
+    assert _rel(got.cpu(), dense.cpu().double()) < 5e-5
+
+
+def test_conv_rows_chain_matches_spynet_level(cuda):
+    """The five 7x7 convs of one SPyNet level (flow_comp.py:181-215), chained through row-gapped / dense hand-offs."""
+    F = torch.nn.functional
+    g = torch.Generator().manual_seed(78)
+    x = torch.randn(3, 8, 24, 40, generator=g)
+    chans = [(8, 32), (32, 64), (64, 32), (32, 16), (16, 2)]
+    ws = [torch.randn(co, ci, 7, 7, generator=g) / (49 * ci) ** 0.5 for ci, co in chans]
+    bs = [torch.randn(co, generator=g) * 0.1 for _, co in chans]
+    want = x.double()
+    for i, (wt, b) in enumerate(zip(ws, bs)):
+        want = F.conv2d(want, wt.double(), b.double(), 1, 3)
+        if i < 4:
+            want = F.relu(want)
+    y = ops.pack_rows(x.to(cuda), lead=3)
+    for i, (wt, b) in enumerate(zip(ws, bs)):
+        wd = torch.nn.Parameter(wt.to(cuda))
+        if i == 4:
+            y = ops.conv3x3(y, wd, b.to(cuda), out="f32")
+        elif chans[i + 1][0] <= 32:
+            y = ops.conv3x3(y, wd, b.to(cuda), negative_slope=0.0, out="rows", out_lead=3)
+        else:
+            y = ops.conv3x3(y, wd, b.to(cuda), negative_slope=0.0, out="split")
+    assert _rel(y.cpu(), want) < 1e-4, _rel(y.cpu(), want)
+
+
+def test_conv_rows_argument_errors(cuda):
+    x = torch.randn(1, 8, 8, 8, device=cuda)
+    w = torch.nn.Parameter(torch.randn(16, 8, 3, 3, device=cuda))
+    rows = ops.pack_rows(x, lead=2)                       # lead must equal the conv's padding (1)
+    with pytest.raises(ValueError):
+        ops.conv3x3(rows, w)
+    with pytest.raises(ValueError):
+        ops.pack_rows(torch.randn(1, 40, 8, 8, device=cuda), lead=1)
+    with pytest.raises(ValueError):
+        ops.conv3x3([x], torch.nn.Parameter(torch.randn(64, 8, 3, 3, device=cuda)), out="rows", out_lead=1)   # 64 channels

@@ -34,6 +34,10 @@ SHAPES = [
     ("dec1 128->64 @120", 64, [128], 120, 216, 64, 1, 3, 1, "f32"),
     ("dec2 64->64 @240", 64, [64], 240, 432, 64, 1, 3, 1, "split"),
     ("dec3 64->3 @240", 64, [64], 240, 432, 3, 1, 3, 1, "f32"),
+    # experiments (not layers of the path): epilogue / weight-tile effects
+    ("x dec3 64->32 f32", 64, [64], 240, 432, 32, 1, 3, 1, "f32"),
+    ("x dec3 64->8 f32", 64, [64], 240, 432, 8, 1, 3, 1, "f32"),
+    ("x dec2 64->64 f32", 64, [64], 240, 432, 64, 1, 3, 1, "f32"),
 ]
 only = sys.argv[1] if len(sys.argv) > 1 else ""
 g = torch.Generator(device="cpu").manual_seed(0)
@@ -42,23 +46,27 @@ for name, n, cins, h, w, cout, groups, ks, stride, out in SHAPES:
     if only and only not in name:
         continue
     srcs = [ops.split_nhwc(torch.randn(n, c, h, w, device=dev)) for c in cins]
+    variants = [("", srcs)]
+    if len(cins) == 1 and cins[0] <= 32 and groups == 1:
+        variants.append((" [rows]", ops.pack_rows(torch.randn(n, cins[0], h, w, device=dev), lead=ks // 2)))
     wt = torch.randn(cout, sum(cins) // groups, ks, ks, device=dev) * 0.05
     bias = torch.randn(cout, device=dev)
-    run = lambda: ops.conv3x3(srcs, wt, bias, groups=groups, negative_slope=0.2, out=out, stride=stride)  # noqa: E731
-    for _ in range(3):
-        run()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    reps = 10
-    e0.record()
-    for _ in range(reps):
-        run()
-    e1.record()
-    torch.cuda.synchronize()
-    us = e0.elapsed_time(e1) / reps * 1e3
-    ho, wo = (h + 2 * (ks // 2) - ks) // stride + 1, (w + 2 * (ks // 2) - ks) // stride + 1
-    flops = 2.0 * n * ho * wo * cout * (sum(cins) // groups) * ks * ks
-    total += us
-    print(f"CONV {name:24s} {us:9.1f} us  {flops / us / 1e6:8.1f} TFLOP/s")
-    del srcs
+    for tag, src in variants:
+        run = lambda: ops.conv3x3(src, wt, bias, groups=groups, negative_slope=0.2, out=out, stride=stride)  # noqa: E731
+        for _ in range(3):
+            run()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 10
+        e0.record()
+        for _ in range(reps):
+            run()
+        e1.record()
+        torch.cuda.synchronize()
+        us = e0.elapsed_time(e1) / reps * 1e3
+        ho, wo = (h + 2 * (ks // 2) - ks) // stride + 1, (w + 2 * (ks // 2) - ks) // stride + 1
+        flops = 2.0 * n * ho * wo * cout * (sum(cins) // groups) * ks * ks
+        total += us if tag or len(variants) == 1 else 0.0
+        print(f"CONV {name + tag:30s} {us:9.1f} us  {flops / us / 1e6:8.1f} TFLOP/s")
+    del srcs, variants
 print(f"CONV total {total / 1e3:.2f} ms")
