@@ -110,7 +110,7 @@ int e2f_focal_window_attention(const void* qkv, const void* qkv_pooled, void* ou
   if (b < 0 || t <= 0 || h <= 0 || w <= 0 || heads <= 0 || wh <= 0 || ww <= 0 || eh < 0 || ew < 0) { set_error("e2f_focal_window_attention: bad shape"); return E2F_ERR_BAD_ARG; }
   if (h % wh || w % ww) { set_error("e2f_focal_window_attention: token grid %dx%d is not a multiple of the window %dx%d", h, w, wh, ww); return E2F_ERR_BAD_ARG; }
   if (use_pooled && (fh <= 0 || fw <= 0 || !(fh & 1) || !(fw & 1))) { set_error("e2f_focal_window_attention: pooled neighbourhood %dx%d must be odd", fh, fw); return E2F_ERR_BAD_ARG; }
-  if (out_dtype != E2F_F32 && out_dtype != E2F_F16) { set_error("e2f_focal_window_attention: out_dtype %d", out_dtype); return E2F_ERR_BAD_ARG; }
+  if (out_dtype != E2F_F32 && out_dtype != E2F_F16 && out_dtype != E2F_SPLIT_BF16) { set_error("e2f_focal_window_attention: out_dtype %d", out_dtype); return E2F_ERR_BAD_ARG; }
   if (head_dim != 128) { set_error("e2f_focal_window_attention: head_dim %d unsupported (128 only)", head_dim); return E2F_ERR_UNSUPPORTED; }
   if (!aligned(qkv, 16) || !aligned(out, 16) || (use_pooled && !aligned(qkv_pooled, 16))) { set_error("e2f_focal_window_attention: 16-byte alignment required"); return E2F_ERR_ALIGNMENT; }
   return finish(launch_focal_attention(qkv, qkv_pooled, out, b, t, h, w, heads, head_dim, wh, ww, eh, ew, fh, fw,
@@ -151,6 +151,17 @@ int e2f_t2t_fold_unfold(const float* tokens_in, float* tokens, void* tokens_hi, 
   st = launch_t2t_fold_unfold(tokens_in, tokens, tokens_hi, tokens_lo, bt, c, h, w, k, stride, pad, gelu, static_cast<cudaStream_t>(stream));
   if (st == E2F_ERR_UNSUPPORTED) { set_error("e2f_t2t_fold_unfold: only k=7 stride=3 pad=3, C %% 4 == 0, bt <= 65535 and W <= 1800 are fused (k=%d s=%d p=%d c=%d w=%d); compose e2f_t2t_fold + e2f_t2t_unfold", k, stride, pad, c, w); return st; }
   return finish(st, "e2f_t2t_fold_unfold");
+}
+
+int e2f_window_pool(const void* x_hi, const void* x_lo, const float* weight, const float* bias, float* out, void* out_hi,
+                    void* out_lo, int bt, int h, int w, int c, int wh, int ww, void* stream) {
+  if (!x_hi || !x_lo || !weight) { set_error("e2f_window_pool: null pointer"); return E2F_ERR_BAD_ARG; }
+  if ((!out && !out_hi) || (!out_hi) != (!out_lo)) { set_error("e2f_window_pool: need out and/or both of out_hi/out_lo"); return E2F_ERR_BAD_ARG; }
+  if (bt < 0 || h <= 0 || w <= 0 || c <= 0 || wh <= 0 || ww <= 0) { set_error("e2f_window_pool: bad shape"); return E2F_ERR_BAD_ARG; }
+  if (h % wh || w % ww) { set_error("e2f_window_pool: token grid %dx%d is not a multiple of the window %dx%d", h, w, wh, ww); return E2F_ERR_BAD_ARG; }
+  if (c % 8 || wh > 8 || static_cast<size_t>(wh) * c * 4 > 48 * 1024 || bt > 65535) { set_error("e2f_window_pool: needs C %% 8 == 0, wh <= 8, wh*C <= 12288, bt <= 65535 (c=%d wh=%d bt=%d)", c, wh, bt); return E2F_ERR_UNSUPPORTED; }
+  if (!aligned(x_hi, 16) || !aligned(x_lo, 16) || (out && !aligned(out, 16)) || (out_hi && (!aligned(out_hi, 16) || !aligned(out_lo, 16)))) { set_error("e2f_window_pool: 16-byte alignment required"); return E2F_ERR_ALIGNMENT; }
+  return finish(launch_window_pool(x_hi, x_lo, weight, bias, out, out_hi, out_lo, bt, h, w, c, wh, ww, static_cast<cudaStream_t>(stream)), "e2f_window_pool");
 }
 
 int e2f_upsample2x_split(const float* x, void* out_hi, void* out_lo, int n, int h, int w, int c, void* stream) {

@@ -108,6 +108,75 @@ __global__ void __launch_bounds__(256) layernorm_split_kernel(const float* __res
   }
 }
 
+// Window pooling of the focal attention's coarse level (pool_layers[0] = nn.Linear(wh*ww, 1) applied across the tokens
+// of each window, per channel; tfocal_transformer.py:508-516):
+//   out[bt][wi][wj][c] = bias + sum_{r,q} x[bt][wi*wh + r][wj*ww + q][c] * weight[r*ww + q]
+// x comes as the bf16 (hi, lo) pair LayerNorm already wrote for the qkv Linear, so the fp32 copy of the normed tokens
+// is never materialised; the result goes out as the (hi, lo) operand pair of the pooled qkv Linear (and/or fp32).
+// Block = one window x 64 channel-octets x wh window rows (threadIdx.y); rows reduced through shared memory.
+__global__ void __launch_bounds__(512) window_pool_kernel(const __nv_bfloat16* __restrict__ xh,
+                                                          const __nv_bfloat16* __restrict__ xl,
+                                                          const float* __restrict__ weight, const float* __restrict__ bias,
+                                                          float* __restrict__ out, __nv_bfloat16* __restrict__ out_hi,
+                                                          __nv_bfloat16* __restrict__ out_lo, int H, int W, int C, int wh,
+                                                          int ww) {
+  extern __shared__ float red[];                   // [wh][C]
+  const int nww = W / ww, nwh = H / wh;
+  const int win = blockIdx.x, bt = blockIdx.y;
+  const int wi = win / nww, wj = win - wi * nww;
+  const int r = threadIdx.y;
+  for (int c0 = threadIdx.x * 8; c0 < C; c0 += blockDim.x * 8) {
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const size_t row0 = ((static_cast<size_t>(bt) * H + wi * wh + r) * W + wj * ww) * C + c0;
+    for (int q = 0; q < ww; ++q) {
+      const float wt = __ldg(weight + r * ww + q);
+      const uint4 a = __ldg(reinterpret_cast<const uint4*>(xh + row0 + static_cast<size_t>(q) * C));
+      const uint4 b = __ldg(reinterpret_cast<const uint4*>(xl + row0 + static_cast<size_t>(q) * C));
+      const uint32_t ah[4] = {a.x, a.y, a.z, a.w}, bl[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 fh = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ah[e]));
+        const float2 fl = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&bl[e]));
+        acc[2 * e] = fmaf(fh.x + fl.x, wt, acc[2 * e]);
+        acc[2 * e + 1] = fmaf(fh.y + fl.y, wt, acc[2 * e + 1]);
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) red[r * C + c0 + e] = acc[e];
+  }
+  __syncthreads();
+  if (r == 0) {
+    const float b0 = bias ? __ldg(bias) : 0.f;
+    for (int c0 = threadIdx.x * 8; c0 < C; c0 += blockDim.x * 8) {
+      float f[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        float t = b0;
+        for (int k = 0; k < wh; ++k) t += red[k * C + c0 + e];
+        f[e] = t;
+      }
+      const size_t o = ((static_cast<size_t>(bt) * nwh + wi) * nww + wj) * C + c0;
+      if (out) {
+        float4* d4 = reinterpret_cast<float4*>(out + o);
+        d4[0] = make_float4(f[0], f[1], f[2], f[3]);
+        d4[1] = make_float4(f[4], f[5], f[6], f[7]);
+      }
+      if (out_hi) split_store8(f, out_hi + o, out_lo + o);
+    }
+  }
+}
+
+int launch_window_pool(const void* xh, const void* xl, const float* weight, const float* bias, float* out, void* out_hi,
+                       void* out_lo, int bt, int h, int w, int c, int wh, int ww, cudaStream_t stream) {
+  if (bt == 0) return 0;
+  const dim3 grid((h / wh) * (w / ww), bt), block(c / 8 < 64 ? c / 8 : 64, wh);
+  window_pool_kernel<<<grid, block, static_cast<size_t>(wh) * c * sizeof(float), stream>>>(
+      static_cast<const __nv_bfloat16*>(xh), static_cast<const __nv_bfloat16*>(xl), weight, bias, out,
+      static_cast<__nv_bfloat16*>(out_hi), static_cast<__nv_bfloat16*>(out_lo), h, w, c, wh, ww);
+  count_launch();
+  return static_cast<int>(cudaGetLastError());
+}
+
 int launch_upsample2x_split(const float* x, void* hi, void* lo, int n, int h, int w, int c, cudaStream_t stream) {
   const long long total = static_cast<long long>(n) * 4 * h * w * (c / 8);
   if (total == 0) return 0;

@@ -26,6 +26,8 @@
 //              buffer that held P(kt) without any extra barrier (the tensor pipe executes in order)
 // Roofline: 4*B*nW*heads*(T*wh*ww)*(T*(wh*ww+ring+fh*fw))*128 FLOP on the tensor pipe.
 #include <cstdlib>
+#include <type_traits>
+#include <cuda_bf16.h>
 #include "common.cuh"
 #include "launch.h"
 
@@ -70,6 +72,7 @@ struct Params {
   const __half* qkv;
   const __half* pooled;
   void* out;
+  void* out_lo;                   // E2F_SPLIT_BF16 only: low term, [B][T][H][W][C] bf16 right behind the high term
   int B, T, H, W, heads, C;       // C = heads*128
   int wh, ww, eh, ew, fh, fw;
   int nWh, nWw;
@@ -176,6 +179,10 @@ __device__ __forceinline__ float max_chunk(const uint32_t (&sv)[32], const float
   const float m = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
   return MODE == MODE_BIASED ? m : m * sc;      // scale > 0: max commutes with the scaling
 }
+
+struct SplitBf16 {                // output tag: bf16 (hi, lo) two-term split of the result (operand of e2f_linear_bf16x3)
+  __nv_bfloat16 v;
+};
 
 template <typename OutT>
 __global__ void __launch_bounds__(THREADS, CTAS_PER_SM) focal_attn_kernel(const __grid_constant__ Params prm) {
@@ -340,11 +347,13 @@ __global__ void __launch_bounds__(THREADS, CTAS_PER_SM) focal_attn_kernel(const 
     const int qi = qt * BM + r;
     const float inv_l = 1.0f / l;
     OutT* dst = nullptr;
+    size_t dst_off = 0;
     if (qi < nq) {
       const int t = qi / area, p = qi - t * area;
       const int y = wi * prm.wh + p / prm.ww, x = wj * prm.ww + p % prm.ww;
       const size_t tok = ((static_cast<size_t>(b) * prm.T + t) * prm.H + y) * prm.W + x;
-      dst = static_cast<OutT*>(prm.out) + tok * prm.C + head * HD;
+      dst_off = tok * prm.C + head * HD;
+      dst = static_cast<OutT*>(prm.out) + dst_off;
     }
 #pragma unroll 1
     for (int c = 0; c < 4; ++c) {
@@ -352,7 +361,25 @@ __global__ void __launch_bounds__(THREADS, CTAS_PER_SM) focal_attn_kernel(const 
       tmem_ld32(lane_addr + COL_O + c * 32, ov);
       tmem_ld_wait();
       if (dst) {
-        if constexpr (sizeof(OutT) == 4) {
+        if constexpr (std::is_same<OutT, SplitBf16>::value) {
+          uint4* dh = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(prm.out) + dst_off + c * 32);
+          uint4* dl = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(prm.out_lo) + dst_off + c * 32);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            uint32_t hp[4], lp[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float f0 = __uint_as_float(ov[8 * i + 2 * j]) * inv_l, f1 = __uint_as_float(ov[8 * i + 2 * j + 1]) * inv_l;
+              const __nv_bfloat162 hb = __floats2bfloat162_rn(f0, f1);
+              const float2 hf = __bfloat1622float2(hb);
+              const __nv_bfloat162 lb = __floats2bfloat162_rn(f0 - hf.x, f1 - hf.y);
+              hp[j] = *reinterpret_cast<const uint32_t*>(&hb);
+              lp[j] = *reinterpret_cast<const uint32_t*>(&lb);
+            }
+            dh[i] = make_uint4(hp[0], hp[1], hp[2], hp[3]);
+            dl[i] = make_uint4(lp[0], lp[1], lp[2], lp[3]);
+          }
+        } else if constexpr (sizeof(OutT) == 4) {
           float4* d4 = reinterpret_cast<float4*>(dst + c * 32);
 #pragma unroll
           for (int i = 0; i < 8; ++i)
@@ -596,7 +623,18 @@ int launch_focal_attention(const void* qkv, const void* qkv_pooled, void* out, i
   }
   const dim3 grid((t * wh * ww + BM - 1) / BM, heads, static_cast<unsigned>(nwin));
   cudaError_t e;
-  if (out_dtype == 1) {
+  prm.out_lo = nullptr;
+  if (out_dtype == 2) {
+    prm.out_lo = static_cast<__nv_bfloat16*>(prm.out) + static_cast<size_t>(b) * t * h * w * prm.C;
+    static bool cfg = false;
+    if (!cfg) {
+      e = cudaFuncSetAttribute(focal_attn_kernel<SplitBf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+      if (e != cudaSuccess) return static_cast<int>(e);
+      cudaFuncSetAttribute(focal_attn_kernel<SplitBf16>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+      cfg = true;
+    }
+    focal_attn_kernel<SplitBf16><<<grid, THREADS, SMEM_BYTES, stream>>>(prm);
+  } else if (out_dtype == 1) {
     static bool cfg = false;
     if (!cfg) {
       e = cudaFuncSetAttribute(focal_attn_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);

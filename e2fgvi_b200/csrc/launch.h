@@ -30,6 +30,8 @@ int launch_t2t_unfold(const float* img, float* tok, void* tok_hi, void* tok_lo, 
 int launch_upsample2x_split(const float* x, void* hi, void* lo, int n, int h, int w, int c, cudaStream_t stream);
 int launch_layernorm_split(const float* x, const float* gamma, const float* beta, float* out, void* hi, void* lo,
                            long long rows, int c, float eps, cudaStream_t stream);
+int launch_window_pool(const void* xh, const void* xl, const float* weight, const float* bias, float* out, void* out_hi,
+                       void* out_lo, int bt, int h, int w, int c, int wh, int ww, cudaStream_t stream);
 int launch_t2t_fold_unfold(const float* tin, float* tok, void* tok_hi, void* tok_lo, int bt, int c, int h, int w, int k,
                            int s, int p, int gelu, cudaStream_t stream);
 int launch_t2t_fold(const float* tok, const float* bias, float* img, int bt, int c, int h, int w, int k, int s,

@@ -68,30 +68,42 @@ __global__ void __launch_bounds__(256) t2t_unfold733_kernel(const float* __restr
   const int c0 = blockIdx.x * U2_CC, ty = blockIdx.y;
   const long long bt = blockIdx.z;
   const float* src = img + (bt * C + c0) * static_cast<long long>(H) * W;
-  for (int i = threadIdx.x; i < U2_CC * 7 * WP; i += blockDim.x) {
-    const int xx = i % WP, r = (i / WP) % 7, cc = i / (7 * WP);
-    const int y = ty * 3 - 3 + r, x = xx - 3;
-    float v = 0.f;
-    if (y >= 0 && y < H && x >= 0 && x < W) {
-      v = __ldg(src + (static_cast<long long>(cc) * H + y) * W + x);
-      if (GELU) v = gelu_exact(v);
+  // one warp per (channel, image row) of the 8 x 7 rows, lanes along x: no per-element index arithmetic
+  for (int rr = threadIdx.x >> 5; rr < U2_CC * 7; rr += 8) {
+    const int cc = rr / 7, r = rr - cc * 7;
+    const int y = ty * 3 - 3 + r;
+    const bool row_ok = y >= 0 && y < H;
+    const float* srow = src + (static_cast<long long>(cc) * H + y) * W;
+    for (int xx = threadIdx.x & 31; xx < WP; xx += 32) {
+      const int x = xx - 3;
+      float v = 0.f;
+      if (row_ok && x >= 0 && x < W) {
+        v = __ldg(srow + x);
+        if (GELU) v = gelu_exact(v);
+      }
+      simg[rr * WP + xx] = v;
     }
-    simg[i] = v;
+  }
+  // thread -> fixed float4 slot q4 of a token's 8*49-value run: the (channel, ky, kx) decode happens once per thread;
+  // 98 slots x 2 tokens in flight per pass (196 of 256 threads active)
+  constexpr int RUN4 = U2_CC * 49 / 4, TSUB = 256 / RUN4;
+  const int q4 = threadIdx.x % RUN4, tsub = threadIdx.x / RUN4;
+  int off[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const int q = q4 * 4 + e;
+    const int cc = q / 49, kk = q - cc * 49;
+    const int ky = kk / 7;
+    off[e] = (cc * 7 + ky) * WP + (kk - ky * 7);
   }
   __syncthreads();
-  const int CK = C * 49, RUN = U2_CC * 49;         // 392 values per token and chunk (multiple of 4)
+  const int CK = C * 49;
   const long long tok0 = (bt * FH + ty) * static_cast<long long>(FW);
-  for (int o = threadIdx.x * 4; o < FW * RUN; o += blockDim.x * 4) {
-    const int tx = o / RUN, rem = o - tx * RUN;
+  for (int tx = tsub; tx < (tsub < TSUB ? FW : 0); tx += TSUB) {
     float v[4];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const int q = rem + e;
-      const int cc = q / 49, kk = q - cc * 49;
-      const int ky = kk / 7, kx = kk - ky * 7;
-      v[e] = simg[(cc * 7 + ky) * WP + tx * 3 + kx];
-    }
-    const long long dst = (tok0 + tx) * CK + c0 * 49 + rem;
+    for (int e = 0; e < 4; ++e) v[e] = simg[tx * 3 + off[e]];
+    const long long dst = (tok0 + tx) * CK + c0 * 49 + q4 * 4;
     if (tok) *reinterpret_cast<float4*>(tok + dst) = make_float4(v[0], v[1], v[2], v[3]);
     if (tok_hi) {
       const __nv_bfloat162 h0 = __floats2bfloat162_rn(v[0], v[1]), h1 = __floats2bfloat162_rn(v[2], v[3]);
@@ -103,28 +115,42 @@ __global__ void __launch_bounds__(256) t2t_unfold733_kernel(const float* __restr
   }
 }
 
-// Fused fold -> / fold(ones) -> unfold -> GELU of the fusion feed-forward (tfocal_transformer.py:89-96) for the 7/3/3
-// geometry: the folded image never goes to HBM.  One block per (CC-channel chunk, band of TR token rows, image):
-//   1. the CC*49 values of every token in rows [ty0-2, ty0+TR+1] are read ONCE, fully coalesced (float4), and added
-//      into the band's folded image in shared memory.  Tokens are visited in 9 phases (ty mod 3, tx mod 3): patches
-//      of one phase are disjoint (stride 3 * 3 >= 7), so plain += suffices — no atomics;
-//   2. every pixel is divided by its patch count and passed through GELU once;
-//   3. the TR x FW tokens of the band are written as coalesced runs (bf16 hi/lo operand pair and/or fp32).
-// Algorithmic bytes: tokens in (x (TR+4)/TR halo re-read, served by L2) + tokens out.
-template <bool GELU, int CC>
-__global__ void __launch_bounds__(256) t2t_fold_unfold733_kernel(const float* __restrict__ tin, float* __restrict__ tok,
-                                                                 __nv_bfloat16* __restrict__ tok_hi,
-                                                                 __nv_bfloat16* __restrict__ tok_lo, int C, int H,
-                                                                 int W, int FH, int FW, int TR) {
-  extern __shared__ float simg[];                  // [CC][ROWS][WP], x padded by 3 on both sides
+// Shared-memory fold for the 7/3/3 geometry, used two ways:
+//   FUSED  = true : fold -> / fold(ones) -> unfold -> GELU of the fusion feed-forward (tfocal_transformer.py:89-96);
+//                   the folded image never goes to HBM.  Block = (CC-channel chunk, band of TR token rows, image).
+//   FUSED  = false: fold (-> / fold(ones)) (+ bias map) of SoftComp (tfocal_transformer.py:65-72) and of the generic
+//                   e2f_t2t_fold.  Block = (CC-channel chunk, band of 3*TR image rows, image).
+// Steps:
+//   1. the CC*49 values of every token whose patch touches the band are read ONCE, fully coalesced (float4), and
+//      added into the band's folded image in shared memory.  Tokens are visited in 9 phases (ty mod 3, tx mod 3):
+//      patches of one phase are disjoint (stride 3 * 3 >= 7), so plain += suffices — no atomics, deterministic;
+//   2. every pixel is divided by its patch count (and passed through GELU / gets its bias) once;
+//   3. FUSED: the TR x FW tokens of the band are written as coalesced runs (bf16 hi/lo operand pair and/or fp32).
+// Algorithmic bytes: tokens in (x (TR+4)/TR or (TR+2)/TR halo re-read, served by L2) + tokens / image out.
+template <bool FUSED, bool GELU, int CC>
+__global__ void __launch_bounds__(256) t2t_fold733_kernel(const float* __restrict__ tin, float* __restrict__ tok,
+                                                          __nv_bfloat16* __restrict__ tok_hi,
+                                                          __nv_bfloat16* __restrict__ tok_lo, float* __restrict__ img,
+                                                          const float* __restrict__ bias, int normalize, int C, int H,
+                                                          int W, int FH, int FW, int TR) {
+  extern __shared__ float simg[];                  // [CC][ROWS][WP], x padded by 3 on both sides; then nx[WP]
   constexpr int RUN4 = CC * 49 / 4;
-  const int WP = W + 6, ROWS = 3 * TR + 4;
-  const int c0 = blockIdx.x * CC, ty0 = blockIdx.y * TR;
+  const int WP = W + 6, ROWS = FUSED ? 3 * TR + 4 : 3 * TR;
+  int* nxtab = reinterpret_cast<int*>(simg + CC * ROWS * WP);
+  const int c0 = blockIdx.x * CC, band = blockIdx.y;
   const long long bt = blockIdx.z;
+  const int ty0 = band * TR;                       // FUSED: first token row of the band
   const int tr = min(TR, FH - ty0);
-  const int ybase = 3 * ty0 - 3;                   // image row held by smem row 0
+  const int ybase = FUSED ? 3 * ty0 - 3 : 3 * TR * band;   // image row held by smem row 0
   const int CK = C * 49;
-  for (int i = threadIdx.x; i < CC * ROWS * WP; i += blockDim.x) simg[i] = 0.f;
+  {
+    float4* z = reinterpret_cast<float4*>(simg);   // CC * ROWS * WP * 4 bytes is a multiple of 16 (CC = 4)
+    for (int i = threadIdx.x; i < CC * ROWS * WP / 4; i += blockDim.x) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int xx = threadIdx.x; xx < WP; xx += blockDim.x) {
+      const int x = xx - 3;                        // #token columns covering x: tx in [ceil((x-3)/3), floor((x+3)/3)]
+      nxtab[xx] = (x >= 0 && x < W) ? min(FW - 1, (x + 3) / 3) - max(0, (x - 1) / 3) + 1 : 0;
+    }
+  }
   // thread -> fixed float4 slot q4 of a token's CC*49 run, so the (channel, ky, kx) decode happens once per thread:
   // RUN4 = 49 slots x TSUB tokens in flight per pass (245 of 256 threads active)
   constexpr int TSUB = 256 / RUN4;
@@ -139,7 +165,9 @@ __global__ void __launch_bounds__(256) t2t_fold_unfold733_kernel(const float* __
     off[e] = (cc * ROWS + kyv[e]) * WP + (kk - kyv[e] * 7);
   }
   __syncthreads();
-  const int tin_lo = max(0, ty0 - 2), tin_hi = min(FH - 1, ty0 + tr + 1);
+  // token rows whose patches touch image rows [ybase, ybase + ROWS)
+  const int tin_lo = FUSED ? max(0, ty0 - 2) : max(0, TR * band - 1);
+  const int tin_hi = FUSED ? min(FH - 1, ty0 + tr + 1) : min(FH - 1, TR * band + TR);
   const float* src = tin + bt * FH * FW * static_cast<long long>(CK) + c0 * 49;
   for (int phase = 0; phase < 9; ++phase) {
     const int a = phase / 3, b = phase - 3 * a;
@@ -147,6 +175,7 @@ __global__ void __launch_bounds__(256) t2t_fold_unfold733_kernel(const float* __
     const int nty = first_ty <= tin_hi ? (tin_hi - first_ty) / 3 + 1 : 0;
     const int ntx = b < FW ? (FW - 1 - b) / 3 + 1 : 0;
     const int ntok = active ? nty * ntx : 0;
+    const float inv_ntx = 1.0f / static_cast<float>(max(ntx, 1));
     // U tokens per thread in flight: all global loads of a batch are issued before the first shared-memory update
     constexpr int U = 6;
     for (int tt = tsub; tt < ntok; tt += TSUB * U) {
@@ -156,10 +185,10 @@ __global__ void __launch_bounds__(256) t2t_fold_unfold733_kernel(const float* __
       for (int u = 0; u < U; ++u) {
         const int t = tt + u * TSUB;
         if (t < ntok) {
-          const int tyi = t / ntx, txi = t - tyi * ntx;
+          const int tyi = __float2int_rz((static_cast<float>(t) + 0.5f) * inv_ntx), txi = t - tyi * ntx;
           const int ty = first_ty + 3 * tyi, tx = b + 3 * txi;
           v4[u] = __ldg(reinterpret_cast<const float4*>(src + static_cast<long long>(ty * FW + tx) * CK) + q4);
-          r0[u] = 3 * ty - 3 - ybase;              // smem row of the patch's first row (negative above the band)
+          r0[u] = 3 * ty - 3 - ybase;              // smem row of the patch's first row (may lie outside the band)
           base[u] = r0[u] * WP + 3 * tx;
         }
       }
@@ -167,34 +196,62 @@ __global__ void __launch_bounds__(256) t2t_fold_unfold733_kernel(const float* __
       for (int u = 0; u < U; ++u) {
         if (tt + u * TSUB < ntok) {
           const float v[4] = {v4[u].x, v4[u].y, v4[u].z, v4[u].w};
+          if (r0[u] >= 0 && r0[u] + 7 <= ROWS) {   // patch entirely inside the band: no per-element checks
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int r = r0[u] + kyv[e];
-            if (r >= 0 && r < ROWS) simg[base[u] + off[e]] += v[e];
+            for (int e = 0; e < 4; ++e) simg[base[u] + off[e]] += v[e];
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int r = r0[u] + kyv[e];
+              if (r >= 0 && r < ROWS) simg[base[u] + off[e]] += v[e];
+            }
           }
         }
       }
     }
     __syncthreads();
   }
-  // patch count of a pixel = (#token rows covering y) * (#token columns covering x); padding -> 0
-  for (int i = threadIdx.x; i < CC * ROWS * WP; i += blockDim.x) {
-    const int xx = i % WP, r = (i / WP) % ROWS;
-    const int y = ybase + r, x = xx - 3;
-    float v = 0.f;
-    if (y >= 0 && y < H && x >= 0 && x < W) {
-      const int ny = min(FH - 1, (y + 3) / 3) - max(0, (y - 1) / 3) + 1;     // ty in [ceil((y-3)/3), floor((y+3)/3)]
-      const int nx = min(FW - 1, (x + 3) / 3) - max(0, (x - 1) / 3) + 1;
-      v = simg[i] / static_cast<float>(ny * nx);
-      if (GELU) v = gelu_exact(v);
+  // per pixel: / patch count = (#token rows covering y) * (#token columns covering x); then GELU (FUSED) or the store
+  // of the image row (+ bias).  One warp per (channel, row), lanes along x.
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int rr = warp; rr < CC * ROWS; rr += 8) {
+    const int cc = rr / ROWS, r = rr - cc * ROWS;
+    const int y = ybase + r;
+    float* row = simg + rr * WP;
+    if (y < 0 || y >= H) {
+      if (FUSED)
+        for (int xx = lane; xx < WP; xx += 32) row[xx] = 0.f;
+      continue;
     }
-    simg[i] = v;
+    const int ny = min(FH - 1, (y + 3) / 3) - max(0, (y - 1) / 3) + 1;     // ty in [ceil((y-3)/3), floor((y+3)/3)]
+    if (FUSED) {
+      for (int xx = lane; xx < WP; xx += 32) {
+        const int nx = nxtab[xx];
+        float v = 0.f;
+        if (nx) {
+          v = row[xx] / static_cast<float>(ny * nx);
+          if (GELU) v = gelu_exact(v);
+        }
+        row[xx] = v;
+      }
+    } else {
+      const long long plane = ((bt * C + c0 + cc) * H + y) * static_cast<long long>(W);
+      const float* brow = bias ? bias + (static_cast<long long>(c0 + cc) * H + y) * W : nullptr;
+      for (int x = lane; x < W; x += 32) {
+        float v = row[x + 3];
+        if (normalize) v = v / static_cast<float>(ny * nxtab[x + 3]);
+        if (brow) v += __ldg(brow + x);
+        img[plane + x] = v;
+      }
+    }
   }
+  if (!FUSED) return;
   __syncthreads();
   const long long tok0 = (bt * FH + ty0) * static_cast<long long>(FW);
   const int nout = active ? tr * FW : 0;
+  const float inv_fw = 1.0f / static_cast<float>(FW);
   for (int t = tsub; t < nout; t += TSUB) {
-    const int tyl = t / FW, tx = t - tyl * FW;
+    const int tyl = __float2int_rz((static_cast<float>(t) + 0.5f) * inv_fw), tx = t - tyl * FW;
     const int base = 3 * tyl * WP + 3 * tx, rem = q4 * 4;
     float v[4];
 #pragma unroll
@@ -286,6 +343,34 @@ int launch_t2t_unfold(const float* img, float* tok, void* tok_hi_v, void* tok_lo
   return static_cast<int>(cudaGetLastError());
 }
 
+// Band height (in token rows) of t2t_fold733_kernel and its dynamic shared memory: the tallest band that keeps 3 blocks
+// per SM; wide images (few rows fit) take up to 200 KB instead.  rows(tr) = 3*tr + extra image rows.  0 = does not fit.
+static int fold733_band(int w, int fh, int extra_rows, size_t* smem) {
+  constexpr int CC = 4;
+  const size_t row_bytes = static_cast<size_t>(CC) * (w + 6) * sizeof(float), tab = (w + 6) * sizeof(int);
+  auto band_rows = [&](size_t budget) {
+    const long long rows = static_cast<long long>((budget - tab) / row_bytes) - extra_rows;
+    return rows < 3 ? 0 : static_cast<int>(rows / 3);
+  };
+  int tr = band_rows(72 * 1024);
+  if (tr < 5 && tr < fh) tr = band_rows(200 * 1024);
+  if (tr < 1) return 0;
+  tr = tr < fh ? tr : fh;
+  const int bands = (fh + tr - 1) / tr;
+  tr = (fh + bands - 1) / bands;                   // even out the bands
+  *smem = row_bytes * (3 * tr + extra_rows) + tab;
+  return tr;
+}
+
+static void fold733_configure() {
+  static bool cfg = false;
+  if (cfg) return;
+  cudaFuncSetAttribute(t2t_fold733_kernel<true, true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(t2t_fold733_kernel<true, false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(t2t_fold733_kernel<false, false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cfg = true;
+}
+
 // Fused fold/normalise/unfold(/GELU).  Returns -2 (unsupported) when the geometry is not 7/3/3 or no band fits in
 // shared memory; the caller then composes launch_t2t_fold + launch_t2t_unfold.
 int launch_t2t_fold_unfold(const float* tin, float* tok, void* tok_hi, void* tok_lo, int bt, int c, int h, int w, int k,
@@ -295,29 +380,17 @@ int launch_t2t_fold_unfold(const float* tin, float* tok, void* tok_hi, void* tok
   const int fh = (h + 2 * p - k) / s + 1, fw = (w + 2 * p - k) / s + 1;
   if (bt == 0 || fh <= 0 || fw <= 0) return 0;
   if (bt > 65535) return -2;
-  // band height: the tallest that keeps 3 blocks per SM; wide images (few rows fit) take up to 200 KB instead
-  const size_t row_bytes = static_cast<size_t>(CC) * (w + 6) * sizeof(float);
-  auto band_rows = [&](size_t budget) { return budget / row_bytes < 7 ? 0 : static_cast<int>((budget / row_bytes - 4) / 3); };
-  int tr = band_rows(72 * 1024);
-  if (tr < 5 && tr < fh) tr = band_rows(200 * 1024);
+  size_t smem = 0;
+  const int tr = fold733_band(w, fh, 4, &smem);
   if (tr < 1) return -2;
-  tr = tr < fh ? tr : fh;
-  const int bands = (fh + tr - 1) / tr;
-  tr = (fh + bands - 1) / bands;                   // even out the bands
-  const size_t smem = row_bytes * (3 * tr + 4);
   auto* hi = static_cast<__nv_bfloat16*>(tok_hi);
   auto* lo = static_cast<__nv_bfloat16*>(tok_lo);
-  const dim3 grid(c / CC, bands, bt);
-  static bool cfg = false;
-  if (!cfg) {
-    cudaFuncSetAttribute(t2t_fold_unfold733_kernel<true, CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(t2t_fold_unfold733_kernel<false, CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cfg = true;
-  }
+  const dim3 grid(c / CC, (fh + tr - 1) / tr, bt);
+  fold733_configure();
   if (gelu)
-    t2t_fold_unfold733_kernel<true, CC><<<grid, 256, smem, stream>>>(tin, tok, hi, lo, c, h, w, fh, fw, tr);
+    t2t_fold733_kernel<true, true, CC><<<grid, 256, smem, stream>>>(tin, tok, hi, lo, nullptr, nullptr, 1, c, h, w, fh, fw, tr);
   else
-    t2t_fold_unfold733_kernel<false, CC><<<grid, 256, smem, stream>>>(tin, tok, hi, lo, c, h, w, fh, fw, tr);
+    t2t_fold733_kernel<true, false, CC><<<grid, 256, smem, stream>>>(tin, tok, hi, lo, nullptr, nullptr, 1, c, h, w, fh, fw, tr);
   count_launch();
   return static_cast<int>(cudaGetLastError());
 }
@@ -329,6 +402,19 @@ int launch_t2t_fold(const float* tok, const float* bias, float* img, int bt, int
   if (total == 0) return 0;
   const int threads = 256;
   const unsigned blocks = static_cast<unsigned>((total + threads - 1) / threads);
+  if (k == 7 && s == 3 && p == 3 && c % 4 == 0 && bt <= 65535) {
+    // shared-memory fold: coalesced token reads, one block per (4 channels, band of 3*tr image rows, image)
+    size_t smem = 0;
+    const int tr = fold733_band(w, (h + 2) / 3, 0, &smem);
+    if (tr >= 1) {
+      fold733_configure();
+      const dim3 grid(c / 4, (h + 3 * tr - 1) / (3 * tr), bt);
+      t2t_fold733_kernel<false, false, 4><<<grid, 256, smem, stream>>>(tok, nullptr, nullptr, nullptr, img, bias, normalize, c, h,
+                                                                       w, fh, fw, tr);
+      count_launch();
+      return static_cast<int>(cudaGetLastError());
+    }
+  }
   if (k == 7 && s == 3 && p == 3)
     t2t_fold_kernel<7, 3, 3><<<blocks, threads, 0, stream>>>(tok, bias, img, bt, c, h, w, k, s, p, fh, fw, normalize);
   else

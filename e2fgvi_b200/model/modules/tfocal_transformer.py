@@ -35,8 +35,8 @@ class SoftSplit(nn.Module):
     def forward(self, x, b, output_size=None):
         output_size = output_size or self.output_size
         f_h, f_w = _token_grid(output_size, self.kernel_size, self.stride, self.padding)
-        feat = ops.linear(ops.t2t_unfold(x, self.kernel_size, self.stride, self.padding), self.embedding.weight,
-                          self.embedding.bias)
+        feat = ops.linear(ops.t2t_unfold(x, self.kernel_size, self.stride, self.padding, out="split"),
+                          self.embedding.weight, self.embedding.bias)
         return feat.view(b, -1, f_h, f_w, feat.size(2))
 
 
@@ -156,15 +156,16 @@ class WindowAttention(nn.Module):
         return tuple(2 * (i // 2) + 1 for i in self.focal_window)
 
     def attend(self, x, pooled, residual=None):
-        """x (B,T,H,W,C) normed tokens (tensor or ops.SplitMat), pooled (B,nWh,nWw,T,C) -> (B,T,H,W,C) after proj
-        (+ residual)."""
+        """x (B,T,H,W,C) normed tokens (tensor or ops.SplitMat), pooled (B,nWh,nWw,T,C) tensor or the SplitMat of
+        ops.window_pool (already (B,T,nWh,nWw,C)) -> (B,T,H,W,C) after proj (+ residual)."""
         qkv = ops.linear(x, self.qkv.weight, self.qkv.bias, out_dtype=torch.float16)
         qkv_pooled = None
         if self.uses_pooled:
-            qkv_pooled = ops.linear(pooled.permute(0, 3, 1, 2, 4).contiguous(), self.qkv.weight, self.qkv.bias,
-                                    out_dtype=torch.float16)
+            if not isinstance(pooled, ops.SplitMat):      # reference layout (B,nWh,nWw,T,C) -> (B,T,nWh,nWw,C)
+                pooled = pooled.permute(0, 3, 1, 2, 4).contiguous()
+            qkv_pooled = ops.linear(pooled, self.qkv.weight, self.qkv.bias, out_dtype=torch.float16)
         out = ops.focal_window_attention(qkv, qkv_pooled, self.num_heads, self.window_size, self.expand_size,
-                                         self.pooled_kernel(), self.scale, out_dtype=torch.float32)
+                                         self.pooled_kernel(), self.scale, out_dtype="split")
         return ops.linear(out, self.proj.weight, self.proj.bias, residual=residual)
 
     def forward(self, x_all, mask_all=None):
@@ -214,9 +215,14 @@ class TemporalFocalTransformerBlock(nn.Module):
     def _forward(self, x, output_size):
         shortcut = x
         B, T, H, W, C = x.shape
-        # LayerNorm writes fp32 (for the window pooling) and the bf16 split operand of the qkv Linear in one pass
-        xn, xn_split = ops.layer_norm(x, self.norm1.weight, self.norm1.bias, self.norm1.eps, out="both")
-        pooled = self._pool_windows(xn) if self.attn.uses_pooled else None
+        # LayerNorm writes the bf16 split operand of the qkv Linear; the window pooling reads the same pair
+        xn_split = ops.layer_norm(x, self.norm1.weight, self.norm1.bias, self.norm1.eps, out="split")
+        pooled = None
+        if self.attn.uses_pooled:
+            if H % self.window_size[0] or W % self.window_size[1]:
+                raise ValueError(f"token grid {H}x{W} must be a multiple of the window {self.window_size}")
+            lin = self.pool_layers[0]
+            pooled = ops.window_pool(xn_split, lin.weight, lin.bias, self.window_size, out="split")
         x = self.attn.attend(xn_split, pooled, residual=shortcut)
         y = ops.layer_norm(x, self.norm2.weight, self.norm2.bias, self.norm2.eps, out="split")
         return self.mlp(y.view(B, T * H * W, C), output_size, residual=x.view(B, T * H * W, C)).view(B, T, H, W, C)

@@ -203,7 +203,9 @@ def focal_window_attention(qkv, qkv_pooled, num_heads, window_size, expand_size,
                            out_dtype=torch.float16):
     """softmax(q k_all^T) v_all of tfocal_transformer.py:226-396, un-partitioned output.
 
-    qkv (B,T,H,W,3C) fp16, qkv_pooled (B,T,nWh,nWw,3C) fp16 or None (focal_level 1) -> (B,T,H,W,C).
+    qkv (B,T,H,W,3C) fp16, qkv_pooled (B,T,nWh,nWw,3C) fp16 or None (focal_level 1) -> (B,T,H,W,C) in
+    ``out_dtype`` (torch.float32 / torch.float16), or — ``out_dtype="split"`` — a ``SplitMat``, the bf16 (hi, lo)
+    operand pair of the following ``linear`` (attn.proj) written by the epilogue.
     """
     _need_cuda(qkv, qkv_pooled)
     B, T, H, W, C3 = qkv.shape
@@ -219,15 +221,19 @@ def focal_window_attention(qkv, qkv_pooled, num_heads, window_size, expand_size,
             raise ValueError(f"qkv_pooled shape {tuple(qkv_pooled.shape)} != {(B, T, H // wh, W // ww, C3)}")
         if qkv_pooled.dtype != torch.float16 or not qkv_pooled.is_contiguous():
             qkv_pooled = qkv_pooled.contiguous().half()
-    out = torch.empty((B, T, H, W, C), dtype=out_dtype, device=qkv.device)
+    split = isinstance(out_dtype, str) and out_dtype == "split"
+    if split:
+        out = torch.empty((2, B, T, H, W, C), dtype=torch.bfloat16, device=qkv.device)
+    else:
+        out = torch.empty((B, T, H, W, C), dtype=out_dtype, device=qkv.device)
     with _timed("focal_window_attention", attention_flops(B, T, H, W, C, window_size, expand_size, focal_window,
                                                             use_pooled)):
         st = _lib.load().e2f_focal_window_attention(
             qkv.data_ptr(), qkv_pooled.data_ptr() if use_pooled else None, out.data_ptr(), B, T, H, W, num_heads,
             C // num_heads, wh, ww, expand_size[0], expand_size[1], focal_window[0], focal_window[1],
-            1 if use_pooled else 0, float(scale), _DT[out_dtype], _stream())
+            1 if use_pooled else 0, float(scale), 2 if split else _DT[out_dtype], _stream())
     _lib.check(st, "e2f_focal_window_attention")
-    return out
+    return SplitMat(out[0], out[1]) if split else out
 
 
 class SplitMat:
@@ -311,6 +317,37 @@ def t2t_fold_unfold(tokens, output_size, kernel_size, stride, padding, gelu=Fals
                                              1 if gelu else 0, _stream())
     _lib.check(st, "e2f_t2t_fold_unfold")
     return tok if out == "f32" else SplitMat(hi, lo)
+
+
+def window_pool(x, weight, bias, window_size, out="split"):
+    """pool_layers[0] (``nn.Linear(wh*ww, 1)`` across the tokens of each window, per channel; tfocal_transformer.py:
+    508-516) in one kernel.  x: the split LayerNorm output as a ``SplitMat`` of shape (B,T,H,W,C); weight (1, wh*ww);
+    bias (1,).  Returns the pooled tokens ordered (B,T,nWh,nWw,C) — the reference's (B,nWh,nWw,T,C) after its
+    ``permute(0,3,1,2,4)`` — as fp32 (out="f32") or ``SplitMat`` (out="split")."""
+    if not isinstance(x, SplitMat):
+        raise TypeError("window_pool takes the SplitMat written by layer_norm(out='split')")
+    _need_cuda(x.hi, weight, bias)
+    B, T, H, W, C = x.shape
+    wh, ww = window_size
+    if H % wh or W % ww:
+        raise ValueError(f"token grid {H}x{W} must be a multiple of the window {wh}x{ww}")
+    shape = (B, T, H // wh, W // ww, C)
+    dev = x.hi.device
+    w32 = weight.detach().float().contiguous()
+    b32 = None if bias is None else bias.detach().float().contiguous()
+    o32 = torch.empty(shape, dtype=torch.float32, device=dev) if out == "f32" else None
+    ohi = torch.empty(shape, dtype=torch.bfloat16, device=dev) if out == "split" else None
+    olo = torch.empty(shape, dtype=torch.bfloat16, device=dev) if out == "split" else None
+    if out not in ("f32", "split"):
+        raise ValueError("out must be 'f32' or 'split'")
+    with _timed("window_pool", float(x.hi.numel() * 4)):
+        st = _lib.load().e2f_window_pool(x.hi.data_ptr(), x.lo.data_ptr(), w32.data_ptr(),
+                                         None if b32 is None else b32.data_ptr(),
+                                         None if o32 is None else o32.data_ptr(),
+                                         None if ohi is None else ohi.data_ptr(),
+                                         None if olo is None else olo.data_ptr(), B * T, H, W, C, wh, ww, _stream())
+    _lib.check(st, "e2f_window_pool")
+    return o32 if out == "f32" else SplitMat(ohi, olo)
 
 
 def upsample2x_split(x):

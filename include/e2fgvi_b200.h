@@ -34,6 +34,8 @@ extern "C" {
 /* element types */
 #define E2F_F32 0
 #define E2F_F16 1
+#define E2F_SPLIT_BF16 2 /* e2f_focal_window_attention only: out = [2][B][T][H][W][C] bf16, the (hi, lo) two-term split
+                          * of the fp32 result = the A operand pair of the following e2f_linear_bf16x3 (attn.proj) */
 
 /* padding modes of e2f_flow_warp (reference: F.grid_sample padding_mode) */
 #define E2F_PAD_ZEROS 0
@@ -123,6 +125,16 @@ int e2f_t2t_fold(const float* tokens, const float* bias, float* img, int bt, int
  * e2f_t2t_unfold (fp32 and/or bf16 hi/lo pair). */
 int e2f_t2t_fold_unfold(const float* tokens_in, float* tokens, void* tokens_hi, void* tokens_lo, int bt, int c, int h,
                         int w, int k, int stride, int pad, int gelu, void* stream);
+
+/* Window pooling of the focal attention's coarse level: pool_layers[0] = nn.Linear(wh*ww, 1) across the tokens of
+ * every window, per channel (tfocal_transformer.py:508-516, the permute/Linear/squeeze chain):
+ *   out[bt][wi][wj][c] = bias[0] + sum_{r<wh, q<ww} x[bt][wi*wh + r][wj*ww + q][c] * weight[r*ww + q]
+ * x_hi / x_lo [BT][H][W][C] bf16 = the split LayerNorm output (e2f_layernorm_split), weight [wh*ww] fp32, bias [1]
+ * fp32 or NULL.  Outputs (at least one): out [BT][H/wh][W/ww][C] fp32 and/or its bf16 (hi, lo) split — the operand of
+ * the pooled qkv Linear.  (The reference orders the pooled tokens (B, nWh, nWw, T, C); this is its
+ * permute(0,3,1,2,4), which is what the qkv Linear + attention consume.) */
+int e2f_window_pool(const void* x_hi, const void* x_lo, const float* weight, const float* bias, float* out, void* out_hi,
+                    void* out_lo, int bt, int h, int w, int c, int wh, int ww, void* stream);
 
 /* x2 bilinear upsample, align_corners=True (F.interpolate in deconv.forward, e2fgvi.py:125-129) of an NHWC fp32
  * tensor [N][H][W][C] (C % 8 == 0), written directly as the bf16 (hi, lo) split [N][2H][2W][C] consumed by

@@ -36,7 +36,8 @@ def _mdcn(x, offset, mask, weight, bias=None, stride=1, padding=0, dilation=1, g
 def _attention(qkv, qkv_pooled, num_heads, window_size, expand_size, focal_window, scale, out_dtype=torch.float32):
     return restate.focal_window_attention(qkv.float(), None if qkv_pooled is None else qkv_pooled.float(), num_heads,
                                           window_size, expand_size, focal_window, scale,
-                                          rolled_valid_indices(window_size, expand_size)).to(out_dtype)
+                                          rolled_valid_indices(window_size, expand_size)).to(
+                                              torch.float32 if isinstance(out_dtype, str) else out_dtype)
 
 
 def _unfold(img, kernel_size, stride, padding, gelu=False, out="f32"):
@@ -69,6 +70,14 @@ def _upsample(x):
 def _layer_norm(x, weight, bias, eps=1e-5, out="f32"):
     y = torch.nn.functional.layer_norm(x, (x.shape[-1],), weight, bias, eps)
     return (y, y) if out == "both" else y
+
+
+def _window_pool(x, weight, bias, window_size, out="split"):
+    """Reference formulation (tfocal_transformer.py:508-516), returned in the reference layout (B,nWh,nWw,T,C)."""
+    B, T, H, W, C = x.shape
+    wh, ww = window_size
+    xw = x.view(B, T, H // wh, wh, W // ww, ww, C).permute(0, 2, 4, 1, 3, 5, 6).reshape(B, H // wh, W // ww, T, wh * ww, C)
+    return torch.nn.functional.linear(xw.transpose(4, 5), weight, bias).flatten(-2)
 
 
 def _pack_rows(x, lead, cin=None):
@@ -104,11 +113,11 @@ def oracle_ops():
     saved = {n: getattr(ops, n) for n in ("flow_warp", "pack_dcn_weight", "deform_align_fused",
                                           "modulated_deform_conv2d", "focal_window_attention", "t2t_unfold",
                                           "t2t_fold", "linear", "conv3x3", "split_nhwc", "upsample2x_split",
-                                          "layer_norm", "dcn_pack_input", "t2t_fold_unfold", "pack_rows")}
+                                          "layer_norm", "dcn_pack_input", "t2t_fold_unfold", "pack_rows", "window_pool")}
     ops.flow_warp, ops.pack_dcn_weight, ops.deform_align_fused = _flow_warp, _pack, _fused
     ops.modulated_deform_conv2d, ops.focal_window_attention = _mdcn, _attention
     ops.t2t_unfold, ops.t2t_fold, ops.linear, ops.t2t_fold_unfold = _unfold, _fold, _linear, _fold_unfold
-    ops.conv3x3, ops.split_nhwc, ops.pack_rows = _conv3x3, _split_nhwc, _pack_rows
+    ops.conv3x3, ops.split_nhwc, ops.pack_rows, ops.window_pool = _conv3x3, _split_nhwc, _pack_rows, _window_pool
     ops.upsample2x_split, ops.layer_norm, ops.dcn_pack_input = _upsample, _layer_norm, _dcn_pack_input
     try:
         yield

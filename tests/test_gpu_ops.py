@@ -178,6 +178,18 @@ def test_focal_window_attention_base_size_fp16_out(cuda):
     assert _rel(got, want) < 3e-3
 
 
+def test_focal_window_attention_split_out(cuda):
+    """out_dtype="split": the bf16 (hi, lo) pair equals the fp32 output to the two-term split's 2^-17."""
+    g = torch.Generator().manual_seed(28)
+    qkv = torch.randn(2, 3, 10, 18, 1536, generator=g).half().to(cuda)
+    pooled = torch.randn(2, 3, 2, 2, 1536, generator=g).half().to(cuda)
+    args = (4, (5, 9), (2, 4), (5, 9), 128 ** -0.5)
+    f32 = ops.focal_window_attention(qkv, pooled, *args, out_dtype=torch.float32)
+    sp = ops.focal_window_attention(qkv, pooled, *args, out_dtype="split")
+    assert isinstance(sp, ops.SplitMat) and sp.shape == f32.shape
+    assert (sp.hi.float() + sp.lo.float() - f32).abs().max().item() < 2e-5 * f32.abs().max().item() + 1e-7
+
+
 def test_focal_attention_rows_sum_property(cuda):
     """Size-independent property at a large size (B=8 clips): with v == 1 the output must be exactly
     (sum_j p_j) / (sum_j p_j + n_masked * exp(-100 - m)) ~= 1 for every token, whatever q and k are."""
@@ -495,3 +507,28 @@ def test_conv_rows_argument_errors(cuda):
         ops.pack_rows(torch.randn(1, 40, 8, 8, device=cuda), lead=1)
     with pytest.raises(ValueError):
         ops.conv3x3([x], torch.nn.Parameter(torch.randn(64, 8, 3, 3, device=cuda)), out="rows", out_lead=1)   # 64 channels
+
+
+@pytest.mark.parametrize("shape", [(2, 8, 20, 36, 512, (5, 9)), (1, 3, 10, 18, 512, (5, 9)), (1, 2, 8, 6, 64, (4, 3))])
+def test_window_pool(cuda, shape):
+    """pool_layers[0] across each window's tokens (tfocal_transformer.py:508-516) from the split LayerNorm output."""
+    B, T, H, W, C, (wh, ww) = shape
+    g = torch.Generator().manual_seed(91)
+    x = torch.randn(B, T, H, W, C, generator=g)
+    lin = torch.nn.Linear(wh * ww, 1)
+    with torch.no_grad():
+        lin.weight.copy_(torch.randn(1, wh * ww, generator=g) / (wh * ww))
+        lin.bias.fill_(0.37)
+    # reference chain: window_partition_noreshape -> (B,nWh,nWw,T,wh*ww,C) -> Linear over the window axis
+    xw = x.view(B, T, H // wh, wh, W // ww, ww, C).permute(0, 2, 4, 1, 3, 5, 6).reshape(B, H // wh, W // ww, T, wh * ww, C)
+    want = lin(xw.transpose(4, 5)).flatten(-2).permute(0, 3, 1, 2, 4).detach()          # (B,T,nWh,nWw,C)
+    hi, lo = ops.split_bf16(x.to(cuda))
+    sp = ops.SplitMat(hi.view(B, T, H, W, C), lo.view(B, T, H, W, C))
+    got = ops.window_pool(sp, lin.weight.to(cuda), lin.bias.to(cuda), (wh, ww), out="f32")
+    assert got.shape == want.shape
+    assert (got.cpu() - want).abs().max().item() < 2e-5
+    got_sp = ops.window_pool(sp, lin.weight.to(cuda), lin.bias.to(cuda), (wh, ww), out="split")
+    assert (_join(got_sp).cpu() - want).abs().max().item() < 5e-5
+    with pytest.raises(ValueError):
+        ops.window_pool(ops.SplitMat(hi.view(B, T, H, W, C)[:, :, :-1], lo.view(B, T, H, W, C)[:, :, :-1]),
+                        lin.weight.to(cuda), lin.bias.to(cuda), (wh, ww))

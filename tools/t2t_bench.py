@@ -36,3 +36,21 @@ for name, fn in (("fold+unfold", pair), ("fused", fused)):
     torch.cuda.synchronize()
     us = e0.elapsed_time(e1) / 10 * 1e3
     print(f"T2T {name:12s} {us:8.1f} us   {tok.numel() * 8 / us / 1e6:.2f} TB/s of the fused kernel's algorithmic bytes")
+
+# SoftComp fold (tokens 64 x 720 x 6272 -> 128 x 60 x 108, + bias) and SoftSplit unfold (the reverse, split output)
+tok2 = torch.randn(bt, 720, 6272, device=dev)
+img2 = torch.randn(bt, 128, 60, 108, device=dev)
+bias = torch.randn(128, 60, 108, device=dev)
+for name, fn, nbytes in (("sc fold", lambda: ops.t2t_fold(tok2, (60, 108), *geo, bias=bias), tok2.numel() * 4 + img2.numel() * 4),
+                         ("ss unfold", lambda: ops.t2t_unfold(img2, *geo, out="split"), tok2.numel() * 4 + img2.numel() * 4)):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    us = e0.elapsed_time(e1) / 10 * 1e3
+    print(f"T2T {name:12s} {us:8.1f} us   {nbytes / us / 1e6:.2f} TB/s")
