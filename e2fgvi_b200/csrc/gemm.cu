@@ -14,6 +14,7 @@
 // tile i's epilogue overlaps tile i+1's main loop.  smem ring: STAGES x (Ah 16K + Al 16K + Wh + Wl).
 // Roofline: tensor-bound, 3 x 2*M*N*K bf16 FLOP of tensor work per 2*M*N*K algorithmic fp32 FLOP.
 #include <cuda.h>
+#include <cstdlib>
 #include <cuda_bf16.h>
 #include "common.cuh"
 #include "launch.h"
@@ -23,8 +24,8 @@ namespace gemm {
 
 constexpr int BM = 128, BK = 64;
 constexpr int A_TILE = BM * BK * 2;                // 16 KB (one bf16 term)
-constexpr int EPI_WARPS = 4;
-constexpr int THREADS = (2 + EPI_WARPS) * 32;      // 192
+constexpr int EPI_WARPS = 8;                       // two warps per TMEM lane quadrant, each owning half of the tile's columns
+constexpr int THREADS = (2 + EPI_WARPS) * 32;      // 320
 
 template <int BN>
 struct Cfg {
@@ -32,7 +33,7 @@ struct Cfg {
   static constexpr int STAGE = 2 * A_TILE + 2 * W_TILE;
   static constexpr int STAGES = (BN == 128) ? 3 : 2;
   static constexpr int TMEM_COLS = 2 * BN;          // double-buffered accumulator (256 or 512 columns)
-  static constexpr int SMEM = STAGES * STAGE + 256 + 1024;
+  static constexpr int SMEM = STAGES * STAGE + 256 + 2 * BN * 4 + 1024;   // + per-tile bias slice, double-buffered
 };
 
 // kind::f16 instruction descriptor with BF16 operands (a_format = b_format = 1), fp32 accumulate, K-major A and B
@@ -41,7 +42,11 @@ __host__ __device__ constexpr uint32_t idesc_bf16(int M, int N) {
          (static_cast<uint32_t>(M >> 4) << 24);
 }
 
-template <int BN, typename OutT>
+// CL = 2: thread-block clusters of two CTAs that work on two M tiles of the same N tile in lockstep.  Each CTA
+// fetches HALF of the W tile and multicasts it to both (W is the larger operand: 64 of the 96 KB per K chunk at
+// BN = 256), which cuts the L2 -> SM traffic that bounds the short-K GEMMs by a third.  A stage is released to the
+// producers of BOTH CTAs by a multicast tcgen05.commit; everything else (MMA, TMEM, epilogue) stays CTA-local.
+template <int BN, typename OutT, int CL>
 __global__ void __launch_bounds__(THREADS, 1)
 linear_kernel(const __grid_constant__ CUtensorMap tm_ah, const __grid_constant__ CUtensorMap tm_al,
               const __grid_constant__ CUtensorMap tm_wh, const __grid_constant__ CUtensorMap tm_wl,
@@ -55,17 +60,23 @@ linear_kernel(const __grid_constant__ CUtensorMap tm_ah, const __grid_constant__
   uint64_t* acc_full = empty + C::STAGES;     // [2]
   uint64_t* acc_empty = acc_full + 2;         // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  float* sbias = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE + 256);   // [2][BN]
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int tiles_m = (M + BM - 1) / BM, tiles_n = (N + BN - 1) / BN;
-  const int num_tiles = tiles_m * tiles_n;
   const int num_kb = (K + BK - 1) / BK;
+  // work item = (N tile, group of CL consecutive M tiles); a cluster walks the items, CTA `rank` takes M tile `rank`
+  // of the group (a tile past the end computes on zero-filled rows and stores nothing)
+  const int rank = CL > 1 ? static_cast<int>(cluster_ctarank()) : 0;
+  const int first_item = blockIdx.x / CL, item_step = gridDim.x / CL;
+  const int num_items = ((tiles_m + CL - 1) / CL) * tiles_n;
+  constexpr uint16_t MC_MASK = (1u << CL) - 1;
 
   if (warp == 1) tmem_alloc(tmem_slot, C::TMEM_COLS);
   if (tid == 0) {
     for (int s = 0; s < C::STAGES; ++s) {
       mbar_init(&full[s], 1);
-      mbar_init(&empty[s], 1);
+      mbar_init(&empty[s], CL);                    // released by the MMA warps of all CTAs that receive the multicast
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&acc_full[s], 1);
@@ -78,7 +89,8 @@ linear_kernel(const __grid_constant__ CUtensorMap tm_ah, const __grid_constant__
     tma_prefetch_desc(&tm_wl);
   }
   tc_fence_before_sync();
-  __syncthreads();
+  if (CL > 1) cluster_sync_all();                  // barriers of every CTA initialised before any remote arrive / copy
+  else __syncthreads();
   tc_fence_after_sync();
   const uint32_t tbase = *tmem_slot;
 
@@ -86,8 +98,8 @@ linear_kernel(const __grid_constant__ CUtensorMap tm_ah, const __grid_constant__
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
       uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
+      for (int item = first_item; item < num_items; item += item_step) {
+        const int m0 = ((item / tiles_n) * CL + rank) * BM, n0 = (item % tiles_n) * BN;
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
           const int stage = it % C::STAGES;
           mbar_wait(&empty[stage], ((it / C::STAGES) & 1) ^ 1);
@@ -95,8 +107,16 @@ linear_kernel(const __grid_constant__ CUtensorMap tm_ah, const __grid_constant__
           const uint32_t s0 = smem_u32(smem + stage * C::STAGE);
           tma_load_2d(s0, &tm_ah, &full[stage], kb * BK, m0);
           tma_load_2d(s0 + A_TILE, &tm_al, &full[stage], kb * BK, m0);
-          tma_load_2d(s0 + 2 * A_TILE, &tm_wh, &full[stage], kb * BK, n0);
-          tma_load_2d(s0 + 2 * A_TILE + C::W_TILE, &tm_wl, &full[stage], kb * BK, n0);
+          if (CL > 1) {
+            // rows [rank*BN/CL, +BN/CL) of the W tile (the maps' box is BN/CL rows), broadcast to the whole cluster
+            const uint32_t part = rank * (C::W_TILE / CL);
+            tma_load_2d_mc(s0 + 2 * A_TILE + part, &tm_wh, &full[stage], kb * BK, n0 + rank * (BN / CL), MC_MASK);
+            tma_load_2d_mc(s0 + 2 * A_TILE + C::W_TILE + part, &tm_wl, &full[stage], kb * BK, n0 + rank * (BN / CL),
+                           MC_MASK);
+          } else {
+            tma_load_2d(s0 + 2 * A_TILE, &tm_wh, &full[stage], kb * BK, n0);
+            tma_load_2d(s0 + 2 * A_TILE + C::W_TILE, &tm_wl, &full[stage], kb * BK, n0);
+          }
         }
       }
     }
@@ -109,7 +129,7 @@ linear_kernel(const __grid_constant__ CUtensorMap tm_ah, const __grid_constant__
       const uint64_t d_al0 = umma_desc_adv(d_ah0, A_TILE), d_wh0 = umma_desc_adv(d_ah0, 2 * A_TILE);
       const uint64_t d_wl0 = umma_desc_adv(d_wh0, C::W_TILE);
       uint32_t it = 0, local = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+      for (int item = first_item; item < num_items; item += item_step, ++local) {
         const int buf = local & 1;
         mbar_wait(&acc_empty[buf], ((local >> 1) & 1) ^ 1);
         tc_fence_after_sync();
@@ -127,46 +147,65 @@ linear_kernel(const __grid_constant__ CUtensorMap tm_ah, const __grid_constant__
             umma_f16(d, dah, dwl, idesc, 1);
             umma_f16(d, dah, dwh, idesc, 1);
           }
-          umma_commit(&empty[stage]);
+          if (CL > 1) umma_commit_mc(&empty[stage], MC_MASK);
+          else umma_commit(&empty[stage]);
         }
         umma_commit(&acc_full[buf]);
       }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue (TMEM lanes by warp id % 4)
-    const int q = warp & 3;
+    // ------------------------------------------------------------------ epilogue
+    // 8 warps: TMEM lane quadrant q = warp % 4 (hardware rule), column half = (warp - 2) / 4.  Per tile the bias slice
+    // goes to shared memory once; the residual of chunk c+1 is fetched while chunk c is converted and stored, and the
+    // first chunk's residual is requested BEFORE waiting for the accumulator, so its latency hides behind the main
+    // loop (short-K GEMMs such as attn.proj used to be bound by these serialised loads).
+    const int q = warp & 3, half = (warp - 2) >> 2;
+    const int et = tid - 64;                                  // 0..255 among the epilogue threads
+    constexpr int CH = BN / 64;                               // 32-column chunks per warp
     uint32_t local = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+    for (int item = first_item; item < num_items; item += item_step, ++local) {
       const int buf = local & 1;
-      const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
+      const int m0 = ((item / tiles_n) * CL + rank) * BM, n0 = (item % tiles_n) * BN;
+      const int row = m0 + q * 32 + lane;
+      float* sb = sbias + buf * BN;
+      if (et < BN) sb[et] = (bias && n0 + et < N) ? __ldg(bias + n0 + et) : 0.f;
+      const bool row_ok = row < M;
+      const size_t orow = static_cast<size_t>(row) * N;
+      float4 rc[8], rn[8];
+      auto fetch = [&](int c, float4* r) {                    // residual of chunk c (full chunks only)
+        const int col0 = n0 + (half * CH + c) * 32;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) r[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (residual && row_ok && col0 + 32 <= N) {
+          const float4* r4 = reinterpret_cast<const float4*>(residual + orow + col0);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) r[i] = __ldg(r4 + i);
+        }
+      };
+      fetch(0, rc);
+      asm volatile("bar.sync 1, 256;" ::: "memory");           // bias slice visible to all epilogue warps
       mbar_wait(&acc_full[buf], (local >> 1) & 1);
       tc_fence_after_sync();
-      const int row = m0 + q * 32 + lane;
-      const uint32_t taddr = tbase + (static_cast<uint32_t>(q * 32) << 16) + buf * BN;
+      const uint32_t taddr = tbase + (static_cast<uint32_t>(q * 32) << 16) + buf * BN + half * (BN / 2);
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = 0; c < CH; ++c) {
         uint32_t v[32];
         tmem_ld32(taddr + c * 32, v);
+        if (c + 1 < CH) fetch(c + 1, rn);
         tmem_ld_wait();
-        const int col0 = n0 + c * 32;
-        if (row < M && col0 < N) {
-          const bool full_chunk = col0 + 32 <= N;
-          float f[32];
+        const int cl = (half * CH + c) * 32;                  // column offset inside the tile
+        const int col0 = n0 + cl;
+        if (row_ok && col0 < N) {
+          const size_t o = orow + col0;
+          if (col0 + 32 <= N) {
+            float f[32];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            float b = 0.f;
-            if (bias && (full_chunk || col0 + i < N)) b = __ldg(bias + col0 + i);
-            f[i] = __uint_as_float(v[i]) + b;
-          }
-          const size_t o = static_cast<size_t>(row) * N + col0;
-          if (full_chunk) {
-            if (residual) {
-              const float4* r4 = reinterpret_cast<const float4*>(residual + o);
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const float4 r = __ldg(r4 + i);
-                f[4 * i] += r.x; f[4 * i + 1] += r.y; f[4 * i + 2] += r.z; f[4 * i + 3] += r.w;
-              }
+            for (int i = 0; i < 8; ++i) {
+              const float4 b4 = *reinterpret_cast<const float4*>(sb + cl + 4 * i);
+              f[4 * i] = __uint_as_float(v[4 * i]) + b4.x + rc[i].x;
+              f[4 * i + 1] = __uint_as_float(v[4 * i + 1]) + b4.y + rc[i].y;
+              f[4 * i + 2] = __uint_as_float(v[4 * i + 2]) + b4.z + rc[i].z;
+              f[4 * i + 3] = __uint_as_float(v[4 * i + 3]) + b4.w + rc[i].w;
             }
             if constexpr (sizeof(OutT) == 4) {
               float4* d4 = reinterpret_cast<float4*>(out + o);
@@ -184,15 +223,17 @@ linear_kernel(const __grid_constant__ CUtensorMap tm_ah, const __grid_constant__
             }
           } else {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {     // static indexing keeps f[] in registers
+            for (int i = 0; i < 32; ++i) {     // static indexing keeps v[] in registers
               if (col0 + i < N) {
-                const float val = f[i] + (residual ? __ldg(residual + o + i) : 0.f);
+                const float val = __uint_as_float(v[i]) + sb[cl + i] + (residual ? __ldg(residual + o + i) : 0.f);
                 if constexpr (sizeof(OutT) == 4) out[o + i] = val;
                 else out[o + i] = __float2half_rn(val);
               }
             }
           }
         }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) rc[i] = rn[i];
       }
       tc_fence_before_sync();
       __syncwarp();
@@ -202,6 +243,7 @@ linear_kernel(const __grid_constant__ CUtensorMap tm_ah, const __grid_constant__
   tc_fence_before_sync();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tbase, C::TMEM_COLS);
+  if (CL > 1) cluster_sync_all();                  // no CTA leaves while a peer may still multicast into it
 }
 
 // x = hi + lo with hi = bf16(x), lo = bf16(x - hi); 8 elements per thread
@@ -265,25 +307,60 @@ static int num_sms() {
   return n;
 }
 
-template <int BN, typename OutT>
+template <int BN, typename OutT, int CL>
 static int launch_variant(const void* ah, const void* al, const void* wh, const void* wl, const float* bias,
                           const float* residual, void* out, int m, int n, int k, cudaStream_t stream) {
   CUtensorMap tah, tal, twh, twl;
   int st;
   if ((st = make_map(&tah, ah, m, k, BM))) return st;
   if ((st = make_map(&tal, al, m, k, BM))) return st;
-  if ((st = make_map(&twh, wh, n, k, BN))) return st;
-  if ((st = make_map(&twl, wl, n, k, BN))) return st;
-  auto kern = linear_kernel<BN, OutT>;
-  static bool configured = false;
-  if (!configured) {
+  if ((st = make_map(&twh, wh, n, k, BN / CL))) return st;
+  if ((st = make_map(&twl, wl, n, k, BN / CL))) return st;
+  auto kern = linear_kernel<BN, OutT, CL>;
+  static int max_ctas = 0;                         // co-resident CTAs (1 per SM; for clusters: CL * active clusters)
+  if (!max_ctas) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM);
     if (e != cudaSuccess) return static_cast<int>(e);
-    configured = true;
+    max_ctas = num_sms();
+    if (CL > 1) {
+      cudaLaunchConfig_t qc = {};
+      qc.gridDim = dim3(num_sms() / CL * CL);
+      qc.blockDim = dim3(THREADS);
+      qc.dynamicSmemBytes = Cfg<BN>::SMEM;
+      cudaLaunchAttribute qa[1];
+      qa[0].id = cudaLaunchAttributeClusterDimension;
+      qa[0].val.clusterDim.x = CL;
+      qa[0].val.clusterDim.y = 1;
+      qa[0].val.clusterDim.z = 1;
+      qc.attrs = qa;
+      qc.numAttrs = 1;
+      int clusters = 0;
+      e = cudaOccupancyMaxActiveClusters(&clusters, kern, &qc);
+      if (e != cudaSuccess || clusters < 1) {
+        max_ctas = 0;
+        set_error("linear: cudaOccupancyMaxActiveClusters failed (%s)", cudaGetErrorString(e));
+        return -4;
+      }
+      max_ctas = clusters * CL;
+    }
   }
-  const int tiles = ((m + BM - 1) / BM) * ((n + BN - 1) / BN);
-  const int grid = tiles < num_sms() ? tiles : num_sms();
-  kern<<<grid, THREADS, Cfg<BN>::SMEM, stream>>>(tah, tal, twh, twl, bias, residual, static_cast<OutT*>(out), m, n, k);
+  const int tiles_m = (m + BM - 1) / BM, tiles_n = (n + BN - 1) / BN;
+  const int items = ((tiles_m + CL - 1) / CL) * tiles_n;
+  const int grid = (items * CL < max_ctas) ? items * CL : max_ctas;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(THREADS);
+  cfg.dynamicSmemBytes = Cfg<BN>::SMEM;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t le = cudaLaunchKernelEx(&cfg, kern, tah, tal, twh, twl, bias, residual, static_cast<OutT*>(out), m, n, k);
+  if (le != cudaSuccess) return static_cast<int>(le);
   count_launch();
   return static_cast<int>(cudaGetLastError());
 }
@@ -305,11 +382,18 @@ int launch_linear_bf16x3(const void* a_hi, const void* a_lo, const void* w_hi, c
                          cudaStream_t stream) {
   using namespace gemm;
   if (m == 0 || n == 0) return 0;
-  if (block_n == 256)
-    return out_dtype == 1 ? launch_variant<256, __half>(a_hi, a_lo, w_hi, w_lo, bias, residual, out, m, n, k, stream)
-                          : launch_variant<256, float>(a_hi, a_lo, w_hi, w_lo, bias, residual, out, m, n, k, stream);
-  return out_dtype == 1 ? launch_variant<128, __half>(a_hi, a_lo, w_hi, w_lo, bias, residual, out, m, n, k, stream)
-                        : launch_variant<128, float>(a_hi, a_lo, w_hi, w_lo, bias, residual, out, m, n, k, stream);
+  // clusters of 2 (W multicast) unless there is a single M tile or E2F_LINEAR_CLUSTER=1 asks for the plain kernel
+  static const bool no_cluster = [] {
+    const char* e = getenv("E2F_LINEAR_CLUSTER");
+    return e && e[0] == '1';
+  }();
+  const bool cl2 = !no_cluster && m > BM;
+#define E2F_LINEAR_GO(BNV, T)                                                                                       \
+  (cl2 ? launch_variant<BNV, T, 2>(a_hi, a_lo, w_hi, w_lo, bias, residual, out, m, n, k, stream)                    \
+       : launch_variant<BNV, T, 1>(a_hi, a_lo, w_hi, w_lo, bias, residual, out, m, n, k, stream))
+  if (block_n == 256) return out_dtype == 1 ? E2F_LINEAR_GO(256, __half) : E2F_LINEAR_GO(256, float);
+  return out_dtype == 1 ? E2F_LINEAR_GO(128, __half) : E2F_LINEAR_GO(128, float);
+#undef E2F_LINEAR_GO
 }
 
 }  // namespace e2f
