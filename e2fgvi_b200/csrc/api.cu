@@ -143,12 +143,14 @@ int e2f_t2t_unfold(const float* img, float* tokens, void* tokens_hi, void* token
 }
 
 int e2f_t2t_fold_unfold(const float* tokens_in, float* tokens, void* tokens_hi, void* tokens_lo, int bt, int c, int h,
-                        int w, int k, int stride, int pad, int gelu, void* stream) {
+                        int w, int k, int stride, int pad, int gelu, int out_pitch, void* stream) {
   if ((!tokens && !tokens_hi) || (!tokens_hi) != (!tokens_lo)) { set_error("e2f_t2t_fold_unfold: need tokens and/or both of tokens_hi/tokens_lo"); return E2F_ERR_BAD_ARG; }
   int st = t2t_checks("e2f_t2t_fold_unfold", tokens_in, tokens ? static_cast<const void*>(tokens) : tokens_hi, bt, c, h, w, k, stride, pad);
   if (st) return st;
   if (tokens_hi && (!aligned(tokens_hi, 16) || !aligned(tokens_lo, 16))) { set_error("e2f_t2t_fold_unfold: 16-byte alignment required"); return E2F_ERR_ALIGNMENT; }
-  st = launch_t2t_fold_unfold(tokens_in, tokens, tokens_hi, tokens_lo, bt, c, h, w, k, stride, pad, gelu, static_cast<cudaStream_t>(stream));
+  if (out_pitch == 0) out_pitch = c * k * k;
+  if (out_pitch < c * k * k || out_pitch % 8) { set_error("e2f_t2t_fold_unfold: out_pitch=%d must be 0 or a multiple of 8 >= C*k*k=%d", out_pitch, c * k * k); return E2F_ERR_BAD_ARG; }
+  st = launch_t2t_fold_unfold(tokens_in, tokens, tokens_hi, tokens_lo, bt, c, h, w, k, stride, pad, gelu, out_pitch, static_cast<cudaStream_t>(stream));
   if (st == E2F_ERR_UNSUPPORTED) { set_error("e2f_t2t_fold_unfold: only k=7 stride=3 pad=3, C %% 4 == 0, bt <= 65535 and W <= 1800 are fused (k=%d s=%d p=%d c=%d w=%d); compose e2f_t2t_fold + e2f_t2t_unfold", k, stride, pad, c, w); return st; }
   return finish(st, "e2f_t2t_fold_unfold");
 }

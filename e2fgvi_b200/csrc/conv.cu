@@ -41,7 +41,8 @@ struct Cfg {
   static constexpr int W_TILE = BN * BK * 2;
   static constexpr int STAGE = 2 * A_TILE + 2 * W_TILE;   // 64 KB (BN=128) / 48 KB (BN=64) / 40 KB (BN=32)
   static constexpr int STAGES = (BN == 128) ? 3 : 4;
-  static constexpr int TMEM_COLS = 2 * BN;
+  static constexpr int ACC_COLS = 2 * BN;                 // accumulator: [Ah.Wh + Al.Wh | Ah.Wl], summed by the epilogue
+  static constexpr int TMEM_COLS = 2 * ACC_COLS;          // double-buffered
   static constexpr int SMEM = STAGES * STAGE + 256 + 1024;
 };
 
@@ -191,16 +192,19 @@ __global__ void __launch_bounds__(THREADS, 1) conv3x3_kernel(const __grid_consta
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0) {
-      const uint32_t idesc = idesc_bf16(BM, BN);
+      // The Wh and Wl tiles are adjacent in a stage, so ONE N = 2*BN instruction multiplies Ah with both
+      // (accumulator columns [0,BN) and [BN,2BN)); a second, N = BN wide, adds Al.Wh to the first half.  Ah is read from
+      // shared memory once instead of twice: 3 -> 2 instructions per K step, ~20% less operand traffic on the
+      // shared-memory port that the TMA writes share.
+      const uint32_t idesc = idesc_bf16(BM, BN), idesc2 = idesc_bf16(BM, 2 * BN);
       const uint64_t d_ah0 = umma_desc_sw128(smem_u32(smem), 16, 1024);
       const uint64_t d_al0 = umma_desc_adv(d_ah0, A_TILE), d_wh0 = umma_desc_adv(d_ah0, 2 * A_TILE);
-      const uint64_t d_wl0 = umma_desc_adv(d_wh0, W_TILE);
       uint32_t it = 0, local = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
         const int buf = local & 1;
         mbar_wait(&acc_empty[buf], ((local >> 1) & 1) ^ 1);
         tc_fence_after_sync();
-        const uint32_t d = tbase + buf * BN;
+        const uint32_t d = tbase + buf * Cfg<BN>::ACC_COLS;
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
           const int stage = it % STAGES;
           mbar_wait(&full[stage], (it / STAGES) & 1);
@@ -209,10 +213,9 @@ __global__ void __launch_bounds__(THREADS, 1) conv3x3_kernel(const __grid_consta
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             const uint64_t dah = d_ah0 + soff + 2 * k, dal = d_al0 + soff + 2 * k;
-            const uint64_t dwh = d_wh0 + soff + 2 * k, dwl = d_wl0 + soff + 2 * k;
-            umma_f16(d, dal, dwh, idesc, (kb | k) != 0);
-            umma_f16(d, dah, dwl, idesc, 1);
-            umma_f16(d, dah, dwh, idesc, 1);
+            const uint64_t dwh = d_wh0 + soff + 2 * k;
+            umma_f16(d, dah, dwh, idesc2, (kb | k) != 0);   // [Ah.Wh | Ah.Wl]
+            umma_f16(d, dal, dwh, idesc, 1);                // + Al.Wh
           }
           umma_commit(&empty[stage]);
         }
@@ -235,12 +238,15 @@ __global__ void __launch_bounds__(THREADS, 1) conv3x3_kernel(const __grid_consta
       const size_t opix = (static_cast<size_t>(t.n) * p.H + y) * p.out_pitch + p.out_lead + x;   // split outputs
       const int co_end = (t.g + 1) * cog;               // exclusive end of this group's output channels
       const bool vec_ok = (p.Cout & 3) == 0;            // 16-byte aligned channel groups
-      const uint32_t taddr = tbase + (static_cast<uint32_t>(q * 32) << 16) + buf * BN;
+      const uint32_t taddr = tbase + (static_cast<uint32_t>(q * 32) << 16) + buf * Cfg<BN>::ACC_COLS;
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
-        uint32_t v[32];
+        uint32_t v[32], v2[32];
         tmem_ld32(taddr + c * 32, v);
+        tmem_ld32(taddr + BN + c * 32, v2);              // the Ah.Wl half of the accumulator
         tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(v2[i]));
         const int co = t.co0 + c * 32;
         if (pix_ok && co < co_end) {
 #pragma unroll

@@ -59,52 +59,71 @@ __global__ void __launch_bounds__(256) upsample2x_split_kernel(const float* __re
   split_store8(f, hi + o, lo + o);
 }
 
-// one warp per row of C = 32 * PER_LANE floats (C = 512 -> 16 per lane); two-pass mean / variance in registers
+// one warp per PAIR of rows of C = 32 * PER_LANE floats (C = 512 -> 16 per lane and row): the loads of both rows are
+// issued before the first reduction (twice the bytes in flight per warp); two-pass mean / variance in registers
 template <int PER_LANE>
 __global__ void __launch_bounds__(256) layernorm_split_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                                               const float* __restrict__ beta, float* __restrict__ out,
                                                               __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
                                                               long long rows, float eps) {
-  constexpr int C = 32 * PER_LANE;
-  const long long row = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= rows) return;
+  constexpr int C = 32 * PER_LANE, R = 2;
+  const long long row0 = (static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5)) * R;
+  if (row0 >= rows) return;
   const int lane = threadIdx.x & 31;
-  const float* xr = x + row * C;
-  float v[PER_LANE];
-  float sum = 0.f;
+  float v[R][PER_LANE];
 #pragma unroll
-  for (int j = 0; j < PER_LANE / 8; ++j) {        // lane owns 8 consecutive floats per 256-float segment
-    const float4 a = __ldg(reinterpret_cast<const float4*>(xr + j * 256 + lane * 8));
-    const float4 b = __ldg(reinterpret_cast<const float4*>(xr + j * 256 + lane * 8) + 1);
-    v[8 * j + 0] = a.x; v[8 * j + 1] = a.y; v[8 * j + 2] = a.z; v[8 * j + 3] = a.w;
-    v[8 * j + 4] = b.x; v[8 * j + 5] = b.y; v[8 * j + 6] = b.z; v[8 * j + 7] = b.w;
+  for (int r = 0; r < R; ++r) {
+    const bool ok = row0 + r < rows;
+    const float* xr = x + (row0 + (ok ? r : 0)) * C;
 #pragma unroll
-    for (int e = 0; e < 8; ++e) sum += v[8 * j + e];
+    for (int j = 0; j < PER_LANE / 8; ++j) {        // lane owns 8 consecutive floats per 256-float segment
+      const float4 a = __ldg(reinterpret_cast<const float4*>(xr + j * 256 + lane * 8));
+      const float4 b = __ldg(reinterpret_cast<const float4*>(xr + j * 256 + lane * 8) + 1);
+      v[r][8 * j + 0] = a.x; v[r][8 * j + 1] = a.y; v[r][8 * j + 2] = a.z; v[r][8 * j + 3] = a.w;
+      v[r][8 * j + 4] = b.x; v[r][8 * j + 5] = b.y; v[r][8 * j + 6] = b.z; v[r][8 * j + 7] = b.w;
+    }
   }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-  const float mean = sum * (1.0f / C);
-  float sq = 0.f;
-#pragma unroll
-  for (int e = 0; e < PER_LANE; ++e) {
-    const float d = v[e] - mean;
-    sq = fmaf(d, d, sq);
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
-  const float rstd = rsqrtf(sq * (1.0f / C) + eps);
+  float g[PER_LANE], bt[PER_LANE];
 #pragma unroll
   for (int j = 0; j < PER_LANE / 8; ++j) {
-    const int c0 = j * 256 + lane * 8;
-    float f[8];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) f[e] = (v[8 * j + e] - mean) * rstd * __ldg(gamma + c0 + e) + __ldg(beta + c0 + e);
-    if (out) {
-      float4* d4 = reinterpret_cast<float4*>(out + row * C + c0);
-      d4[0] = make_float4(f[0], f[1], f[2], f[3]);
-      d4[1] = make_float4(f[4], f[5], f[6], f[7]);
+    for (int e = 0; e < 8; ++e) {
+      g[8 * j + e] = __ldg(gamma + j * 256 + lane * 8 + e);
+      bt[8 * j + e] = __ldg(beta + j * 256 + lane * 8 + e);
     }
-    if (hi) split_store8(f, hi + row * C + c0, lo + row * C + c0);
+  }
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    if (row0 + r >= rows) break;
+    const long long row = row0 + r;
+    float sum = 0.f;
+#pragma unroll
+    for (int e = 0; e < PER_LANE; ++e) sum += v[r][e];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float mean = sum * (1.0f / C);
+    float sq = 0.f;
+#pragma unroll
+    for (int e = 0; e < PER_LANE; ++e) {
+      const float d = v[r][e] - mean;
+      sq = fmaf(d, d, sq);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    const float rstd = rsqrtf(sq * (1.0f / C) + eps);
+#pragma unroll
+    for (int j = 0; j < PER_LANE / 8; ++j) {
+      const int c0 = j * 256 + lane * 8;
+      float f[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) f[e] = (v[r][8 * j + e] - mean) * rstd * g[8 * j + e] + bt[8 * j + e];
+      if (out) {
+        float4* d4 = reinterpret_cast<float4*>(out + row * C + c0);
+        d4[0] = make_float4(f[0], f[1], f[2], f[3]);
+        d4[1] = make_float4(f[4], f[5], f[6], f[7]);
+      }
+      if (hi) split_store8(f, hi + row * C + c0, lo + row * C + c0);
+    }
   }
 }
 
@@ -194,7 +213,7 @@ int launch_layernorm_split(const float* x, const float* gamma, const float* beta
     set_error("layernorm_split is specialised for 512 channels (got %d)", c);
     return -2;
   }
-  const int threads = 256, rows_per_block = threads / 32;
+  const int threads = 256, rows_per_block = 2 * (threads / 32);
   layernorm_split_kernel<16><<<static_cast<unsigned>((rows + rows_per_block - 1) / rows_per_block), threads, 0, stream>>>(
       x, gamma, beta, out, static_cast<__nv_bfloat16*>(hi), static_cast<__nv_bfloat16*>(lo), rows, eps);
   count_launch();

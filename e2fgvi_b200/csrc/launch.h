@@ -33,7 +33,7 @@ int launch_layernorm_split(const float* x, const float* gamma, const float* beta
 int launch_window_pool(const void* xh, const void* xl, const float* weight, const float* bias, float* out, void* out_hi,
                        void* out_lo, int bt, int h, int w, int c, int wh, int ww, cudaStream_t stream);
 int launch_t2t_fold_unfold(const float* tin, float* tok, void* tok_hi, void* tok_lo, int bt, int c, int h, int w, int k,
-                           int s, int p, int gelu, cudaStream_t stream);
+                           int s, int p, int gelu, int out_pitch, cudaStream_t stream);
 int launch_t2t_fold(const float* tok, const float* bias, float* img, int bt, int c, int h, int w, int k, int s,
                     int p, int normalize, cudaStream_t stream);
 

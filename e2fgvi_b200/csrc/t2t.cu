@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(256) t2t_fold733_kernel(const float* __restric
                                                           __nv_bfloat16* __restrict__ tok_hi,
                                                           __nv_bfloat16* __restrict__ tok_lo, float* __restrict__ img,
                                                           const float* __restrict__ bias, int normalize, int C, int H,
-                                                          int W, int FH, int FW, int TR) {
+                                                          int W, int FH, int FW, int TR, int CKP) {
   extern __shared__ float simg[];                  // [CC][ROWS][WP], x padded by 3 on both sides; then nx[WP]
   constexpr int RUN4 = CC * 49 / 4;
   const int WP = W + 6, ROWS = FUSED ? 3 * TR + 4 : 3 * TR;
@@ -256,7 +256,7 @@ __global__ void __launch_bounds__(256) t2t_fold733_kernel(const float* __restric
     float v[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) v[e] = simg[base + off[e]];
-    const long long dst = (tok0 + t) * CK + c0 * 49 + rem;
+    const long long dst = (tok0 + t) * CKP + c0 * 49 + rem;      // CKP: output row pitch (>= C*49)
     if (tok) *reinterpret_cast<float4*>(tok + dst) = make_float4(v[0], v[1], v[2], v[3]);
     if (tok_hi) {
       const __nv_bfloat162 h0 = __floats2bfloat162_rn(v[0], v[1]), h1 = __floats2bfloat162_rn(v[2], v[3]);
@@ -264,6 +264,20 @@ __global__ void __launch_bounds__(256) t2t_fold733_kernel(const float* __restric
       const __nv_bfloat162 l0 = __floats2bfloat162_rn(v[0] - f0.x, v[1] - f0.y), l1 = __floats2bfloat162_rn(v[2] - f1.x, v[3] - f1.y);
       *reinterpret_cast<uint2*>(tok_hi + dst) = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
       *reinterpret_cast<uint2*>(tok_lo + dst) = make_uint2(*reinterpret_cast<const uint32_t*>(&l0), *reinterpret_cast<const uint32_t*>(&l1));
+    }
+  }
+  // padded rows: the block of the last channel chunk zeroes columns [C*49, CKP) of its tokens (a following GEMM
+  // multiplies them by zero weights, so they only have to be finite — zeros keep the buffer deterministic)
+  if (CKP > CK && blockIdx.x == gridDim.x - 1) {
+    const int padw = (CKP - CK) / 4;                             // both are multiples of 4
+    for (int i = threadIdx.x; i < tr * FW * padw; i += blockDim.x) {
+      const int t = i / padw, j = i - t * padw;
+      const long long dst = (tok0 + t) * CKP + CK + 4 * j;
+      if (tok) *reinterpret_cast<float4*>(tok + dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (tok_hi) {
+        *reinterpret_cast<uint2*>(tok_hi + dst) = make_uint2(0u, 0u);
+        *reinterpret_cast<uint2*>(tok_lo + dst) = make_uint2(0u, 0u);
+      }
     }
   }
 }
@@ -374,7 +388,7 @@ static void fold733_configure() {
 // Fused fold/normalise/unfold(/GELU).  Returns -2 (unsupported) when the geometry is not 7/3/3 or no band fits in
 // shared memory; the caller then composes launch_t2t_fold + launch_t2t_unfold.
 int launch_t2t_fold_unfold(const float* tin, float* tok, void* tok_hi, void* tok_lo, int bt, int c, int h, int w, int k,
-                           int s, int p, int gelu, cudaStream_t stream) {
+                           int s, int p, int gelu, int out_pitch, cudaStream_t stream) {
   constexpr int CC = 4;                            // 4 channels = 784-byte runs per token, 16-byte aligned
   if (k != 7 || s != 3 || p != 3 || c % CC) return -2;
   const int fh = (h + 2 * p - k) / s + 1, fw = (w + 2 * p - k) / s + 1;
@@ -388,9 +402,11 @@ int launch_t2t_fold_unfold(const float* tin, float* tok, void* tok_hi, void* tok
   const dim3 grid(c / CC, (fh + tr - 1) / tr, bt);
   fold733_configure();
   if (gelu)
-    t2t_fold733_kernel<true, true, CC><<<grid, 256, smem, stream>>>(tin, tok, hi, lo, nullptr, nullptr, 1, c, h, w, fh, fw, tr);
+    t2t_fold733_kernel<true, true, CC><<<grid, 256, smem, stream>>>(tin, tok, hi, lo, nullptr, nullptr, 1, c, h, w, fh, fw, tr,
+                                                                    out_pitch);
   else
-    t2t_fold733_kernel<true, false, CC><<<grid, 256, smem, stream>>>(tin, tok, hi, lo, nullptr, nullptr, 1, c, h, w, fh, fw, tr);
+    t2t_fold733_kernel<true, false, CC><<<grid, 256, smem, stream>>>(tin, tok, hi, lo, nullptr, nullptr, 1, c, h, w, fh, fw, tr,
+                                                                     out_pitch);
   count_launch();
   return static_cast<int>(cudaGetLastError());
 }
@@ -410,7 +426,7 @@ int launch_t2t_fold(const float* tok, const float* bias, float* img, int bt, int
       fold733_configure();
       const dim3 grid(c / 4, (h + 3 * tr - 1) / (3 * tr), bt);
       t2t_fold733_kernel<false, false, 4><<<grid, 256, smem, stream>>>(tok, nullptr, nullptr, nullptr, img, bias, normalize, c, h,
-                                                                       w, fh, fw, tr);
+                                                                       w, fh, fw, tr, c * 49);
       count_launch();
       return static_cast<int>(cudaGetLastError());
     }

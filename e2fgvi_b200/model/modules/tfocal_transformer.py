@@ -87,8 +87,10 @@ class FusionFeedForward(nn.Module):
         x = ops.linear(x, self.conv1[0].weight, self.conv1[0].bias)
         b, n, c = x.size()
         # fold / fold(ones) -> unfold -> conv2[0] (GELU): one kernel, the folded image stays in shared memory
+        # rows padded 1960 -> 1984 (zero columns) so that the A operand of conv2 starts every row on a 128-byte line
         x = ops.t2t_fold_unfold(x.view(-1, n_vecs, c), output_size, p["kernel_size"], p["stride"], p["padding"],
-                                gelu=True, out="split").view(b, n, c)
+                                gelu=True, out="split", pitch=(c + 63) // 64 * 64)
+        x = x.view(b, n, x.shape[-1])
         return ops.linear(x, self.conv2[1].weight, self.conv2[1].bias, residual=residual)
 
 

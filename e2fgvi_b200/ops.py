@@ -282,11 +282,12 @@ def t2t_unfold(img, kernel_size, stride, padding, gelu=False, out="f32"):
     return tok if out == "f32" else SplitMat(hi, lo)
 
 
-def t2t_fold_unfold(tokens, output_size, kernel_size, stride, padding, gelu=False, out="f32"):
+def t2t_fold_unfold(tokens, output_size, kernel_size, stride, padding, gelu=False, out="f32", pitch=None):
     """``unfold(fold(tokens) / fold(ones))`` (+ exact GELU): the middle of FusionFeedForward.forward
     (tfocal_transformer.py:89-96) as ONE kernel for the 7/3/3 geometry — the folded image lives in shared memory only.
     Other geometries compose ``t2t_fold(normalize=True)`` and ``t2t_unfold``.  tokens (BT, L, C*k*k) fp32 -> same
-    shape, fp32 (out="f32") or ``SplitMat`` (out="split")."""
+    shape, fp32 (out="f32") or ``SplitMat`` (out="split").  ``pitch`` (multiple of 8 >= C*k*k) pads every output row
+    with zero columns — ``linear`` zero-pads its weight to match — so that GEMM rows start on 128-byte lines."""
     _need_cuda(tokens)
     (k, k2), (s, s2), (p, p2) = _pair(kernel_size), _pair(stride), _pair(padding)
     if k != k2 or s != s2 or p != p2:
@@ -302,19 +303,23 @@ def t2t_fold_unfold(tokens, output_size, kernel_size, stride, padding, gelu=Fals
     if not fused:
         img = t2t_fold(tokens, output_size, kernel_size, stride, padding, normalize=True)
         return t2t_unfold(img, kernel_size, stride, padding, gelu=gelu, out=out)
+    pitch = ck if pitch is None else int(pitch)
+    if pitch < ck or pitch % 8:
+        raise ValueError(f"t2t_fold_unfold: pitch {pitch} must be a multiple of 8 >= {ck}")
+    oshape = (bt, n_tok, pitch)
     tok = hi = lo = None
     if out == "f32":
-        tok = torch.empty_like(tokens)
+        tok = torch.empty(oshape, dtype=torch.float32, device=tokens.device)
     elif out == "split":
-        hi = torch.empty(tokens.shape, dtype=torch.bfloat16, device=tokens.device)
-        lo = torch.empty(tokens.shape, dtype=torch.bfloat16, device=tokens.device)
+        hi = torch.empty(oshape, dtype=torch.bfloat16, device=tokens.device)
+        lo = torch.empty(oshape, dtype=torch.bfloat16, device=tokens.device)
     else:
         raise ValueError("out must be 'f32' or 'split'")
     with _timed("t2t_fold_unfold", float(tokens.numel() * 8)):
         st = _lib.load().e2f_t2t_fold_unfold(tokens.data_ptr(), None if tok is None else tok.data_ptr(),
                                              None if hi is None else hi.data_ptr(),
                                              None if lo is None else lo.data_ptr(), bt, c, h, w, k, s, p,
-                                             1 if gelu else 0, _stream())
+                                             1 if gelu else 0, pitch, _stream())
     _lib.check(st, "e2f_t2t_fold_unfold")
     return tok if out == "f32" else SplitMat(hi, lo)
 
@@ -431,12 +436,17 @@ def split_bf16(x):
 _WEIGHT_SPLITS = {}  # id(Parameter) -> (weakref to it, (version, data_ptr), hi, lo); dropped when the parameter dies
 
 
-def _split_weight(weight):
-    key = id(weight)
+def _split_weight(weight, k_pad=0):
+    """bf16 (hi, lo) split of a (N, K) weight, cached per parameter; k_pad > K appends zero columns (for an A operand
+    whose rows are padded to k_pad)."""
+    key = (id(weight), k_pad)
     tag = (weight._version, weight.data_ptr())
     hit = _WEIGHT_SPLITS.get(key)
     if hit is None or hit[0]() is not weight or hit[1] != tag:
-        hi, lo = split_bf16(weight.detach().reshape(weight.shape[0], -1))
+        w2 = weight.detach().reshape(weight.shape[0], -1)
+        if k_pad > w2.shape[1]:
+            w2 = torch.nn.functional.pad(w2.float(), (0, k_pad - w2.shape[1]))
+        hi, lo = split_bf16(w2)
         if hit is None or hit[0]() is not weight:
             weakref.finalize(weight, _WEIGHT_SPLITS.pop, key, None)
         hit = (weakref.ref(weight), tag, hi, lo)
@@ -451,8 +461,13 @@ def linear(x, weight, bias=None, residual=None, out_dtype=torch.float32, tile_hi
     when the parameter changes), bias (N,), residual (..., N) fp32 -> (..., N) ``out_dtype``."""
     n, k = weight.shape[:2]            # (N, K) Linear weight or (N, K, 1, 1) 1x1-conv weight
     lead = x.shape[:-1]
+    k_pad = 0
     if isinstance(x, SplitMat):         # operand pair written by a fused producer
         _need_cuda(weight, bias, residual)
+        if x.shape[-1] != k:            # rows padded with zero columns (t2t_fold_unfold pitch): pad the weight alike
+            if x.shape[-1] < k:
+                raise ValueError(f"linear: operand has {x.shape[-1]} columns, weight expects {k}")
+            k_pad = k = x.shape[-1]
         a_hi, a_lo = x.hi.reshape(-1, k), x.lo.reshape(-1, k)
         m = a_hi.shape[0]
     else:
@@ -460,7 +475,7 @@ def linear(x, weight, bias=None, residual=None, out_dtype=torch.float32, tile_hi
         x2 = x.reshape(-1, k)
         m = x2.shape[0]
         a_hi, a_lo = split_bf16(x2)
-    w_hi, w_lo = _split_weight(weight)
+    w_hi, w_lo = _split_weight(weight, k_pad)
     b32 = None if bias is None else bias.detach().float().contiguous()
     res = None
     if residual is not None:

@@ -122,9 +122,11 @@ int e2f_t2t_fold(const float* tokens, const float* bias, float* img, int bt, int
  *   out = gelu?( unfold( fold(tokens_in) / fold(ones) ) ), tokens [BT][L][C*k*k] -> tokens [BT][L][C*k*k];
  * the folded image stays in shared memory.  Fused for k=7, stride=3, pad=3 (the only geometry on the path); returns
  * E2F_ERR_UNSUPPORTED otherwise, and the caller composes e2f_t2t_fold(normalize=1) + e2f_t2t_unfold.  Outputs as
- * e2f_t2t_unfold (fp32 and/or bf16 hi/lo pair). */
+ * e2f_t2t_unfold (fp32 and/or bf16 hi/lo pair), with rows of out_pitch elements (0 = C*k*k; otherwise a multiple of 8
+ * >= C*k*k, columns past C*k*k written as zeros): 1960 -> 1984 makes every row of the following GEMM's A operand
+ * start on a 128-byte line, which its TMA loads want. */
 int e2f_t2t_fold_unfold(const float* tokens_in, float* tokens, void* tokens_hi, void* tokens_lo, int bt, int c, int h,
-                        int w, int k, int stride, int pad, int gelu, void* stream);
+                        int w, int k, int stride, int pad, int gelu, int out_pitch, void* stream);
 
 /* Window pooling of the focal attention's coarse level: pool_layers[0] = nn.Linear(wh*ww, 1) across the tokens of
  * every window, per channel (tfocal_transformer.py:508-516, the permute/Linear/squeeze chain):

@@ -54,7 +54,7 @@ def _fold(tokens, output_size, kernel_size, stride, padding, normalize=False, bi
     return img if bias is None else img + bias[None]
 
 
-def _fold_unfold(tokens, output_size, kernel_size, stride, padding, gelu=False, out="f32"):
+def _fold_unfold(tokens, output_size, kernel_size, stride, padding, gelu=False, out="f32", pitch=None):
     return _unfold(_fold(tokens, output_size, kernel_size, stride, padding, normalize=True), kernel_size, stride, padding,
                    gelu=gelu)
 

@@ -251,6 +251,15 @@ def test_t2t_fold_unfold_fused(cuda, shape):
     assert (got.cpu() - want).abs().max().item() < 1e-5
     sp = ops.t2t_fold_unfold(tok.to(cuda), (h, w), (7, 7), (3, 3), (3, 3), gelu=True, out="split")
     assert (_join(sp).cpu() - F.gelu(want)).abs().max().item() < 5e-5
+    # padded rows (pitch): same values, zero columns behind; a Linear fed by them pads its weight with zero columns
+    pitch = (c * 49 + 63) // 64 * 64 + 8
+    spp = ops.t2t_fold_unfold(tok.to(cuda), (h, w), (7, 7), (3, 3), (3, 3), gelu=True, out="split", pitch=pitch)
+    assert spp.shape == (bt, fh * fw, pitch)
+    assert torch.equal(spp.hi[..., : c * 49], sp.hi) and torch.equal(spp.lo[..., : c * 49], sp.lo)
+    assert float(spp.hi[..., c * 49:].float().abs().max()) == 0.0 and float(spp.lo[..., c * 49:].float().abs().max()) == 0.0
+    if (c * 49) % 8 == 0:                                            # the unpadded GEMM needs K % 8 == 0
+        wl = torch.nn.Parameter(torch.randn(24, c * 49, generator=g).to(cuda) / (c * 49) ** 0.5)
+        assert _rel(ops.linear(spp, wl), ops.linear(sp, wl)) < 1e-6
     # agrees with the two-kernel composition it replaces
     img = ops.t2t_fold(tok.to(cuda), (h, w), (7, 7), (3, 3), (3, 3), normalize=True)
     two = ops.t2t_unfold(torch.nan_to_num(img, nan=0.0, posinf=0.0, neginf=0.0), (7, 7), (3, 3), (3, 3))
