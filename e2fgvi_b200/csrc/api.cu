@@ -139,7 +139,18 @@ int e2f_t2t_unfold(const float* img, float* tokens, void* tokens_hi, void* token
   int st = t2t_checks("e2f_t2t_unfold", img, tokens ? static_cast<const void*>(tokens) : tokens_hi, bt, c, h, w, k, stride, pad);
   if (st) return st;
   if (tokens_hi && (!aligned(tokens_hi, 16) || !aligned(tokens_lo, 16))) { set_error("e2f_t2t_unfold: 16-byte alignment required"); return E2F_ERR_ALIGNMENT; }
-  return finish(launch_t2t_unfold(img, tokens, tokens_hi, tokens_lo, bt, c, h, w, k, stride, pad, gelu, static_cast<cudaStream_t>(stream)), "e2f_t2t_unfold");
+  return finish(launch_t2t_unfold(img, tokens, tokens_hi, tokens_lo, bt, c, h, w, k, stride, pad, gelu, 0, static_cast<cudaStream_t>(stream)), "e2f_t2t_unfold");
+}
+
+int e2f_t2t_unfold_nhwc(const float* img_nhwc, float* tokens, void* tokens_hi, void* tokens_lo, int bt, int c, int h, int w,
+                        int k, int stride, int pad, int gelu, void* stream) {
+  if ((!tokens && !tokens_hi) || (!tokens_hi) != (!tokens_lo)) { set_error("e2f_t2t_unfold_nhwc: need tokens and/or both of tokens_hi/tokens_lo"); return E2F_ERR_BAD_ARG; }
+  int st = t2t_checks("e2f_t2t_unfold_nhwc", img_nhwc, tokens ? static_cast<const void*>(tokens) : tokens_hi, bt, c, h, w, k, stride, pad);
+  if (st) return st;
+  if (tokens_hi && (!aligned(tokens_hi, 16) || !aligned(tokens_lo, 16))) { set_error("e2f_t2t_unfold_nhwc: 16-byte alignment required"); return E2F_ERR_ALIGNMENT; }
+  st = launch_t2t_unfold(img_nhwc, tokens, tokens_hi, tokens_lo, bt, c, h, w, k, stride, pad, gelu, 1, static_cast<cudaStream_t>(stream));
+  if (st == E2F_ERR_UNSUPPORTED) { set_error("e2f_t2t_unfold_nhwc: channels_last input needs k=7 stride=3 pad=3 and C %% 8 == 0 (k=%d s=%d p=%d c=%d)", k, stride, pad, c); return st; }
+  return finish(st, "e2f_t2t_unfold_nhwc");
 }
 
 int e2f_t2t_fold_unfold(const float* tokens_in, float* tokens, void* tokens_hi, void* tokens_lo, int bt, int c, int h,
@@ -149,7 +160,7 @@ int e2f_t2t_fold_unfold(const float* tokens_in, float* tokens, void* tokens_hi, 
   if (st) return st;
   if (tokens_hi && (!aligned(tokens_hi, 16) || !aligned(tokens_lo, 16))) { set_error("e2f_t2t_fold_unfold: 16-byte alignment required"); return E2F_ERR_ALIGNMENT; }
   if (out_pitch == 0) out_pitch = c * k * k;
-  if (out_pitch < c * k * k || out_pitch % 8) { set_error("e2f_t2t_fold_unfold: out_pitch=%d must be 0 or a multiple of 8 >= C*k*k=%d", out_pitch, c * k * k); return E2F_ERR_BAD_ARG; }
+  if (out_pitch < c * k * k || out_pitch % 4) { set_error("e2f_t2t_fold_unfold: out_pitch=%d must be 0 or a multiple of 4 >= C*k*k=%d", out_pitch, c * k * k); return E2F_ERR_BAD_ARG; }
   st = launch_t2t_fold_unfold(tokens_in, tokens, tokens_hi, tokens_lo, bt, c, h, w, k, stride, pad, gelu, out_pitch, static_cast<cudaStream_t>(stream));
   if (st == E2F_ERR_UNSUPPORTED) { set_error("e2f_t2t_fold_unfold: only k=7 stride=3 pad=3, C %% 4 == 0, bt <= 65535 and W <= 1800 are fused (k=%d s=%d p=%d c=%d w=%d); compose e2f_t2t_fold + e2f_t2t_unfold", k, stride, pad, c, w); return st; }
   return finish(st, "e2f_t2t_fold_unfold");
@@ -188,6 +199,16 @@ int e2f_t2t_fold(const float* tokens, const float* bias, float* img, int bt, int
   int st = t2t_checks("e2f_t2t_fold", tokens, img, bt, c, h, w, k, stride, pad);
   if (st) return st;
   return finish(launch_t2t_fold(tokens, bias, img, bt, c, h, w, k, stride, pad, normalize, static_cast<cudaStream_t>(stream)), "e2f_t2t_fold");
+}
+
+int e2f_t2t_fold_nhwc(const float* tokens, const float* bias, const float* residual_nhwc, float* img_nhwc, int bt, int c,
+                      int h, int w, int k, int stride, int pad, int normalize, void* stream) {
+  int st = t2t_checks("e2f_t2t_fold_nhwc", tokens, img_nhwc, bt, c, h, w, k, stride, pad);
+  if (st) return st;
+  if (residual_nhwc && !aligned(residual_nhwc, 16)) { set_error("e2f_t2t_fold_nhwc: 16-byte alignment required"); return E2F_ERR_ALIGNMENT; }
+  st = launch_t2t_fold_nhwc(tokens, bias, residual_nhwc, img_nhwc, bt, c, h, w, k, stride, pad, normalize, static_cast<cudaStream_t>(stream));
+  if (st == E2F_ERR_UNSUPPORTED) { set_error("e2f_t2t_fold_nhwc: needs k=7 stride=3 pad=3, C %% 8 == 0, bt <= 65535 (k=%d s=%d p=%d c=%d)", k, stride, pad, c); return st; }
+  return finish(st, "e2f_t2t_fold_nhwc");
 }
 
 int e2f_split_bf16(const float* x, void* hi_bf16, void* lo_bf16, int64_t n, void* stream) {

@@ -26,7 +26,7 @@ int launch_focal_attention(const void* qkv, const void* qkv_pooled, void* out, i
                            int out_dtype, cudaStream_t stream);
 
 int launch_t2t_unfold(const float* img, float* tok, void* tok_hi, void* tok_lo, int bt, int c, int h, int w, int k,
-                      int s, int p, int gelu, cudaStream_t stream);
+                      int s, int p, int gelu, int nhwc, cudaStream_t stream);
 int launch_upsample2x_split(const float* x, void* hi, void* lo, int n, int h, int w, int c, cudaStream_t stream);
 int launch_layernorm_split(const float* x, const float* gamma, const float* beta, float* out, void* hi, void* lo,
                            long long rows, int c, float eps, cudaStream_t stream);
@@ -34,6 +34,8 @@ int launch_window_pool(const void* xh, const void* xl, const float* weight, cons
                        void* out_lo, int bt, int h, int w, int c, int wh, int ww, cudaStream_t stream);
 int launch_t2t_fold_unfold(const float* tin, float* tok, void* tok_hi, void* tok_lo, int bt, int c, int h, int w, int k,
                            int s, int p, int gelu, int out_pitch, cudaStream_t stream);
+int launch_t2t_fold_nhwc(const float* tok, const float* bias, const float* residual, float* img, int bt, int c, int h,
+                         int w, int k, int s, int p, int normalize, cudaStream_t stream);
 int launch_t2t_fold(const float* tok, const float* bias, float* img, int bt, int c, int h, int w, int k, int s,
                     int p, int normalize, cudaStream_t stream);
 

@@ -58,7 +58,8 @@ __global__ void __launch_bounds__(256) t2t_unfold_kernel(const float* __restrict
 // rows a token row touches are loaded once (coalesced, zero-padded, GELU applied ONCE per pixel instead of once per
 // unfolded copy), then the 36 x (8*49) token values are written as fully coalesced runs (fp32 and/or bf16 split).
 constexpr int U2_CC = 8;
-template <bool GELU>
+// NHWC = true reads img as [BT][H][W][C] (channels_last storage, e.g. straight from a conv epilogue) instead of NCHW.
+template <bool GELU, bool NHWC>
 __global__ void __launch_bounds__(256) t2t_unfold733_kernel(const float* __restrict__ img, float* __restrict__ tok,
                                                             __nv_bfloat16* __restrict__ tok_hi,
                                                             __nv_bfloat16* __restrict__ tok_lo, int C, int H, int W,
@@ -67,6 +68,29 @@ __global__ void __launch_bounds__(256) t2t_unfold733_kernel(const float* __restr
   const int WP = W + 6;
   const int c0 = blockIdx.x * U2_CC, ty = blockIdx.y;
   const long long bt = blockIdx.z;
+  if (NHWC) {
+    // one warp per image row of the 7, lanes along x; each lane reads its pixel's 8 channels (32 contiguous bytes)
+    for (int r = threadIdx.x >> 5; r < 7; r += 8) {
+      const int y = ty * 3 - 3 + r;
+      const bool row_ok = y >= 0 && y < H;
+      const float* srow = img + ((bt * H + y) * static_cast<long long>(W)) * C + c0;
+      for (int xx = threadIdx.x & 31; xx < WP; xx += 32) {
+        const int x = xx - 3;
+        float v[U2_CC] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (row_ok && x >= 0 && x < W) {
+          const float4 a = __ldg(reinterpret_cast<const float4*>(srow + static_cast<long long>(x) * C));
+          const float4 b = __ldg(reinterpret_cast<const float4*>(srow + static_cast<long long>(x) * C) + 1);
+          v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+          if (GELU) {
+#pragma unroll
+            for (int cc = 0; cc < U2_CC; ++cc) v[cc] = gelu_exact(v[cc]);
+          }
+        }
+#pragma unroll
+        for (int cc = 0; cc < U2_CC; ++cc) simg[(cc * 7 + r) * WP + xx] = v[cc];
+      }
+    }
+  } else {
   const float* src = img + (bt * C + c0) * static_cast<long long>(H) * W;
   // one warp per (channel, image row) of the 8 x 7 rows, lanes along x: no per-element index arithmetic
   for (int rr = threadIdx.x >> 5; rr < U2_CC * 7; rr += 8) {
@@ -83,6 +107,7 @@ __global__ void __launch_bounds__(256) t2t_unfold733_kernel(const float* __restr
       }
       simg[rr * WP + xx] = v;
     }
+  }
   }
   // thread -> fixed float4 slot q4 of a token's 8*49-value run: the (channel, ky, kx) decode happens once per thread;
   // 98 slots x 2 tokens in flight per pass (196 of 256 threads active)
@@ -127,12 +152,15 @@ __global__ void __launch_bounds__(256) t2t_unfold733_kernel(const float* __restr
 //   2. every pixel is divided by its patch count (and passed through GELU / gets its bias) once;
 //   3. FUSED: the TR x FW tokens of the band are written as coalesced runs (bf16 hi/lo operand pair and/or fp32).
 // Algorithmic bytes: tokens in (x (TR+4)/TR or (TR+2)/TR halo re-read, served by L2) + tokens / image out.
-template <bool FUSED, bool GELU, int CC>
+// OUT_NHWC (fold only): the image is written channels_last, [BT][H][W][C], with an optional residual of the same
+// layout added (enc_feat + trans_feat of e2fgvi.py:263 folded into the store) — the layout the decoder's convs read.
+template <bool FUSED, bool GELU, int CC, bool OUT_NHWC = false>
 __global__ void __launch_bounds__(256) t2t_fold733_kernel(const float* __restrict__ tin, float* __restrict__ tok,
                                                           __nv_bfloat16* __restrict__ tok_hi,
                                                           __nv_bfloat16* __restrict__ tok_lo, float* __restrict__ img,
                                                           const float* __restrict__ bias, int normalize, int C, int H,
-                                                          int W, int FH, int FW, int TR, int CKP) {
+                                                          int W, int FH, int FW, int TR, int CKP,
+                                                          const float* __restrict__ residual = nullptr) {
   extern __shared__ float simg[];                  // [CC][ROWS][WP], x padded by 3 on both sides; then nx[WP]
   constexpr int RUN4 = CC * 49 / 4;
   const int WP = W + 6, ROWS = FUSED ? 3 * TR + 4 : 3 * TR;
@@ -144,7 +172,7 @@ __global__ void __launch_bounds__(256) t2t_fold733_kernel(const float* __restric
   const int ybase = FUSED ? 3 * ty0 - 3 : 3 * TR * band;   // image row held by smem row 0
   const int CK = C * 49;
   {
-    float4* z = reinterpret_cast<float4*>(simg);   // CC * ROWS * WP * 4 bytes is a multiple of 16 (CC = 4)
+    float4* z = reinterpret_cast<float4*>(simg);   // CC * ROWS * WP * 4 bytes is a multiple of 16 (CC % 4 == 0)
     for (int i = threadIdx.x; i < CC * ROWS * WP / 4; i += blockDim.x) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int xx = threadIdx.x; xx < WP; xx += blockDim.x) {
       const int x = xx - 3;                        // #token columns covering x: tx in [ceil((x-3)/3), floor((x+3)/3)]
@@ -214,6 +242,36 @@ __global__ void __launch_bounds__(256) t2t_fold733_kernel(const float* __restric
   // per pixel: / patch count = (#token rows covering y) * (#token columns covering x); then GELU (FUSED) or the store
   // of the image row (+ bias).  One warp per (channel, row), lanes along x.
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (!FUSED && OUT_NHWC) {
+    // channels_last store: one warp per image row, each lane writes its pixel's CC channels (CC * 4 contiguous bytes)
+    for (int r = warp; r < ROWS; r += 8) {
+      const int y = ybase + r;
+      if (y >= H) break;
+      const int ny = min(FH - 1, (y + 3) / 3) - max(0, (y - 1) / 3) + 1;
+      for (int x = lane; x < W; x += 32) {
+        const long long pix = (bt * H + y) * static_cast<long long>(W) + x;
+        float v[CC];
+#pragma unroll
+        for (int cc = 0; cc < CC; ++cc) {
+          float t = simg[(cc * ROWS + r) * WP + x + 3];
+          if (normalize) t = t / static_cast<float>(ny * nxtab[x + 3]);
+          if (bias) t += __ldg(bias + (static_cast<long long>(c0 + cc) * H + y) * W + x);
+          v[cc] = t;
+        }
+        if (residual) {
+#pragma unroll
+          for (int j = 0; j < CC / 4; ++j) {
+            const float4 rr = __ldg(reinterpret_cast<const float4*>(residual + pix * C + c0) + j);
+            v[4 * j] += rr.x; v[4 * j + 1] += rr.y; v[4 * j + 2] += rr.z; v[4 * j + 3] += rr.w;
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < CC / 4; ++j)
+          reinterpret_cast<float4*>(img + pix * C + c0)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+      }
+    }
+    return;
+  }
   for (int rr = warp; rr < CC * ROWS; rr += 8) {
     const int cc = rr / ROWS, r = rr - cc * ROWS;
     const int y = ybase + r;
@@ -320,7 +378,7 @@ __global__ void __launch_bounds__(256) t2t_fold_kernel(const float* __restrict__
 }
 
 int launch_t2t_unfold(const float* img, float* tok, void* tok_hi_v, void* tok_lo_v, int bt, int c, int h, int w, int k,
-                      int s, int p, int gelu, cudaStream_t stream) {
+                      int s, int p, int gelu, int nhwc, cudaStream_t stream) {
   __nv_bfloat16* tok_hi = static_cast<__nv_bfloat16*>(tok_hi_v);
   __nv_bfloat16* tok_lo = static_cast<__nv_bfloat16*>(tok_lo_v);
   const int fh = (h + 2 * p - k) / s + 1, fw = (w + 2 * p - k) / s + 1;
@@ -333,18 +391,25 @@ int launch_t2t_unfold(const float* img, float* tok, void* tok_hi_v, void* tok_lo
   if (fast && c % U2_CC == 0 && smem2 <= 200 * 1024 && fh <= 65535 && bt <= 65535) {
     static bool cfg = false;
     if (!cfg) {
-      cudaFuncSetAttribute(t2t_unfold733_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-      cudaFuncSetAttribute(t2t_unfold733_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      cudaFuncSetAttribute(t2t_unfold733_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      cudaFuncSetAttribute(t2t_unfold733_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      cudaFuncSetAttribute(t2t_unfold733_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      cudaFuncSetAttribute(t2t_unfold733_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
       cfg = true;
     }
     const dim3 grid(c / U2_CC, fh, bt);
-    if (gelu)
-      t2t_unfold733_kernel<true><<<grid, threads, smem2, stream>>>(img, tok, tok_hi, tok_lo, c, h, w, fh, fw);
+    if (gelu && nhwc)
+      t2t_unfold733_kernel<true, true><<<grid, threads, smem2, stream>>>(img, tok, tok_hi, tok_lo, c, h, w, fh, fw);
+    else if (gelu)
+      t2t_unfold733_kernel<true, false><<<grid, threads, smem2, stream>>>(img, tok, tok_hi, tok_lo, c, h, w, fh, fw);
+    else if (nhwc)
+      t2t_unfold733_kernel<false, true><<<grid, threads, smem2, stream>>>(img, tok, tok_hi, tok_lo, c, h, w, fh, fw);
     else
-      t2t_unfold733_kernel<false><<<grid, threads, smem2, stream>>>(img, tok, tok_hi, tok_lo, c, h, w, fh, fw);
+      t2t_unfold733_kernel<false, false><<<grid, threads, smem2, stream>>>(img, tok, tok_hi, tok_lo, c, h, w, fh, fw);
     count_launch();
     return static_cast<int>(cudaGetLastError());
   }
+  if (nhwc) return -2;                               // channels_last input: only the staged 7/3/3 kernel reads it
   if (gelu && fast)
     t2t_unfold_kernel<true, 7, 3, 3><<<blocks, threads, 0, stream>>>(img, tok, tok_hi, tok_lo, bt, c, h, w, k, s, p, fh, fw);
   else if (fast)
@@ -359,8 +424,7 @@ int launch_t2t_unfold(const float* img, float* tok, void* tok_hi_v, void* tok_lo
 
 // Band height (in token rows) of t2t_fold733_kernel and its dynamic shared memory: the tallest band that keeps 3 blocks
 // per SM; wide images (few rows fit) take up to 200 KB instead.  rows(tr) = 3*tr + extra image rows.  0 = does not fit.
-static int fold733_band(int w, int fh, int extra_rows, size_t* smem) {
-  constexpr int CC = 4;
+static int fold733_band(int w, int fh, int extra_rows, size_t* smem, int CC = 4) {
   const size_t row_bytes = static_cast<size_t>(CC) * (w + 6) * sizeof(float), tab = (w + 6) * sizeof(int);
   auto band_rows = [&](size_t budget) {
     const long long rows = static_cast<long long>((budget - tab) / row_bytes) - extra_rows;
@@ -382,6 +446,7 @@ static void fold733_configure() {
   cudaFuncSetAttribute(t2t_fold733_kernel<true, true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   cudaFuncSetAttribute(t2t_fold733_kernel<true, false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   cudaFuncSetAttribute(t2t_fold733_kernel<false, false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(t2t_fold733_kernel<false, false, 8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   cfg = true;
 }
 
@@ -407,6 +472,23 @@ int launch_t2t_fold_unfold(const float* tin, float* tok, void* tok_hi, void* tok
   else
     t2t_fold733_kernel<true, false, CC><<<grid, 256, smem, stream>>>(tin, tok, hi, lo, nullptr, nullptr, 1, c, h, w, fh, fw, tr,
                                                                      out_pitch);
+  count_launch();
+  return static_cast<int>(cudaGetLastError());
+}
+
+// fold (+ / fold(ones)) (+ bias map) (+ channels_last residual) -> channels_last image.  7/3/3 with C % 8 == 0 only (-2).
+int launch_t2t_fold_nhwc(const float* tok, const float* bias, const float* residual, float* img, int bt, int c, int h,
+                         int w, int k, int s, int p, int normalize, cudaStream_t stream) {
+  if (k != 7 || s != 3 || p != 3 || c % 8 || bt > 65535) return -2;
+  const int fh = (h + 2 * p - k) / s + 1, fw = (w + 2 * p - k) / s + 1;
+  if (bt == 0) return 0;
+  size_t smem = 0;
+  const int tr = fold733_band(w, (h + 2) / 3, 0, &smem, 8);
+  if (tr < 1) return -2;
+  fold733_configure();
+  const dim3 grid(c / 8, (h + 3 * tr - 1) / (3 * tr), bt);
+  t2t_fold733_kernel<false, false, 8, true><<<grid, 256, smem, stream>>>(tok, nullptr, nullptr, nullptr, img, bias, normalize, c,
+                                                                         h, w, fh, fw, tr, c * 49, residual);
   count_launch();
   return static_cast<int>(cudaGetLastError());
 }

@@ -170,7 +170,10 @@ class InpaintGenerator(BaseNetwork):
         enc_feat = enc_feat.view(b, t, c, h, w)
         # NB: (forward, backward) flows go to (flows_backward, flows_forward) exactly as e2fgvi.py:249-250 does
         local_feat = self.feat_prop_module(enc_feat[:, :l_t], pred_flows[0], pred_flows[1])
-        enc_feat = torch.cat((local_feat, enc_feat[:, l_t:]), dim=1)
+        # keep the features channels_last ((b,t,h,w,c) storage): the unfold reads it, the fold adds it back and
+        # writes it, and the decoder's convs consume it without a layout copy
+        enc_feat = torch.cat((local_feat.permute(0, 1, 3, 4, 2), enc_feat[:, l_t:].permute(0, 1, 3, 4, 2)), dim=1)
+        enc_feat = enc_feat.permute(0, 1, 4, 2, 3)                      # logical (b,t,c,h,w)
 
         fold_size = (h, w)
         tokens = self.ss(enc_feat.reshape(-1, c, h, w), b, fold_size if self.HQ else None)
@@ -178,10 +181,10 @@ class InpaintGenerator(BaseNetwork):
             tokens = self.transformer([tokens, fold_size])[0]
         else:
             tokens = self.transformer(tokens)
-        trans_feat = self.sc(tokens, t, fold_size if self.HQ else None).view(b, t, -1, h, w)
-        enc_feat = enc_feat + trans_feat
+        # enc_feat + trans_feat (e2fgvi.py:263) is fused into SoftComp's fold / conv epilogue
+        enc_feat = self.sc(tokens, t, fold_size if self.HQ else None, residual=enc_feat.reshape(-1, c, h, w))
 
-        output = torch.tanh(self._decode(enc_feat.reshape(b * t, c, h, w)))
+        output = torch.tanh(self._decode(enc_feat))
         return output.contiguous(), pred_flows
 
     def _decode(self, x):

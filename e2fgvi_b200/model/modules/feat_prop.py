@@ -142,7 +142,11 @@ class BidirectionalPropagation(nn.Module):
                 hist.append(prop)
             swept[name] = hist[::-1] if backward else hist
         # 1x1 fusion conv == a Linear over pixels; "+ x" is its fused residual (feat_prop.py:143-149)
-        both = torch.stack([torch.cat([swept["backward_"][i], swept["forward_"][i]], dim=1) for i in range(t)], 1)
-        tokens = both.permute(0, 1, 3, 4, 2)                               # (b,t,h,w,2c)
+        # cat(backward, forward) of every frame, written straight into the (b,t,h,w,2c) token buffer (no per-frame cat
+        # followed by a stack)
+        tokens = torch.empty((b, t, h, w, 2 * c), dtype=x.dtype, device=x.device)
+        for i in range(t):
+            tokens[:, i, :, :, :c].copy_(swept["backward_"][i].permute(0, 2, 3, 1))
+            tokens[:, i, :, :, c:].copy_(swept["forward_"][i].permute(0, 2, 3, 1))
         out = ops.linear(tokens, self.fusion.weight, self.fusion.bias, residual=x.permute(0, 1, 3, 4, 2))
         return out.permute(0, 1, 4, 2, 3)

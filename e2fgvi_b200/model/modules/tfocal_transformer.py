@@ -54,14 +54,19 @@ class SoftComp(nn.Module):
         else:
             self.bias = nn.Parameter(torch.zeros((channel, output_size[0], output_size[1]), dtype=torch.float32))
 
-    def forward(self, x, t, output_size=None):
+    def forward(self, x, t, output_size=None, residual=None):
+        """``residual`` (b*t, C, H, W), optional: added to the result by the fold kernel (base model) or the conv
+        epilogue (HQ) — the ``enc_feat + trans_feat`` of e2fgvi.py:263; the result is then channels_last."""
         output_size = output_size or self.output_size
         b_, _, _, _, c_ = x.shape
         feat = ops.linear(x.view(b_, -1, c_), self.embedding.weight, self.embedding.bias)
         b, _, c = feat.size()
-        feat = ops.t2t_fold(feat.view(b * t, -1, c), output_size, self.kernel_size, self.stride, self.padding,
-                            bias=None if self.hq else self.bias)
-        return ops.conv3x3([feat], self.bias_conv.weight, self.bias_conv.bias) if self.hq else feat
+        if self.hq:
+            feat = ops.t2t_fold(feat.view(b * t, -1, c), output_size, self.kernel_size, self.stride, self.padding,
+                                channels_last=residual is not None)
+            return ops.conv3x3([feat], self.bias_conv.weight, self.bias_conv.bias, residual=residual)
+        return ops.t2t_fold(feat.view(b * t, -1, c), output_size, self.kernel_size, self.stride, self.padding,
+                            bias=self.bias, residual=residual, channels_last=residual is not None)
 
 
 class FusionFeedForward(nn.Module):

@@ -261,8 +261,12 @@ def t2t_unfold(img, kernel_size, stride, padding, gelu=False, out="f32"):
     (k, k2), (s, s2), (p, p2) = _pair(kernel_size), _pair(stride), _pair(padding)
     if k != k2 or s != s2 or p != p2:
         raise NotImplementedError("square kernel / stride / padding only (E2FGVI uses 7 / 3 / 3)")
-    img = img.contiguous().float()
     bt, c, h, w = img.shape
+    # channels_last storage (conv / linear epilogues write it) is read in place by the staged 7/3/3 kernel
+    nhwc = ((k, s, p) == (7, 3, 3) and c % 8 == 0 and img.dtype == torch.float32 and not img.is_contiguous()
+            and img.permute(0, 2, 3, 1).is_contiguous() and bt <= 65535)
+    if not nhwc:
+        img = img.contiguous().float()
     fh, fw = (h + 2 * p - k) // s + 1, (w + 2 * p - k) // s + 1
     shape = (bt, fh * fw, c * k * k)
     tok = hi = lo = None
@@ -275,7 +279,8 @@ def t2t_unfold(img, kernel_size, stride, padding, gelu=False, out="f32"):
         raise ValueError("out must be 'f32' or 'split'")
     numel = shape[0] * shape[1] * shape[2]
     with _timed("t2t_unfold", float(numel * 4 + img.numel() * 4)):
-        st = _lib.load().e2f_t2t_unfold(img.data_ptr(), None if tok is None else tok.data_ptr(),
+        fn = _lib.load().e2f_t2t_unfold_nhwc if nhwc else _lib.load().e2f_t2t_unfold
+        st = fn(img.data_ptr(), None if tok is None else tok.data_ptr(),
                                         None if hi is None else hi.data_ptr(), None if lo is None else lo.data_ptr(),
                                         bt, c, h, w, k, s, p, 1 if gelu else 0, _stream())
     _lib.check(st, "e2f_t2t_unfold")
@@ -286,7 +291,7 @@ def t2t_fold_unfold(tokens, output_size, kernel_size, stride, padding, gelu=Fals
     """``unfold(fold(tokens) / fold(ones))`` (+ exact GELU): the middle of FusionFeedForward.forward
     (tfocal_transformer.py:89-96) as ONE kernel for the 7/3/3 geometry — the folded image lives in shared memory only.
     Other geometries compose ``t2t_fold(normalize=True)`` and ``t2t_unfold``.  tokens (BT, L, C*k*k) fp32 -> same
-    shape, fp32 (out="f32") or ``SplitMat`` (out="split").  ``pitch`` (multiple of 8 >= C*k*k) pads every output row
+    shape, fp32 (out="f32") or ``SplitMat`` (out="split").  ``pitch`` (multiple of 4 >= C*k*k) pads every output row
     with zero columns — ``linear`` zero-pads its weight to match — so that GEMM rows start on 128-byte lines."""
     _need_cuda(tokens)
     (k, k2), (s, s2), (p, p2) = _pair(kernel_size), _pair(stride), _pair(padding)
@@ -304,8 +309,8 @@ def t2t_fold_unfold(tokens, output_size, kernel_size, stride, padding, gelu=Fals
         img = t2t_fold(tokens, output_size, kernel_size, stride, padding, normalize=True)
         return t2t_unfold(img, kernel_size, stride, padding, gelu=gelu, out=out)
     pitch = ck if pitch is None else int(pitch)
-    if pitch < ck or pitch % 8:
-        raise ValueError(f"t2t_fold_unfold: pitch {pitch} must be a multiple of 8 >= {ck}")
+    if pitch < ck or pitch % 4:
+        raise ValueError(f"t2t_fold_unfold: pitch {pitch} must be a multiple of 4 >= {ck}")
     oshape = (bt, n_tok, pitch)
     tok = hi = lo = None
     if out == "f32":
@@ -395,11 +400,13 @@ def layer_norm(x, weight, bias, eps=1e-5, out="f32"):
     return o32 if out == "f32" else sp if out == "split" else (o32, sp)
 
 
-def t2t_fold(tokens, output_size, kernel_size, stride, padding, normalize=False, bias=None):
+def t2t_fold(tokens, output_size, kernel_size, stride, padding, normalize=False, bias=None, residual=None,
+             channels_last=False):
     """``F.fold(tokens.permute(0, 2, 1), output_size, k, padding=p, stride=s)`` (tfocal_transformer.py:65-72,
     :89-96), optionally divided by fold(ones) and/or with a (C,H,W) bias map added.
-    tokens (BT, L, C*k*k) fp32 -> img (BT, C, H, W) fp32."""
-    _need_cuda(tokens, bias)
+    tokens (BT, L, C*k*k) fp32 -> img (BT, C, H, W) fp32.  ``channels_last=True`` returns the image in channels_last
+    storage (what the decoder's convs read) and lets ``residual`` (BT,C,H,W) be added by the same kernel."""
+    _need_cuda(tokens, bias, residual)
     (k, k2), (s, s2), (p, p2) = _pair(kernel_size), _pair(stride), _pair(padding)
     if k != k2 or s != s2 or p != p2:
         raise NotImplementedError("square kernel / stride / padding only (E2FGVI uses 7 / 3 / 3)")
@@ -414,12 +421,25 @@ def t2t_fold(tokens, output_size, kernel_size, stride, padding, normalize=False,
         if tuple(bias.shape) != (c, h, w):
             raise ValueError(f"bias {tuple(bias.shape)} != {(c, h, w)}")
         bias = bias.detach().contiguous().float()
+    if residual is not None and tuple(residual.shape) != (bt, c, h, w):
+        raise ValueError(f"residual {tuple(residual.shape)} != {(bt, c, h, w)}")
+    if channels_last and (k, s, p) == (7, 3, 3) and c % 8 == 0 and bt <= 65535:
+        res = None if residual is None else residual.permute(0, 2, 3, 1).contiguous().float()   # no-op if channels_last
+        img = torch.empty((bt, h, w, c), dtype=torch.float32, device=tokens.device)
+        with _timed("t2t_fold", float(tokens.numel() * 4 + img.numel() * (8 if res is not None else 4))):
+            st = _lib.load().e2f_t2t_fold_nhwc(tokens.data_ptr(), None if bias is None else bias.data_ptr(),
+                                               None if res is None else res.data_ptr(), img.data_ptr(), bt, c, h, w,
+                                               k, s, p, 1 if normalize else 0, _stream())
+        _lib.check(st, "e2f_t2t_fold_nhwc")
+        return img.permute(0, 3, 1, 2)
     img = torch.empty((bt, c, h, w), dtype=torch.float32, device=tokens.device)
     with _timed("t2t_fold", float(tokens.numel() * 4 + img.numel() * 4)):
         st = _lib.load().e2f_t2t_fold(tokens.data_ptr(), None if bias is None else bias.data_ptr(), img.data_ptr(), bt,
                                       c, h, w, k, s, p, 1 if normalize else 0, _stream())
     _lib.check(st, "e2f_t2t_fold")
-    return img
+    if residual is not None:
+        img = img + residual
+    return img.contiguous(memory_format=torch.channels_last) if channels_last else img
 
 
 def split_bf16(x):

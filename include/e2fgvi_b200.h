@@ -117,12 +117,21 @@ int e2f_t2t_unfold(const float* img, float* tokens, void* tokens_hi, void* token
                    int k, int stride, int pad, int gelu, void* stream);
 int e2f_t2t_fold(const float* tokens, const float* bias, float* img, int bt, int c, int h, int w, int k, int stride,
                  int pad, int normalize, void* stream);
+/* e2f_t2t_fold writing a channels_last image [BT][H][W][C] = fold(tokens) (/ fold(ones)) (+ bias [C][H][W]) (+ residual
+ * [BT][H][W][C]): SoftComp's output with "enc_feat + trans_feat" (e2fgvi.py:263) fused into the store, in the layout
+ * the decoder's convs read.  Only k=7, stride=3, pad=3 with C % 8 == 0 (E2F_ERR_UNSUPPORTED otherwise). */
+int e2f_t2t_fold_nhwc(const float* tokens, const float* bias, const float* residual_nhwc, float* img_nhwc, int bt, int c,
+                      int h, int w, int k, int stride, int pad, int normalize, void* stream);
+/* e2f_t2t_unfold reading a channels_last image [BT][H][W][C] (what the conv / linear epilogues write), so SoftSplit
+ * needs no NHWC -> NCHW copy.  Only k=7, stride=3, pad=3 with C % 8 == 0 (E2F_ERR_UNSUPPORTED otherwise). */
+int e2f_t2t_unfold_nhwc(const float* img_nhwc, float* tokens, void* tokens_hi, void* tokens_lo, int bt, int c, int h, int w,
+                        int k, int stride, int pad, int gelu, void* stream);
 
 /* FusionFeedForward's middle (tfocal_transformer.py:89-96) in ONE launch:
  *   out = gelu?( unfold( fold(tokens_in) / fold(ones) ) ), tokens [BT][L][C*k*k] -> tokens [BT][L][C*k*k];
  * the folded image stays in shared memory.  Fused for k=7, stride=3, pad=3 (the only geometry on the path); returns
  * E2F_ERR_UNSUPPORTED otherwise, and the caller composes e2f_t2t_fold(normalize=1) + e2f_t2t_unfold.  Outputs as
- * e2f_t2t_unfold (fp32 and/or bf16 hi/lo pair), with rows of out_pitch elements (0 = C*k*k; otherwise a multiple of 8
+ * e2f_t2t_unfold (fp32 and/or bf16 hi/lo pair), with rows of out_pitch elements (0 = C*k*k; otherwise a multiple of 4
  * >= C*k*k, columns past C*k*k written as zeros): 1960 -> 1984 makes every row of the following GEMM's A operand
  * start on a 128-byte line, which its TMA loads want. */
 int e2f_t2t_fold_unfold(const float* tokens_in, float* tokens, void* tokens_hi, void* tokens_lo, int bt, int c, int h,

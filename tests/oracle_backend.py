@@ -45,13 +45,15 @@ def _unfold(img, kernel_size, stride, padding, gelu=False, out="f32"):
     return torch.nn.functional.gelu(t) if gelu else t
 
 
-def _fold(tokens, output_size, kernel_size, stride, padding, normalize=False, bias=None):
+def _fold(tokens, output_size, kernel_size, stride, padding, normalize=False, bias=None, residual=None,
+          channels_last=False):
     F = torch.nn.functional
     img = F.fold(tokens.permute(0, 2, 1), output_size, kernel_size, padding=padding, stride=stride)
     if normalize:
         ones = torch.ones(1, kernel_size[0] * kernel_size[1], tokens.shape[1], dtype=tokens.dtype)
         img = img / F.fold(ones, output_size, kernel_size, padding=padding, stride=stride)
-    return img if bias is None else img + bias[None]
+    img = img if bias is None else img + bias[None]
+    return img if residual is None else img + residual
 
 
 def _fold_unfold(tokens, output_size, kernel_size, stride, padding, gelu=False, out="f32", pitch=None):

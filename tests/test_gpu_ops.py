@@ -226,6 +226,21 @@ def test_t2t_unfold_fold(cuda, shape):
     want_n = folded / ones + bias[None]
     ok = torch.isfinite(want_n)
     assert (got_n.cpu()[ok] - want_n[ok]).abs().max().item() < 1e-5
+    if c % 8 == 0:
+        # channels_last image in (read in place, no NCHW copy) / out (+ residual added by the fold kernel)
+        img_cl = img.to(cuda).contiguous(memory_format=torch.channels_last)
+        assert torch.equal(ops.t2t_unfold(img_cl, (7, 7), (3, 3), (3, 3)), got)
+        sp_a = ops.t2t_unfold(img_cl, (7, 7), (3, 3), (3, 3), gelu=True, out="split")
+        sp_b = ops.t2t_unfold(img.to(cuda), (7, 7), (3, 3), (3, 3), gelu=True, out="split")
+        assert torch.equal(sp_a.hi, sp_b.hi) and torch.equal(sp_a.lo, sp_b.lo)
+        res = torch.randn(bt, c, h, w, generator=g)
+        got_cl = ops.t2t_fold(tok.to(cuda), (h, w), (7, 7), (3, 3), (3, 3), bias=bias.to(cuda),
+                              residual=res.to(cuda).contiguous(memory_format=torch.channels_last), channels_last=True)
+        assert got_cl.shape == (bt, c, h, w) and got_cl.permute(0, 2, 3, 1).is_contiguous()
+        assert (got_cl.cpu() - (folded + bias[None] + res)).abs().max().item() < 2e-5
+        got_cl2 = ops.t2t_fold(tok.to(cuda), (h, w), (7, 7), (3, 3), (3, 3), normalize=True, channels_last=True)
+        want2 = folded / ones
+        assert (got_cl2.cpu()[torch.isfinite(want2)] - want2[torch.isfinite(want2)]).abs().max().item() < 1e-5
 
 
 @pytest.mark.parametrize("shape", [(3, 40, 60, 108), (2, 12, 30, 54), (1, 4, 7, 7), (2, 8, 61, 110), (1, 40, 135, 240),
