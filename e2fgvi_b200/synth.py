@@ -118,3 +118,25 @@ def synth_frames(b, t, h, w, seed=0, holes=True):
                 x0 = int(torch.randint(0, w - ww + 1, (1,), generator=g))
                 x[bi, ti, :, y0:y0 + hh, x0:x0 + ww] = 0.0
     return x.contiguous()
+
+
+def synth_video(n, h, w, seed=0):
+    """A synthetic RGB video and its hole masks for the video-level driver (test.py:125-141):
+    ``frames`` (n,h,w,3) uint8 — drifting sinusoid texture + noise — and ``masks`` (n,h,w) uint8 in {0,1} — a
+    rectangle that moves across the frame (before the reference's 4x cross dilation)."""
+    import numpy as np
+    g = _gen(seed, f"video:{n}:{h}:{w}")
+    yy = torch.linspace(0, 1, h).view(1, h, 1, 1)
+    xx = torch.linspace(0, 1, w).view(1, 1, w, 1)
+    tt = torch.arange(n, dtype=torch.float32).view(n, 1, 1, 1)
+    ph = torch.rand((1, 1, 1, 3), generator=g) * 6.28
+    base = 0.5 + 0.35 * torch.sin(6.28 * (2.0 * xx + 0.02 * tt) + ph) * torch.cos(6.28 * (1.5 * yy - 0.015 * tt))
+    x = (base + 0.15 * (torch.rand((n, h, w, 3), generator=g) - 0.5)).clamp_(0, 1)
+    frames = (x * 255).round().to(torch.uint8).numpy()
+    masks = np.zeros((n, h, w), dtype=np.uint8)
+    hh, ww = max(h // 3, 1), max(w // 4, 1)
+    for i in range(n):
+        y0 = int((h - hh) * (0.5 + 0.4 * math.sin(0.5 * i)))
+        x0 = int((w - ww) * (i / max(n - 1, 1)))
+        masks[i, y0:y0 + hh, x0:x0 + ww] = 1
+    return frames, masks
