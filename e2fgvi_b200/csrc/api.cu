@@ -296,4 +296,34 @@ int e2f_conv3x3_bf16x3(int nsrc, const void* const* src_hi, const void* const* s
                            cout, groups, leaky_slope, 3, 1, 1, stream);
 }
 
+int e2f_video_prepare_clip(const uint8_t* frames, const uint8_t* masks, const int* ids, float* out, int t, int h, int w,
+                           int hp, int wp, void* stream) {
+  if (!frames || !masks || !ids || !out) { set_error("e2f_video_prepare_clip: null pointer"); return E2F_ERR_BAD_ARG; }
+  if (t < 0 || h <= 0 || w <= 0 || hp < h || wp < w || hp > 2 * h || wp > 2 * w) {
+    set_error("e2f_video_prepare_clip: bad shape t=%d h=%d w=%d hp=%d wp=%d (mirror padding needs h <= hp <= 2h, w <= wp <= 2w)", t, h, w, hp, wp);
+    return E2F_ERR_BAD_ARG;
+  }
+  return finish(launch_video_prepare_clip(frames, masks, ids, out, t, h, w, hp, wp, static_cast<cudaStream_t>(stream)), "e2f_video_prepare_clip");
+}
+
+int e2f_video_compose(const float* pred, const uint8_t* frames, const uint8_t* masks, const int* ids, uint8_t* img,
+                      int n_local, int h, int w, int hp, int wp, void* stream) {
+  if (!pred || !frames || !masks || !ids || !img) { set_error("e2f_video_compose: null pointer"); return E2F_ERR_BAD_ARG; }
+  if (n_local < 0 || h <= 0 || w <= 0 || hp < h || wp < w) { set_error("e2f_video_compose: bad shape n_local=%d h=%d w=%d hp=%d wp=%d", n_local, h, w, hp, wp); return E2F_ERR_BAD_ARG; }
+  return finish(launch_video_compose(pred, frames, masks, ids, img, n_local, h, w, hp, wp, static_cast<cudaStream_t>(stream)), "e2f_video_compose");
+}
+
+int e2f_video_blend(const uint8_t* img, const int* ids, const int* first, float* comp, int n_local, int64_t frame_elems,
+                    void* stream) {
+  if (!img || !ids || !first || !comp) { set_error("e2f_video_blend: null pointer"); return E2F_ERR_BAD_ARG; }
+  if (n_local < 0 || frame_elems <= 0) { set_error("e2f_video_blend: bad shape"); return E2F_ERR_BAD_ARG; }
+  return finish(launch_video_blend(img, ids, first, comp, n_local, static_cast<long long>(frame_elems), static_cast<cudaStream_t>(stream)), "e2f_video_blend");
+}
+
+int e2f_video_finalize(const float* comp, uint8_t* out, int64_t count, void* stream) {
+  if (!comp || !out) { set_error("e2f_video_finalize: null pointer"); return E2F_ERR_BAD_ARG; }
+  if (count < 0) { set_error("e2f_video_finalize: bad count"); return E2F_ERR_BAD_ARG; }
+  return finish(launch_video_finalize(comp, out, static_cast<long long>(count), static_cast<cudaStream_t>(stream)), "e2f_video_finalize");
+}
+
 }  // extern "C"

@@ -53,4 +53,12 @@ int conv_rows_pitch(int w, int lead, int channels);
 int launch_pack_rows(const float* x, void* hi, void* lo, int n, int c, int h, int w, int cin, int lead,
                      cudaStream_t stream);
 
+int launch_video_prepare_clip(const uint8_t* frames, const uint8_t* masks, const int* ids, float* out, int t, int h,
+                              int w, int hp, int wp, cudaStream_t stream);
+int launch_video_compose(const float* pred, const uint8_t* frames, const uint8_t* masks, const int* ids, uint8_t* img,
+                         int n_local, int h, int w, int hp, int wp, cudaStream_t stream);
+int launch_video_blend(const uint8_t* img, const int* ids, const int* first, float* comp, int n_local,
+                       long long frame_elems, cudaStream_t stream);
+int launch_video_finalize(const float* comp, uint8_t* out, long long count, cudaStream_t stream);
+
 }  // namespace e2f

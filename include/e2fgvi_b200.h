@@ -228,6 +228,26 @@ int e2f_conv2d_rows_bf16x3(int nsrc, const void* const* src_hi, const void* cons
                            float* out, void* out_hi, void* out_lo, int out_lead, int n, int h, int w, int cout, int groups,
                            float leaky_slope, int ksize, int stride, int pad, void* stream);
 
+/* Video-level driver — replaces the per-window host / eager-torch code of test.py:132-179.
+ * All buffers are device memory; `frames` [N][H][W][3] uint8 RGB, `masks` [N][H][W] uint8 (non-zero = hole, already
+ * dilated like test.py:55-68), `ids` int32 frame indices of the window (neighbours first, then reference frames).
+ *   e2f_video_prepare_clip : out[k][c][y][x] fp32, k < t, y < hp, x < wp  =  (frames[ids[k]]/255*2-1) * (1-mask),
+ *                            mirror-padded from (h, w) to (hp, wp) exactly like test.py:156-165
+ *                            (cat(x, flip(x))[:h + h_pad]); needs h <= hp <= 2h, w <= wp <= 2w.
+ *   e2f_video_compose      : img[k][y][x][c] uint8, k < n_local = hole ? uint8(((pred+1)/2)*255) : frame
+ *                            (test.py:167-174); pred is [>= n_local][3][hp][wp] fp32.
+ *   e2f_video_blend        : comp[ids[k]] = first[k] ? img[k] : comp*0.5 + img[k]*0.5, comp fp32 [N][frame_elems]
+ *                            (test.py:175-179); windows must be blended in schedule order.
+ *   e2f_video_finalize     : out uint8 = truncation of comp (test.py:195).
+ * Results are bit-identical to the reference's numpy / torch-CPU arithmetic. */
+int e2f_video_prepare_clip(const uint8_t* frames, const uint8_t* masks, const int* ids, float* out, int t, int h, int w,
+                           int hp, int wp, void* stream);
+int e2f_video_compose(const float* pred, const uint8_t* frames, const uint8_t* masks, const int* ids, uint8_t* img,
+                      int n_local, int h, int w, int hp, int wp, void* stream);
+int e2f_video_blend(const uint8_t* img, const int* ids, const int* first, float* comp, int n_local, int64_t frame_elems,
+                    void* stream);
+int e2f_video_finalize(const float* comp, uint8_t* out, int64_t count, void* stream);
+
 /* Number of kernel launches issued through this library since load (all threads); used by bench.py's
  * "gpu_launches" accounting. */
 int64_t e2f_launch_count(void);

@@ -95,3 +95,41 @@ def inpaint_video(model, frames_u8, masks_u8, neighbor_stride=5, ref_length=10, 
 def finalize(comp_frames):
     """The ``comp_frames[f].astype(np.uint8)`` of test.py:195 for every frame -> (N,H,W,3) uint8."""
     return np.stack([c.astype(np.uint8) for c in comp_frames])
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# The same arithmetic cut at the four kernel boundaries of e2fgvi_b200/csrc/video.cu (torch CPU, fp32), so that each
+# kernel can be checked bit for bit and the driver's host logic can run on a CPU-only box (tests only).
+def prepare_clip(frames, masks, ids, hp, wp):
+    """test.py:132,139,152-165 for one window: (N,H,W,3) u8, (N,H,W) u8, ids -> (t,3,hp,wp) fp32."""
+    ids = [int(i) for i in ids]
+    h, w = frames.shape[1:3]
+    imgs = frames[ids].permute(0, 3, 1, 2).contiguous().float().div(255) * 2 - 1
+    m = (masks[ids] != 0).float().unsqueeze(1)
+    x = imgs * (1 - m)
+    x = torch.cat([x, torch.flip(x, [2])], 2)[:, :, :hp, :]
+    x = torch.cat([x, torch.flip(x, [3])], 3)[:, :, :, :wp]
+    return x.contiguous()
+
+
+def compose(pred, frames, masks, ids, n_local):
+    """test.py:167-174: (>=n_local,3,hp,wp) fp32 -> (n_local,H,W,3) u8."""
+    ids = [int(i) for i in ids][:n_local]
+    h, w = frames.shape[1:3]
+    p = (pred[:n_local, :, :h, :w] + 1) / 2
+    p = (p.permute(0, 2, 3, 1).numpy() * 255).astype(np.uint8)
+    b = (masks[ids] != 0).numpy().astype(np.uint8)[..., None]
+    return torch.from_numpy(p * b + frames[ids].numpy() * (1 - b))
+
+
+def blend(img, ids, first, comp):
+    """test.py:175-179 on an fp32 canvas (N,H,W,3); uint8 -> fp32 is exact, so keeping first-seen frames as fp32 is
+    equivalent to the reference's uint8-then-float32 bookkeeping."""
+    for k, idx in enumerate([int(i) for i in ids]):
+        v = img[k].float()
+        comp[idx] = v if int(first[k]) else comp[idx] * 0.5 + v * 0.5
+    return comp
+
+
+def finalize_canvas(comp):
+    return torch.from_numpy(comp.numpy().astype(np.uint8))
