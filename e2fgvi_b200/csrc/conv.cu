@@ -21,6 +21,7 @@
 // Pipeline = gemm.cu: persistent CTAs, TMA warp / MMA warp / 4 epilogue warps, double-buffered TMEM accumulator.
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cstdlib>
 #include "common.cuh"
 #include "launch.h"
 
@@ -30,7 +31,8 @@ namespace conv {
 constexpr int BM = 128, BK = 64;
 constexpr int TILE_H = 8, TILE_W = 16;                  // 8 x 16 output pixels = 128 GEMM rows
 constexpr int A_TILE = BM * BK * 2;
-constexpr int EPI_WARPS = 4;
+constexpr int EPI_WARPS = 8;                             // two warps per TMEM lane quarter, half of the tile's columns each
+constexpr int MAX_COUT = 512;                            // bias staged in shared memory once per CTA
 constexpr int THREADS = (2 + EPI_WARPS) * 32;
 constexpr int MAX_SRC = 4;
 
@@ -43,7 +45,7 @@ struct Cfg {
   static constexpr int STAGES = (BN == 128) ? 3 : 4;
   static constexpr int ACC_COLS = 2 * BN;                 // accumulator: [Ah.Wh + Al.Wh | Ah.Wl], summed by the epilogue
   static constexpr int TMEM_COLS = 2 * ACC_COLS;          // double-buffered
-  static constexpr int SMEM = STAGES * STAGE + 256 + 1024;
+  static constexpr int SMEM = STAGES * STAGE + 256 + MAX_COUT * 4 + 1024;
 };
 
 struct Maps {
@@ -103,6 +105,104 @@ __device__ __forceinline__ TileCoord decode_tile(int tile, const Params& p, int 
   return t;
 }
 
+// Epilogue of one 128-pixel x BN-channel tile for the calling thread's accumulator row `r` (TMEM lane): sums the two
+// accumulator halves, + bias, LeakyReLU, optional residual, fp32 and/or bf16-split NHWC stores.  TW = tile width in
+// pixels (row r is pixel (y0 + r / TW, x0 + r % TW)); taddr = TMEM address of the row's first accumulator column.
+// The calling warp handles the 32-column chunks [c_begin, c_end) of the tile.  bias_s = the layer's bias in SHARED
+// memory (zeros when the layer has none): the per-channel __ldg's this replaces queued behind the epilogue's own
+// 32-line-per-instruction stores and made up 59 % of the epilogue warps' stall samples, which bounded every layer
+// whose main loop is shorter than ~10k cycles per tile (profiles/r01/ncu_conv_epilogue_r01.txt).
+template <int BN, int TW>
+__device__ __forceinline__ void epilogue_tile(const Params& p, const TileCoord& t, uint32_t taddr, int r, int cog,
+                                              const float* __restrict__ bias_s, int c_begin, int c_end) {
+  const int y = t.y0 + r / TW, x = t.x0 + r % TW;
+  const bool pix_ok = (y < p.H) && (x < p.W);
+  const size_t pix = (static_cast<size_t>(t.n) * p.H + y) * p.W + x;                      // fp32 out, residual
+  const size_t opix = (static_cast<size_t>(t.n) * p.H + y) * p.out_pitch + p.out_lead + x;   // split outputs
+  const int co_end = (t.g + 1) * cog;               // exclusive end of this group's output channels
+  const bool vec_ok = (p.Cout & 3) == 0;            // 16-byte aligned channel groups
+#pragma unroll 1
+  for (int c = c_begin; c < c_end; ++c) {
+    uint32_t v[32], v2[32];
+    tmem_ld32(taddr + c * 32, v);
+    tmem_ld32(taddr + BN + c * 32, v2);              // the Ah.Wl half of the accumulator
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(v2[i]));
+    const int co = t.co0 + c * 32;
+    if (pix_ok && co < co_end) {
+#pragma unroll
+      for (int g8 = 0; g8 < 4; ++g8) {              // 8 output channels at a time
+        const int cb = co + g8 * 8;
+        if (vec_ok && cb + 8 <= co_end) {
+          float f[8];
+          const float4 b0 = *reinterpret_cast<const float4*>(bias_s + cb), b1 = *reinterpret_cast<const float4*>(bias_s + cb + 4);
+          const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float a = __uint_as_float(v[g8 * 8 + i]) + bb[i];
+            f[i] = a > 0.f ? a : a * p.slope;
+          }
+          if (p.residual) {
+            const float4* r4 = reinterpret_cast<const float4*>(p.residual + pix * p.Cout + cb);
+            const float4 ra = __ldg(r4), rb = __ldg(r4 + 1);
+            f[0] += ra.x; f[1] += ra.y; f[2] += ra.z; f[3] += ra.w;
+            f[4] += rb.x; f[5] += rb.y; f[6] += rb.z; f[7] += rb.w;
+          }
+          if (p.out) {
+            float4* d4 = reinterpret_cast<float4*>(p.out + pix * p.Cout + cb);
+            d4[0] = make_float4(f[0], f[1], f[2], f[3]);
+            d4[1] = make_float4(f[4], f[5], f[6], f[7]);
+          }
+          if (p.out_hi) {
+            uint32_t hp[4], lp[4];                  // packed bf16 pairs, kept in registers
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const __nv_bfloat162 hb = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+              const float2 hf = __bfloat1622float2(hb);
+              const __nv_bfloat162 lb = __floats2bfloat162_rn(f[2 * i] - hf.x, f[2 * i + 1] - hf.y);
+              hp[i] = *reinterpret_cast<const uint32_t*>(&hb);
+              lp[i] = *reinterpret_cast<const uint32_t*>(&lb);
+            }
+            *reinterpret_cast<uint4*>(p.out_hi + opix * p.Cout + cb) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
+            *reinterpret_cast<uint4*>(p.out_lo + opix * p.Cout + cb) = make_uint4(lp[0], lp[1], lp[2], lp[3]);
+          }
+        } else if (cb < co_end) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            if (cb + i < co_end) {
+              float a = __uint_as_float(v[g8 * 8 + i]) + bias_s[cb + i];
+              a = a > 0.f ? a : a * p.slope;
+              if (p.residual) a += __ldg(p.residual + pix * p.Cout + cb + i);
+              if (p.out) p.out[pix * p.Cout + cb + i] = a;
+              if (p.out_hi) {
+                const __nv_bfloat16 hb = __float2bfloat16_rn(a);
+                p.out_hi[opix * p.Cout + cb + i] = hb;
+                p.out_lo[opix * p.Cout + cb + i] = __float2bfloat16_rn(a - __bfloat162float(hb));
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+  // row-gapped split output: the pixel at x == 0 also writes the zero gap in front of its row, the very last pixel
+  // the zero tail (once per pixel: only the first N tile of group 0 does it; Cout % 8 == 0 is checked by the API)
+  if (p.out_hi && p.out_lead && pix_ok && t.co0 == 0 && c_begin == 0) {
+    const uint4 z = make_uint4(0, 0, 0, 0);
+    if (x == 0) {
+      uint4* zh = reinterpret_cast<uint4*>(p.out_hi + (opix - p.out_lead) * p.Cout);
+      uint4* zl = reinterpret_cast<uint4*>(p.out_lo + (opix - p.out_lead) * p.Cout);
+      for (int i = 0; i < p.out_lead * p.Cout / 8; ++i) zh[i] = zl[i] = z;
+    }
+    if (x == p.W - 1 && y == p.H - 1 && t.n == p.N - 1) {
+      uint4* zh = reinterpret_cast<uint4*>(p.out_hi + (opix + 1) * p.Cout);
+      uint4* zl = reinterpret_cast<uint4*>(p.out_lo + (opix + 1) * p.Cout);
+      for (int i = 0; i < p.out_tail * p.Cout / 8; ++i) zh[i] = zl[i] = z;
+    }
+  }
+}
+
 template <int BN>
 __global__ void __launch_bounds__(THREADS, 1) conv3x3_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Params p) {
   constexpr int W_TILE = Cfg<BN>::W_TILE, STAGE = Cfg<BN>::STAGE, STAGES = Cfg<BN>::STAGES, TMEM_COLS = Cfg<BN>::TMEM_COLS;
@@ -113,8 +213,10 @@ __global__ void __launch_bounds__(THREADS, 1) conv3x3_kernel(const __grid_consta
   uint64_t* acc_full = empty + STAGES;
   uint64_t* acc_empty = acc_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  float* bias_s = reinterpret_cast<float*>(smem + STAGES * STAGE + 256);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int i = tid; i < MAX_COUT; i += THREADS) bias_s[i] = (p.bias && i < p.Cout) ? __ldg(p.bias + i) : 0.f;
   const int tiles_y = (p.H + TILE_H - 1) / TILE_H, tiles_x = (p.W + TILE_W - 1) / TILE_W;
   const int cog = p.Cout / p.groups;
   const int tiles_ng = (cog + BN - 1) / BN;
@@ -146,7 +248,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv3x3_kernel(const __grid_consta
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (im2col by coordinates)
-    if (lane == 0) {
+    if (elect_one()) {   // one thread, chosen by elect.sync: ptxas then emits bare UTCHMMA / UTMALDG (no per-instruction ELECT loop)
       uint32_t it = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const TileCoord t = decode_tile<BN>(tile, p, tiles_y, tiles_x, tiles_ng);
@@ -191,7 +293,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv3x3_kernel(const __grid_consta
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    if (elect_one()) {   // one thread, chosen by elect.sync: ptxas then emits bare UTCHMMA / UTMALDG (no per-instruction ELECT loop)
       // The Wh and Wl tiles are adjacent in a stage, so ONE N = 2*BN instruction multiplies Ah with both
       // (accumulator columns [0,BN) and [BN,2BN)); a second, N = BN wide, adds Al.Wh to the first half.  Ah is read from
       // shared memory once instead of twice: 3 -> 2 instructions per K step, ~20% less operand traffic on the
@@ -224,99 +326,176 @@ __global__ void __launch_bounds__(THREADS, 1) conv3x3_kernel(const __grid_consta
     }
   } else {
     // ------------------------------------------------------------------ epilogue
-    const int q = warp & 3;
+    const int q = warp & 3;                                   // TMEM lane quarter this warp may read
+    constexpr int NCH = BN / 32;                              // 32-column chunks per tile, split between the two warps of a quarter
+    const int c_begin = (warp - 2) < 4 ? 0 : (NCH + 1) / 2, c_end = (warp - 2) < 4 ? (NCH + 1) / 2 : NCH;
     uint32_t local = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
       const int buf = local & 1;
       const TileCoord t = decode_tile<BN>(tile, p, tiles_y, tiles_x, tiles_ng);
       mbar_wait(&acc_full[buf], (local >> 1) & 1);
       tc_fence_after_sync();
-      const int r = q * 32 + lane;
-      const int y = t.y0 + r / TILE_W, x = t.x0 + r % TILE_W;
-      const bool pix_ok = (y < p.H) && (x < p.W);
-      const size_t pix = (static_cast<size_t>(t.n) * p.H + y) * p.W + x;                      // fp32 out, residual
-      const size_t opix = (static_cast<size_t>(t.n) * p.H + y) * p.out_pitch + p.out_lead + x;   // split outputs
-      const int co_end = (t.g + 1) * cog;               // exclusive end of this group's output channels
-      const bool vec_ok = (p.Cout & 3) == 0;            // 16-byte aligned channel groups
-      const uint32_t taddr = tbase + (static_cast<uint32_t>(q * 32) << 16) + buf * Cfg<BN>::ACC_COLS;
+      epilogue_tile<BN, TILE_W>(p, t, tbase + (static_cast<uint32_t>(q * 32) << 16) + buf * Cfg<BN>::ACC_COLS, q * 32 + lane, cog,
+                                bias_s, c_begin, c_end);
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[buf]);
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tbase, TMEM_COLS);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// HALO variant for the low-Cout, high-resolution 3x3 / stride 1 / pad 1 layers (encoder conv 2, decoder deconv-2 conv, the
+// 3-channel output conv: Cout <= 64, groups 1).  There the generic kernel is bound by the L2 -> SM fabric (~6300 B/clk
+// chip-wide): every 64-channel chunk of a tile is fetched nine times, once per tap, and the matching weight tile comes
+// along every time — 432 KB per 128 x 64 output tile against 3456 MMA cycles.  Here
+//  * the tile is 8 x 16 pixels and ONE TMA box {64 ch, 10 x, 18 y} per (chunk, hi | lo) brings its whole halo
+//    (23 KB instead of 9 x 16 KB); tap (dy, dx) reads it in place through a UMMA descriptor whose start address is shifted
+//    by (dy*10 + dx) pixels of 128 B and whose 8-row-group stride (SBO) is one halo row, 1280 B.  The 128B swizzle is a
+//    function of absolute shared-memory address bits, so the shifted start needs no base offset (tools/halo_probe.cu,
+//    profiles/r01/halo_probe.log);
+//  * all weight tiles of the layer (9 taps x chunks x [Wh | Wl]) are loaded ONCE per persistent CTA and stay in shared
+//    memory (144 KB for 64 -> 64), so steady-state L2 traffic is the 46 KB halo pair per chunk;
+//  * the halo ring holds single (hi or lo) pieces: all Ah MMAs of a chunk (9 taps x 4, N = 2*BN against [Wh | Wl]) are
+//    issued from one piece, then all Al MMAs (N = BN against Wh) from the next.
+constexpr int HTILE_W = 8, HTILE_H = 16, HALO_W = HTILE_W + 2, HALO_H = HTILE_H + 2;
+constexpr int HALO_BYTES = HALO_W * HALO_H * BK * 2;     // 23040
+constexpr int HALO_SLOT = 23552;                        // rounded up to the 1024-byte swizzle atom
+constexpr int HALO_MAX_SLOTS = 6;
+constexpr int SMEM_LIMIT = 232448;                      // 227 KB opt-in maximum per CTA
+
+__host__ __device__ constexpr int halo_w_bytes(int bn, int chunks_total) { return 9 * chunks_total * 2 * bn * BK * 2; }
+
+template <int BN>
+__global__ void __launch_bounds__(THREADS, 1) conv3x3_halo_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Params p,
+                                                                  const int nslots) {
+  constexpr int W_TILE = Cfg<BN>::W_TILE, TMEM_COLS = Cfg<BN>::TMEM_COLS;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int w_bytes = halo_w_bytes(BN, p.chunks_total);
+  uint8_t* ring = smem + w_bytes;                                   // w_bytes is a multiple of 1024
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(ring + nslots * HALO_SLOT);
+  uint64_t* a_empty = a_full + HALO_MAX_SLOTS;
+  uint64_t* acc_full = a_empty + HALO_MAX_SLOTS;
+  uint64_t* acc_empty = acc_full + 2;
+  uint64_t* w_full = acc_empty + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_full + 1);
+  float* bias_s = reinterpret_cast<float*>(ring + nslots * HALO_SLOT + 256);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int i = tid; i < MAX_COUT; i += THREADS) bias_s[i] = (p.bias && i < p.Cout) ? __ldg(p.bias + i) : 0.f;
+  const int tiles_y = (p.H + HTILE_H - 1) / HTILE_H, tiles_x = (p.W + HTILE_W - 1) / HTILE_W;
+  const int num_tiles = p.N * tiles_y * tiles_x;
+  const int pieces = 2 * p.chunks_total;                            // (chunk, hi | lo) halo pieces per tile
+
+  if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+  if (tid == 0) {
+    for (int s = 0; s < nslots; ++s) {
+      mbar_init(&a_full[s], 1);
+      mbar_init(&a_empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&acc_full[s], 1);
+      mbar_init(&acc_empty[s], EPI_WARPS);
+    }
+    mbar_init(w_full, 1);
+    fence_barrier_init();
+    tma_prefetch_desc(&maps.w_hi);
+    tma_prefetch_desc(&maps.w_lo);
+    for (int i = 0; i < p.nsrc; ++i) {
+      tma_prefetch_desc(&maps.a_hi[i]);
+      tma_prefetch_desc(&maps.a_lo[i]);
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tbase = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (elect_one()) {   // one thread, chosen by elect.sync: ptxas then emits bare UTCHMMA / UTMALDG (no per-instruction ELECT loop)
+      // resident weights: slot (tap, chunk) = [Wh (BN rows) | Wl (BN rows)], K column of the packed weight = (tap, chunk)
+      mbar_arrive_expect_tx(w_full, static_cast<uint32_t>(w_bytes));
+      for (int tap = 0; tap < 9; ++tap)
+        for (int c = 0; c < p.chunks_total; ++c) {
+          const int kb = tap * p.chunks_total + c;
+          const uint32_t dst = smem_u32(smem) + kb * 2 * W_TILE;
+          tma_load_2d(dst, &maps.w_hi, w_full, kb * BK, 0);
+          tma_load_2d(dst + W_TILE, &maps.w_lo, w_full, kb * BK, 0);
+        }
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int tx = tile % tiles_x, ty = (tile / tiles_x) % tiles_y, n = tile / (tiles_x * tiles_y);
+        const int xx = tx * HTILE_W - 1, yy = ty * HTILE_H - 1;
+        for (int s = 0; s < p.nsrc; ++s)
+          for (int j = 0; j < p.chunks[s]; ++j)
+            for (int part = 0; part < 2; ++part, ++it) {
+              const int slot = it % nslots;
+              mbar_wait(&a_empty[slot], ((it / nslots) & 1) ^ 1);
+              mbar_arrive_expect_tx(&a_full[slot], HALO_BYTES);
+              tma_load_4d(smem_u32(ring + slot * HALO_SLOT), part ? &maps.a_lo[s] : &maps.a_hi[s], &a_full[slot], j * BK,
+                          xx, yy, n);
+            }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (elect_one()) {   // one thread, chosen by elect.sync: ptxas then emits bare UTCHMMA / UTMALDG (no per-instruction ELECT loop)
+      const uint32_t idesc = idesc_bf16(BM, BN), idesc2 = idesc_bf16(BM, 2 * BN);
+      const uint64_t d_a0 = umma_desc_sw128(smem_u32(ring), 16, HALO_W * 128);
+      const uint64_t d_w0 = umma_desc_sw128(smem_u32(smem), 16, 1024);
+      mbar_wait(w_full, 0);
+      uint32_t it = 0, local = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+        const int buf = local & 1;
+        mbar_wait(&acc_empty[buf], ((local >> 1) & 1) ^ 1);
+        tc_fence_after_sync();
+        const uint32_t d = tbase + buf * Cfg<BN>::ACC_COLS;
+        for (int pc = 0; pc < pieces; ++pc, ++it) {
+          const int slot = it % nslots;
+          const int chunk = pc >> 1, lo = pc & 1;
+          mbar_wait(&a_full[slot], (it / nslots) & 1);
+          tc_fence_after_sync();
+          const uint64_t da = d_a0 + ((slot * HALO_SLOT) >> 4);
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t v[32], v2[32];
-        tmem_ld32(taddr + c * 32, v);
-        tmem_ld32(taddr + BN + c * 32, v2);              // the Ah.Wl half of the accumulator
-        tmem_ld_wait();
+          for (int tap = 0; tap < 9; ++tap) {
+            const uint64_t dat = da + (((tap / 3) * HALO_W + tap % 3) * 128 >> 4);
+            const uint64_t dw = d_w0 + (((tap * p.chunks_total + chunk) * 2 * W_TILE) >> 4);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(v2[i]));
-        const int co = t.co0 + c * 32;
-        if (pix_ok && co < co_end) {
-#pragma unroll
-          for (int g8 = 0; g8 < 4; ++g8) {              // 8 output channels at a time
-            const int cb = co + g8 * 8;
-            if (vec_ok && cb + 8 <= co_end) {
-              float f[8];
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const float a = __uint_as_float(v[g8 * 8 + i]) + (p.bias ? __ldg(p.bias + cb + i) : 0.f);
-                f[i] = a > 0.f ? a : a * p.slope;
-              }
-              if (p.residual) {
-                const float4* r4 = reinterpret_cast<const float4*>(p.residual + pix * p.Cout + cb);
-                const float4 ra = __ldg(r4), rb = __ldg(r4 + 1);
-                f[0] += ra.x; f[1] += ra.y; f[2] += ra.z; f[3] += ra.w;
-                f[4] += rb.x; f[5] += rb.y; f[6] += rb.z; f[7] += rb.w;
-              }
-              if (p.out) {
-                float4* d4 = reinterpret_cast<float4*>(p.out + pix * p.Cout + cb);
-                d4[0] = make_float4(f[0], f[1], f[2], f[3]);
-                d4[1] = make_float4(f[4], f[5], f[6], f[7]);
-              }
-              if (p.out_hi) {
-                uint32_t hp[4], lp[4];                  // packed bf16 pairs, kept in registers
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                  const __nv_bfloat162 hb = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
-                  const float2 hf = __bfloat1622float2(hb);
-                  const __nv_bfloat162 lb = __floats2bfloat162_rn(f[2 * i] - hf.x, f[2 * i + 1] - hf.y);
-                  hp[i] = *reinterpret_cast<const uint32_t*>(&hb);
-                  lp[i] = *reinterpret_cast<const uint32_t*>(&lb);
-                }
-                *reinterpret_cast<uint4*>(p.out_hi + opix * p.Cout + cb) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
-                *reinterpret_cast<uint4*>(p.out_lo + opix * p.Cout + cb) = make_uint4(lp[0], lp[1], lp[2], lp[3]);
-              }
-            } else if (cb < co_end) {
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                if (cb + i < co_end) {
-                  float a = __uint_as_float(v[g8 * 8 + i]) + (p.bias ? __ldg(p.bias + cb + i) : 0.f);
-                  a = a > 0.f ? a : a * p.slope;
-                  if (p.residual) a += __ldg(p.residual + pix * p.Cout + cb + i);
-                  if (p.out) p.out[pix * p.Cout + cb + i] = a;
-                  if (p.out_hi) {
-                    const __nv_bfloat16 hb = __float2bfloat16_rn(a);
-                    p.out_hi[opix * p.Cout + cb + i] = hb;
-                    p.out_lo[opix * p.Cout + cb + i] = __float2bfloat16_rn(a - __bfloat162float(hb));
-                  }
-                }
-              }
+            for (int k = 0; k < BK / 16; ++k) {
+              if (lo)
+                umma_f16(d, dat + 2 * k, dw + 2 * k, idesc, 1);                          // + Al.Wh
+              else
+                umma_f16(d, dat + 2 * k, dw + 2 * k, idesc2, (pc | tap | k) != 0);       // [Ah.Wh | Ah.Wl]
             }
           }
+          umma_commit(&a_empty[slot]);
         }
+        umma_commit(&acc_full[buf]);
       }
-      // row-gapped split output: the pixel at x == 0 also writes the zero gap in front of its row, the very last pixel
-      // the zero tail (once per pixel: only the first N tile of group 0 does it; Cout % 8 == 0 is checked by the API)
-      if (p.out_hi && p.out_lead && pix_ok && t.co0 == 0) {
-        const uint4 z = make_uint4(0, 0, 0, 0);
-        if (x == 0) {
-          uint4* zh = reinterpret_cast<uint4*>(p.out_hi + (opix - p.out_lead) * p.Cout);
-          uint4* zl = reinterpret_cast<uint4*>(p.out_lo + (opix - p.out_lead) * p.Cout);
-          for (int i = 0; i < p.out_lead * p.Cout / 8; ++i) zh[i] = zl[i] = z;
-        }
-        if (x == p.W - 1 && y == p.H - 1 && t.n == p.N - 1) {
-          uint4* zh = reinterpret_cast<uint4*>(p.out_hi + (opix + 1) * p.Cout);
-          uint4* zl = reinterpret_cast<uint4*>(p.out_lo + (opix + 1) * p.Cout);
-          for (int i = 0; i < p.out_tail * p.Cout / 8; ++i) zh[i] = zl[i] = z;
-        }
-      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue
+    const int q = warp & 3;                                   // TMEM lane quarter this warp may read
+    constexpr int NCH = BN / 32;                              // 32-column chunks per tile, split between the two warps of a quarter
+    const int c_begin = (warp - 2) < 4 ? 0 : (NCH + 1) / 2, c_end = (warp - 2) < 4 ? (NCH + 1) / 2 : NCH;
+    uint32_t local = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+      const int buf = local & 1;
+      TileCoord t;
+      t.x0 = (tile % tiles_x) * HTILE_W;
+      t.y0 = ((tile / tiles_x) % tiles_y) * HTILE_H;
+      t.n = tile / (tiles_x * tiles_y);
+      t.g = 0;
+      t.co0 = 0;
+      mbar_wait(&acc_full[buf], (local >> 1) & 1);
+      tc_fence_after_sync();
+      epilogue_tile<BN, HTILE_W>(p, t, tbase + (static_cast<uint32_t>(q * 32) << 16) + buf * Cfg<BN>::ACC_COLS, q * 32 + lane,
+                                 p.Cout, bias_s, c_begin, c_end);
       tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[buf]);
@@ -409,6 +588,10 @@ int launch_conv3x3(int nsrc, const void* const* src_hi, const void* const* src_l
     set_error("cuTensorMapEncodeTiled is not available from the driver");
     return -4;
   }
+  if (cout > MAX_COUT) {
+    set_error("conv3x3: at most %d output channels (the bias is staged in shared memory), got %d", MAX_COUT, cout);
+    return -2;
+  }
   const int cog = cout / groups;
   const int bn = cog <= 32 ? 32 : (cog <= 64 ? 64 : 128);
   Maps maps;
@@ -451,6 +634,19 @@ int launch_conv3x3(int nsrc, const void* const* src_hi, const void* const* src_l
       }
     }
   }
+  // HALO variant (see conv3x3_halo_kernel): dense 3x3 / s1 / p1 layers with <= 64 output channels whose weights fit
+  // in shared memory next to >= 3 halo slots.  E2F_CONV_HALO=0 forces the generic kernel (A/B timing, debugging).
+  int chunks_all = 0;
+  for (int i = 0; i < nsrc; ++i) chunks_all += (src_channels[i] / groups + BK - 1) / BK;
+  int halo_slots = 0;
+  if (!in_rows && ks == 3 && stride == 1 && pad == 1 && groups == 1 && cout <= 64) {
+    static const bool enabled = [] {
+      const char* e = getenv("E2F_CONV_HALO");
+      return !(e && e[0] == '0');
+    }();
+    const int room = SMEM_LIMIT - 1024 - 256 - MAX_COUT * 4 - halo_w_bytes(bn, chunks_all);
+    if (enabled && room >= 3 * HALO_SLOT) halo_slots = room / HALO_SLOT < HALO_MAX_SLOTS ? room / HALO_SLOT : HALO_MAX_SLOTS;
+  }
   const cuuint32_t estr4[4] = {1, static_cast<cuuint32_t>(stride), static_cast<cuuint32_t>(stride), 1};
   for (int i = 0; i < (in_rows ? 0 : nsrc); ++i) {
     const int c = src_channels[i];
@@ -462,7 +658,8 @@ int launch_conv3x3(int nsrc, const void* const* src_hi, const void* const* src_l
     const cuuint64_t strides[3] = {static_cast<cuuint64_t>(c) * 2, static_cast<cuuint64_t>(w_in) * c * 2,
                                    static_cast<cuuint64_t>(h_in) * w_in * c * 2};
     // the box spans TILE*stride input elements and is traversed with elementStrides = stride: TILE elements land
-    const cuuint32_t box[4] = {BK, static_cast<cuuint32_t>(TILE_W * stride), static_cast<cuuint32_t>(TILE_H * stride), 1};
+    const cuuint32_t box[4] = {BK, static_cast<cuuint32_t>(halo_slots ? HALO_W : TILE_W * stride),
+                               static_cast<cuuint32_t>(halo_slots ? HALO_H : TILE_H * stride), 1};
     for (int part = 0; part < 2; ++part) {
       CUresult r = enc(part ? &maps.a_lo[i] : &maps.a_hi[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4,
                        const_cast<void*>(part ? src_lo[i] : src_hi[i]), dims, strides, box, estr4,
@@ -501,6 +698,30 @@ int launch_conv3x3(int nsrc, const void* const* src_hi, const void* const* src_l
       e = cudaFuncSetAttribute(conv3x3_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<32>::SMEM);
     if (e != cudaSuccess) return static_cast<int>(e);
     configured = true;
+  }
+  if (halo_slots) {
+    static bool halo_configured = false;
+    if (!halo_configured) {
+      cudaError_t e = cudaFuncSetAttribute(conv3x3_halo_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+      if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(conv3x3_halo_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+      if (e != cudaSuccess) return static_cast<int>(e);
+      halo_configured = true;
+    }
+    const long long htiles = static_cast<long long>(n) * ((h + HTILE_H - 1) / HTILE_H) * ((w + HTILE_W - 1) / HTILE_W);
+    if (htiles == 0) return 0;
+    if (htiles > 0x7FFFFFFFLL) {
+      set_error("conv3x3: too many tiles");
+      return -2;
+    }
+    const int hgrid = htiles < num_sms() ? static_cast<int>(htiles) : num_sms();
+    const int hsmem = 1024 + halo_w_bytes(bn, chunks_all) + halo_slots * HALO_SLOT + 256 + MAX_COUT * 4;
+    if (bn == 32)
+      conv3x3_halo_kernel<32><<<hgrid, THREADS, hsmem, stream>>>(maps, p, halo_slots);
+    else
+      conv3x3_halo_kernel<64><<<hgrid, THREADS, hsmem, stream>>>(maps, p, halo_slots);
+    count_launch();
+    return static_cast<int>(cudaGetLastError());
   }
   const int tiles_y = (h + TILE_H - 1) / TILE_H, tiles_x = (w + TILE_W - 1) / TILE_W;
   const int tiles_ng = (cout / groups + bn - 1) / bn;

@@ -201,7 +201,7 @@ dcn_kernel(const __grid_constant__ CUtensorMap tmap_w, const __half* __restrict_
     }
   } else if (warp == TMA_WARP) {
     // ------------------------------------------------------------------ B producer: packed weight via TMA
-    if (lane == 0) {
+    if (elect_one()) {   // one thread, chosen by elect.sync: ptxas then emits bare UTCHMMA / UTMALDG (no per-instruction ELECT loop)
       for (int j = 0; j < NUM_KB; ++j) {
         const int stage = j % STAGES;
         const uint32_t phase = (j / STAGES) & 1;
@@ -212,7 +212,7 @@ dcn_kernel(const __grid_constant__ CUtensorMap tmap_w, const __half* __restrict_
     }
   } else {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    if (elect_one()) {   // one thread, chosen by elect.sync: ptxas then emits bare UTCHMMA / UTMALDG (no per-instruction ELECT loop)
       const uint32_t idesc = umma_idesc_f16(BLOCK_M, COUT, 0, 0);
       const uint64_t d_a0 = umma_desc_sw128(smem_u32(sA), 16, 1024), d_b0 = umma_desc_sw128(smem_u32(sB), 16, 1024);
       for (int j = 0; j < NUM_KB; ++j) {

@@ -503,7 +503,7 @@ __global__ void __launch_bounds__(THREADS, CTAS_PER_SM) focal_attn_kernel(const 
     }
   } else {
     // =================================================================== tcgen05 issuer
-    if (lane == 0) {
+    if (elect_one()) {   // one thread, chosen by elect.sync: ptxas then emits bare UTCHMMA (no per-instruction ELECT loop)
       const uint32_t idesc_s = umma_idesc_f16(BM, BN, 0, 0);   // S = Q K^T, both K-major (d contiguous)
       const uint32_t idesc_o = umma_idesc_f16(BM, HD, 0, 1);   // O = P V: P from TMEM, V MN-major (d contiguous per key)
       const uint32_t sQ = smem_u32(smem + Smem::Q), sK = smem_u32(smem + Smem::K);

@@ -96,7 +96,7 @@ linear_kernel(const __grid_constant__ CUtensorMap tm_ah, const __grid_constant__
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    if (elect_one()) {   // one thread, chosen by elect.sync: ptxas then emits bare UTCHMMA / UTMALDG (no per-instruction ELECT loop)
       uint32_t it = 0;
       for (int item = first_item; item < num_items; item += item_step) {
         const int m0 = ((item / tiles_n) * CL + rank) * BM, n0 = (item % tiles_n) * BN;
@@ -122,7 +122,7 @@ linear_kernel(const __grid_constant__ CUtensorMap tm_ah, const __grid_constant__
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    if (elect_one()) {   // one thread, chosen by elect.sync: ptxas then emits bare UTCHMMA / UTMALDG (no per-instruction ELECT loop)
       const uint32_t idesc = idesc_bf16(BM, BN);
       // stage-0 descriptors; stage s / K step k are reached with one 64-bit add each
       const uint64_t d_ah0 = umma_desc_sw128(smem_u32(smem), 16, 1024);

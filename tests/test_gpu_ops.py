@@ -330,6 +330,11 @@ def test_linear_weight_cache_tracks_updates(cuda):
     dict(n=1, h=24, w=40, src=[64], cout=3),                                    # last decoder conv (3 output channels)
     dict(n=1, h=10, w=14, src=[128], cout=432),                                 # offset-head conv 6
     dict(n=1, h=7, w=5, src=[8], cout=16),                                      # tiny
+    # HALO variant (Cout <= 64, groups 1): ragged 8 x 16 tiles, several images, residual, 2 sources, 2 K chunks
+    dict(n=3, h=40, w=44, src=[64], cout=64, slope=0.2),                        # encoder conv 1 / decoder conv 4 shape
+    dict(n=2, h=33, w=21, src=[32, 16], cout=40, residual=True, slope=0.1),
+    dict(n=1, h=16, w=8, src=[128], cout=16),                                   # exactly one tile, 2 chunks x (hi, lo)
+    dict(n=2, h=50, w=30, src=[64, 64], cout=24),                               # 2 chunks from 2 sources, BN = 32
 ])
 def test_conv3x3_bf16x3(cuda, case):
     F = torch.nn.functional
