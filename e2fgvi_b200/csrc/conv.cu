@@ -33,6 +33,7 @@ constexpr int TILE_H = 8, TILE_W = 16;                  // 8 x 16 output pixels 
 constexpr int A_TILE = BM * BK * 2;
 constexpr int EPI_WARPS = 8;                             // two warps per TMEM lane quarter, half of the tile's columns each
 constexpr int MAX_COUT = 512;                            // bias staged in shared memory once per CTA
+constexpr int EPI_STAGE = 2048;                          // per epilogue warp: 32 rows x 64 bytes store-transposition buffer
 constexpr int THREADS = (2 + EPI_WARPS) * 32;
 constexpr int MAX_SRC = 4;
 
@@ -45,7 +46,7 @@ struct Cfg {
   static constexpr int STAGES = (BN == 128) ? 3 : 4;
   static constexpr int ACC_COLS = 2 * BN;                 // accumulator: [Ah.Wh + Al.Wh | Ah.Wl], summed by the epilogue
   static constexpr int TMEM_COLS = 2 * ACC_COLS;          // double-buffered
-  static constexpr int SMEM = STAGES * STAGE + 256 + MAX_COUT * 4 + 1024;
+  static constexpr int SMEM = STAGES * STAGE + 256 + MAX_COUT * 4 + EPI_WARPS * EPI_STAGE + 1024;
 };
 
 struct Maps {
@@ -112,9 +113,17 @@ __device__ __forceinline__ TileCoord decode_tile(int tile, const Params& p, int 
 // memory (zeros when the layer has none): the per-channel __ldg's this replaces queued behind the epilogue's own
 // 32-line-per-instruction stores and made up 59 % of the epilogue warps' stall samples, which bounded every layer
 // whose main loop is shorter than ~10k cycles per tile (profiles/r01/ncu_conv_epilogue_r01.txt).
+//
+// Stores are STAGED through `stage` (2 KB of shared memory per epilogue warp): with thread = pixel, a direct 16-byte store
+// per thread hits 32 different 128-byte lines per instruction (pixels are Cout * 2 or 4 bytes apart), ~125 cycles each,
+// which made the epilogue the bottleneck of the layers with a short main loop.  Each warp instead transposes its
+// 32 rows x 64 bytes through a conflict-free XOR-swizzled buffer so that 4 consecutive lanes write one pixel's 64
+// contiguous bytes (8 lines per instruction).  Chunks that are not 32 full, 16-byte-aligned channels take the direct path.
 template <int BN, int TW>
 __device__ __forceinline__ void epilogue_tile(const Params& p, const TileCoord& t, uint32_t taddr, int r, int cog,
-                                              const float* __restrict__ bias_s, int c_begin, int c_end) {
+                                              const float* __restrict__ bias_s, int c_begin, int c_end,
+                                              uint8_t* __restrict__ stage) {
+  const int lane = r & 31;
   const int y = t.y0 + r / TW, x = t.x0 + r % TW;
   const bool pix_ok = (y < p.H) && (x < p.W);
   const size_t pix = (static_cast<size_t>(t.n) * p.H + y) * p.W + x;                      // fp32 out, residual
@@ -130,7 +139,93 @@ __device__ __forceinline__ void epilogue_tile(const Params& p, const TileCoord& 
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(v2[i]));
     const int co = t.co0 + c * 32;
-    if (pix_ok && co < co_end) {
+    if (vec_ok && co + 32 <= co_end) {
+      // ------------------------------------------------------------ staged, coalesced stores (warp-uniform branch)
+      float f[32];
+#pragma unroll
+      for (int g4 = 0; g4 < 8; ++g4) {
+        const float4 b = *reinterpret_cast<const float4*>(bias_s + co + g4 * 4);
+        const float bb[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float a = __uint_as_float(v[g4 * 4 + i]) + bb[i];
+          f[g4 * 4 + i] = a > 0.f ? a : a * p.slope;
+        }
+      }
+      if (p.residual && pix_ok) {
+        const float4* r4 = reinterpret_cast<const float4*>(p.residual + pix * p.Cout + co);
+#pragma unroll
+        for (int g4 = 0; g4 < 8; ++g4) {
+          const float4 ra = __ldg(r4 + g4);
+          f[g4 * 4] += ra.x; f[g4 * 4 + 1] += ra.y; f[g4 * 4 + 2] += ra.z; f[g4 * 4 + 3] += ra.w;
+        }
+      }
+      // write side: row = lane, logical 16-byte chunk cc at physical chunk cc ^ ((lane >> 1) & 3); read side: lanes
+      // 4k..4k+3 fetch the 4 chunks of row j*8 + k.  Both sides touch 8 distinct bank groups per quarter-warp.
+      const uint32_t wbase = smem_u32(stage) + lane * 64, wsw = (lane >> 1) & 3;
+      const int sub = lane & 3, prow = lane >> 2, rbase = r - lane;
+      auto st_chunk = [&](int cc, uint32_t a, uint32_t b, uint32_t c2, uint32_t d) {
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(wbase + ((cc ^ wsw) << 4)), "r"(a), "r"(b), "r"(c2), "r"(d)
+                     : "memory");
+      };
+      auto ld_chunk = [&](int rr) {
+        uint4 u;
+        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w)
+                     : "r"(smem_u32(stage) + rr * 64 + ((sub ^ ((rr >> 1) & 3)) << 4))
+                     : "memory");
+        return u;
+      };
+      if (p.out) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {                 // 16 fp32 channels = 64 bytes per row and pass
+#pragma unroll
+          for (int cc = 0; cc < 4; ++cc)
+            st_chunk(cc, __float_as_uint(f[h * 16 + cc * 4]), __float_as_uint(f[h * 16 + cc * 4 + 1]),
+                     __float_as_uint(f[h * 16 + cc * 4 + 2]), __float_as_uint(f[h * 16 + cc * 4 + 3]));
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int rr = j * 8 + prow, R = rbase + rr;
+            const int yy = t.y0 + R / TW, xx = t.x0 + R % TW;
+            const uint4 u = ld_chunk(rr);
+            if (yy < p.H && xx < p.W)
+              *reinterpret_cast<uint4*>(p.out + ((static_cast<size_t>(t.n) * p.H + yy) * p.W + xx) * p.Cout + co + h * 16 +
+                                        sub * 4) = u;
+          }
+          __syncwarp();
+        }
+      }
+      if (p.out_hi) {
+        uint32_t hp[16], lp[16];                      // packed bf16 pairs
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const __nv_bfloat162 hb = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+          const float2 hf = __bfloat1622float2(hb);
+          const __nv_bfloat162 lb = __floats2bfloat162_rn(f[2 * i] - hf.x, f[2 * i + 1] - hf.y);
+          hp[i] = *reinterpret_cast<const uint32_t*>(&hb);
+          lp[i] = *reinterpret_cast<const uint32_t*>(&lb);
+        }
+#pragma unroll
+        for (int part = 0; part < 2; ++part) {        // 32 bf16 channels = 64 bytes per row: hi, then lo
+          const uint32_t* src = part ? lp : hp;
+          __nv_bfloat16* dst = part ? p.out_lo : p.out_hi;
+#pragma unroll
+          for (int cc = 0; cc < 4; ++cc) st_chunk(cc, src[cc * 4], src[cc * 4 + 1], src[cc * 4 + 2], src[cc * 4 + 3]);
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int rr = j * 8 + prow, R = rbase + rr;
+            const int yy = t.y0 + R / TW, xx = t.x0 + R % TW;
+            const uint4 u = ld_chunk(rr);
+            if (yy < p.H && xx < p.W)
+              *reinterpret_cast<uint4*>(dst + ((static_cast<size_t>(t.n) * p.H + yy) * p.out_pitch + p.out_lead + xx) * p.Cout +
+                                        co + sub * 8) = u;
+          }
+          __syncwarp();
+        }
+      }
+    } else if (pix_ok && co < co_end) {
 #pragma unroll
       for (int g8 = 0; g8 < 4; ++g8) {              // 8 output channels at a time
         const int cb = co + g8 * 8;
@@ -214,9 +309,11 @@ __global__ void __launch_bounds__(THREADS, 1) conv3x3_kernel(const __grid_consta
   uint64_t* acc_empty = acc_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
   float* bias_s = reinterpret_cast<float*>(smem + STAGES * STAGE + 256);
+  uint8_t* epi_stage = smem + STAGES * STAGE + 256 + MAX_COUT * 4;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  for (int i = tid; i < MAX_COUT; i += THREADS) bias_s[i] = (p.bias && i < p.Cout) ? __ldg(p.bias + i) : 0.f;
+  const int epi_warps = (blockDim.x >> 5) - 2;                // 8, or 4 when the launch has no room for 8 staging buffers
+  for (int i = tid; i < MAX_COUT; i += blockDim.x) bias_s[i] = (p.bias && i < p.Cout) ? __ldg(p.bias + i) : 0.f;
   const int tiles_y = (p.H + TILE_H - 1) / TILE_H, tiles_x = (p.W + TILE_W - 1) / TILE_W;
   const int cog = p.Cout / p.groups;
   const int tiles_ng = (cog + BN - 1) / BN;
@@ -231,7 +328,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv3x3_kernel(const __grid_consta
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&acc_full[s], 1);
-      mbar_init(&acc_empty[s], EPI_WARPS);
+      mbar_init(&acc_empty[s], epi_warps);
     }
     fence_barrier_init();
     tma_prefetch_desc(&maps.w_hi);
@@ -328,7 +425,9 @@ __global__ void __launch_bounds__(THREADS, 1) conv3x3_kernel(const __grid_consta
     // ------------------------------------------------------------------ epilogue
     const int q = warp & 3;                                   // TMEM lane quarter this warp may read
     constexpr int NCH = BN / 32;                              // 32-column chunks per tile, split between the two warps of a quarter
-    const int c_begin = (warp - 2) < 4 ? 0 : (NCH + 1) / 2, c_end = (warp - 2) < 4 ? (NCH + 1) / 2 : NCH;
+    const int c_split = epi_warps > 4 ? (NCH + 1) / 2 : NCH;
+    const int c_begin = (warp - 2) < 4 ? 0 : c_split, c_end = (warp - 2) < 4 ? c_split : NCH;
+    uint8_t* my_stage = epi_stage + (warp - 2) * EPI_STAGE;
     uint32_t local = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
       const int buf = local & 1;
@@ -336,7 +435,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv3x3_kernel(const __grid_consta
       mbar_wait(&acc_full[buf], (local >> 1) & 1);
       tc_fence_after_sync();
       epilogue_tile<BN, TILE_W>(p, t, tbase + (static_cast<uint32_t>(q * 32) << 16) + buf * Cfg<BN>::ACC_COLS, q * 32 + lane, cog,
-                                bias_s, c_begin, c_end);
+                                bias_s, c_begin, c_end, my_stage);
       tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[buf]);
@@ -384,9 +483,11 @@ __global__ void __launch_bounds__(THREADS, 1) conv3x3_halo_kernel(const __grid_c
   uint64_t* w_full = acc_empty + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_full + 1);
   float* bias_s = reinterpret_cast<float*>(ring + nslots * HALO_SLOT + 256);
+  uint8_t* epi_stage = ring + nslots * HALO_SLOT + 256 + MAX_COUT * 4;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  for (int i = tid; i < MAX_COUT; i += THREADS) bias_s[i] = (p.bias && i < p.Cout) ? __ldg(p.bias + i) : 0.f;
+  const int epi_warps = (blockDim.x >> 5) - 2;                // 8, or 4 when the launch has no room for 8 staging buffers
+  for (int i = tid; i < MAX_COUT; i += blockDim.x) bias_s[i] = (p.bias && i < p.Cout) ? __ldg(p.bias + i) : 0.f;
   const int tiles_y = (p.H + HTILE_H - 1) / HTILE_H, tiles_x = (p.W + HTILE_W - 1) / HTILE_W;
   const int num_tiles = p.N * tiles_y * tiles_x;
   const int pieces = 2 * p.chunks_total;                            // (chunk, hi | lo) halo pieces per tile
@@ -399,7 +500,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv3x3_halo_kernel(const __grid_c
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&acc_full[s], 1);
-      mbar_init(&acc_empty[s], EPI_WARPS);
+      mbar_init(&acc_empty[s], epi_warps);
     }
     mbar_init(w_full, 1);
     fence_barrier_init();
@@ -460,17 +561,25 @@ __global__ void __launch_bounds__(THREADS, 1) conv3x3_halo_kernel(const __grid_c
           const int chunk = pc >> 1, lo = pc & 1;
           mbar_wait(&a_full[slot], (it / nslots) & 1);
           tc_fence_after_sync();
+          // Issue loop kept as tight as possible — the layers served here are bound by the issuing thread, not by the
+          // tensor pipe (N <= 128: the pipe needs <= 64 cycles per MMA): taps fully unrolled so that the halo shift
+          // (dy*10 + dx pixels) is an immediate, one running 64-bit add per weight slot, hi / lo pieces in separate loops.
           const uint64_t da = d_a0 + ((slot * HALO_SLOT) >> 4);
-#pragma unroll 1
-          for (int tap = 0; tap < 9; ++tap) {
-            const uint64_t dat = da + (((tap / 3) * HALO_W + tap % 3) * 128 >> 4);
-            const uint64_t dw = d_w0 + (((tap * p.chunks_total + chunk) * 2 * W_TILE) >> 4);
+          uint64_t dw = d_w0 + ((chunk * 2 * W_TILE) >> 4);
+          const uint32_t wstep = static_cast<uint32_t>(p.chunks_total * 2 * W_TILE) >> 4;
+          if (lo) {
 #pragma unroll
-            for (int k = 0; k < BK / 16; ++k) {
-              if (lo)
-                umma_f16(d, dat + 2 * k, dw + 2 * k, idesc, 1);                          // + Al.Wh
-              else
-                umma_f16(d, dat + 2 * k, dw + 2 * k, idesc2, (pc | tap | k) != 0);       // [Ah.Wh | Ah.Wl]
+            for (int tap = 0; tap < 9; ++tap, dw += wstep) {
+              const uint64_t dat = da + ((((tap / 3) * HALO_W + tap % 3) * 128) >> 4);
+#pragma unroll
+              for (int k = 0; k < BK / 16; ++k) umma_f16(d, dat + 2 * k, dw + 2 * k, idesc, 1);                 // + Al.Wh
+            }
+          } else {
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap, dw += wstep) {
+              const uint64_t dat = da + ((((tap / 3) * HALO_W + tap % 3) * 128) >> 4);
+#pragma unroll
+              for (int k = 0; k < BK / 16; ++k) umma_f16(d, dat + 2 * k, dw + 2 * k, idesc2, (pc | tap | k) != 0);   // [Ah.Wh | Ah.Wl]
             }
           }
           umma_commit(&a_empty[slot]);
@@ -482,7 +591,9 @@ __global__ void __launch_bounds__(THREADS, 1) conv3x3_halo_kernel(const __grid_c
     // ------------------------------------------------------------------ epilogue
     const int q = warp & 3;                                   // TMEM lane quarter this warp may read
     constexpr int NCH = BN / 32;                              // 32-column chunks per tile, split between the two warps of a quarter
-    const int c_begin = (warp - 2) < 4 ? 0 : (NCH + 1) / 2, c_end = (warp - 2) < 4 ? (NCH + 1) / 2 : NCH;
+    const int c_split = epi_warps > 4 ? (NCH + 1) / 2 : NCH;
+    const int c_begin = (warp - 2) < 4 ? 0 : c_split, c_end = (warp - 2) < 4 ? c_split : NCH;
+    uint8_t* my_stage = epi_stage + (warp - 2) * EPI_STAGE;
     uint32_t local = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
       const int buf = local & 1;
@@ -495,7 +606,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv3x3_halo_kernel(const __grid_c
       mbar_wait(&acc_full[buf], (local >> 1) & 1);
       tc_fence_after_sync();
       epilogue_tile<BN, HTILE_W>(p, t, tbase + (static_cast<uint32_t>(q * 32) << 16) + buf * Cfg<BN>::ACC_COLS, q * 32 + lane,
-                                 p.Cout, bias_s, c_begin, c_end);
+                                 p.Cout, bias_s, c_begin, c_end, my_stage);
       tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[buf]);
@@ -638,13 +749,16 @@ int launch_conv3x3(int nsrc, const void* const* src_hi, const void* const* src_l
   // in shared memory next to >= 3 halo slots.  E2F_CONV_HALO=0 forces the generic kernel (A/B timing, debugging).
   int chunks_all = 0;
   for (int i = 0; i < nsrc; ++i) chunks_all += (src_channels[i] / groups + BK - 1) / BK;
-  int halo_slots = 0;
+  int halo_slots = 0, halo_epi = 8;
   if (!in_rows && ks == 3 && stride == 1 && pad == 1 && groups == 1 && cout <= 64) {
     static const bool enabled = [] {
       const char* e = getenv("E2F_CONV_HALO");
       return !(e && e[0] == '0');
     }();
-    const int room = SMEM_LIMIT - 1024 - 256 - MAX_COUT * 4 - halo_w_bytes(bn, chunks_all);
+    // 8 epilogue warps when their staging buffers fit next to the resident weights, else 4 (64 -> 64: 144 KB of weights)
+    const int room8 = SMEM_LIMIT - 1024 - 256 - MAX_COUT * 4 - halo_w_bytes(bn, chunks_all) - 8 * EPI_STAGE;
+    halo_epi = room8 >= 3 * HALO_SLOT ? 8 : 4;
+    const int room = room8 + (8 - halo_epi) * EPI_STAGE;
     if (enabled && room >= 3 * HALO_SLOT) halo_slots = room / HALO_SLOT < HALO_MAX_SLOTS ? room / HALO_SLOT : HALO_MAX_SLOTS;
   }
   const cuuint32_t estr4[4] = {1, static_cast<cuuint32_t>(stride), static_cast<cuuint32_t>(stride), 1};
@@ -715,11 +829,12 @@ int launch_conv3x3(int nsrc, const void* const* src_hi, const void* const* src_l
       return -2;
     }
     const int hgrid = htiles < num_sms() ? static_cast<int>(htiles) : num_sms();
-    const int hsmem = 1024 + halo_w_bytes(bn, chunks_all) + halo_slots * HALO_SLOT + 256 + MAX_COUT * 4;
+    const int hsmem = 1024 + halo_w_bytes(bn, chunks_all) + halo_slots * HALO_SLOT + 256 + MAX_COUT * 4 + halo_epi * EPI_STAGE;
+    const int hthreads = (2 + halo_epi) * 32;
     if (bn == 32)
-      conv3x3_halo_kernel<32><<<hgrid, THREADS, hsmem, stream>>>(maps, p, halo_slots);
+      conv3x3_halo_kernel<32><<<hgrid, hthreads, hsmem, stream>>>(maps, p, halo_slots);
     else
-      conv3x3_halo_kernel<64><<<hgrid, THREADS, hsmem, stream>>>(maps, p, halo_slots);
+      conv3x3_halo_kernel<64><<<hgrid, hthreads, hsmem, stream>>>(maps, p, halo_slots);
     count_launch();
     return static_cast<int>(cudaGetLastError());
   }
