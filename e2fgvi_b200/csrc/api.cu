@@ -296,6 +296,23 @@ int e2f_conv3x3_bf16x3(int nsrc, const void* const* src_hi, const void* const* s
                            cout, groups, leaky_slope, 3, 1, 1, stream);
 }
 
+int e2f_prop_prologue(const float* prop, const float* feat_n2, const float* flow_n1, int64_t flow_n1_bstride,
+                      const float* flow_prev, int64_t flow_prev_bstride, void* cond1_hi, void* cond1_lo, void* cond2_hi,
+                      void* cond2_lo, float* flow1_out, float* flow2_out, void* flows_hi, void* flows_lo, void* x_grouped,
+                      int n, int h, int w, int c, void* stream) {
+  if (!prop || !flow_n1 || !cond1_hi || !cond1_lo || !cond2_hi || !cond2_lo || !flow1_out || !flow2_out || !flows_hi ||
+      !flows_lo || !x_grouped) { set_error("e2f_prop_prologue: null pointer"); return E2F_ERR_BAD_ARG; }
+  if ((feat_n2 == nullptr) != (flow_prev == nullptr)) { set_error("e2f_prop_prologue: feat_n2 and flow_prev must both be given or both be NULL"); return E2F_ERR_BAD_ARG; }
+  if (n < 0 || h <= 0 || w <= 0 || c <= 0 || c % 16) { set_error("e2f_prop_prologue: bad shape n=%d h=%d w=%d c=%d (C must be a multiple of 16)", n, h, w, c); return E2F_ERR_BAD_ARG; }
+  if (!aligned(prop, 16) || (feat_n2 && !aligned(feat_n2, 16)) || !aligned(cond1_hi, 8) || !aligned(cond1_lo, 8) || !aligned(cond2_hi, 8) ||
+      !aligned(cond2_lo, 8) || !aligned(flow1_out, 8) || !aligned(flow2_out, 8) || !aligned(flows_hi, 16) || !aligned(flows_lo, 16) ||
+      !aligned(x_grouped, 16)) { set_error("e2f_prop_prologue: alignment"); return E2F_ERR_ALIGNMENT; }
+  return finish(launch_prop_prologue(prop, feat_n2, flow_n1, static_cast<long long>(flow_n1_bstride), flow_prev,
+                                     static_cast<long long>(flow_prev_bstride), cond1_hi, cond1_lo, cond2_hi, cond2_lo, flow1_out,
+                                     flow2_out, flows_hi, flows_lo, x_grouped, n, h, w, c, static_cast<cudaStream_t>(stream)),
+                "e2f_prop_prologue");
+}
+
 int e2f_video_prepare_clip(const uint8_t* frames, const uint8_t* masks, const int* ids, float* out, int t, int h, int w,
                            int hp, int wp, void* stream) {
   if (!frames || !masks || !ids || !out) { set_error("e2f_video_prepare_clip: null pointer"); return E2F_ERR_BAD_ARG; }

@@ -13,6 +13,10 @@ int launch_flow_warp_nhwc(const void* x, const float* flow, void* out, int n, in
 int launch_flow_warp_nchw(const float* x, const float* flow, float* out, int n, int c, int h, int w, int pad_mode,
                           cudaStream_t stream);
 
+int launch_prop_prologue(const float* prop, const float* feat2, const float* flow1, long long f1_bs, const float* flowp,
+                         long long fp_bs, void* c1h, void* c1l, void* c2h, void* c2l, float* f1_out, float* f2_out,
+                         void* flh, void* fll, void* xg, int n, int h, int w, int c, cudaStream_t stream);
+
 int launch_dcn_pack_weight(const float* w, void* w_packed, int cout, int cin, int dg, cudaStream_t stream);
 // head != nullptr selects the fused (tanh / flow / sigmoid) prologue; otherwise offset+mask are final values.
 int launch_dcn(const void* x, const float* offset, const float* mask, const float* head, const float* flow1,

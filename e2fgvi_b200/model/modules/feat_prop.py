@@ -9,6 +9,7 @@ sweep directions (feat_prop.py:94-103) and the caller passes (forward, backward)
 (flows_backward, flows_forward) (e2fgvi.py:249-250).
 """
 import math
+import os
 
 import torch
 import torch.nn as nn
@@ -59,19 +60,21 @@ class SecondOrderDeformableAlignment(nn.Module):
         nn.init.zeros_(self.conv_offset[-1].weight)
         nn.init.zeros_(self.conv_offset[-1].bias)
 
-    def offset_head(self, cond_sources, flow_1, flow_2):
+    def offset_head(self, cond_sources, flow_1, flow_2, flows=None):
         """conv_offset on cat[cond..., flow_1, flow_2] (feat_prop.py:36-37) without building the cat: each tensor is
         one TMA source of the first conv; LeakyReLU(0.1) is fused into the conv epilogues.  Returns the raw
-        27*dg-channel head, fp32, channels_last."""
+        27*dg-channel head, fp32, channels_last.  ``flows``: cat(flow_1, flow_2) already in conv-operand form (from
+        ``ops.prop_prologue``)."""
         co = self.conv_offset
-        flows = torch.cat([flow_1, flow_2], dim=1)
+        if flows is None:
+            flows = torch.cat([flow_1, flow_2], dim=1)
         y = ops.conv3x3(list(cond_sources) + [flows], co[0].weight, co[0].bias, negative_slope=0.1, out="split")
         y = ops.conv3x3([y], co[2].weight, co[2].bias, negative_slope=0.1, out="split")
         y = ops.conv3x3([y], co[4].weight, co[4].bias, negative_slope=0.1, out="split")
         return ops.conv3x3([y], co[6].weight, co[6].bias)
 
-    def align(self, x, cond_sources, flow_1, flow_2):
-        head = self.offset_head(cond_sources, flow_1, flow_2)
+    def align(self, x, cond_sources, flow_1, flow_2, flows=None):
+        head = self.offset_head(cond_sources, flow_1, flow_2, flows)
         if self.fused:
             return ops.deform_align_fused(x, head, flow_1, flow_2, self.packed_weight(), self.bias, self.deform_groups,
                                           self.max_residue_magnitude)
@@ -107,11 +110,16 @@ class BidirectionalPropagation(nn.Module):
                 nn.Conv2d((2 + i) * channel, channel, 3, 1, 1), nn.LeakyReLU(0.1, inplace=True),
                 nn.Conv2d(channel, channel, 3, 1, 1))
         self.fusion = nn.Conv2d(2 * channel, channel, 1, 1, 0)
+        # False (or E2F_PROP_FUSED=0): the operator-by-operator sequence of feat_prop.py:106-126
+        self.fused_prologue = os.environ.get("E2F_PROP_FUSED", "1") != "0"
 
     def forward(self, x, flows_backward, flows_forward):
         """x (b,t,c,h,w); flows_* (b,t-1,2,h,w) -> (b,t,c,h,w)."""
         b, t, c, h, w = x.shape
         frames = [x[:, i].contiguous(memory_format=torch.channels_last) for i in range(t)]
+        # every frame is a source of two convs per direction: split it into the bf16 operand pair once
+        frame_ops = [ops.split_nhwc(f) for f in frames]
+        fused = self.fused_prologue and c % 16 == 0
         swept = {}
         for name in self.DIRECTIONS:
             backward = name == "backward_"
@@ -121,8 +129,13 @@ class BidirectionalPropagation(nn.Module):
             prop = torch.zeros_like(frames[0])
             hist = []
             for i, idx in enumerate(order):
-                cur = frames[idx]
-                if i > 0:
+                cur = frame_ops[idx]
+                if i > 0 and fused:
+                    # one launch: both warps, the second-order flow, the operand splits and the DCN input (rank 3)
+                    xg, cond_n1, cond_n2, flows_op, flow_n1, flow_n2 = ops.prop_prologue(
+                        prop, hist[-2] if i > 1 else None, flows[:, i - 1], flows[:, i - 2] if i > 1 else None)
+                    prop = align.align(xg, [cond_n1, cur, cond_n2], flow_n1, flow_n2, flows=flows_op)
+                elif i > 0:
                     flow_n1 = flows[:, i - 1]
                     grid_n1 = flow_n1.permute(0, 2, 3, 1)
                     cond_n1 = flow_warp(prop, grid_n1)

@@ -169,6 +169,53 @@ def dcn_pack_input(a, b):
     return GroupedX(xg, (n, ca + cb, h, w))
 
 
+def prop_prologue(prop, feat_n2, flow_n1, flow_prev):
+    """Everything one propagation step does before its offset-head conv and its DCN (feat_prop.py:106-126), fused:
+
+        cond_n1 = flow_warp(prop, flow_n1);  flow_n2 = flow_n1 + flow_warp(flow_prev, flow_n1)
+        cond_n2 = flow_warp(feat_n2, flow_n2);  cat([flow_n1, flow_n2], 1);  cat([prop, feat_n2], 1)
+
+    prop, feat_n2: (n,c,h,w) fp32 channels_last (feat_n2 / flow_prev None on the second frame of a sweep: zeros);
+    flow_n1, flow_prev: (n,2,h,w) fp32 with contiguous (h,w) planes (slices ``flows[:, i]`` of the (b,t-1,2,h,w) tensor).
+    Returns ``(x, cond_n1, cond_n2, flows, flow_n1, flow_n2)``: x a ``GroupedX`` (DCN input), cond_* / flows ``SplitNHWC``
+    conv operands, flow_n1 / flow_n2 (n,2,h,w) views of NHWC buffers (what ``deform_align_fused`` reads without a copy).
+    Bit-identical to the unfused sequence of ``flow_warp`` / add / ``split_nhwc`` / ``dcn_pack_input``."""
+    _need_cuda(prop, feat_n2, flow_n1, flow_prev)
+    n, c, h, w = prop.shape
+    if (feat_n2 is None) != (flow_prev is None):
+        raise ValueError("prop_prologue: feat_n2 and flow_prev go together")
+    if c % 16:
+        raise ValueError("prop_prologue: the channel count must be a multiple of 16")
+
+    def nhwc(t):
+        return t if (t.dtype == torch.float32 and _is_cl(t)) else t.float().contiguous(memory_format=torch.channels_last)
+
+    def planes(f):
+        if f.dtype != torch.float32 or f.stride()[1:] != (h * w, w, 1):
+            f = f.float().contiguous()
+        return f
+
+    prop, flow_n1 = nhwc(prop), planes(flow_n1)
+    if feat_n2 is not None:
+        feat_n2, flow_prev = nhwc(feat_n2), planes(flow_prev)
+    dev = prop.device
+    bf = torch.bfloat16
+    c1h, c1l = torch.empty((n, h, w, c), dtype=bf, device=dev), torch.empty((n, h, w, c), dtype=bf, device=dev)
+    c2h, c2l = torch.empty((n, h, w, c), dtype=bf, device=dev), torch.empty((n, h, w, c), dtype=bf, device=dev)
+    f1 = torch.empty((n, h, w, 2), dtype=torch.float32, device=dev)
+    f2 = torch.empty((n, h, w, 2), dtype=torch.float32, device=dev)
+    flh, fll = torch.empty((n, h, w, 8), dtype=bf, device=dev), torch.empty((n, h, w, 8), dtype=bf, device=dev)
+    xg = torch.empty((n, 2 * c // 16, h, w, 16), dtype=torch.float16, device=dev)
+    st = _lib.load().e2f_prop_prologue(
+        prop.data_ptr(), None if feat_n2 is None else feat_n2.data_ptr(), flow_n1.data_ptr(), flow_n1.stride(0),
+        None if flow_prev is None else flow_prev.data_ptr(), 0 if flow_prev is None else flow_prev.stride(0),
+        c1h.data_ptr(), c1l.data_ptr(), c2h.data_ptr(), c2l.data_ptr(), f1.data_ptr(), f2.data_ptr(), flh.data_ptr(),
+        fll.data_ptr(), xg.data_ptr(), n, h, w, c, _stream())
+    _lib.check(st, "e2f_prop_prologue")
+    return (GroupedX(xg, (n, 2 * c, h, w)), SplitNHWC(c1h, c1l, (n, c, h, w)), SplitNHWC(c2h, c2l, (n, c, h, w)),
+            SplitNHWC(flh, fll, (n, 4, h, w)), f1.permute(0, 3, 1, 2), f2.permute(0, 3, 1, 2))
+
+
 def deform_align_fused(x, head, flow_1, flow_2, w_packed, bias, deform_groups, max_residue_magnitude=10.0,
                        out_dtype=torch.float32):
     """feat_prop.py:41-58 in one kernel: 10*tanh + flow.flip(1) add, sigmoid, deformable sampling, GEMM, bias.

@@ -228,6 +228,23 @@ int e2f_conv2d_rows_bf16x3(int nsrc, const void* const* src_hi, const void* cons
                            float* out, void* out_hi, void* out_lo, int out_lead, int n, int h, int w, int cout, int groups,
                            float leaky_slope, int ksize, int stride, int pad, void* stream);
 
+/* Fused prologue of one propagation step — replaces feat_prop.py:106-126 up to the offset-head conv:
+ * the two feature warps, the second-order flow (flow_n1 + warp(flow_prev, flow_n1)), the operand splits of the offset
+ * head's conv sources and the fp16 group-major DCN input, in one launch.
+ *   prop, feat_n2     [N][H][W][C] fp32 NHWC (feat_n2 may be NULL: second frame of a sweep -> cond_n2, flow_n2, the second
+ *                     half of x are zeros); C % 16 == 0
+ *   flow_n1, flow_prev  fp32 planes [2][H][W] per image (u then v), image i at + i*bstride elements (a slice of the
+ *                     [B][T-1][2][H][W] flow tensor); flow_prev NULL iff feat_n2 NULL
+ *   cond1_hi/lo, cond2_hi/lo  [N][H][W][C] bf16: (hi, lo) split of flow_warp(prop, flow_n1) / flow_warp(feat_n2, flow_n2)
+ *   flow1_out, flow2_out      [N][H][W][2] fp32: flow_n1 and flow_n2 in the layout e2f_deform_align_fused reads
+ *   flows_hi/lo       [N][H][W][8] bf16 split of cat(flow_n1, flow_n2) (4 channels + 4 zero), conv operand
+ *   x_grouped         [N][2C/16][H][W][16] fp16 = e2f_dcn_pack_input(prop, feat_n2)
+ * Bit-identical to the unfused sequence of e2f_flow_warp / e2f_flow_warp_nchw / add / e2f_split_bf16 / e2f_dcn_pack_input. */
+int e2f_prop_prologue(const float* prop, const float* feat_n2, const float* flow_n1, int64_t flow_n1_bstride,
+                      const float* flow_prev, int64_t flow_prev_bstride, void* cond1_hi, void* cond1_lo, void* cond2_hi,
+                      void* cond2_lo, float* flow1_out, float* flow2_out, void* flows_hi, void* flows_lo, void* x_grouped,
+                      int n, int h, int w, int c, void* stream);
+
 /* Video-level driver — replaces the per-window host / eager-torch code of test.py:132-179.
  * All buffers are device memory; `frames` [N][H][W][3] uint8 RGB, `masks` [N][H][W] uint8 (non-zero = hole, already
  * dilated like test.py:55-68), `ids` int32 frame indices of the window (neighbours first, then reference frames).

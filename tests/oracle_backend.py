@@ -65,6 +65,18 @@ def _dcn_pack_input(a, b):
     return torch.cat([a, b], 1)
 
 
+def _prop_prologue(prop, feat_n2, flow_n1, flow_prev):
+    """feat_prop.py:106-126 operator by operator (the sequence ops.prop_prologue fuses)."""
+    grid_n1 = flow_n1.permute(0, 2, 3, 1)
+    cond_n1 = _flow_warp(prop, grid_n1)
+    if feat_n2 is not None:
+        flow_n2 = flow_n1 + _flow_warp(flow_prev, grid_n1)
+        cond_n2 = _flow_warp(feat_n2, flow_n2.permute(0, 2, 3, 1))
+    else:
+        feat_n2, flow_n2, cond_n2 = torch.zeros_like(prop), torch.zeros_like(flow_n1), torch.zeros_like(cond_n1)
+    return torch.cat([prop, feat_n2], 1), cond_n1, cond_n2, torch.cat([flow_n1, flow_n2], 1), flow_n1, flow_n2
+
+
 def _upsample(x):
     return torch.nn.functional.interpolate(x, scale_factor=2, mode="bilinear", align_corners=True)
 
@@ -115,12 +127,14 @@ def oracle_ops():
     saved = {n: getattr(ops, n) for n in ("flow_warp", "pack_dcn_weight", "deform_align_fused",
                                           "modulated_deform_conv2d", "focal_window_attention", "t2t_unfold",
                                           "t2t_fold", "linear", "conv3x3", "split_nhwc", "upsample2x_split",
-                                          "layer_norm", "dcn_pack_input", "t2t_fold_unfold", "pack_rows", "window_pool")}
+                                          "layer_norm", "dcn_pack_input", "t2t_fold_unfold", "pack_rows", "window_pool",
+                                          "prop_prologue")}
     ops.flow_warp, ops.pack_dcn_weight, ops.deform_align_fused = _flow_warp, _pack, _fused
     ops.modulated_deform_conv2d, ops.focal_window_attention = _mdcn, _attention
     ops.t2t_unfold, ops.t2t_fold, ops.linear, ops.t2t_fold_unfold = _unfold, _fold, _linear, _fold_unfold
     ops.conv3x3, ops.split_nhwc, ops.pack_rows, ops.window_pool = _conv3x3, _split_nhwc, _pack_rows, _window_pool
     ops.upsample2x_split, ops.layer_norm, ops.dcn_pack_input = _upsample, _layer_norm, _dcn_pack_input
+    ops.prop_prologue = _prop_prologue
     try:
         yield
     finally:

@@ -561,3 +561,34 @@ def test_window_pool(cuda, shape):
     with pytest.raises(ValueError):
         ops.window_pool(ops.SplitMat(hi.view(B, T, H, W, C)[:, :, :-1], lo.view(B, T, H, W, C)[:, :, :-1]),
                         lin.weight.to(cuda), lin.bias.to(cuda), (wh, ww))
+
+
+# ------------------------------------------------------------------------------------------ fused propagation prologue
+@pytest.mark.parametrize("second_order", [True, False])
+def test_prop_prologue_matches_unfused_sequence(cuda, second_order):
+    """ops.prop_prologue == flow_warp x3 + add + split_nhwc + dcn_pack_input (feat_prop.py:106-126), bit for bit."""
+    g = torch.Generator().manual_seed(81)
+    b, t, c, h, w = 2, 4, 128, 13, 22
+    flows = (torch.randn(b, t - 1, 2, h, w, generator=g) * 3).to(cuda)
+    prop = torch.randn(b, c, h, w, generator=g).to(cuda).contiguous(memory_format=torch.channels_last)
+    feat2 = torch.randn(b, c, h, w, generator=g).to(cuda).contiguous(memory_format=torch.channels_last)
+    flow_n1 = flows[:, 1]
+    flow_prev = flows[:, 0] if second_order else None
+    xg, c1, c2, fl, f1, f2 = ops.prop_prologue(prop, feat2 if second_order else None, flow_n1, flow_prev)
+    grid = flow_n1.permute(0, 2, 3, 1)
+    want_c1 = ops.split_nhwc(ops.flow_warp(prop, grid))
+    if second_order:
+        want_f2 = flow_n1 + ops.flow_warp(flows[:, 0], grid)
+        want_c2 = ops.split_nhwc(ops.flow_warp(feat2, want_f2.permute(0, 2, 3, 1)))
+        want_x = ops.dcn_pack_input(prop, feat2)
+    else:
+        want_f2 = torch.zeros_like(flow_n1)
+        want_c2 = ops.split_nhwc(torch.zeros_like(prop))
+        want_x = ops.dcn_pack_input(prop, torch.zeros_like(prop))
+    want_fl = ops.split_nhwc(torch.cat([flow_n1, want_f2], 1))
+    assert torch.equal(f1, flow_n1) and torch.equal(f2, want_f2)
+    for got, want in ((c1, want_c1), (c2, want_c2), (fl, want_fl)):
+        assert got.shape == want.shape
+        assert torch.equal(got.hi, want.hi) and torch.equal(got.lo, want.lo)
+    assert torch.equal(xg.data, want_x.data) and xg.shape == want_x.shape
+    assert f1.permute(0, 2, 3, 1).is_contiguous() and f2.permute(0, 2, 3, 1).is_contiguous()
