@@ -38,6 +38,21 @@ def test_argument_errors_without_gpu(lib):
     assert b"specialised" in lib.e2f_last_error()
 
 
+def test_argument_errors_new_entry_points(lib):
+    """Video-driver and propagation-prologue entry points validate before any CUDA call."""
+    assert lib.e2f_video_prepare_clip(None, 16, 16, 16, 2, 8, 8, 60, 108, None) == -1
+    assert lib.e2f_video_prepare_clip(16, 16, 16, 16, 2, 100, 200, 240, 216, None) == -1      # hp > 2h: not a mirror pad
+    assert b"mirror" in lib.e2f_last_error()
+    assert lib.e2f_video_compose(16, 16, 16, 16, None, 1, 8, 8, 60, 108, None) == -1
+    assert lib.e2f_video_blend(16, 16, 16, 16, 1, 0, None) == -1
+    assert lib.e2f_video_finalize(16, None, 10, None) == -1
+    args = [16, 16, 16, 0, 16, 0] + [16] * 9
+    assert lib.e2f_prop_prologue(*args, 1, 4, 4, 24, None) == -1                             # C % 16
+    assert lib.e2f_prop_prologue(16, None, 16, 0, 16, 0, *[16] * 9, 1, 4, 4, 32, None) == -1   # feat_n2 without flow_prev
+    assert b"both" in lib.e2f_last_error()
+    assert lib.e2f_prop_prologue(8, 16, 16, 0, 16, 0, *[16] * 9, 1, 4, 4, 32, None) == -3      # misaligned prop
+
+
 def test_no_cpu_fallback():
     import torch
     from e2fgvi_b200 import ops
