@@ -281,7 +281,7 @@ def main():
                 vf_t, vm_t = torch.from_numpy(vf).pin_memory(), torch.from_numpy(vm).pin_memory()
                 drv = VideoInpainter(model, clips_per_call=4)
                 drv(vf_t, vm_t)
-                sync()
+                torch.cuda.synchronize()          # rank-0-only section: no collective (sync() holds a barrier)
                 v0, v1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 v0.record()
                 comp = drv(vf_t, vm_t).cpu()
