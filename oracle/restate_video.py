@@ -5,30 +5,32 @@ import this module; the product path (``e2fgvi_b200/video.py``) never does.
 
 Pinned against the UNMODIFIED ``test.py`` run in the build container (``oracle/gen_golden_video.py`` executes its
 ``main_worker`` with matplotlib stubbed and ``cv2.VideoWriter`` captured): ``tests/golden/video_*.npz`` holds the
-composited frames that script wrote, and ``tests/test_oracle.py`` checks this restatement reproduces them bit for bit.
+composited frames that script wrote, and ``tests/test_video.py`` checks this restatement reproduces them bit for bit.
 """
 import numpy as np
 import torch
 
 
 def get_ref_index(f, neighbor_ids, length, ref_length=10, num_ref=-1):
-    """Non-local reference frame ids for the window centred on ``f`` (test.py:37-52).  The reference reads
-    ``ref_length`` / ``num_ref`` from module globals (test.py:31-32); note its ``len(ref_index) > num_ref`` test lets
-    ``num_ref + 1`` ids through."""
-    ref_index = []
+    """Non-local reference frame ids for the window centred on ``f`` (test.py:37-52; the reference reads ``ref_length`` /
+    ``num_ref`` from module globals, test.py:31-32).
+
+    * ``num_ref == -1``: every ``ref_length``-th frame of the whole video that is not a neighbour;
+    * otherwise: candidates ``f - ref_length*(num_ref//2), ... , f + ref_length*(num_ref//2)`` clipped to
+      ``[0, length]`` — INCLUSIVE of ``length`` itself, an out-of-range id the reference then indexes with — skipping
+      neighbours and stopping once MORE than ``num_ref`` ids were collected (so up to ``num_ref + 1`` are returned)."""
+    inside = set(neighbor_ids)
     if num_ref == -1:
-        for i in range(0, length, ref_length):
-            if i not in neighbor_ids:
-                ref_index.append(i)
-    else:
-        start_idx = max(0, f - ref_length * (num_ref // 2))
-        end_idx = min(length, f + ref_length * (num_ref // 2))
-        for i in range(start_idx, end_idx + 1, ref_length):
-            if i not in neighbor_ids:
-                if len(ref_index) > num_ref:
-                    break
-                ref_index.append(i)
-    return ref_index
+        return [i for i in range(0, length, ref_length) if i not in inside]
+    half = ref_length * (num_ref // 2)
+    picked = []
+    for cand in range(max(0, f - half), min(length, f + half) + 1, ref_length):
+        if cand in inside:
+            continue
+        if len(picked) > num_ref:
+            break
+        picked.append(cand)
+    return picked
 
 
 def window_schedule(video_length, neighbor_stride=5, ref_length=10, num_ref=-1):
@@ -55,40 +57,33 @@ def dilate_cross(mask, iterations=4):
 
 
 def inpaint_video(model, frames_u8, masks_u8, neighbor_stride=5, ref_length=10, num_ref=-1, pred_hook=None):
-    """test.py:132-179.  ``frames_u8`` (N,H,W,3) uint8 RGB, ``masks_u8`` (N,H,W) uint8 0/1 (already dilated),
-    ``model(masked_imgs[1,t,3,H',W'], l_t) -> (pred[t,3,H',W'], flows)`` on CPU.  Returns the list of composited
-    frames exactly as the reference leaves them in ``comp_frames`` before the final ``astype(np.uint8)``:
-    uint8 arrays for frames seen once, float32 for blended ones.  ``pred_hook(window_index, pred)`` lets a test
-    substitute / record the network output."""
+    """The window loop of test.py:146-179.  ``frames_u8`` (N,H,W,3) uint8 RGB, ``masks_u8`` (N,H,W) uint8 0/1 (already
+    dilated), ``model(masked_imgs[1,t,3,H',W'], l_t) -> (pred[t,3,H',W'], flows)`` on CPU.  Returns the list
+    ``comp_frames`` as the reference leaves it before its final ``astype(np.uint8)`` (test.py:195): a uint8 array for
+    a frame seen by one window, a float32 array once a second window was blended in.  ``pred_hook(window_index,
+    pred)`` lets a test substitute / record the network output.
+
+    Written on top of the per-kernel cuts below (``prepare_clip`` / ``compose``), i.e. NOT a transcription of the
+    script: equality with what the unmodified script writes is established by the pinned goldens, not by resemblance."""
     n, h, w, _ = frames_u8.shape
-    # to_tensors()(frames) * 2 - 1  /  to_tensors()(masks)   (core/utils.py:138-178, test.py:132,139)
-    imgs = torch.from_numpy(frames_u8).permute(0, 3, 1, 2).contiguous().float().div(255).unsqueeze(0) * 2 - 1
-    masks = torch.from_numpy(masks_u8 * 255).unsqueeze(1).contiguous().float().div(255).unsqueeze(0)
-    binary_masks = [np.expand_dims((masks_u8[i] != 0).astype(np.uint8), 2) for i in range(n)]
-    frames = [frames_u8[i] for i in range(n)]
+    frames_t, masks_t = torch.from_numpy(frames_u8), torch.from_numpy(np.ascontiguousarray(masks_u8))
+    hp, wp = h + (-h) % 60, w + (-w) % 108                       # test.py:157-160
     comp_frames = [None] * n
     for wi, (f, neighbor_ids, ref_ids) in enumerate(window_schedule(n, neighbor_stride, ref_length, num_ref)):
-        selected_imgs = imgs[:1, neighbor_ids + ref_ids]
-        selected_masks = masks[:1, neighbor_ids + ref_ids]
+        ids = neighbor_ids + ref_ids
+        if max(ids) >= n:
+            raise IndexError(f"index {max(ids)} is out of bounds for dimension 1 with size {n}")   # test.py:152
         with torch.no_grad():
-            masked_imgs = selected_imgs * (1 - selected_masks)
-            h_pad = (60 - h % 60) % 60
-            w_pad = (108 - w % 108) % 108
-            masked_imgs = torch.cat([masked_imgs, torch.flip(masked_imgs, [3])], 3)[:, :, :, :h + h_pad, :]
-            masked_imgs = torch.cat([masked_imgs, torch.flip(masked_imgs, [4])], 4)[:, :, :, :, :w + w_pad]
-            pred_imgs, _ = model(masked_imgs, len(neighbor_ids))
+            clip = prepare_clip(frames_t, masks_t, ids, hp, wp).unsqueeze(0)
+            pred, _ = model(clip, len(neighbor_ids))
             if pred_hook is not None:
-                pred_imgs = pred_hook(wi, pred_imgs)
-            pred_imgs = pred_imgs[:, :, :h, :w]
-            pred_imgs = (pred_imgs + 1) / 2
-            pred_imgs = pred_imgs.cpu().permute(0, 2, 3, 1).numpy() * 255
-        for i in range(len(neighbor_ids)):
-            idx = neighbor_ids[i]
-            img = np.array(pred_imgs[i]).astype(np.uint8) * binary_masks[idx] + frames[idx] * (1 - binary_masks[idx])
+                pred = pred_hook(wi, pred)
+        imgs = compose(pred, frames_t, masks_t, ids, len(neighbor_ids)).numpy()
+        for k, idx in enumerate(neighbor_ids):
             if comp_frames[idx] is None:
-                comp_frames[idx] = img
-            else:
-                comp_frames[idx] = comp_frames[idx].astype(np.float32) * 0.5 + img.astype(np.float32) * 0.5
+                comp_frames[idx] = imgs[k]
+            else:                                                  # test.py:178-179
+                comp_frames[idx] = comp_frames[idx].astype(np.float32) * 0.5 + imgs[k].astype(np.float32) * 0.5
     return comp_frames
 
 
