@@ -1,5 +1,6 @@
 // extern "C" boundary of libe2fgvi_b200.so (declared in include/e2fgvi_b200.h): argument validation, error
-// strings, launch accounting.  No torch types, no allocation, no global device state.
+// strings, launch accounting.  No torch types, no allocation; the only process-wide state is per-device-ordinal caches
+// of immutable facts (SM count, "function attributes already set on device d", cluster occupancy; launch.h DeviceOnce).
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
@@ -14,6 +15,18 @@ static thread_local char g_err[512] = {0};
 static std::atomic<long long> g_launches{0};
 
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+int num_sms() {
+  static std::atomic<int> cache[64];
+  const int dev = current_device();
+  int v = (dev >= 0 && dev < 64) ? cache[dev].load(std::memory_order_relaxed) : 0;
+  if (!v) {
+    v = 148;
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    if (dev >= 0 && dev < 64) cache[dev].store(v, std::memory_order_relaxed);
+  }
+  return v;
+}
 
 void set_error(const char* fmt, ...) {
   va_list ap;

@@ -631,15 +631,6 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 
-static int num_sms() {
-  static int n = [] {
-    int dev = 0, v = 148;
-    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
-    return v;
-  }();
-  return n;
-}
-
 // NCHW fp32 (C <= cin channels) -> row-gapped NHWC bf16 (hi, lo) [N][H][lead + W][cin] + tail, zeros in the gaps, the
 // tail and channels >= C: the operand layout of the window-packed conv.  One thread per (row pixel incl. gap, n*H+y).
 __global__ void __launch_bounds__(256) pack_rows_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ hi,
@@ -803,24 +794,24 @@ int launch_conv3x3(int nsrc, const void* const* src_hi, const void* const* src_l
       }
     }
   }
-  static bool configured = false;
-  if (!configured) {
+  static DeviceOnce configured, halo_configured;
+  const int dev = current_device();
+  if (!device_done(configured, dev)) {
     cudaError_t e = cudaFuncSetAttribute(conv3x3_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<128>::SMEM);
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(conv3x3_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<64>::SMEM);
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(conv3x3_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<32>::SMEM);
     if (e != cudaSuccess) return static_cast<int>(e);
-    configured = true;
+    device_mark(configured, dev);
   }
   if (halo_slots) {
-    static bool halo_configured = false;
-    if (!halo_configured) {
+    if (!device_done(halo_configured, dev)) {
       cudaError_t e = cudaFuncSetAttribute(conv3x3_halo_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
       if (e == cudaSuccess)
         e = cudaFuncSetAttribute(conv3x3_halo_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
       if (e != cudaSuccess) return static_cast<int>(e);
-      halo_configured = true;
+      device_mark(halo_configured, dev);
     }
     const long long htiles = static_cast<long long>(n) * ((h + HTILE_H - 1) / HTILE_H) * ((w + HTILE_W - 1) / HTILE_W);
     if (htiles == 0) return 0;

@@ -290,11 +290,12 @@ static int launch_variant(const CUtensorMap& tmap, const void* x, const float* o
                           const float* head, const float* flow1, const float* flow2, const float* bias, void* out,
                           int M, int h, int w, float max_res, cudaStream_t stream) {
   auto kern = dcn_kernel<FUSED, GROUPED, OutT>;
-  static bool configured = false;
-  if (!configured) {
+  static DeviceOnce configured;                    // one per template instantiation, one bit per device
+  const int dev = current_device();
+  if (!device_done(configured, dev)) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     if (e != cudaSuccess) return static_cast<int>(e);
-    configured = true;
+    device_mark(configured, dev);
   }
   const unsigned blocks = static_cast<unsigned>((M + BLOCK_M - 1) / BLOCK_M);
   kern<<<blocks, THREADS, SMEM_BYTES, stream>>>(tmap, static_cast<const __half*>(x), offset, mask, head,

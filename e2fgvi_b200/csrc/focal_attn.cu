@@ -78,8 +78,10 @@ struct Params {
   int nWh, nWw;
   int use_pooled;
   float scale_log2;               // scale * log2(e)
+#ifdef E2F_ATTN_DEVTOOLS          // developer builds only (-DE2F_ATTN_DEVTOOLS): never compiled into the shipped library
   int debug;                      // perf-experiment bits (E2F_ATTN_DEBUG): 1 skip softmax math, 2 skip gathers, 4 skip MMAs
   long long* trace;               // optional [3 roles][64 events] clock64 stamps of CTA (0,0,0) (E2F_ATTN_TRACE)
+#endif
   int n1, n2;                     // expanded-window positions listed once / more than once by the reference
   uint8_t ring_pos[MAX_RING];     // positions (er*EW + ec): the n1 single ones first, then the n2 multiple ones
   uint8_t ring_mult[MAX_RING];    // multiplicity of each entry
@@ -203,11 +205,19 @@ __global__ void __launch_bounds__(THREADS, CTAS_PER_SM) focal_attn_kernel(const 
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + Smem::TMEM_SLOT);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // The ablation bits and the clock64 trace of round 1 exist only in developer builds: in the shipped library `dbg` is
+  // the compile-time constant 0 and stamp() is empty, so no environment variable can alter the result.
+#ifdef E2F_ATTN_DEVTOOLS
+  const int dbg = prm.debug;
   const bool tracing = prm.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
   int tr_n = 0;
   auto stamp = [&](int role) {     // role 0 softmax (warp 0 lane 0), 1 loader (warp 4 lane 0), 2 MMA thread
     if (tracing && tr_n < 64) prm.trace[role * 64 + tr_n++] = clock64();
   };
+#else
+  constexpr int dbg = 0;
+  auto stamp = [](int) {};
+#endif
 
   // ---- problem geometry (uniform per CTA)
   const int area = prm.wh * prm.ww;
@@ -274,7 +284,7 @@ __global__ void __launch_bounds__(THREADS, CTAS_PER_SM) focal_attn_kernel(const 
       const uint32_t s_addr = lane_addr + COL_S + sb * BN;
       const float4* bias4 = reinterpret_cast<const float4*>(key_bias + stage * BN);
       float mx = -INFINITY;
-      if (prm.debug & 1) {
+      if (dbg & 1) {
         mx = 0.f;
       } else {
 #pragma unroll 1
@@ -285,7 +295,7 @@ __global__ void __launch_bounds__(THREADS, CTAS_PER_SM) focal_attn_kernel(const 
           mx = fmaxf(mx, biased ? max_chunk<MODE_BIASED>(sv, bias4 + c * 8, sc) : max_chunk<MODE_FAST>(sv, bias4, sc));
         }
       }
-      if (tid == 0 && kt < 10 && (prm.debug & 8)) stamp(0);   // (fine trace) max done
+      if (tid == 0 && kt < 10 && (dbg & 8)) stamp(0);   // (fine trace) max done
       // lazy rescale: only move the reference max when it grew by more than 2^8
       float alpha = 1.0f;
       bool need = false;
@@ -297,7 +307,7 @@ __global__ void __launch_bounds__(THREADS, CTAS_PER_SM) focal_attn_kernel(const 
         need = true;
       }
       const bool any_need = __any_sync(0xffffffffu, need);
-      if (tid == 0 && kt < 10 && (prm.debug & 8)) stamp(0);   // (fine trace) rescale decided
+      if (tid == 0 && kt < 10 && (dbg & 8)) stamp(0);   // (fine trace) rescale decided
       if (any_need) {
         l *= alpha;
         if (kt > 0) {                      // O holds PV(0..kt-1): wait for PV(kt-1), then scale the row in TMEM
@@ -326,7 +336,7 @@ __global__ void __launch_bounds__(THREADS, CTAS_PER_SM) focal_attn_kernel(const 
         tmem_ld32(s_addr + c * 32, sv);
         tmem_ld_wait();
         uint32_t pk[16];
-        if (prm.debug & 1) softmax_chunk<MODE_NOEXP>(sv, bias4, sc, neg_m, pk, l0, l1, l2, l3);
+        if (dbg & 1) softmax_chunk<MODE_NOEXP>(sv, bias4, sc, neg_m, pk, l0, l1, l2, l3);
         else if (biased) softmax_chunk<MODE_BIASED>(sv, bias4 + c * 8, sc, neg_m, pk, l0, l1, l2, l3);
         else softmax_chunk<MODE_FAST>(sv, bias4, sc, neg_m, pk, l0, l1, l2, l3);
         tmem_st16(s_addr + c * 16, pk);
@@ -483,7 +493,7 @@ __global__ void __launch_bounds__(THREADS, CTAS_PER_SM) focal_attn_kernel(const 
         key_bias[stage * BN + lt] = bias;
       }
       loader_barrier();
-      if (!(prm.debug & 2) || kt < KV_STAGES) {
+      if (!(dbg & 2) || kt < KV_STAGES) {
         gather_rows<BN>(smem_u32(smem + Smem::K + stage * KTILE), key_ptr + stage * BN, lwarp, lane, 0);
         cp_async_commit();
         gather_rows<BN>(smem_u32(smem + Smem::V + stage * KTILE), key_ptr + stage * BN, lwarp, lane, prm.C);
@@ -508,7 +518,7 @@ __global__ void __launch_bounds__(THREADS, CTAS_PER_SM) focal_attn_kernel(const 
       const uint32_t idesc_o = umma_idesc_f16(BM, HD, 0, 1);   // O = P V: P from TMEM, V MN-major (d contiguous per key)
       const uint32_t sQ = smem_u32(smem + Smem::Q), sK = smem_u32(smem + Smem::K);
       const uint32_t sV = smem_u32(smem + Smem::V);
-      const bool run_mma = !(prm.debug & 4);
+      const bool run_mma = !(dbg & 4);
       // descriptors hoisted out of the issue loops (one 64-bit add per K step instead of ~40 integer instructions)
       const uint64_t dq0 = umma_desc_sw128(sQ, 16, 1024), dq1 = umma_desc_adv(dq0, QATOM);
       const uint64_t dk0 = umma_desc_sw128(sK, 16, 1024);
@@ -598,12 +608,14 @@ int launch_focal_attention(const void* qkv, const void* qkv_pooled, void* out, i
   prm.nWh = h / wh; prm.nWw = w / ww;
   prm.use_pooled = use_pooled;
   prm.scale_log2 = scale * LOG2E;
+#ifdef E2F_ATTN_DEVTOOLS
   {
     const char* dbg = getenv("E2F_ATTN_DEBUG");
     prm.debug = dbg ? atoi(dbg) : 0;
     const char* tr = getenv("E2F_ATTN_TRACE");      // hex device address of a [3][64] int64 buffer (perf experiments)
     prm.trace = tr ? reinterpret_cast<long long*>(strtoull(tr, nullptr, 16)) : nullptr;
   }
+#endif
   // order the expanded-window positions: single-listed first, multiply-listed last (positions never listed are dropped)
   prm.n1 = prm.n2 = 0;
   for (int pass = 0; pass < 2; ++pass)
@@ -624,33 +636,24 @@ int launch_focal_attention(const void* qkv, const void* qkv_pooled, void* out, i
   const dim3 grid((t * wh * ww + BM - 1) / BM, heads, static_cast<unsigned>(nwin));
   cudaError_t e;
   prm.out_lo = nullptr;
+  static DeviceOnce cfg;
+  const int dev = current_device();
+  if (!device_done(cfg, dev)) {
+    e = cudaFuncSetAttribute(focal_attn_kernel<SplitBf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(focal_attn_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(focal_attn_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    cudaFuncSetAttribute(focal_attn_kernel<SplitBf16>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    cudaFuncSetAttribute(focal_attn_kernel<__half>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    cudaFuncSetAttribute(focal_attn_kernel<float>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    device_mark(cfg, dev);
+  }
   if (out_dtype == 2) {
     prm.out_lo = static_cast<__nv_bfloat16*>(prm.out) + static_cast<size_t>(b) * t * h * w * prm.C;
-    static bool cfg = false;
-    if (!cfg) {
-      e = cudaFuncSetAttribute(focal_attn_kernel<SplitBf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-      if (e != cudaSuccess) return static_cast<int>(e);
-      cudaFuncSetAttribute(focal_attn_kernel<SplitBf16>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-      cfg = true;
-    }
     focal_attn_kernel<SplitBf16><<<grid, THREADS, SMEM_BYTES, stream>>>(prm);
   } else if (out_dtype == 1) {
-    static bool cfg = false;
-    if (!cfg) {
-      e = cudaFuncSetAttribute(focal_attn_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-      if (e != cudaSuccess) return static_cast<int>(e);
-      cudaFuncSetAttribute(focal_attn_kernel<__half>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-      cfg = true;
-    }
     focal_attn_kernel<__half><<<grid, THREADS, SMEM_BYTES, stream>>>(prm);
   } else {
-    static bool cfg = false;
-    if (!cfg) {
-      e = cudaFuncSetAttribute(focal_attn_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-      if (e != cudaSuccess) return static_cast<int>(e);
-      cudaFuncSetAttribute(focal_attn_kernel<float>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-      cfg = true;
-    }
     focal_attn_kernel<float><<<grid, THREADS, SMEM_BYTES, stream>>>(prm);
   }
   count_launch();

@@ -298,15 +298,6 @@ static int make_map(CUtensorMap* tm, const void* base, int rows, int k, int box_
   return 0;
 }
 
-static int num_sms() {
-  static int n = [] {
-    int dev = 0, v = 148;
-    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
-    return v;
-  }();
-  return n;
-}
-
 template <int BN, typename OutT, int CL>
 static int launch_variant(const void* ah, const void* al, const void* wh, const void* wl, const float* bias,
                           const float* residual, void* out, int m, int n, int k, cudaStream_t stream) {
@@ -317,7 +308,10 @@ static int launch_variant(const void* ah, const void* al, const void* wh, const 
   if ((st = make_map(&twh, wh, n, k, BN / CL))) return st;
   if ((st = make_map(&twl, wl, n, k, BN / CL))) return st;
   auto kern = linear_kernel<BN, OutT, CL>;
-  static int max_ctas = 0;                         // co-resident CTAs (1 per SM; for clusters: CL * active clusters)
+  // co-resident CTAs (1 per SM; for clusters: CL * active clusters), per device ordinal (0 = not configured yet)
+  static std::atomic<int> max_ctas_dev[64];
+  const int dev = current_device();
+  int max_ctas = (dev >= 0 && dev < 64) ? max_ctas_dev[dev].load(std::memory_order_acquire) : 0;
   if (!max_ctas) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM);
     if (e != cudaSuccess) return static_cast<int>(e);
@@ -343,6 +337,7 @@ static int launch_variant(const void* ah, const void* al, const void* wh, const 
       }
       max_ctas = clusters * CL;
     }
+    if (dev >= 0 && dev < 64) max_ctas_dev[dev].store(max_ctas, std::memory_order_release);
   }
   const int tiles_m = (m + BM - 1) / BM, tiles_n = (n + BN - 1) / BN;
   const int items = ((tiles_m + CL - 1) / CL) * tiles_n;

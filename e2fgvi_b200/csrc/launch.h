@@ -1,9 +1,30 @@
 // Internal host-side launcher declarations shared by api.cu and the kernel translation units.
 #pragma once
 #include <cuda_runtime.h>
+#include <atomic>
 #include <cstdint>
 
 namespace e2f {
+
+// Function attributes (opt-in dynamic shared memory), SM counts and cluster occupancy are PER DEVICE: a process that
+// drives several GPUs (model moved to cuda:1, one thread per device) must configure each of them.  One bit per device
+// ordinal; devices >= 64 are simply configured on every call.  Setting an attribute twice is idempotent, so two threads
+// racing on the same bit are harmless.
+struct DeviceOnce {
+  std::atomic<unsigned long long> done{0};
+};
+inline int current_device() {
+  int d = 0;
+  cudaGetDevice(&d);
+  return d;
+}
+inline bool device_done(const DeviceOnce& o, int dev) {
+  return dev >= 0 && dev < 64 && ((o.done.load(std::memory_order_acquire) >> dev) & 1ull);
+}
+inline void device_mark(DeviceOnce& o, int dev) {
+  if (dev >= 0 && dev < 64) o.done.fetch_or(1ull << dev, std::memory_order_release);
+}
+int num_sms();                             // api.cu: SM count of the CURRENT device (cached per device ordinal)
 
 void count_launch();                       // api.cu: atomic launch counter behind e2f_launch_count()
 void set_error(const char* fmt, ...);      // api.cu: thread-local message behind e2f_last_error()

@@ -389,13 +389,14 @@ int launch_t2t_unfold(const float* img, float* tok, void* tok_hi_v, void* tok_lo
   const bool fast = (k == 7 && s == 3 && p == 3);
   const int smem2 = U2_CC * 7 * (w + 6) * 4;
   if (fast && c % U2_CC == 0 && smem2 <= 200 * 1024 && fh <= 65535 && bt <= 65535) {
-    static bool cfg = false;
-    if (!cfg) {
+    static DeviceOnce cfg;
+    const int dev = current_device();
+    if (!device_done(cfg, dev)) {
       cudaFuncSetAttribute(t2t_unfold733_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
       cudaFuncSetAttribute(t2t_unfold733_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
       cudaFuncSetAttribute(t2t_unfold733_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
       cudaFuncSetAttribute(t2t_unfold733_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-      cfg = true;
+      device_mark(cfg, dev);
     }
     const dim3 grid(c / U2_CC, fh, bt);
     if (gelu && nhwc)
@@ -441,13 +442,14 @@ static int fold733_band(int w, int fh, int extra_rows, size_t* smem, int CC = 4)
 }
 
 static void fold733_configure() {
-  static bool cfg = false;
-  if (cfg) return;
+  static DeviceOnce cfg;
+  const int dev = current_device();
+  if (device_done(cfg, dev)) return;
   cudaFuncSetAttribute(t2t_fold733_kernel<true, true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   cudaFuncSetAttribute(t2t_fold733_kernel<true, false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   cudaFuncSetAttribute(t2t_fold733_kernel<false, false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   cudaFuncSetAttribute(t2t_fold733_kernel<false, false, 8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-  cfg = true;
+  device_mark(cfg, dev);
 }
 
 // Fused fold/normalise/unfold(/GELU).  Returns -2 (unsupported) when the geometry is not 7/3/3 or no band fits in

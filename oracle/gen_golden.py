@@ -21,32 +21,45 @@ from oracle.reference_loader import import_reference, reference_generator  # noq
 
 OUT = os.path.join(ROOT, "tests", "golden")
 
-# name -> (hq, H, W, T, l_t, family, weight seed, frame seed)
+# name -> (hq, H, W, T, l_t, family, weight seed, frame seed[, clips b, pixel subsample stride])
 E2E_CASES = {
     "e2e_base_stress": (False, 240, 432, 8, 5, "stress", 0, 3),
     "e2e_base_default": (False, 240, 432, 8, 5, "default", 0, 3),
     "e2e_hq_tiny_stress": (True, 120, 216, 4, 3, "stress", 0, 5),
     "e2e_hq_small_stress": (True, 180, 324, 5, 3, "stress", 1, 6),
+    # round 2: the shapes bench.py measures (BASELINE configs[2], [3] per-GPU share, [4]) and a mid-size 10+6 case.
+    # Subsample strides are coprime with the 12-pixel token pitch and the 60x108-pixel attention window so that every
+    # phase of the fold / window geometry is sampled.
+    "e2e_base_b8_stress": (False, 240, 432, 8, 5, "stress", 0, 11, 8, 5),
+    "e2e_hq720_stress": (True, 720, 1296, 8, 5, "stress", 2, 7, 1, 7),
+    "e2e_hq360_t16_stress": (True, 360, 648, 16, 10, "stress", 3, 8, 1, 5),
+    "e2e_hq1080_t16_stress": (True, 1080, 1944, 16, 10, "stress", 4, 9, 1, 11),
 }
 
 
-def gen_e2e():
-    for name, (hq, H, W, T, lt, family, wseed, fseed) in E2E_CASES.items():
+def gen_e2e(only=None):
+    import time
+    for name, case in E2E_CASES.items():
+        if only and name not in only:
+            continue
+        hq, H, W, T, lt, family, wseed, fseed = case[:8]
+        b = case[8] if len(case) > 8 else 1
+        t0 = time.time()
         ref = reference_generator(hq)
         mine = importlib.import_module("e2fgvi_b200.model." + ("e2fgvi_hq" if hq else "e2fgvi")).InpaintGenerator()
         sd = synth_state_dict(mine, family, wseed)
         ref.load_state_dict(sd, strict=True)
-        x = synth_frames(1, T, H, W, seed=fseed)
+        x = synth_frames(b, T, H, W, seed=fseed)
         with torch.no_grad():
             pred, (ff, fb) = ref(x, lt)
         # full-size cases keep every 2nd pixel (exact fp32 values) + whole-tensor statistics to stay small in git
-        sub = 2 if H * W > 100000 else 1
-        torch.save({"case": dict(hq=hq, H=H, W=W, T=T, l_t=lt, family=family, weight_seed=wseed, frame_seed=fseed),
+        sub = case[9] if len(case) > 9 else (2 if H * W > 100000 else 1)
+        torch.save({"case": dict(hq=hq, H=H, W=W, T=T, l_t=lt, family=family, weight_seed=wseed, frame_seed=fseed, b=b),
                     "subsample": sub, "pred": pred[:, :, ::sub, ::sub].contiguous(),
                     "pred_sum": float(pred.double().sum()), "pred_abs_sum": float(pred.double().abs().sum()),
                     "flows_forward": ff.contiguous(), "flows_backward": fb.contiguous()},
                    os.path.join(OUT, name + ".pt"))
-        print(name, tuple(pred.shape), float(pred.abs().max()))
+        print(name, tuple(pred.shape), float(pred.abs().max()), f"{time.time() - t0:.0f} s", flush=True)
 
 
 def gen_ops():
@@ -104,6 +117,10 @@ if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     if "--layout-only" in sys.argv:
         gen_layout()
+        sys.exit(0)
+    if "--e2e" in sys.argv:          # python -m oracle.gen_golden --e2e name [name ...]: only these end-to-end cases
+        torch.set_num_threads(os.cpu_count())
+        gen_e2e(set(sys.argv[sys.argv.index("--e2e") + 1:]))
         sys.exit(0)
     torch.manual_seed(0)
     torch.set_num_threads(os.cpu_count())

@@ -20,18 +20,31 @@ def _model(hq, family, seed, device):
     return m.to(device)
 
 
-@pytest.mark.parametrize("name", ["e2e_hq_tiny_stress", "e2e_hq_small_stress", "e2e_base_stress", "e2e_base_default"])
+# the last four are the shapes bench.py measures: BASELINE configs[3]'s per-GPU share (8 clips per call), configs[2]
+# (HQ 720x1280 mirror-padded to 720x1296, 5+3), a mid-size 10+6 case (T = 16: six q-tiles and 2704+ keys per window,
+# multi-band folds) and configs[4] itself (HQ 1080x1920 -> 1080x1944, 10+6)
+@pytest.mark.parametrize("name", ["e2e_hq_tiny_stress", "e2e_hq_small_stress", "e2e_base_stress", "e2e_base_default",
+                                  "e2e_base_b8_stress", "e2e_hq720_stress", "e2e_hq360_t16_stress",
+                                  "e2e_hq1080_t16_stress"])
 def test_forward_matches_reference_golden(cuda, name):
-    g = torch.load(os.path.join(GOLDEN, name + ".pt"))
+    path = os.path.join(GOLDEN, name + ".pt")
+    if not os.path.exists(path):
+        pytest.skip(f"{name}.pt not generated (python -m oracle.gen_golden --e2e {name})")
+    g = torch.load(path)
     c = g["case"]
+    b = c.get("b", 1)
     model = _model(c["hq"], c["family"], c["weight_seed"], cuda)
-    x = synth_frames(1, c["T"], c["H"], c["W"], seed=c["frame_seed"]).to(cuda)
+    x = synth_frames(b, c["T"], c["H"], c["W"], seed=c["frame_seed"]).to(cuda)
     with torch.no_grad():
         pred, (ff, fb) = model(x, c["l_t"])
-    assert pred.dtype == torch.float32 and pred.shape == (c["T"], 3, c["H"], c["W"])
+    assert pred.dtype == torch.float32 and pred.shape == (b * c["T"], 3, c["H"], c["W"])
     s = g["subsample"]
     err = (pred[:, :, ::s, ::s].cpu() - g["pred"]).abs().max().item()
     assert err < TOL, f"{name}: max abs err {err:.3e}"
+    # whole-tensor statistics of the reference output: catch an error confined to pixels the subsample skips
+    n = pred.numel()
+    assert abs(float(pred.double().sum()) - g["pred_sum"]) / n < 5e-5
+    assert abs(float(pred.double().abs().sum()) - g["pred_abs_sum"]) / n < 5e-5
     # flows are O(1..90) pixels and come out of a 30-conv fp32 pyramid: compare relative to their range
     for got, want in ((ff, g["flows_forward"]), (fb, g["flows_backward"])):
         assert (got.cpu() - want).abs().max().item() < 2e-3 * max(1.0, want.abs().max().item())

@@ -89,6 +89,48 @@ def test_modulated_deform_conv2d(cuda, shape):
     assert rel < 1.5e-3, rel
 
 
+@pytest.mark.parametrize("shape", [(1, 60, 108), (2, 9, 11)])
+def test_modulated_deform_conv2d_unrounded_fp32_oracle(cuda, shape):
+    """The same operator against the oracle fed the ORIGINAL fp32 x and weight (no pre-rounding): bounds what the
+    kernel's fp16 operand policy (BASELINE configs[1]: "fp16 deform-conv") costs against the fp32 reference.
+    Each product x*w carries two independent 2^-12-rms roundings; over K = 2304 terms of magnitude |x||w| the error
+    of one output is ~ sqrt(K) * |x||w| * 2^-11.3 while the output itself is ~ sqrt(K) * |x||w| * E[mask * blend]:
+    a few 1e-4 of the output scale.  Stated tolerance: 1e-3 of max|out| (the e2e budget is 1e-3 absolute on O(1))
+    and 3e-4 of rms(out) for the rms error."""
+    n, h, w = shape
+    x, offset, mask, weight, bias = _dcn_inputs(n, h, w, seed=21)
+    want = restate.modulated_deform_conv2d(x.double(), offset.double(), mask.double(), weight.double(), bias.double(),
+                                           1, 1, 1, 1, 16)
+    got = ops.modulated_deform_conv2d(x.to(cuda), offset.to(cuda), mask.to(cuda), weight.to(cuda), bias.to(cuda),
+                                      1, 1, 1, 1, 16).cpu().double()
+    err = got - want
+    assert err.abs().max().item() < 1e-3 * want.abs().max().item(), err.abs().max().item() / want.abs().max().item()
+    assert err.pow(2).mean().sqrt().item() < 3e-4 * want.pow(2).mean().sqrt().item()
+
+
+def test_deform_align_fused_unrounded_fp32_oracle(cuda):
+    """Fused tail of feat_prop.py:41-58 (10*tanh + flow, sigmoid, DCN) against the oracle on unrounded fp32 inputs."""
+    g = torch.Generator().manual_seed(23)
+    n, h, w = 2, 12, 20
+    x = torch.randn(n, 256, h, w, generator=g)
+    head = torch.randn(n, 432, h, w, generator=g) * 1.5
+    f1 = torch.randn(n, 2, h, w, generator=g) * 2
+    f2 = torch.randn(n, 2, h, w, generator=g) * 2
+    weight = torch.randn(128, 256, 3, 3, generator=g) / 48.0
+    bias = torch.randn(128, generator=g) * 0.1
+    o1, o2, m = torch.chunk(head.double(), 3, dim=1)
+    off = 10.0 * torch.tanh(torch.cat((o1, o2), 1))
+    a, b = torch.chunk(off, 2, dim=1)
+    off = torch.cat([a + f1.double().flip(1).repeat(1, 72, 1, 1), b + f2.double().flip(1).repeat(1, 72, 1, 1)], 1)
+    want = restate.modulated_deform_conv2d(x.double(), off, torch.sigmoid(m), weight.double(), bias.double(),
+                                           1, 1, 1, 1, 16)
+    wp = ops.pack_dcn_weight(weight.to(cuda), 16)
+    got = ops.deform_align_fused(x.to(cuda), head.to(cuda), f1.to(cuda), f2.to(cuda), wp, bias.to(cuda), 16, 10.0)
+    err = got.cpu().double() - want
+    assert err.abs().max().item() < 1e-3 * want.abs().max().item()
+    assert err.pow(2).mean().sqrt().item() < 3e-4 * want.pow(2).mean().sqrt().item()
+
+
 def test_modulated_deform_conv2d_border_cases(cuda):
     """Offsets that land exactly on -1, H, integer grid points and far outside (zero-padding rule)."""
     n, h, w = 1, 6, 10
@@ -561,6 +603,57 @@ def test_window_pool(cuda, shape):
     with pytest.raises(ValueError):
         ops.window_pool(ops.SplitMat(hi.view(B, T, H, W, C)[:, :, :-1], lo.view(B, T, H, W, C)[:, :, :-1]),
                         lin.weight.to(cuda), lin.bias.to(cuda), (wh, ww))
+
+
+# ------------------------------------------------------------------------------------------ propagation vs oracle taps
+@pytest.mark.parametrize("fused", [True, False])
+def test_bidirectional_propagation_matches_oracle_taps(cuda, fused):
+    """BidirectionalPropagation (feat_prop.py:81-149) on the GPU against the CPU oracle, step by step: every
+    deformable-alignment output of both sweeps (restate.bidirectional_propagation(..., taps)) and the final fused
+    features.  Stress weights: live offset conv (offsets = flow + up to +-10 px), biases, O(1) activations."""
+    import importlib
+    from e2fgvi_b200.synth import synth_state_dict
+    net = importlib.import_module("model.e2fgvi")
+    model = net.InpaintGenerator().eval()
+    sd = synth_state_dict(model, "stress", 0)
+    model.load_state_dict(sd, strict=True)
+    prop = model.feat_prop_module.to(cuda)
+    prop.fused_prologue = fused
+    g = torch.Generator().manual_seed(91)
+    b, t, c, h, w = 2, 4, 128, 20, 36
+    x = torch.randn(b, t, c, h, w, generator=g) * 0.5
+    fb = torch.randn(b, t - 1, 2, h, w, generator=g) * 2.5
+    ff = torch.randn(b, t - 1, 2, h, w, generator=g) * 2.5
+    taps = []
+    with torch.no_grad():
+        want = restate.bidirectional_propagation({k: v.double() for k, v in sd.items() if v.is_floating_point()},
+                                                 "feat_prop_module", x.double(), fb.double(), ff.double(), taps)
+    got_taps = []
+    originals = {}
+    for name, mod in prop.deform_align.items():
+        originals[name] = mod.align
+
+        def recorder(*a, _orig=mod.align, _name=name, **kw):
+            out = _orig(*a, **kw)
+            got_taps.append((_name, out))
+            return out
+        mod.align = recorder
+    try:
+        with torch.no_grad():
+            got = prop(x.to(cuda), fb.to(cuda), ff.to(cuda))
+    finally:
+        for name, mod in prop.deform_align.items():
+            mod.align = originals[name]
+    assert len(got_taps) == len(taps) == 2 * (t - 1)
+    for (name, out), tap in zip(got_taps, taps):
+        assert name == tap["dir"]
+        ref = tap["out"]
+        # fp16 operands in the deformable GEMM (see test_modulated_deform_conv2d_unrounded_fp32_oracle); errors of
+        # earlier steps propagate through the recurrence, hence 2e-3 of max per step
+        rel = (out.cpu().double() - ref).abs().max().item() / ref.abs().max().item()
+        assert rel < 2e-3, (name, tap["step"], rel)
+    rel = (got.cpu().double() - want).abs().max().item() / want.abs().max().item()
+    assert got.shape == want.shape and rel < 2e-3, rel
 
 
 # ------------------------------------------------------------------------------------------ fused propagation prologue
