@@ -1,15 +1,19 @@
 #!/usr/bin/env python
 """bench.py — frames/sec of InpaintGenerator.forward on synthetic 432x240 5+3 clips (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--clips-per-gpu B]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--clips-per-gpu B] [--workload W]
     torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...        (N > 1, one rank per GPU, NCCL)
 
-A step = one forward over B clips per GPU (default 8 = BASELINE configs[3]'s per-GPU share: 64 clips over 8 GPUs)
-followed, for N > 1, by the single all-gather output stitch.  Prints ONE JSON line on rank 0.
+Headline: a step = one forward over B clips per GPU (default 8 = BASELINE configs[3]'s per-GPU share: 64 clips over
+8 GPUs) followed, for N > 1, by the single all-gather output stitch (asynchronous, overlapped with the next step's
+forward).  The same JSON line also carries, as first-class fields, the other BASELINE configs measured in the same
+process: ``workloads.b1`` (configs[1]: ONE 432x240 5+3 clip per call, eager and CUDA-graph), ``workloads.hq720``
+(configs[2]) and ``workloads.hq1080`` (configs[4], one clip per GPU).  Prints ONE JSON line on rank 0.
 """
 import argparse
 import importlib
 import json
+import math
 import os
 import statistics
 import subprocess
@@ -22,15 +26,15 @@ if ROOT not in sys.path:
 
 import torch  # noqa: E402
 
-H, W, T, L_T = 240, 432, 8, 5
-METRIC = "frames/sec InpaintGenerator.forward 432x240x(5+3)"
-# other BASELINE.json configs, selectable with --workload (the default "base" is the headline one):
-#   name -> (model module, H, W (mirror-padded to multiples of 60 / 108 like test.py:156-165), T, l_t, clips per GPU)
+# BASELINE.json configs.  name -> (model module, H, W (mirror-padded to multiples of 60 / 108 like test.py:156-165),
+# T, l_t, clips per GPU per step, BASELINE config index)
 WORKLOADS = {
-    "base": ("model.e2fgvi", 240, 432, 8, 5, 8),
-    "hq720": ("model.e2fgvi_hq", 720, 1296, 8, 5, 1),       # configs[2]: 720x1280, 5+3
-    "hq1080": ("model.e2fgvi_hq", 1080, 1944, 16, 10, 1),   # configs[4]: 1080x1920, 10+6, one clip per GPU
+    "base": ("model.e2fgvi", 240, 432, 8, 5, 8, 3),          # configs[3] per-GPU share (64 clips over 8 GPUs)
+    "b1": ("model.e2fgvi", 240, 432, 8, 5, 1, 1),            # configs[1]: one clip per call
+    "hq720": ("model.e2fgvi_hq", 720, 1296, 8, 5, 1, 2),     # configs[2]: 720x1280, 5+3
+    "hq1080": ("model.e2fgvi_hq", 1080, 1944, 16, 10, 1, 4),  # configs[4]: 1080x1920, 10+6, one clip per GPU
 }
+L2_BYTES = 126e6
 
 
 def log(msg):
@@ -105,46 +109,266 @@ def make_model(device, module="model.e2fgvi"):
     model = net.InpaintGenerator().eval()
     sd = synth_state_dict(model, "default", 0)          # the reference's own init family (BASELINE config)
     model.load_state_dict(sd, strict=True)
-    return model.to(device), sd
+    return (model.to(device) if device is not None else model), sd
 
 
-def cpu_oracle_fps(sd, steps=1, warmup=0):
+def workload_config(name, B, world, precision="strict"):
+    """The ``config`` object of the JSON line — IDENTICAL for the GPU arm and the reference arm of one workload."""
+    module, H, W, T, l_t, _, idx = WORKLOADS[name]
+    set_mb = B * T * 3 * H * W * 4 / 1e6
+    return {"workload": f"{module.split('.')[-1]} {W}x{H}" + (" (mirror-padded)" if name.startswith("hq") else "")
+                        + f", {l_t} local + {T - l_t} ref frames, {B} clip(s) per GPU per step (BASELINE configs[{idx}]"
+                        + (" per-GPU share)" if name == "base" else ")"),
+            "global_batch_clips": B * world, "frames_per_clip": T, "parallelism": f"clip-dp{world}",
+            "l2": f"inputs rotate over {n_input_sets(set_mb * 1e6)} sets x {set_mb:.0f} MB (> 126 MB L2)",
+            "precision": precision,
+            "weights": "random-init, reference default family (e2fgvi_b200.synth 'default', seed 0)"}
+
+
+def n_input_sets(set_bytes):
+    return max(2, min(32, math.ceil(1.3 * L2_BYTES / set_bytes)))
+
+
+def metric_name(name):
+    _, H, W, T, l_t, _, _ = WORKLOADS[name]
+    base = f"frames/sec InpaintGenerator.forward {W}x{H}x({l_t}+{T - l_t})"
+    return base if name == "base" else base + f" [{name}]"
+
+
+def cpu_oracle_fps(sd, name="base", steps=1, warmup=0):
     """The reference's CPU implementation of the path: the oracle port (oracle/restate.py) on all host threads,
-    one 5+3 clip per step (the reference itself is single-process, b=1: test.py:108,152-166)."""
+    ONE clip of the workload's shape per step (the reference itself is single-process, b=1: test.py:108,152-166;
+    clips are independent, so its frames/s does not depend on how many clips a step holds)."""
     from e2fgvi_b200.synth import synth_frames
     from oracle import restate
+    _, H, W, T, l_t, _, _ = WORKLOADS[name]
     torch.set_num_threads(host_cores())
     x = synth_frames(1, T, H, W, seed=3)
     with torch.no_grad():
         for _ in range(warmup):
-            restate.inpaint_generator_forward(sd, x, L_T)
+            restate.inpaint_generator_forward(sd, x, l_t)
         t0 = time.perf_counter()
         for _ in range(steps):
-            restate.inpaint_generator_forward(sd, x, L_T)
+            restate.inpaint_generator_forward(sd, x, l_t)
         dt = time.perf_counter() - t0
     return steps * T / dt, dt / steps, torch.get_num_threads()
 
 
-def run_reference(args, rank):
-    """--impl reference: the reference's CPU path (oracle port; /root/reference does not exist on the GPU box)."""
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU path (oracle port; /root/reference does not exist on the GPU box), on
+    the SAME config object as the GPU arm.  Each step is a bounded sample of the workload: one of its clips."""
     if rank != 0:
         return
-    net = importlib.import_module("model.e2fgvi")
-    from e2fgvi_b200.synth import synth_state_dict
-    sd = synth_state_dict(net.InpaintGenerator(), "default", 0)
-    fps, s_per_step, cores = cpu_oracle_fps(sd, steps=args.steps, warmup=args.warmup)
+    name = args.workload
+    module, H, W, T, l_t, default_b, _ = WORKLOADS[name]
+    B = args.clips_per_gpu or default_b
+    _, sd = make_model(None, module)
+    steps, warmup = args.steps, args.warmup
+    if name.startswith("hq"):               # 65 s (720p) .. minutes (1080p) per clip on a CPU: one clip, no warm-up
+        steps, warmup = 1, 0
+    fps, s_per_step, cores = cpu_oracle_fps(sd, name, steps=steps, warmup=warmup)
     line = {
-        "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": s_per_step * 1e3, "higher_is_better": True,
+        "impl": "reference", "metric": metric_name(name), "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
+        "steps": steps, "warmup": warmup, "ms_per_step": s_per_step * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "e2fgvi 432x240, 5 local + 3 ref frames, 1 clip per step, CPU", "frames_per_clip": T},
+        "config": workload_config(name, B, world, args.precision),
         "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
-                         "sample": f"{args.steps} x one 5+3 clip forward (oracle/restate.py, torch CPU fp32; DCN = "
-                                   "explicit restatement, mmcv is not installable offline)"},
+                         "sample": f"{steps} step(s), each ONE clip of the workload's {B} per GPU ({T} frames {W}x{H}; "
+                                   "clips are independent, so CPU frames/s does not depend on the clips per step): "
+                                   "oracle/restate.py, torch CPU fp32 on all host threads; DCN = explicit "
+                                   "restatement (mmcv is not installable offline)"},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+# ops._timed name -> (kernel name, roofline that bounds it, tensor-work multiplier)
+KINDS = {"focal_window_attention": ("focal_attn_kernel", "tensor", 1.0),
+         "deform_align_fused": ("dcn_kernel", "tensor", 1.0),
+         # bf16x3 kernels: algorithmic fp32 FLOPs; each costs 3 bf16 MMAs, so <= 1/3 of the bf16 peak
+         "conv3x3_bf16x3": ("conv3x3_kernel", "tensor", 3.0),
+         "linear_bf16x3": ("linear_kernel", "tensor", 3.0),
+         "t2t_fold_unfold": ("t2t_fold733_kernel", "hbm", 1.0),
+         "t2t_fold": ("t2t_fold_kernel", "hbm", 1.0), "t2t_unfold": ("t2t_unfold733_kernel", "hbm", 1.0),
+         "layernorm_split": ("layernorm_split_kernel", "hbm", 1.0),
+         "upsample2x_split": ("upsample2x_split_kernel", "hbm", 1.0),
+         "window_pool": ("window_pool_kernel", "hbm", 1.0), "pack_rows": ("pack_rows_kernel", "hbm", 1.0)}
+
+
+def kernel_rooflines(prof, total_ms, traffic):
+    """Per-kernel live timing (CUDA events around each launch inside the timed region) -> roofline entries."""
+    hbm, _, tf_sust, _ = peaks()
+    kernels = {}
+    for key, (kname, bound, mult) in KINDS.items():
+        ev = prof.get(key, [])
+        if not ev:
+            continue
+        durs = [a.elapsed_time(b) for a, b, _ in ev]
+        work = sum(w for _, _, w in ev)
+        tot_ms = sum(durs)
+        if bound == "tensor":
+            ach, peak, unit = work / (tot_ms * 1e-3) / 1e12, tf_sust, "TFLOP/s"
+        else:
+            ach, peak, unit = work / (tot_ms * 1e-3) / 1e9, hbm, "GB/s"
+        kernels[kname] = {"bound": bound, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak,
+                          "launches_timed": len(durs), "avg_launch_ms": tot_ms / len(durs),
+                          "share_of_step": tot_ms / total_ms, "traffic": (traffic or {}).get(kname)}
+        if mult != 1.0:
+            kernels[kname]["tensor_work_multiplier"] = mult
+            kernels[kname]["tensor_pipe_frac"] = mult * ach / peak
+    return kernels
+
+
+def dominant(kernels):
+    if not kernels:
+        return None
+    _, _, _, src = peaks()
+    dom = max(kernels, key=lambda k: kernels[k]["share_of_step"])
+    return dict(kernels[dom], kernel=dom,
+                peak_source=f"{src} " + ("bf16_tflops_sustained" if kernels[dom]["bound"] == "tensor" else "hbm_gbs"),
+                note="achieved = algorithmic work (SURVEY 8d) / live CUDA-event launch time inside the timed region")
+
+
+class Measurement:
+    """One workload on this rank's GPU: device-resident timing (value), per-kernel live timing, end-to-end timing
+    through the public API with pinned HOST buffers (H2D of the inputs and D2H of the result inside the timed region)."""
+
+    def __init__(self, name, model, dev, rank, world, B, steps, warmup):
+        from e2fgvi_b200 import clips as C
+        from e2fgvi_b200.synth import synth_frames
+        self.C = C
+        self.name, self.model, self.dev, self.rank, self.world = name, model, dev, rank, world
+        _, self.H, self.W, self.T, self.l_t, _, _ = WORKLOADS[name]
+        self.B, self.steps, self.warmup = B, steps, max(warmup, 3)
+        set_bytes = B * self.T * 3 * self.H * self.W * 4
+        self.n_sets = n_input_sets(set_bytes)
+        self.host_sets = [synth_frames(B, self.T, self.H, self.W, seed=100 + rank * 32 + i).pin_memory()
+                          for i in range(self.n_sets)]
+        self.dev_sets = [h.to(dev) for h in self.host_sets]
+        self.out_host = torch.empty((B * self.T, 3, self.H, self.W), dtype=torch.float32).pin_memory()
+        self.num_clips = B * world
+        self.stitch = C.ClipStitcher(self.num_clips, self.T, rank, world)
+
+    def sync(self):
+        if self.world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    def _loop(self, n, inputs, to_host=False):
+        """n steps; the stitch of step i overlaps the forward of step i+1 (double-buffered landing zone)."""
+        pending = None
+        B, T = self.B, self.T
+        for i in range(n):
+            x = inputs[i % self.n_sets]
+            if to_host:
+                x = x.to(self.dev, non_blocking=True)
+            pred, _ = self.model(x, self.l_t)
+            nxt = self.stitch.start(pred) if self.world > 1 else None
+            if pending is not None:
+                got = pending.wait()
+                if to_host:
+                    self.out_host.copy_(got[self.rank * B * T:(self.rank + 1) * B * T], non_blocking=True)
+            if self.world == 1 and to_host:
+                self.out_host.copy_(pred, non_blocking=True)
+            pending = nxt
+        if pending is not None:
+            got = pending.wait()
+            if to_host:
+                self.out_host.copy_(got[self.rank * B * T:(self.rank + 1) * B * T], non_blocking=True)
+
+    def run(self, sample_clocks=False, profile=True):
+        from e2fgvi_b200 import ops
+        res = {}
+        with torch.no_grad():
+            self._loop(self.warmup, self.dev_sets)
+            self.sync()
+            prof = ops.profile_kernels(True) if profile else None
+            sampler = ClockSampler(self.dev.index) if (sample_clocks and self.rank == 0) else None
+            n0 = ops.launch_count()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            self.sync()
+            e0.record()
+            self._loop(self.steps, self.dev_sets)
+            e1.record()
+            self.sync()
+            res["launches"] = ops.launch_count() - n0
+            res["clocks"] = sampler.stop() if sampler else None
+            if profile:
+                ops.profile_kernels(False)
+            ms = e0.elapsed_time(e1)
+            # ---- end to end through the public API with HOST buffers
+            self._loop(2, self.host_sets, to_host=True)
+            self.sync()
+            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            f0.record()
+            self._loop(self.steps, self.host_sets, to_host=True)
+            f1.record()
+            self.sync()
+            ms_e2e = f0.elapsed_time(f1)
+        t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=self.dev)
+        if self.world > 1:
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        ms, ms_e2e = float(t[0]), float(t[1])
+        frames = self.num_clips * self.T * self.steps
+        nbytes = self.B * self.T * 3 * self.H * self.W * 4 * self.world
+        res.update(ms=ms, ms_per_step=ms / self.steps, value=frames / (ms * 1e-3), prof=prof,
+                   e2e={"value": frames / (ms_e2e * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": nbytes,
+                        "d2h_bytes_per_step": nbytes, "ms_per_step": ms_e2e / self.steps})
+        log(f"{self.name}: {res['ms_per_step']:.2f} ms/step device, {ms_e2e / self.steps:.2f} ms/step e2e")
+        return res
+
+    def free(self):
+        self.host_sets = self.dev_sets = self.out_host = None
+        torch.cuda.empty_cache()
+
+
+def traffic_for(name):
+    """DRAM bytes per launch from the committed `ncu` step capture of THIS workload (profiles/ncu_traffic.json,
+    keyed by workload); None for workloads without a capture (never the bytes of another shape)."""
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if not os.path.exists(tpath):
+        return None
+    d = json.load(open(tpath))
+    return d.get(name) if isinstance(d.get(name), dict) else None
+
+
+def graph_latency(model, one, l_t, reps=10):
+    from e2fgvi_b200.graph import GraphedGenerator
+    graphed = GraphedGenerator(model, one, l_t)
+    for _ in range(3):
+        graphed(one)
+    torch.cuda.synchronize()
+    h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    h0.record()
+    for _ in range(reps):
+        graphed(one)
+    h1.record()
+    torch.cuda.synchronize()
+    return h0.elapsed_time(h1) / reps
+
+
+def video_driver_run(model, H, W):
+    """test.py's sliding-window loop on a synthetic 60-frame video, pinned uint8 host -> host."""
+    import numpy as np
+    from e2fgvi_b200.synth import synth_video
+    from e2fgvi_b200.video import VideoInpainter
+    vf, vm = synth_video(60, H, W, 21)
+    vf_t, vm_t = torch.from_numpy(vf).pin_memory(), torch.from_numpy(vm).pin_memory()
+    drv = VideoInpainter(model, clips_per_call=4)
+    drv(vf_t, vm_t)
+    torch.cuda.synchronize()          # rank-0-only section: no collective
+    v0, v1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    v0.record()
+    comp = drv(vf_t, vm_t).cpu()
+    v1.record()
+    torch.cuda.synchronize()
+    ms_v = v0.elapsed_time(v1)
+    sched = drv.schedule(60)
+    net_frames = sum(len(nb) + len(rf) for _, nb, rf in sched)
+    return {"video_frames": 60, "windows": len(sched), "network_frames": net_frames, "ms": ms_v,
+            "video_frames_per_s": 60 / (ms_v * 1e-3), "network_frames_per_s": net_frames / (ms_v * 1e-3),
+            "untouched_pixels_exact": bool(np.array_equal(comp.numpy()[vm == 0], vf[vm == 0]))}
 
 
 def main():
@@ -156,223 +380,104 @@ def main():
     ap.add_argument("--clips-per-gpu", type=int, default=None)
     ap.add_argument("--workload", default="base", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra-workloads", action="store_true",
+                    help="skip the b1 / hq720 / hq1080 / video-driver sections of the default run")
     ap.add_argument("--precision", default="strict", choices=["strict", "tf32"],
-                    help="library conv/linear precision: strict = fp32 (TF32 off), tf32 = PyTorch GPU defaults")
+                    help="library op precision (only matters for the few remaining torch glue ops)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
-    global H, W, T, L_T, METRIC
-    module, H, W, T, L_T, default_b = WORKLOADS[args.workload]
-    if args.clips_per_gpu is None:
-        args.clips_per_gpu = default_b
-    if args.workload != "base":
-        METRIC = f"frames/sec InpaintGenerator.forward {W}x{H}x({L_T}+{T - L_T}) [{args.workload}]"
 
     from e2fgvi_b200 import clips as C
     if args.impl == "reference":
-        run_reference(args, int(os.environ.get("RANK", "0")))
+        run_reference(args, int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")))
         return
-    args.warmup = max(args.warmup, 3)
     rank, world, local_rank = C.init_from_env()
     assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU fallback); use --impl reference for the CPU arm"
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
     from e2fgvi_b200 import build as _build
-    from e2fgvi_b200 import ops
-    from e2fgvi_b200.synth import synth_frames
     _build.build()
-    model, sd = make_model(dev, module)
-    model.precision = args.precision
-    log(f"rank {rank}/{world}: model ready, precision={args.precision}, host cores={host_cores()}")
-    B = args.clips_per_gpu
-    num_clips = B * world
+    name = args.workload
+    module, H, W, T, l_t, default_b, _ = WORKLOADS[name]
+    B = args.clips_per_gpu or default_b
+    models = {}
 
-    # rotating input sets: 4 x B clips (4 x 80 MB at B=8) > 126 MB L2, so no step re-reads a cached input
-    n_sets = 4
-    host_sets = [synth_frames(B, T, H, W, seed=100 + rank * n_sets + i).pin_memory() for i in range(n_sets)]
-    dev_sets = [h.to(dev) for h in host_sets]
-    out_host = torch.empty((B * T, 3, H, W), dtype=torch.float32).pin_memory()
+    def get_model(mod):
+        if mod not in models:
+            models[mod] = make_model(dev, mod)
+            models[mod][0].precision = args.precision
+        return models[mod]
 
-    def step(i):
-        pred, _ = model(dev_sets[i % n_sets], L_T)
-        return C.gather_outputs(pred, num_clips, T, rank, world) if world > 1 else pred
+    model, sd = get_model(module)
+    log(f"rank {rank}/{world}: model ready, workload={name}, host cores={host_cores()}")
+    head = Measurement(name, model, dev, rank, world, B, args.steps, args.warmup)
+    main_res = head.run(sample_clocks=True)
+    kernels = kernel_rooflines(main_res["prof"], main_res["ms"], traffic_for(name)) if rank == 0 else {}
+    one_clip = head.dev_sets[0][:1].clone()
+    head.free()
 
-    def sync():
-        if world > 1:
-            torch.distributed.barrier()
-        torch.cuda.synchronize()
-
-    with torch.no_grad():
-        for i in range(args.warmup):
-            step(i)
-        sync()
-        log("warm-up done")
-        # ---------------- device-resident timing (value) + live kernel timing for the roofline
-        prof = ops.profile_kernels(True)
-        sampler = ClockSampler(local_rank) if rank == 0 else None
-        n0 = ops.launch_count()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        sync()
-        e0.record()
-        for i in range(args.steps):
-            step(i)
-        e1.record()
-        sync()
-        launches = ops.launch_count() - n0
-        clocks = sampler.stop() if sampler else None
-        ops.profile_kernels(False)
-        ms = e0.elapsed_time(e1)
-        log(f"timed region: {ms / args.steps:.2f} ms/step")
-        # ---------------- end-to-end through the public API with HOST buffers (pinned H2D in, D2H of the result)
-        for i in range(2):
-            pred, _ = model(host_sets[i].to(dev, non_blocking=True), L_T)
-            out_host.copy_(pred, non_blocking=True)
-        sync()
-        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        f0.record()
-        for i in range(args.steps):
-            x = host_sets[i % n_sets].to(dev, non_blocking=True)
-            pred, _ = model(x, L_T)
-            if world > 1:
-                pred = C.gather_outputs(pred, num_clips, T, rank, world)[rank * B * T:(rank + 1) * B * T]
-            out_host.copy_(pred, non_blocking=True)
-        f1.record()
-        sync()
-        ms_e2e = f0.elapsed_time(f1)
-        log(f"e2e: {ms_e2e / args.steps:.2f} ms/step")
-        # single-clip latency (BASELINE configs[1] shape, b=1)
-        one = dev_sets[0][:1]
-        n_sets_b1 = 1
-        for _ in range(3):
-            model(one, L_T)
-        sync()
-        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        g0.record()
-        for _ in range(5):
-            model(one, L_T)
-        g1.record()
-        sync()
-        ms_b1 = g0.elapsed_time(g1) / 5
-        # the same single clip replayed from a CUDA graph (launch-bound case)
-        ms_b1_graph = None
-        try:
-            from e2fgvi_b200.graph import GraphedGenerator
-            graphed = GraphedGenerator(model, one, L_T)
-            for _ in range(3):
-                graphed(one)
-            sync()
-            h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            h0.record()
-            for _ in range(10):
-                graphed(one)
-            h1.record()
-            sync()
-            ms_b1_graph = h0.elapsed_time(h1) / 10
-        except Exception as exc:      # reported, never fatal for the headline numbers
-            log(f"CUDA-graph latency run failed: {exc!r}")
-        # video-level driver (test.py's sliding-window loop): a synthetic 60-frame 432x240 video
-        # from pinned uint8 host buffers to the composited uint8 result back on the host
-        video = None
-        if args.workload == "base" and rank == 0:
+    extra, b1 = {}, None
+    video = None
+    if not args.no_extra_workloads and name == "base":
+        # ---- BASELINE configs[1] / [2] / [4] in the same process (every rank runs them; whole-job aggregate)
+        for wname in ("b1", "hq720", "hq1080"):
+            wmod, wH, wW, wT, wl_t, wB, _ = WORKLOADS[wname]
             try:
-                import numpy as np
-                from e2fgvi_b200.synth import synth_video
-                from e2fgvi_b200.video import VideoInpainter
-                vf, vm = synth_video(60, H, W, 21)
-                vf_t, vm_t = torch.from_numpy(vf).pin_memory(), torch.from_numpy(vm).pin_memory()
-                drv = VideoInpainter(model, clips_per_call=4)
-                drv(vf_t, vm_t)
-                torch.cuda.synchronize()          # rank-0-only section: no collective (sync() holds a barrier)
-                v0, v1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                v0.record()
-                comp = drv(vf_t, vm_t).cpu()
-                v1.record()
-                torch.cuda.synchronize()
-                ms_v = v0.elapsed_time(v1)
-                sched = drv.schedule(60)
-                video = {"video_frames": 60, "windows": len(sched),
-                         "network_frames": sum(len(nb) + len(rf) for _, nb, rf in sched), "ms": ms_v,
-                         "video_frames_per_s": 60 / (ms_v * 1e-3),
-                         "network_frames_per_s": sum(len(nb) + len(rf) for _, nb, rf in sched) / (ms_v * 1e-3),
-                         "untouched_pixels_exact": bool(np.array_equal(comp.numpy()[vm == 0], vf[vm == 0]))}
+                wm, _ = get_model(wmod)
+                steps = {"b1": 20, "hq720": 5, "hq1080": 3}[wname]
+                m = Measurement(wname, wm, dev, rank, world, wB, steps, 3)
+                r = m.run()
+                entry = {"metric": metric_name(wname), "value": r["value"], "unit": "frames/s", "steps": steps, "warmup": 3,
+                         "ms_per_step": r["ms_per_step"], "e2e": r["e2e"], "gpu_launches": r["launches"],
+                         "config": workload_config(wname, wB, world, args.precision)}
+                if rank == 0:
+                    wk = kernel_rooflines(r["prof"], r["ms"], traffic_for(wname))
+                    entry["roofline"] = dominant(wk)
+                    entry["roofline_kernels"] = wk
+                if wname == "b1" and world == 1:
+                    try:
+                        entry["cuda_graph_ms_per_step"] = graph_latency(wm, one_clip, wl_t)
+                        entry["cuda_graph_value"] = wT / (entry["cuda_graph_ms_per_step"] * 1e-3)
+                    except Exception as exc:      # reported, never fatal for the headline numbers
+                        log(f"CUDA-graph latency run failed: {exc!r}")
+                m.free()
+                extra[wname] = entry
+            except Exception as exc:
+                log(f"workload {wname} failed: {exc!r}")
+                extra[wname] = {"error": repr(exc)}
+        b1 = extra.get("b1")
+        if rank == 0:
+            try:
+                video = video_driver_run(model, H, W)
             except Exception as exc:
                 log(f"video driver run failed: {exc!r}")
 
-    t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
-    if world > 1:
-        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
-    ms, ms_e2e = float(t[0]), float(t[1])
-    frames = num_clips * T * args.steps
-    value = frames / (ms * 1e-3)
-    e2e = frames / (ms_e2e * 1e-3)
-
     if rank == 0:
-        hbm, tf_burst, tf_sust, src = peaks()
-        # per-kernel live timing (CUDA events around each launch inside the timed region)
-        kinds = {"focal_window_attention": ("focal_attn_kernel", "tensor", 1.0),
-                 "deform_align_fused": ("dcn_kernel", "tensor", 1.0),
-                 # bf16x3 kernels: algorithmic fp32 FLOPs; each costs 3 bf16 MMAs, so <= 1/3 of the bf16 peak
-                 "conv3x3_bf16x3": ("conv3x3_kernel", "tensor", 3.0),
-                 "linear_bf16x3": ("linear_kernel", "tensor", 3.0),
-                 "t2t_fold": ("t2t_fold_kernel", "hbm", 1.0), "t2t_unfold": ("t2t_unfold733_kernel", "hbm", 1.0)}
-        traffic = {}
-        tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")   # dram bytes / launch from `ncu --set full`
-        if os.path.exists(tpath):
-            traffic = json.load(open(tpath))
-        kernels = {}
-        for key, (kname, bound, mult) in kinds.items():
-            ev = prof.get(key, [])
-            if not ev:
-                continue
-            durs = [a.elapsed_time(b) for a, b, _ in ev]
-            work = sum(w for _, _, w in ev)
-            tot_ms = sum(durs)
-            if bound == "tensor":
-                ach = work / (tot_ms * 1e-3) / 1e12
-                peak, unit = tf_sust, "TFLOP/s"
-            else:
-                ach = work / (tot_ms * 1e-3) / 1e9
-                peak, unit = hbm, "GB/s"
-            kernels[kname] = {"bound": bound, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak,
-                              "launches_timed": len(durs), "avg_launch_ms": tot_ms / len(durs),
-                              "share_of_step": tot_ms / ms, "traffic": traffic.get(kname)}
-            if mult != 1.0:
-                kernels[kname]["tensor_work_multiplier"] = mult
-                kernels[kname]["tensor_pipe_frac"] = mult * ach / peak
-        roof = None
-        if kernels:
-            dom = max(kernels, key=lambda k: kernels[k]["share_of_step"])
-            roof = dict(kernels[dom], kernel=dom,
-                        peak_source=f"{src} " + ("bf16_tflops_sustained" if kernels[dom]["bound"] == "tensor" else "hbm_gbs"),
-                        note="achieved = algorithmic work (SURVEY 8d) / live CUDA-event launch time inside the timed region")
         cpu = None
-        if not args.no_cpu_baseline and args.workload == "base":
+        if not args.no_cpu_baseline and name in ("base", "b1"):
             log("timing the CPU oracle (1 warm-up + 2 clips) ...")
-            fps, s_per, cores = cpu_oracle_fps(sd, steps=2, warmup=1)
+            fps, s_per, cores = cpu_oracle_fps(sd, name, steps=2, warmup=1)
             log(f"CPU oracle: {s_per:.2f} s/clip on {cores} threads")
             cpu = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
-                   "sample": "2 x one 5+3 clip forward after 1 warm-up (oracle/restate.py, torch CPU fp32)"}
+                   "sample": "2 x one 5+3 clip forward after 1 warm-up (oracle/restate.py, torch CPU fp32; clips are "
+                             "independent, so CPU frames/s does not depend on the clips per step)"}
         line = {
-            "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None,
+            "metric": metric_name(name), "value": main_res["value"], "unit": "frames/s", "n_gpus": world,
+            "steps": args.steps, "warmup": head.warmup, "ms_per_step": main_res["ms_per_step"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f16 operands / f32 accumulate (DCN, attention kernels); bf16 3-term split operands / f32 "
-                     "accumulate = fp32-level accuracy (conv, linear kernels)"
-                     + ("" if args.precision == "strict" else "; torch library ops tf32"),
-            "data": "synthetic",
-            "config": {"workload": (f"e2fgvi 432x240, 5 local + 3 ref frames, {B} clips per GPU per step "
-                                    "(BASELINE configs[3] per-GPU share)") if args.workload == "base" else
-                                   f"{module.split('.')[-1]} {W}x{H} (mirror-padded), {L_T} local + {T - L_T} ref frames, "
-                                   f"{B} clip(s) per GPU per step",
-                       "global_batch_clips": num_clips, "frames_per_clip": T, "parallelism": f"clip-dp{world}",
-                       "l2": f"inputs rotate over {n_sets} sets x {B * T * 3 * H * W * 4 / 1e6:.0f} MB (> 126 MB L2)",
-                       "precision": args.precision,
-                       "weights": "random-init, reference default family (e2fgvi_b200.synth 'default', seed 0)"},
-            "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": B * T * 3 * H * W * 4 * world,
-                    "d2h_bytes_per_step": B * T * 3 * H * W * 4 * world, "ms_per_step": ms_e2e / args.steps},
-            "gpu_launches": launches, "clocks": clocks, "roofline": roof, "roofline_kernels": kernels,
-            "cpu_baseline": cpu, "latency_b1_ms": ms_b1, "fps_b1": T / (ms_b1 * 1e-3),
-            "latency_b1_cuda_graph_ms": ms_b1_graph, "video_driver": video,
-            "fps_b1_cuda_graph": None if not ms_b1_graph else T / (ms_b1_graph * 1e-3),
+                     "accumulate = fp32-level accuracy (conv, linear kernels)",
+            "data": "synthetic", "config": workload_config(name, B, world, args.precision),
+            "e2e": main_res["e2e"], "gpu_launches": main_res["launches"], "clocks": main_res["clocks"],
+            "roofline": dominant(kernels), "roofline_kernels": kernels, "cpu_baseline": cpu,
+            # BASELINE configs[1] (one clip per call) as first-class numbers next to the batched headline
+            "fps_b1": None if not b1 or "value" not in b1 else b1["value"],
+            "latency_b1_ms": None if not b1 or "ms_per_step" not in b1 else b1["ms_per_step"],
+            "fps_b1_e2e": None if not b1 or "e2e" not in b1 else b1["e2e"]["value"],
+            "fps_b1_cuda_graph": None if not b1 else b1.get("cuda_graph_value"),
+            "latency_b1_cuda_graph_ms": None if not b1 else b1.get("cuda_graph_ms_per_step"),
+            "speedup_vs_cpu_b1": None if not (b1 and cpu and "value" in b1) else b1["value"] / cpu["value"],
+            "workloads": extra, "video_driver": video,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

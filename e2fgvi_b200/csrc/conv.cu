@@ -38,14 +38,16 @@ constexpr int THREADS = (2 + EPI_WARPS) * 32;
 constexpr int MAX_SRC = 4;
 
 // N tile: 128 output channels; 64 / 32 for the layers with <= 64 / <= 32 output channels per group (decoder, encoder
-// conv 1, SPyNet, the 3-channel output conv), which would otherwise waste most of every MMA.
+// conv 1, SPyNet, the 3-channel output conv), which would otherwise waste most of every MMA; 96 for the encoder's
+// groups-of-96 conv (e2fgvi.py:86: 768 -> 384, groups 4), where a 128-wide tile would compute 25 % padding.
 template <int BN>
 struct Cfg {
   static constexpr int W_TILE = BN * BK * 2;
   static constexpr int STAGE = 2 * A_TILE + 2 * W_TILE;   // 64 KB (BN=128) / 48 KB (BN=64) / 40 KB (BN=32)
-  static constexpr int STAGES = (BN == 128) ? 3 : 4;
+  static constexpr int STAGES = (BN >= 96) ? 3 : 4;
   static constexpr int ACC_COLS = 2 * BN;                 // accumulator: [Ah.Wh + Al.Wh | Ah.Wl], summed by the epilogue
-  static constexpr int TMEM_COLS = 2 * ACC_COLS;          // double-buffered
+  // double-buffered; tcgen05.alloc wants a power of two (BN = 96: 384 columns used of 512)
+  static constexpr int TMEM_COLS = (4 * BN <= 128) ? 128 : (4 * BN <= 256) ? 256 : 512;
   static constexpr int SMEM = STAGES * STAGE + 256 + MAX_COUT * 4 + EPI_WARPS * EPI_STAGE + 1024;
 };
 
@@ -695,7 +697,14 @@ int launch_conv3x3(int nsrc, const void* const* src_hi, const void* const* src_l
     return -2;
   }
   const int cog = cout / groups;
-  const int bn = cog <= 32 ? 32 : (cog <= 64 ? 64 : 128);
+  int bn = cog <= 32 ? 32 : (cog <= 64 ? 64 : (cog == 96 ? 96 : 128));
+  // few tiles (single-clip propagation steps: 51 pixel tiles on 148 SMs): halve the N tile so that twice as many SMs
+  // work; a tile then costs (64 + 55) instead of (128 + 64) tensor-pipe cycles per K step (tools/mma_rate_probe.cu)
+  if (bn == 128 && cog % 64 == 0 && !in_rows) {
+    const long long t128 = static_cast<long long>(n) * ((h + TILE_H - 1) / TILE_H) * ((w + TILE_W - 1) / TILE_W) * groups *
+                           ((cog + 127) / 128);
+    if (2 * t128 <= num_sms()) bn = 64;
+  }
   Maps maps;
   Params p;
   p.N = n; p.H = h; p.W = w; p.Cout = cout; p.groups = groups; p.nsrc = nsrc;
@@ -799,6 +808,8 @@ int launch_conv3x3(int nsrc, const void* const* src_hi, const void* const* src_l
   if (!device_done(configured, dev)) {
     cudaError_t e = cudaFuncSetAttribute(conv3x3_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<128>::SMEM);
     if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(conv3x3_kernel<96>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<96>::SMEM);
+    if (e == cudaSuccess)
       e = cudaFuncSetAttribute(conv3x3_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<64>::SMEM);
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(conv3x3_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<32>::SMEM);
@@ -842,6 +853,8 @@ int launch_conv3x3(int nsrc, const void* const* src_hi, const void* const* src_l
     conv3x3_kernel<32><<<grid, THREADS, Cfg<32>::SMEM, stream>>>(maps, p);
   else if (bn == 64)
     conv3x3_kernel<64><<<grid, THREADS, Cfg<64>::SMEM, stream>>>(maps, p);
+  else if (bn == 96)
+    conv3x3_kernel<96><<<grid, THREADS, Cfg<96>::SMEM, stream>>>(maps, p);
   else
     conv3x3_kernel<128><<<grid, THREADS, Cfg<128>::SMEM, stream>>>(maps, p);
   count_launch();

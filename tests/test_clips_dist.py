@@ -27,7 +27,27 @@ def _worker(rank, world, port, num_clips, q):
     clips = torch.randn(num_clips, 4, 3, 6, 8, generator=g)
     out = C.run_clips(_ToyModel(), clips, 3, rank=r, world=w, clips_per_call=2)
     want, _ = _ToyModel()(clips, 3)
-    q.put((rank, bool(torch.equal(out, want)), tuple(out.shape)))
+    ok = bool(torch.equal(out, want))
+    # compact payloads (what test.py keeps is the uint8 frame, test.py:168-169)
+    out8 = C.run_clips(_ToyModel(), clips.clamp(-1, 1), 3, rank=r, world=w, clips_per_call=2, payload="uint8")
+    want8 = ((_ToyModel()(clips.clamp(-1, 1), 3)[0] + 1) / 2 * 255).clamp(0, 255).to(torch.uint8)
+    ok = ok and out8.dtype == torch.uint8 and bool(torch.equal(out8, want8))
+    # asynchronous double-buffered stitch: two stitches in flight, joined in order
+    share, T = C.padded_share(num_clips, w), clips.shape[1]
+    st = C.ClipStitcher(num_clips, T, r, w)
+    pend = []
+    for k in range(3):
+        mine = C.shard_clips(num_clips, r, w)
+        local, _ = _ToyModel()(clips[mine] + k, 3)
+        if local.shape[0] < share * T:
+            local = torch.cat([local, local.new_zeros((share * T - local.shape[0],) + tuple(local.shape[1:]))])
+        pend.append((k, st.start(local)))
+        if len(pend) == 2:
+            kk, h = pend.pop(0)
+            ok = ok and bool(torch.equal(h.wait(), _ToyModel()(clips + kk, 3)[0]))
+    for kk, h in pend:
+        ok = ok and bool(torch.equal(h.wait(), _ToyModel()(clips + kk, 3)[0]))
+    q.put((rank, ok, tuple(out.shape)))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -58,7 +78,8 @@ def test_two_rank_stitch_ragged():
 
 def test_shard_helpers():
     from e2fgvi_b200 import clips as C
-    assert C.shard_clips(5, 0, 2) == [0, 2, 4] and C.shard_clips(5, 1, 2) == [1, 3]
+    assert C.shard_clips(5, 0, 2) == [0, 1, 2] and C.shard_clips(5, 1, 2) == [3, 4]      # contiguous blocks
+    assert C.shard_clips(64, 3, 8) == list(range(24, 32)) and C.shard_clips(3, 3, 4) == []
     assert C.padded_share(5, 2) == 3 and C.padded_share(64, 8) == 8
     x = torch.arange(12.).view(12, 1, 1, 1)
     assert torch.equal(C.gather_outputs(x, 3, 4, 0, 1), x)

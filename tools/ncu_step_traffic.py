@@ -4,7 +4,7 @@
 capture: every launch of the step is measured (not a sample of a few launches), so `traffic` in bench.py's roofline
 block is the mean over exactly the launches whose live duration `achieved` averages.  Writes profiles/ncu_traffic.json
 (bytes per launch; the HALO conv variant is folded into conv3x3_kernel, the name bench.py reports) and prints a table.
-    python tools/ncu_step_traffic.py <csv> [<out.txt>]"""
+    python tools/ncu_step_traffic.py <csv> [<out.txt>] [<workload key of profiles/ncu_traffic.json, default base>]"""
 import collections
 import csv
 import json
@@ -54,5 +54,6 @@ if len(sys.argv) > 2:
     open(sys.argv[2], "w").write("\n".join(out) + "\n")
 jpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
 old = json.load(open(jpath)) if os.path.exists(jpath) else {}
-old.update(traffic)
+workload = sys.argv[3] if len(sys.argv) > 3 else "base"       # bench.py reads the entry of the workload it measures
+old.setdefault(workload, {}).update(traffic)
 json.dump(old, open(jpath, "w"), indent=1)
