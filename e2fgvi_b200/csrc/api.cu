@@ -280,6 +280,37 @@ int e2f_conv2d_rows_bf16x3(int nsrc, const void* const* src_hi, const void* cons
   return finish(launch_conv3x3(nsrc, src_hi, src_lo, src_channels, w_hi, w_lo, bias, residual, out, out_hi, out_lo, n, h, w, cout, groups, leaky_slope, ksize, stride, pad, in_rows ? 1 : 0, out_lead, static_cast<cudaStream_t>(stream)), who);
 }
 
+int e2f_conv_gather_bf16x3(int nsrc, const void* const* src_hi, const void* const* src_lo, const int* src_channels,
+                           const void* w_hi, const void* w_lo, const float* bias, const float* bias_map,
+                           const float* residual, float* out, void* out_hi, void* out_lo, int n, int h_in, int w_in,
+                           int cout, float leaky_slope, int stride, int grid_h, int grid_w, int tile_w, int tile_h,
+                           int ntaps, const int8_t* tap_dy, const int8_t* tap_dx, int nphase, const uint8_t* ph_tap0,
+                           const uint8_t* ph_oy, const uint8_t* ph_ox, int ostep, int out_h, int out_w, void* stream) {
+  const char* who = "e2f_conv_gather_bf16x3";
+  if (!src_hi || !src_lo || !src_channels || !w_hi || !w_lo || !tap_dy || !tap_dx || !ph_tap0 || !ph_oy || !ph_ox) { set_error("%s: null pointer", who); return E2F_ERR_BAD_ARG; }
+  if ((!out && !out_hi) || (!out_hi) != (!out_lo)) { set_error("%s: need out and/or both of out_hi/out_lo", who); return E2F_ERR_BAD_ARG; }
+  if (out_hi && cout % 8) { set_error("%s: split output needs Cout %% 8 == 0", who); return E2F_ERR_UNSUPPORTED; }
+  if (nsrc < 1 || nsrc > 4) { set_error("%s: nsrc=%d (1..4 supported)", who, nsrc); return E2F_ERR_UNSUPPORTED; }
+  if (n < 0 || h_in <= 0 || w_in <= 0 || cout <= 0 || grid_h <= 0 || grid_w <= 0 || out_h <= 0 || out_w <= 0) { set_error("%s: bad shape", who); return E2F_ERR_BAD_ARG; }
+  if (stride < 1 || stride > 8 || ntaps < 1 || ntaps > 64 || nphase < 1 || nphase > 9 || ostep < 1 || ostep > 8 || tile_w < 1 || tile_h < 1 || tile_w * tile_h > 128) { set_error("%s: unsupported geometry stride=%d taps=%d phases=%d ostep=%d tile=%dx%d", who, stride, ntaps, nphase, ostep, tile_w, tile_h); return E2F_ERR_UNSUPPORTED; }
+  if (ph_tap0[0] != 0 || ph_tap0[nphase] != ntaps) { set_error("%s: ph_tap0 must start at 0 and end at ntaps", who); return E2F_ERR_BAD_ARG; }
+  for (int i = 0; i < nphase; ++i) {
+    if (ph_tap0[i] >= ph_tap0[i + 1] || ph_oy[i] >= ostep || ph_ox[i] >= ostep) { set_error("%s: phase %d is empty or its offset exceeds ostep", who, i); return E2F_ERR_BAD_ARG; }
+  }
+  for (int i = 0; i < nsrc; ++i) {
+    if (!src_hi[i] || !src_lo[i]) { set_error("%s: null source %d", who, i); return E2F_ERR_BAD_ARG; }
+    if (src_channels[i] <= 0 || src_channels[i] % 8) { set_error("%s: source %d has %d channels (needs a multiple of 8)", who, i, src_channels[i]); return E2F_ERR_UNSUPPORTED; }
+    if (!aligned(src_hi[i], 16) || !aligned(src_lo[i], 16)) { set_error("%s: 16-byte alignment required", who); return E2F_ERR_ALIGNMENT; }
+  }
+  if (!aligned(w_hi, 16) || !aligned(w_lo, 16) || (out && !aligned(out, 16)) || (out_hi && (!aligned(out_hi, 16) || !aligned(out_lo, 16))) || (residual && !aligned(residual, 16)) || (bias_map && !aligned(bias_map, 16))) { set_error("%s: 16-byte alignment required", who); return E2F_ERR_ALIGNMENT; }
+  if (n == 0) return 0;
+  ConvGeom g;
+  g.grid_h = grid_h; g.grid_w = grid_w; g.out_h = out_h; g.out_w = out_w; g.tile_w = tile_w; g.tile_h = tile_h;
+  g.ntaps = ntaps; g.nphase = nphase; g.ostep = ostep; g.tap_dy = tap_dy; g.tap_dx = tap_dx; g.ph_tap0 = ph_tap0;
+  g.ph_oy = ph_oy; g.ph_ox = ph_ox; g.bias_map = bias_map;
+  return finish(launch_conv3x3(nsrc, src_hi, src_lo, src_channels, w_hi, w_lo, bias, residual, out, out_hi, out_lo, n, h_in, w_in, cout, 1, leaky_slope, 0, stride, 0, 0, 0, static_cast<cudaStream_t>(stream), &g), who);
+}
+
 int e2f_conv2d_bf16x3(int nsrc, const void* const* src_hi, const void* const* src_lo, const int* src_channels,
                       const void* w_hi, const void* w_lo, const float* bias, const float* residual, float* out,
                       void* out_hi, void* out_lo, int n, int h, int w, int cout, int groups, float leaky_slope, int ksize,

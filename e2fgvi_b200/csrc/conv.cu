@@ -66,9 +66,19 @@ struct Params {
   int cig[MAX_SRC];        // channels per group of each source
   int chunks[MAX_SRC];     // ceil(cig / 64)
   int chunks_total;        // sum of chunks
+  // Tap table ("gather conv"): tap i reads the input at (y*stride + tap_dy[i], x*stride + tap_dx[i]); a plain k x k conv
+  // lists its k*k taps with dy = ky - pad, dx = kx - pad.  Taps are grouped into PHASES: phase ph owns taps
+  // [ph_tap0[ph], ph_tap0[ph+1]) and writes output pixel (y*ostep + ph_oy[ph], x*ostep + ph_ox[ph]) of an
+  // out_H x out_W image — one phase for a conv; nine for the transposed 7x7 / stride-3 conv that SoftComp's
+  // Linear + fold is (tfocal_transformer.py:65-72): output pixels with the same (y mod 3, x mod 3) share a tap set.
+  int tile_w, tile_h;      // GEMM-grid pixels per tile (tile_w * tile_h <= 128; rows beyond are idle)
+  int nphase, ostep, out_H, out_W;
+  int8_t tap_dy[64], tap_dx[64];
+  uint8_t ph_tap0[10], ph_oy[9], ph_ox[9];
   float slope;             // LeakyReLU negative slope (1 = identity)
   const float* bias;
-  const float* residual;   // NHWC fp32 [N][H][W][Cout] or null
+  const float* bias_map;   // optional fp32 [out_H][out_W][Cout] added per output pixel (folded Linear bias + sc.bias) or null
+  const float* residual;   // NHWC fp32 [N][out_H][out_W][Cout] or null
   float* out;              // NHWC fp32 or null
   __nv_bfloat16* out_hi;   // NHWC bf16 split of the result (operand format of the next conv) or null
   __nv_bfloat16* out_lo;
@@ -89,6 +99,7 @@ __device__ __forceinline__ void tma_load_4d(uint32_t smem_dst, const void* tmap,
 
 struct TileCoord {
   int n, y0, x0, g, co0;   // co0: first output channel of the tile (global index)
+  int ph, oy, ox;          // phase and its output-pixel offset
 };
 
 template <int BN>
@@ -98,13 +109,17 @@ __device__ __forceinline__ TileCoord decode_tile(int tile, const Params& p, int 
   int r = tile / tiles_ng;
   t.g = r % p.groups;
   r /= p.groups;
+  t.ph = r % p.nphase;
+  r /= p.nphase;
   const int tx = r % tiles_x;
   r /= tiles_x;
   const int ty = r % tiles_y;
   t.n = r / tiles_y;
-  t.y0 = ty * TILE_H;
-  t.x0 = tx * TILE_W;
+  t.y0 = ty * p.tile_h;
+  t.x0 = tx * p.tile_w;
   t.co0 = t.g * (p.Cout / p.groups) + nt * BN;
+  t.oy = p.ph_oy[t.ph];
+  t.ox = p.ph_ox[t.ph];
   return t;
 }
 
@@ -121,15 +136,23 @@ __device__ __forceinline__ TileCoord decode_tile(int tile, const Params& p, int 
 // which made the epilogue the bottleneck of the layers with a short main loop.  Each warp instead transposes its
 // 32 rows x 64 bytes through a conflict-free XOR-swizzled buffer so that 4 consecutive lanes write one pixel's 64
 // contiguous bytes (8 lines per instruction).  Chunks that are not 32 full, 16-byte-aligned channels take the direct path.
-template <int BN, int TW>
+template <int BN>
 __device__ __forceinline__ void epilogue_tile(const Params& p, const TileCoord& t, uint32_t taddr, int r, int cog,
                                               const float* __restrict__ bias_s, int c_begin, int c_end,
-                                              uint8_t* __restrict__ stage) {
+                                              uint8_t* __restrict__ stage, const int TW, const int TH) {
   const int lane = r & 31;
-  const int y = t.y0 + r / TW, x = t.x0 + r % TW;
-  const bool pix_ok = (y < p.H) && (x < p.W);
-  const size_t pix = (static_cast<size_t>(t.n) * p.H + y) * p.W + x;                      // fp32 out, residual
-  const size_t opix = (static_cast<size_t>(t.n) * p.H + y) * p.out_pitch + p.out_lead + x;   // split outputs
+  // accumulator row R -> GEMM-grid pixel (gy, gx) -> output pixel (Y, X) of the out_H x out_W image
+  auto map_row = [&](int R, int& Y, int& X) -> bool {
+    const int ly = R / TW, gy = t.y0 + ly, gx = t.x0 + (R - ly * TW);
+    Y = gy * p.ostep + t.oy;
+    X = gx * p.ostep + t.ox;
+    return ly < TH && gy < p.H && gx < p.W && Y < p.out_H && X < p.out_W;
+  };
+  int y, x;                                            // this thread's OUTPUT pixel
+  const bool pix_ok = map_row(r, y, x);
+  const size_t pix = (static_cast<size_t>(t.n) * p.out_H + y) * p.out_W + x;                      // fp32 out, residual
+  const size_t opix = (static_cast<size_t>(t.n) * p.out_H + y) * p.out_pitch + p.out_lead + x;   // split outputs
+  const size_t mpix = static_cast<size_t>(y) * p.out_W + x;                                         // bias map
   const int co_end = (t.g + 1) * cog;               // exclusive end of this group's output channels
   const bool vec_ok = (p.Cout & 3) == 0;            // 16-byte aligned channel groups
 #pragma unroll 1
@@ -162,6 +185,14 @@ __device__ __forceinline__ void epilogue_tile(const Params& p, const TileCoord& 
           f[g4 * 4] += ra.x; f[g4 * 4 + 1] += ra.y; f[g4 * 4 + 2] += ra.z; f[g4 * 4 + 3] += ra.w;
         }
       }
+      if (p.bias_map && pix_ok) {
+        const float4* m4 = reinterpret_cast<const float4*>(p.bias_map + mpix * p.Cout + co);
+#pragma unroll
+        for (int g4 = 0; g4 < 8; ++g4) {
+          const float4 ra = __ldg(m4 + g4);
+          f[g4 * 4] += ra.x; f[g4 * 4 + 1] += ra.y; f[g4 * 4 + 2] += ra.z; f[g4 * 4 + 3] += ra.w;
+        }
+      }
       // write side: row = lane, logical 16-byte chunk cc at physical chunk cc ^ ((lane >> 1) & 3); read side: lanes
       // 4k..4k+3 fetch the 4 chunks of row j*8 + k.  Both sides touch 8 distinct bank groups per quarter-warp.
       const uint32_t wbase = smem_u32(stage) + lane * 64, wsw = (lane >> 1) & 3;
@@ -189,10 +220,11 @@ __device__ __forceinline__ void epilogue_tile(const Params& p, const TileCoord& 
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const int rr = j * 8 + prow, R = rbase + rr;
-            const int yy = t.y0 + R / TW, xx = t.x0 + R % TW;
+            int yy, xx;
+            const bool ok = map_row(R, yy, xx);
             const uint4 u = ld_chunk(rr);
-            if (yy < p.H && xx < p.W)
-              *reinterpret_cast<uint4*>(p.out + ((static_cast<size_t>(t.n) * p.H + yy) * p.W + xx) * p.Cout + co + h * 16 +
+            if (ok)
+              *reinterpret_cast<uint4*>(p.out + ((static_cast<size_t>(t.n) * p.out_H + yy) * p.out_W + xx) * p.Cout + co + h * 16 +
                                         sub * 4) = u;
           }
           __syncwarp();
@@ -218,10 +250,11 @@ __device__ __forceinline__ void epilogue_tile(const Params& p, const TileCoord& 
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const int rr = j * 8 + prow, R = rbase + rr;
-            const int yy = t.y0 + R / TW, xx = t.x0 + R % TW;
+            int yy, xx;
+            const bool ok = map_row(R, yy, xx);
             const uint4 u = ld_chunk(rr);
-            if (yy < p.H && xx < p.W)
-              *reinterpret_cast<uint4*>(dst + ((static_cast<size_t>(t.n) * p.H + yy) * p.out_pitch + p.out_lead + xx) * p.Cout +
+            if (ok)
+              *reinterpret_cast<uint4*>(dst + ((static_cast<size_t>(t.n) * p.out_H + yy) * p.out_pitch + p.out_lead + xx) * p.Cout +
                                         co + sub * 8) = u;
           }
           __syncwarp();
@@ -242,6 +275,12 @@ __device__ __forceinline__ void epilogue_tile(const Params& p, const TileCoord& 
           }
           if (p.residual) {
             const float4* r4 = reinterpret_cast<const float4*>(p.residual + pix * p.Cout + cb);
+            const float4 ra = __ldg(r4), rb = __ldg(r4 + 1);
+            f[0] += ra.x; f[1] += ra.y; f[2] += ra.z; f[3] += ra.w;
+            f[4] += rb.x; f[5] += rb.y; f[6] += rb.z; f[7] += rb.w;
+          }
+          if (p.bias_map) {
+            const float4* r4 = reinterpret_cast<const float4*>(p.bias_map + mpix * p.Cout + cb);
             const float4 ra = __ldg(r4), rb = __ldg(r4 + 1);
             f[0] += ra.x; f[1] += ra.y; f[2] += ra.z; f[3] += ra.w;
             f[4] += rb.x; f[5] += rb.y; f[6] += rb.z; f[7] += rb.w;
@@ -271,6 +310,7 @@ __device__ __forceinline__ void epilogue_tile(const Params& p, const TileCoord& 
               float a = __uint_as_float(v[g8 * 8 + i]) + bias_s[cb + i];
               a = a > 0.f ? a : a * p.slope;
               if (p.residual) a += __ldg(p.residual + pix * p.Cout + cb + i);
+              if (p.bias_map) a += __ldg(p.bias_map + mpix * p.Cout + cb + i);
               if (p.out) p.out[pix * p.Cout + cb + i] = a;
               if (p.out_hi) {
                 const __nv_bfloat16 hb = __float2bfloat16_rn(a);
@@ -292,7 +332,7 @@ __device__ __forceinline__ void epilogue_tile(const Params& p, const TileCoord& 
       uint4* zl = reinterpret_cast<uint4*>(p.out_lo + (opix - p.out_lead) * p.Cout);
       for (int i = 0; i < p.out_lead * p.Cout / 8; ++i) zh[i] = zl[i] = z;
     }
-    if (x == p.W - 1 && y == p.H - 1 && t.n == p.N - 1) {
+    if (x == p.out_W - 1 && y == p.out_H - 1 && t.n == p.N - 1) {
       uint4* zh = reinterpret_cast<uint4*>(p.out_hi + (opix + 1) * p.Cout);
       uint4* zl = reinterpret_cast<uint4*>(p.out_lo + (opix + 1) * p.Cout);
       for (int i = 0; i < p.out_tail * p.Cout / 8; ++i) zh[i] = zl[i] = z;
@@ -316,11 +356,10 @@ __global__ void __launch_bounds__(THREADS, 1) conv3x3_kernel(const __grid_consta
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int epi_warps = (blockDim.x >> 5) - 2;                // 8, or 4 when the launch has no room for 8 staging buffers
   for (int i = tid; i < MAX_COUT; i += blockDim.x) bias_s[i] = (p.bias && i < p.Cout) ? __ldg(p.bias + i) : 0.f;
-  const int tiles_y = (p.H + TILE_H - 1) / TILE_H, tiles_x = (p.W + TILE_W - 1) / TILE_W;
+  const int tiles_y = (p.H + p.tile_h - 1) / p.tile_h, tiles_x = (p.W + p.tile_w - 1) / p.tile_w;
   const int cog = p.Cout / p.groups;
   const int tiles_ng = (cog + BN - 1) / BN;
-  const int num_tiles = p.N * tiles_y * tiles_x * p.groups * tiles_ng;
-  const int num_kb = p.rows_px ? p.ks * p.rows_g : p.ks * p.ks * p.chunks_total;
+  const int num_tiles = p.N * tiles_y * tiles_x * p.nphase * p.groups * tiles_ng;
 
   if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
   if (tid == 0) {
@@ -352,6 +391,8 @@ __global__ void __launch_bounds__(THREADS, 1) conv3x3_kernel(const __grid_consta
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const TileCoord t = decode_tile<BN>(tile, p, tiles_y, tiles_x, tiles_ng);
         int kb = 0;
+        // bytes a stage receives: two A boxes of tile_w * tile_h rows x 128 B (rows beyond stay idle) + [Wh | Wl]
+        const uint32_t stage_tx = 2u * static_cast<uint32_t>(p.tile_w * p.tile_h) * 128u + 2u * W_TILE;
         if (p.rows_px) {
           // window-packed K: chunk (ky, g) = pixels [x*stride - pad + g*PX, +PX) x cin of input row y*stride - pad + ky
           for (int ky = 0; ky < p.ks; ++ky) {
@@ -359,7 +400,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv3x3_kernel(const __grid_consta
             for (int g = 0; g < p.rows_g; ++g, ++kb, ++it) {
               const int stage = it % STAGES;
               mbar_wait(&empty[stage], ((it / STAGES) & 1) ^ 1);
-              mbar_arrive_expect_tx(&full[stage], STAGE);
+              mbar_arrive_expect_tx(&full[stage], stage_tx);
               const uint32_t s0 = smem_u32(smem + stage * STAGE);
               const int xi = t.x0 + g * p.rows_px / p.stride;       // window-start index (row gap = left padding)
               tma_load_4d(s0, &maps.a_hi[0], &full[stage], 0, xi, yy, t.n);
@@ -370,16 +411,17 @@ __global__ void __launch_bounds__(THREADS, 1) conv3x3_kernel(const __grid_consta
           }
           continue;
         }
-        const int taps = p.ks * p.ks;
-        for (int tap = 0; tap < taps; ++tap) {
+        const int tap0 = p.ph_tap0[t.ph], tap1 = p.ph_tap0[t.ph + 1];
+        kb = tap0 * p.chunks_total;                      // K blocks of the packed weight are ordered by tap
+        for (int tap = tap0; tap < tap1; ++tap) {
           // input coordinate of the tile's first output pixel for this tap (TMA steps by `stride` inside the box)
-          const int yy = t.y0 * p.stride - p.pad + tap / p.ks, xx = t.x0 * p.stride - p.pad + tap % p.ks;
+          const int yy = t.y0 * p.stride + p.tap_dy[tap], xx = t.x0 * p.stride + p.tap_dx[tap];
           for (int s = 0; s < p.nsrc; ++s) {
             const int c_base = t.g * p.cig[s];
             for (int j = 0; j < p.chunks[s]; ++j, ++kb, ++it) {
               const int stage = it % STAGES;
               mbar_wait(&empty[stage], ((it / STAGES) & 1) ^ 1);
-              mbar_arrive_expect_tx(&full[stage], STAGE);
+              mbar_arrive_expect_tx(&full[stage], stage_tx);
               const uint32_t s0 = smem_u32(smem + stage * STAGE);
               tma_load_4d(s0, &maps.a_hi[s], &full[stage], c_base + j * BK, xx, yy, t.n);
               tma_load_4d(s0 + A_TILE, &maps.a_lo[s], &full[stage], c_base + j * BK, xx, yy, t.n);
@@ -403,6 +445,11 @@ __global__ void __launch_bounds__(THREADS, 1) conv3x3_kernel(const __grid_consta
       uint32_t it = 0, local = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
         const int buf = local & 1;
+        int num_kb = p.ks * p.rows_g;                     // window-packed K
+        if (!p.rows_px) {
+          const int ph = (tile / (tiles_ng * p.groups)) % p.nphase;
+          num_kb = (p.ph_tap0[ph + 1] - p.ph_tap0[ph]) * p.chunks_total;
+        }
         mbar_wait(&acc_empty[buf], ((local >> 1) & 1) ^ 1);
         tc_fence_after_sync();
         const uint32_t d = tbase + buf * Cfg<BN>::ACC_COLS;
@@ -436,8 +483,8 @@ __global__ void __launch_bounds__(THREADS, 1) conv3x3_kernel(const __grid_consta
       const TileCoord t = decode_tile<BN>(tile, p, tiles_y, tiles_x, tiles_ng);
       mbar_wait(&acc_full[buf], (local >> 1) & 1);
       tc_fence_after_sync();
-      epilogue_tile<BN, TILE_W>(p, t, tbase + (static_cast<uint32_t>(q * 32) << 16) + buf * Cfg<BN>::ACC_COLS, q * 32 + lane, cog,
-                                bias_s, c_begin, c_end, my_stage);
+      epilogue_tile<BN>(p, t, tbase + (static_cast<uint32_t>(q * 32) << 16) + buf * Cfg<BN>::ACC_COLS, q * 32 + lane, cog,
+                        bias_s, c_begin, c_end, my_stage, p.tile_w, p.tile_h);
       tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[buf]);
@@ -605,10 +652,11 @@ __global__ void __launch_bounds__(THREADS, 1) conv3x3_halo_kernel(const __grid_c
       t.n = tile / (tiles_x * tiles_y);
       t.g = 0;
       t.co0 = 0;
+      t.ph = t.oy = t.ox = 0;
       mbar_wait(&acc_full[buf], (local >> 1) & 1);
       tc_fence_after_sync();
-      epilogue_tile<BN, HTILE_W>(p, t, tbase + (static_cast<uint32_t>(q * 32) << 16) + buf * Cfg<BN>::ACC_COLS, q * 32 + lane,
-                                 p.Cout, bias_s, c_begin, c_end, my_stage);
+      epilogue_tile<BN>(p, t, tbase + (static_cast<uint32_t>(q * 32) << 16) + buf * Cfg<BN>::ACC_COLS, q * 32 + lane,
+                        p.Cout, bias_s, c_begin, c_end, my_stage, HTILE_W, HTILE_H);
       tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[buf]);
@@ -684,9 +732,18 @@ int launch_pack_rows(const float* x, void* hi, void* lo, int n, int c, int h, in
 int launch_conv3x3(int nsrc, const void* const* src_hi, const void* const* src_lo, const int* src_channels,
                    const void* w_hi, const void* w_lo, const float* bias, const float* residual, float* out,
                    void* out_hi, void* out_lo, int n, int h_in, int w_in, int cout, int groups, float slope, int ks,
-                   int stride, int pad, int in_rows, int out_lead, cudaStream_t stream) {
+                   int stride, int pad, int in_rows, int out_lead, cudaStream_t stream, const ConvGeom* geom) {
   using namespace conv;
-  const int h = (h_in + 2 * pad - ks) / stride + 1, w = (w_in + 2 * pad - ks) / stride + 1;   // output size
+  // GEMM grid = output size of the plain conv, or what the generalised geometry says
+  const int h = geom ? geom->grid_h : (h_in + 2 * pad - ks) / stride + 1;
+  const int w = geom ? geom->grid_w : (w_in + 2 * pad - ks) / stride + 1;
+  const int tile_w = geom ? geom->tile_w : TILE_W, tile_h = geom ? geom->tile_h : TILE_H;
+  const int ntaps = geom ? geom->ntaps : ks * ks;
+  if (ntaps < 1 || ntaps > 64 || tile_w < 1 || tile_h < 1 || tile_w * tile_h > BM || tile_w * stride > 256 ||
+      tile_h * stride > 256 || (geom && (geom->nphase < 1 || geom->nphase > 9 || geom->ostep < 1))) {
+    set_error("conv: unsupported geometry (taps=%d tile=%dx%d stride=%d)", ntaps, tile_w, tile_h, stride);
+    return -2;
+  }
   EncodeTiledFn enc = get_encode();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled is not available from the driver");
@@ -701,8 +758,8 @@ int launch_conv3x3(int nsrc, const void* const* src_hi, const void* const* src_l
   // few tiles (single-clip propagation steps: 51 pixel tiles on 148 SMs): halve the N tile so that twice as many SMs
   // work; a tile then costs (64 + 55) instead of (128 + 64) tensor-pipe cycles per K step (tools/mma_rate_probe.cu)
   if (bn == 128 && cog % 64 == 0 && !in_rows) {
-    const long long t128 = static_cast<long long>(n) * ((h + TILE_H - 1) / TILE_H) * ((w + TILE_W - 1) / TILE_W) * groups *
-                           ((cog + 127) / 128);
+    const long long t128 = static_cast<long long>(n) * ((h + tile_h - 1) / tile_h) * ((w + tile_w - 1) / tile_w) * groups *
+                           ((cog + 127) / 128) * (geom ? geom->nphase : 1);
     if (2 * t128 <= num_sms()) bn = 64;
   }
   Maps maps;
@@ -714,7 +771,20 @@ int launch_conv3x3(int nsrc, const void* const* src_hi, const void* const* src_l
   p.chunks_total = 0;
   p.rows_px = p.rows_g = 0;
   p.out_lead = out_lead;
-  p.out_pitch = conv_rows_pitch(w, out_lead, cout);   // == w + out_lead: split outputs have >= 8 channels
+  p.tile_w = tile_w; p.tile_h = tile_h;
+  p.bias_map = nullptr;
+  if (geom) {
+    p.nphase = geom->nphase; p.ostep = geom->ostep; p.out_H = geom->out_h; p.out_W = geom->out_w;
+    p.bias_map = geom->bias_map;
+    for (int i = 0; i < ntaps; ++i) { p.tap_dy[i] = geom->tap_dy[i]; p.tap_dx[i] = geom->tap_dx[i]; }
+    for (int i = 0; i < geom->nphase; ++i) { p.ph_tap0[i] = geom->ph_tap0[i]; p.ph_oy[i] = geom->ph_oy[i]; p.ph_ox[i] = geom->ph_ox[i]; }
+    p.ph_tap0[geom->nphase] = geom->ph_tap0[geom->nphase];
+  } else {
+    p.nphase = 1; p.ostep = 1; p.out_H = h; p.out_W = w;
+    for (int i = 0; i < ntaps; ++i) { p.tap_dy[i] = static_cast<int8_t>(i / ks - pad); p.tap_dx[i] = static_cast<int8_t>(i % ks - pad); }
+    p.ph_tap0[0] = 0; p.ph_tap0[1] = static_cast<uint8_t>(ntaps); p.ph_oy[0] = p.ph_ox[0] = 0;
+  }
+  p.out_pitch = conv_rows_pitch(p.out_W, out_lead, cout);   // == out_W + out_lead: split outputs have >= 8 channels
   p.out_tail = out_lead ? conv_rows_tail(out_lead, cout) : 0;
   for (int i = 0; i < MAX_SRC; ++i) p.cig[i] = p.chunks[i] = 0;
   if (in_rows) {
@@ -750,7 +820,7 @@ int launch_conv3x3(int nsrc, const void* const* src_hi, const void* const* src_l
   int chunks_all = 0;
   for (int i = 0; i < nsrc; ++i) chunks_all += (src_channels[i] / groups + BK - 1) / BK;
   int halo_slots = 0, halo_epi = 8;
-  if (!in_rows && ks == 3 && stride == 1 && pad == 1 && groups == 1 && cout <= 64) {
+  if (!geom && !in_rows && ks == 3 && stride == 1 && pad == 1 && groups == 1 && cout <= 64) {
     static const bool enabled = [] {
       const char* e = getenv("E2F_CONV_HALO");
       return !(e && e[0] == '0');
@@ -772,8 +842,8 @@ int launch_conv3x3(int nsrc, const void* const* src_hi, const void* const* src_l
     const cuuint64_t strides[3] = {static_cast<cuuint64_t>(c) * 2, static_cast<cuuint64_t>(w_in) * c * 2,
                                    static_cast<cuuint64_t>(h_in) * w_in * c * 2};
     // the box spans TILE*stride input elements and is traversed with elementStrides = stride: TILE elements land
-    const cuuint32_t box[4] = {BK, static_cast<cuuint32_t>(halo_slots ? HALO_W : TILE_W * stride),
-                               static_cast<cuuint32_t>(halo_slots ? HALO_H : TILE_H * stride), 1};
+    const cuuint32_t box[4] = {BK, static_cast<cuuint32_t>(halo_slots ? HALO_W : tile_w * stride),
+                               static_cast<cuuint32_t>(halo_slots ? HALO_H : tile_h * stride), 1};
     for (int part = 0; part < 2; ++part) {
       CUresult r = enc(part ? &maps.a_lo[i] : &maps.a_hi[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4,
                        const_cast<void*>(part ? src_lo[i] : src_hi[i]), dims, strides, box, estr4,
@@ -787,7 +857,7 @@ int launch_conv3x3(int nsrc, const void* const* src_hi, const void* const* src_l
     }
   }
   {
-    const int kpad = (in_rows ? ks * p.rows_g : ks * ks * p.chunks_total) * BK;
+    const int kpad = (in_rows ? ks * p.rows_g : ntaps * p.chunks_total) * BK;
     const cuuint64_t dims[2] = {static_cast<cuuint64_t>(kpad), static_cast<cuuint64_t>(cout)};
     const cuuint64_t strides[1] = {static_cast<cuuint64_t>(kpad) * 2};
     const cuuint32_t box[2] = {BK, static_cast<cuuint32_t>(bn)};
@@ -840,9 +910,9 @@ int launch_conv3x3(int nsrc, const void* const* src_hi, const void* const* src_l
     count_launch();
     return static_cast<int>(cudaGetLastError());
   }
-  const int tiles_y = (h + TILE_H - 1) / TILE_H, tiles_x = (w + TILE_W - 1) / TILE_W;
+  const int tiles_y = (h + tile_h - 1) / tile_h, tiles_x = (w + tile_w - 1) / tile_w;
   const int tiles_ng = (cout / groups + bn - 1) / bn;
-  const long long tiles = static_cast<long long>(n) * tiles_y * tiles_x * groups * tiles_ng;
+  const long long tiles = static_cast<long long>(n) * tiles_y * tiles_x * p.nphase * groups * tiles_ng;
   if (tiles == 0) return 0;
   if (tiles > 0x7FFFFFFFLL) {
     set_error("conv3x3: too many tiles");

@@ -69,10 +69,24 @@ int launch_linear_bf16x3(const void* a_hi, const void* a_lo, const void* w_hi, c
                          const float* residual, void* out, int m, int n, int k, int out_dtype, int block_n,
                          cudaStream_t stream);
 
+// Optional generalised geometry of the implicit-GEMM conv ("gather conv", see conv.cu Params): explicit tap offsets,
+// output phases and tile shape.  nullptr = the plain k x k / stride / pad conv.
+struct ConvGeom {
+  int grid_h, grid_w;            // GEMM grid (per phase): one accumulator row per grid pixel
+  int out_h, out_w;              // output image; grid pixel (y, x) of phase ph -> (y*ostep + ph_oy[ph], x*ostep + ph_ox[ph])
+  int tile_w, tile_h;            // grid pixels per tile, tile_w * tile_h <= 128
+  int ntaps, nphase, ostep;
+  const int8_t* tap_dy;          // [ntaps] input offset of tap i relative to (y*stride, x*stride)
+  const int8_t* tap_dx;
+  const uint8_t* ph_tap0;        // [nphase + 1]
+  const uint8_t* ph_oy;          // [nphase]
+  const uint8_t* ph_ox;
+  const float* bias_map;         // fp32 [out_h][out_w][cout] or null
+};
 int launch_conv3x3(int nsrc, const void* const* src_hi, const void* const* src_lo, const int* src_channels,
                    const void* w_hi, const void* w_lo, const float* bias, const float* residual, float* out,
                    void* out_hi, void* out_lo, int n, int h_in, int w_in, int cout, int groups, float slope, int ks,
-                   int stride, int pad, int in_rows, int out_lead, cudaStream_t stream);
+                   int stride, int pad, int in_rows, int out_lead, cudaStream_t stream, const ConvGeom* geom = nullptr);
 int conv_rows_tail(int lead, int channels);
 int conv_rows_pitch(int w, int lead, int channels);
 int launch_pack_rows(const float* x, void* hi, void* lo, int n, int c, int h, int w, int cin, int lead,

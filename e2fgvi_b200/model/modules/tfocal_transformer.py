@@ -35,8 +35,8 @@ class SoftSplit(nn.Module):
     def forward(self, x, b, output_size=None):
         output_size = output_size or self.output_size
         f_h, f_w = _token_grid(output_size, self.kernel_size, self.stride, self.padding)
-        feat = ops.linear(ops.t2t_unfold(x, self.kernel_size, self.stride, self.padding, out="split"),
-                          self.embedding.weight, self.embedding.bias)
+        # unfold + Linear == a 7x7 / stride-3 conv: one implicit-GEMM launch, the 49x unfolded operand never exists
+        feat = ops.soft_split(x, self.embedding.weight, self.embedding.bias, self.kernel_size, self.stride, self.padding)
         return feat.view(b, -1, f_h, f_w, feat.size(2))
 
 
@@ -58,15 +58,16 @@ class SoftComp(nn.Module):
         """``residual`` (b*t, C, H, W), optional: added to the result by the fold kernel (base model) or the conv
         epilogue (HQ) — the ``enc_feat + trans_feat`` of e2fgvi.py:263; the result is then channels_last."""
         output_size = output_size or self.output_size
-        b_, _, _, _, c_ = x.shape
-        feat = ops.linear(x.view(b_, -1, c_), self.embedding.weight, self.embedding.bias)
-        b, _, c = feat.size()
+        b_, t_, f_h, f_w, c_ = x.shape
+        # Linear + fold == the transposed 7x7 / stride-3 conv: one implicit-GEMM launch over nine output phases; the
+        # 6272-wide token matrix and the fold pass never exist
+        tokens = x.view(b_ * t_, f_h, f_w, c_)
         if self.hq:
-            feat = ops.t2t_fold(feat.view(b * t, -1, c), output_size, self.kernel_size, self.stride, self.padding,
-                                channels_last=residual is not None)
+            feat = ops.soft_comp(tokens, self.embedding.weight, self.embedding.bias, output_size, self.kernel_size,
+                                 self.stride, self.padding, out="split")
             return ops.conv3x3([feat], self.bias_conv.weight, self.bias_conv.bias, residual=residual)
-        return ops.t2t_fold(feat.view(b * t, -1, c), output_size, self.kernel_size, self.stride, self.padding,
-                            bias=self.bias, residual=residual, channels_last=residual is not None)
+        return ops.soft_comp(tokens, self.embedding.weight, self.embedding.bias, output_size, self.kernel_size,
+                             self.stride, self.padding, bias_map_extra=self.bias, residual=residual)
 
 
 class FusionFeedForward(nn.Module):

@@ -791,6 +791,182 @@ def conv3x3(sources, weight, bias=None, groups=1, negative_slope=1.0, residual=N
     return t32 if out == "f32" else sp if out == "split" else (t32, sp)
 
 
+# ------------------------------------------------------------------------------------------------- SoftSplit / SoftComp
+_DERIVED = {}   # (id(param), tag...) -> (weakref, (version, data_ptr) tuple, value): weight-derived operands, per parameter
+
+
+def _derived(params, tag, build):
+    """Cache of operands derived from one or more nn.Parameters (packed weights, folded bias maps); rebuilt when any
+    of them changes version or address, dropped when the first one dies."""
+    key = (tuple(id(p) for p in params),) + tuple(tag)
+    stamp = tuple((p._version, p.data_ptr()) for p in params)
+    hit = _DERIVED.get(key)
+    if hit is None or any(r() is not p for r, p in zip(hit[0], params)) or hit[1] != stamp:
+        val = build()
+        if hit is None or hit[0][0]() is not params[0]:
+            weakref.finalize(params[0], _DERIVED.pop, key, None)
+        hit = (tuple(weakref.ref(p) for p in params), stamp, val)
+        _DERIVED[key] = hit
+    return hit[2]
+
+
+def _best_tile(gh, gw, stride):
+    """(tile_w, tile_h) with tile_w * tile_h <= 128 that wastes the fewest accumulator rows on a gh x gw GEMM grid
+    (12 x 10 tiles the 20x36 and 60x108 token grids exactly; 18 x 7 the 90x162 one)."""
+    best, best_cost = (16, 8), None
+    for tw in range(1, min(gw, 128, 256 // stride) + 1):
+        th = min(128 // tw, gh, 256 // stride)
+        cost = -(-gh // th) * -(-gw // tw)                 # number of 128-row tiles
+        key = (cost, abs(tw - th), -tw * th)            # fewest tiles, then the squarest (best TMA box / L2 reuse)
+        if best_cost is None or key < best_cost:
+            best, best_cost = (tw, th), key
+    return best
+
+
+def _as_split_nhwc(x):
+    if isinstance(x, SplitNHWC):
+        return x
+    return split_nhwc(x)
+
+
+def _conv_gather(src, w_hi, w_lo, bias, bias_map, residual, out, n, h_in, w_in, cout, stride, grid, taps, phases, ostep,
+                 out_size, flops):
+    """One launch of e2f_conv_gather_bf16x3.  taps: list of (dy, dx); phases: list of (first tap, oy, ox)."""
+    gh, gw = grid
+    oh, ow = out_size
+    tw, th = _best_tile(gh, gw, stride)
+    dev = src.hi.device
+    want_f32, want_split = out in ("f32", "both"), out in ("split", "both")
+    if not (want_f32 or want_split):
+        raise ValueError("out must be 'f32', 'split' or 'both'")
+    o32 = torch.empty((n, oh, ow, cout), dtype=torch.float32, device=dev) if want_f32 else None
+    ohi = torch.empty((n, oh, ow, cout), dtype=torch.bfloat16, device=dev) if want_split else None
+    olo = torch.empty((n, oh, ow, cout), dtype=torch.bfloat16, device=dev) if want_split else None
+    import ctypes
+    nt, nph = len(taps), len(phases)
+    dy = (ctypes.c_int8 * nt)(*[t[0] for t in taps])
+    dx = (ctypes.c_int8 * nt)(*[t[1] for t in taps])
+    tap0 = (ctypes.c_uint8 * (nph + 1))(*([p[0] for p in phases] + [nt]))
+    oy = (ctypes.c_uint8 * nph)(*[p[1] for p in phases])
+    ox = (ctypes.c_uint8 * nph)(*[p[2] for p in phases])
+    hi_arr = (_lib._vp * 1)(src.hi.data_ptr())
+    lo_arr = (_lib._vp * 1)(src.lo.data_ptr())
+    ch_arr = (_lib._i * 1)(src.hi.shape[-1])
+    b32 = None if bias is None else bias.detach().float().contiguous()
+    res = None if residual is None else residual.permute(0, 2, 3, 1).contiguous().float()   # no-op if channels_last
+    with _timed("conv3x3_bf16x3", flops):
+        st = _lib.load().e2f_conv_gather_bf16x3(
+            1, hi_arr, lo_arr, ch_arr, w_hi.data_ptr(), w_lo.data_ptr(), None if b32 is None else b32.data_ptr(),
+            None if bias_map is None else bias_map.data_ptr(), None if res is None else res.data_ptr(),
+            None if o32 is None else o32.data_ptr(), None if ohi is None else ohi.data_ptr(),
+            None if olo is None else olo.data_ptr(), n, h_in, w_in, cout, 1.0, stride, gh, gw, tw, th, nt, dy, dx, nph,
+            tap0, oy, ox, ostep, oh, ow, _stream())
+    _lib.check(st, "e2f_conv_gather_bf16x3")
+    t32 = o32.permute(0, 3, 1, 2) if want_f32 else None
+    sp = SplitNHWC(ohi, olo, (n, cout, oh, ow)) if want_split else None
+    return t32 if out == "f32" else sp if out == "split" else (t32, sp)
+
+
+def soft_split(x, weight, bias, kernel_size, stride, padding):
+    """SoftSplit.forward (tfocal_transformer.py:39-46): ``Linear(unfold(x, k, s, p))`` evaluated as the k x k / stride-s
+    convolution it is — an implicit GEMM whose A operand is fetched by TMA straight from the NHWC feature map; the
+    k*k-times larger unfolded token matrix is never built.
+
+    x (BT,C,H,W) fp32 (any memory format) or ``SplitNHWC``; weight (hidden, C*k*k) = ``ss.embedding.weight``;
+    bias (hidden,).  Returns tokens (BT, fh*fw, hidden) fp32 — exactly ``embedding(unfold(x).permute(0, 2, 1))``."""
+    (k, k2), (s, s2), (p, p2) = _pair(kernel_size), _pair(stride), _pair(padding)
+    if k != k2 or s != s2 or p != p2:
+        raise NotImplementedError("square kernel / stride / padding only (E2FGVI uses 7 / 3 / 3)")
+    src = _as_split_nhwc(x)
+    n, c, h, w = src.shape
+    hidden = weight.shape[0]
+    if weight.shape[1] != c * k * k or k * k > 64 or c % 8:
+        raise ValueError(f"soft_split: weight {tuple(weight.shape)} does not match C={c}, k={k}")
+    _need_cuda(weight, bias)
+    fh, fw = (h + 2 * p - k) // s + 1, (w + 2 * p - k) // s + 1
+    w_hi, w_lo = _derived([weight], ("soft_split", c, k),
+                          lambda: pack_conv3x3_weight(weight.detach().view(hidden, c, k, k), [c], 1))
+    taps = [(ky - p, kx - p) for ky in range(k) for kx in range(k)]
+    tok = _conv_gather(src, w_hi, w_lo, bias, None, None, "f32", n, h, w, hidden, s, (fh, fw), taps, [(0, 0, 0)], 1,
+                       (fh, fw), 2.0 * n * fh * fw * hidden * c * k * k)
+    return tok.permute(0, 2, 3, 1).reshape(n, fh * fw, hidden)       # NHWC storage: a view
+
+
+def _soft_comp_tables(k, s, p):
+    """Phases and taps of the transposed conv that Linear + fold(k, s, p) is, for p == s (E2FGVI: 7 / 3 / 3): output
+    pixel (s*a + ry, s*b + rx) sums token (a + 1 - dy, b + 1 - dx) times the (ky, kx) = (s*dy + ry, s*dx + rx) slice
+    of the weight over all dy, dx with ky, kx < k.  Returns (taps [(dy_tok, dx_tok)], phases [(tap0, ry, rx)],
+    kernel positions [(ky, kx)] in tap order)."""
+    if p != s:
+        raise NotImplementedError("soft_comp: the phase decomposition is implemented for padding == stride (7 / 3 / 3)")
+    taps, phases, kpos = [], [], []
+    for ry in range(s):
+        for rx in range(s):
+            phases.append((len(taps), ry, rx))
+            for dy in range((k - 1 - ry) // s + 1):
+                for dx in range((k - 1 - rx) // s + 1):
+                    taps.append((1 - dy, 1 - dx))
+                    kpos.append((s * dy + ry, s * dx + rx))
+    return taps, phases, kpos
+
+
+def soft_comp(tokens, weight, bias, output_size, kernel_size, stride, padding, bias_map_extra=None, residual=None,
+              out="f32"):
+    """SoftComp.forward up to (and including) the fold (tfocal_transformer.py:65-72, _hq.py:67-79):
+    ``fold(Linear(tokens))`` evaluated as the transposed convolution it is, one implicit-GEMM launch over the nine
+    output phases; the (C*k*k)-wide token matrix and the fold pass never exist.
+
+    tokens (BT, fh, fw, hidden) fp32 or ``SplitMat``; weight (C*k*k, hidden) = ``sc.embedding.weight``; bias (C*k*k,);
+    ``bias_map_extra``: the base model's ``sc.bias`` (C, H, W) parameter or None; ``residual`` (BT, C, H, W) fp32 added
+    in the epilogue (enc_feat + trans_feat, e2fgvi.py:263).  Returns (BT, C, H, W) fp32 channels_last (out="f32"),
+    a ``SplitNHWC`` (out="split", operand of the HQ model's bias_conv) or both."""
+    (k, k2), (s, s2), (p, p2) = _pair(kernel_size), _pair(stride), _pair(padding)
+    if k != k2 or s != s2 or p != p2:
+        raise NotImplementedError("square kernel / stride / padding only (E2FGVI uses 7 / 3 / 3)")
+    h, w = output_size
+    fh, fw = (h + 2 * p - k) // s + 1, (w + 2 * p - k) // s + 1
+    hidden = weight.shape[1]
+    c = weight.shape[0] // (k * k)
+    if isinstance(tokens, SplitMat):
+        hi, lo = tokens.hi, tokens.lo
+    else:
+        _need_cuda(tokens)
+        hi, lo = split_bf16(tokens)
+    n = hi.numel() // (fh * fw * hidden)
+    if hi.numel() != n * fh * fw * hidden or hidden % 64 or c * k * k != weight.shape[0]:
+        raise ValueError(f"soft_comp: tokens {tuple(hi.shape)} / weight {tuple(weight.shape)} do not match output_size "
+                         f"{output_size}")
+    _need_cuda(weight, bias, bias_map_extra, residual)
+    if residual is not None and tuple(residual.shape) != (n, c, h, w):
+        raise ValueError(f"residual {tuple(residual.shape)} != {(n, c, h, w)}")
+    taps, phases, kpos = _soft_comp_tables(k, s, p)
+    src = SplitNHWC(hi.view(n, fh, fw, hidden), lo.view(n, fh, fw, hidden), (n, hidden, fh, fw))
+
+    def pack():
+        order = torch.tensor([ky * k + kx for ky, kx in kpos], device=weight.device)
+        wp = weight.detach().float().view(c, k * k, hidden)[:, order, :].reshape(c, k * k * hidden)
+        return split_bf16(wp)
+
+    w_hi, w_lo = _derived([weight], ("soft_comp", k, s), pack)
+
+    def fold_bias():
+        # fold of the Linear bias: every pixel receives b[c, ky, kx] from each token patch that covers it (border
+        # pixels from fewer patches) + the base model's learned (C, H, W) bias map; layout [H][W][C]
+        F = torch.nn.functional
+        m = torch.zeros((1, c, h, w), dtype=torch.float32, device=weight.device)
+        if bias is not None:
+            cols = bias.detach().float().view(1, c * k * k, 1).expand(1, c * k * k, fh * fw)
+            m = F.fold(cols, (h, w), (k, k), padding=(p, p), stride=(s, s))
+        if bias_map_extra is not None:
+            m = m + bias_map_extra.detach().float().view(1, c, h, w)
+        return m[0].permute(1, 2, 0).contiguous()
+
+    bparams = [q for q in (bias, bias_map_extra) if q is not None]
+    bias_map = _derived(bparams, ("soft_comp_bias", h, w, k, s), fold_bias) if bparams else None
+    return _conv_gather(src, w_hi, w_lo, None, bias_map, residual, out, n, fh, fw, c, 1, (fh, fw), taps, phases, s,
+                        (h, w), 2.0 * n * fh * fw * hidden * c * k * k)
+
+
 def attention_flops(B, T, H, W, C, window_size, expand_size, focal_window, use_pooled=True):
     """Algorithmic FLOPs of one attention launch as the REFERENCE counts keys: QK^T + PV over
     T*(own window + listed ring keys incl. duplicates + fh*fw pooled keys incl. masked ones) keys per query."""

@@ -228,6 +228,31 @@ int e2f_conv2d_rows_bf16x3(int nsrc, const void* const* src_hi, const void* cons
                            float* out, void* out_hi, void* out_lo, int out_lead, int n, int h, int w, int cout, int groups,
                            float leaky_slope, int ksize, int stride, int pad, void* stream);
 
+/* "Gather conv": the same implicit GEMM with an explicit TAP TABLE, OUTPUT PHASES and tile shape (groups == 1).
+ * Replaces, without ever building the unfolded operand:
+ *   - SoftSplit (model/modules/tfocal_transformer.py:39-46; HQ _hq.py:39-46): F.unfold(7x7, stride 3, pad 3) + nn.Linear
+ *     IS a 7x7 / stride-3 conv 128 -> 512: one phase, 49 taps (dy = ky - 3, dx = kx - 3), stride = 3, GEMM grid = the
+ *     token grid, tokens written as the NHWC output [BT][fh][fw][512].  The 49x larger unfolded token matrix
+ *     (1.3 GB per call at 8 clips) does not exist.
+ *   - SoftComp (tfocal_transformer.py:65-72; _hq.py:67-79): nn.Linear(512 -> 49*128) + F.fold IS the transposed conv.
+ *     Output pixel (3a + ry, 3b + rx) sums token (a + 1 - dy, b + 1 - dx) times W[(c, 3dy + ry, 3dx + rx), :] over the
+ *     taps with 3dy + ry <= 6, 3dx + rx <= 6: nine phases (ry, rx) with 9 / 6 / 4 taps, stride = 1, GEMM grid = token
+ *     grid, ostep = 3.  The 6272-wide token matrix and the fold pass do not exist; the folded Linear bias (+ the base
+ *     model's sc.bias[c, y, x], tfocal_transformer.py:60-63) arrives as `bias_map`, `enc_feat + trans_feat`
+ *     (e2fgvi.py:263) as `residual`.
+ * Tap i reads input pixel (y*stride + tap_dy[i], x*stride + tap_dx[i]) (zero outside); phase ph owns taps
+ * [ph_tap0[ph], ph_tap0[ph+1]) and writes output pixel (y*ostep + ph_oy[ph], x*ostep + ph_ox[ph]) of the
+ * out_h x out_w image for every GEMM-grid pixel (y, x) in grid_h x grid_w.  Weights: [Cout][ntaps * T * 64] bf16
+ * (hi, lo), tap-major (in table order), then source, then 64-channel chunk (T = chunks over all sources).
+ * tile_w * tile_h <= 128 grid pixels per tile (12 x 10 tiles the 20x36 / 60x108 / 90x162 token grids exactly).
+ * bias: per-channel [Cout] or NULL; bias_map: fp32 [out_h][out_w][Cout] or NULL; residual: fp32 NHWC of the output. */
+int e2f_conv_gather_bf16x3(int nsrc, const void* const* src_hi, const void* const* src_lo, const int* src_channels,
+                           const void* w_hi, const void* w_lo, const float* bias, const float* bias_map,
+                           const float* residual, float* out, void* out_hi, void* out_lo, int n, int h_in, int w_in,
+                           int cout, float leaky_slope, int stride, int grid_h, int grid_w, int tile_w, int tile_h,
+                           int ntaps, const int8_t* tap_dy, const int8_t* tap_dx, int nphase, const uint8_t* ph_tap0,
+                           const uint8_t* ph_oy, const uint8_t* ph_ox, int ostep, int out_h, int out_w, void* stream);
+
 /* Fused prologue of one propagation step — replaces feat_prop.py:106-126 up to the offset-head conv:
  * the two feature warps, the second-order flow (flow_n1 + warp(flow_prev, flow_n1)), the operand splits of the offset
  * head's conv sources and the fp16 group-major DCN input, in one launch.

@@ -122,19 +122,38 @@ def _linear(x, weight, bias=None, residual=None, out_dtype=torch.float32, tile_h
     return (y if residual is None else y + residual.reshape(y.shape)).to(out_dtype if x.is_cuda else torch.float32)
 
 
+def _soft_split(x, weight, bias, kernel_size, stride, padding):
+    F = torch.nn.functional
+    return F.linear(F.unfold(x, kernel_size, padding=padding, stride=stride).permute(0, 2, 1), weight, bias)
+
+
+def _soft_comp(tokens, weight, bias, output_size, kernel_size, stride, padding, bias_map_extra=None, residual=None,
+               out="f32"):
+    F = torch.nn.functional
+    n = tokens.shape[0]
+    feat = F.linear(tokens.reshape(n, -1, tokens.shape[-1]), weight, bias)
+    y = F.fold(feat.permute(0, 2, 1), output_size, kernel_size, padding=padding, stride=stride)
+    if bias_map_extra is not None:
+        y = y + bias_map_extra
+    if residual is not None:
+        y = y + residual
+    return (y, y) if out == "both" else y
+
+
 @contextlib.contextmanager
 def oracle_ops():
     saved = {n: getattr(ops, n) for n in ("flow_warp", "pack_dcn_weight", "deform_align_fused",
                                           "modulated_deform_conv2d", "focal_window_attention", "t2t_unfold",
                                           "t2t_fold", "linear", "conv3x3", "split_nhwc", "upsample2x_split",
                                           "layer_norm", "dcn_pack_input", "t2t_fold_unfold", "pack_rows", "window_pool",
-                                          "prop_prologue")}
+                                          "prop_prologue", "soft_split", "soft_comp")}
     ops.flow_warp, ops.pack_dcn_weight, ops.deform_align_fused = _flow_warp, _pack, _fused
     ops.modulated_deform_conv2d, ops.focal_window_attention = _mdcn, _attention
     ops.t2t_unfold, ops.t2t_fold, ops.linear, ops.t2t_fold_unfold = _unfold, _fold, _linear, _fold_unfold
     ops.conv3x3, ops.split_nhwc, ops.pack_rows, ops.window_pool = _conv3x3, _split_nhwc, _pack_rows, _window_pool
     ops.upsample2x_split, ops.layer_norm, ops.dcn_pack_input = _upsample, _layer_norm, _dcn_pack_input
     ops.prop_prologue = _prop_prologue
+    ops.soft_split, ops.soft_comp = _soft_split, _soft_comp
     try:
         yield
     finally:

@@ -605,6 +605,54 @@ def test_window_pool(cuda, shape):
                         lin.weight.to(cuda), lin.bias.to(cuda), (wh, ww))
 
 
+# ------------------------------------------------------------------------------------------ SoftSplit / SoftComp as gather convs
+@pytest.mark.parametrize("shape", [(3, 128, 60, 108), (2, 64, 15, 27), (1, 128, 45, 81), (2, 128, 30, 54)])
+def test_soft_split_matches_unfold_linear(cuda, shape):
+    """ops.soft_split (7x7 / stride-3 implicit-GEMM conv, tile 12x10 / 18x7, TMA element strides 3) against
+    tfocal_transformer.py:39-46 evaluated literally in fp64 on the CPU."""
+    import torch.nn.functional as F
+    n, c, h, w = shape
+    g = torch.Generator().manual_seed(31)
+    x = torch.randn(n, c, h, w, generator=g)
+    lin = torch.nn.Linear(c * 49, 512)
+    want = F.linear(F.unfold(x.double(), 7, padding=3, stride=3).permute(0, 2, 1), lin.weight.double(), lin.bias.double())
+    lin = lin.to(cuda)
+    with torch.no_grad():
+        got = ops.soft_split(x.to(cuda).contiguous(memory_format=torch.channels_last), lin.weight, lin.bias, 7, 3, 3)
+    assert got.shape == want.shape and got.dtype == torch.float32
+    # bf16 3-term split: ~2^-17 relative per product, K = 49*C terms
+    assert _rel(got.cpu(), want) < 5e-5
+
+
+@pytest.mark.parametrize("shape", [(3, 60, 108), (2, 15, 27), (1, 45, 81)])
+@pytest.mark.parametrize("mode", ["base", "hq"])
+def test_soft_comp_matches_linear_fold(cuda, shape, mode):
+    """ops.soft_comp (nine-phase transposed conv, bias map, residual, fp32 or split output) against
+    tfocal_transformer.py:65-72 / _hq.py:67-79 evaluated literally in fp64 on the CPU."""
+    import torch.nn.functional as F
+    n, h, w = shape
+    fh, fw = (h - 1) // 3 + 1, (w - 1) // 3 + 1
+    g = torch.Generator().manual_seed(32)
+    tok = torch.randn(n, fh, fw, 512, generator=g)
+    lin = torch.nn.Linear(512, 128 * 49)
+    extra = torch.nn.Parameter(torch.randn(128, h, w, generator=g) * 0.3)
+    res = torch.randn(n, 128, h, w, generator=g)
+    want = F.fold(F.linear(tok.double().view(n, fh * fw, 512), lin.weight.double(), lin.bias.double()).permute(0, 2, 1),
+                  (h, w), 7, padding=3, stride=3)
+    lin = lin.to(cuda)
+    with torch.no_grad():
+        if mode == "base":
+            want = want + extra.double() + res.double()
+            got = ops.soft_comp(tok.to(cuda), lin.weight, lin.bias, (h, w), 7, 3, 3,
+                                bias_map_extra=torch.nn.Parameter(extra.detach().to(cuda)),
+                                residual=res.to(cuda).contiguous(memory_format=torch.channels_last))
+        else:
+            sp = ops.soft_comp(tok.to(cuda), lin.weight, lin.bias, (h, w), 7, 3, 3, out="split")
+            got = (sp.hi.float() + sp.lo.float()).permute(0, 3, 1, 2)
+    assert got.shape == want.shape
+    assert _rel(got.cpu(), want) < 5e-5
+
+
 # ------------------------------------------------------------------------------------------ propagation vs oracle taps
 @pytest.mark.parametrize("fused", [True, False])
 def test_bidirectional_propagation_matches_oracle_taps(cuda, fused):
