@@ -283,7 +283,6 @@ class Measurement:
         with torch.no_grad():
             self._loop(self.warmup, self.dev_sets)
             self.sync()
-            prof = ops.profile_kernels(True) if profile else None
             sampler = ClockSampler(self.dev.index) if (sample_clocks and self.rank == 0) else None
             n0 = ops.launch_count()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -294,9 +293,19 @@ class Measurement:
             self.sync()
             res["launches"] = ops.launch_count() - n0
             res["clocks"] = sampler.stop() if sampler else None
-            if profile:
-                ops.profile_kernels(False)
             ms = e0.elapsed_time(e1)
+            # ---- per-kernel live timing in a SEPARATE pass over the same steps: two CUDA events per launch cost host time
+            #      that would distort a launch-bound workload (one clip per call) if it ran inside the region above
+            prof, ms_prof = None, None
+            if profile:
+                prof = ops.profile_kernels(True)
+                p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                p0.record()
+                self._loop(self.steps, self.dev_sets)
+                p1.record()
+                self.sync()
+                ops.profile_kernels(False)
+                ms_prof = p0.elapsed_time(p1)
             # ---- end to end through the public API with HOST buffers
             self._loop(2, self.host_sets, to_host=True)
             self.sync()
@@ -312,7 +321,7 @@ class Measurement:
         ms, ms_e2e = float(t[0]), float(t[1])
         frames = self.num_clips * self.T * self.steps
         nbytes = self.B * self.T * 3 * self.H * self.W * 4 * self.world
-        res.update(ms=ms, ms_per_step=ms / self.steps, value=frames / (ms * 1e-3), prof=prof,
+        res.update(ms=ms, ms_per_step=ms / self.steps, value=frames / (ms * 1e-3), prof=prof, ms_prof=ms_prof,
                    e2e={"value": frames / (ms_e2e * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": nbytes,
                         "d2h_bytes_per_step": nbytes, "ms_per_step": ms_e2e / self.steps})
         log(f"{self.name}: {res['ms_per_step']:.2f} ms/step device, {ms_e2e / self.steps:.2f} ms/step e2e")
@@ -412,7 +421,7 @@ def main():
     log(f"rank {rank}/{world}: model ready, workload={name}, host cores={host_cores()}")
     head = Measurement(name, model, dev, rank, world, B, args.steps, args.warmup)
     main_res = head.run(sample_clocks=True)
-    kernels = kernel_rooflines(main_res["prof"], main_res["ms"], traffic_for(name)) if rank == 0 else {}
+    kernels = kernel_rooflines(main_res["prof"], main_res["ms_prof"], traffic_for(name)) if rank == 0 else {}
     one_clip = head.dev_sets[0][:1].clone()
     head.free()
 
@@ -431,7 +440,7 @@ def main():
                          "ms_per_step": r["ms_per_step"], "e2e": r["e2e"], "gpu_launches": r["launches"],
                          "config": workload_config(wname, wB, world, args.precision)}
                 if rank == 0:
-                    wk = kernel_rooflines(r["prof"], r["ms"], traffic_for(wname))
+                    wk = kernel_rooflines(r["prof"], r["ms_prof"], traffic_for(wname))
                     entry["roofline"] = dominant(wk)
                     entry["roofline_kernels"] = wk
                 if wname == "b1" and world == 1:

@@ -116,6 +116,20 @@ int e2f_deform_align_fused(const void* x, const float* head, const float* flow1,
                 "e2f_deform_align_fused");
 }
 
+int e2f_deform_align_fused_split(const void* x, const float* head, const float* flow1, const float* flow2,
+                                 const void* w_packed, const float* bias, float* out, void* out_hi, void* out_lo, int n,
+                                 int h, int w, int cin, int cout, int deform_groups, float max_residue, int x_layout,
+                                 void* stream) {
+  const char* who = "e2f_deform_align_fused_split";
+  int st = dcn_common_checks(who, x, w_packed, out, n, h, w, E2F_F32);
+  if (st) return st;
+  if (!head || !flow1 || !flow2 || !out_hi || !out_lo) { set_error("%s: null pointer", who); return E2F_ERR_BAD_ARG; }
+  if (!aligned(head, 8) || !aligned(flow1, 8) || !aligned(flow2, 8) || !aligned(out_hi, 16) || !aligned(out_lo, 16)) { set_error("%s: head/flow need 8-byte, out_hi/out_lo 16-byte alignment", who); return E2F_ERR_ALIGNMENT; }
+  if (x_layout != E2F_X_NHWC && x_layout != E2F_X_GROUPED) { set_error("%s: x_layout %d", who, x_layout); return E2F_ERR_BAD_ARG; }
+  return finish(launch_dcn(x, nullptr, nullptr, head, flow1, flow2, w_packed, bias, out, n, h, w, cin, cout,
+                           deform_groups, max_residue, E2F_F32, x_layout, static_cast<cudaStream_t>(stream), out_hi, out_lo), who);
+}
+
 int e2f_focal_window_attention(const void* qkv, const void* qkv_pooled, void* out, int b, int t, int h, int w,
                                int heads, int head_dim, int wh, int ww, int eh, int ew, int fh, int fw,
                                int use_pooled, float scale, int out_dtype, void* stream) {
@@ -177,6 +191,16 @@ int e2f_t2t_fold_unfold(const float* tokens_in, float* tokens, void* tokens_hi, 
   st = launch_t2t_fold_unfold(tokens_in, tokens, tokens_hi, tokens_lo, bt, c, h, w, k, stride, pad, gelu, out_pitch, static_cast<cudaStream_t>(stream));
   if (st == E2F_ERR_UNSUPPORTED) { set_error("e2f_t2t_fold_unfold: only k=7 stride=3 pad=3, C %% 4 == 0, bt <= 65535 and W <= 1800 are fused (k=%d s=%d p=%d c=%d w=%d); compose e2f_t2t_fold + e2f_t2t_unfold", k, stride, pad, c, w); return st; }
   return finish(st, "e2f_t2t_fold_unfold");
+}
+
+int e2f_layernorm_pool_split(const float* x, const float* gamma, const float* beta, const float* pool_w,
+                             const float* pool_b, void* out_hi, void* out_lo, int bt, int h, int w, int c, int wh, int ww,
+                             float eps, void* stream) {
+  const char* who = "e2f_layernorm_pool_split";
+  if (!x || !gamma || !beta || !pool_w || !out_hi || !out_lo) { set_error("%s: null pointer", who); return E2F_ERR_BAD_ARG; }
+  if (bt < 0 || h <= 0 || w <= 0 || c <= 0 || wh <= 0 || ww <= 0 || h % wh || w % ww) { set_error("%s: bad shape bt=%d h=%d w=%d c=%d window=%dx%d", who, bt, h, w, c, wh, ww); return E2F_ERR_BAD_ARG; }
+  if (!aligned(x, 16) || !aligned(out_hi, 16) || !aligned(out_lo, 16) || !aligned(gamma, 4) || !aligned(beta, 4)) { set_error("%s: 16-byte alignment required", who); return E2F_ERR_ALIGNMENT; }
+  return finish(launch_layernorm_pool_split(x, gamma, beta, pool_w, pool_b, out_hi, out_lo, bt, h, w, c, wh, ww, eps, static_cast<cudaStream_t>(stream)), who);
 }
 
 int e2f_window_pool(const void* x_hi, const void* x_lo, const float* weight, const float* bias, float* out, void* out_hi,
@@ -285,8 +309,10 @@ int e2f_conv_gather_bf16x3(int nsrc, const void* const* src_hi, const void* cons
                            const float* residual, float* out, void* out_hi, void* out_lo, int n, int h_in, int w_in,
                            int cout, float leaky_slope, int stride, int grid_h, int grid_w, int tile_w, int tile_h,
                            int ntaps, const int8_t* tap_dy, const int8_t* tap_dx, int nphase, const uint8_t* ph_tap0,
-                           const uint8_t* ph_oy, const uint8_t* ph_ox, int ostep, int out_h, int out_w, void* stream) {
+                           const uint8_t* ph_oy, const uint8_t* ph_ox, int ostep, int out_h, int out_w,
+                           const int64_t* src_nstride, int64_t out_nstride, void* stream) {
   const char* who = "e2f_conv_gather_bf16x3";
+  if (out_nstride < 0) { set_error("%s: negative out_nstride", who); return E2F_ERR_BAD_ARG; }
   if (!src_hi || !src_lo || !src_channels || !w_hi || !w_lo || !tap_dy || !tap_dx || !ph_tap0 || !ph_oy || !ph_ox) { set_error("%s: null pointer", who); return E2F_ERR_BAD_ARG; }
   if ((!out && !out_hi) || (!out_hi) != (!out_lo)) { set_error("%s: need out and/or both of out_hi/out_lo", who); return E2F_ERR_BAD_ARG; }
   if (out_hi && cout % 8) { set_error("%s: split output needs Cout %% 8 == 0", who); return E2F_ERR_UNSUPPORTED; }
@@ -308,6 +334,10 @@ int e2f_conv_gather_bf16x3(int nsrc, const void* const* src_hi, const void* cons
   g.grid_h = grid_h; g.grid_w = grid_w; g.out_h = out_h; g.out_w = out_w; g.tile_w = tile_w; g.tile_h = tile_h;
   g.ntaps = ntaps; g.nphase = nphase; g.ostep = ostep; g.tap_dy = tap_dy; g.tap_dx = tap_dx; g.ph_tap0 = ph_tap0;
   g.ph_oy = ph_oy; g.ph_ox = ph_ox; g.bias_map = bias_map;
+  long long sn[4] = {0, 0, 0, 0};
+  for (int i = 0; src_nstride && i < nsrc; ++i) sn[i] = static_cast<long long>(src_nstride[i]);
+  g.src_nstride = src_nstride ? sn : nullptr;
+  g.out_nstride = static_cast<long long>(out_nstride);
   return finish(launch_conv3x3(nsrc, src_hi, src_lo, src_channels, w_hi, w_lo, bias, residual, out, out_hi, out_lo, n, h_in, w_in, cout, 1, leaky_slope, 0, stride, 0, 0, 0, static_cast<cudaStream_t>(stream), &g), who);
 }
 

@@ -73,6 +73,8 @@ struct Params {
   // Linear + fold is (tfocal_transformer.py:65-72): output pixels with the same (y mod 3, x mod 3) share a tap set.
   int tile_w, tile_h;      // GEMM-grid pixels per tile (tile_w * tile_h <= 128; rows beyond are idle)
   int nphase, ostep, out_H, out_W;
+  long long out_nstride;   // pixels between consecutive images of the fp32 output / residual (dense: out_H * out_W)
+  long long osp_nstride;   // ... of the split outputs (dense: out_H * out_pitch)
   int8_t tap_dy[64], tap_dx[64];
   uint8_t ph_tap0[10], ph_oy[9], ph_ox[9];
   float slope;             // LeakyReLU negative slope (1 = identity)
@@ -150,8 +152,8 @@ __device__ __forceinline__ void epilogue_tile(const Params& p, const TileCoord& 
   };
   int y, x;                                            // this thread's OUTPUT pixel
   const bool pix_ok = map_row(r, y, x);
-  const size_t pix = (static_cast<size_t>(t.n) * p.out_H + y) * p.out_W + x;                      // fp32 out, residual
-  const size_t opix = (static_cast<size_t>(t.n) * p.out_H + y) * p.out_pitch + p.out_lead + x;   // split outputs
+  const size_t pix = static_cast<size_t>(t.n) * p.out_nstride + static_cast<size_t>(y) * p.out_W + x;        // fp32 out, residual
+  const size_t opix = static_cast<size_t>(t.n) * p.osp_nstride + static_cast<size_t>(y) * p.out_pitch + p.out_lead + x;   // split outputs
   const size_t mpix = static_cast<size_t>(y) * p.out_W + x;                                         // bias map
   const int co_end = (t.g + 1) * cog;               // exclusive end of this group's output channels
   const bool vec_ok = (p.Cout & 3) == 0;            // 16-byte aligned channel groups
@@ -224,8 +226,8 @@ __device__ __forceinline__ void epilogue_tile(const Params& p, const TileCoord& 
             const bool ok = map_row(R, yy, xx);
             const uint4 u = ld_chunk(rr);
             if (ok)
-              *reinterpret_cast<uint4*>(p.out + ((static_cast<size_t>(t.n) * p.out_H + yy) * p.out_W + xx) * p.Cout + co + h * 16 +
-                                        sub * 4) = u;
+              *reinterpret_cast<uint4*>(p.out + (static_cast<size_t>(t.n) * p.out_nstride + static_cast<size_t>(yy) * p.out_W + xx) * p.Cout +
+                                        co + h * 16 + sub * 4) = u;
           }
           __syncwarp();
         }
@@ -254,8 +256,8 @@ __device__ __forceinline__ void epilogue_tile(const Params& p, const TileCoord& 
             const bool ok = map_row(R, yy, xx);
             const uint4 u = ld_chunk(rr);
             if (ok)
-              *reinterpret_cast<uint4*>(dst + ((static_cast<size_t>(t.n) * p.out_H + yy) * p.out_pitch + p.out_lead + xx) * p.Cout +
-                                        co + sub * 8) = u;
+              *reinterpret_cast<uint4*>(dst + (static_cast<size_t>(t.n) * p.osp_nstride + static_cast<size_t>(yy) * p.out_pitch + p.out_lead + xx) *
+                                              p.Cout + co + sub * 8) = u;
           }
           __syncwarp();
         }
@@ -785,6 +787,15 @@ int launch_conv3x3(int nsrc, const void* const* src_hi, const void* const* src_l
     p.ph_tap0[0] = 0; p.ph_tap0[1] = static_cast<uint8_t>(ntaps); p.ph_oy[0] = p.ph_ox[0] = 0;
   }
   p.out_pitch = conv_rows_pitch(p.out_W, out_lead, cout);   // == out_W + out_lead: split outputs have >= 8 channels
+  p.out_nstride = static_cast<long long>(p.out_H) * p.out_W;
+  p.osp_nstride = static_cast<long long>(p.out_H) * p.out_pitch;
+  if (geom && geom->out_nstride > 0) {                       // batch-strided output (a frame slice of a (b, t, h, w, c) buffer)
+    if (out_lead || geom->out_nstride < p.out_nstride) {
+      set_error("conv: a batch-strided output needs a dense row layout and a stride >= out_h * out_w pixels");
+      return -2;
+    }
+    p.out_nstride = p.osp_nstride = geom->out_nstride;
+  }
   p.out_tail = out_lead ? conv_rows_tail(out_lead, cout) : 0;
   for (int i = 0; i < MAX_SRC; ++i) p.cig[i] = p.chunks[i] = 0;
   if (in_rows) {
@@ -839,8 +850,16 @@ int launch_conv3x3(int nsrc, const void* const* src_hi, const void* const* src_l
     p.chunks_total += p.chunks[i];
     const cuuint64_t dims[4] = {static_cast<cuuint64_t>(c), static_cast<cuuint64_t>(w_in),
                                 static_cast<cuuint64_t>(h_in), static_cast<cuuint64_t>(n)};
+    long long nstride = static_cast<long long>(h_in) * w_in;                       // pixels between consecutive images
+    if (geom && geom->src_nstride && geom->src_nstride[i] > 0) {
+      if (geom->src_nstride[i] < nstride) {
+        set_error("conv: source %d batch stride %lld is smaller than one image (%lld pixels)", i, geom->src_nstride[i], nstride);
+        return -2;
+      }
+      nstride = geom->src_nstride[i];
+    }
     const cuuint64_t strides[3] = {static_cast<cuuint64_t>(c) * 2, static_cast<cuuint64_t>(w_in) * c * 2,
-                                   static_cast<cuuint64_t>(h_in) * w_in * c * 2};
+                                   static_cast<cuuint64_t>(nstride) * c * 2};
     // the box spans TILE*stride input elements and is traversed with elementStrides = stride: TILE elements land
     const cuuint32_t box[4] = {BK, static_cast<cuuint32_t>(halo_slots ? HALO_W : tile_w * stride),
                                static_cast<cuuint32_t>(halo_slots ? HALO_H : tile_h * stride), 1};

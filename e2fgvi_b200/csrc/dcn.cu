@@ -11,6 +11,7 @@
 // Roofline: 2*128*2304*M FLOP per call (3.82 GFLOP at M=6480) on the tensor pipe; min bytes
 // (x + offset + mask + W + out).
 #include <cuda.h>
+#include <cuda_bf16.h>
 #include "common.cuh"
 #include "launch.h"
 
@@ -47,7 +48,8 @@ __global__ void __launch_bounds__(THREADS, 1)
 dcn_kernel(const __grid_constant__ CUtensorMap tmap_w, const __half* __restrict__ x,
            const float* __restrict__ offset, const float* __restrict__ mask, const float* __restrict__ head,
            const float2* __restrict__ flow1, const float2* __restrict__ flow2, const float* __restrict__ bias,
-           OutT* __restrict__ out, int M, int H, int W, float max_res) {
+           OutT* __restrict__ out, int M, int H, int W, float max_res, __nv_bfloat16* __restrict__ out_hi,
+           __nv_bfloat16* __restrict__ out_lo) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
@@ -188,6 +190,26 @@ dcn_kernel(const __grid_constant__ CUtensorMap tmap_w, const __half* __restrict_
         float4* dst = reinterpret_cast<float4*>(out + om * COUT + cc * 32);
 #pragma unroll
         for (int i = 0; i < 8; ++i) dst[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+        if (out_hi) {
+          // bf16 (hi, lo) split of the same values: the operand pair of the backbone conv that consumes the aligned
+          // features (feat_prop.py:131-136), so no standalone split pass runs between the DCN and that conv
+          uint4* dh = reinterpret_cast<uint4*>(out_hi + om * COUT + cc * 32);
+          uint4* dl = reinterpret_cast<uint4*>(out_lo + om * COUT + cc * 32);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            uint32_t hp[4], lp[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const __nv_bfloat162 hb = __floats2bfloat162_rn(f[8 * i + 2 * j], f[8 * i + 2 * j + 1]);
+              const float2 hf = __bfloat1622float2(hb);
+              const __nv_bfloat162 lb = __floats2bfloat162_rn(f[8 * i + 2 * j] - hf.x, f[8 * i + 2 * j + 1] - hf.y);
+              hp[j] = *reinterpret_cast<const uint32_t*>(&hb);
+              lp[j] = *reinterpret_cast<const uint32_t*>(&lb);
+            }
+            dh[i] = make_uint4(hp[0], hp[1], hp[2], hp[3]);
+            dl[i] = make_uint4(lp[0], lp[1], lp[2], lp[3]);
+          }
+        }
       } else {
         uint4* dst = reinterpret_cast<uint4*>(out + om * COUT + cc * 32);
 #pragma unroll
@@ -288,7 +310,7 @@ __global__ void __launch_bounds__(256) pack_input_kernel(const float* __restrict
 template <bool FUSED, bool GROUPED, typename OutT>
 static int launch_variant(const CUtensorMap& tmap, const void* x, const float* offset, const float* mask,
                           const float* head, const float* flow1, const float* flow2, const float* bias, void* out,
-                          int M, int h, int w, float max_res, cudaStream_t stream) {
+                          int M, int h, int w, float max_res, void* out_hi, void* out_lo, cudaStream_t stream) {
   auto kern = dcn_kernel<FUSED, GROUPED, OutT>;
   static DeviceOnce configured;                    // one per template instantiation, one bit per device
   const int dev = current_device();
@@ -301,7 +323,8 @@ static int launch_variant(const CUtensorMap& tmap, const void* x, const float* o
   kern<<<blocks, THREADS, SMEM_BYTES, stream>>>(tmap, static_cast<const __half*>(x), offset, mask, head,
                                                 reinterpret_cast<const float2*>(flow1),
                                                 reinterpret_cast<const float2*>(flow2), bias,
-                                                static_cast<OutT*>(out), M, h, w, max_res);
+                                                static_cast<OutT*>(out), M, h, w, max_res,
+                                                static_cast<__nv_bfloat16*>(out_hi), static_cast<__nv_bfloat16*>(out_lo));
   count_launch();
   return static_cast<int>(cudaGetLastError());
 }
@@ -319,8 +342,13 @@ int launch_dcn_pack_weight(const float* w, void* w_packed, int cout, int cin, in
 
 int launch_dcn(const void* x, const float* offset, const float* mask, const float* head, const float* flow1,
                const float* flow2, const void* w_packed, const float* bias, void* out, int n, int h, int w, int cin,
-               int cout, int dg, float max_residue, int out_dtype, int x_grouped, cudaStream_t stream) {
+               int cout, int dg, float max_residue, int out_dtype, int x_grouped, cudaStream_t stream, void* out_hi,
+               void* out_lo) {
   using namespace dcn;
+  if ((out_hi || out_lo) && (out_dtype != 0 || !out_hi || !out_lo)) {
+    set_error("deformable conv: the bf16 split output goes with the fp32 output and needs both halves");
+    return -1;
+  }
   if (cin != CIN || cout != COUT || dg != DG) {
     set_error("deformable conv is specialised for Cin=256, Cout=128, deform_groups=16 (got %d, %d, %d)", cin, cout,
               dg);
@@ -350,7 +378,7 @@ int launch_dcn(const void* x, const float* offset, const float* mask, const floa
     return -4;
   }
   const int Mi = static_cast<int>(M);
-#define E2F_DCN_LAUNCH(F, G, T) launch_variant<F, G, T>(tmap, x, offset, mask, head, flow1, flow2, bias, out, Mi, h, w, max_residue, stream)
+#define E2F_DCN_LAUNCH(F, G, T) launch_variant<F, G, T>(tmap, x, offset, mask, head, flow1, flow2, bias, out, Mi, h, w, max_residue, out_hi, out_lo, stream)
   if (head) {
     if (x_grouped) return out_dtype == 1 ? E2F_DCN_LAUNCH(true, true, __half) : E2F_DCN_LAUNCH(true, true, float);
     return out_dtype == 1 ? E2F_DCN_LAUNCH(true, false, __half) : E2F_DCN_LAUNCH(true, false, float);

@@ -127,6 +127,99 @@ __global__ void __launch_bounds__(256) layernorm_split_kernel(const float* __res
   }
 }
 
+// LayerNorm + FOCAL WINDOW POOLING in one pass (tfocal_transformer.py:470 norm1 + :508-516 pool_layers[0]): one CTA per
+// (frame, window); each warp normalises whole token rows (512 channels, 16 per lane) and, with the normalised fp32
+// values still IN REGISTERS, accumulates its share of the window's pooled token  sum_tok w[tok] * LN(x[tok])  per channel;
+// the 8 per-warp partial rows are reduced through 16 KB of shared memory.  Outputs: the bf16 (hi, lo) split of the
+// normalised tokens, rows [0, BT*H*W), and of the pooled tokens, rows [BT*H*W, +BT*nW) of the SAME buffers, ordered
+// (bt, wi, wj) — so ONE qkv GEMM serves tokens and pooled tokens and the standalone pool / pooled-qkv launches are gone.
+template <int PER_LANE>
+__global__ void __launch_bounds__(256) layernorm_pool_split_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                                   const float* __restrict__ beta,
+                                                                   const float* __restrict__ pool_w,
+                                                                   const float* __restrict__ pool_b,
+                                                                   __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
+                                                                   int H, int W, int wh, int ww, long long rows, float eps) {
+  constexpr int C = 32 * PER_LANE;
+  __shared__ float red[8][C];
+  const int nww = W / ww, nwh = H / wh;
+  const int win = blockIdx.x, bt = blockIdx.y;
+  const int wi = win / nww, wj = win - wi * nww;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float g[PER_LANE], bt_[PER_LANE], acc[PER_LANE];
+#pragma unroll
+  for (int j = 0; j < PER_LANE / 8; ++j) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      g[8 * j + e] = __ldg(gamma + j * 256 + lane * 8 + e);
+      bt_[8 * j + e] = __ldg(beta + j * 256 + lane * 8 + e);
+      acc[8 * j + e] = 0.f;
+    }
+  }
+  const int ntok = wh * ww;
+  for (int tok = warp; tok < ntok; tok += 8) {
+    const int r = tok / ww, q = tok - r * ww;
+    const long long row = (static_cast<long long>(bt) * H + wi * wh + r) * W + wj * ww + q;
+    const float* xr = x + row * C;
+    float v[PER_LANE];
+#pragma unroll
+    for (int j = 0; j < PER_LANE / 8; ++j) {        // lane owns 8 consecutive floats per 256-float segment
+      const float4 a = __ldg(reinterpret_cast<const float4*>(xr + j * 256 + lane * 8));
+      const float4 b = __ldg(reinterpret_cast<const float4*>(xr + j * 256 + lane * 8) + 1);
+      v[8 * j + 0] = a.x; v[8 * j + 1] = a.y; v[8 * j + 2] = a.z; v[8 * j + 3] = a.w;
+      v[8 * j + 4] = b.x; v[8 * j + 5] = b.y; v[8 * j + 6] = b.z; v[8 * j + 7] = b.w;
+    }
+    float sum = 0.f;
+#pragma unroll
+    for (int e = 0; e < PER_LANE; ++e) sum += v[e];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float mean = sum * (1.0f / C);
+    float sq = 0.f;
+#pragma unroll
+    for (int e = 0; e < PER_LANE; ++e) {
+      const float d = v[e] - mean;
+      sq = fmaf(d, d, sq);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    const float rstd = rsqrtf(sq * (1.0f / C) + eps);
+    const float wt = __ldg(pool_w + tok);
+#pragma unroll
+    for (int j = 0; j < PER_LANE / 8; ++j) {
+      const int c0 = j * 256 + lane * 8;
+      float f[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        f[e] = (v[8 * j + e] - mean) * rstd * g[8 * j + e] + bt_[8 * j + e];
+        acc[8 * j + e] = fmaf(wt, f[e], acc[8 * j + e]);
+      }
+      split_store8(f, hi + row * C + c0, lo + row * C + c0);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < PER_LANE / 8; ++j) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) red[warp][j * 256 + lane * 8 + e] = acc[8 * j + e];
+  }
+  __syncthreads();
+  // pooled token: fixed summation order over the 8 warps (deterministic); 64 threads x 8 channels
+  if (threadIdx.x < C / 8) {
+    const int c0 = threadIdx.x * 8;
+    const float b0 = pool_b ? __ldg(pool_b) : 0.f;
+    float f[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      float t = b0;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) t += red[k][c0 + e];
+      f[e] = t;
+    }
+    const long long prow = rows + (static_cast<long long>(bt) * nwh + wi) * nww + wj;
+    split_store8(f, hi + prow * C + c0, lo + prow * C + c0);
+  }
+}
+
 // Window pooling of the focal attention's coarse level (pool_layers[0] = nn.Linear(wh*ww, 1) applied across the tokens
 // of each window, per channel; tfocal_transformer.py:508-516):
 //   out[bt][wi][wj][c] = bias + sum_{r,q} x[bt][wi*wh + r][wj*ww + q][c] * weight[r*ww + q]
@@ -192,6 +285,22 @@ int launch_window_pool(const void* xh, const void* xl, const float* weight, cons
   window_pool_kernel<<<grid, block, static_cast<size_t>(wh) * c * sizeof(float), stream>>>(
       static_cast<const __nv_bfloat16*>(xh), static_cast<const __nv_bfloat16*>(xl), weight, bias, out,
       static_cast<__nv_bfloat16*>(out_hi), static_cast<__nv_bfloat16*>(out_lo), h, w, c, wh, ww);
+  count_launch();
+  return static_cast<int>(cudaGetLastError());
+}
+
+int launch_layernorm_pool_split(const float* x, const float* gamma, const float* beta, const float* pool_w,
+                                const float* pool_b, void* hi, void* lo, int bt, int h, int w, int c, int wh, int ww,
+                                float eps, cudaStream_t stream) {
+  if (bt == 0) return 0;
+  if (c != 512) {
+    set_error("layernorm_pool_split is specialised for 512 channels (got %d)", c);
+    return -2;
+  }
+  const dim3 grid((h / wh) * (w / ww), bt);
+  layernorm_pool_split_kernel<16><<<grid, 256, 0, stream>>>(x, gamma, beta, pool_w, pool_b, static_cast<__nv_bfloat16*>(hi),
+                                                            static_cast<__nv_bfloat16*>(lo), h, w, wh, ww,
+                                                            static_cast<long long>(bt) * h * w, eps);
   count_launch();
   return static_cast<int>(cudaGetLastError());
 }

@@ -26,6 +26,7 @@ constexpr int BM = 128, BK = 64;
 constexpr int A_TILE = BM * BK * 2;                // 16 KB (one bf16 term)
 constexpr int EPI_WARPS = 8;                       // two warps per TMEM lane quadrant, each owning half of the tile's columns
 constexpr int THREADS = (2 + EPI_WARPS) * 32;      // 320
+constexpr int EPI_STAGE = 2048;                    // per epilogue warp: 32 rows x 64 bytes transposition buffer
 
 template <int BN>
 struct Cfg {
@@ -33,7 +34,8 @@ struct Cfg {
   static constexpr int STAGE = 2 * A_TILE + 2 * W_TILE;
   static constexpr int STAGES = (BN == 128) ? 3 : 2;
   static constexpr int TMEM_COLS = 2 * BN;          // double-buffered accumulator (256 or 512 columns)
-  static constexpr int SMEM = STAGES * STAGE + 256 + 2 * BN * 4 + 1024;   // + per-tile bias slice, double-buffered
+  // + per-tile bias slice (double-buffered) + the epilogue warps' store/load transposition buffers
+  static constexpr int SMEM = STAGES * STAGE + 256 + 2 * BN * 4 + EPI_WARPS * EPI_STAGE + 1024;
 };
 
 // kind::f16 instruction descriptor with BF16 operands (a_format = b_format = 1), fp32 accumulate, K-major A and B
@@ -61,6 +63,7 @@ linear_kernel(const __grid_constant__ CUtensorMap tm_ah, const __grid_constant__
   uint64_t* acc_empty = acc_full + 2;         // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
   float* sbias = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE + 256);   // [2][BN]
+  uint8_t* epi_stage = smem + C::STAGES * C::STAGE + 256 + 2 * BN * 4;           // [EPI_WARPS][EPI_STAGE]
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int tiles_m = (M + BM - 1) / BM, tiles_n = (N + BN - 1) / BN;
@@ -162,27 +165,45 @@ linear_kernel(const __grid_constant__ CUtensorMap tm_ah, const __grid_constant__
     const int q = warp & 3, half = (warp - 2) >> 2;
     const int et = tid - 64;                                  // 0..255 among the epilogue threads
     constexpr int CH = BN / 64;                               // 32-column chunks per warp
+    // Global accesses are TRANSPOSED through a per-warp 32-row x 64-byte buffer (same scheme as conv.cu, XOR-swizzled,
+    // conflict-free): with thread = row, a direct 16-byte access per thread touches 32 different 128-byte lines per
+    // instruction (rows are N*4 bytes apart) and the LSU, not the tensor pipe, bounded every short-K GEMM
+    // (attn.proj K=512: 20 us per tile against a 6.5 us main loop, profiles/r02).  Transposed, 4 consecutive lanes
+    // move one row's 64 contiguous bytes: 8 lines per instruction, for the stores AND the residual loads.
+    const uint32_t stg = smem_u32(epi_stage + (warp - 2) * EPI_STAGE);
+    const uint32_t wsw = (lane >> 1) & 3;
+    const int sub = lane & 3, prow = lane >> 2;
+    auto st_own = [&](int cc, uint32_t a, uint32_t b, uint32_t c2, uint32_t d) {       // own row, logical chunk cc
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + lane * 64 + ((cc ^ wsw) << 4)), "r"(a), "r"(b), "r"(c2), "r"(d)
+                   : "memory");
+    };
+    auto ld_own = [&](int cc) {
+      uint4 u;
+      asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w)
+                   : "r"(stg + lane * 64 + ((cc ^ wsw) << 4)) : "memory");
+      return u;
+    };
+    auto st_row = [&](int rr, uint4 u) {                                                 // row rr, logical chunk `sub`
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + rr * 64 + ((sub ^ ((rr >> 1) & 3)) << 4)), "r"(u.x), "r"(u.y), "r"(u.z), "r"(u.w)
+                   : "memory");
+    };
+    auto ld_row = [&](int rr) {
+      uint4 u;
+      asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w)
+                   : "r"(stg + rr * 64 + ((sub ^ ((rr >> 1) & 3)) << 4)) : "memory");
+      return u;
+    };
+    const bool vec_ok = (N & 3) == 0;                         // rows start on 16-byte boundaries
     uint32_t local = 0;
     for (int item = first_item; item < num_items; item += item_step, ++local) {
       const int buf = local & 1;
       const int m0 = ((item / tiles_n) * CL + rank) * BM, n0 = (item % tiles_n) * BN;
-      const int row = m0 + q * 32 + lane;
+      const int rbase = m0 + q * 32;                          // first row of this warp's TMEM lane quarter
+      const int row = rbase + lane;
       float* sb = sbias + buf * BN;
       if (et < BN) sb[et] = (bias && n0 + et < N) ? __ldg(bias + n0 + et) : 0.f;
       const bool row_ok = row < M;
       const size_t orow = static_cast<size_t>(row) * N;
-      float4 rc[8], rn[8];
-      auto fetch = [&](int c, float4* r) {                    // residual of chunk c (full chunks only)
-        const int col0 = n0 + (half * CH + c) * 32;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) r[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (residual && row_ok && col0 + 32 <= N) {
-          const float4* r4 = reinterpret_cast<const float4*>(residual + orow + col0);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) r[i] = __ldg(r4 + i);
-        }
-      };
-      fetch(0, rc);
       asm volatile("bar.sync 1, 256;" ::: "memory");           // bias slice visible to all epilogue warps
       mbar_wait(&acc_full[buf], (local >> 1) & 1);
       tc_fence_after_sync();
@@ -191,49 +212,87 @@ linear_kernel(const __grid_constant__ CUtensorMap tm_ah, const __grid_constant__
       for (int c = 0; c < CH; ++c) {
         uint32_t v[32];
         tmem_ld32(taddr + c * 32, v);
-        if (c + 1 < CH) fetch(c + 1, rn);
         tmem_ld_wait();
         const int cl = (half * CH + c) * 32;                  // column offset inside the tile
         const int col0 = n0 + cl;
-        if (row_ok && col0 < N) {
+        if (col0 >= N) continue;                              // warp-uniform
+        if (vec_ok && col0 + 32 <= N) {
+          float f[32];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 b4 = *reinterpret_cast<const float4*>(sb + cl + 4 * i);
+            f[4 * i] = __uint_as_float(v[4 * i]) + b4.x;
+            f[4 * i + 1] = __uint_as_float(v[4 * i + 1]) + b4.y;
+            f[4 * i + 2] = __uint_as_float(v[4 * i + 2]) + b4.z;
+            f[4 * i + 3] = __uint_as_float(v[4 * i + 3]) + b4.w;
+          }
+          if (residual) {
+            // all eight coalesced 16-byte loads of the chunk are in flight before the first one is consumed
+            uint4 ru[2][4];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {                     // 16 fp32 columns = 64 bytes per row and pass
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const int R = rbase + j * 8 + prow;
+                ru[h][j] = make_uint4(0u, 0u, 0u, 0u);
+                if (R < M) ru[h][j] = __ldg(reinterpret_cast<const uint4*>(residual + static_cast<size_t>(R) * N + col0 + h * 16 + sub * 4));
+              }
+            }
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) st_row(j * 8 + prow, ru[h][j]);
+              __syncwarp();
+#pragma unroll
+              for (int cc = 0; cc < 4; ++cc) {
+                const uint4 u = ld_own(cc);
+                f[h * 16 + cc * 4] += __uint_as_float(u.x);     f[h * 16 + cc * 4 + 1] += __uint_as_float(u.y);
+                f[h * 16 + cc * 4 + 2] += __uint_as_float(u.z); f[h * 16 + cc * 4 + 3] += __uint_as_float(u.w);
+              }
+              __syncwarp();
+            }
+          }
+          if constexpr (sizeof(OutT) == 4) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+#pragma unroll
+              for (int cc = 0; cc < 4; ++cc)
+                st_own(cc, __float_as_uint(f[h * 16 + cc * 4]), __float_as_uint(f[h * 16 + cc * 4 + 1]),
+                       __float_as_uint(f[h * 16 + cc * 4 + 2]), __float_as_uint(f[h * 16 + cc * 4 + 3]));
+              __syncwarp();
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const int rr = j * 8 + prow, R = rbase + rr;
+                const uint4 u = ld_row(rr);
+                if (R < M) *reinterpret_cast<uint4*>(out + static_cast<size_t>(R) * N + col0 + h * 16 + sub * 4) = u;
+              }
+              __syncwarp();
+            }
+          } else {                                            // fp16: 32 columns = 64 bytes per row, one pass
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc)
+              st_own(cc, pack_half2(f[cc * 8], f[cc * 8 + 1]), pack_half2(f[cc * 8 + 2], f[cc * 8 + 3]),
+                     pack_half2(f[cc * 8 + 4], f[cc * 8 + 5]), pack_half2(f[cc * 8 + 6], f[cc * 8 + 7]));
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int rr = j * 8 + prow, R = rbase + rr;
+              const uint4 u = ld_row(rr);
+              if (R < M) *reinterpret_cast<uint4*>(out + static_cast<size_t>(R) * N + col0 + sub * 8) = u;
+            }
+            __syncwarp();
+          }
+        } else if (row_ok) {
           const size_t o = orow + col0;
-          if (col0 + 32 <= N) {
-            float f[32];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float4 b4 = *reinterpret_cast<const float4*>(sb + cl + 4 * i);
-              f[4 * i] = __uint_as_float(v[4 * i]) + b4.x + rc[i].x;
-              f[4 * i + 1] = __uint_as_float(v[4 * i + 1]) + b4.y + rc[i].y;
-              f[4 * i + 2] = __uint_as_float(v[4 * i + 2]) + b4.z + rc[i].z;
-              f[4 * i + 3] = __uint_as_float(v[4 * i + 3]) + b4.w + rc[i].w;
-            }
-            if constexpr (sizeof(OutT) == 4) {
-              float4* d4 = reinterpret_cast<float4*>(out + o);
-#pragma unroll
-              for (int i = 0; i < 8; ++i) d4[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
-            } else {
-              uint4* d4 = reinterpret_cast<uint4*>(out + o);
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                uint4 u;
-                u.x = pack_half2(f[8 * i], f[8 * i + 1]);     u.y = pack_half2(f[8 * i + 2], f[8 * i + 3]);
-                u.z = pack_half2(f[8 * i + 4], f[8 * i + 5]); u.w = pack_half2(f[8 * i + 6], f[8 * i + 7]);
-                d4[i] = u;
-              }
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {     // static indexing keeps v[] in registers
-              if (col0 + i < N) {
-                const float val = __uint_as_float(v[i]) + sb[cl + i] + (residual ? __ldg(residual + o + i) : 0.f);
-                if constexpr (sizeof(OutT) == 4) out[o + i] = val;
-                else out[o + i] = __float2half_rn(val);
-              }
+          for (int i = 0; i < 32; ++i) {     // static indexing keeps v[] in registers
+            if (col0 + i < N) {
+              const float val = __uint_as_float(v[i]) + sb[cl + i] + (residual ? __ldg(residual + o + i) : 0.f);
+              if constexpr (sizeof(OutT) == 4) out[o + i] = val;
+              else out[o + i] = __float2half_rn(val);
             }
           }
         }
-#pragma unroll
-        for (int i = 0; i < 8; ++i) rc[i] = rn[i];
       }
       tc_fence_before_sync();
       __syncwarp();

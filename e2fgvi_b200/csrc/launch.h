@@ -42,7 +42,8 @@ int launch_dcn_pack_weight(const float* w, void* w_packed, int cout, int cin, in
 // head != nullptr selects the fused (tanh / flow / sigmoid) prologue; otherwise offset+mask are final values.
 int launch_dcn(const void* x, const float* offset, const float* mask, const float* head, const float* flow1,
                const float* flow2, const void* w_packed, const float* bias, void* out, int n, int h, int w, int cin,
-               int cout, int dg, float max_residue, int out_dtype, int x_grouped, cudaStream_t stream);
+               int cout, int dg, float max_residue, int out_dtype, int x_grouped, cudaStream_t stream,
+               void* out_hi = nullptr, void* out_lo = nullptr);   // optional bf16 split of the fp32 result
 int launch_dcn_pack_input(const float* a, const float* b, void* xg, int n, int h, int w, int ca, int cb,
                           cudaStream_t stream);
 
@@ -55,6 +56,9 @@ int launch_t2t_unfold(const float* img, float* tok, void* tok_hi, void* tok_lo, 
 int launch_upsample2x_split(const float* x, void* hi, void* lo, int n, int h, int w, int c, cudaStream_t stream);
 int launch_layernorm_split(const float* x, const float* gamma, const float* beta, float* out, void* hi, void* lo,
                            long long rows, int c, float eps, cudaStream_t stream);
+int launch_layernorm_pool_split(const float* x, const float* gamma, const float* beta, const float* pool_w,
+                                const float* pool_b, void* hi, void* lo, int bt, int h, int w, int c, int wh, int ww,
+                                float eps, cudaStream_t stream);
 int launch_window_pool(const void* xh, const void* xl, const float* weight, const float* bias, float* out, void* out_hi,
                        void* out_lo, int bt, int h, int w, int c, int wh, int ww, cudaStream_t stream);
 int launch_t2t_fold_unfold(const float* tin, float* tok, void* tok_hi, void* tok_lo, int bt, int c, int h, int w, int k,
@@ -82,6 +86,8 @@ struct ConvGeom {
   const uint8_t* ph_oy;          // [nphase]
   const uint8_t* ph_ox;
   const float* bias_map;         // fp32 [out_h][out_w][cout] or null
+  const long long* src_nstride;  // [nsrc] pixels between consecutive images of each source (0 / null = dense)
+  long long out_nstride;         // pixels between consecutive images of every output and of the residual (0 = dense)
 };
 int launch_conv3x3(int nsrc, const void* const* src_hi, const void* const* src_lo, const int* src_channels,
                    const void* w_hi, const void* w_lo, const float* bias, const float* residual, float* out,

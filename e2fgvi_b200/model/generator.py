@@ -67,16 +67,17 @@ class Encoder(nn.Module):
             layers += [nn.Conv2d(cin, cout, 3, stride, 1, groups=groups), nn.LeakyReLU(0.2, inplace=True)]
         self.layers = nn.ModuleList(layers)
 
-    def forward(self, x):
+    def forward(self, x, last_out="f32"):
         """All nine convs run on the tcgen05 implicit-GEMM kernel (stride 2 via TMA element strides) with LeakyReLU
         fused and the bf16 split operand handed from epilogue to the next conv; the group-wise concatenation of
-        e2fgvi.py:103-108 is expressed as two TMA sources, never materialised."""
+        e2fgvi.py:103-108 is expressed as two TMA sources, never materialised.  ``last_out="both"`` also returns the
+        bf16 (hi, lo) split of the features (operand of the propagation convs and of SoftSplit)."""
         out = x
         x0 = None
         last = len(_ENC) - 1
         for k, (_, _, stride, _) in enumerate(_ENC):
             conv = self.layers[2 * k]
-            mode = "f32" if k == last else "split"
+            mode = last_out if k == last else "split"
             if k == 0:
                 # 3-channel stem: row-gapped 4-channel layout, window-packed K (3 K chunks per tile instead of 9
                 # taps zero-padded from 3 to 64 channels)
@@ -165,24 +166,34 @@ class InpaintGenerator(BaseNetwork):
         b, t, ori_c, ori_h, ori_w = masked_frames.size()
         pred_flows = self.forward_bidirect_flow((masked_frames[:, :l_t] + 1) / 2)
 
-        enc_feat = self.encoder(masked_frames.reshape(b * t, ori_c, ori_h, ori_w))
-        _, c, h, w = enc_feat.size()
-        enc_feat = enc_feat.view(b, t, c, h, w)
-        # NB: (forward, backward) flows go to (flows_backward, flows_forward) exactly as e2fgvi.py:249-250 does
-        local_feat = self.feat_prop_module(enc_feat[:, :l_t], pred_flows[0], pred_flows[1])
-        # keep the features channels_last ((b,t,h,w,c) storage): the unfold reads it, the fold adds it back and
-        # writes it, and the decoder's convs consume it without a layout copy
-        enc_feat = torch.cat((local_feat.permute(0, 1, 3, 4, 2), enc_feat[:, l_t:].permute(0, 1, 3, 4, 2)), dim=1)
-        enc_feat = enc_feat.permute(0, 1, 4, 2, 3)                      # logical (b,t,c,h,w)
+        # encoder output: fp32 (b*t,c,h,w) in NHWC storage + its bf16 (hi, lo) split, both viewed as (b,t,h,w,c)
+        enc32, enc_sp = self.encoder(masked_frames.reshape(b * t, ori_c, ori_h, ori_w), last_out="both")
+        _, c, h, w = enc32.size()
+        x32 = enc32.permute(0, 2, 3, 1).view(b, t, h, w, c)
+        x_hi, x_lo = enc_sp.hi.view(b, t, h, w, c), enc_sp.lo.view(b, t, h, w, c)
+        # NB: (forward, backward) flows go to (flows_backward, flows_forward) exactly as e2fgvi.py:249-250 does.
+        # The local frames are propagated IN PLACE inside the (b,t,h,w,c) feature buffers (frame slices are read and
+        # written by batch-strided convs): the cat(local_feat, enc_feat[:, l_t:]) of e2fgvi.py:252 is the buffer itself
+        prop = self.feat_prop_module
+        if prop.fused_prologue and c % 16 == 0:
+            prop.propagate_frames(x32[:, :l_t], x_hi[:, :l_t], x_lo[:, :l_t], pred_flows[0], pred_flows[1],
+                                  into=(x32[:, :l_t], x_hi[:, :l_t], x_lo[:, :l_t]))
+            ss_in = enc_sp
+        else:                                  # operator-by-operator reference sequence (E2F_PROP_FUSED=0)
+            local = prop(x32[:, :l_t].permute(0, 1, 4, 2, 3), pred_flows[0], pred_flows[1])
+            x32 = torch.cat((local.permute(0, 1, 3, 4, 2), x32[:, l_t:]), dim=1)
+            enc32 = x32.view(b * t, h, w, c).permute(0, 3, 1, 2)
+            ss_in = enc32
+        enc_feat = enc32                                                # logical (b*t,c,h,w), NHWC storage
 
         fold_size = (h, w)
-        tokens = self.ss(enc_feat.reshape(-1, c, h, w), b, fold_size if self.HQ else None)
+        tokens = self.ss(ss_in, b, fold_size if self.HQ else None)
         if self.HQ:
             tokens = self.transformer([tokens, fold_size])[0]
         else:
             tokens = self.transformer(tokens)
         # enc_feat + trans_feat (e2fgvi.py:263) is fused into SoftComp's fold / conv epilogue
-        enc_feat = self.sc(tokens, t, fold_size if self.HQ else None, residual=enc_feat.reshape(-1, c, h, w))
+        enc_feat = self.sc(tokens, t, fold_size if self.HQ else None, residual=enc_feat)
 
         output = torch.tanh(self._decode(enc_feat))
         return output.contiguous(), pred_flows

@@ -73,6 +73,21 @@ class SecondOrderDeformableAlignment(nn.Module):
         y = ops.conv3x3([y], co[4].weight, co[4].bias, negative_slope=0.1, out="split")
         return ops.conv3x3([y], co[6].weight, co[6].bias)
 
+    def offset_head_frames(self, cond_sources, flows):
+        """``offset_head`` for sources that may be frame slices of (b,t,h,w,c) buffers (``ops.conv_frames``)."""
+        co = self.conv_offset
+        y = ops.conv_frames(list(cond_sources) + [flows], co[0].weight, co[0].bias, negative_slope=0.1, out="split")
+        y = ops.conv_frames([y], co[2].weight, co[2].bias, negative_slope=0.1, out="split")
+        y = ops.conv_frames([y], co[4].weight, co[4].bias, negative_slope=0.1, out="split")
+        return ops.conv_frames([y], co[6].weight, co[6].bias)
+
+    def align_split(self, x, cond_sources, flow_1, flow_2, flows):
+        """Fused alignment returning ``(fp32 tensor, SplitNHWC)``: the DCN epilogue also writes the bf16 operand pair of
+        the backbone conv that follows (feat_prop.py:131-136)."""
+        head = self.offset_head_frames(cond_sources, flows)
+        return ops.deform_align_fused(x, head, flow_1, flow_2, self.packed_weight(), self.bias, self.deform_groups,
+                                      self.max_residue_magnitude, out_split=True)
+
     def align(self, x, cond_sources, flow_1, flow_2, flows=None):
         head = self.offset_head(cond_sources, flow_1, flow_2, flows)
         if self.fused:
@@ -113,9 +128,56 @@ class BidirectionalPropagation(nn.Module):
         # False (or E2F_PROP_FUSED=0): the operator-by-operator sequence of feat_prop.py:106-126
         self.fused_prologue = os.environ.get("E2F_PROP_FUSED", "1") != "0"
 
+    def propagate_frames(self, x32, x_hi, x_lo, flows_backward, flows_forward, into=None):
+        """The fast path: every per-frame tensor is a FRAME SLICE of a (b,t,h,w,c) buffer, read and written in place.
+
+        x32 / x_hi / x_lo: (b,t,h,w,c) fp32 features and their bf16 (hi, lo) split (dense inner (h,w,c); the t axis may
+        be a prefix slice of a longer buffer).  ``into`` = (o32, ohi, olo) buffers of the same shape that receive the
+        fused result frame by frame — passing the inputs themselves updates them IN PLACE (each pixel's residual is
+        read by the thread that overwrites it; the sweeps are complete before the first fusion launch).  No
+        ``x[:, i].contiguous()`` gathers, no per-step split passes, no token-buffer copies, no stack / cat:
+        per step = prologue, 4 offset-head convs, DCN (+ split epilogue), 2 backbone convs."""
+        b, t, h, w, c = x32.shape
+        cur = [ops.SplitNHWC(x_hi[:, i], x_lo[:, i], (b, c, h, w)) for i in range(t)]
+        zero = torch.zeros((b, h, w, c), dtype=torch.bfloat16, device=x32.device)
+        zero_sp = ops.SplitNHWC(zero, zero, (b, c, h, w))
+        swept32, swept_sp = {}, {}
+        for name in self.DIRECTIONS:
+            backward = name == "backward_"
+            order = list(range(t - 1, -1, -1)) if backward else list(range(t))
+            flows = flows_backward if backward else flows_forward
+            align, backbone = self.deform_align[name], self.backbone[name]
+            hist32, hist_sp = [], []
+            for i, idx in enumerate(order):
+                prop32, prop_sp = None, zero_sp
+                if i > 0:
+                    xg, cond_n1, cond_n2, flows_op, flow_n1, flow_n2 = ops.prop_prologue(
+                        hist32[-1], hist32[-2] if i > 1 else None, flows[:, i - 1], flows[:, i - 2] if i > 1 else None)
+                    prop32, prop_sp = align.align_split(xg, [cond_n1, cur[idx], cond_n2], flow_n1, flow_n2, flows_op)
+                parts = [cur[idx], prop_sp] if backward else [cur[idx], swept_sp["backward_"][idx], prop_sp]
+                y = ops.conv_frames(parts, backbone[0].weight, backbone[0].bias, negative_slope=0.1, out="split")
+                new32, new_sp = ops.conv_frames([y], backbone[2].weight, backbone[2].bias, residual=prop32, out="both")
+                hist32.append(new32)
+                hist_sp.append(new_sp)
+            swept32[name] = hist32[::-1] if backward else hist32
+            swept_sp[name] = hist_sp[::-1] if backward else hist_sp
+        if into is None:
+            into = (torch.empty_like(x32), torch.empty_like(x_hi), torch.empty_like(x_lo))
+        o32, ohi, olo = into
+        for i in range(t):
+            # 1x1 fusion conv over cat(backward, forward) as two sources, "+ x" fused (feat_prop.py:143-149)
+            ops.conv_frames([swept_sp["backward_"][i], swept_sp["forward_"][i]], self.fusion.weight, self.fusion.bias,
+                            residual=x32[:, i].permute(0, 3, 1, 2), out="both", into=(o32[:, i], ohi[:, i], olo[:, i]))
+        return o32, ohi, olo
+
     def forward(self, x, flows_backward, flows_forward):
         """x (b,t,c,h,w); flows_* (b,t-1,2,h,w) -> (b,t,c,h,w)."""
         b, t, c, h, w = x.shape
+        if self.fused_prologue and c % 16 == 0:
+            x32 = x.permute(0, 1, 3, 4, 2).contiguous().float()          # no-op for (b,t,h,w,c) storage
+            x_hi, x_lo = ops.split_bf16(x32)
+            o32, _, _ = self.propagate_frames(x32, x_hi, x_lo, flows_backward, flows_forward)
+            return o32.permute(0, 1, 4, 2, 3)
         frames = [x[:, i].contiguous(memory_format=torch.channels_last) for i in range(t)]
         # every frame is a source of two convs per direction: split it into the bf16 operand pair once
         frame_ops = [ops.split_nhwc(f) for f in frames]

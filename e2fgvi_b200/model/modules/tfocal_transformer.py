@@ -163,15 +163,25 @@ class WindowAttention(nn.Module):
         """Neighbourhood of pooled windows each query window attends (unfold kernel, tfocal_transformer.py:186-196)."""
         return tuple(2 * (i // 2) + 1 for i in self.focal_window)
 
-    def attend(self, x, pooled, residual=None):
+    def attend(self, x, pooled, residual=None, joint_shape=None):
         """x (B,T,H,W,C) normed tokens (tensor or ops.SplitMat), pooled (B,nWh,nWw,T,C) tensor or the SplitMat of
-        ops.window_pool (already (B,T,nWh,nWw,C)) -> (B,T,H,W,C) after proj (+ residual)."""
-        qkv = ops.linear(x, self.qkv.weight, self.qkv.bias, out_dtype=torch.float16)
-        qkv_pooled = None
-        if self.uses_pooled:
-            if not isinstance(pooled, ops.SplitMat):      # reference layout (B,nWh,nWw,T,C) -> (B,T,nWh,nWw,C)
-                pooled = pooled.permute(0, 3, 1, 2, 4).contiguous()
-            qkv_pooled = ops.linear(pooled, self.qkv.weight, self.qkv.bias, out_dtype=torch.float16)
+        ops.window_pool (already (B,T,nWh,nWw,C)) -> (B,T,H,W,C) after proj (+ residual).
+        ``joint_shape`` = (B,T,H,W): x is the SplitMat of ``ops.layer_norm_pool`` (token rows followed by pooled rows) and
+        ONE qkv GEMM serves both."""
+        if joint_shape is not None:
+            B, T, H, W = joint_shape
+            wh, ww = self.window_size
+            n_tok = B * T * H * W
+            both = ops.linear(x, self.qkv.weight, self.qkv.bias, out_dtype=torch.float16)
+            qkv = both[:n_tok].view(B, T, H, W, -1)
+            qkv_pooled = both[n_tok:].view(B, T, H // wh, W // ww, -1)
+        else:
+            qkv = ops.linear(x, self.qkv.weight, self.qkv.bias, out_dtype=torch.float16)
+            qkv_pooled = None
+            if self.uses_pooled:
+                if not isinstance(pooled, ops.SplitMat):      # reference layout (B,nWh,nWw,T,C) -> (B,T,nWh,nWw,C)
+                    pooled = pooled.permute(0, 3, 1, 2, 4).contiguous()
+                qkv_pooled = ops.linear(pooled, self.qkv.weight, self.qkv.bias, out_dtype=torch.float16)
         out = ops.focal_window_attention(qkv, qkv_pooled, self.num_heads, self.window_size, self.expand_size,
                                          self.pooled_kernel(), self.scale, out_dtype="split")
         return ops.linear(out, self.proj.weight, self.proj.bias, residual=residual)
@@ -223,15 +233,18 @@ class TemporalFocalTransformerBlock(nn.Module):
     def _forward(self, x, output_size):
         shortcut = x
         B, T, H, W, C = x.shape
-        # LayerNorm writes the bf16 split operand of the qkv Linear; the window pooling reads the same pair
-        xn_split = ops.layer_norm(x, self.norm1.weight, self.norm1.bias, self.norm1.eps, out="split")
-        pooled = None
         if self.attn.uses_pooled:
             if H % self.window_size[0] or W % self.window_size[1]:
                 raise ValueError(f"token grid {H}x{W} must be a multiple of the window {self.window_size}")
+            # norm1 + focal window pooling in one kernel (pooled tokens accumulated in registers next to the LayerNorm);
+            # token rows and pooled rows share one operand buffer, so one qkv GEMM serves both
             lin = self.pool_layers[0]
-            pooled = ops.window_pool(xn_split, lin.weight, lin.bias, self.window_size, out="split")
-        x = self.attn.attend(xn_split, pooled, residual=shortcut)
+            rows, _ = ops.layer_norm_pool(x, self.norm1.weight, self.norm1.bias, self.norm1.eps, lin.weight, lin.bias,
+                                          self.window_size)
+            x = self.attn.attend(rows, None, residual=shortcut, joint_shape=(B, T, H, W))
+        else:
+            xn_split = ops.layer_norm(x, self.norm1.weight, self.norm1.bias, self.norm1.eps, out="split")
+            x = self.attn.attend(xn_split, None, residual=shortcut)
         y = ops.layer_norm(x, self.norm2.weight, self.norm2.bias, self.norm2.eps, out="split")
         return self.mlp(y.view(B, T * H * W, C), output_size, residual=x.view(B, T * H * W, C)).view(B, T, H, W, C)
 

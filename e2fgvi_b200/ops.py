@@ -217,11 +217,13 @@ def prop_prologue(prop, feat_n2, flow_n1, flow_prev):
 
 
 def deform_align_fused(x, head, flow_1, flow_2, w_packed, bias, deform_groups, max_residue_magnitude=10.0,
-                       out_dtype=torch.float32):
+                       out_dtype=torch.float32, out_split=False):
     """feat_prop.py:41-58 in one kernel: 10*tanh + flow.flip(1) add, sigmoid, deformable sampling, GEMM, bias.
 
     x (n,cin,h,w) fp16 channels_last; head (n,27*dg,h,w) fp32 channels_last (raw conv_offset output);
-    flow_k (n,2,h,w) any layout (converted to (n,h,w,2) fp32).  Returns (n,cout,h,w) channels_last.
+    flow_k (n,2,h,w) any layout (converted to (n,h,w,2) fp32).  Returns (n,cout,h,w) channels_last; with
+    ``out_split=True`` (fp32 output only) ``(tensor, SplitNHWC)`` — the bf16 operand pair of the backbone conv that
+    consumes the aligned features, written by the same epilogue.
     """
     grouped = isinstance(x, GroupedX)
     _need_cuda(None if grouped else x, head, flow_1, flow_2, w_packed, bias)
@@ -237,6 +239,18 @@ def deform_align_fused(x, head, flow_1, flow_2, w_packed, bias, deform_groups, m
     f2 = flow_2.permute(0, 2, 3, 1).contiguous().float()
     b32 = None if bias is None else bias.detach().float().contiguous()
     out = torch.empty((n, cout, h, w), dtype=out_dtype, device=head.device, memory_format=torch.channels_last)
+    if out_split:
+        if out_dtype != torch.float32:
+            raise ValueError("deform_align_fused: out_split goes with the fp32 output")
+        ohi = torch.empty((n, h, w, cout), dtype=torch.bfloat16, device=head.device)
+        olo = torch.empty((n, h, w, cout), dtype=torch.bfloat16, device=head.device)
+        with _timed("deform_align_fused", 2.0 * cout * cin * 9 * n * h * w):
+            st = _lib.load().e2f_deform_align_fused_split(
+                x.data_ptr(), head.data_ptr(), f1.data_ptr(), f2.data_ptr(), w_packed.data_ptr(),
+                None if b32 is None else b32.data_ptr(), out.data_ptr(), ohi.data_ptr(), olo.data_ptr(), n, h, w, cin,
+                cout, deform_groups, float(max_residue_magnitude), 1 if grouped else 0, _stream())
+        _lib.check(st, "e2f_deform_align_fused_split")
+        return out, SplitNHWC(ohi, olo, (n, cout, h, w))
     with _timed("deform_align_fused", 2.0 * cout * cin * 9 * n * h * w):
         st = _lib.load().e2f_deform_align_fused(
             x.data_ptr(), head.data_ptr(), f1.data_ptr(), f2.data_ptr(), w_packed.data_ptr(),
@@ -445,6 +459,34 @@ def layer_norm(x, weight, bias, eps=1e-5, out="f32"):
     _lib.check(st, "e2f_layernorm_split")
     sp = SplitMat(hi, lo) if want_split else None
     return o32 if out == "f32" else sp if out == "split" else (o32, sp)
+
+
+def layer_norm_pool(x, weight, bias, eps, pool_weight, pool_bias, window_size):
+    """norm1 + pool_layers[0] of a TemporalFocalTransformerBlock in one kernel (tfocal_transformer.py:470, :508-516):
+    LayerNorm every token and — from the normalised values still in registers — pool every (frame, window) with the
+    ``nn.Linear(wh*ww, 1)`` weights.  x (B,T,H,W,C) fp32, C = 512.
+
+    Returns ``(all_rows, n_tok)``: ``all_rows`` a ``SplitMat`` of shape (B*T*H*W + B*T*nWh*nWw, C) — the normalised
+    tokens followed by the pooled tokens ordered (B,T,nWh,nWw) — so ONE qkv ``linear`` over it yields qkv and qkv_pooled
+    back to back; ``n_tok`` = B*T*H*W."""
+    _need_cuda(x, weight, bias, pool_weight, pool_bias)
+    B, T, H, W, C = x.shape
+    wh, ww = window_size
+    if H % wh or W % ww:
+        raise ValueError(f"token grid {H}x{W} must be a multiple of the window {wh}x{ww}")
+    xc = x.contiguous().float()
+    n_tok, n_pool = B * T * H * W, B * T * (H // wh) * (W // ww)
+    hi = torch.empty((n_tok + n_pool, C), dtype=torch.bfloat16, device=x.device)
+    lo = torch.empty((n_tok + n_pool, C), dtype=torch.bfloat16, device=x.device)
+    g32, b32 = weight.detach().float().contiguous(), bias.detach().float().contiguous()
+    pw = pool_weight.detach().float().contiguous()
+    pb = None if pool_bias is None else pool_bias.detach().float().contiguous()
+    with _timed("layernorm_split", float(xc.numel() * 8 + n_pool * C * 4)):
+        st = _lib.load().e2f_layernorm_pool_split(xc.data_ptr(), g32.data_ptr(), b32.data_ptr(), pw.data_ptr(),
+                                                  None if pb is None else pb.data_ptr(), hi.data_ptr(), lo.data_ptr(),
+                                                  B * T, H, W, C, wh, ww, float(eps), _stream())
+    _lib.check(st, "e2f_layernorm_pool_split")
+    return SplitMat(hi, lo), n_tok
 
 
 def t2t_fold(tokens, output_size, kernel_size, stride, padding, normalize=False, bias=None, residual=None,
@@ -829,42 +871,107 @@ def _as_split_nhwc(x):
     return split_nhwc(x)
 
 
-def _conv_gather(src, w_hi, w_lo, bias, bias_map, residual, out, n, h_in, w_in, cout, stride, grid, taps, phases, ostep,
-                 out_size, flops):
-    """One launch of e2f_conv_gather_bf16x3.  taps: list of (dy, dx); phases: list of (first tap, oy, ox)."""
+def _nhwc_stride(t, what):
+    """Batch stride in PIXELS of a (n, h, w, c) tensor whose inner three dims are dense (a frame slice of a
+    (b, t, h, w, c) buffer is such a view)."""
+    n, h, w, c = t.shape
+    if t.stride()[1:] != (w * c, c, 1) or (n > 1 and t.stride(0) % c):
+        raise ValueError(f"{what}: expected a (n, h, w, c) tensor with dense (h, w, c) dims, got strides {t.stride()}")
+    return (t.stride(0) // c) if n > 1 else h * w
+
+
+def _conv_gather(sources, w_hi, w_lo, bias, bias_map, residual, out, cout, stride, grid, taps, phases, ostep,
+                 out_size, flops, slope=1.0, into=None):
+    """One launch of e2f_conv_gather_bf16x3.  sources: list of ``SplitNHWC`` (hi / lo may be batch-strided views);
+    taps: list of (dy, dx); phases: list of (first tap, oy, ox); residual: logical (n, cout, oh, ow) fp32 with NHWC
+    storage; ``into`` = (o32, ohi, olo) optional pre-existing (n, oh, ow, cout) NHWC views to write (batch-strided allowed,
+    all with the same batch stride, which the residual must share)."""
+    import ctypes
+    sources = list(sources)
+    n, _, h_in, w_in = sources[0].shape
     gh, gw = grid
     oh, ow = out_size
     tw, th = _best_tile(gh, gw, stride)
-    dev = src.hi.device
+    dev = sources[0].hi.device
     want_f32, want_split = out in ("f32", "both"), out in ("split", "both")
     if not (want_f32 or want_split):
         raise ValueError("out must be 'f32', 'split' or 'both'")
-    o32 = torch.empty((n, oh, ow, cout), dtype=torch.float32, device=dev) if want_f32 else None
-    ohi = torch.empty((n, oh, ow, cout), dtype=torch.bfloat16, device=dev) if want_split else None
-    olo = torch.empty((n, oh, ow, cout), dtype=torch.bfloat16, device=dev) if want_split else None
-    import ctypes
+    o32 = ohi = olo = None
+    if into is not None:
+        o32, ohi, olo = into
+        if (want_f32 and o32 is None) or (want_split and (ohi is None or olo is None)):
+            raise ValueError("conv: `into` lacks a buffer for the requested output")
+        o32 = o32 if want_f32 else None
+        ohi, olo = (ohi, olo) if want_split else (None, None)
+    else:
+        if want_f32:
+            o32 = torch.empty((n, oh, ow, cout), dtype=torch.float32, device=dev)
+        if want_split:
+            ohi = torch.empty((n, oh, ow, cout), dtype=torch.bfloat16, device=dev)
+            olo = torch.empty((n, oh, ow, cout), dtype=torch.bfloat16, device=dev)
+    outs = [t for t in (o32, ohi, olo) if t is not None]
+    for t in outs:
+        if tuple(t.shape) != (n, oh, ow, cout):
+            raise ValueError(f"conv: output buffer {tuple(t.shape)} != {(n, oh, ow, cout)}")
+    ostrides = {_nhwc_stride(t, "conv output") for t in outs}
+    res = None
+    if residual is not None:
+        res = residual.permute(0, 2, 3, 1)
+        if res.dtype != torch.float32 or res.stride()[1:] != (ow * cout, cout, 1):
+            res = res.contiguous().float()
+        ostrides.add(_nhwc_stride(res, "conv residual"))
+    if len(ostrides) != 1:
+        raise ValueError(f"conv: outputs and residual must share one batch stride, got {sorted(ostrides)}")
+    out_nstride = ostrides.pop()
+    k = len(sources)
+    for s_ in sources:
+        if (s_.shape[0], s_.shape[2], s_.shape[3]) != (n, h_in, w_in):
+            raise ValueError("conv sources must share N, H, W")
     nt, nph = len(taps), len(phases)
     dy = (ctypes.c_int8 * nt)(*[t[0] for t in taps])
     dx = (ctypes.c_int8 * nt)(*[t[1] for t in taps])
     tap0 = (ctypes.c_uint8 * (nph + 1))(*([p[0] for p in phases] + [nt]))
     oy = (ctypes.c_uint8 * nph)(*[p[1] for p in phases])
     ox = (ctypes.c_uint8 * nph)(*[p[2] for p in phases])
-    hi_arr = (_lib._vp * 1)(src.hi.data_ptr())
-    lo_arr = (_lib._vp * 1)(src.lo.data_ptr())
-    ch_arr = (_lib._i * 1)(src.hi.shape[-1])
+    hi_arr = (_lib._vp * k)(*[s_.hi.data_ptr() for s_ in sources])
+    lo_arr = (_lib._vp * k)(*[s_.lo.data_ptr() for s_ in sources])
+    ch_arr = (_lib._i * k)(*[s_.hi.shape[-1] for s_ in sources])
+    sn = [_nhwc_stride(s_.hi, "conv source") for s_ in sources]
+    for s_, v in zip(sources, sn):
+        if _nhwc_stride(s_.lo, "conv source") != v:
+            raise ValueError("conv: hi / lo of a source must share the batch stride")
+    sn_arr = (ctypes.c_int64 * k)(*sn)
     b32 = None if bias is None else bias.detach().float().contiguous()
-    res = None if residual is None else residual.permute(0, 2, 3, 1).contiguous().float()   # no-op if channels_last
     with _timed("conv3x3_bf16x3", flops):
         st = _lib.load().e2f_conv_gather_bf16x3(
-            1, hi_arr, lo_arr, ch_arr, w_hi.data_ptr(), w_lo.data_ptr(), None if b32 is None else b32.data_ptr(),
+            k, hi_arr, lo_arr, ch_arr, w_hi.data_ptr(), w_lo.data_ptr(), None if b32 is None else b32.data_ptr(),
             None if bias_map is None else bias_map.data_ptr(), None if res is None else res.data_ptr(),
             None if o32 is None else o32.data_ptr(), None if ohi is None else ohi.data_ptr(),
-            None if olo is None else olo.data_ptr(), n, h_in, w_in, cout, 1.0, stride, gh, gw, tw, th, nt, dy, dx, nph,
-            tap0, oy, ox, ostep, oh, ow, _stream())
+            None if olo is None else olo.data_ptr(), n, h_in, w_in, cout, float(slope), stride, gh, gw, tw, th, nt, dy, dx,
+            nph, tap0, oy, ox, ostep, oh, ow, sn_arr, out_nstride, _stream())
     _lib.check(st, "e2f_conv_gather_bf16x3")
     t32 = o32.permute(0, 3, 1, 2) if want_f32 else None
     sp = SplitNHWC(ohi, olo, (n, cout, oh, ow)) if want_split else None
     return t32 if out == "f32" else sp if out == "split" else (t32, sp)
+
+
+def conv_frames(sources, weight, bias=None, negative_slope=1.0, residual=None, out="f32", into=None):
+    """``conv3x3`` (k x k, stride 1, pad k//2, groups 1) whose sources, residual and outputs may be FRAME SLICES of
+    (b, t, h, w, c) buffers (batch-strided NHWC views): the per-frame tensors of BidirectionalPropagation
+    (feat_prop.py:88-149) are read and written in place — no ``x[:, i].contiguous()`` gathers, no stack / cat copies.
+    sources: list of ``SplitNHWC`` (or fp32 tensors, split on the fly); ``into`` = (o32, ohi, olo) NHWC views or None."""
+    cout, ks = weight.shape[0], weight.shape[2]
+    pad = ks // 2
+    _need_cuda(weight, bias, residual)
+    splits = [_as_split_nhwc(s_) for s_ in (sources if isinstance(sources, (list, tuple)) else [sources])]
+    chans = [s_.shape[1] for s_ in splits]
+    if any(s_.hi.shape[-1] != c for s_, c in zip(splits, chans)) or sum(chans) != weight.shape[1]:
+        raise ValueError("conv_frames: channel counts must be multiples of 8 and add up to the weight's input channels")
+    n, _, h, w = splits[0].shape
+    w_hi, w_lo, _ = _packed_conv_weight(weight, chans, 1)
+    taps = [(ky - pad, kx - pad) for ky in range(ks) for kx in range(ks)]
+    return _conv_gather(splits, w_hi, w_lo, bias, None, residual, out, cout, 1, (h, w), taps, [(0, 0, 0)], 1, (h, w),
+                        2.0 * n * h * w * cout * weight.shape[1] * ks * ks, slope=negative_slope, into=into)
 
 
 def soft_split(x, weight, bias, kernel_size, stride, padding):
@@ -887,7 +994,7 @@ def soft_split(x, weight, bias, kernel_size, stride, padding):
     w_hi, w_lo = _derived([weight], ("soft_split", c, k),
                           lambda: pack_conv3x3_weight(weight.detach().view(hidden, c, k, k), [c], 1))
     taps = [(ky - p, kx - p) for ky in range(k) for kx in range(k)]
-    tok = _conv_gather(src, w_hi, w_lo, bias, None, None, "f32", n, h, w, hidden, s, (fh, fw), taps, [(0, 0, 0)], 1,
+    tok = _conv_gather([src], w_hi, w_lo, bias, None, None, "f32", hidden, s, (fh, fw), taps, [(0, 0, 0)], 1,
                        (fh, fw), 2.0 * n * fh * fw * hidden * c * k * k)
     return tok.permute(0, 2, 3, 1).reshape(n, fh * fw, hidden)       # NHWC storage: a view
 
@@ -963,7 +1070,7 @@ def soft_comp(tokens, weight, bias, output_size, kernel_size, stride, padding, b
 
     bparams = [q for q in (bias, bias_map_extra) if q is not None]
     bias_map = _derived(bparams, ("soft_comp_bias", h, w, k, s), fold_bias) if bparams else None
-    return _conv_gather(src, w_hi, w_lo, None, bias_map, residual, out, n, fh, fw, c, 1, (fh, fw), taps, phases, s,
+    return _conv_gather([src], w_hi, w_lo, None, bias_map, residual, out, c, 1, (fh, fw), taps, phases, s,
                         (h, w), 2.0 * n * fh * fw * hidden * c * k * k)
 
 

@@ -90,6 +90,14 @@ int e2f_deform_align_fused(const void* x, const float* head, const float* flow1,
                            int cout, int deform_groups, float max_residue, int out_dtype, int x_layout,
                            void* stream);
 
+/* e2f_deform_align_fused with fp32 output PLUS the bf16 (hi, lo) split of the same values ([N][H][W][Cout] each): the
+ * operand pair of the backbone conv that consumes the aligned features (feat_prop.py:131-136), written by the DCN
+ * epilogue so that no separate split pass sits on the serial propagation chain. */
+int e2f_deform_align_fused_split(const void* x, const float* head, const float* flow1, const float* flow2,
+                                 const void* w_packed, const float* bias, float* out, void* out_hi, void* out_lo, int n,
+                                 int h, int w, int cin, int cout, int deform_groups, float max_residue, int x_layout,
+                                 void* stream);
+
 /* Temporal focal window attention core — replaces model/modules/tfocal_transformer.py:226-396 (everything in
  * WindowAttention.forward between the qkv Linear and the proj Linear): window partition of q, the own-window keys,
  * the 4 circularly rolled ring key sets (with their duplicated tokens), the pooled-window keys with the -100
@@ -146,6 +154,16 @@ int e2f_t2t_fold_unfold(const float* tokens_in, float* tokens, void* tokens_hi, 
  * permute(0,3,1,2,4), which is what the qkv Linear + attention consume.) */
 int e2f_window_pool(const void* x_hi, const void* x_lo, const float* weight, const float* bias, float* out, void* out_hi,
                     void* out_lo, int bt, int h, int w, int c, int wh, int ww, void* stream);
+
+/* norm1 + focal window pooling in ONE pass (tfocal_transformer.py:470 and :508-516): LayerNorm of every token and, from
+ * the normalised values still in registers, the pooled token of every (frame, window),
+ *   pooled[bt][wi][wj][c] = pool_b[0] + sum_{r<wh, q<ww} pool_w[r*ww + q] * LN(x)[bt][wi*wh + r][wj*ww + q][c].
+ * x [BT][H][W][C] fp32 (C = 512, H % wh == W % ww == 0).  out_hi / out_lo: bf16 [(BT*H*W + BT*(H/wh)*(W/ww))][C] — rows
+ * [0, BT*H*W) hold the split normalised tokens, the following BT*nW rows the split pooled tokens ordered (bt, wi, wj):
+ * one e2f_linear_bf16x3 over all rows yields qkv and qkv_pooled of e2f_focal_window_attention back to back. */
+int e2f_layernorm_pool_split(const float* x, const float* gamma, const float* beta, const float* pool_w,
+                             const float* pool_b, void* out_hi, void* out_lo, int bt, int h, int w, int c, int wh, int ww,
+                             float eps, void* stream);
 
 /* x2 bilinear upsample, align_corners=True (F.interpolate in deconv.forward, e2fgvi.py:125-129) of an NHWC fp32
  * tensor [N][H][W][C] (C % 8 == 0), written directly as the bf16 (hi, lo) split [N][2H][2W][C] consumed by
@@ -245,13 +263,18 @@ int e2f_conv2d_rows_bf16x3(int nsrc, const void* const* src_hi, const void* cons
  * out_h x out_w image for every GEMM-grid pixel (y, x) in grid_h x grid_w.  Weights: [Cout][ntaps * T * 64] bf16
  * (hi, lo), tap-major (in table order), then source, then 64-channel chunk (T = chunks over all sources).
  * tile_w * tile_h <= 128 grid pixels per tile (12 x 10 tiles the 20x36 / 60x108 / 90x162 token grids exactly).
- * bias: per-channel [Cout] or NULL; bias_map: fp32 [out_h][out_w][Cout] or NULL; residual: fp32 NHWC of the output. */
+ * bias: per-channel [Cout] or NULL; bias_map: fp32 [out_h][out_w][Cout] or NULL; residual: fp32 NHWC of the output.
+ * Batch strides (pixels between consecutive images; NULL / 0 = dense) let a source or the output be ONE FRAME of a
+ * (b, t, h, w, c) buffer — the per-frame tensors of BidirectionalPropagation (feat_prop.py:88-149) are then read and
+ * written in place, with no gather / stack copies: src_nstride[i] for source i, out_nstride for out, out_hi / out_lo and
+ * the residual alike. */
 int e2f_conv_gather_bf16x3(int nsrc, const void* const* src_hi, const void* const* src_lo, const int* src_channels,
                            const void* w_hi, const void* w_lo, const float* bias, const float* bias_map,
                            const float* residual, float* out, void* out_hi, void* out_lo, int n, int h_in, int w_in,
                            int cout, float leaky_slope, int stride, int grid_h, int grid_w, int tile_w, int tile_h,
                            int ntaps, const int8_t* tap_dy, const int8_t* tap_dx, int nphase, const uint8_t* ph_tap0,
-                           const uint8_t* ph_oy, const uint8_t* ph_ox, int ostep, int out_h, int out_w, void* stream);
+                           const uint8_t* ph_oy, const uint8_t* ph_ox, int ostep, int out_h, int out_w,
+                           const int64_t* src_nstride, int64_t out_nstride, void* stream);
 
 /* Fused prologue of one propagation step — replaces feat_prop.py:106-126 up to the offset-head conv:
  * the two feature warps, the second-order flow (flow_n1 + warp(flow_prev, flow_n1)), the operand splits of the offset

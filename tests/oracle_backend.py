@@ -18,7 +18,13 @@ def _pack(weight, deform_groups):
 
 
 def _fused(x, head, flow_1, flow_2, w_packed, bias, deform_groups, max_residue_magnitude=10.0,
-           out_dtype=torch.float32):
+           out_dtype=torch.float32, out_split=False):
+    y = _fused_plain(x, head, flow_1, flow_2, w_packed, bias, deform_groups, max_residue_magnitude, out_dtype)
+    return (y, _as_split(y)) if out_split else y
+
+
+def _fused_plain(x, head, flow_1, flow_2, w_packed, bias, deform_groups, max_residue_magnitude=10.0,
+                 out_dtype=torch.float32):
     o1, o2, mask = torch.chunk(head, 3, dim=1)
     off = max_residue_magnitude * torch.tanh(torch.cat((o1, o2), 1))
     a, b = torch.chunk(off, 2, dim=1)
@@ -94,14 +100,55 @@ def _window_pool(x, weight, bias, window_size, out="split"):
     return torch.nn.functional.linear(xw.transpose(4, 5), weight, bias).flatten(-2)
 
 
+def _layer_norm_pool(x, weight, bias, eps, pool_weight, pool_bias, window_size):
+    B, T, H, W, C = x.shape
+    y = torch.nn.functional.layer_norm(x, (C,), weight, bias, eps)
+    pooled = _window_pool(y, pool_weight, pool_bias, window_size).permute(0, 3, 1, 2, 4)      # (B,T,nWh,nWw,C)
+    return torch.cat([y.reshape(-1, C), pooled.reshape(-1, C)]), B * T * H * W
+
+
 def _pack_rows(x, lead, cin=None):
     return x
+
+
+def _dense(s):
+    """fp32 (n,c,h,w) of a conv source: a tensor, or a SplitNHWC whose hi / lo are (n,h,w,c) tensors (any dtype)."""
+    if isinstance(s, ops.SplitNHWC):
+        return (s.hi.float() + s.lo.float()).permute(0, 3, 1, 2)
+    return s
+
+
+def _as_split(y):
+    """(n,c,h,w) fp32 -> SplitNHWC stand-in: hi = the fp32 NHWC values, lo = zeros."""
+    nhwc = y.permute(0, 2, 3, 1).contiguous()
+    return ops.SplitNHWC(nhwc, torch.zeros_like(nhwc), tuple(y.shape))
+
+
+def _split_bf16(x):
+    return x.clone(), torch.zeros_like(x)
+
+
+def _conv_frames(sources, weight, bias=None, negative_slope=1.0, residual=None, out="f32", into=None):
+    F = torch.nn.functional
+    srcs = [_dense(s) for s in (sources if isinstance(sources, (list, tuple)) else [sources])]
+    y = F.leaky_relu(F.conv2d(torch.cat(srcs, 1), weight, bias, 1, weight.shape[2] // 2), negative_slope)
+    y = y if residual is None else y + residual
+    if into is not None:
+        o32, ohi, olo = into
+        nhwc = y.permute(0, 2, 3, 1)
+        for t_ in (o32, ohi):
+            if t_ is not None:
+                t_.copy_(nhwc)
+        if olo is not None:
+            olo.zero_()
+    sp = _as_split(y)
+    return y if out == "f32" else sp if out == "split" else (y, sp)
 
 
 def _conv3x3(sources, weight, bias=None, groups=1, negative_slope=1.0, residual=None, out="f32", stride=1,
              padding=None, out_lead=0):
     F = torch.nn.functional
-    srcs = sources if isinstance(sources, (list, tuple)) else [sources]
+    srcs = [_dense(s_) for s_ in (sources if isinstance(sources, (list, tuple)) else [sources])]
     if groups == 1:
         x = torch.cat(srcs, 1)
     else:  # group-wise concatenation (e2fgvi.py:103-108)
@@ -110,7 +157,7 @@ def _conv3x3(sources, weight, bias=None, groups=1, negative_slope=1.0, residual=
     pad = weight.shape[2] // 2 if padding is None else padding
     y = F.leaky_relu(F.conv2d(x, weight, bias, stride, pad, 1, groups), negative_slope)
     y = y if residual is None else y + residual
-    return (y, y) if out == "both" else y
+    return (y, _as_split(y)) if out == "both" else y
 
 
 def _split_nhwc(x):
@@ -124,6 +171,7 @@ def _linear(x, weight, bias=None, residual=None, out_dtype=torch.float32, tile_h
 
 def _soft_split(x, weight, bias, kernel_size, stride, padding):
     F = torch.nn.functional
+    x = _dense(x)
     return F.linear(F.unfold(x, kernel_size, padding=padding, stride=stride).permute(0, 2, 1), weight, bias)
 
 
@@ -146,14 +194,15 @@ def oracle_ops():
                                           "modulated_deform_conv2d", "focal_window_attention", "t2t_unfold",
                                           "t2t_fold", "linear", "conv3x3", "split_nhwc", "upsample2x_split",
                                           "layer_norm", "dcn_pack_input", "t2t_fold_unfold", "pack_rows", "window_pool",
-                                          "prop_prologue", "soft_split", "soft_comp")}
+                                          "prop_prologue", "soft_split", "soft_comp", "layer_norm_pool", "conv_frames", "split_bf16")}
     ops.flow_warp, ops.pack_dcn_weight, ops.deform_align_fused = _flow_warp, _pack, _fused
     ops.modulated_deform_conv2d, ops.focal_window_attention = _mdcn, _attention
     ops.t2t_unfold, ops.t2t_fold, ops.linear, ops.t2t_fold_unfold = _unfold, _fold, _linear, _fold_unfold
     ops.conv3x3, ops.split_nhwc, ops.pack_rows, ops.window_pool = _conv3x3, _split_nhwc, _pack_rows, _window_pool
     ops.upsample2x_split, ops.layer_norm, ops.dcn_pack_input = _upsample, _layer_norm, _dcn_pack_input
     ops.prop_prologue = _prop_prologue
-    ops.soft_split, ops.soft_comp = _soft_split, _soft_comp
+    ops.soft_split, ops.soft_comp, ops.layer_norm_pool = _soft_split, _soft_comp, _layer_norm_pool
+    ops.conv_frames, ops.split_bf16 = _conv_frames, _split_bf16
     try:
         yield
     finally:

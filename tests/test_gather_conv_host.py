@@ -17,9 +17,12 @@ def _split_cpu(x):
     return hi, (x - hi.float()).to(torch.bfloat16)
 
 
-def _gather_ref(src, w_hi, w_lo, bias, bias_map, residual, out, n, h_in, w_in, cout, stride, grid, taps, phases, ostep,
-                out_size, flops):
-    """e2f_conv_gather_bf16x3 semantics, fp64 on the CPU (one source)."""
+def _gather_ref(sources, w_hi, w_lo, bias, bias_map, residual, out, cout, stride, grid, taps, phases, ostep,
+                out_size, flops, slope=1.0, into=None):
+    """e2f_conv_gather_bf16x3 semantics, fp64 on the CPU (sources concatenated along channels, 64-ch chunk padding)."""
+    assert len(sources) == 1 and into is None and slope == 1.0
+    src = sources[0]
+    n, _, h_in, w_in = src.shape
     x = (src.hi.double() + src.lo.double())                      # (n, h_in, w_in, C)
     C = x.shape[-1]
     wt = (w_hi.double() + w_lo.double()).view(cout, len(taps), -1)[:, :, :C]    # K per tap is padded to 64-ch chunks

@@ -96,7 +96,8 @@ def test_modulated_deform_conv2d_unrounded_fp32_oracle(cuda, shape):
     Each product x*w carries two independent 2^-12-rms roundings; over K = 2304 terms of magnitude |x||w| the error
     of one output is ~ sqrt(K) * |x||w| * 2^-11.3 while the output itself is ~ sqrt(K) * |x||w| * E[mask * blend]:
     a few 1e-4 of the output scale.  Stated tolerance: 1e-3 of max|out| (the e2e budget is 1e-3 absolute on O(1))
-    and 3e-4 of rms(out) for the rms error."""
+    and 7e-4 of rms(out) for the rms error (three independent 2^-12-rms
+    roundings per product - x, weight, the sampled value - give ~5e-4)."""
     n, h, w = shape
     x, offset, mask, weight, bias = _dcn_inputs(n, h, w, seed=21)
     want = restate.modulated_deform_conv2d(x.double(), offset.double(), mask.double(), weight.double(), bias.double(),
@@ -105,7 +106,7 @@ def test_modulated_deform_conv2d_unrounded_fp32_oracle(cuda, shape):
                                       1, 1, 1, 1, 16).cpu().double()
     err = got - want
     assert err.abs().max().item() < 1e-3 * want.abs().max().item(), err.abs().max().item() / want.abs().max().item()
-    assert err.pow(2).mean().sqrt().item() < 3e-4 * want.pow(2).mean().sqrt().item()
+    assert err.pow(2).mean().sqrt().item() < 7e-4 * want.pow(2).mean().sqrt().item()
 
 
 def test_deform_align_fused_unrounded_fp32_oracle(cuda):
@@ -128,7 +129,7 @@ def test_deform_align_fused_unrounded_fp32_oracle(cuda):
     got = ops.deform_align_fused(x.to(cuda), head.to(cuda), f1.to(cuda), f2.to(cuda), wp, bias.to(cuda), 16, 10.0)
     err = got.cpu().double() - want
     assert err.abs().max().item() < 1e-3 * want.abs().max().item()
-    assert err.pow(2).mean().sqrt().item() < 3e-4 * want.pow(2).mean().sqrt().item()
+    assert err.pow(2).mean().sqrt().item() < 7e-4 * want.pow(2).mean().sqrt().item()
 
 
 def test_modulated_deform_conv2d_border_cases(cuda):
@@ -605,6 +606,35 @@ def test_window_pool(cuda, shape):
                         lin.weight.to(cuda), lin.bias.to(cuda), (wh, ww))
 
 
+@pytest.mark.parametrize("shape", [(2, 8, 20, 36, (5, 9)), (1, 3, 10, 18, (5, 9)), (1, 16, 30, 54, (5, 9))])
+def test_layer_norm_pool_fused(cuda, shape):
+    """norm1 + pool_layers[0] in one kernel (tfocal_transformer.py:470, :508-516): token rows == LayerNorm, the
+    trailing rows == the reference's window pooling of the normalised tokens, ordered (B,T,nWh,nWw)."""
+    import torch.nn.functional as F
+    B, T, H, W, (wh, ww) = shape
+    C = 512
+    g = torch.Generator().manual_seed(92)
+    x = torch.randn(B, T, H, W, C, generator=g) * 1.7 + 0.3
+    gamma = 1.0 + 0.1 * torch.randn(C, generator=g)
+    beta = 0.1 * torch.randn(C, generator=g)
+    lin = torch.nn.Linear(wh * ww, 1)
+    with torch.no_grad():
+        lin.weight.copy_(torch.randn(1, wh * ww, generator=g) / (wh * ww))
+        lin.bias.fill_(-0.21)
+    yn = F.layer_norm(x.double(), (C,), gamma.double(), beta.double(), 1e-5)
+    xw = yn.view(B, T, H // wh, wh, W // ww, ww, C).permute(0, 2, 4, 1, 3, 5, 6).reshape(B, H // wh, W // ww, T, wh * ww, C)
+    want_pool = F.linear(xw.transpose(4, 5), lin.weight.double(), lin.bias.double()).flatten(-2).permute(0, 3, 1, 2, 4)
+    rows, n_tok = ops.layer_norm_pool(x.to(cuda), gamma.to(cuda), beta.to(cuda), 1e-5, lin.weight.to(cuda),
+                                      lin.bias.to(cuda), (wh, ww))
+    assert n_tok == B * T * H * W and rows.shape == (n_tok + B * T * (H // wh) * (W // ww), C)
+    got = _join(rows).cpu().double()
+    assert (got[:n_tok].view(B, T, H, W, C) - yn).abs().max().item() < 5e-5
+    assert (got[n_tok:].view(B, T, H // wh, W // ww, C) - want_pool).abs().max().item() < 5e-5
+    with pytest.raises(ValueError):
+        ops.layer_norm_pool(x[:, :, :-1].to(cuda), gamma.to(cuda), beta.to(cuda), 1e-5, lin.weight.to(cuda),
+                            lin.bias.to(cuda), (wh, ww))
+
+
 # ------------------------------------------------------------------------------------------ SoftSplit / SoftComp as gather convs
 @pytest.mark.parametrize("shape", [(3, 128, 60, 108), (2, 64, 15, 27), (1, 128, 45, 81), (2, 128, 30, 54)])
 def test_soft_split_matches_unfold_linear(cuda, shape):
@@ -679,19 +709,26 @@ def test_bidirectional_propagation_matches_oracle_taps(cuda, fused):
     got_taps = []
     originals = {}
     for name, mod in prop.deform_align.items():
-        originals[name] = mod.align
+        originals[name] = (mod.align, mod.align_split)
 
         def recorder(*a, _orig=mod.align, _name=name, **kw):
             out = _orig(*a, **kw)
             got_taps.append((_name, out))
             return out
-        mod.align = recorder
+
+        def recorder_split(*a, _orig=mod.align_split, _name=name, **kw):      # frame-slice fast path: (fp32, SplitNHWC)
+            out = _orig(*a, **kw)
+            got_taps.append((_name, out[0]))
+            # the bf16 pair written by the DCN epilogue must be the split of the fp32 output
+            assert (out[1].hi.float() + out[1].lo.float() - out[0].permute(0, 2, 3, 1)).abs().max().item() < 1e-4
+            return out
+        mod.align, mod.align_split = recorder, recorder_split
     try:
         with torch.no_grad():
             got = prop(x.to(cuda), fb.to(cuda), ff.to(cuda))
     finally:
         for name, mod in prop.deform_align.items():
-            mod.align = originals[name]
+            mod.align, mod.align_split = originals[name]
     assert len(got_taps) == len(taps) == 2 * (t - 1)
     for (name, out), tap in zip(got_taps, taps):
         assert name == tap["dir"]
