@@ -38,6 +38,7 @@ SIGNATURES = {
                                _i, _i, _i, _i, _i, _f, _i, _i, _i, _vp]),
     "e2f_conv2d_rows_bf16x3": (_i, [_i, _c.POINTER(_vp), _c.POINTER(_vp), _c.POINTER(_i), _i, _vp, _vp, _fp, _fp, _fp, _vp,
                                     _vp, _i, _i, _i, _i, _i, _i, _f, _i, _i, _i, _vp]),
+    "e2f_conv3x3_tanh_nchw": (_i, [_vp, _vp, _i, _vp, _vp, _fp, _fp, _i, _i, _i, _i, _vp]),
     "e2f_conv_gather_bf16x3": (_i, [_i, _c.POINTER(_vp), _c.POINTER(_vp), _c.POINTER(_i), _vp, _vp, _fp, _fp, _fp, _fp,
                                     _vp, _vp, _i, _i, _i, _i, _f, _i, _i, _i, _i, _i, _i, _c.POINTER(_c.c_int8),
                                     _c.POINTER(_c.c_int8), _i, _c.POINTER(_c.c_uint8), _c.POINTER(_c.c_uint8),
@@ -49,6 +50,9 @@ SIGNATURES = {
     "e2f_window_pool": (_i, [_vp, _vp, _fp, _fp, _fp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "e2f_prop_prologue": (_i, [_fp, _fp, _fp, _c.c_int64, _fp, _c.c_int64, _vp, _vp, _vp, _vp, _fp, _fp, _vp, _vp, _vp,
                                _i, _i, _i, _i, _vp]),
+    "e2f_spynet_pyramid": (_i, [_fp, _fp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _fp, _fp, _vp]),
+    "e2f_spynet_level_input": (_i, [_fp, _fp, _vp, _vp, _fp, _i, _i, _i, _i, _i, _vp]),
+    "e2f_spynet_final": (_i, [_fp, _fp, _fp, _i, _i, _i, _i, _i, _i, _vp]),
     "e2f_video_prepare_clip": (_i, [_vp, _vp, _vp, _fp, _i, _i, _i, _i, _i, _vp]),
     "e2f_video_compose": (_i, [_fp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "e2f_video_blend": (_i, [_vp, _vp, _vp, _fp, _i, _c.c_int64, _vp]),

@@ -341,6 +341,19 @@ int e2f_conv_gather_bf16x3(int nsrc, const void* const* src_hi, const void* cons
   return finish(launch_conv3x3(nsrc, src_hi, src_lo, src_channels, w_hi, w_lo, bias, residual, out, out_hi, out_lo, n, h_in, w_in, cout, 1, leaky_slope, 0, stride, 0, 0, 0, static_cast<cudaStream_t>(stream), &g), who);
 }
 
+int e2f_conv3x3_tanh_nchw(const void* src_hi, const void* src_lo, int cin, const void* w_hi, const void* w_lo,
+                          const float* bias, float* out, int n, int h, int w, int cout, void* stream) {
+  const char* who = "e2f_conv3x3_tanh_nchw";
+  if (!src_hi || !src_lo || !w_hi || !w_lo || !out) { set_error("%s: null pointer", who); return E2F_ERR_BAD_ARG; }
+  if (n < 0 || h <= 0 || w <= 0 || cin <= 0 || cin % 8 || cout <= 0 || cout > 32 || (cout & 3) == 0) { set_error("%s: bad shape n=%d h=%d w=%d cin=%d cout=%d (cin %% 8 == 0, cout <= 32 and not a multiple of 4)", who, n, h, w, cin, cout); return E2F_ERR_UNSUPPORTED; }
+  if (!aligned(src_hi, 16) || !aligned(src_lo, 16) || !aligned(w_hi, 16) || !aligned(w_lo, 16) || !aligned(out, 4)) { set_error("%s: alignment", who); return E2F_ERR_ALIGNMENT; }
+  if (n == 0) return 0;
+  const void* hi[1] = {src_hi};
+  const void* lo[1] = {src_lo};
+  const int ch[1] = {cin};
+  return finish(launch_conv3x3(1, hi, lo, ch, w_hi, w_lo, bias, nullptr, out, nullptr, nullptr, n, h, w, cout, 1, 1.0f, 3, 1, 1, 0, 0, static_cast<cudaStream_t>(stream), nullptr, 3), who);
+}
+
 int e2f_conv2d_bf16x3(int nsrc, const void* const* src_hi, const void* const* src_lo, const int* src_channels,
                       const void* w_hi, const void* w_lo, const float* bias, const float* residual, float* out,
                       void* out_hi, void* out_lo, int n, int h, int w, int cout, int groups, float leaky_slope, int ksize,
@@ -385,6 +398,33 @@ int e2f_prop_prologue(const float* prop, const float* feat_n2, const float* flow
                                      static_cast<long long>(flow_prev_bstride), cond1_hi, cond1_lo, cond2_hi, cond2_lo, flow1_out,
                                      flow2_out, flows_hi, flows_lo, x_grouped, n, h, w, c, static_cast<cudaStream_t>(stream)),
                 "e2f_prop_prologue");
+}
+
+int e2f_spynet_pyramid(const float* frames, float* pyramid, int b, int t, int l_t, int H, int W, int h, int w, int h_up,
+                       int w_up, const float* mean3, const float* std3, void* stream) {
+  const char* who = "e2f_spynet_pyramid";
+  if (!frames || !pyramid || !mean3 || !std3) { set_error("%s: null pointer", who); return E2F_ERR_BAD_ARG; }
+  if (b < 0 || t <= 0 || l_t <= 0 || l_t > t || H <= 0 || W <= 0 || h <= 1 || w <= 1 || h > H || w > W) { set_error("%s: bad shape b=%d t=%d l_t=%d %dx%d -> %dx%d", who, b, t, l_t, H, W, h, w); return E2F_ERR_BAD_ARG; }
+  if (h_up < h || w_up < w || h_up % 32 || w_up % 32) { set_error("%s: the working size %dx%d must be multiples of 32 >= %dx%d", who, h_up, w_up, h, w); return E2F_ERR_BAD_ARG; }
+  return finish(launch_spynet_pyramid(frames, pyramid, b, t, l_t, H, W, h, w, h_up, w_up, mean3, std3, static_cast<cudaStream_t>(stream)), who);
+}
+
+int e2f_spynet_level_input(const float* level_img, const float* prev_flow, void* rows_hi, void* rows_lo, float* flow_up,
+                           int b, int l_t, int hk, int wk, int lead, void* stream) {
+  const char* who = "e2f_spynet_level_input";
+  if (!level_img || !rows_hi || !rows_lo || !flow_up) { set_error("%s: null pointer", who); return E2F_ERR_BAD_ARG; }
+  if (b < 0 || l_t < 2 || hk <= 0 || wk <= 0 || lead < 0 || lead > 8 || (prev_flow && ((hk | wk) & 1))) { set_error("%s: bad shape b=%d l_t=%d %dx%d lead=%d", who, b, l_t, hk, wk, lead); return E2F_ERR_BAD_ARG; }
+  if (!aligned(rows_hi, 16) || !aligned(rows_lo, 16) || !aligned(flow_up, 8) || (prev_flow && !aligned(prev_flow, 8))) { set_error("%s: alignment", who); return E2F_ERR_ALIGNMENT; }
+  return finish(launch_spynet_level_input(level_img, prev_flow, rows_hi, rows_lo, flow_up, b, l_t, hk, wk, lead, static_cast<cudaStream_t>(stream)), who);
+}
+
+int e2f_spynet_final(const float* flow, float* flows_forward, float* flows_backward, int b, int l_t, int h, int w, int h_up,
+                     int w_up, void* stream) {
+  const char* who = "e2f_spynet_final";
+  if (!flow || !flows_forward || !flows_backward) { set_error("%s: null pointer", who); return E2F_ERR_BAD_ARG; }
+  if (b < 0 || l_t < 2 || h <= 0 || w <= 0 || h_up < h || w_up < w) { set_error("%s: bad shape", who); return E2F_ERR_BAD_ARG; }
+  if (!aligned(flow, 8)) { set_error("%s: flow needs 8-byte alignment", who); return E2F_ERR_ALIGNMENT; }
+  return finish(launch_spynet_final(flow, flows_forward, flows_backward, b, l_t, h, w, h_up, w_up, static_cast<cudaStream_t>(stream)), who);
 }
 
 int e2f_video_prepare_clip(const uint8_t* frames, const uint8_t* masks, const int* ids, float* out, int t, int h, int w,

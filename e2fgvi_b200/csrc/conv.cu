@@ -78,6 +78,7 @@ struct Params {
   int8_t tap_dy[64], tap_dx[64];
   uint8_t ph_tap0[10], ph_oy[9], ph_ox[9];
   float slope;             // LeakyReLU negative slope (1 = identity)
+  int epi_flags;           // EPI_TANH: tanh after the activation; EPI_NCHW: fp32 output stored [N][Cout][out_H][out_W]
   const float* bias;
   const float* bias_map;   // optional fp32 [out_H][out_W][Cout] added per output pixel (folded Linear bias + sc.bias) or null
   const float* residual;   // NHWC fp32 [N][out_H][out_W][Cout] or null
@@ -85,6 +86,8 @@ struct Params {
   __nv_bfloat16* out_hi;   // NHWC bf16 split of the result (operand format of the next conv) or null
   __nv_bfloat16* out_lo;
 };
+
+constexpr int EPI_TANH = 1, EPI_NCHW = 2;     // both only on the element-wise store path (Cout % 4 != 0: the 3-channel output conv)
 
 __host__ __device__ constexpr uint32_t idesc_bf16(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(N >> 3) << 17) |
@@ -313,7 +316,13 @@ __device__ __forceinline__ void epilogue_tile(const Params& p, const TileCoord& 
               a = a > 0.f ? a : a * p.slope;
               if (p.residual) a += __ldg(p.residual + pix * p.Cout + cb + i);
               if (p.bias_map) a += __ldg(p.bias_map + mpix * p.Cout + cb + i);
-              if (p.out) p.out[pix * p.Cout + cb + i] = a;
+              if (p.epi_flags & EPI_TANH) a = tanhf(a);
+              if (p.out) {
+                if (p.epi_flags & EPI_NCHW)   // thread = pixel: consecutive lanes write consecutive x of one channel plane
+                  p.out[((static_cast<size_t>(t.n) * p.Cout + cb + i) * p.out_H + y) * p.out_W + x] = a;
+                else
+                  p.out[pix * p.Cout + cb + i] = a;
+              }
               if (p.out_hi) {
                 const __nv_bfloat16 hb = __float2bfloat16_rn(a);
                 p.out_hi[opix * p.Cout + cb + i] = hb;
@@ -734,8 +743,12 @@ int launch_pack_rows(const float* x, void* hi, void* lo, int n, int c, int h, in
 int launch_conv3x3(int nsrc, const void* const* src_hi, const void* const* src_lo, const int* src_channels,
                    const void* w_hi, const void* w_lo, const float* bias, const float* residual, float* out,
                    void* out_hi, void* out_lo, int n, int h_in, int w_in, int cout, int groups, float slope, int ks,
-                   int stride, int pad, int in_rows, int out_lead, cudaStream_t stream, const ConvGeom* geom) {
+                   int stride, int pad, int in_rows, int out_lead, cudaStream_t stream, const ConvGeom* geom, int epi_flags) {
   using namespace conv;
+  if (epi_flags && ((cout & 3) == 0 || out_hi || residual || geom)) {
+    set_error("conv: tanh / NCHW epilogues are implemented for the element-wise store path (Cout %% 4 != 0, fp32 output only)");
+    return -2;
+  }
   // GEMM grid = output size of the plain conv, or what the generalised geometry says
   const int h = geom ? geom->grid_h : (h_in + 2 * pad - ks) / stride + 1;
   const int w = geom ? geom->grid_w : (w_in + 2 * pad - ks) / stride + 1;
@@ -768,7 +781,7 @@ int launch_conv3x3(int nsrc, const void* const* src_hi, const void* const* src_l
   Params p;
   p.N = n; p.H = h; p.W = w; p.Cout = cout; p.groups = groups; p.nsrc = nsrc;
   p.ks = ks; p.stride = stride; p.pad = pad;
-  p.slope = slope; p.bias = bias; p.residual = residual; p.out = out;
+  p.slope = slope; p.bias = bias; p.residual = residual; p.out = out; p.epi_flags = epi_flags;
   p.out_hi = static_cast<__nv_bfloat16*>(out_hi); p.out_lo = static_cast<__nv_bfloat16*>(out_lo);
   p.chunks_total = 0;
   p.rows_px = p.rows_g = 0;

@@ -204,6 +204,24 @@ linear_kernel(const __grid_constant__ CUtensorMap tm_ah, const __grid_constant__
       if (et < BN) sb[et] = (bias && n0 + et < N) ? __ldg(bias + n0 + et) : 0.f;
       const bool row_ok = row < M;
       const size_t orow = static_cast<size_t>(row) * N;
+      // residual of one 32-column chunk as eight coalesced 16-byte loads per lane (4 lanes = one row's 64 bytes); the
+      // loads of chunk c+1 are issued before chunk c is stored, and chunk 0's before the accumulator is awaited, so
+      // their latency hides behind the main loop / the previous chunk's stores
+      uint4 ru[2][4], rn[2][4];
+      auto fetch = [&](int c, uint4 (&r)[2][4]) {
+        const int col0 = n0 + (half * CH + c) * 32;
+        const bool on = residual && vec_ok && c < CH && col0 + 32 <= N;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int R = rbase + j * 8 + prow;
+            r[h][j] = make_uint4(0u, 0u, 0u, 0u);
+            if (on && R < M) r[h][j] = __ldg(reinterpret_cast<const uint4*>(residual + static_cast<size_t>(R) * N + col0 + h * 16 + sub * 4));
+          }
+        }
+      };
+      fetch(0, ru);
       asm volatile("bar.sync 1, 256;" ::: "memory");           // bias slice visible to all epilogue warps
       mbar_wait(&acc_full[buf], (local >> 1) & 1);
       tc_fence_after_sync();
@@ -212,11 +230,11 @@ linear_kernel(const __grid_constant__ CUtensorMap tm_ah, const __grid_constant__
       for (int c = 0; c < CH; ++c) {
         uint32_t v[32];
         tmem_ld32(taddr + c * 32, v);
+        fetch(c + 1, rn);
         tmem_ld_wait();
         const int cl = (half * CH + c) * 32;                  // column offset inside the tile
         const int col0 = n0 + cl;
-        if (col0 >= N) continue;                              // warp-uniform
-        if (vec_ok && col0 + 32 <= N) {
+        if (col0 < N && vec_ok && col0 + 32 <= N) {
           float f[32];
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
@@ -227,17 +245,6 @@ linear_kernel(const __grid_constant__ CUtensorMap tm_ah, const __grid_constant__
             f[4 * i + 3] = __uint_as_float(v[4 * i + 3]) + b4.w;
           }
           if (residual) {
-            // all eight coalesced 16-byte loads of the chunk are in flight before the first one is consumed
-            uint4 ru[2][4];
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {                     // 16 fp32 columns = 64 bytes per row and pass
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const int R = rbase + j * 8 + prow;
-                ru[h][j] = make_uint4(0u, 0u, 0u, 0u);
-                if (R < M) ru[h][j] = __ldg(reinterpret_cast<const uint4*>(residual + static_cast<size_t>(R) * N + col0 + h * 16 + sub * 4));
-              }
-            }
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
 #pragma unroll
@@ -292,6 +299,11 @@ linear_kernel(const __grid_constant__ CUtensorMap tm_ah, const __grid_constant__
               else out[o + i] = __float2half_rn(val);
             }
           }
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) ru[h][j] = rn[h][j];
         }
       }
       tc_fence_before_sync();

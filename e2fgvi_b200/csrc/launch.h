@@ -92,11 +92,19 @@ struct ConvGeom {
 int launch_conv3x3(int nsrc, const void* const* src_hi, const void* const* src_lo, const int* src_channels,
                    const void* w_hi, const void* w_lo, const float* bias, const float* residual, float* out,
                    void* out_hi, void* out_lo, int n, int h_in, int w_in, int cout, int groups, float slope, int ks,
-                   int stride, int pad, int in_rows, int out_lead, cudaStream_t stream, const ConvGeom* geom = nullptr);
+                   int stride, int pad, int in_rows, int out_lead, cudaStream_t stream, const ConvGeom* geom = nullptr,
+                   int epi_flags = 0);     // 1: tanh, 2: NCHW fp32 output (3-channel output conv only)
 int conv_rows_tail(int lead, int channels);
 int conv_rows_pitch(int w, int lead, int channels);
 int launch_pack_rows(const float* x, void* hi, void* lo, int n, int c, int h, int w, int cin, int lead,
                      cudaStream_t stream);
+
+int launch_spynet_pyramid(const float* frames, float* pyr, int b, int t, int lt, int H, int W, int h, int w, int hu, int wu,
+                          const float* mean3, const float* std3, cudaStream_t stream);
+int launch_spynet_level_input(const float* img, const float* prev, void* hi, void* lo, float* flow_up, int b, int lt, int hk,
+                              int wk, int lead, cudaStream_t stream);
+int launch_spynet_final(const float* flow, float* out_fwd, float* out_bwd, int b, int lt, int h, int w, int hu, int wu,
+                        cudaStream_t stream);
 
 int launch_video_prepare_clip(const uint8_t* frames, const uint8_t* masks, const int* ids, float* out, int t, int h,
                               int w, int hp, int wp, cudaStream_t stream);

@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(256) t2t_unfold733_kernel(const float* __restr
 // OUT_NHWC (fold only): the image is written channels_last, [BT][H][W][C], with an optional residual of the same
 // layout added (enc_feat + trans_feat of e2fgvi.py:263 folded into the store) — the layout the decoder's convs read.
 template <bool FUSED, bool GELU, int CC, bool OUT_NHWC = false>
-__global__ void __launch_bounds__(256) t2t_fold733_kernel(const float* __restrict__ tin, float* __restrict__ tok,
+__global__ void __launch_bounds__(256, 2) t2t_fold733_kernel(const float* __restrict__ tin, float* __restrict__ tok,
                                                           __nv_bfloat16* __restrict__ tok_hi,
                                                           __nv_bfloat16* __restrict__ tok_lo, float* __restrict__ img,
                                                           const float* __restrict__ bias, int normalize, int C, int H,
@@ -204,11 +204,14 @@ __global__ void __launch_bounds__(256) t2t_fold733_kernel(const float* __restric
     const int ntx = b < FW ? (FW - 1 - b) / 3 + 1 : 0;
     const int ntok = active ? nty * ntx : 0;
     const float inv_ntx = 1.0f / static_cast<float>(max(ntx, 1));
-    // U tokens per thread in flight: all global loads of a batch are issued before the first shared-memory update
-    constexpr int U = 6;
-    for (int tt = tsub; tt < ntok; tt += TSUB * U) {
-      float4 v4[U];
-      int base[U], r0[U];
+    // U tokens per thread in flight: all global loads of a batch are issued before the first shared-memory update, and
+    // the NEXT batch's loads are issued before the current batch is folded (register double buffer), so a CTA's 8
+    // warps keep ~12 x 16 B per thread in flight.  The read-modify-writes of a batch are issued as loads-then-stores:
+    // the patches of one phase are disjoint and a thread's 4 elements are distinct addresses, but the compiler cannot
+    // know that, so `simg[i] += v` per element serialises LDS -> FADD -> STS chains (r01/r02 profiles: this kernel was
+    // latency-bound at 0.38 of HBM peak, 0.18 on the HQ shapes).
+    constexpr int U = 4;
+    auto issue = [&](int tt, float4 (&v4)[U], int (&base)[U], int (&r0)[U]) {
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const int t = tt + u * TSUB;
@@ -220,22 +223,43 @@ __global__ void __launch_bounds__(256) t2t_fold733_kernel(const float* __restric
           base[u] = r0[u] * WP + 3 * tx;
         }
       }
+    };
+    auto fold = [&](int tt, const float4 (&v4)[U], const int (&base)[U], const int (&r0)[U]) {
+      float cur[U][4];
+      bool ok[U][4];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-        if (tt + u * TSUB < ntok) {
-          const float v[4] = {v4[u].x, v4[u].y, v4[u].z, v4[u].w};
-          if (r0[u] >= 0 && r0[u] + 7 <= ROWS) {   // patch entirely inside the band: no per-element checks
+        const bool live = tt + u * TSUB < ntok;
+        const bool whole = r0[u] >= 0 && r0[u] + 7 <= ROWS;     // patch entirely inside the band: no per-element checks
 #pragma unroll
-            for (int e = 0; e < 4; ++e) simg[base[u] + off[e]] += v[e];
-          } else {
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int r = r0[u] + kyv[e];
-              if (r >= 0 && r < ROWS) simg[base[u] + off[e]] += v[e];
-            }
-          }
+        for (int e = 0; e < 4; ++e) {
+          const int r = r0[u] + kyv[e];
+          ok[u][e] = live && (whole || (r >= 0 && r < ROWS));
+          cur[u][e] = ok[u][e] ? simg[base[u] + off[e]] : 0.f;
         }
       }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const float v[4] = {v4[u].x, v4[u].y, v4[u].z, v4[u].w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (ok[u][e]) simg[base[u] + off[e]] = cur[u][e] + v[e];
+      }
+    };
+    float4 va[U], vb[U];
+    int ba[U], bb[U], ra[U], rb[U];
+    int tt = tsub;
+    if (tt < ntok) issue(tt, va, ba, ra);
+    while (tt < ntok) {
+      const int nx = tt + TSUB * U;
+      if (nx < ntok) issue(nx, vb, bb, rb);
+      fold(tt, va, ba, ra);
+      tt = nx;
+      if (tt >= ntok) break;
+      const int nx2 = tt + TSUB * U;
+      if (nx2 < ntok) issue(nx2, va, ba, ra);
+      fold(tt, vb, bb, rb);
+      tt = nx2;
     }
     __syncthreads();
   }

@@ -56,6 +56,19 @@ class BaseNetwork(nn.Module):
                 nn.init.normal_(m.weight.data, 0.0, gain)
                 if getattr(m, "bias", None) is not None:
                     nn.init.constant_(m.bias.data, 0.0)
+        self._invalidate_derived()          # `.data` updates do not bump Parameter versions
+
+    def _invalidate_derived(self):
+        """Forget every kernel operand derived from the parameters (see ``ops.invalidate_weight_caches``)."""
+        ops.invalidate_weight_caches()
+        for m in self.modules():
+            if isinstance(m, SecondOrderDeformableAlignment):
+                m._packed = None
+
+    def load_state_dict(self, *args, **kwargs):
+        out = super().load_state_dict(*args, **kwargs)
+        self._invalidate_derived()
+        return out
 
 
 class Encoder(nn.Module):
@@ -157,14 +170,28 @@ class InpaintGenerator(BaseNetwork):
 
     precision = "strict"
 
+    _warned_grad = False
+
     def forward(self, masked_frames, num_local_frames):
+        """INFERENCE ONLY, CUDA ONLY: the kernels have no backward (outputs carry no grad_fn) and there is no CPU path
+        (the reference's ``train.py`` / CPU use is out of scope)."""
+        # (CPU tensors fail loudly inside the first kernel wrapper: ops._need_cuda, "there is no CPU fallback")
+        if torch.is_grad_enabled() and not InpaintGenerator._warned_grad and any(p.requires_grad for p in self.parameters()):
+            import warnings
+            InpaintGenerator._warned_grad = True
+            warnings.warn("e2fgvi_b200.InpaintGenerator.forward is inference-only: its outputs do not track gradients "
+                          "(call it under torch.no_grad())", RuntimeWarning, stacklevel=2)
         with library_precision(self.precision):
             return self._forward(masked_frames, num_local_frames)
 
     def _forward(self, masked_frames, num_local_frames):
         l_t = num_local_frames
         b, t, ori_c, ori_h, ori_w = masked_frames.size()
-        pred_flows = self.forward_bidirect_flow((masked_frames[:, :l_t] + 1) / 2)
+        if masked_frames.is_cuda and l_t > 1:
+            # fused glue: (x + 1) / 2, the 1/4 downsample, the pyramids, per-level upsample + warp + cat (38 launches)
+            pred_flows = self.update_spynet.bidirect_flows(masked_frames, l_t)
+        else:
+            pred_flows = self.forward_bidirect_flow((masked_frames[:, :l_t] + 1) / 2)
 
         # encoder output: fp32 (b*t,c,h,w) in NHWC storage + its bf16 (hi, lo) split, both viewed as (b,t,h,w,c)
         enc32, enc_sp = self.encoder(masked_frames.reshape(b * t, ori_c, ori_h, ori_w), last_out="both")
@@ -195,16 +222,17 @@ class InpaintGenerator(BaseNetwork):
         # enc_feat + trans_feat (e2fgvi.py:263) is fused into SoftComp's fold / conv epilogue
         enc_feat = self.sc(tokens, t, fold_size if self.HQ else None, residual=enc_feat)
 
-        output = torch.tanh(self._decode(enc_feat))
-        return output.contiguous(), pred_flows
+        # tanh and the NCHW layout of the prediction are fused into the last decoder conv's epilogue
+        return self._decode(enc_feat), pred_flows
 
     def _decode(self, x):
-        """self.decoder (e2fgvi.py:143-150) with the convs on the tcgen05 kernel and LeakyReLU(0.2) fused."""
+        """tanh(self.decoder(x)) (e2fgvi.py:143-150, :262) with the convs on the tcgen05 kernel, LeakyReLU(0.2) fused, and
+        tanh + the NCHW store fused into the output conv."""
         d = self.decoder
         y = ops.conv3x3([ops.upsample2x_split(x)], d[0].conv.weight, d[0].conv.bias, negative_slope=0.2, out="split")
         y = ops.conv3x3([y], d[2].weight, d[2].bias, negative_slope=0.2)
         y = ops.conv3x3([ops.upsample2x_split(y)], d[4].conv.weight, d[4].conv.bias, negative_slope=0.2, out="split")
-        return ops.conv3x3([y], d[6].weight, d[6].bias)
+        return ops.conv3x3_tanh_nchw(y, d[6].weight, d[6].bias)
 
 
 class InpaintGeneratorHQ(InpaintGenerator):

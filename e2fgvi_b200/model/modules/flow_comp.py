@@ -56,6 +56,23 @@ class SPyNetBasicModule(nn.Module):
                 y = ops.conv3x3(y, conv.weight, conv.bias, negative_slope=0.0, out="split")
 
 
+def _basic_module_rows(module, rows, residual):
+    """SPyNetBasicModule on a ready row-gapped operand; the last conv adds ``residual`` = flow_up (flow_comp.py:127:
+    ``flow = flow_up + basic_module(...)``) in its epilogue and returns the new flow (P, hk, wk, 2) fp32."""
+    convs = [holder.conv for holder in module.basic_module]
+    y = rows
+    last = len(convs) - 1
+    for i, conv in enumerate(convs):
+        if i == last:
+            out = ops.conv3x3(y, conv.weight, conv.bias, negative_slope=1.0, out="f32", residual=residual.permute(0, 3, 1, 2))
+            return out.permute(0, 2, 3, 1)                     # NHWC storage: a view, (P, hk, wk, 2) contiguous
+        nxt = convs[i + 1]
+        if ops.rows_channels(nxt.in_channels) == nxt.in_channels:
+            y = ops.conv3x3(y, conv.weight, conv.bias, negative_slope=0.0, out="rows", out_lead=nxt.padding[0])
+        else:
+            y = ops.conv3x3(y, conv.weight, conv.bias, negative_slope=0.0, out="split")
+
+
 class SPyNet(nn.Module):
     """6-level coarse-to-fine flow estimator (flow_comp.py:49-169). ``forward(ref, supp) -> flow (n,2,h,w)``."""
 
@@ -84,6 +101,18 @@ class SPyNet(nn.Module):
             warped = flow_warp(s, flow_up.permute(0, 2, 3, 1), padding_mode="border")
             flow = flow_up + self.basic_module[level](torch.cat([r, warped, flow_up], 1))
         return flow
+
+    def bidirect_flows(self, masked_frames, num_local_frames):
+        """Both flow directions of ``InpaintGenerator.forward_bidirect_flow`` (e2fgvi.py:210-234) straight from the
+        masked frames (b,t,3,H,W) in [-1,1]: 1 pyramid launch, per level 1 input launch + five 7x7 convs, 1 final
+        launch.  Returns (flows_forward, flows_backward), each (b, l_t-1, 2, H/4, W/4)."""
+        pyr = ops.spynet_pyramid(masked_frames, num_local_frames, self.mean, self.std)
+        flow = None
+        for level in range(_NUM_LEVELS):
+            rows, flow_up = ops.spynet_level_input(pyr, _NUM_LEVELS - 1 - level, flow,
+                                                   lead=self.basic_module[level].basic_module[0].conv.padding[0])
+            flow = _basic_module_rows(self.basic_module[level], rows, flow_up)
+        return ops.spynet_final(flow, pyr)
 
     def forward(self, ref, supp):
         h, w = ref.shape[2:4]

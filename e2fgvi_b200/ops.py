@@ -964,9 +964,9 @@ def conv_frames(sources, weight, bias=None, negative_slope=1.0, residual=None, o
     pad = ks // 2
     _need_cuda(weight, bias, residual)
     splits = [_as_split_nhwc(s_) for s_ in (sources if isinstance(sources, (list, tuple)) else [sources])]
-    chans = [s_.shape[1] for s_ in splits]
-    if any(s_.hi.shape[-1] != c for s_, c in zip(splits, chans)) or sum(chans) != weight.shape[1]:
-        raise ValueError("conv_frames: channel counts must be multiples of 8 and add up to the weight's input channels")
+    chans = [s_.shape[1] for s_ in splits]         # true channel counts (storage may be zero-padded to a multiple of 8)
+    if sum(chans) != weight.shape[1]:
+        raise ValueError(f"conv_frames: source channels {chans} do not add up to the weight's {weight.shape[1]} input channels")
     n, _, h, w = splits[0].shape
     w_hi, w_lo, _ = _packed_conv_weight(weight, chans, 1)
     taps = [(ky - pad, kx - pad) for ky in range(ks) for kx in range(ks)]
@@ -1074,6 +1074,104 @@ def soft_comp(tokens, weight, bias, output_size, kernel_size, stride, padding, b
                         (h, w), 2.0 * n * fh * fw * hidden * c * k * k)
 
 
+def conv3x3_tanh_nchw(x, weight, bias):
+    """``torch.tanh(F.conv2d(x, weight, bias, 1, 1))`` returned as a CONTIGUOUS (N, Cout, H, W) fp32 tensor: the
+    decoder's 64 -> 3 output conv (e2fgvi.py:149-150) with the tanh of :262 and the NHWC -> NCHW layout change of the
+    prediction fused into the conv epilogue.  x: (N,C,H,W) fp32 or ``SplitNHWC``."""
+    src = _as_split_nhwc(x)
+    n, c, h, w = src.shape
+    cout = weight.shape[0]
+    _need_cuda(weight, bias)
+    if tuple(weight.shape[1:]) != (c, 3, 3) or cout > 32 or cout % 4 == 0:
+        raise ValueError(f"conv3x3_tanh_nchw: weight {tuple(weight.shape)} (needs (Cout, {c}, 3, 3), Cout <= 32, Cout % 4 != 0)")
+    w_hi, w_lo, _ = _packed_conv_weight(weight, [c], 1)
+    b32 = None if bias is None else bias.detach().float().contiguous()
+    out = torch.empty((n, cout, h, w), dtype=torch.float32, device=weight.device)
+    with _timed("conv3x3_bf16x3", 2.0 * n * h * w * cout * c * 9):
+        st = _lib.load().e2f_conv3x3_tanh_nchw(src.hi.data_ptr(), src.lo.data_ptr(), src.hi.shape[-1], w_hi.data_ptr(),
+                                               w_lo.data_ptr(), None if b32 is None else b32.data_ptr(), out.data_ptr(),
+                                               n, h, w, cout, _stream())
+    _lib.check(st, "e2f_conv3x3_tanh_nchw")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------- SPyNet glue
+class FlowPyramid:
+    """The six normalised pyramid levels of every local frame (``spynet_pyramid``)."""
+
+    __slots__ = ("levels", "b", "l_t", "size", "up")
+
+    def __init__(self, levels, b, l_t, size, up):
+        self.levels, self.b, self.l_t, self.size, self.up = levels, b, l_t, size, up
+
+
+def spynet_pyramid(masked_frames, num_local_frames, mean, std):
+    """Everything in front of SPyNet's first level, once per LOCAL FRAME (the reference does it per (ref, supp) pair):
+    ``(x + 1) / 2`` and the 1/4 bilinear downsample of e2fgvi.py:210-218,247, the resize to multiples of 32, the
+    normalisation and the five 2x2 average pools of flow_comp.py:95-115,152-158.  masked_frames (b,t,3,H,W) fp32;
+    mean / std: the (1,3,1,1) buffers.  Returns a ``FlowPyramid``: levels[k] = (b*l_t, 3, h_up >> k, w_up >> k) fp32."""
+    _need_cuda(masked_frames, mean, std)
+    b, t, c, H, W = masked_frames.shape
+    if c != 3:
+        raise ValueError("spynet_pyramid: frames must have 3 channels")
+    x = masked_frames.contiguous().float()
+    l_t = int(num_local_frames)
+    h, w = int(H * 0.25), int(W * 0.25)                 # F.interpolate(scale_factor=1/4, recompute_scale_factor=True)
+    hu = h if h % 32 == 0 else 32 * (h // 32 + 1)
+    wu = w if w % 32 == 0 else 32 * (w // 32 + 1)
+    n = b * l_t
+    sizes = [n * 3 * (hu >> k) * (wu >> k) for k in range(6)]
+    buf = torch.empty(sum(sizes), dtype=torch.float32, device=x.device)
+    m32, s32 = mean.detach().float().contiguous(), std.detach().float().contiguous()
+    st = _lib.load().e2f_spynet_pyramid(x.data_ptr(), buf.data_ptr(), b, t, l_t, H, W, h, w, hu, wu, m32.data_ptr(),
+                                        s32.data_ptr(), _stream())
+    _lib.check(st, "e2f_spynet_pyramid")
+    levels, off = [], 0
+    for k in range(6):
+        levels.append(buf[off: off + sizes[k]].view(n, 3, hu >> k, wu >> k))
+        off += sizes[k]
+    return FlowPyramid(levels, b, l_t, (h, w), (hu, wu))
+
+
+def spynet_level_input(pyr, k, prev_flow, lead=3):
+    """Input of one SPyNet level for all 2*b*(l_t-1) (ref, supp) pairs (forward pairs, then backward pairs): x2 flow
+    upsample * 2, border warp of the support frame, ``cat([ref, warped, flow_up])`` (flow_comp.py:121-133) as the
+    row-gapped ``RowsNHWC`` operand of the level's first 7x7 conv, plus ``flow_up`` (P, hk, wk, 2) fp32 — the residual the
+    level's last conv adds.  pyr: ``FlowPyramid``; k: pyramid level (5 = coarsest); prev_flow (P, hk/2, wk/2, 2) or None."""
+    img = pyr.levels[k]
+    _, _, hk, wk = img.shape
+    P = 2 * pyr.b * (pyr.l_t - 1)
+    numel = _rows_numel(P, hk, wk, lead, 8)
+    dev = img.device
+    hi = torch.empty(numel, dtype=torch.bfloat16, device=dev)
+    lo = torch.empty(numel, dtype=torch.bfloat16, device=dev)
+    flow_up = torch.empty((P, hk, wk, 2), dtype=torch.float32, device=dev)
+    if prev_flow is not None:
+        if tuple(prev_flow.shape) != (P, hk // 2, wk // 2, 2) or not prev_flow.is_contiguous() or prev_flow.dtype != torch.float32:
+            raise ValueError(f"spynet_level_input: prev_flow {tuple(prev_flow.shape)} != {(P, hk // 2, wk // 2, 2)} fp32 contiguous")
+    st = _lib.load().e2f_spynet_level_input(img.data_ptr(), None if prev_flow is None else prev_flow.data_ptr(),
+                                            hi.data_ptr(), lo.data_ptr(), flow_up.data_ptr(), pyr.b, pyr.l_t, hk, wk, lead,
+                                            _stream())
+    _lib.check(st, "e2f_spynet_level_input")
+    return RowsNHWC(hi, lo, (P, 8, hk, wk), lead, 8), flow_up
+
+
+def spynet_final(flow, pyr):
+    """flow_comp.py:160-167 for both directions: level-0 flow (P, h_up, w_up, 2) fp32 -> (flows_forward, flows_backward),
+    each (b, l_t-1, 2, h, w) fp32 (resize to (h, w), u * w / w_up, v * h / h_up)."""
+    _need_cuda(flow)
+    h, w = pyr.size
+    hu, wu = pyr.up
+    P = 2 * pyr.b * (pyr.l_t - 1)
+    if tuple(flow.shape) != (P, hu, wu, 2) or not flow.is_contiguous() or flow.dtype != torch.float32:
+        raise ValueError(f"spynet_final: flow {tuple(flow.shape)} != {(P, hu, wu, 2)} fp32 contiguous")
+    fwd = torch.empty((pyr.b, pyr.l_t - 1, 2, h, w), dtype=torch.float32, device=flow.device)
+    bwd = torch.empty((pyr.b, pyr.l_t - 1, 2, h, w), dtype=torch.float32, device=flow.device)
+    st = _lib.load().e2f_spynet_final(flow.data_ptr(), fwd.data_ptr(), bwd.data_ptr(), pyr.b, pyr.l_t, h, w, hu, wu, _stream())
+    _lib.check(st, "e2f_spynet_final")
+    return fwd, bwd
+
+
 def attention_flops(B, T, H, W, C, window_size, expand_size, focal_window, use_pooled=True):
     """Algorithmic FLOPs of one attention launch as the REFERENCE counts keys: QK^T + PV over
     T*(own window + listed ring keys incl. duplicates + fh*fw pooled keys incl. masked ones) keys per query."""
@@ -1082,6 +1180,16 @@ def attention_flops(B, T, H, W, C, window_size, expand_size, focal_window, use_p
     ring = 4 * (wh * ww - (wh - eh) * (ww - ew)) if (eh or ew) else 0
     keys = T * (wh * ww + ring + (focal_window[0] * focal_window[1] if use_pooled else 0))
     return 4.0 * B * T * H * W * keys * C
+
+
+def invalidate_weight_caches():
+    """Drop every operand derived from model parameters (bf16 splits, packed conv / gather-conv weights, folded bias
+    maps).  The caches key on ``(param._version, data_ptr)``; in-place updates through ``param.data`` (``nn.init`` on
+    ``.data``, EMA ``p.data.copy_()``, manual surgery) do NOT bump the version, so call this after such updates.
+    ``InpaintGenerator.init_weights`` and ``load_state_dict`` do it for you."""
+    _WEIGHT_SPLITS.clear()
+    _CONV_PACKS.clear()
+    _DERIVED.clear()
 
 
 def launch_count():

@@ -246,6 +246,14 @@ int e2f_conv2d_rows_bf16x3(int nsrc, const void* const* src_hi, const void* cons
                            float* out, void* out_hi, void* out_lo, int out_lead, int n, int h, int w, int cout, int groups,
                            float leaky_slope, int ksize, int stride, int pad, void* stream);
 
+/* The decoder's output conv with its tanh and the NCHW layout of the result fused into the epilogue — replaces
+ * `torch.tanh(self.decoder(...))` (model/e2fgvi.py:149-150 last nn.Conv2d(64, 3, 3, 1, 1) and :262) and the
+ * channels-last -> NCHW copy of the prediction: out [N][Cout][H][W] fp32 = tanh(conv3x3(x) + bias), x as one NHWC bf16
+ * (hi, lo) source with cin channels (cin % 8 == 0), weights packed like e2f_conv3x3_bf16x3, Cout <= 32 and not a
+ * multiple of 4 (the 3-channel image). */
+int e2f_conv3x3_tanh_nchw(const void* src_hi, const void* src_lo, int cin, const void* w_hi, const void* w_lo,
+                          const float* bias, float* out, int n, int h, int w, int cout, void* stream);
+
 /* "Gather conv": the same implicit GEMM with an explicit TAP TABLE, OUTPUT PHASES and tile shape (groups == 1).
  * Replaces, without ever building the unfolded operand:
  *   - SoftSplit (model/modules/tfocal_transformer.py:39-46; HQ _hq.py:39-46): F.unfold(7x7, stride 3, pad 3) + nn.Linear
@@ -292,6 +300,30 @@ int e2f_prop_prologue(const float* prop, const float* feat_n2, const float* flow
                       const float* flow_prev, int64_t flow_prev_bstride, void* cond1_hi, void* cond1_lo, void* cond2_hi,
                       void* cond2_lo, float* flow1_out, float* flow2_out, void* flows_hi, void* flows_lo, void* x_grouped,
                       int n, int h, int w, int c, void* stream);
+
+/* SPyNet glue (model/modules/flow_comp.py:84-169, model/e2fgvi.py:210-234) — one bidirectional flow estimate is
+ * 1 + 6 x (1 + five 7x7 convs) + 1 launches.
+ *   e2f_spynet_pyramid: frames (b, t, 3, H, W) fp32 in [-1, 1] -> for every LOCAL frame (j < l_t; index bi*l_t + j) the
+ *     six normalised pyramid levels: (x + 1) / 2 (e2fgvi.py:247), 1/4 bilinear downsample to h x w (align_corners=True,
+ *     e2fgvi.py:214-218), bilinear resize to h_up x w_up = multiples of 32 (align_corners=False, flow_comp.py:152-158),
+ *     (v - mean) / std (mean3 / std3: device pointers to the 3 buffer values, flow_comp.py:95-96), five 2x2 average
+ *     pools (:101-115).  `pyramid`: levels 0..5 back to back, level k = [b*l_t][3][h_up >> k][w_up >> k] fp32.
+ *   e2f_spynet_level_input: one pyramid level -> the level's network input for all P = 2*b*(l_t-1) (ref, supp) pairs
+ *     (direction-major: forward pairs (j, j+1) of every clip, then the backward pairs (j+1, j); e2fgvi.py:221-229):
+ *     flow_up = 2 * bilinear_x2(prev_flow) (align_corners=True, flow_comp.py:121-126; prev_flow NULL = level 0, zero
+ *     flow), border-mode warp of the support image (:128-132), cat([ref, warped, flow_up]) (:127-133) written as the
+ *     row-gapped 8-channel bf16 (hi, lo) operand of e2f_conv2d_rows_bf16x3 (lead zero pixels per row + tail, see
+ *     e2f_conv_rows_pitch / _tail) and flow_up [P][hk][wk][2] fp32 — the residual the level's last conv adds.
+ *     prev_flow: [P][hk/2][wk/2][2] fp32.
+ *   e2f_spynet_final: level-5 flow [P][h_up][w_up][2] fp32 -> bilinear resize to h x w (align_corners=False) and the
+ *     u * w / w_up, v * h / h_up rescale (flow_comp.py:160-167), written as flows_forward / flows_backward
+ *     (b, l_t - 1, 2, h, w) fp32 — pred_flows of InpaintGenerator.forward. */
+int e2f_spynet_pyramid(const float* frames, float* pyramid, int b, int t, int l_t, int H, int W, int h, int w, int h_up,
+                       int w_up, const float* mean3, const float* std3, void* stream);
+int e2f_spynet_level_input(const float* level_img, const float* prev_flow, void* rows_hi, void* rows_lo, float* flow_up,
+                           int b, int l_t, int hk, int wk, int lead, void* stream);
+int e2f_spynet_final(const float* flow, float* flows_forward, float* flows_backward, int b, int l_t, int h, int w, int h_up,
+                     int w_up, void* stream);
 
 /* Video-level driver — replaces the per-window host / eager-torch code of test.py:132-179.
  * All buffers are device memory; `frames` [N][H][W][3] uint8 RGB, `masks` [N][H][W] uint8 (non-zero = hole, already

@@ -160,6 +160,10 @@ def _conv3x3(sources, weight, bias=None, groups=1, negative_slope=1.0, residual=
     return (y, _as_split(y)) if out == "both" else y
 
 
+def _conv3x3_tanh_nchw(x, weight, bias):
+    return torch.tanh(torch.nn.functional.conv2d(_dense(x), weight, bias, 1, 1)).contiguous()
+
+
 def _split_nhwc(x):
     return x
 
@@ -194,7 +198,7 @@ def oracle_ops():
                                           "modulated_deform_conv2d", "focal_window_attention", "t2t_unfold",
                                           "t2t_fold", "linear", "conv3x3", "split_nhwc", "upsample2x_split",
                                           "layer_norm", "dcn_pack_input", "t2t_fold_unfold", "pack_rows", "window_pool",
-                                          "prop_prologue", "soft_split", "soft_comp", "layer_norm_pool", "conv_frames", "split_bf16")}
+                                          "prop_prologue", "soft_split", "soft_comp", "layer_norm_pool", "conv_frames", "split_bf16", "conv3x3_tanh_nchw")}
     ops.flow_warp, ops.pack_dcn_weight, ops.deform_align_fused = _flow_warp, _pack, _fused
     ops.modulated_deform_conv2d, ops.focal_window_attention = _mdcn, _attention
     ops.t2t_unfold, ops.t2t_fold, ops.linear, ops.t2t_fold_unfold = _unfold, _fold, _linear, _fold_unfold
@@ -202,7 +206,7 @@ def oracle_ops():
     ops.upsample2x_split, ops.layer_norm, ops.dcn_pack_input = _upsample, _layer_norm, _dcn_pack_input
     ops.prop_prologue = _prop_prologue
     ops.soft_split, ops.soft_comp, ops.layer_norm_pool = _soft_split, _soft_comp, _layer_norm_pool
-    ops.conv_frames, ops.split_bf16 = _conv_frames, _split_bf16
+    ops.conv_frames, ops.split_bf16, ops.conv3x3_tanh_nchw = _conv_frames, _split_bf16, _conv3x3_tanh_nchw
     try:
         yield
     finally:

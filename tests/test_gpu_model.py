@@ -50,6 +50,28 @@ def test_forward_matches_reference_golden(cuda, name):
         assert (got.cpu() - want).abs().max().item() < 2e-3 * max(1.0, want.abs().max().item())
 
 
+@pytest.mark.parametrize("shape", [(2, 4, 3, 120, 216), (1, 8, 5, 240, 432), (1, 3, 2, 128, 256)])
+def test_spynet_fused_glue_matches_oracle(cuda, shape):
+    """SPyNet with its glue as three kernels (pyramid per frame, per-level upsample + border warp + cat as the conv
+    operand, final resize + rescale; flow_comp.py:84-169, e2fgvi.py:210-234) against the CPU oracle, both directions.
+    Also against the module's own operator-by-operator path (``forward_bidirect_flow``)."""
+    from oracle import restate
+    b, t, l_t, H, W = shape
+    model = _model(False, "stress", 0, cuda)
+    sd = synth_state_dict(model, "stress", 0)
+    x = synth_frames(b, t, H, W, seed=17)
+    with torch.no_grad():
+        want_f, want_b = restate.bidirect_flow(sd, (x[:, :l_t] + 1) / 2)
+        got_f, got_b = model.update_spynet.bidirect_flows(x.to(cuda), l_t)
+        old_f, old_b = model.forward_bidirect_flow((x.to(cuda)[:, :l_t] + 1) / 2)
+    for got, want, old in ((got_f, want_f, old_f), (got_b, want_b, old_b)):
+        assert got.shape == want.shape == (b, l_t - 1, 2, H // 4, W // 4)
+        scale = max(1.0, want.abs().max().item())
+        # flows are O(1..90) pixels out of a 30-conv pyramid with x2 amplification per level: relative to their range
+        assert (got.cpu() - want).abs().max().item() < 2e-3 * scale
+        assert (got - old).abs().max().item() < 2e-3 * scale
+
+
 def test_batch_independence(cuda):
     """Clips are independent units: clip 0 of a b=2 batch equals the b=1 result."""
     model = _model(True, "stress", 0, cuda)

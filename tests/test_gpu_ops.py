@@ -635,6 +635,24 @@ def test_layer_norm_pool_fused(cuda, shape):
                             lin.bias.to(cuda), (wh, ww))
 
 
+@pytest.mark.parametrize("shape", [(2, 64, 48, 80), (1, 64, 17, 23), (3, 16, 8, 8)])
+def test_conv3x3_tanh_nchw(cuda, shape):
+    """Decoder output conv + tanh + NCHW store in one epilogue (e2fgvi.py:149-150, :262)."""
+    import torch.nn.functional as F
+    n, c, h, w = shape
+    g = torch.Generator().manual_seed(77)
+    x = torch.randn(n, c, h, w, generator=g)
+    conv = torch.nn.Conv2d(c, 3, 3, 1, 1)
+    with torch.no_grad():
+        conv.weight.mul_(3.0)                   # spread the pre-activations over tanh's curved range
+    want = torch.tanh(F.conv2d(x.double(), conv.weight.double(), conv.bias.double(), 1, 1))
+    conv = conv.to(cuda)
+    with torch.no_grad():
+        got = ops.conv3x3_tanh_nchw(x.to(cuda), conv.weight, conv.bias)
+    assert got.shape == want.shape and got.is_contiguous() and got.dtype == torch.float32
+    assert (got.cpu().double() - want).abs().max().item() < 2e-5
+
+
 # ------------------------------------------------------------------------------------------ SoftSplit / SoftComp as gather convs
 @pytest.mark.parametrize("shape", [(3, 128, 60, 108), (2, 64, 15, 27), (1, 128, 45, 81), (2, 128, 30, 54)])
 def test_soft_split_matches_unfold_linear(cuda, shape):
