@@ -752,7 +752,9 @@ int launch_conv3x3(int nsrc, const void* const* src_hi, const void* const* src_l
   // GEMM grid = output size of the plain conv, or what the generalised geometry says
   const int h = geom ? geom->grid_h : (h_in + 2 * pad - ks) / stride + 1;
   const int w = geom ? geom->grid_w : (w_in + 2 * pad - ks) / stride + 1;
-  const int tile_w = geom ? geom->tile_w : TILE_W, tile_h = geom ? geom->tile_h : TILE_H;
+  // images smaller than a 16 x 8 tile (SPyNet's coarse pyramid levels: 2x4, 4x8 pixels) take a tile of their own size:
+  // the A boxes shrink from 16 KB to 1-4 KB per K block, and these few-CTA launches are bound by the per-SM L2 port
+  const int tile_w = geom ? geom->tile_w : (w < TILE_W ? w : TILE_W), tile_h = geom ? geom->tile_h : (h < TILE_H ? h : TILE_H);
   const int ntaps = geom ? geom->ntaps : ks * ks;
   if (ntaps < 1 || ntaps > 64 || tile_w < 1 || tile_h < 1 || tile_w * tile_h > BM || tile_w * stride > 256 ||
       tile_h * stride > 256 || (geom && (geom->nphase < 1 || geom->nphase > 9 || geom->ostep < 1))) {
@@ -825,7 +827,7 @@ int launch_conv3x3(int nsrc, const void* const* src_hi, const void* const* src_l
                                 static_cast<cuuint64_t>(n)};
     const cuuint64_t strides[3] = {static_cast<cuuint64_t>(stride) * cin * 2, static_cast<cuuint64_t>(pitch) * cin * 2,
                                    static_cast<cuuint64_t>(h_in) * pitch * cin * 2};
-    const cuuint32_t box[4] = {BK, TILE_W, static_cast<cuuint32_t>(TILE_H * stride), 1};
+    const cuuint32_t box[4] = {BK, static_cast<cuuint32_t>(tile_w), static_cast<cuuint32_t>(tile_h * stride), 1};
     const cuuint32_t estr[4] = {1, 1, static_cast<cuuint32_t>(stride), 1};
     for (int part = 0; part < 2; ++part) {
       CUresult r = enc(part ? &maps.a_lo[0] : &maps.a_hi[0], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4,

@@ -12,18 +12,20 @@ class GraphedGenerator:
         if not example_frames.is_cuda:
             raise RuntimeError("GraphedGenerator needs a CUDA example input")
         self.model = model
+        # the un-graphed forward (InpaintGenerator.forward itself may dispatch to a graph replay)
+        self._eager = getattr(model, "_forward_eager", model)
         self.num_local_frames = num_local_frames
         self.static_in = example_frames.clone()
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side), torch.no_grad():
             for _ in range(warmup):               # builds the per-parameter operand caches, sets func attributes
-                model(self.static_in, num_local_frames)
+                self._eager(self.static_in, num_local_frames)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
         with torch.no_grad(), torch.cuda.graph(self.graph):
-            self.static_out, self.static_flows = model(self.static_in, num_local_frames)
+            self.static_out, self.static_flows = self._eager(self.static_in, num_local_frames)
 
     @torch.no_grad()
     def __call__(self, masked_frames, num_local_frames=None):

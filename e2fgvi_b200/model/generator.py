@@ -68,6 +68,8 @@ class BaseNetwork(nn.Module):
     def load_state_dict(self, *args, **kwargs):
         out = super().load_state_dict(*args, **kwargs)
         self._invalidate_derived()
+        if self._graphs is not None:
+            self._graphs = {}                               # captured graphs hold the old derived operands
         return out
 
 
@@ -181,8 +183,40 @@ class InpaintGenerator(BaseNetwork):
             InpaintGenerator._warned_grad = True
             warnings.warn("e2fgvi_b200.InpaintGenerator.forward is inference-only: its outputs do not track gradients "
                           "(call it under torch.no_grad())", RuntimeWarning, stacklevel=2)
+        if self._graphs is not None and masked_frames.is_cuda and not torch.cuda.is_current_stream_capturing():
+            return self._forward_graphed(masked_frames, num_local_frames)
+        return self._forward_eager(masked_frames, num_local_frames)
+
+    def _forward_eager(self, masked_frames, num_local_frames):
         with library_precision(self.precision):
             return self._forward(masked_frames, num_local_frames)
+
+    # ---- CUDA-graph replay behind the SAME call (model(x, l_t)): a single 432x240 clip is ~195 kernel launches for ~6 ms
+    # of GPU work, so launching from Python costs more than the GPU time.  Opt-in, because replay returns tensors
+    # produced by a captured allocation pool and requires the weights not to change between calls.
+    _graphs = None
+    _graph_limit = 4
+
+    def enable_cuda_graphs(self, enabled=True, max_shapes=4):
+        """``model.enable_cuda_graphs()``: every subsequent ``model(x, l_t)`` with a CUDA input replays a CUDA graph
+        captured on the first call with that (shape, l_t) (up to ``max_shapes`` distinct shapes are kept, least recently
+        used dropped).  Outputs are fresh tensors (copies of the graph's static outputs).  Weights must stay constant
+        (inference); call ``enable_cuda_graphs(False)`` or ``load_state_dict`` to drop the captures."""
+        self._graphs = {} if enabled else None
+        self._graph_limit = int(max_shapes)
+        return self
+
+    def _forward_graphed(self, masked_frames, num_local_frames):
+        from ..graph import GraphedGenerator
+        key = (tuple(masked_frames.shape), int(num_local_frames), masked_frames.device.index, masked_frames.dtype)
+        g = self._graphs.pop(key, None)
+        if g is None:
+            if len(self._graphs) >= self._graph_limit:
+                self._graphs.pop(next(iter(self._graphs)))
+            g = GraphedGenerator(self, masked_frames, num_local_frames)
+        self._graphs[key] = g                               # most recently used last
+        pred, flows = g(masked_frames)
+        return pred.clone(), tuple(f.clone() for f in flows)
 
     def _forward(self, masked_frames, num_local_frames):
         l_t = num_local_frames

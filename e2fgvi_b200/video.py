@@ -108,8 +108,13 @@ class VideoInpainter:
     frames (N,H,W,3) uint8 RGB and masks (N,H,W) uint8 (non-zero = hole, already dilated) may live on the host (they
     are uploaded once) or on the GPU.  ``clips_per_call`` same-shape windows share one forward."""
 
-    def __init__(self, model, neighbor_stride=5, ref_length=10, num_ref=-1, clips_per_call=4, rank=0, world=1):
+    def __init__(self, model, neighbor_stride=5, ref_length=10, num_ref=-1, clips_per_call=4, rank=0, world=1,
+                 cuda_graphs=True):
         self.model = model
+        # every window shape (clips per call, local frames, reference frames) repeats across a video and across
+        # videos: replay a CUDA graph per shape instead of ~200 Python-side launches per forward
+        if cuda_graphs and hasattr(model, "enable_cuda_graphs") and getattr(model, "_graphs", None) is None:
+            model.enable_cuda_graphs(True, max_shapes=8)
         self.neighbor_stride, self.ref_length, self.num_ref = neighbor_stride, ref_length, num_ref
         self.clips_per_call = max(1, clips_per_call)
         self.rank, self.world = rank, world

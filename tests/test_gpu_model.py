@@ -106,6 +106,25 @@ def test_reference_operator_goldens(cuda):
     assert got.shape == wa["out"].shape and rel < 2e-3, rel
 
 
+def test_cuda_graphs_behind_the_public_call(cuda):
+    """model.enable_cuda_graphs(): the SAME call replays a per-shape captured graph, bit-identical to eager, for
+    several shapes (LRU of captures) and fresh output tensors per call."""
+    model = _model(True, "stress", 0, cuda)
+    xs = [synth_frames(1, 4, 120, 216, seed=5).to(cuda), synth_frames(2, 4, 120, 216, seed=6).to(cuda)]
+    with torch.no_grad():
+        want = [model(x, 3) for x in xs]
+        model.enable_cuda_graphs(True, max_shapes=1)        # forces a re-capture when the shape alternates
+        for _ in range(2):
+            for x, (wp, (wf, wb)) in zip(xs, want):
+                pred, (ff, fb) = model(x, 3)
+                assert torch.equal(pred, wp) and torch.equal(ff, wf) and torch.equal(fb, wb)
+        first, _ = model(xs[0], 3)
+        second, _ = model(xs[0] * 0.5, 3)
+        assert first.data_ptr() != second.data_ptr() and torch.equal(first, want[0][0])
+        model.enable_cuda_graphs(False)
+        assert torch.equal(model(xs[0], 3)[0], want[0][0])
+
+
 def test_cuda_graph_replay_matches_eager(cuda):
     from e2fgvi_b200.graph import GraphedGenerator
     model = _model(True, "stress", 0, cuda)

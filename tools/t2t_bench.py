@@ -24,7 +24,10 @@ def fused():
     return ops.t2t_fold_unfold(tok, (60, 108), *geo, gelu=True, out="split")
 
 
+only = sys.argv[2] if len(sys.argv) > 2 else ""
 for name, fn in (("fold+unfold", pair), ("fused", fused)):
+    if only and only != name:
+        continue
     for _ in range(3):
         fn()
     torch.cuda.synchronize()
@@ -37,6 +40,8 @@ for name, fn in (("fold+unfold", pair), ("fused", fused)):
     us = e0.elapsed_time(e1) / 10 * 1e3
     print(f"T2T {name:12s} {us:8.1f} us   {tok.numel() * 8 / us / 1e6:.2f} TB/s of the fused kernel's algorithmic bytes")
 
+if only:
+    sys.exit(0)
 # SoftComp fold (tokens 64 x 720 x 6272 -> 128 x 60 x 108, + bias) and SoftSplit unfold (the reverse, split output)
 tok2 = torch.randn(bt, 720, 6272, device=dev)
 img2 = torch.randn(bt, 128, 60, 108, device=dev)
