@@ -447,6 +447,185 @@ int launch_t2t_unfold(const float* img, float* tok, void* tok_hi_v, void* tok_lo
   return static_cast<int>(cudaGetLastError());
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// FFN middle, second generation (round 2): fold -> / fold(ones) -> (GELU) -> unfold of FusionFeedForward
+// (tfocal_transformer.py:89-96) for the 7/3/3 geometry, one block per (4-channel chunk x token-column tile, token-row band,
+// image).  ncu of the first-generation kernel (profiles/r02): 200 M warp instructions per launch for 90 M elements, 53 %
+// of them integer / predicate arithmetic (per-token divisions, per-element band checks), issue slots 68 % busy at 24 %
+// occupancy — instruction-bound, 0.37 of the HBM peak; on the HQ shapes the full-width image left one block per SM
+// (0.18).  Changes:
+//   * the band's image in shared memory carries 2 token rows / columns of MARGIN on every side, so every patch of every
+//     token that touches the tile lands inside it: the fold is 4 x (LDS, FADD, STS) per float4 with NO bounds checks;
+//   * token coordinates advance incrementally (no divisions); loads of the next batch are issued before the current
+//     batch is folded (register double buffer);
+//   * wide images are tiled in x (<= 36 token columns per tile), so the shared-memory footprint — and 2 blocks per SM —
+//     no longer depend on the image width.
+// Tokens are visited in 9 phases (ty mod 3, tx mod 3): patches of one phase are disjoint (stride 3 * 3 >= 7), so plain
+// read-modify-writes suffice — no atomics, deterministic.
+constexpr int MID_CC = 4, MID_RUN4 = MID_CC * 49 / 4, MID_TSUB = 256 / MID_RUN4, MID_U = 4;
+
+template <bool GELU>
+__global__ void __launch_bounds__(256, 2) t2t_ffn_mid_kernel(const float* __restrict__ tin, float* __restrict__ tok,
+                                                             __nv_bfloat16* __restrict__ tok_hi,
+                                                             __nv_bfloat16* __restrict__ tok_lo, int C, int H, int W, int FH,
+                                                             int FW, int TR, int TW, int XT, int CKP) {
+  extern __shared__ float simg[];                  // [CC][R][WP] + int ny[R] + int nx[WP]
+  const int chunk = blockIdx.x / XT, xt = blockIdx.x - chunk * XT;
+  const int c0 = chunk * MID_CC;
+  const long long bt = blockIdx.z;
+  const int ty0 = blockIdx.y * TR, tx0 = xt * TW;                       // first OUTPUT token of the tile
+  const int tr = min(TR, FH - ty0), tw = min(TW, FW - tx0);
+  const int R = 3 * (TR + 4) + 4, WP = 3 * (TW + 4) + 4;                // image rows / columns held (incl. margins)
+  const int tyb = ty0 - 2, txb = tx0 - 2;                               // token whose patch starts at smem row / col 0
+  int* nytab = reinterpret_cast<int*>(simg + MID_CC * R * WP);
+  int* nxtab = nytab + R;
+  const int CK = C * 49;
+  {
+    float4* z = reinterpret_cast<float4*>(simg);                        // CC * R * WP * 4 bytes is a multiple of 16
+    for (int i = threadIdx.x; i < MID_CC * R * WP / 4; i += 256) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    // number of token rows / columns whose patch covers image row y / column x (0 outside the image)
+    for (int r = threadIdx.x; r < R; r += 256) {
+      const int y = 3 * tyb - 3 + r;
+      nytab[r] = (y >= 0 && y < H) ? max(0, min(FH - 1, (y + 3) / 3) - max(0, (y - 1) / 3) + 1) : 0;
+    }
+    for (int cc = threadIdx.x; cc < WP; cc += 256) {
+      const int x = 3 * txb - 3 + cc;
+      nxtab[cc] = (x >= 0 && x < W) ? max(0, min(FW - 1, (x + 3) / 3) - max(0, (x - 1) / 3) + 1) : 0;
+    }
+  }
+  // thread -> fixed float4 slot q4 of a token's CC*49 run (49 slots) x token lane tsub (5 lanes; 245 of 256 threads)
+  const int q4 = threadIdx.x % MID_RUN4, tsub = threadIdx.x / MID_RUN4;
+  const bool active = tsub < MID_TSUB;
+  int off[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const int q = q4 * 4 + e;
+    const int cc = q / 49, kk = q - cc * 49;
+    const int ky = kk / 7;
+    off[e] = (cc * R + ky) * WP + (kk - ky * 7);
+  }
+  __syncthreads();
+  // input tokens whose patches touch the tile's output patches
+  const int ty_lo = max(0, tyb), ty_hi = min(FH - 1, ty0 + tr + 1);
+  const int tx_lo = max(0, txb), tx_hi = min(FW - 1, tx0 + tw + 1);
+  const float* src = tin + bt * FH * FW * static_cast<long long>(CK) + c0 * 49 + q4 * 4;
+  for (int phase = 0; phase < 9; ++phase) {
+    const int a = phase / 3, b = phase - 3 * a;
+    const int fy = ty_lo + (a - ty_lo % 3 + 3) % 3, fx = tx_lo + (b - tx_lo % 3 + 3) % 3;   // first token of the phase
+    const int nty = fy <= ty_hi ? (ty_hi - fy) / 3 + 1 : 0, ntx = fx <= tx_hi ? (tx_hi - fx) / 3 + 1 : 0;
+    const int ntok = active ? nty * ntx : 0;
+    // this thread's tokens: linear index t = tsub, tsub + TSUB, ... over the (nty x ntx) grid, advanced incrementally
+    int iy = 0, ix = tsub;
+    while (ntx > 0 && ix >= ntx) { ix -= ntx; ++iy; }
+    auto advance = [&]() {
+      ix += MID_TSUB;
+      while (ix >= ntx) { ix -= ntx; ++iy; }
+    };
+    float4 va[MID_U], vb[MID_U];
+    int ba[MID_U], bb[MID_U];
+    auto issue = [&](int t, float4 (&v4)[MID_U], int (&base)[MID_U]) {
+#pragma unroll
+      for (int u = 0; u < MID_U; ++u) {
+        if (t + u * MID_TSUB < ntok) {
+          const int ty = fy + 3 * iy, tx = fx + 3 * ix;
+          v4[u] = __ldg(reinterpret_cast<const float4*>(src + static_cast<long long>(ty * FW + tx) * CK));
+          base[u] = 3 * (ty - tyb) * WP + 3 * (tx - txb);
+          advance();
+        }
+      }
+    };
+    auto fold = [&](int t, const float4 (&v4)[MID_U], const int (&base)[MID_U]) {
+      float cur[MID_U][4];
+#pragma unroll
+      for (int u = 0; u < MID_U; ++u) {
+        if (t + u * MID_TSUB < ntok) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) cur[u][e] = simg[base[u] + off[e]];
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < MID_U; ++u) {
+        if (t + u * MID_TSUB < ntok) {
+          simg[base[u] + off[0]] = cur[u][0] + v4[u].x;
+          simg[base[u] + off[1]] = cur[u][1] + v4[u].y;
+          simg[base[u] + off[2]] = cur[u][2] + v4[u].z;
+          simg[base[u] + off[3]] = cur[u][3] + v4[u].w;
+        }
+      }
+    };
+    int t = tsub;
+    if (t < ntok) issue(t, va, ba);
+    while (t < ntok) {
+      const int n1 = t + MID_TSUB * MID_U;
+      if (n1 < ntok) issue(n1, vb, bb);
+      fold(t, va, ba);
+      t = n1;
+      if (t >= ntok) break;
+      const int n2 = t + MID_TSUB * MID_U;
+      if (n2 < ntok) issue(n2, va, ba);
+      fold(t, vb, bb);
+      t = n2;
+    }
+    __syncthreads();
+  }
+  // per pixel: / (#token rows covering y) * (#token columns covering x), GELU; pixels outside the image (and pixels
+  // no patch covers) become exact zeros — they are the unfold's zero padding.  One warp per (channel, row).
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int rr = warp; rr < MID_CC * R; rr += 8) {
+    const int r = rr % R;
+    float* row = simg + rr * WP;
+    const int ny = nytab[r];
+    for (int xx = lane; xx < WP; xx += 32) {
+      const int cnt = ny * nxtab[xx];
+      float v = 0.f;
+      if (cnt) {
+        v = row[xx] / static_cast<float>(cnt);
+        if (GELU) v = gelu_exact(v);
+      }
+      row[xx] = v;
+    }
+  }
+  __syncthreads();
+  // unfold: the tr x tw tokens of the tile as coalesced runs (bf16 hi/lo operand pair and/or fp32)
+  {
+    const int nout = active ? tr * tw : 0;
+    int iy = 0, ix = tsub;
+    while (tw > 0 && ix >= tw) { ix -= tw; ++iy; }
+    for (int t = tsub; t < nout; t += MID_TSUB) {
+      const int base = 3 * (iy + 2) * WP + 3 * (ix + 2);
+      float v[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) v[e] = simg[base + off[e]];
+      const long long dst = ((bt * FH + ty0 + iy) * static_cast<long long>(FW) + tx0 + ix) * CKP + c0 * 49 + q4 * 4;
+      if (tok) *reinterpret_cast<float4*>(tok + dst) = make_float4(v[0], v[1], v[2], v[3]);
+      if (tok_hi) {
+        const __nv_bfloat162 h0 = __floats2bfloat162_rn(v[0], v[1]), h1 = __floats2bfloat162_rn(v[2], v[3]);
+        const float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
+        const __nv_bfloat162 l0 = __floats2bfloat162_rn(v[0] - f0.x, v[1] - f0.y), l1 = __floats2bfloat162_rn(v[2] - f1.x, v[3] - f1.y);
+        *reinterpret_cast<uint2*>(tok_hi + dst) = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
+        *reinterpret_cast<uint2*>(tok_lo + dst) = make_uint2(*reinterpret_cast<const uint32_t*>(&l0), *reinterpret_cast<const uint32_t*>(&l1));
+      }
+      ix += MID_TSUB;
+      while (ix >= tw) { ix -= tw; ++iy; }
+    }
+  }
+  // padded rows: the block of the last channel chunk zeroes columns [C*49, CKP) of its tokens (a following GEMM
+  // multiplies them by zero weights, so they only have to be finite — zeros keep the buffer deterministic)
+  if (CKP > CK && chunk == C / MID_CC - 1) {
+    const int padw = (CKP - CK) / 4;                             // both are multiples of 4
+    for (int i = threadIdx.x; i < tr * tw * padw; i += 256) {
+      const int tk = i / padw, j = i - tk * padw;
+      const int iy = tk / tw, ix = tk - iy * tw;
+      const long long dst = ((bt * FH + ty0 + iy) * static_cast<long long>(FW) + tx0 + ix) * CKP + CK + 4 * j;
+      if (tok) *reinterpret_cast<float4*>(tok + dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (tok_hi) {
+        *reinterpret_cast<uint2*>(tok_hi + dst) = make_uint2(0u, 0u);
+        *reinterpret_cast<uint2*>(tok_lo + dst) = make_uint2(0u, 0u);
+      }
+    }
+  }
+}
+
 // Band height (in token rows) of t2t_fold733_kernel and its dynamic shared memory: the tallest band that keeps 3 blocks
 // per SM; wide images (few rows fit) take up to 200 KB instead.  rows(tr) = 3*tr + extra image rows.  0 = does not fit.
 static int fold733_band(int w, int fh, int extra_rows, size_t* smem, int CC = 4) {
@@ -480,24 +659,34 @@ static void fold733_configure() {
 // shared memory; the caller then composes launch_t2t_fold + launch_t2t_unfold.
 int launch_t2t_fold_unfold(const float* tin, float* tok, void* tok_hi, void* tok_lo, int bt, int c, int h, int w, int k,
                            int s, int p, int gelu, int out_pitch, cudaStream_t stream) {
-  constexpr int CC = 4;                            // 4 channels = 784-byte runs per token, 16-byte aligned
-  if (k != 7 || s != 3 || p != 3 || c % CC) return -2;
+  if (k != 7 || s != 3 || p != 3 || c % MID_CC) return -2;
   const int fh = (h + 2 * p - k) / s + 1, fw = (w + 2 * p - k) / s + 1;
   if (bt == 0 || fh <= 0 || fw <= 0) return 0;
   if (bt > 65535) return -2;
-  size_t smem = 0;
-  const int tr = fold733_band(w, fh, 4, &smem);
-  if (tr < 1) return -2;
+  // tile: <= 36 token columns (x tiles evened out) and the tallest band of token rows that keeps two blocks per SM
+  const int xt = (fw + 35) / 36, tw = (fw + xt - 1) / xt;
+  const int wp = 3 * (tw + 4) + 4;
+  auto smem_of = [&](int tr) { return static_cast<size_t>(MID_CC) * (3 * (tr + 4) + 4) * wp * 4 + (3 * (tr + 4) + 4 + wp) * 4; };
+  int tr = fh < 12 ? fh : 12;
+  while (tr > 1 && smem_of(tr) > 100 * 1024) --tr;
+  const int bands = (fh + tr - 1) / tr;
+  tr = (fh + bands - 1) / bands;                   // even out the bands
+  const size_t smem = smem_of(tr);
+  if (smem > 200 * 1024 || bands > 65535) return -2;
+  static DeviceOnce cfg;
+  const int dev = current_device();
+  if (!device_done(cfg, dev)) {
+    cudaFuncSetAttribute(t2t_ffn_mid_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(t2t_ffn_mid_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    device_mark(cfg, dev);
+  }
   auto* hi = static_cast<__nv_bfloat16*>(tok_hi);
   auto* lo = static_cast<__nv_bfloat16*>(tok_lo);
-  const dim3 grid(c / CC, (fh + tr - 1) / tr, bt);
-  fold733_configure();
+  const dim3 grid((c / MID_CC) * xt, bands, bt);
   if (gelu)
-    t2t_fold733_kernel<true, true, CC><<<grid, 256, smem, stream>>>(tin, tok, hi, lo, nullptr, nullptr, 1, c, h, w, fh, fw, tr,
-                                                                    out_pitch);
+    t2t_ffn_mid_kernel<true><<<grid, 256, smem, stream>>>(tin, tok, hi, lo, c, h, w, fh, fw, tr, tw, xt, out_pitch);
   else
-    t2t_fold733_kernel<true, false, CC><<<grid, 256, smem, stream>>>(tin, tok, hi, lo, nullptr, nullptr, 1, c, h, w, fh, fw, tr,
-                                                                     out_pitch);
+    t2t_ffn_mid_kernel<false><<<grid, 256, smem, stream>>>(tin, tok, hi, lo, c, h, w, fh, fw, tr, tw, xt, out_pitch);
   count_launch();
   return static_cast<int>(cudaGetLastError());
 }

@@ -365,7 +365,7 @@ def t2t_fold_unfold(tokens, output_size, kernel_size, stride, padding, gelu=Fals
     fh, fw = (h + 2 * p - k) // s + 1, (w + 2 * p - k) // s + 1
     if n_tok != fh * fw or c * k * k != ck:
         raise ValueError(f"t2t_fold_unfold: tokens {tuple(tokens.shape)} do not match output_size {output_size}")
-    fused = (k, s, p) == (7, 3, 3) and c % 4 == 0 and bt <= 65535 and 16 * (w + 6) * 7 <= 200 * 1024
+    fused = (k, s, p) == (7, 3, 3) and c % 4 == 0 and bt <= 65535      # any width: the kernel tiles wide images in x
     if not fused:
         img = t2t_fold(tokens, output_size, kernel_size, stride, padding, normalize=True)
         return t2t_unfold(img, kernel_size, stride, padding, gelu=gelu, out=out)
