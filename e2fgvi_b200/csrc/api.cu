@@ -96,7 +96,7 @@ int e2f_modulated_deform_conv2d(const void* x, const float* offset, const float*
   int st = dcn_common_checks("e2f_modulated_deform_conv2d", x, w_packed, out, n, h, w, out_dtype);
   if (st) return st;
   if (!offset || !mask) { set_error("e2f_modulated_deform_conv2d: null offset/mask"); return E2F_ERR_BAD_ARG; }
-  if (!aligned(offset, 8)) { set_error("e2f_modulated_deform_conv2d: offset needs 8-byte alignment"); return E2F_ERR_ALIGNMENT; }
+  if (!aligned(offset, 16) || !aligned(mask, 16)) { set_error("e2f_modulated_deform_conv2d: offset / mask need 16-byte alignment"); return E2F_ERR_ALIGNMENT; }
   if (x_layout != E2F_X_NHWC && x_layout != E2F_X_GROUPED) { set_error("e2f_modulated_deform_conv2d: x_layout %d", x_layout); return E2F_ERR_BAD_ARG; }
   return finish(launch_dcn(x, offset, mask, nullptr, nullptr, nullptr, w_packed, bias, out, n, h, w, cin, cout,
                            deform_groups, 0.f, out_dtype, x_layout, static_cast<cudaStream_t>(stream)),
@@ -109,7 +109,7 @@ int e2f_deform_align_fused(const void* x, const float* head, const float* flow1,
   int st = dcn_common_checks("e2f_deform_align_fused", x, w_packed, out, n, h, w, out_dtype);
   if (st) return st;
   if (!head || !flow1 || !flow2) { set_error("e2f_deform_align_fused: null head/flow"); return E2F_ERR_BAD_ARG; }
-  if (!aligned(head, 8) || !aligned(flow1, 8) || !aligned(flow2, 8)) { set_error("e2f_deform_align_fused: head/flow need 8-byte alignment"); return E2F_ERR_ALIGNMENT; }
+  if (!aligned(head, 16) || !aligned(flow1, 8) || !aligned(flow2, 8)) { set_error("e2f_deform_align_fused: head needs 16-byte, flow 8-byte alignment"); return E2F_ERR_ALIGNMENT; }
   if (x_layout != E2F_X_NHWC && x_layout != E2F_X_GROUPED) { set_error("e2f_deform_align_fused: x_layout %d", x_layout); return E2F_ERR_BAD_ARG; }
   return finish(launch_dcn(x, nullptr, nullptr, head, flow1, flow2, w_packed, bias, out, n, h, w, cin, cout,
                            deform_groups, max_residue, out_dtype, x_layout, static_cast<cudaStream_t>(stream)),
@@ -124,7 +124,7 @@ int e2f_deform_align_fused_split(const void* x, const float* head, const float* 
   int st = dcn_common_checks(who, x, w_packed, out, n, h, w, E2F_F32);
   if (st) return st;
   if (!head || !flow1 || !flow2 || !out_hi || !out_lo) { set_error("%s: null pointer", who); return E2F_ERR_BAD_ARG; }
-  if (!aligned(head, 8) || !aligned(flow1, 8) || !aligned(flow2, 8) || !aligned(out_hi, 16) || !aligned(out_lo, 16)) { set_error("%s: head/flow need 8-byte, out_hi/out_lo 16-byte alignment", who); return E2F_ERR_ALIGNMENT; }
+  if (!aligned(head, 16) || !aligned(flow1, 8) || !aligned(flow2, 8) || !aligned(out_hi, 16) || !aligned(out_lo, 16)) { set_error("%s: head / out_hi / out_lo need 16-byte, flow 8-byte alignment", who); return E2F_ERR_ALIGNMENT; }
   if (x_layout != E2F_X_NHWC && x_layout != E2F_X_GROUPED) { set_error("%s: x_layout %d", who, x_layout); return E2F_ERR_BAD_ARG; }
   return finish(launch_dcn(x, nullptr, nullptr, head, flow1, flow2, w_packed, bias, out, n, h, w, cin, cout,
                            deform_groups, max_residue, E2F_F32, x_layout, static_cast<cudaStream_t>(stream), out_hi, out_lo), who);

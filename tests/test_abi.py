@@ -34,7 +34,7 @@ def test_argument_errors_without_gpu(lib):
     assert lib.e2f_flow_warp(8, 16, 16, 1, 4, 4, 8, 0, 0, None) == -3           # misaligned
     assert lib.e2f_focal_window_attention(16, 16, 16, 1, 2, 10, 18, 4, 64, 5, 9, 2, 4, 5, 9, 1, 0.1, 0, None) == -2
     assert lib.e2f_focal_window_attention(16, 16, 16, 1, 2, 11, 18, 4, 128, 5, 9, 2, 4, 5, 9, 1, 0.1, 0, None) == -1
-    assert lib.e2f_modulated_deform_conv2d(32, 8, 8, 128, None, 16, 1, 4, 4, 64, 128, 16, 0, 0, None) == -2
+    assert lib.e2f_modulated_deform_conv2d(32, 16, 16, 128, None, 16, 1, 4, 4, 64, 128, 16, 0, 0, None) == -2
     assert b"specialised" in lib.e2f_last_error()
 
 
