@@ -11,10 +11,11 @@
 
 namespace e2f {
 
-#ifndef E2F_SPIN_LIMIT
-// A lost arrive must end in a trap (launch failure), never in a hung GPU: bounded number of try_wait polls
-// (each poll suspends in hardware for up to the try_wait time limit, so this is seconds, not microseconds).
-#define E2F_SPIN_LIMIT (1u << 24)
+#ifndef E2F_WAIT_LIMIT_NS
+// A lost arrive must end in a trap (launch failure), never in a hung GPU: every 1024 polls the waiting thread reads
+// %globaltimer and traps once a single wait has lasted E2F_WAIT_LIMIT_NS (a healthy wait takes microseconds to a few
+// milliseconds).  Time-based, so the bound does not depend on how long one try_wait poll suspends in hardware.
+#define E2F_WAIT_LIMIT_NS 20000000000ull
 #endif
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -54,8 +55,14 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   // bare poll loop: waiting warps share an SM sub-partition with working warps, so the loop body must stay tiny
   uint32_t spins = 0;
+  uint64_t t0 = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > E2F_SPIN_LIMIT) asm volatile("trap;");
+    if (((++spins) & 1023u) == 0) {
+      uint64_t now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > E2F_WAIT_LIMIT_NS) asm volatile("trap;");
+    }
   }
 }
 

@@ -80,16 +80,7 @@ dcn_kernel(const __grid_constant__ CUtensorMap tmap_w, const __half* __restrict_
 
   if (warp < PRODUCER_WARPS) {
     // ------------------------------------------------------------------ A producer: sampler + im2col
-    // Four lanes cooperate on one sample point (round 2).  Round 1 gave every thread a whole sample point = 8 x 16-byte
-    // loads from 4 scattered corners, i.e. 32 different 128-byte lines per warp instruction: the L1 tag stage, which
-    // resolves one line per cycle, ran at 86 % while the tensor pipe idled at 12 % (profiles/r01 ncu_full_dcn).  In the
-    // group-major layout the two horizontally adjacent corners of a sample are ONE contiguous 64-byte run, so lanes
-    // (cx, ch) = (corner column, channel half) of a 4-lane group read it with one 16-byte load each: 8 line look-ups per
-    // warp instruction instead of 32, two instructions (top row, bottom row) per sample point.  Each lane blends its
-    // column in fp32, the two columns are summed across lanes (shfl.xor 2), the cx = 0 lanes round once to fp16 and store.
-    // A group owns output row r = tid / 4 and walks the 4 sample points of a K block.
-    const int r = tid >> 2, sub = tid & 3;
-    const int cx = sub >> 1, chh = sub & 1;
+    const int r = tid >> 2, s = tid & 3;
     const long long m = static_cast<long long>(blockIdx.x) * BLOCK_M + r;
     const bool row_valid = m < M;
     const long long mm = row_valid ? m : 0;
@@ -105,82 +96,79 @@ dcn_kernel(const __grid_constant__ CUtensorMap tmap_w, const __half* __restrict_
       fl1 = __ldg(flow1 + mm);
       fl2 = __ldg(flow2 + mm);
     }
-    // offsets / masks of the 4 sample points of K block j: 8 + 4 consecutive floats (16-byte aligned: 1728- / 1152- /
-    // 576-byte row pitches), the same addresses for the 4 lanes of a group
-    float4 oa_n = __ldg(reinterpret_cast<const float4*>(off_p)), ob_n = __ldg(reinterpret_cast<const float4*>(off_p) + 1);
-    float4 mk_n = __ldg(reinterpret_cast<const float4*>(msk_p));
+    const uint32_t row_off0 = sw128_offset(r, 2 * s), row_off1 = sw128_offset(r, 2 * s + 1);
+
+    float2 o_next = __ldg(reinterpret_cast<const float2*>(off_p) + s);
+    float m_next = __ldg(msk_p + s);
     for (int j = 0; j < NUM_KB; ++j) {
       const int stage = j % STAGES;
       const uint32_t phase = (j / STAGES) & 1;
-      const float4 oa = oa_n, ob = ob_n, mk4 = mk_n;
+      const int sp = j * SP_PER_KB + s;
+      float2 o = o_next;
+      float mk = m_next;
       if (j + 1 < NUM_KB) {
-        oa_n = __ldg(reinterpret_cast<const float4*>(off_p) + 2 * (j + 1));
-        ob_n = __ldg(reinterpret_cast<const float4*>(off_p) + 2 * (j + 1) + 1);
-        mk_n = __ldg(reinterpret_cast<const float4*>(msk_p) + (j + 1));
+        o_next = __ldg(reinterpret_cast<const float2*>(off_p) + sp + SP_PER_KB);
+        m_next = __ldg(msk_p + sp + SP_PER_KB);
       }
-      const float offs[8] = {oa.x, oa.y, oa.z, oa.w, ob.x, ob.y, ob.z, ob.w};
-      const float mks[4] = {mk4.x, mk4.y, mk4.z, mk4.w};
-      uint4 res[SP_PER_KB];
+      const int g = sp / TAPS, tap = sp - g * TAPS;
+      if (FUSED) {
+        // offset = max_res * tanh(o) + flow.flip(1): even channel (dy) gets v, odd (dx) gets u (feat_prop.py:41-50)
+        const float2 fl = (sp < NSP / 2) ? fl1 : fl2;
+        o.x = fmaf(max_res, fast_tanh(o.x), fl.y);
+        o.y = fmaf(max_res, fast_tanh(o.y), fl.x);
+        mk = fast_sigmoid(mk);
+      }
+      const int ti = tap / 3, tj = tap - ti * 3;
+      const float h_im = static_cast<float>(py - 1 + ti) + o.x;
+      const float w_im = static_cast<float>(px - 1 + tj) + o.y;
+      const bool inside = row_valid && (h_im > -1.f) && (w_im > -1.f) && (h_im < static_cast<float>(H)) &&
+                          (w_im < static_cast<float>(W));
+      float acc[16];
 #pragma unroll
-      for (int sidx = 0; sidx < SP_PER_KB; ++sidx) {
-        const int sp = j * SP_PER_KB + sidx;
-        float ox = offs[2 * sidx], oy = offs[2 * sidx + 1], mk = mks[sidx];
-        const int g = sp / TAPS, tap = sp - g * TAPS;
-        if (FUSED) {
-          // offset = max_res * tanh(o) + flow.flip(1): even channel (dy) gets v, odd (dx) gets u (feat_prop.py:41-50)
-          const float2 fl = (sp < NSP / 2) ? fl1 : fl2;
-          ox = fmaf(max_res, fast_tanh(ox), fl.y);
-          oy = fmaf(max_res, fast_tanh(oy), fl.x);
-          mk = fast_sigmoid(mk);
+      for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+      if (inside) {
+        const float fy = floorf(h_im), fx = floorf(w_im);
+        const float ly = h_im - fy, lx = w_im - fx;
+        const int y0 = static_cast<int>(fy), x0 = static_cast<int>(fx);
+        const __half* xg = GROUPED ? xn + static_cast<long long>(g) * H * W * CPG : xn + g * CPG;
+        uint4 lo[4], hi[4];
+        float wgt[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int dy = k >> 1, dx = k & 1;
+          const int yy = y0 + dy, xx = x0 + dx;
+          const bool in = (yy >= 0) && (yy < H) && (xx >= 0) && (xx < W);
+          wgt[k] = in ? (dy ? ly : 1.f - ly) * (dx ? lx : 1.f - lx) * mk : 0.f;
+          const int po = min(max(yy, 0), H - 1) * W + min(max(xx, 0), W - 1);
+          const uint4* p = reinterpret_cast<const uint4*>(xg + static_cast<long long>(po) * PIX_STRIDE);
+          lo[k] = __ldg(p);
+          hi[k] = __ldg(p + 1);
         }
-        const int ti = tap / 3, tj = tap - ti * 3;
-        const float h_im = static_cast<float>(py - 1 + ti) + ox;
-        const float w_im = static_cast<float>(px - 1 + tj) + oy;
-        const bool inside = row_valid && (h_im > -1.f) && (w_im > -1.f) && (h_im < static_cast<float>(H)) &&
-                            (w_im < static_cast<float>(W));
-        float acc[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-        if (inside) {                                     // uniform over the 4 lanes of the group
-          const float fy = floorf(h_im), fx = floorf(w_im);
-          const float ly = h_im - fy, lx = w_im - fx;
-          const int y0 = static_cast<int>(fy), x0 = static_cast<int>(fx);
-          const int xx = x0 + cx;                           // this lane's corner column
-          const bool x_in = (xx >= 0) && (xx < W);
-          const float wx = x_in ? (cx ? lx : 1.f - lx) * mk : 0.f;
-          const float wt = (y0 >= 0) ? wx * (1.f - ly) : 0.f;               // y0 < H follows from h_im < H
-          const float wb = (y0 + 1 < H) ? wx * ly : 0.f;                     // y0 + 1 >= 0 follows from h_im > -1
-          const __half* xg = GROUPED ? xn + static_cast<long long>(g) * H * W * CPG : xn + g * CPG;
-          const int xc = min(max(xx, 0), W - 1);
-          const uint4 top = __ldg(reinterpret_cast<const uint4*>(
-              xg + static_cast<long long>(min(max(y0, 0), H - 1) * W + xc) * PIX_STRIDE + chh * 8));
-          const uint4 bot = __ldg(reinterpret_cast<const uint4*>(
-              xg + static_cast<long long>(min(max(y0 + 1, 0), H - 1) * W + xc) * PIX_STRIDE + chh * 8));
-          const __half2* pt = reinterpret_cast<const __half2*>(&top);
-          const __half2* pb = reinterpret_cast<const __half2*>(&bot);
+        for (int k = 0; k < 4; ++k) {
+          const __half2* pl = reinterpret_cast<const __half2*>(&lo[k]);
+          const __half2* ph = reinterpret_cast<const __half2*>(&hi[k]);
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            const float2 a = __half22float2(pt[i]);
-            const float2 b = __half22float2(pb[i]);
-            acc[2 * i] = fmaf(wb, b.x, wt * a.x);
-            acc[2 * i + 1] = fmaf(wb, b.y, wt * a.y);
+            const float2 a = __half22float2(pl[i]);
+            const float2 b = __half22float2(ph[i]);
+            acc[2 * i] = fmaf(wgt[k], a.x, acc[2 * i]);
+            acc[2 * i + 1] = fmaf(wgt[k], a.y, acc[2 * i + 1]);
+            acc[8 + 2 * i] = fmaf(wgt[k], b.x, acc[8 + 2 * i]);
+            acc[8 + 2 * i + 1] = fmaf(wgt[k], b.y, acc[8 + 2 * i + 1]);
           }
         }
-        // the other corner column lives two lanes away (all 32 lanes take part in the shuffle)
-#pragma unroll
-        for (int i = 0; i < 8; ++i) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 2);
-        res[sidx].x = pack_half2(acc[0], acc[1]);
-        res[sidx].y = pack_half2(acc[2], acc[3]);
-        res[sidx].z = pack_half2(acc[4], acc[5]);
-        res[sidx].w = pack_half2(acc[6], acc[7]);
       }
+      uint4 v0, v1;
+      v0.x = pack_half2(acc[0], acc[1]);   v0.y = pack_half2(acc[2], acc[3]);
+      v0.z = pack_half2(acc[4], acc[5]);   v0.w = pack_half2(acc[6], acc[7]);
+      v1.x = pack_half2(acc[8], acc[9]);   v1.y = pack_half2(acc[10], acc[11]);
+      v1.z = pack_half2(acc[12], acc[13]); v1.w = pack_half2(acc[14], acc[15]);
+
       mbar_wait(&empty[stage], phase ^ 1);
-      if (cx == 0) {                                        // lanes (0, ch): 16 bytes = 8 channels of every sample point
-        uint8_t* a_tile = sA + stage * A_BYTES;
-#pragma unroll
-        for (int sidx = 0; sidx < SP_PER_KB; ++sidx)
-          *reinterpret_cast<uint4*>(a_tile + sw128_offset(r, 2 * sidx + chh)) = res[sidx];
-      }
+      uint8_t* a_tile = sA + stage * A_BYTES;
+      *reinterpret_cast<uint4*>(a_tile + row_off0) = v0;
+      *reinterpret_cast<uint4*>(a_tile + row_off1) = v1;
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(&full_a[stage]);

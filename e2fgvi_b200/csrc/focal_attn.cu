@@ -41,6 +41,7 @@ constexpr int KATOM = BN * 128;            // [64 keys][64 halfs] swizzled sub-t
 constexpr int QTILE = 2 * QATOM;           // 32 KB
 constexpr int KTILE = 2 * KATOM;           // 16 KB
 constexpr int KV_STAGES = 2;
+constexpr int BIAS_SLOTS = 4;              // logit-bias rows outlive their K stage (the K stage is recycled after S, not PV)
 constexpr int SOFTMAX_WARPS = 4, LOADER_WARPS = 4;
 constexpr int SOFTMAX_THREADS = SOFTMAX_WARPS * 32;
 constexpr int MMA_WARP = SOFTMAX_WARPS + LOADER_WARPS;
@@ -58,11 +59,11 @@ struct Smem {
   static constexpr int K = Q + QTILE;
   static constexpr int V = K + KV_STAGES * KTILE;
   static constexpr int KEYPTR = V + KV_STAGES * KTILE;          // [128] uint64 (Q rows at start, then [stages][64])
-  static constexpr int BIAS = KEYPTR + BM * 8;                  // [stages][64] float
-  static constexpr int FTAB = BIAS + KV_STAGES * BN * 4;        // [MAX_FRAME_KEYS] int32: key offset inside its frame
+  static constexpr int BIAS = KEYPTR + BM * 8;                  // [BIAS_SLOTS][64] float (slot = key tile & 3)
+  static constexpr int FTAB = BIAS + BIAS_SLOTS * BN * 4;       // [MAX_FRAME_KEYS] int32: key offset inside its frame
   static constexpr int FBIAS = FTAB + MAX_FRAME_KEYS * 4;       // [MAX_FRAME_KEYS] float: logit bias (log2 multiplicity)
   static constexpr int BARS = FBIAS + MAX_FRAME_KEYS * 4;
-  static constexpr int NUM_BARS = 1 + 3 * KV_STAGES + 2 + 2 + 2;
+  static constexpr int NUM_BARS = 1 + 4 * KV_STAGES + 2 + 2 + 2;
   static constexpr int TMEM_SLOT = BARS + NUM_BARS * 8;
   static constexpr int BYTES = TMEM_SLOT + 16;
 };
@@ -198,8 +199,9 @@ __global__ void __launch_bounds__(THREADS, CTAS_PER_SM) focal_attn_kernel(const 
   uint64_t* q_full = bars;
   uint64_t* k_full = bars + 1;
   uint64_t* v_full = k_full + KV_STAGES;
-  uint64_t* kv_empty = v_full + KV_STAGES;
-  uint64_t* s_full = kv_empty + KV_STAGES;      // [2] S tile written by the MMA
+  uint64_t* k_empty = v_full + KV_STAGES;       // K stage read by S(kt): free again as soon as that MMA group completes
+  uint64_t* v_empty = k_empty + KV_STAGES;      // V stage read by PV(kt)
+  uint64_t* s_full = v_empty + KV_STAGES;       // [2] S tile written by the MMA
   uint64_t* p_full = s_full + 2;                // [2] P written into the S tile's columns by the softmax warps
   uint64_t* pv_done = p_full + 2;               // [2] PV MMA of that buffer complete (O updated, buffer reusable)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + Smem::TMEM_SLOT);
@@ -249,7 +251,8 @@ __global__ void __launch_bounds__(THREADS, CTAS_PER_SM) focal_attn_kernel(const 
     for (int s = 0; s < KV_STAGES; ++s) {
       mbar_init(&k_full[s], LOADER_WARPS);
       mbar_init(&v_full[s], LOADER_WARPS);
-      mbar_init(&kv_empty[s], 1);
+      mbar_init(&k_empty[s], 1);
+      mbar_init(&v_empty[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&s_full[s], 1);
@@ -282,7 +285,7 @@ __global__ void __launch_bounds__(THREADS, CTAS_PER_SM) focal_attn_kernel(const 
       // Two passes over the S tile in 32-column chunks (TMEM re-reads are cheap; holding all 64 logits plus the 32
       // packed outputs in registers does not fit the 96-register budget of 2 CTAs/SM and went to local memory).
       const uint32_t s_addr = lane_addr + COL_S + sb * BN;
-      const float4* bias4 = reinterpret_cast<const float4*>(key_bias + stage * BN);
+      const float4* bias4 = reinterpret_cast<const float4*>(key_bias + (kt & (BIAS_SLOTS - 1)) * BN);
       float mx = -INFINITY;
       if (dbg & 1) {
         mx = 0.f;
@@ -486,31 +489,40 @@ __global__ void __launch_bounds__(THREADS, CTAS_PER_SM) focal_attn_kernel(const 
         }
       }
       if (lt == 0 && kt < 12) stamp(1);                  // [5kt+0] index math done
-      mbar_wait(&kv_empty[stage], ((kt / KV_STAGES) & 1) ^ 1);
-      if (lt == 0 && kt < 12) stamp(1);                  // [5kt+1] stage free
+      // The K stage is recycled as soon as S(kt-2) has read it (k_empty, committed right behind that MMA group), the V
+      // stage only after PV(kt-2) (v_empty): the gather of K(kt) — the operand the next S waits for — overlaps the
+      // softmax and the PV of the tiles in flight instead of starting after them.  Round 1 recycled both on PV(kt-2),
+      // which exposed one full gather latency per key tile (profiles/r01 attn_trace).
+      mbar_wait(&k_empty[stage], ((kt / KV_STAGES) & 1) ^ 1);
+      if (lt == 0 && kt < 12) stamp(1);                  // [5kt+1] K stage free
       if (lt < BN) {
         key_ptr[stage * BN + lt] = p;
-        key_bias[stage * BN + lt] = bias;
+        key_bias[(kt & (BIAS_SLOTS - 1)) * BN + lt] = bias;
       }
       loader_barrier();
-      if (!(dbg & 2) || kt < KV_STAGES) {
-        gather_rows<BN>(smem_u32(smem + Smem::K + stage * KTILE), key_ptr + stage * BN, lwarp, lane, 0);
-        cp_async_commit();
-        gather_rows<BN>(smem_u32(smem + Smem::V + stage * KTILE), key_ptr + stage * BN, lwarp, lane, prm.C);
-        cp_async_commit();
+      if (!(dbg & 2) || kt < KV_STAGES) gather_rows<BN>(smem_u32(smem + Smem::K + stage * KTILE), key_ptr + stage * BN, lwarp, lane, 0);
+      cp_async_commit();
+      if (lt == 0 && kt < 12) stamp(1);                  // [5kt+2] K gather issued
+      if (kt > 0) {                                      // V(kt-1), committed one group earlier, has landed
+        cp_async_wait<1>();
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&v_full[(kt - 1) % KV_STAGES]);
       }
-      if (lt == 0 && kt < 12) stamp(1);                  // [5kt+2] gathers issued
-      cp_async_wait<1>();                               // K landed
+      cp_async_wait<0>();                               // K landed
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(&k_full[stage]);
       if (lt == 0 && kt < 12) stamp(1);                  // [5kt+3] K landed + arrived
-      cp_async_wait<0>();                               // V landed
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&v_full[stage]);
-      if (lt == 0 && kt < 12) stamp(1);                  // [5kt+4] V landed + arrived
+      mbar_wait(&v_empty[stage], ((kt / KV_STAGES) & 1) ^ 1);
+      if (!(dbg & 2) || kt < KV_STAGES) gather_rows<BN>(smem_u32(smem + Smem::V + stage * KTILE), key_ptr + stage * BN, lwarp, lane, prm.C);
+      cp_async_commit();
+      if (lt == 0 && kt < 12) stamp(1);                  // [5kt+4] V gather issued
     }
+    cp_async_wait<0>();                                 // V of the last tile
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&v_full[(num_kt - 1) % KV_STAGES]);
   } else {
     // =================================================================== tcgen05 issuer
     if (elect_one()) {   // one thread, chosen by elect.sync: ptxas then emits bare UTCHMMA (no per-instruction ELECT loop)
@@ -535,6 +547,7 @@ __global__ void __launch_bounds__(THREADS, CTAS_PER_SM) focal_attn_kernel(const 
                      dk + (k < 4 ? 0 : (KATOM >> 4)) + 2 * (k & 3), idesc_s, k != 0);
         }
         umma_commit(&s_full[sb]);
+        umma_commit(&k_empty[stage]);                    // S(kt) was the only reader of this K stage
       };
       mbar_wait(q_full, 0);
       issue_s(0);
@@ -562,7 +575,7 @@ __global__ void __launch_bounds__(THREADS, CTAS_PER_SM) focal_attn_kernel(const 
                 : "memory");
           }
         }
-        umma_commit(&kv_empty[stage]);
+        umma_commit(&v_empty[stage]);
         umma_commit(&pv_done[sb]);
         if (kt < 15) stamp(2);                           // [4kt+2] PV issued
         if (kt + 2 < num_kt) issue_s(kt + 2);           // tensor pipe order: ... PV(kt), S(kt+2), PV(kt+1), ...

@@ -570,12 +570,14 @@ __global__ void __launch_bounds__(256, 2) t2t_ffn_mid_kernel(const float* __rest
   }
   // per pixel: / (#token rows covering y) * (#token columns covering x), GELU; pixels outside the image (and pixels
   // no patch covers) become exact zeros — they are the unfold's zero padding.  One warp per (channel, row).
+  // Only rows / columns [6, 3*t + 13) are read by the tile's output patches (the margins only absorb stray patch rows).
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int rr = warp; rr < MID_CC * R; rr += 8) {
-    const int r = rr % R;
-    float* row = simg + rr * WP;
+  const int nr = 3 * tr + 7, ncol = 3 * tw + 7;
+  for (int rr = warp; rr < MID_CC * nr; rr += 8) {
+    const int cc = rr / nr, r = rr - cc * nr + 6;
+    float* row = simg + (cc * R + r) * WP;
     const int ny = nytab[r];
-    for (int xx = lane; xx < WP; xx += 32) {
+    for (int xx = 6 + lane; xx < 6 + ncol; xx += 32) {
       const int cnt = ny * nxtab[xx];
       float v = 0.f;
       if (cnt) {
@@ -657,12 +659,35 @@ static void fold733_configure() {
 
 // Fused fold/normalise/unfold(/GELU).  Returns -2 (unsupported) when the geometry is not 7/3/3 or no band fits in
 // shared memory; the caller then composes launch_t2t_fold + launch_t2t_unfold.
+// First-generation launch (whole image width per block): measured faster than the x-tiled kernel while the image is
+// narrow enough for >= 2 blocks per SM (432x240 clips: 280 vs 310 us per launch at 8 clips, profiles/r02).
+static int launch_fold733_fullwidth(const float* tin, float* tok, void* tok_hi, void* tok_lo, int bt, int c, int h, int w,
+                                    int fh, int fw, int gelu, int out_pitch, cudaStream_t stream) {
+  constexpr int CC = 4;
+  size_t smem = 0;
+  const int tr = fold733_band(w, fh, 4, &smem);
+  if (tr < 1) return -2;
+  auto* hi = static_cast<__nv_bfloat16*>(tok_hi);
+  auto* lo = static_cast<__nv_bfloat16*>(tok_lo);
+  const dim3 grid(c / CC, (fh + tr - 1) / tr, bt);
+  fold733_configure();
+  if (gelu)
+    t2t_fold733_kernel<true, true, CC><<<grid, 256, smem, stream>>>(tin, tok, hi, lo, nullptr, nullptr, 1, c, h, w, fh, fw, tr,
+                                                                    out_pitch);
+  else
+    t2t_fold733_kernel<true, false, CC><<<grid, 256, smem, stream>>>(tin, tok, hi, lo, nullptr, nullptr, 1, c, h, w, fh, fw, tr,
+                                                                     out_pitch);
+  count_launch();
+  return static_cast<int>(cudaGetLastError());
+}
+
 int launch_t2t_fold_unfold(const float* tin, float* tok, void* tok_hi, void* tok_lo, int bt, int c, int h, int w, int k,
                            int s, int p, int gelu, int out_pitch, cudaStream_t stream) {
   if (k != 7 || s != 3 || p != 3 || c % MID_CC) return -2;
   const int fh = (h + 2 * p - k) / s + 1, fw = (w + 2 * p - k) / s + 1;
   if (bt == 0 || fh <= 0 || fw <= 0) return 0;
   if (bt > 65535) return -2;
+  if (fw <= 40) return launch_fold733_fullwidth(tin, tok, tok_hi, tok_lo, bt, c, h, w, fh, fw, gelu, out_pitch, stream);
   // tile: <= 36 token columns (x tiles evened out) and the tallest band of token rows that keeps two blocks per SM
   const int xt = (fw + 35) / 36, tw = (fw + xt - 1) / xt;
   const int wp = 3 * (tw + 4) + 4;
