@@ -171,6 +171,16 @@ class InpaintGenerator(BaseNetwork):
         return fwd, bwd
 
     precision = "strict"
+    overlap_flow = True          # SPyNet on a side stream next to the encoder (see _forward)
+    _side_streams = None
+
+    def _side_stream(self, device):
+        if self._side_streams is None:
+            self._side_streams = {}
+        key = device.index if device.index is not None else torch.cuda.current_device()
+        if key not in self._side_streams:
+            self._side_streams[key] = torch.cuda.Stream(device=device)
+        return self._side_streams[key]
 
     _warned_grad = False
 
@@ -221,14 +231,29 @@ class InpaintGenerator(BaseNetwork):
     def _forward(self, masked_frames, num_local_frames):
         l_t = num_local_frames
         b, t, ori_c, ori_h, ori_w = masked_frames.size()
+        side = None
         if masked_frames.is_cuda and l_t > 1:
-            # fused glue: (x + 1) / 2, the 1/4 downsample, the pyramids, per-level upsample + warp + cat (38 launches)
-            pred_flows = self.update_spynet.bidirect_flows(masked_frames, l_t)
+            # fused glue: (x + 1) / 2, the 1/4 downsample, the pyramids, per-level upsample + warp + cat (38 launches).
+            # SPyNet only depends on the input frames, like the encoder: it runs on a side stream (a parallel branch of
+            # a captured CUDA graph) so that its latency-bound coarse pyramid levels (8-32 CTAs for ~20 us each) fill in
+            # next to the encoder's convs instead of preceding them on the single-clip critical path
+            if self.overlap_flow:
+                main = torch.cuda.current_stream()
+                side = self._side_stream(masked_frames.device)
+                side.wait_stream(main)
+                with torch.cuda.stream(side):
+                    pred_flows = self.update_spynet.bidirect_flows(masked_frames, l_t)
+            else:
+                pred_flows = self.update_spynet.bidirect_flows(masked_frames, l_t)
         else:
             pred_flows = self.forward_bidirect_flow((masked_frames[:, :l_t] + 1) / 2)
 
         # encoder output: fp32 (b*t,c,h,w) in NHWC storage + its bf16 (hi, lo) split, both viewed as (b,t,h,w,c)
         enc32, enc_sp = self.encoder(masked_frames.reshape(b * t, ori_c, ori_h, ori_w), last_out="both")
+        if side is not None:
+            torch.cuda.current_stream().wait_stream(side)
+            for f in pred_flows:                       # produced on the side stream, consumed (and freed) on this one
+                f.record_stream(torch.cuda.current_stream())
         _, c, h, w = enc32.size()
         x32 = enc32.permute(0, 2, 3, 1).view(b, t, h, w, c)
         x_hi, x_lo = enc_sp.hi.view(b, t, h, w, c), enc_sp.lo.view(b, t, h, w, c)
