@@ -6,6 +6,7 @@ checkpoint is strict-compatible (243 entries base / 244 HQ), and
 The constructor never downloads SPyNet weights.
 """
 import contextlib
+import os
 
 import torch
 import torch.nn as nn
@@ -171,7 +172,8 @@ class InpaintGenerator(BaseNetwork):
         return fwd, bwd
 
     precision = "strict"
-    overlap_flow = True          # SPyNet on a side stream next to the encoder (see _forward)
+    # SPyNet on a side stream next to the encoder (see _forward); E2F_NO_OVERLAP=1 keeps everything on one stream (A/B)
+    overlap_flow = os.environ.get("E2F_NO_OVERLAP", "0") != "1"
     _side_streams = None
 
     def _side_stream(self, device):
