@@ -8,6 +8,7 @@
 Same names / argument meaning / error behaviour as the reference operators; every call goes through the C ABI of
 ``libe2fgvi_b200.so`` on the current CUDA stream.  There is no CPU path: CPU tensors raise.
 """
+import os
 import weakref
 
 import torch
@@ -834,6 +835,8 @@ def conv3x3(sources, weight, bias=None, groups=1, negative_slope=1.0, residual=N
 
 
 # ------------------------------------------------------------------------------------------------- SoftSplit / SoftComp
+KXN_CONVS = os.environ.get("E2F_KXN", "1") != "0"     # small-Cout layers on the kx-in-N kernel (E2F_KXN=0: A/B, debugging)
+
 _DERIVED = {}   # (id(param), tag...) -> (weakref, (version, data_ptr) tuple, value): weight-derived operands, per parameter
 
 
@@ -1074,10 +1077,76 @@ def soft_comp(tokens, weight, bias, output_size, kernel_size, stride, padding, b
                         (h, w), 2.0 * n * fh * fw * hidden * c * k * k)
 
 
+def pack_conv_kxn_weight(weight, co_pad):
+    """fp32 (Cout, C, k, k) -> (hi, lo) bf16 (k*co_pad, k*chunks*64) in the operand order of ``e2f_conv_kxn_bf16x3``:
+    row = kx*co_pad + co, column = (ky*chunks + chunk)*64 + channel; zeros for co >= Cout and padded channels."""
+    cout, c, kh, kw = weight.shape
+    assert kh == kw and cout <= co_pad
+    chunks = (c + 63) // 64
+    w = weight.detach().float()
+    packed = torch.zeros((kw, co_pad, kh, chunks * 64), dtype=torch.float32, device=weight.device)
+    packed[:, :cout, :, :c] = w.permute(3, 0, 2, 1)                # [kx][co][ky][c]
+    return split_bf16(packed.view(kw * co_pad, kh * chunks * 64))
+
+
+def _kxn_co_pad(cout, ks):
+    """Smallest padded channel count (multiple of 8, <= 32) with ks*co_pad % 16 == 0 that holds cout, or None."""
+    for cp in (8, 16, 24, 32):
+        if cp >= cout and (ks * cp) % 16 == 0:
+            return cp
+    return None
+
+
+def conv_kxn(x, weight, bias=None, negative_slope=1.0, residual=None, out="f32", tanh_nchw=False):
+    """k x k / stride 1 / pad k//2 conv (k = 3 or 7) with FEW output channels (<= 32) on the "kx-in-N" kernel: SPyNet's
+    64 -> 32 / 32 -> 16 / 16 -> 2 convs (flow_comp.py:181-215) and the decoder's output conv (e2fgvi.py:149-150).
+    x: (N,C,H,W) fp32 or ``SplitNHWC``; residual (N,Cout,H,W) logical with NHWC storage; out = "f32" | "split" | "both";
+    ``tanh_nchw``: tanh + contiguous NCHW fp32 result (the prediction, e2fgvi.py:262)."""
+    src = _as_split_nhwc(x)
+    n, c, h, w = src.shape
+    cout, cin, ks, ks2 = weight.shape
+    co_pad = _kxn_co_pad(cout, ks)
+    if ks != ks2 or ks not in (3, 7) or cin != c or co_pad is None:
+        raise ValueError(f"conv_kxn: unsupported weight {tuple(weight.shape)} for a {c}-channel source")
+    _need_cuda(weight, bias, residual)
+    w_hi, w_lo = _derived([weight], ("kxn", co_pad), lambda: pack_conv_kxn_weight(weight, co_pad))
+    b32 = None if bias is None else bias.detach().float().contiguous()
+    dev = weight.device
+    want_f32, want_split = out in ("f32", "both"), out in ("split", "both")
+    if tanh_nchw and out != "f32":
+        raise ValueError("conv_kxn: tanh_nchw returns the fp32 NCHW tensor only")
+    if want_split and cout % 8:
+        raise ValueError("conv_kxn: split output needs Cout % 8 == 0")
+    res = None
+    if residual is not None:
+        res = residual.permute(0, 2, 3, 1).contiguous().float()          # no-op for NHWC storage
+    o32 = ohi = olo = None
+    if want_f32:
+        o32 = torch.empty((n, cout, h, w) if tanh_nchw else (n, h, w, cout), dtype=torch.float32, device=dev)
+    if want_split:
+        ohi = torch.empty((n, h, w, cout), dtype=torch.bfloat16, device=dev)
+        olo = torch.empty((n, h, w, cout), dtype=torch.bfloat16, device=dev)
+    with _timed("conv3x3_bf16x3", 2.0 * n * h * w * cout * cin * ks * ks):
+        st = _lib.load().e2f_conv_kxn_bf16x3(src.hi.data_ptr(), src.lo.data_ptr(), src.hi.shape[-1], w_hi.data_ptr(),
+                                             w_lo.data_ptr(), None if b32 is None else b32.data_ptr(),
+                                             None if res is None else res.data_ptr(),
+                                             None if o32 is None else o32.data_ptr(), None if ohi is None else ohi.data_ptr(),
+                                             None if olo is None else olo.data_ptr(), n, h, w, cout, co_pad, ks,
+                                             float(negative_slope), 3 if tanh_nchw else 0, _stream())
+    _lib.check(st, "e2f_conv_kxn_bf16x3")
+    if tanh_nchw:
+        return o32
+    t32 = o32.permute(0, 3, 1, 2) if want_f32 else None
+    sp = SplitNHWC(ohi, olo, (n, cout, h, w)) if want_split else None
+    return t32 if out == "f32" else sp if out == "split" else (t32, sp)
+
+
 def conv3x3_tanh_nchw(x, weight, bias):
     """``torch.tanh(F.conv2d(x, weight, bias, 1, 1))`` returned as a CONTIGUOUS (N, Cout, H, W) fp32 tensor: the
     decoder's 64 -> 3 output conv (e2fgvi.py:149-150) with the tanh of :262 and the NHWC -> NCHW layout change of the
     prediction fused into the conv epilogue.  x: (N,C,H,W) fp32 or ``SplitNHWC``."""
+    if KXN_CONVS and weight.shape[0] <= 32 and tuple(weight.shape[2:]) == (3, 3):
+        return conv_kxn(x, weight, bias, tanh_nchw=True)
     src = _as_split_nhwc(x)
     n, c, h, w = src.shape
     cout = weight.shape[0]

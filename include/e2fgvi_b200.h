@@ -254,6 +254,22 @@ int e2f_conv2d_rows_bf16x3(int nsrc, const void* const* src_hi, const void* cons
 int e2f_conv3x3_tanh_nchw(const void* src_hi, const void* src_lo, int cin, const void* w_hi, const void* w_lo,
                           const float* bias, float* out, int n, int h, int w, int cout, void* stream);
 
+/* "kx-in-N" k x k / stride 1 / pad k/2 convolution for layers with FEW output channels — SPyNet's 64 -> 32, 32 -> 16 and
+ * 16 -> 2 7x7 convs (model/modules/flow_comp.py:181-215) and the decoder's 64 -> 3 output conv (model/e2fgvi.py:149-150).
+ * The kernel-COLUMN taps go into the GEMM's N dimension, D[(y, xin), (kx, co)] = sum_{ky, c} X[y+ky-pad, xin, c] * W[co,c,ky,kx],
+ * and the epilogue adds the kx columns with a horizontal shift (warp shuffles: one warp per tile row), out[y, x, co] =
+ * sum_kx D[(y, x+kx-pad), (kx, co)]: one read of an A tile feeds k times more output columns, so these layers are bound
+ * by tensor math instead of by re-reading the A operand for every tap.
+ *   src_hi / src_lo: ONE NHWC bf16 (hi, lo) source [N][H][W][cin] (cin % 8 == 0; channels beyond cin are zero-filled)
+ *   w_hi / w_lo:     [k*co_pad rows][k*ceil(cin/64)*64] bf16: row = kx*co_pad + co, column = (ky*chunks + chunk)*64 + c
+ *                    (zeros for co >= Cout and padded channels); co_pad % 8 == 0, <= 32, and k*co_pad % 16 == 0
+ *   epilogue: + bias[Cout], LeakyReLU(leaky_slope) (1 = none, 0 = ReLU), + residual (NHWC fp32 [N][H][W][Cout] or NULL),
+ *             flags bit 0: tanh, bit 1: fp32 output stored NCHW ([N][Cout][H][W]); outputs: out fp32 NHWC (or NCHW) and / or
+ *             the bf16 (hi, lo) split NHWC [N][H][W][Cout] (Cout % 8 == 0). */
+int e2f_conv_kxn_bf16x3(const void* src_hi, const void* src_lo, int cin, const void* w_hi, const void* w_lo,
+                        const float* bias, const float* residual, float* out, void* out_hi, void* out_lo, int n, int h, int w,
+                        int cout, int co_pad, int ksize, float leaky_slope, int flags, void* stream);
+
 /* "Gather conv": the same implicit GEMM with an explicit TAP TABLE, OUTPUT PHASES and tile shape (groups == 1).
  * Replaces, without ever building the unfolded operand:
  *   - SoftSplit (model/modules/tfocal_transformer.py:39-46; HQ _hq.py:39-46): F.unfold(7x7, stride 3, pad 3) + nn.Linear

@@ -114,3 +114,39 @@ def test_best_tile_fills_the_token_grids():
     for (gh, gw), tiles in (((20, 36), 6), ((60, 108), 54), ((90, 162), 117)):
         tw, th = ops._best_tile(gh, gw, 3)
         assert tw * th <= 128 and -(-gh // th) * -(-gw // tw) == tiles
+
+
+@pytest.mark.parametrize("case", [(64, 32, 7), (32, 16, 7), (16, 2, 7), (64, 3, 3), (72, 5, 3)])
+def test_kxn_weight_packing_and_shift_sum(case):
+    """e2f_conv_kxn_bf16x3's documented two-step semantics executed in torch with the packed weight of
+    ops.pack_conv_kxn_weight: D[(y, xin), (kx, co)] = sum_{ky, c} X[y+ky-pad, xin, c] W[co, c, ky, kx], then
+    out[y, x, co] = sum_kx D[(y, x+kx-pad), (kx, co)]  ==  F.conv2d(x, w, padding=k//2)."""
+    cin, cout, ks = case
+    pad = ks // 2
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn(2, cin, 9, 13, generator=g)
+    w = torch.randn(cout, cin, ks, ks, generator=g) / (cin * ks * ks) ** 0.5
+    co_pad = ops._kxn_co_pad(cout, ks)
+    assert co_pad is not None and (ks * co_pad) % 16 == 0
+    saved = ops.split_bf16
+    ops.split_bf16 = _split_cpu
+    try:
+        hi, lo = ops.pack_conv_kxn_weight(w, co_pad)
+    finally:
+        ops.split_bf16 = saved
+    chunks = (cin + 63) // 64
+    wp = (hi.double() + lo.double()).view(ks, co_pad, ks, chunks * 64)[:, :, :, :cin]         # [kx][co][ky][c]
+    xp = F.pad(x.double(), (pad, pad, pad, pad))                                               # zero padding = TMA OOB fill
+    n, _, h, wd = x.shape
+    # D over the padded column range xin in [-pad, W + pad): D[n, y, xin, kx, co]
+    D = torch.zeros(n, h, wd + 2 * pad, ks, co_pad, dtype=torch.float64)
+    for ky in range(ks):
+        rows = xp[:, :, ky:ky + h, :]                                                           # X[y + ky - pad, xin]
+        D += torch.einsum("ncyx,koc->nyxko", rows, wp[:, :, ky, :])
+    out = torch.zeros(n, h, wd, co_pad, dtype=torch.float64)
+    for kx in range(ks):
+        out += D[:, :, kx:kx + wd, kx, :]                                                       # D[(y, x + kx - pad)] in padded coords
+    want = F.conv2d(x.double(), w.double(), padding=pad)
+    got = out[..., :cout].permute(0, 3, 1, 2)
+    assert (got - want).abs().max().item() < 2e-4 * want.abs().max().item()
+    assert float(out[..., cout:].abs().max()) == 0.0 if co_pad > cout else True

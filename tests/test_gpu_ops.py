@@ -654,6 +654,45 @@ def test_conv3x3_tanh_nchw(cuda, shape):
     assert (got.cpu().double() - want).abs().max().item() < 1e-4
 
 
+@pytest.mark.parametrize("case", [
+    dict(n=3, cin=64, cout=32, ks=7, h=64, w=128, out="split", slope=0.0),     # SPyNet conv 2 at the finest level
+    dict(n=2, cin=32, cout=16, ks=7, h=17, w=29, out="split", slope=0.0),      # SPyNet conv 3, ragged tiles
+    dict(n=5, cin=16, cout=2, ks=7, h=2, w=4, out="f32", residual=True),       # SPyNet conv 4, coarsest level (2x4 pixels)
+    dict(n=2, cin=16, cout=2, ks=7, h=32, w=64, out="f32", residual=True),
+    dict(n=2, cin=64, cout=3, ks=3, h=48, w=80, out="f32", tanh_nchw=True),    # decoder output conv
+    dict(n=1, cin=64, cout=3, ks=3, h=31, w=61, out="f32"),
+    dict(n=1, cin=128, cout=24, ks=3, h=9, w=33, out="both", slope=0.2),       # two K chunks, Cout not a power of two
+])
+def test_conv_kxn(cuda, case):
+    """kx-in-N conv kernel (kernel-column taps in the GEMM's N, horizontal shift-add by warp shuffles in the epilogue)
+    against F.conv2d in fp64: flow_comp.py:181-215 (64->32, 32->16, 16->2 with the flow_up residual), e2fgvi.py:149-150."""
+    import torch.nn.functional as F
+    c = dict(slope=1.0, residual=False, tanh_nchw=False)
+    c.update(case)
+    g = torch.Generator().manual_seed(55)
+    x = torch.randn(c["n"], c["cin"], c["h"], c["w"], generator=g)
+    conv = torch.nn.Conv2d(c["cin"], c["cout"], c["ks"], 1, c["ks"] // 2)
+    res = torch.randn(c["n"], c["cout"], c["h"], c["w"], generator=g) if c["residual"] else None
+    want = F.leaky_relu(F.conv2d(x.double(), conv.weight.double(), conv.bias.double(), 1, c["ks"] // 2), c["slope"])
+    if res is not None:
+        want = want + res.double()
+    if c["tanh_nchw"]:
+        want = torch.tanh(want)
+    conv = conv.to(cuda)
+    with torch.no_grad():
+        got = ops.conv_kxn(x.to(cuda), conv.weight, conv.bias, negative_slope=c["slope"],
+                           residual=None if res is None else res.to(cuda).contiguous(memory_format=torch.channels_last),
+                           out=c["out"], tanh_nchw=c["tanh_nchw"])
+    outs = got if isinstance(got, tuple) else (got,)
+    for o in outs:
+        if isinstance(o, ops.SplitNHWC):
+            o = (o.hi.float() + o.lo.float()).permute(0, 3, 1, 2)
+        assert o.shape == want.shape
+        assert _rel(o.cpu(), want) < 5e-5
+    if c["tanh_nchw"]:
+        assert got.is_contiguous()
+
+
 # ------------------------------------------------------------------------------------------ SoftSplit / SoftComp as gather convs
 @pytest.mark.parametrize("shape", [(3, 128, 60, 108), (2, 64, 15, 27), (1, 128, 45, 81), (2, 128, 30, 54)])
 def test_soft_split_matches_unfold_linear(cuda, shape):
