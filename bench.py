@@ -299,6 +299,8 @@ class Measurement:
             prof, ms_prof = None, None
             if profile:
                 saved_graphs = getattr(self.model, "_graphs", None)
+                saved_overlap = getattr(self.model, "overlap_flow", False)
+                self.model.overlap_flow = False         # concurrent streams would inflate each other's event-timed launches
                 if saved_graphs is not None:
                     self.model._graphs = None           # kernels inside a replayed graph cannot be timed one by one
                     self._loop(2, self.dev_sets)
@@ -313,6 +315,7 @@ class Measurement:
                 ms_prof = p0.elapsed_time(p1)
                 if saved_graphs is not None:
                     self.model._graphs = saved_graphs
+                self.model.overlap_flow = saved_overlap
             # ---- end to end through the public API with HOST buffers
             self._loop(2, self.host_sets, to_host=True)
             self.sync()
