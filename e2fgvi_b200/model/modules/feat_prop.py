@@ -139,15 +139,23 @@ class BidirectionalPropagation(nn.Module):
         per step = prologue, 4 offset-head convs, DCN (+ split epilogue), 2 backbone convs."""
         b, t, h, w, c = x32.shape
         cur = [ops.SplitNHWC(x_hi[:, i], x_lo[:, i], (b, c, h, w)) for i in range(t)]
-        zero = torch.zeros((b, h, w, c), dtype=torch.bfloat16, device=x32.device)
+        zero = torch.zeros((b, h, w, c), dtype=x_hi.dtype, device=x32.device)
         zero_sp = ops.SplitNHWC(zero, zero, (b, c, h, w))
-        swept32, swept_sp = {}, {}
+        # per-direction results live in (t, b, h, w, c) buffers: frame idx is the dense slice buf[idx], and for a single
+        # clip (b == 1) all frames are one contiguous batch, so the 1x1 fusion runs as ONE launch instead of t
+        bufs = {}
+        for name in self.DIRECTIONS:
+            bufs[name] = (torch.empty((t, b, h, w, c), dtype=torch.float32, device=x32.device),
+                          torch.empty((t, b, h, w, c), dtype=x_hi.dtype, device=x32.device),
+                          torch.empty((t, b, h, w, c), dtype=x_lo.dtype, device=x32.device))
+        swept_sp = {}
         for name in self.DIRECTIONS:
             backward = name == "backward_"
             order = list(range(t - 1, -1, -1)) if backward else list(range(t))
             flows = flows_backward if backward else flows_forward
             align, backbone = self.deform_align[name], self.backbone[name]
-            hist32, hist_sp = [], []
+            r32, rhi, rlo = bufs[name]
+            hist32 = []
             for i, idx in enumerate(order):
                 prop32, prop_sp = None, zero_sp
                 if i > 0:
@@ -156,18 +164,22 @@ class BidirectionalPropagation(nn.Module):
                     prop32, prop_sp = align.align_split(xg, [cond_n1, cur[idx], cond_n2], flow_n1, flow_n2, flows_op)
                 parts = [cur[idx], prop_sp] if backward else [cur[idx], swept_sp["backward_"][idx], prop_sp]
                 y = ops.conv_frames(parts, backbone[0].weight, backbone[0].bias, negative_slope=0.1, out="split")
-                new32, new_sp = ops.conv_frames([y], backbone[2].weight, backbone[2].bias, residual=prop32, out="both")
+                new32, _ = ops.conv_frames([y], backbone[2].weight, backbone[2].bias, residual=prop32, out="both",
+                                           into=(r32[idx], rhi[idx], rlo[idx]))
                 hist32.append(new32)
-                hist_sp.append(new_sp)
-            swept32[name] = hist32[::-1] if backward else hist32
-            swept_sp[name] = hist_sp[::-1] if backward else hist_sp
+            swept_sp[name] = [ops.SplitNHWC(rhi[i], rlo[i], (b, c, h, w)) for i in range(t)]
         if into is None:
             into = (torch.empty_like(x32), torch.empty_like(x_hi), torch.empty_like(x_lo))
         o32, ohi, olo = into
-        for i in range(t):
-            # 1x1 fusion conv over cat(backward, forward) as two sources, "+ x" fused (feat_prop.py:143-149)
-            ops.conv_frames([swept_sp["backward_"][i], swept_sp["forward_"][i]], self.fusion.weight, self.fusion.bias,
-                            residual=x32[:, i].permute(0, 3, 1, 2), out="both", into=(o32[:, i], ohi[:, i], olo[:, i]))
+        # 1x1 fusion conv over cat(backward, forward) as two sources, "+ x" fused (feat_prop.py:143-149)
+        if b == 1:
+            srcs = [ops.SplitNHWC(bufs[n_][1].view(t, h, w, c), bufs[n_][2].view(t, h, w, c), (t, c, h, w)) for n_ in self.DIRECTIONS]
+            ops.conv_frames(srcs, self.fusion.weight, self.fusion.bias, residual=x32[0].permute(0, 3, 1, 2), out="both",
+                            into=(o32[0], ohi[0], olo[0]))
+        else:
+            for i in range(t):
+                ops.conv_frames([swept_sp["backward_"][i], swept_sp["forward_"][i]], self.fusion.weight, self.fusion.bias,
+                                residual=x32[:, i].permute(0, 3, 1, 2), out="both", into=(o32[:, i], ohi[:, i], olo[:, i]))
         return o32, ohi, olo
 
     def forward(self, x, flows_backward, flows_forward):
