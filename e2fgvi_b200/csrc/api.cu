@@ -354,20 +354,26 @@ int e2f_conv3x3_tanh_nchw(const void* src_hi, const void* src_lo, int cin, const
   return finish(launch_conv3x3(1, hi, lo, ch, w_hi, w_lo, bias, nullptr, out, nullptr, nullptr, n, h, w, cout, 1, 1.0f, 3, 1, 1, 0, 0, static_cast<cudaStream_t>(stream), nullptr, 3), who);
 }
 
-int e2f_conv_kxn_bf16x3(const void* src_hi, const void* src_lo, int cin, const void* w_hi, const void* w_lo,
-                        const float* bias, const float* residual, float* out, void* out_hi, void* out_lo, int n, int h, int w,
-                        int cout, int co_pad, int ksize, float leaky_slope, int flags, void* stream) {
+int e2f_conv_kxn_bf16x3(int nsrc, const void* const* src_hi, const void* const* src_lo, const int* src_channels,
+                        const void* w_hi, const void* w_lo, const float* bias, const float* residual, float* out, void* out_hi,
+                        void* out_lo, int n, int h, int w, int cout, int groups, int co_pad, int ksize, float leaky_slope,
+                        int flags, void* stream) {
   const char* who = "e2f_conv_kxn_bf16x3";
-  if (!src_hi || !src_lo || !w_hi || !w_lo) { set_error("%s: null pointer", who); return E2F_ERR_BAD_ARG; }
+  if (!src_hi || !src_lo || !src_channels || !w_hi || !w_lo) { set_error("%s: null pointer", who); return E2F_ERR_BAD_ARG; }
   if ((!out && !out_hi) || (!out_hi) != (!out_lo)) { set_error("%s: need out and/or both of out_hi/out_lo", who); return E2F_ERR_BAD_ARG; }
-  if (n < 0 || h <= 0 || w <= 0 || cin <= 0 || cout <= 0) { set_error("%s: bad shape", who); return E2F_ERR_BAD_ARG; }
+  if (nsrc < 1 || nsrc > 2) { set_error("%s: nsrc=%d (1..2 supported)", who, nsrc); return E2F_ERR_UNSUPPORTED; }
+  if (n < 0 || h <= 0 || w <= 0 || cout <= 0 || groups <= 0) { set_error("%s: bad shape", who); return E2F_ERR_BAD_ARG; }
   if (flags & ~3) { set_error("%s: flags %d", who, flags); return E2F_ERR_BAD_ARG; }
   if ((flags & 2) && (!out || out_hi)) { set_error("%s: the NCHW store goes with an fp32-only output", who); return E2F_ERR_BAD_ARG; }
-  if (!aligned(src_hi, 16) || !aligned(src_lo, 16) || !aligned(w_hi, 16) || !aligned(w_lo, 16) || (out && !aligned(out, 16)) ||
+  for (int i = 0; i < nsrc; ++i) {
+    if (!src_hi[i] || !src_lo[i]) { set_error("%s: null source %d", who, i); return E2F_ERR_BAD_ARG; }
+    if (!aligned(src_hi[i], 16) || !aligned(src_lo[i], 16)) { set_error("%s: alignment", who); return E2F_ERR_ALIGNMENT; }
+  }
+  if (!aligned(w_hi, 16) || !aligned(w_lo, 16) || (out && !aligned(out, 16)) ||
       (out_hi && (!aligned(out_hi, 16) || !aligned(out_lo, 16))) || (residual && !aligned(residual, 8))) { set_error("%s: alignment", who); return E2F_ERR_ALIGNMENT; }
   if (n == 0) return 0;
-  return finish(launch_conv_kxn(src_hi, src_lo, cin, w_hi, w_lo, bias, residual, out, out_hi, out_lo, n, h, w, cout, co_pad, ksize,
-                                leaky_slope, flags, static_cast<cudaStream_t>(stream)), who);
+  return finish(launch_conv_kxn(nsrc, src_hi, src_lo, src_channels, w_hi, w_lo, bias, residual, out, out_hi, out_lo, n, h, w, cout,
+                                groups, co_pad, ksize, leaky_slope, flags, static_cast<cudaStream_t>(stream)), who);
 }
 
 int e2f_conv2d_bf16x3(int nsrc, const void* const* src_hi, const void* const* src_lo, const int* src_channels,

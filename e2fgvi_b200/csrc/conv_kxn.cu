@@ -26,12 +26,16 @@ constexpr int A_TILE = BM * BK * 2;
 constexpr int THREADS = 6 * 32;                       // TMA, MMA, 4 epilogue warps
 constexpr int EPI_TANH = 1, EPI_NCHW = 2;
 
+constexpr int MAX_SRC = 2;
 struct Maps {
-  CUtensorMap a_hi, a_lo, w_hi, w_lo;
+  CUtensorMap a_hi[MAX_SRC], a_lo[MAX_SRC], w_hi, w_lo;
 };
 
 struct Params {
-  int N, H, W, Cout, co_pad, ks, pad, chunks, NB;   // NB = ks * co_pad accumulator columns (multiple of 16, <= 256)
+  int N, H, W, Cout, co_pad, ks, pad, chunks, NB;   // Cout: output channels PER GROUP; NB = ks * co_pad accumulator
+                                                    // columns (multiple of 16, <= 256); chunks = K chunks per ky (all sources)
+  int groups, cout_total;                           // grouped conv (encoder conv 7, e2fgvi.py:97): tile = (pixels, group)
+  int nsrc, cig[MAX_SRC], src_chunks[MAX_SRC];      // channels per group and 64-wide K chunks of each source
   int stage_bytes, stages;
   float slope;
   int flags;
@@ -61,16 +65,16 @@ __global__ void __launch_bounds__(THREADS, 1) conv_kxn_kernel(const __grid_const
   uint64_t* acc_full = empty + 4;
   uint64_t* acc_empty = acc_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
-  float* bias_s = reinterpret_cast<float*>(smem + p.stages * p.stage_bytes + 128);     // [32]
+  float* bias_s = reinterpret_cast<float*>(smem + p.stages * p.stage_bytes + 128);     // [512]
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int W_TILE = p.NB * BK * 2;
   const int step_x = TW - 2 * p.pad;                                   // output columns a tile produces
   const int tiles_x = (p.W + step_x - 1) / step_x, tiles_y = (p.H + TH - 1) / TH;
-  const int num_tiles = p.N * tiles_y * tiles_x;
+  const int num_tiles = p.N * tiles_y * tiles_x * p.groups;
   const int num_kb = p.ks * p.chunks;
   const uint32_t tmem_cols = (2 * p.NB <= 256) ? 256u : 512u;
-  if (tid < 32) bias_s[tid] = (p.bias && tid < p.Cout) ? __ldg(p.bias + tid) : 0.f;
+  for (int i = tid; i < 512; i += THREADS) bias_s[i] = (p.bias && i < p.cout_total) ? __ldg(p.bias + i) : 0.f;
 
   if (warp == 1) tmem_alloc(tmem_slot, tmem_cols);
   if (tid == 0) {
@@ -83,8 +87,10 @@ __global__ void __launch_bounds__(THREADS, 1) conv_kxn_kernel(const __grid_const
       mbar_init(&acc_empty[s], 4);
     }
     fence_barrier_init();
-    tma_prefetch_desc(&maps.a_hi);
-    tma_prefetch_desc(&maps.a_lo);
+    for (int i = 0; i < p.nsrc; ++i) {
+      tma_prefetch_desc(&maps.a_hi[i]);
+      tma_prefetch_desc(&maps.a_lo[i]);
+    }
     tma_prefetch_desc(&maps.w_hi);
     tma_prefetch_desc(&maps.w_lo);
   }
@@ -99,20 +105,24 @@ __global__ void __launch_bounds__(THREADS, 1) conv_kxn_kernel(const __grid_const
       const uint32_t stage_tx = 2u * A_TILE + 2u * static_cast<uint32_t>(W_TILE);
       uint32_t it = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int tx = tile % tiles_x, ty = (tile / tiles_x) % tiles_y, n = tile / (tiles_x * tiles_y);
+        const int g = tile % p.groups, tp = tile / p.groups;
+        const int tx = tp % tiles_x, ty = (tp / tiles_x) % tiles_y, n = tp / (tiles_x * tiles_y);
         const int xs = tx * step_x - p.pad, y0 = ty * TH;              // first D-grid column / row of the tile
         int kb = 0;
         for (int ky = 0; ky < p.ks; ++ky)
-          for (int j = 0; j < p.chunks; ++j, ++kb, ++it) {
-            const int stage = it % p.stages;
-            mbar_wait(&empty[stage], ((it / p.stages) & 1) ^ 1);
-            mbar_arrive_expect_tx(&full[stage], stage_tx);
-            const uint32_t s0 = smem_u32(smem + stage * p.stage_bytes);
-            tma_load_4d(s0, &maps.a_hi, &full[stage], j * BK, xs, y0 + ky - p.pad, n);
-            tma_load_4d(s0 + A_TILE, &maps.a_lo, &full[stage], j * BK, xs, y0 + ky - p.pad, n);
-            tma_load_2d(s0 + 2 * A_TILE, &maps.w_hi, &full[stage], kb * BK, 0);
-            tma_load_2d(s0 + 2 * A_TILE + W_TILE, &maps.w_lo, &full[stage], kb * BK, 0);
-          }
+          for (int s = 0; s < p.nsrc; ++s)
+            for (int j = 0; j < p.src_chunks[s]; ++j, ++kb, ++it) {
+              const int stage = it % p.stages;
+              mbar_wait(&empty[stage], ((it / p.stages) & 1) ^ 1);
+              mbar_arrive_expect_tx(&full[stage], stage_tx);
+              const uint32_t s0 = smem_u32(smem + stage * p.stage_bytes);
+              // channels past the group's slice (the next group's, or out of bounds = zero) meet zero weights
+              const int c0 = g * p.cig[s] + j * BK;
+              tma_load_4d(s0, &maps.a_hi[s], &full[stage], c0, xs, y0 + ky - p.pad, n);
+              tma_load_4d(s0 + A_TILE, &maps.a_lo[s], &full[stage], c0, xs, y0 + ky - p.pad, n);
+              tma_load_2d(s0 + 2 * A_TILE, &maps.w_hi, &full[stage], kb * BK, g * p.NB);
+              tma_load_2d(s0 + 2 * A_TILE + W_TILE, &maps.w_lo, &full[stage], kb * BK, g * p.NB);
+            }
       }
     }
   } else if (warp == 1) {
@@ -152,7 +162,10 @@ __global__ void __launch_bounds__(THREADS, 1) conv_kxn_kernel(const __grid_const
     uint32_t local = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
       const int buf = local & 1;
-      const int tx = tile % tiles_x, ty = (tile / tiles_x) % tiles_y, n = tile / (tiles_x * tiles_y);
+      const int g = tile % p.groups, tp = tile / p.groups;
+      const int tx = tp % tiles_x, ty = (tp / tiles_x) % tiles_y, n = tp / (tiles_x * tiles_y);
+      const int cbase = g * p.Cout;                                       // first output channel of the group
+      const int CT = p.cout_total;
       const int y = ty * TH + q, x = tx * step_x + lane - p.pad;          // this lane's OUTPUT pixel
       const bool ok = lane >= p.pad && lane < TW - p.pad && y < p.H && x < p.W;
       const size_t pix = (static_cast<size_t>(n) * p.H + y) * p.W + x;
@@ -177,9 +190,9 @@ __global__ void __launch_bounds__(THREADS, 1) conv_kxn_kernel(const __grid_const
         if (ok && co0 < p.Cout) {
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            float a = acc[i] + bias_s[(co0 + i) & 31];
+            float a = acc[i] + bias_s[(cbase + co0 + i) & 511];
             a = a > 0.f ? a : a * p.slope;
-            if (p.residual && co0 + i < p.Cout) a += __ldg(p.residual + pix * p.Cout + co0 + i);
+            if (p.residual && co0 + i < p.Cout) a += __ldg(p.residual + pix * CT + cbase + co0 + i);
             if (p.flags & EPI_TANH) a = tanhf(a);
             acc[i] = a;
           }
@@ -187,15 +200,15 @@ __global__ void __launch_bounds__(THREADS, 1) conv_kxn_kernel(const __grid_const
             if (p.flags & EPI_NCHW) {
 #pragma unroll
               for (int i = 0; i < 8; ++i)
-                if (co0 + i < p.Cout) p.out[((static_cast<size_t>(n) * p.Cout + co0 + i) * p.H + y) * p.W + x] = acc[i];
-            } else if (co0 + 8 <= p.Cout && (p.Cout & 3) == 0) {
-              float4* d4 = reinterpret_cast<float4*>(p.out + pix * p.Cout + co0);
+                if (co0 + i < p.Cout) p.out[((static_cast<size_t>(n) * CT + cbase + co0 + i) * p.H + y) * p.W + x] = acc[i];
+            } else if (co0 + 8 <= p.Cout && (CT & 3) == 0 && (cbase & 3) == 0) {
+              float4* d4 = reinterpret_cast<float4*>(p.out + pix * CT + cbase + co0);
               d4[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
               d4[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
             } else {
 #pragma unroll
               for (int i = 0; i < 8; ++i)
-                if (co0 + i < p.Cout) p.out[pix * p.Cout + co0 + i] = acc[i];
+                if (co0 + i < p.Cout) p.out[pix * CT + cbase + co0 + i] = acc[i];
             }
           }
           if (p.out_hi && co0 + 8 <= p.Cout) {                // split output: Cout % 8 == 0 (checked by the launcher)
@@ -208,8 +221,8 @@ __global__ void __launch_bounds__(THREADS, 1) conv_kxn_kernel(const __grid_const
               hp[i] = *reinterpret_cast<const uint32_t*>(&hb);
               lp[i] = *reinterpret_cast<const uint32_t*>(&lb);
             }
-            *reinterpret_cast<uint4*>(p.out_hi + pix * p.Cout + co0) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
-            *reinterpret_cast<uint4*>(p.out_lo + pix * p.Cout + co0) = make_uint4(lp[0], lp[1], lp[2], lp[3]);
+            *reinterpret_cast<uint4*>(p.out_hi + pix * CT + cbase + co0) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
+            *reinterpret_cast<uint4*>(p.out_lo + pix * CT + cbase + co0) = make_uint4(lp[0], lp[1], lp[2], lp[3]);
           }
         }
       }
@@ -239,56 +252,77 @@ static EncodeTiledFn get_encode() {
 
 }  // namespace kxn
 
-// src: one NHWC bf16 (hi, lo) source with `c` stored channels (multiple of 8); weights [ks*co_pad rows][ks*chunks*64]
-// bf16 (hi, lo): row = kx*co_pad + co, column = (ky*chunks + chunk)*64 + channel (ops.pack_conv_kxn_weight).
-int launch_conv_kxn(const void* src_hi, const void* src_lo, int c, const void* w_hi, const void* w_lo, const float* bias,
-                    const float* residual, float* out, void* out_hi, void* out_lo, int n, int h, int w, int cout, int co_pad,
-                    int ks, float slope, int flags, cudaStream_t stream) {
+// sources: nsrc <= 2 NHWC bf16 (hi, lo) tensors with src_c[i] stored channels (multiples of 8; for groups > 1 multiples of
+// `groups`); cout = output channels in total (cout / groups <= co_pad per group).  Weights [groups * ks*co_pad rows]
+// [ks * chunks * 64] bf16 (hi, lo): row = g*ks*co_pad + kx*co_pad + co, column = (ky*chunks + chunk)*64 + channel with
+// the chunks of source 0 first, then source 1 (ops.pack_conv_kxn_weight).
+int launch_conv_kxn(int nsrc, const void* const* src_hi, const void* const* src_lo, const int* src_c, const void* w_hi,
+                    const void* w_lo, const float* bias, const float* residual, float* out, void* out_hi, void* out_lo, int n,
+                    int h, int w, int cout, int groups, int co_pad, int ks, float slope, int flags, cudaStream_t stream) {
   using namespace kxn;
   EncodeTiledFn enc = get_encode();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled is not available from the driver");
     return -4;
   }
-  const int NB = ks * co_pad, pad = ks / 2, chunks = (c + BK - 1) / BK;
-  if ((ks != 3 && ks != 7) || co_pad % 8 || cout > co_pad || co_pad > 32 || NB % 16 || NB > 256 || c % 8) {
-    set_error("conv_kxn: unsupported shape (ks=%d cout=%d co_pad=%d c=%d): needs ks in {3,7}, co_pad %% 8 == 0 <= 32, ks*co_pad %% 16 == 0", ks, cout, co_pad, c);
+  const int NB = ks * co_pad, pad = ks / 2;
+  if (nsrc < 1 || nsrc > MAX_SRC || groups < 1 || cout % groups || cout > 512) {
+    set_error("conv_kxn: nsrc=%d groups=%d cout=%d", nsrc, groups, cout);
     return -2;
   }
-  if (out_hi && cout % 8) {
-    set_error("conv_kxn: split output needs Cout %% 8 == 0");
+  const int cog = cout / groups;
+  if ((ks != 3 && ks != 7) || co_pad % 8 || cog > co_pad || co_pad > 32 || NB % 16 || NB > 256) {
+    set_error("conv_kxn: unsupported shape (ks=%d cout/groups=%d co_pad=%d): needs ks in {3,7}, co_pad %% 8 == 0 <= 32, ks*co_pad %% 16 == 0", ks, cog, co_pad);
+    return -2;
+  }
+  if (out_hi && (cog % 8 || cout % 8)) {
+    set_error("conv_kxn: split output needs Cout %% 8 == 0 per group");
     return -2;
   }
   Maps maps;
   Params p;
-  p.N = n; p.H = h; p.W = w; p.Cout = cout; p.co_pad = co_pad; p.ks = ks; p.pad = pad; p.chunks = chunks; p.NB = NB;
+  p.N = n; p.H = h; p.W = w; p.Cout = cog; p.co_pad = co_pad; p.ks = ks; p.pad = pad; p.NB = NB;
+  p.groups = groups; p.cout_total = cout; p.nsrc = nsrc;
   p.slope = slope; p.flags = flags; p.bias = bias; p.residual = residual; p.out = out;
   p.out_hi = static_cast<__nv_bfloat16*>(out_hi); p.out_lo = static_cast<__nv_bfloat16*>(out_lo);
+  p.chunks = 0;
+  for (int i = 0; i < MAX_SRC; ++i) p.cig[i] = p.src_chunks[i] = 0;
+  for (int i = 0; i < nsrc; ++i) {
+    const int c = src_c[i];
+    if (c <= 0 || c % 8 || c % groups) {
+      set_error("conv_kxn: source %d has %d channels (needs a multiple of 8 and of groups)", i, c);
+      return -2;
+    }
+    p.cig[i] = c / groups;
+    p.src_chunks[i] = (p.cig[i] + BK - 1) / BK;
+    p.chunks += p.src_chunks[i];
+  }
   const int w_tile = NB * BK * 2;
   p.stage_bytes = 2 * A_TILE + 2 * w_tile;                      // multiple of 1024 (NB % 16 == 0 -> NB*128 % 2048 == 0)
-  p.stages = (3 * p.stage_bytes + 2048 <= 225 * 1024) ? 3 : 2;
-  if (p.stages * p.stage_bytes + 2048 > 227 * 1024) {
+  p.stages = (3 * p.stage_bytes + 4096 <= 225 * 1024) ? 3 : 2;
+  if (p.stages * p.stage_bytes + 4096 > 227 * 1024) {
     set_error("conv_kxn: stage does not fit in shared memory");
     return -2;
   }
-  {
+  for (int i = 0; i < nsrc; ++i) {
+    const int c = src_c[i];
     const cuuint64_t dims[4] = {static_cast<cuuint64_t>(c), static_cast<cuuint64_t>(w), static_cast<cuuint64_t>(h), static_cast<cuuint64_t>(n)};
     const cuuint64_t strides[3] = {static_cast<cuuint64_t>(c) * 2, static_cast<cuuint64_t>(w) * c * 2, static_cast<cuuint64_t>(h) * w * c * 2};
     const cuuint32_t box[4] = {BK, TW, TH, 1};
     const cuuint32_t estr[4] = {1, 1, 1, 1};
     for (int part = 0; part < 2; ++part) {
-      CUresult r = enc(part ? &maps.a_lo : &maps.a_hi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(part ? src_lo : src_hi),
-                       dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                       CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      CUresult r = enc(part ? &maps.a_lo[i] : &maps.a_hi[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4,
+                       const_cast<void*>(part ? src_lo[i] : src_hi[i]), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                       CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       if (r != CUDA_SUCCESS) {
-        set_error("conv_kxn: cuTensorMapEncodeTiled(source) failed with CUresult %d", static_cast<int>(r));
+        set_error("conv_kxn: cuTensorMapEncodeTiled(source %d) failed with CUresult %d", i, static_cast<int>(r));
         return -4;
       }
     }
   }
   {
-    const int kcols = ks * chunks * BK;
-    const cuuint64_t dims[2] = {static_cast<cuuint64_t>(kcols), static_cast<cuuint64_t>(NB)};
+    const int kcols = ks * p.chunks * BK;
+    const cuuint64_t dims[2] = {static_cast<cuuint64_t>(kcols), static_cast<cuuint64_t>(groups) * NB};
     const cuuint64_t strides[1] = {static_cast<cuuint64_t>(kcols) * 2};
     const cuuint32_t box[2] = {BK, static_cast<cuuint32_t>(NB)};
     const cuuint32_t estr[2] = {1, 1};
@@ -310,14 +344,14 @@ int launch_conv_kxn(const void* src_hi, const void* src_lo, int c, const void* w
     device_mark(cfg, dev);
   }
   const int step_x = TW - 2 * pad;
-  const long long tiles = static_cast<long long>(n) * ((h + TH - 1) / TH) * ((w + step_x - 1) / step_x);
+  const long long tiles = static_cast<long long>(n) * ((h + TH - 1) / TH) * ((w + step_x - 1) / step_x) * groups;
   if (tiles == 0) return 0;
   if (tiles > 0x7FFFFFFFLL) {
     set_error("conv_kxn: too many tiles");
     return -2;
   }
   const int grid = tiles < num_sms() ? static_cast<int>(tiles) : num_sms();
-  const int smem = p.stages * p.stage_bytes + 2048;
+  const int smem = p.stages * p.stage_bytes + 4096;
   conv_kxn_kernel<<<grid, THREADS, smem, stream>>>(maps, p);
   count_launch();
   return static_cast<int>(cudaGetLastError());

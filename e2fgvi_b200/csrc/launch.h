@@ -94,9 +94,9 @@ int launch_conv3x3(int nsrc, const void* const* src_hi, const void* const* src_l
                    void* out_hi, void* out_lo, int n, int h_in, int w_in, int cout, int groups, float slope, int ks,
                    int stride, int pad, int in_rows, int out_lead, cudaStream_t stream, const ConvGeom* geom = nullptr,
                    int epi_flags = 0);     // 1: tanh, 2: NCHW fp32 output (3-channel output conv only)
-int launch_conv_kxn(const void* src_hi, const void* src_lo, int c, const void* w_hi, const void* w_lo, const float* bias,
-                    const float* residual, float* out, void* out_hi, void* out_lo, int n, int h, int w, int cout, int co_pad,
-                    int ks, float slope, int flags, cudaStream_t stream);
+int launch_conv_kxn(int nsrc, const void* const* src_hi, const void* const* src_lo, const int* src_c, const void* w_hi,
+                    const void* w_lo, const float* bias, const float* residual, float* out, void* out_hi, void* out_lo, int n,
+                    int h, int w, int cout, int groups, int co_pad, int ks, float slope, int flags, cudaStream_t stream);
 int conv_rows_tail(int lead, int channels);
 int conv_rows_pitch(int w, int lead, int channels);
 int launch_pack_rows(const float* x, void* hi, void* lo, int n, int c, int h, int w, int cin, int lead,

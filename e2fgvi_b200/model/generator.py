@@ -100,7 +100,10 @@ class Encoder(nn.Module):
                 out = ops.pack_rows(out, lead=conv.padding[0])
             if k == 4:
                 x0 = out
-            if k > 4:
+            if k > 4 and ops.KXN_CONVS and conv.out_channels // conv.groups <= 32 and mode == "split":
+                # groups of 32 output channels (e2fgvi.py:97): the kx-in-N kernel, one tile per (pixels, group)
+                out = ops.conv_kxn([x0, out], conv.weight, conv.bias, negative_slope=0.2, out=mode, groups=conv.groups)
+            elif k > 4:
                 out = ops.conv3x3([x0, out], conv.weight, conv.bias, groups=self.group[k - 4], negative_slope=0.2,
                                   out=mode)
             else:

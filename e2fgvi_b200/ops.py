@@ -1077,16 +1077,29 @@ def soft_comp(tokens, weight, bias, output_size, kernel_size, stride, padding, b
                         (h, w), 2.0 * n * fh * fw * hidden * c * k * k)
 
 
-def pack_conv_kxn_weight(weight, co_pad):
-    """fp32 (Cout, C, k, k) -> (hi, lo) bf16 (k*co_pad, k*chunks*64) in the operand order of ``e2f_conv_kxn_bf16x3``:
-    row = kx*co_pad + co, column = (ky*chunks + chunk)*64 + channel; zeros for co >= Cout and padded channels."""
-    cout, c, kh, kw = weight.shape
-    assert kh == kw and cout <= co_pad
-    chunks = (c + 63) // 64
-    w = weight.detach().float()
-    packed = torch.zeros((kw, co_pad, kh, chunks * 64), dtype=torch.float32, device=weight.device)
-    packed[:, :cout, :, :c] = w.permute(3, 0, 2, 1)                # [kx][co][ky][c]
-    return split_bf16(packed.view(kw * co_pad, kh * chunks * 64))
+def pack_conv_kxn_weight(weight, co_pad, src_channels=None, groups=1):
+    """fp32 (Cout, Cin/G, k, k) -> (hi, lo) bf16 (G*k*co_pad, k*chunks*64) in the operand order of ``e2f_conv_kxn_bf16x3``:
+    row = g*k*co_pad + kx*co_pad + co, column = (ky*chunks + chunk)*64 + channel, the chunks of source 0 first, then source
+    1 (the group-local input channel axis is the concatenation of the sources' per-group slices, like
+    ``pack_conv3x3_weight``); zeros for co >= Cout/G and for padded channels."""
+    cout, cin_g, kh, kw = weight.shape
+    assert kh == kw and cout % groups == 0
+    cog = cout // groups
+    assert cog <= co_pad
+    src_channels = [cin_g * groups] if src_channels is None else list(src_channels)
+    cig = [c // groups for c in src_channels]
+    assert sum(cig) == cin_g, (src_channels, groups, cin_g)
+    nch = [(c + 63) // 64 for c in cig]
+    chunks = sum(nch)
+    w = weight.detach().float().view(groups, cog, cin_g, kh, kw)
+    packed = torch.zeros((groups, kw, co_pad, kh, chunks * 64), dtype=torch.float32, device=weight.device)
+    off, base = 0, 0
+    for c, n_ in zip(cig, nch):
+        # [g][co][c][ky][kx] -> [g][kx][co][ky][c]
+        packed[:, :, :cog, :, base * 64: base * 64 + c] = w[:, :, off: off + c].permute(0, 4, 1, 3, 2)
+        off += c
+        base += n_
+    return split_bf16(packed.view(groups * kw * co_pad, kh * chunks * 64))
 
 
 def _kxn_co_pad(cout, ks):
@@ -1097,26 +1110,33 @@ def _kxn_co_pad(cout, ks):
     return None
 
 
-def conv_kxn(x, weight, bias=None, negative_slope=1.0, residual=None, out="f32", tanh_nchw=False):
-    """k x k / stride 1 / pad k//2 conv (k = 3 or 7) with FEW output channels (<= 32) on the "kx-in-N" kernel: SPyNet's
-    64 -> 32 / 32 -> 16 / 16 -> 2 convs (flow_comp.py:181-215) and the decoder's output conv (e2fgvi.py:149-150).
-    x: (N,C,H,W) fp32 or ``SplitNHWC``; residual (N,Cout,H,W) logical with NHWC storage; out = "f32" | "split" | "both";
-    ``tanh_nchw``: tanh + contiguous NCHW fp32 result (the prediction, e2fgvi.py:262)."""
-    src = _as_split_nhwc(x)
-    n, c, h, w = src.shape
-    cout, cin, ks, ks2 = weight.shape
-    co_pad = _kxn_co_pad(cout, ks)
-    if ks != ks2 or ks not in (3, 7) or cin != c or co_pad is None:
-        raise ValueError(f"conv_kxn: unsupported weight {tuple(weight.shape)} for a {c}-channel source")
+def conv_kxn(x, weight, bias=None, negative_slope=1.0, residual=None, out="f32", tanh_nchw=False, groups=1):
+    """k x k / stride 1 / pad k//2 conv (k = 3 or 7) with FEW output channels per group (<= 32) on the "kx-in-N" kernel:
+    SPyNet's 64 -> 32 / 32 -> 16 / 16 -> 2 convs (flow_comp.py:181-215), the decoder's output conv (e2fgvi.py:149-150) and
+    the encoder's groups-of-32 conv (e2fgvi.py:97; two sources, group-wise concatenation never built).
+    x: (N,C,H,W) fp32 / ``SplitNHWC`` or a list of up to two of them; residual (N,Cout,H,W) logical with NHWC storage;
+    out = "f32" | "split" | "both"; ``tanh_nchw``: tanh + contiguous NCHW fp32 result (the prediction, e2fgvi.py:262)."""
+    srcs = [_as_split_nhwc(s_) for s_ in (x if isinstance(x, (list, tuple)) else [x])]
+    n, _, h, w = srcs[0].shape
+    chans = [s_.shape[1] for s_ in srcs]
+    cout, cin_g, ks, ks2 = weight.shape
+    co_pad = _kxn_co_pad(cout // groups, ks) if cout % groups == 0 else None
+    if (ks != ks2 or ks not in (3, 7) or sum(chans) != cin_g * groups or co_pad is None or len(srcs) > 2
+            or any(c % groups or s_.hi.shape[-1] != c for c, s_ in zip(chans, srcs))):
+        raise ValueError(f"conv_kxn: unsupported weight {tuple(weight.shape)} / groups {groups} for sources {chans}")
+    for s_ in srcs:
+        if (s_.shape[0], s_.shape[2], s_.shape[3]) != (n, h, w) or not s_.hi.is_contiguous() or not s_.lo.is_contiguous():
+            raise ValueError("conv_kxn: sources must be dense and share N, H, W")
     _need_cuda(weight, bias, residual)
-    w_hi, w_lo = _derived([weight], ("kxn", co_pad), lambda: pack_conv_kxn_weight(weight, co_pad))
+    w_hi, w_lo = _derived([weight], ("kxn", co_pad, tuple(chans), groups),
+                          lambda: pack_conv_kxn_weight(weight, co_pad, chans, groups))
     b32 = None if bias is None else bias.detach().float().contiguous()
     dev = weight.device
     want_f32, want_split = out in ("f32", "both"), out in ("split", "both")
     if tanh_nchw and out != "f32":
         raise ValueError("conv_kxn: tanh_nchw returns the fp32 NCHW tensor only")
-    if want_split and cout % 8:
-        raise ValueError("conv_kxn: split output needs Cout % 8 == 0")
+    if want_split and (cout // groups) % 8:
+        raise ValueError("conv_kxn: split output needs Cout / groups % 8 == 0")
     res = None
     if residual is not None:
         res = residual.permute(0, 2, 3, 1).contiguous().float()          # no-op for NHWC storage
@@ -1126,12 +1146,16 @@ def conv_kxn(x, weight, bias=None, negative_slope=1.0, residual=None, out="f32",
     if want_split:
         ohi = torch.empty((n, h, w, cout), dtype=torch.bfloat16, device=dev)
         olo = torch.empty((n, h, w, cout), dtype=torch.bfloat16, device=dev)
-    with _timed("conv3x3_bf16x3", 2.0 * n * h * w * cout * cin * ks * ks):
-        st = _lib.load().e2f_conv_kxn_bf16x3(src.hi.data_ptr(), src.lo.data_ptr(), src.hi.shape[-1], w_hi.data_ptr(),
-                                             w_lo.data_ptr(), None if b32 is None else b32.data_ptr(),
+    k = len(srcs)
+    hi_arr = (_lib._vp * k)(*[s_.hi.data_ptr() for s_ in srcs])
+    lo_arr = (_lib._vp * k)(*[s_.lo.data_ptr() for s_ in srcs])
+    ch_arr = (_lib._i * k)(*[s_.hi.shape[-1] for s_ in srcs])
+    with _timed("conv3x3_bf16x3", 2.0 * n * h * w * cout * cin_g * ks * ks):
+        st = _lib.load().e2f_conv_kxn_bf16x3(k, hi_arr, lo_arr, ch_arr, w_hi.data_ptr(), w_lo.data_ptr(),
+                                             None if b32 is None else b32.data_ptr(),
                                              None if res is None else res.data_ptr(),
                                              None if o32 is None else o32.data_ptr(), None if ohi is None else ohi.data_ptr(),
-                                             None if olo is None else olo.data_ptr(), n, h, w, cout, co_pad, ks,
+                                             None if olo is None else olo.data_ptr(), n, h, w, cout, groups, co_pad, ks,
                                              float(negative_slope), 3 if tanh_nchw else 0, _stream())
     _lib.check(st, "e2f_conv_kxn_bf16x3")
     if tanh_nchw:

@@ -260,15 +260,21 @@ int e2f_conv3x3_tanh_nchw(const void* src_hi, const void* src_lo, int cin, const
  * and the epilogue adds the kx columns with a horizontal shift (warp shuffles: one warp per tile row), out[y, x, co] =
  * sum_kx D[(y, x+kx-pad), (kx, co)]: one read of an A tile feeds k times more output columns, so these layers are bound
  * by tensor math instead of by re-reading the A operand for every tap.
- *   src_hi / src_lo: ONE NHWC bf16 (hi, lo) source [N][H][W][cin] (cin % 8 == 0; channels beyond cin are zero-filled)
- *   w_hi / w_lo:     [k*co_pad rows][k*ceil(cin/64)*64] bf16: row = kx*co_pad + co, column = (ky*chunks + chunk)*64 + c
- *                    (zeros for co >= Cout and padded channels); co_pad % 8 == 0, <= 32, and k*co_pad % 16 == 0
+ * Also the encoder's groups-of-32 conv (model/e2fgvi.py:97, 640 -> 256, groups 8: 32 + 48 input and 32 output channels per
+ * group), whose 64-wide N tiles / K chunks were half zero padding in the plain kernel: a tile is (pixels, group).
+ *   src_hi / src_lo: nsrc <= 2 NHWC bf16 (hi, lo) sources [N][H][W][src_channels[i]] (multiples of 8 and of `groups`); the
+ *                    group-local input channel axis is the concatenation of the sources' per-group slices (the
+ *                    group-wise torch.cat of e2fgvi.py:103-108), never materialised
+ *   w_hi / w_lo:     [groups * k*co_pad rows][k*chunks*64] bf16: row = g*k*co_pad + kx*co_pad + co, column =
+ *                    (ky*chunks + chunk)*64 + c, chunks = sum_i ceil(src_channels[i]/groups/64) with source 0's chunks
+ *                    first (zeros for co >= Cout/groups and padded channels); co_pad % 8 == 0, <= 32, k*co_pad % 16 == 0
  *   epilogue: + bias[Cout], LeakyReLU(leaky_slope) (1 = none, 0 = ReLU), + residual (NHWC fp32 [N][H][W][Cout] or NULL),
  *             flags bit 0: tanh, bit 1: fp32 output stored NCHW ([N][Cout][H][W]); outputs: out fp32 NHWC (or NCHW) and / or
- *             the bf16 (hi, lo) split NHWC [N][H][W][Cout] (Cout % 8 == 0). */
-int e2f_conv_kxn_bf16x3(const void* src_hi, const void* src_lo, int cin, const void* w_hi, const void* w_lo,
-                        const float* bias, const float* residual, float* out, void* out_hi, void* out_lo, int n, int h, int w,
-                        int cout, int co_pad, int ksize, float leaky_slope, int flags, void* stream);
+ *             the bf16 (hi, lo) split NHWC [N][H][W][Cout] (Cout/groups % 8 == 0). */
+int e2f_conv_kxn_bf16x3(int nsrc, const void* const* src_hi, const void* const* src_lo, const int* src_channels,
+                        const void* w_hi, const void* w_lo, const float* bias, const float* residual, float* out, void* out_hi,
+                        void* out_lo, int n, int h, int w, int cout, int groups, int co_pad, int ksize, float leaky_slope,
+                        int flags, void* stream);
 
 /* "Gather conv": the same implicit GEMM with an explicit TAP TABLE, OUTPUT PHASES and tile shape (groups == 1).
  * Replaces, without ever building the unfolded operand:

@@ -160,6 +160,14 @@ def _conv3x3(sources, weight, bias=None, groups=1, negative_slope=1.0, residual=
     return (y, _as_split(y)) if out == "both" else y
 
 
+def _conv_kxn(x, weight, bias=None, negative_slope=1.0, residual=None, out="f32", tanh_nchw=False, groups=1):
+    y = _conv3x3(x if isinstance(x, (list, tuple)) else [x], weight, bias, groups=groups, negative_slope=negative_slope,
+                 residual=residual, out="f32")
+    if tanh_nchw:
+        return torch.tanh(y).contiguous()
+    return y if out == "f32" else _as_split(y) if out == "split" else (y, _as_split(y))
+
+
 def _conv3x3_tanh_nchw(x, weight, bias):
     return torch.tanh(torch.nn.functional.conv2d(_dense(x), weight, bias, 1, 1)).contiguous()
 
@@ -198,7 +206,7 @@ def oracle_ops():
                                           "modulated_deform_conv2d", "focal_window_attention", "t2t_unfold",
                                           "t2t_fold", "linear", "conv3x3", "split_nhwc", "upsample2x_split",
                                           "layer_norm", "dcn_pack_input", "t2t_fold_unfold", "pack_rows", "window_pool",
-                                          "prop_prologue", "soft_split", "soft_comp", "layer_norm_pool", "conv_frames", "split_bf16", "conv3x3_tanh_nchw")}
+                                          "prop_prologue", "soft_split", "soft_comp", "layer_norm_pool", "conv_frames", "split_bf16", "conv3x3_tanh_nchw", "conv_kxn")}
     ops.flow_warp, ops.pack_dcn_weight, ops.deform_align_fused = _flow_warp, _pack, _fused
     ops.modulated_deform_conv2d, ops.focal_window_attention = _mdcn, _attention
     ops.t2t_unfold, ops.t2t_fold, ops.linear, ops.t2t_fold_unfold = _unfold, _fold, _linear, _fold_unfold
@@ -207,6 +215,7 @@ def oracle_ops():
     ops.prop_prologue = _prop_prologue
     ops.soft_split, ops.soft_comp, ops.layer_norm_pool = _soft_split, _soft_comp, _layer_norm_pool
     ops.conv_frames, ops.split_bf16, ops.conv3x3_tanh_nchw = _conv_frames, _split_bf16, _conv3x3_tanh_nchw
+    ops.conv_kxn = _conv_kxn
     try:
         yield
     finally:

@@ -693,6 +693,27 @@ def test_conv_kxn(cuda, case):
         assert got.is_contiguous()
 
 
+@pytest.mark.parametrize("shape", [(2, 12, 20), (1, 60, 108)])
+def test_conv_kxn_grouped_two_sources(cuda, shape):
+    """Encoder conv 7 (e2fgvi.py:97,103-108): 640 -> 256, groups 8, input = group-wise cat of x0 (256 ch) and the previous
+    output (384 ch), on the kx-in-N kernel with one tile per (pixels, group); the cat is never built."""
+    import torch.nn.functional as F
+    n, h, w = shape
+    g = torch.Generator().manual_seed(56)
+    x0 = torch.randn(n, 256, h, w, generator=g)
+    x1 = torch.randn(n, 384, h, w, generator=g)
+    conv = torch.nn.Conv2d(640, 256, 3, 1, 1, groups=8)
+    xcat = torch.cat([x0.view(n, 8, -1, h, w), x1.view(n, 8, -1, h, w)], 2).view(n, -1, h, w)
+    want = F.leaky_relu(F.conv2d(xcat.double(), conv.weight.double(), conv.bias.double(), 1, 1, 1, 8), 0.2)
+    conv = conv.to(cuda)
+    with torch.no_grad():
+        t32, sp = ops.conv_kxn([x0.to(cuda), x1.to(cuda)], conv.weight, conv.bias, negative_slope=0.2, out="both", groups=8)
+        old = ops.conv3x3([x0.to(cuda), x1.to(cuda)], conv.weight, conv.bias, groups=8, negative_slope=0.2)
+    assert _rel(t32.cpu(), want) < 5e-5
+    assert _rel((sp.hi.float() + sp.lo.float()).permute(0, 3, 1, 2).cpu(), want) < 5e-5
+    assert _rel(old.cpu(), want) < 5e-5
+
+
 # ------------------------------------------------------------------------------------------ SoftSplit / SoftComp as gather convs
 @pytest.mark.parametrize("shape", [(3, 128, 60, 108), (2, 64, 15, 27), (1, 128, 45, 81), (2, 128, 30, 54)])
 def test_soft_split_matches_unfold_linear(cuda, shape):

@@ -36,3 +36,14 @@ for name, n, cin, cout, ks, h, w in (("spynet 64->32 k7", 112, 64, 32, 7, 64, 12
     t_old = timeit(lambda: ops.conv3x3(src_old, wt, b, negative_slope=0.0, out="f32"))
     t_new = timeit(lambda: ops.conv_kxn(xs, wt, b, negative_slope=0.0, out="f32"))
     print(f"KXN {name:18s} plain {t_old:8.1f} us ({flops / t_old / 1e6:6.1f} TFLOP/s)   kx-in-N {t_new:8.1f} us ({flops / t_new / 1e6:6.1f} TFLOP/s)")
+
+# encoder conv 7: 640 -> 256, groups 8, two sources (256 + 384 channels), 64 frames at 60x108
+x0 = torch.randn(64, 256, 60, 108, device=dev)
+x1 = torch.randn(64, 384, 60, 108, device=dev)
+s0, s1 = ops.split_nhwc(x0), ops.split_nhwc(x1)
+wt = torch.nn.Parameter(torch.randn(256, 80, 3, 3, device=dev) * 0.05)
+b = torch.nn.Parameter(torch.randn(256, device=dev))
+flops = 2.0 * 64 * 60 * 108 * 256 * 80 * 9
+t_old = timeit(lambda: ops.conv3x3([s0, s1], wt, b, groups=8, negative_slope=0.2, out="split"))
+t_new = timeit(lambda: ops.conv_kxn([s0, s1], wt, b, negative_slope=0.2, out="split", groups=8))
+print(f"KXN enc7 640->256 g8      plain {t_old:8.1f} us ({flops / t_old / 1e6:6.1f} TFLOP/s)   kx-in-N {t_new:8.1f} us ({flops / t_new / 1e6:6.1f} TFLOP/s)")
