@@ -249,6 +249,7 @@ class Measurement:
         self.out_host = torch.empty((B * self.T, 3, self.H, self.W), dtype=torch.float32).pin_memory()
         self.num_clips = B * world
         self.stitch = C.ClipStitcher(self.num_clips, self.T, rank, world)
+        self._copy_streams = None
 
     def sync(self):
         if self.world > 1:
@@ -256,26 +257,62 @@ class Measurement:
         torch.cuda.synchronize()
 
     def _loop(self, n, inputs, to_host=False):
-        """n steps; the stitch of step i overlaps the forward of step i+1 (double-buffered landing zone)."""
+        """n steps; the stitch of step i overlaps the forward of step i+1 (double-buffered landing zone).
+
+        ``to_host``: the end-to-end pipeline a caller of the public API runs — every step's inputs come from PINNED HOST
+        memory and its result goes back to pinned host memory, inside the timed region.  The copies ride their own
+        streams: the H2D of step i+1 is issued while step i computes (double-buffered device input), the D2H of step i
+        runs while step i+1 computes; the forward itself is the unchanged ``model(x, l_t)`` call on the current stream."""
         pending = None
         B, T = self.B, self.T
+        main = torch.cuda.current_stream()
+        if to_host and self._copy_streams is None:
+            self._copy_streams = (torch.cuda.Stream(device=self.dev), torch.cuda.Stream(device=self.dev))
+        h2d, d2h = self._copy_streams if to_host else (None, None)
+
+        def upload(i):
+            with torch.cuda.stream(h2d):
+                x = inputs[i % self.n_sets].to(self.dev, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(h2d)
+            return x, ev
+
+        def download(t):
+            """device tensor produced on `main` -> pinned host, on the D2H stream"""
+            ev = torch.cuda.Event()
+            ev.record(main)
+            with torch.cuda.stream(d2h):
+                d2h.wait_event(ev)
+                self.out_host.copy_(t, non_blocking=True)
+            t.record_stream(d2h)
+
+        nxt_in = upload(0) if to_host and n > 0 else None
         for i in range(n):
-            x = inputs[i % self.n_sets]
             if to_host:
-                x = x.to(self.dev, non_blocking=True)
+                x, ev = nxt_in
+                main.wait_event(ev)
+                x.record_stream(main)
+            else:
+                x = inputs[i % self.n_sets]
             pred, _ = self.model(x, self.l_t)
+            if to_host and i + 1 < n:
+                nxt_in = upload(i + 1)                    # overlaps this step's forward
+            if to_host and self.world > 1:
+                main.wait_stream(d2h)                     # the landing buffer about to be reused has been read out
             nxt = self.stitch.start(pred) if self.world > 1 else None
             if pending is not None:
                 got = pending.wait()
                 if to_host:
-                    self.out_host.copy_(got[self.rank * B * T:(self.rank + 1) * B * T], non_blocking=True)
+                    download(got[self.rank * B * T:(self.rank + 1) * B * T])
             if self.world == 1 and to_host:
-                self.out_host.copy_(pred, non_blocking=True)
+                download(pred)
             pending = nxt
         if pending is not None:
             got = pending.wait()
             if to_host:
-                self.out_host.copy_(got[self.rank * B * T:(self.rank + 1) * B * T], non_blocking=True)
+                download(got[self.rank * B * T:(self.rank + 1) * B * T])
+        if to_host:
+            main.wait_stream(d2h)                          # the timed region ends when the last result is on the host
 
     def run(self, sample_clocks=False, profile=True):
         from e2fgvi_b200 import ops

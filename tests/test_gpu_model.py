@@ -106,6 +106,27 @@ def test_reference_operator_goldens(cuda):
     assert got.shape == wa["out"].shape and rel < 2e-3, rel
 
 
+def test_two_devices_in_one_process():
+    """Function attributes (opt-in shared memory), SM counts and cluster occupancy are cached PER DEVICE (launch.h
+    DeviceOnce): a second GPU driven from the same process must work (a process-wide `static bool configured`
+    made every > 48 KB-smem kernel fail with cudaErrorInvalidValue on cuda:1)."""
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs in one process")
+    from e2fgvi_b200 import build
+    build.build()
+    x = synth_frames(1, 4, 120, 216, seed=5)
+    outs = []
+    for idx in (0, 1):
+        dev = torch.device("cuda", idx)
+        with torch.cuda.device(dev):
+            model = _model(True, "stress", 0, dev)
+            with torch.no_grad():
+                pred, _ = model(x.to(dev), 3)
+            torch.cuda.synchronize(dev)
+            outs.append(pred.cpu())
+    assert torch.equal(outs[0], outs[1])
+
+
 def test_cuda_graphs_behind_the_public_call(cuda):
     """model.enable_cuda_graphs(): the SAME call replays a per-shape captured graph, bit-identical to eager, for
     several shapes (LRU of captures) and fresh output tensors per call."""
