@@ -15,6 +15,7 @@
 // Pipeline = conv.cu: persistent CTAs, TMA warp / MMA warp / 4 epilogue warps, double-buffered TMEM accumulator.
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cstdlib>
 #include "common.cuh"
 #include "launch.h"
 
@@ -36,7 +37,9 @@ struct Params {
                                                     // columns (multiple of 16, <= 256); chunks = K chunks per ky (all sources)
   int groups, cout_total;                           // grouped conv (encoder conv 7, e2fgvi.py:97): tile = (pixels, group)
   int nsrc, cig[MAX_SRC], src_chunks[MAX_SRC];      // channels per group and 64-wide K chunks of each source
-  int stage_bytes, stages;
+  int stage_bytes, stages;     // plain variant: ring of [Ah | Al | Wh | Wl] stages, one per (ky, chunk)
+  int a_slot_bytes, a_slots;   // HALO variant: ring of [Ah halo | Al halo] slots, one per chunk: (TH + ks - 1) x 32 pixel rows
+  int w_slot_bytes, w_slots;   //               ring of [Wh | Wl] slots, one per (chunk, ky)
   float slope;
   int flags;
   const float* bias;
@@ -57,15 +60,23 @@ __device__ __forceinline__ void tma_load_4d(uint32_t smem_dst, const void* tmap,
       : "memory");
 }
 
+// HALO = true (N <= 112 columns: the A operand dominates the L2 -> SM traffic): instead of one 4-row A box per (ky, chunk),
+// ONE box of TH + ks - 1 rows per chunk brings the tile's whole vertical halo; the A tile of tap row ky is rows
+// [32*ky, 32*ky + 128) of it — a descriptor start shifted by ky * 4096 B, a multiple of the 1024-byte swizzle atom — and only
+// the weights stream per ky through their own ring.  A bytes per tile drop 2x (3x3) to 2.8x (7x7).
+template <bool HALO>
 __global__ void __launch_bounds__(THREADS, 1) conv_kxn_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Params p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + p.stages * p.stage_bytes);
+  const int ring_bytes = HALO ? p.a_slots * p.a_slot_bytes + p.w_slots * p.w_slot_bytes : p.stages * p.stage_bytes;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + ring_bytes);      // plain: stage full / HALO: A slot full
   uint64_t* empty = full + 4;
   uint64_t* acc_full = empty + 4;
   uint64_t* acc_empty = acc_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
-  float* bias_s = reinterpret_cast<float*>(smem + p.stages * p.stage_bytes + 128);     // [512]
+  uint64_t* w_full = acc_empty + 2;                                      // HALO: weight ring
+  uint64_t* w_empty = w_full + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_empty + 4);
+  float* bias_s = reinterpret_cast<float*>(smem + ring_bytes + 256);     // [512]
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int W_TILE = p.NB * BK * 2;
@@ -78,9 +89,11 @@ __global__ void __launch_bounds__(THREADS, 1) conv_kxn_kernel(const __grid_const
 
   if (warp == 1) tmem_alloc(tmem_slot, tmem_cols);
   if (tid == 0) {
-    for (int s = 0; s < p.stages; ++s) {
+    for (int s = 0; s < 4; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
+      mbar_init(&w_full[s], 1);
+      mbar_init(&w_empty[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&acc_full[s], 1);
@@ -102,6 +115,37 @@ __global__ void __launch_bounds__(THREADS, 1) conv_kxn_kernel(const __grid_const
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (elect_one()) {
+      if (HALO) {
+        const int HR = TH + p.ks - 1;
+        const uint32_t a_tx = 2u * static_cast<uint32_t>(HR) * TW * 128u, w_tx = 2u * static_cast<uint32_t>(W_TILE);
+        uint8_t* wring = smem + p.a_slots * p.a_slot_bytes;
+        uint32_t ia = 0, iw = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+          const int g = tile % p.groups, tp = tile / p.groups;
+          const int tx = tp % tiles_x, ty = (tp / tiles_x) % tiles_y, n = tp / (tiles_x * tiles_y);
+          const int xs = tx * step_x - p.pad, ys = ty * TH - p.pad;     // first D-grid column / first halo row
+          int chunk = 0;
+          for (int s = 0; s < p.nsrc; ++s)
+            for (int j = 0; j < p.src_chunks[s]; ++j, ++chunk, ++ia) {
+              const int aslot = ia % p.a_slots;
+              mbar_wait(&empty[aslot], ((ia / p.a_slots) & 1) ^ 1);
+              mbar_arrive_expect_tx(&full[aslot], a_tx);
+              const uint32_t a0 = smem_u32(smem + aslot * p.a_slot_bytes);
+              const int c0 = g * p.cig[s] + j * BK;
+              tma_load_4d(a0, &maps.a_hi[s], &full[aslot], c0, xs, ys, n);
+              tma_load_4d(a0 + HR * TW * 128, &maps.a_lo[s], &full[aslot], c0, xs, ys, n);
+              for (int ky = 0; ky < p.ks; ++ky, ++iw) {
+                const int wslot = iw % p.w_slots;
+                mbar_wait(&w_empty[wslot], ((iw / p.w_slots) & 1) ^ 1);
+                mbar_arrive_expect_tx(&w_full[wslot], w_tx);
+                const uint32_t w0 = smem_u32(wring + wslot * p.w_slot_bytes);
+                const int kb = ky * p.chunks + chunk;
+                tma_load_2d(w0, &maps.w_hi, &w_full[wslot], kb * BK, g * p.NB);
+                tma_load_2d(w0 + W_TILE, &maps.w_lo, &w_full[wslot], kb * BK, g * p.NB);
+              }
+            }
+        }
+      } else {
       const uint32_t stage_tx = 2u * A_TILE + 2u * static_cast<uint32_t>(W_TILE);
       uint32_t it = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -124,11 +168,48 @@ __global__ void __launch_bounds__(THREADS, 1) conv_kxn_kernel(const __grid_const
               tma_load_2d(s0 + 2 * A_TILE + W_TILE, &maps.w_lo, &full[stage], kb * BK, g * p.NB);
             }
       }
+      }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
     if (elect_one()) {
       const uint32_t idesc = idesc_bf16(BM, p.NB);
+      if (HALO) {
+        const int HR = TH + p.ks - 1;
+        const uint32_t lo_off = static_cast<uint32_t>(HR * TW * 128) >> 4;
+        const uint64_t d_a0 = umma_desc_sw128(smem_u32(smem), 16, 1024);
+        const uint64_t d_w0 = umma_desc_sw128(smem_u32(smem + p.a_slots * p.a_slot_bytes), 16, 1024);
+        uint32_t ia = 0, iw = 0, local = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+          const int buf = local & 1;
+          mbar_wait(&acc_empty[buf], ((local >> 1) & 1) ^ 1);
+          tc_fence_after_sync();
+          const uint32_t d = tbase + buf * p.NB;
+          for (int chunk = 0; chunk < p.chunks; ++chunk, ++ia) {
+            const int aslot = ia % p.a_slots;
+            mbar_wait(&full[aslot], (ia / p.a_slots) & 1);
+            const uint64_t d_ah = d_a0 + (static_cast<uint32_t>(aslot * p.a_slot_bytes) >> 4);
+            for (int ky = 0; ky < p.ks; ++ky, ++iw) {
+              const int wslot = iw % p.w_slots;
+              mbar_wait(&w_full[wslot], (iw / p.w_slots) & 1);
+              tc_fence_after_sync();
+              const uint64_t dah0 = d_ah + ((static_cast<uint32_t>(ky) * TW * 128) >> 4);   // rows [32 ky, 32 ky + 128) of the halo
+              const uint64_t dwh0 = d_w0 + (static_cast<uint32_t>(wslot * p.w_slot_bytes) >> 4);
+              const uint64_t dwl0 = dwh0 + (static_cast<uint32_t>(W_TILE) >> 4);
+#pragma unroll
+              for (int k = 0; k < BK / 16; ++k) {
+                const uint64_t dah = dah0 + 2 * k, dal = dah0 + lo_off + 2 * k;
+                umma_f16(d, dal, dwh0 + 2 * k, idesc, (chunk | ky | k) != 0);   // small terms first
+                umma_f16(d, dah, dwl0 + 2 * k, idesc, 1);
+                umma_f16(d, dah, dwh0 + 2 * k, idesc, 1);
+              }
+              umma_commit(&w_empty[wslot]);
+            }
+            umma_commit(&empty[aslot]);
+          }
+          umma_commit(&acc_full[buf]);
+        }
+      } else {
       const uint64_t d_ah0 = umma_desc_sw128(smem_u32(smem), 16, 1024);
       const uint64_t d_al0 = umma_desc_adv(d_ah0, A_TILE), d_wh0 = umma_desc_adv(d_ah0, 2 * A_TILE);
       const uint64_t d_wl0 = umma_desc_adv(d_wh0, W_TILE);
@@ -154,6 +235,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_kxn_kernel(const __grid_const
           umma_commit(&empty[stage]);
         }
         umma_commit(&acc_full[buf]);
+      }
       }
     }
   } else {
@@ -300,7 +382,23 @@ int launch_conv_kxn(int nsrc, const void* const* src_hi, const void* const* src_
   const int w_tile = NB * BK * 2;
   p.stage_bytes = 2 * A_TILE + 2 * w_tile;                      // multiple of 1024 (NB % 16 == 0 -> NB*128 % 2048 == 0)
   p.stages = (3 * p.stage_bytes + 4096 <= 225 * 1024) ? 3 : 2;
-  if (p.stages * p.stage_bytes + 4096 > 227 * 1024) {
+  // HALO variant where A dominates the operand traffic and two halo slots + >= 2 weight slots fit
+  const int HR = TH + ks - 1;
+  p.a_slot_bytes = 2 * HR * TW * 128;
+  p.a_slots = 2;
+  p.w_slot_bytes = 2 * w_tile;
+  p.w_slots = 3;
+  bool halo = NB <= 112;
+  if (halo && p.a_slots * p.a_slot_bytes + p.w_slots * p.w_slot_bytes + 4096 > 227 * 1024) p.w_slots = 2;
+  if (halo && p.a_slots * p.a_slot_bytes + p.w_slots * p.w_slot_bytes + 4096 > 227 * 1024) halo = false;
+  {
+    static const bool off = [] {
+      const char* e = getenv("E2F_KXN_HALO");
+      return e && e[0] == '0';
+    }();
+    if (off) halo = false;
+  }
+  if (!halo && p.stages * p.stage_bytes + 4096 > 227 * 1024) {
     set_error("conv_kxn: stage does not fit in shared memory");
     return -2;
   }
@@ -308,7 +406,7 @@ int launch_conv_kxn(int nsrc, const void* const* src_hi, const void* const* src_
     const int c = src_c[i];
     const cuuint64_t dims[4] = {static_cast<cuuint64_t>(c), static_cast<cuuint64_t>(w), static_cast<cuuint64_t>(h), static_cast<cuuint64_t>(n)};
     const cuuint64_t strides[3] = {static_cast<cuuint64_t>(c) * 2, static_cast<cuuint64_t>(w) * c * 2, static_cast<cuuint64_t>(h) * w * c * 2};
-    const cuuint32_t box[4] = {BK, TW, TH, 1};
+    const cuuint32_t box[4] = {BK, TW, static_cast<cuuint32_t>(halo ? HR : TH), 1};
     const cuuint32_t estr[4] = {1, 1, 1, 1};
     for (int part = 0; part < 2; ++part) {
       CUresult r = enc(part ? &maps.a_lo[i] : &maps.a_hi[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4,
@@ -339,7 +437,8 @@ int launch_conv_kxn(int nsrc, const void* const* src_hi, const void* const* src_
   static DeviceOnce cfg;
   const int dev = current_device();
   if (!device_done(cfg, dev)) {
-    cudaError_t e = cudaFuncSetAttribute(conv_kxn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(conv_kxn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_kxn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return static_cast<int>(e);
     device_mark(cfg, dev);
   }
@@ -351,8 +450,13 @@ int launch_conv_kxn(int nsrc, const void* const* src_hi, const void* const* src_
     return -2;
   }
   const int grid = tiles < num_sms() ? static_cast<int>(tiles) : num_sms();
-  const int smem = p.stages * p.stage_bytes + 4096;
-  conv_kxn_kernel<<<grid, THREADS, smem, stream>>>(maps, p);
+  if (halo) {
+    const int smem = p.a_slots * p.a_slot_bytes + p.w_slots * p.w_slot_bytes + 4096;
+    conv_kxn_kernel<true><<<grid, THREADS, smem, stream>>>(maps, p);
+  } else {
+    const int smem = p.stages * p.stage_bytes + 4096;
+    conv_kxn_kernel<false><<<grid, THREADS, smem, stream>>>(maps, p);
+  }
   count_launch();
   return static_cast<int>(cudaGetLastError());
 }
