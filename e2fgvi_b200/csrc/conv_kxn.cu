@@ -388,7 +388,9 @@ int launch_conv_kxn(int nsrc, const void* const* src_hi, const void* const* src_
   p.a_slots = 2;
   p.w_slot_bytes = 2 * w_tile;
   p.w_slots = 3;
-  bool halo = NB <= 112;
+  // measured (profiles/r02/kxn_bench_run11*.log): the halo variant wins for the two-chunk 3x3 grouped layer (enc7: 843 ->
+  // 804 us) and loses where a tile has ONE chunk (no A prefetch across the tile boundary hides behind 3 or 7 tap rows)
+  bool halo = NB <= 112 && ks == 3 && p.chunks >= 2;
   if (halo && p.a_slots * p.a_slot_bytes + p.w_slots * p.w_slot_bytes + 4096 > 227 * 1024) p.w_slots = 2;
   if (halo && p.a_slots * p.a_slot_bytes + p.w_slots * p.w_slot_bytes + 4096 > 227 * 1024) halo = false;
   {
