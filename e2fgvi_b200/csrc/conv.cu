@@ -752,9 +752,31 @@ int launch_conv3x3(int nsrc, const void* const* src_hi, const void* const* src_l
   // GEMM grid = output size of the plain conv, or what the generalised geometry says
   const int h = geom ? geom->grid_h : (h_in + 2 * pad - ks) / stride + 1;
   const int w = geom ? geom->grid_w : (w_in + 2 * pad - ks) / stride + 1;
-  // images smaller than a 16 x 8 tile (SPyNet's coarse pyramid levels: 2x4, 4x8 pixels) take a tile of their own size:
-  // the A boxes shrink from 16 KB to 1-4 KB per K block, and these few-CTA launches are bound by the per-SM L2 port
-  const int tile_w = geom ? geom->tile_w : (w < TILE_W ? w : TILE_W), tile_h = geom ? geom->tile_h : (h < TILE_H ? h : TILE_H);
+  // Tile shape.  Images smaller than a 16 x 8 tile (SPyNet's coarse pyramid levels: 2x4, 4x8 pixels) take a tile of their
+  // own size: the A boxes shrink from 16 KB to 1-4 KB per K block, and these few-CTA launches are bound by the per-SM L2
+  // port.  Otherwise the tile_w x tile_h <= 128 box that covers the image with the FEWEST tiles: at 60 x 108 (every
+  // propagation / encoder conv of a 432x240 clip) 12 x 10 tiles the image exactly with 54 tiles where 16 x 8 needs 56 —
+  // at 8 clips that is 432 instead of 448 tiles on 148 SMs, i.e. 3 waves instead of 4.
+  int tile_w = TILE_W, tile_h = TILE_H;
+  if (geom) {
+    tile_w = geom->tile_w;
+    tile_h = geom->tile_h;
+  } else if (w < TILE_W || h < TILE_H) {
+    tile_w = w < TILE_W ? w : TILE_W;
+    tile_h = h < TILE_H ? h : TILE_H;
+  } else if (!in_rows) {
+    long long best = static_cast<long long>((h + TILE_H - 1) / TILE_H) * ((w + TILE_W - 1) / TILE_W);
+    for (int tw = 32; tw >= 8; --tw) {                        // ties go to the wider tile (longer contiguous TMA rows)
+      const int th = BM / tw;
+      if (th < 4 || th > h || tw > w || tw * stride > 256 || th * stride > 256) continue;
+      const long long cnt = static_cast<long long>((h + th - 1) / th) * ((w + tw - 1) / tw);
+      if (cnt < best) {
+        best = cnt;
+        tile_w = tw;
+        tile_h = th;
+      }
+    }
+  }
   const int ntaps = geom ? geom->ntaps : ks * ks;
   if (ntaps < 1 || ntaps > 64 || tile_w < 1 || tile_h < 1 || tile_w * tile_h > BM || tile_w * stride > 256 ||
       tile_h * stride > 256 || (geom && (geom->nphase < 1 || geom->nphase > 9 || geom->ostep < 1))) {
