@@ -197,69 +197,67 @@ __global__ void __launch_bounds__(256, 2) t2t_fold733_kernel(const float* __rest
   const int tin_lo = FUSED ? max(0, ty0 - 2) : max(0, TR * band - 1);
   const int tin_hi = FUSED ? min(FH - 1, ty0 + tr + 1) : min(FH - 1, TR * band + TR);
   const float* src = tin + bt * FH * FW * static_cast<long long>(CK) + c0 * 49;
+  // Row-structured walk (round 2): the token row (uniform over the block) is the outer loop, each thread takes the
+  // tokens tsub, tsub + TSUB, ... of the row's phase columns.  Source pointer and shared-memory base advance by constants,
+  // the "patch entirely inside the band" test is per ROW, and the read-modify-writes of up to 4 tokens are issued as
+  // loads-then-stores (disjoint patches within a phase).  ncu of the first version: 64 thread instructions per folded
+  // float4, most of them per-token index / predicate arithmetic; this loop needs ~17.
+  const float* src_q = src + q4 * 4;
   for (int phase = 0; phase < 9; ++phase) {
     const int a = phase / 3, b = phase - 3 * a;
     const int first_ty = tin_lo + (a - tin_lo % 3 + 3) % 3;
-    const int nty = first_ty <= tin_hi ? (tin_hi - first_ty) / 3 + 1 : 0;
     const int ntx = b < FW ? (FW - 1 - b) / 3 + 1 : 0;
-    const int ntok = active ? nty * ntx : 0;
-    const float inv_ntx = 1.0f / static_cast<float>(max(ntx, 1));
-    // U tokens per thread in flight: all global loads of a batch are issued before the first shared-memory update, and
-    // the NEXT batch's loads are issued before the current batch is folded (register double buffer), so a CTA's 8
-    // warps keep ~12 x 16 B per thread in flight.  The read-modify-writes of a batch are issued as loads-then-stores:
-    // the patches of one phase are disjoint and a thread's 4 elements are distinct addresses, but the compiler cannot
-    // know that, so `simg[i] += v` per element serialises LDS -> FADD -> STS chains (r01/r02 profiles: this kernel was
-    // latency-bound at 0.38 of HBM peak, 0.18 on the HQ shapes).
-    constexpr int U = 4;
-    auto issue = [&](int tt, float4 (&v4)[U], int (&base)[U], int (&r0)[U]) {
+    if (active) {
+      for (int ty = first_ty; ty <= tin_hi; ty += 3) {
+        const int r0 = 3 * ty - 3 - ybase;                    // smem row of the patches' first row (may lie outside the band)
+        const bool whole = r0 >= 0 && r0 + 7 <= ROWS;
+        const float* rsrc = src_q + static_cast<long long>(ty * FW + b) * CK;
+        const int rbase = r0 * WP + 3 * b;
+        for (int t0 = tsub; t0 < ntx; t0 += 4 * TSUB) {
+          float4 v4[4];
+          bool live[4];
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int t = tt + u * TSUB;
-        if (t < ntok) {
-          const int tyi = __float2int_rz((static_cast<float>(t) + 0.5f) * inv_ntx), txi = t - tyi * ntx;
-          const int ty = first_ty + 3 * tyi, tx = b + 3 * txi;
-          v4[u] = __ldg(reinterpret_cast<const float4*>(src + static_cast<long long>(ty * FW + tx) * CK) + q4);
-          r0[u] = 3 * ty - 3 - ybase;              // smem row of the patch's first row (may lie outside the band)
-          base[u] = r0[u] * WP + 3 * tx;
+          for (int u = 0; u < 4; ++u) {
+            const int txi = t0 + u * TSUB;
+            live[u] = txi < ntx;
+            if (live[u]) v4[u] = __ldg(reinterpret_cast<const float4*>(rsrc + static_cast<long long>(3 * txi) * CK));
+          }
+          if (whole) {
+            float cur[4][4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              if (live[u]) {
+                const int base = rbase + 9 * (t0 + u * TSUB);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) cur[u][e] = simg[base + off[e]];
+              }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              if (live[u]) {
+                const int base = rbase + 9 * (t0 + u * TSUB);
+                simg[base + off[0]] = cur[u][0] + v4[u].x;
+                simg[base + off[1]] = cur[u][1] + v4[u].y;
+                simg[base + off[2]] = cur[u][2] + v4[u].z;
+                simg[base + off[3]] = cur[u][3] + v4[u].w;
+              }
+            }
+          } else {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              if (live[u]) {
+                const int base = rbase + 9 * (t0 + u * TSUB);
+                const float v[4] = {v4[u].x, v4[u].y, v4[u].z, v4[u].w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const int r = r0 + kyv[e];
+                  if (r >= 0 && r < ROWS) simg[base + off[e]] += v[e];
+                }
+              }
+            }
+          }
         }
       }
-    };
-    auto fold = [&](int tt, const float4 (&v4)[U], const int (&base)[U], const int (&r0)[U]) {
-      float cur[U][4];
-      bool ok[U][4];
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const bool live = tt + u * TSUB < ntok;
-        const bool whole = r0[u] >= 0 && r0[u] + 7 <= ROWS;     // patch entirely inside the band: no per-element checks
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int r = r0[u] + kyv[e];
-          ok[u][e] = live && (whole || (r >= 0 && r < ROWS));
-          cur[u][e] = ok[u][e] ? simg[base[u] + off[e]] : 0.f;
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const float v[4] = {v4[u].x, v4[u].y, v4[u].z, v4[u].w};
-#pragma unroll
-        for (int e = 0; e < 4; ++e)
-          if (ok[u][e]) simg[base[u] + off[e]] = cur[u][e] + v[e];
-      }
-    };
-    float4 va[U], vb[U];
-    int ba[U], bb[U], ra[U], rb[U];
-    int tt = tsub;
-    if (tt < ntok) issue(tt, va, ba, ra);
-    while (tt < ntok) {
-      const int nx = tt + TSUB * U;
-      if (nx < ntok) issue(nx, vb, bb, rb);
-      fold(tt, va, ba, ra);
-      tt = nx;
-      if (tt >= ntok) break;
-      const int nx2 = tt + TSUB * U;
-      if (nx2 < ntok) issue(nx2, va, ba, ra);
-      fold(tt, vb, bb, rb);
-      tt = nx2;
     }
     __syncthreads();
   }
@@ -330,22 +328,25 @@ __global__ void __launch_bounds__(256, 2) t2t_fold733_kernel(const float* __rest
   if (!FUSED) return;
   __syncthreads();
   const long long tok0 = (bt * FH + ty0) * static_cast<long long>(FW);
-  const int nout = active ? tr * FW : 0;
-  const float inv_fw = 1.0f / static_cast<float>(FW);
-  for (int t = tsub; t < nout; t += TSUB) {
-    const int tyl = __float2int_rz((static_cast<float>(t) + 0.5f) * inv_fw), tx = t - tyl * FW;
-    const int base = 3 * tyl * WP + 3 * tx, rem = q4 * 4;
-    float v[4];
+  if (active) {
+    for (int iy = 0; iy < tr; ++iy) {
+      const int rb = 3 * iy * WP;
+      const long long drow = (tok0 + static_cast<long long>(iy) * FW) * CKP + c0 * 49 + q4 * 4;
+      for (int tx = tsub; tx < FW; tx += TSUB) {
+        const int base = rb + 3 * tx;
+        float v[4];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) v[e] = simg[base + off[e]];
-    const long long dst = (tok0 + t) * CKP + c0 * 49 + rem;      // CKP: output row pitch (>= C*49)
-    if (tok) *reinterpret_cast<float4*>(tok + dst) = make_float4(v[0], v[1], v[2], v[3]);
-    if (tok_hi) {
-      const __nv_bfloat162 h0 = __floats2bfloat162_rn(v[0], v[1]), h1 = __floats2bfloat162_rn(v[2], v[3]);
-      const float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
-      const __nv_bfloat162 l0 = __floats2bfloat162_rn(v[0] - f0.x, v[1] - f0.y), l1 = __floats2bfloat162_rn(v[2] - f1.x, v[3] - f1.y);
-      *reinterpret_cast<uint2*>(tok_hi + dst) = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
-      *reinterpret_cast<uint2*>(tok_lo + dst) = make_uint2(*reinterpret_cast<const uint32_t*>(&l0), *reinterpret_cast<const uint32_t*>(&l1));
+        for (int e = 0; e < 4; ++e) v[e] = simg[base + off[e]];
+        const long long dst = drow + static_cast<long long>(tx) * CKP;      // CKP: output row pitch (>= C*49)
+        if (tok) *reinterpret_cast<float4*>(tok + dst) = make_float4(v[0], v[1], v[2], v[3]);
+        if (tok_hi) {
+          const __nv_bfloat162 h0 = __floats2bfloat162_rn(v[0], v[1]), h1 = __floats2bfloat162_rn(v[2], v[3]);
+          const float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
+          const __nv_bfloat162 l0 = __floats2bfloat162_rn(v[0] - f0.x, v[1] - f0.y), l1 = __floats2bfloat162_rn(v[2] - f1.x, v[3] - f1.y);
+          *reinterpret_cast<uint2*>(tok_hi + dst) = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
+          *reinterpret_cast<uint2*>(tok_lo + dst) = make_uint2(*reinterpret_cast<const uint32_t*>(&l0), *reinterpret_cast<const uint32_t*>(&l1));
+        }
+      }
     }
   }
   // padded rows: the block of the last channel chunk zeroes columns [C*49, CKP) of its tokens (a following GEMM
