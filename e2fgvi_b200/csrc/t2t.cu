@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(256) t2t_unfold733_kernel(const float* __restr
 // OUT_NHWC (fold only): the image is written channels_last, [BT][H][W][C], with an optional residual of the same
 // layout added (enc_feat + trans_feat of e2fgvi.py:263 folded into the store) — the layout the decoder's convs read.
 template <bool FUSED, bool GELU, int CC, bool OUT_NHWC = false>
-__global__ void __launch_bounds__(256, 2) t2t_fold733_kernel(const float* __restrict__ tin, float* __restrict__ tok,
+__global__ void __launch_bounds__(256, 3) t2t_fold733_kernel(const float* __restrict__ tin, float* __restrict__ tok,
                                                           __nv_bfloat16* __restrict__ tok_hi,
                                                           __nv_bfloat16* __restrict__ tok_lo, float* __restrict__ img,
                                                           const float* __restrict__ bias, int normalize, int C, int H,
@@ -165,6 +165,7 @@ __global__ void __launch_bounds__(256, 2) t2t_fold733_kernel(const float* __rest
   constexpr int RUN4 = CC * 49 / 4;
   const int WP = W + 6, ROWS = FUSED ? 3 * TR + 4 : 3 * TR;
   int* nxtab = reinterpret_cast<int*>(simg + CC * ROWS * WP);
+  float* rnx = reinterpret_cast<float*>(nxtab + WP);                 // 1 / nxtab (0 outside the image)
   const int c0 = blockIdx.x * CC, band = blockIdx.y;
   const long long bt = blockIdx.z;
   const int ty0 = band * TR;                       // FUSED: first token row of the band
@@ -176,7 +177,9 @@ __global__ void __launch_bounds__(256, 2) t2t_fold733_kernel(const float* __rest
     for (int i = threadIdx.x; i < CC * ROWS * WP / 4; i += blockDim.x) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int xx = threadIdx.x; xx < WP; xx += blockDim.x) {
       const int x = xx - 3;                        // #token columns covering x: tx in [ceil((x-3)/3), floor((x+3)/3)]
-      nxtab[xx] = (x >= 0 && x < W) ? min(FW - 1, (x + 3) / 3) - max(0, (x - 1) / 3) + 1 : 0;
+      const int nx = (x >= 0 && x < W) ? min(FW - 1, (x + 3) / 3) - max(0, (x - 1) / 3) + 1 : 0;
+      nxtab[xx] = nx;
+      rnx[xx] = nx ? 1.0f / static_cast<float>(nx) : 0.f;
     }
   }
   // thread -> fixed float4 slot q4 of a token's CC*49 run, so the (channel, ky, kx) decode happens once per thread:
@@ -197,66 +200,89 @@ __global__ void __launch_bounds__(256, 2) t2t_fold733_kernel(const float* __rest
   const int tin_lo = FUSED ? max(0, ty0 - 2) : max(0, TR * band - 1);
   const int tin_hi = FUSED ? min(FH - 1, ty0 + tr + 1) : min(FH - 1, TR * band + TR);
   const float* src = tin + bt * FH * FW * static_cast<long long>(CK) + c0 * 49;
-  // Row-structured walk (round 2): the token row (uniform over the block) is the outer loop, each thread takes the
-  // tokens tsub, tsub + TSUB, ... of the row's phase columns.  Source pointer and shared-memory base advance by constants,
-  // the "patch entirely inside the band" test is per ROW, and the read-modify-writes of up to 4 tokens are issued as
-  // loads-then-stores (disjoint patches within a phase).  ncu of the first version: 64 thread instructions per folded
-  // float4, most of them per-token index / predicate arithmetic; this loop needs ~17.
-  const float* src_q = src + q4 * 4;
+  // Row-structured walk (round 2).  ncu of the first version: 64-95 thread instructions per folded float4, almost all of
+  // them per-token index / 64-bit address / predicate arithmetic.  Here a thread owns the tokens tsub, tsub + TSUB,
+  // tsub + 2 TSUB (U = 3 slots; more segments only for images wider than 45 tokens) of every token row of the phase and
+  // walks DOWN the rows: the global pointer and the four shared-memory pointers (one per element of its float4) advance
+  // by constants, slot offsets are immediates, slot liveness is per phase and the "patches entirely inside the band"
+  // test per row.  A row's read-modify-writes are issued as loads-then-stores (patches of a phase are disjoint), and
+  // the NEXT row's global loads are in flight while the current row is folded (register double buffer).
+  constexpr int U = 3;
+  const long long gslot = 3ll * TSUB * CK, grow = 3ll * FW * CK;     // floats between slots / phase rows
+  const int srow = 9 * WP;                                           // floats between phase rows in the band image
   for (int phase = 0; phase < 9; ++phase) {
     const int a = phase / 3, b = phase - 3 * a;
     const int first_ty = tin_lo + (a - tin_lo % 3 + 3) % 3;
     const int ntx = b < FW ? (FW - 1 - b) / 3 + 1 : 0;
-    if (active) {
-      for (int ty = first_ty; ty <= tin_hi; ty += 3) {
-        const int r0 = 3 * ty - 3 - ybase;                    // smem row of the patches' first row (may lie outside the band)
-        const bool whole = r0 >= 0 && r0 + 7 <= ROWS;
-        const float* rsrc = src_q + static_cast<long long>(ty * FW + b) * CK;
-        const int rbase = r0 * WP + 3 * b;
-        for (int t0 = tsub; t0 < ntx; t0 += 4 * TSUB) {
-          float4 v4[4];
-          bool live[4];
+    const int nrows = first_ty <= tin_hi ? (tin_hi - first_ty) / 3 + 1 : 0;
+    for (int ts = tsub; active && ts < ntx && nrows > 0; ts += U * TSUB) {
+      const bool live1 = ts + TSUB < ntx, live2 = ts + 2 * TSUB < ntx;
+      const float* g = src + (static_cast<long long>(first_ty) * FW + b + 3 * ts) * CK + q4 * 4;
+      int r0 = 3 * first_ty - 3 - ybase;                    // smem row of the patches' first row (may lie outside the band)
+      float* se[4];
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int txi = t0 + u * TSUB;
-            live[u] = txi < ntx;
-            if (live[u]) v4[u] = __ldg(reinterpret_cast<const float4*>(rsrc + static_cast<long long>(3 * txi) * CK));
+      for (int e = 0; e < 4; ++e) se[e] = simg + (r0 * WP + 3 * b + 9 * ts + off[e]);
+      auto load = [&](float4 (&v)[U], const float* gp) {
+        v[0] = __ldg(reinterpret_cast<const float4*>(gp));
+        if (live1) v[1] = __ldg(reinterpret_cast<const float4*>(gp + gslot));
+        if (live2) v[2] = __ldg(reinterpret_cast<const float4*>(gp + 2 * gslot));
+      };
+      auto foldrow = [&](const float4 (&v)[U]) {
+        if (r0 >= 0 && r0 + 7 <= ROWS) {                    // no per-element row checks
+          float c0v[4], c1v[4], c2v[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) c0v[e] = se[e][0];
+          if (live1) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) c1v[e] = se[e][9 * TSUB];
           }
-          if (whole) {
-            float cur[4][4];
+          if (live2) {
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              if (live[u]) {
-                const int base = rbase + 9 * (t0 + u * TSUB);
+            for (int e = 0; e < 4; ++e) c2v[e] = se[e][18 * TSUB];
+          }
+          se[0][0] = c0v[0] + v[0].x; se[1][0] = c0v[1] + v[0].y; se[2][0] = c0v[2] + v[0].z; se[3][0] = c0v[3] + v[0].w;
+          if (live1) {
+            se[0][9 * TSUB] = c1v[0] + v[1].x; se[1][9 * TSUB] = c1v[1] + v[1].y;
+            se[2][9 * TSUB] = c1v[2] + v[1].z; se[3][9 * TSUB] = c1v[3] + v[1].w;
+          }
+          if (live2) {
+            se[0][18 * TSUB] = c2v[0] + v[2].x; se[1][18 * TSUB] = c2v[1] + v[2].y;
+            se[2][18 * TSUB] = c2v[2] + v[2].z; se[3][18 * TSUB] = c2v[3] + v[2].w;
+          }
+        } else {
 #pragma unroll
-                for (int e = 0; e < 4; ++e) cur[u][e] = simg[base + off[e]];
-              }
-            }
+          for (int u = 0; u < U; ++u) {
+            if (u == 0 || (u == 1 ? live1 : live2)) {
+              const float w[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              if (live[u]) {
-                const int base = rbase + 9 * (t0 + u * TSUB);
-                simg[base + off[0]] = cur[u][0] + v4[u].x;
-                simg[base + off[1]] = cur[u][1] + v4[u].y;
-                simg[base + off[2]] = cur[u][2] + v4[u].z;
-                simg[base + off[3]] = cur[u][3] + v4[u].w;
-              }
-            }
-          } else {
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              if (live[u]) {
-                const int base = rbase + 9 * (t0 + u * TSUB);
-                const float v[4] = {v4[u].x, v4[u].y, v4[u].z, v4[u].w};
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  const int r = r0 + kyv[e];
-                  if (r >= 0 && r < ROWS) simg[base + off[e]] += v[e];
-                }
+              for (int e = 0; e < 4; ++e) {
+                const int r = r0 + kyv[e];
+                if (r >= 0 && r < ROWS) se[e][9 * TSUB * u] += w[e];
               }
             }
           }
         }
+      };
+      auto next_row = [&]() {
+        g += grow;
+        r0 += 9;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) se[e] += srow;
+      };
+      float4 va[U], vb[U];
+      load(va, g);
+      for (int i = 0;;) {
+        const bool more1 = i + 1 < nrows;
+        if (more1) load(vb, g + grow);
+        foldrow(va);
+        if (!more1) break;
+        next_row();
+        const bool more2 = i + 2 < nrows;
+        if (more2) load(va, g + grow);
+        foldrow(vb);
+        if (!more2) break;
+        next_row();
+        i += 2;
       }
     }
     __syncthreads();
@@ -294,8 +320,11 @@ __global__ void __launch_bounds__(256, 2) t2t_fold733_kernel(const float* __rest
     }
     return;
   }
-  for (int rr = warp; rr < CC * ROWS; rr += 8) {
-    const int cc = rr / ROWS, r = rr - cc * ROWS;
+  for (int rr = warp, cc = 0, r = warp; rr < CC * ROWS; rr += 8, r += 8) {
+    while (r >= ROWS) {
+      r -= ROWS;
+      ++cc;
+    }
     const int y = ybase + r;
     float* row = simg + rr * WP;
     if (y < 0 || y >= H) {
@@ -305,13 +334,12 @@ __global__ void __launch_bounds__(256, 2) t2t_fold733_kernel(const float* __rest
     }
     const int ny = min(FH - 1, (y + 3) / 3) - max(0, (y - 1) / 3) + 1;     // ty in [ceil((y-3)/3), floor((y+3)/3)]
     if (FUSED) {
+      // x (1/ny)(1/nx) instead of / (ny nx): <= 1.5 ulp from the reference's fp32 division, no IEEE-division sequence and
+      // no branch (columns outside the image hold finite partial sums and get the factor 0; GELU(0) = 0)
+      const float rny = 1.0f / static_cast<float>(ny);
       for (int xx = lane; xx < WP; xx += 32) {
-        const int nx = nxtab[xx];
-        float v = 0.f;
-        if (nx) {
-          v = row[xx] / static_cast<float>(ny * nx);
-          if (GELU) v = gelu_exact(v);
-        }
+        float v = row[xx] * (rny * rnx[xx]);
+        if (GELU) v = gelu_exact(v);
         row[xx] = v;
       }
     } else {
@@ -329,15 +357,20 @@ __global__ void __launch_bounds__(256, 2) t2t_fold733_kernel(const float* __rest
   __syncthreads();
   const long long tok0 = (bt * FH + ty0) * static_cast<long long>(FW);
   if (active) {
+    // thread = (float4 slot q4, token column tsub + k TSUB); pointers advance by constants (see the fold loop)
+    const long long dstep = static_cast<long long>(TSUB) * CKP;          // CKP: output row pitch (>= C*49)
     for (int iy = 0; iy < tr; ++iy) {
-      const int rb = 3 * iy * WP;
-      const long long drow = (tok0 + static_cast<long long>(iy) * FW) * CKP + c0 * 49 + q4 * 4;
-      for (int tx = tsub; tx < FW; tx += TSUB) {
-        const int base = rb + 3 * tx;
+      const float* pe[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) pe[e] = simg + (3 * iy * WP + 3 * tsub + off[e]);
+      long long dst = (tok0 + static_cast<long long>(iy) * FW + tsub) * CKP + c0 * 49 + q4 * 4;
+      for (int tx = tsub; tx < FW; tx += TSUB, dst += dstep) {
         float v[4];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) v[e] = simg[base + off[e]];
-        const long long dst = drow + static_cast<long long>(tx) * CKP;      // CKP: output row pitch (>= C*49)
+        for (int e = 0; e < 4; ++e) {
+          v[e] = *pe[e];
+          pe[e] += 3 * TSUB;
+        }
         if (tok) *reinterpret_cast<float4*>(tok + dst) = make_float4(v[0], v[1], v[2], v[3]);
         if (tok_hi) {
           const __nv_bfloat162 h0 = __floats2bfloat162_rn(v[0], v[1]), h1 = __floats2bfloat162_rn(v[2], v[3]);
@@ -631,8 +664,8 @@ __global__ void __launch_bounds__(256, 2) t2t_ffn_mid_kernel(const float* __rest
 
 // Band height (in token rows) of t2t_fold733_kernel and its dynamic shared memory: the tallest band that keeps 3 blocks
 // per SM; wide images (few rows fit) take up to 200 KB instead.  rows(tr) = 3*tr + extra image rows.  0 = does not fit.
-static int fold733_band(int w, int fh, int extra_rows, size_t* smem, int CC = 4) {
-  const size_t row_bytes = static_cast<size_t>(CC) * (w + 6) * sizeof(float), tab = (w + 6) * sizeof(int);
+static int fold733_band(int w, int fh, int extra_rows, size_t* smem, int CC = 4, long long blocks_per_band = 0) {
+  const size_t row_bytes = static_cast<size_t>(CC) * (w + 6) * sizeof(float), tab = 2 * (w + 6) * sizeof(int);   // nxtab + rnx
   auto band_rows = [&](size_t budget) {
     const long long rows = static_cast<long long>((budget - tab) / row_bytes) - extra_rows;
     return rows < 3 ? 0 : static_cast<int>(rows / 3);
@@ -641,7 +674,10 @@ static int fold733_band(int w, int fh, int extra_rows, size_t* smem, int CC = 4)
   if (tr < 5 && tr < fh) tr = band_rows(200 * 1024);
   if (tr < 1) return 0;
   tr = tr < fh ? tr : fh;
-  const int bands = (fh + tr - 1) / tr;
+  int bands = (fh + tr - 1) / tr;
+  // few images (one clip per call): a band is walked serially by one block, so shorter bands until every SM holds two
+  // blocks (the extra halo re-reads are L2 hits): 66 -> ~40 us per launch at one clip
+  while (blocks_per_band > 0 && bands * blocks_per_band < 2ll * num_sms() && (fh + bands - 1) / bands > 4) ++bands;
   tr = (fh + bands - 1) / bands;                   // even out the bands
   *smem = row_bytes * (3 * tr + extra_rows) + tab;
   return tr;
@@ -655,6 +691,9 @@ static void fold733_configure() {
   cudaFuncSetAttribute(t2t_fold733_kernel<true, false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   cudaFuncSetAttribute(t2t_fold733_kernel<false, false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   cudaFuncSetAttribute(t2t_fold733_kernel<false, false, 8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  // three ~63 KB bands per SM need the large shared-memory carve-out (ncu: the default left room for two)
+  cudaFuncSetAttribute(t2t_fold733_kernel<true, true, 4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  cudaFuncSetAttribute(t2t_fold733_kernel<true, false, 4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   device_mark(cfg, dev);
 }
 
@@ -666,7 +705,7 @@ static int launch_fold733_fullwidth(const float* tin, float* tok, void* tok_hi, 
                                     int fh, int fw, int gelu, int out_pitch, cudaStream_t stream) {
   constexpr int CC = 4;
   size_t smem = 0;
-  const int tr = fold733_band(w, fh, 4, &smem);
+  const int tr = fold733_band(w, fh, 4, &smem, CC, static_cast<long long>(c / CC) * bt);
   if (tr < 1) return -2;
   auto* hi = static_cast<__nv_bfloat16*>(tok_hi);
   auto* lo = static_cast<__nv_bfloat16*>(tok_lo);

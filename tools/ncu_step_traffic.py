@@ -3,7 +3,7 @@
         --clock-control none --profile-from-start off --csv --log-file <csv> python tools/profile_step.py
 capture: every launch of the step is measured (not a sample of a few launches), so `traffic` in bench.py's roofline
 block is the mean over exactly the launches whose live duration `achieved` averages.  Writes profiles/ncu_traffic.json
-(bytes per launch; the HALO conv variant is folded into conv3x3_kernel, the name bench.py reports) and prints a table.
+(bytes per launch; the HALO and kx-in-N conv variants are folded into conv3x3_kernel, the name bench.py reports) and prints a table.
     python tools/ncu_step_traffic.py <csv> [<out.txt>] [<workload key of profiles/ncu_traffic.json, default base>]"""
 import collections
 import csv
@@ -49,6 +49,11 @@ for name, (n, us, b, tp) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         traffic[name] = b / n
     out.append(f"{name[:34]:34s} launches={n:4d} total={us / 1e3:8.3f} ms ({100 * us / tot:4.1f}%) dram={b / n / 1e6:9.2f} MB/launch "
                f"({b / max(us, 1e-9) / 1e3:7.1f} GB/s) tensor-pipe active={tp / max(us, 1e-9):5.1f}%")
+# bench.py times the conv kernels (tap-table / halo / kx-in-N) under ONE op kind: its traffic entry is the mean over all
+# of them; the table above keeps the kx-in-N kernel on its own line
+if "conv_kxn_kernel" in agg and "conv3x3_kernel" in agg:
+    a, k = agg["conv3x3_kernel"], agg["conv_kxn_kernel"]
+    traffic["conv3x3_kernel"] = (a[2] + k[2]) / (a[0] + k[0])
 print("\n".join(out))
 if len(sys.argv) > 2:
     open(sys.argv[2], "w").write("\n".join(out) + "\n")
