@@ -250,6 +250,7 @@ class Measurement:
         self.num_clips = B * world
         self.stitch = C.ClipStitcher(self.num_clips, self.T, rank, world)
         self._copy_streams = None
+        self._dev_in = None
 
     def sync(self):
         if self.world > 1:
@@ -270,12 +271,20 @@ class Measurement:
             self._copy_streams = (torch.cuda.Stream(device=self.dev), torch.cuda.Stream(device=self.dev))
         h2d, d2h = self._copy_streams if to_host else (None, None)
 
+        if to_host and self._dev_in is None:                # two device input buffers, refilled in place (no allocation
+            self._dev_in = [torch.empty_like(inputs[0], device=self.dev) for _ in range(2)]   # inside the timed loop)
+        consumed = [None, None]                             # event: the forward that read buffer j has been enqueued on `main`
+        landed = []                                         # events: result of step i is on the host
+
         def upload(i):
+            j = i % 2
             with torch.cuda.stream(h2d):
-                x = inputs[i % self.n_sets].to(self.dev, non_blocking=True)
+                if consumed[j] is not None:
+                    h2d.wait_event(consumed[j])             # step i-2 has read this buffer
+                self._dev_in[j].copy_(inputs[i % self.n_sets], non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(h2d)
-            return x, ev
+            return self._dev_in[j], ev
 
         def download(t):
             """device tensor produced on `main` -> pinned host, on the D2H stream"""
@@ -284,17 +293,27 @@ class Measurement:
             with torch.cuda.stream(d2h):
                 d2h.wait_event(ev)
                 self.out_host.copy_(t, non_blocking=True)
+                done = torch.cuda.Event()
+                done.record(d2h)
             t.record_stream(d2h)
+            landed.append(done)
 
         nxt_in = upload(0) if to_host and n > 0 else None
         for i in range(n):
             if to_host:
                 x, ev = nxt_in
                 main.wait_event(ev)
-                x.record_stream(main)
+                if len(landed) > 2:
+                    # bounded queue depth, as a real caller would run it: the host never runs more than three results ahead
+                    # (the device still has two steps queued, so this wait costs no device time; without it the caching
+                    # allocator keeps growing the pool of in-flight 80 MB results and cudaMalloc synchronises the device)
+                    landed[len(landed) - 3].synchronize()
             else:
                 x = inputs[i % self.n_sets]
             pred, _ = self.model(x, self.l_t)
+            if to_host:
+                consumed[i % 2] = torch.cuda.Event()
+                consumed[i % 2].record(main)
             if to_host and i + 1 < n:
                 nxt_in = upload(i + 1)                    # overlaps this step's forward
             if to_host and self.world > 1:

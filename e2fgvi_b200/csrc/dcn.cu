@@ -18,6 +18,14 @@
 namespace e2f {
 namespace dcn {
 
+// 256-bit read-only load (sm_100+, PTX 8.8): the 16 fp16 channels of one (pixel, deform group) are 32 contiguous, 32-byte
+// aligned bytes in both input layouts.  The sampler is bound by L1 tag look-ups (ncu: l1tex 86 %), one per thread and request.
+__device__ __forceinline__ void ldg256(const uint4* p, uint4& a, uint4& b) {
+  asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
+               : "l"(p));
+}
+
 constexpr int CIN = 256, COUT = 128, DG = 16, CPG = CIN / DG, TAPS = 9;
 constexpr int KTOT = CIN * TAPS;             // 2304
 constexpr int NSP = DG * TAPS;               // 144 sample points per output pixel
@@ -141,8 +149,7 @@ dcn_kernel(const __grid_constant__ CUtensorMap tmap_w, const __half* __restrict_
           wgt[k] = in ? (dy ? ly : 1.f - ly) * (dx ? lx : 1.f - lx) * mk : 0.f;
           const int po = min(max(yy, 0), H - 1) * W + min(max(xx, 0), W - 1);
           const uint4* p = reinterpret_cast<const uint4*>(xg + static_cast<long long>(po) * PIX_STRIDE);
-          lo[k] = __ldg(p);
-          hi[k] = __ldg(p + 1);
+          ldg256(p, lo[k], hi[k]);        // one 32-byte request per corner (LDG.E.256): half the L1 tag look-ups of 2 x LDG.128
         }
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
