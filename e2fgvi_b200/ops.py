@@ -326,7 +326,8 @@ def t2t_unfold(img, kernel_size, stride, padding, gelu=False, out="f32"):
     bt, c, h, w = img.shape
     # channels_last storage (conv / linear epilogues write it) is read in place by the staged 7/3/3 kernel
     nhwc = ((k, s, p) == (7, 3, 3) and c % 8 == 0 and img.dtype == torch.float32 and not img.is_contiguous()
-            and img.permute(0, 2, 3, 1).is_contiguous() and bt <= 65535)
+            and img.permute(0, 2, 3, 1).is_contiguous() and bt <= 65535
+            and 8 * 7 * (w + 6) * 4 <= 200 * 1024)      # the staged kernel's shared-memory row buffer (t2t.cu: U2_CC rows)
     if not nhwc:
         img = img.contiguous().float()
     fh, fw = (h + 2 * p - k) // s + 1, (w + 2 * p - k) // s + 1
@@ -513,7 +514,9 @@ def t2t_fold(tokens, output_size, kernel_size, stride, padding, normalize=False,
         bias = bias.detach().contiguous().float()
     if residual is not None and tuple(residual.shape) != (bt, c, h, w):
         raise ValueError(f"residual {tuple(residual.shape)} != {(bt, c, h, w)}")
-    if channels_last and (k, s, p) == (7, 3, 3) and c % 8 == 0 and bt <= 65535:
+    # the shared-memory fold needs a band of >= 3 image rows x 8 channels (+ two count tables) in 200 KB (t2t.cu)
+    band_fits = (8 * 3 * 4 + 8) * (w + 6) <= 200 * 1024
+    if channels_last and (k, s, p) == (7, 3, 3) and c % 8 == 0 and bt <= 65535 and band_fits:
         res = None if residual is None else residual.permute(0, 2, 3, 1).contiguous().float()   # no-op if channels_last
         img = torch.empty((bt, h, w, c), dtype=torch.float32, device=tokens.device)
         with _timed("t2t_fold", float(tokens.numel() * 4 + img.numel() * (8 if res is not None else 4))):
