@@ -248,7 +248,7 @@ class Measurement:
         self.dev_sets = [h.to(dev) for h in self.host_sets]
         self.out_host = torch.empty((B * self.T, 3, self.H, self.W), dtype=torch.float32).pin_memory()
         self.num_clips = B * world
-        self.stitch = C.ClipStitcher(self.num_clips, self.T, rank, world)
+        self.stitch = C.make_stitcher(self.num_clips, self.T, rank, world, device=self.dev)   # peer-memory pushes on one NVLink box
         self._copy_streams = None
         self._dev_in = None
 
@@ -257,7 +257,7 @@ class Measurement:
             torch.distributed.barrier()
         torch.cuda.synchronize()
 
-    def _loop(self, n, inputs, to_host=False):
+    def _loop(self, n, inputs, to_host=False, stitch=True):
         """n steps; the stitch of step i overlaps the forward of step i+1 (double-buffered landing zone).
 
         ``to_host``: the end-to-end pipeline a caller of the public API runs — every step's inputs come from PINNED HOST
@@ -318,7 +318,7 @@ class Measurement:
                 nxt_in = upload(i + 1)                    # overlaps this step's forward
             if to_host and self.world > 1:
                 main.wait_stream(d2h)                     # the landing buffer about to be reused has been read out
-            nxt = self.stitch.start(pred) if self.world > 1 else None
+            nxt = self.stitch.start(pred) if (self.world > 1 and stitch) else None
             if pending is not None:
                 got = pending.wait()
                 if to_host:
@@ -350,6 +350,17 @@ class Measurement:
             res["launches"] = ops.launch_count() - n0
             res["clocks"] = sampler.stop() if sampler else None
             ms = e0.elapsed_time(e1)
+            ms_free = ms
+            if self.world > 1:
+                # diagnosis of the scaling loss: the same steps WITHOUT the stitch — every rank runs free, so the max over
+                # ranks is the slowest GPU's own time (boards differ by a few % under the power cap) and the difference to
+                # the stitched loop is what the exchange itself costs
+                g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                g0.record()
+                self._loop(self.steps, self.dev_sets, stitch=False)
+                g1.record()
+                self.sync()
+                ms_free = g0.elapsed_time(g1)
             # ---- per-kernel live timing in a SEPARATE pass over the same steps: two CUDA events per launch cost host time
             #      that would distort a launch-bound workload (one clip per call) if it ran inside the region above
             prof, ms_prof = None, None
@@ -381,9 +392,16 @@ class Measurement:
             f1.record()
             self.sync()
             ms_e2e = f0.elapsed_time(f1)
-        t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=self.dev)
+        t = torch.tensor([ms, ms_e2e, ms_free], dtype=torch.float64, device=self.dev)
         if self.world > 1:
+            per_rank = [torch.zeros_like(t) for _ in range(self.world)]
+            torch.distributed.all_gather(per_rank, t)
             torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+            res["ranks"] = {"ms_per_step": [float(x[0]) / self.steps for x in per_rank],
+                            "ms_per_step_without_stitch": [float(x[2]) / self.steps for x in per_rank],
+                            "stitch_cost_ms_per_step": (float(t[0]) - float(t[2])) / self.steps,
+                            "note": "value uses the max over ranks of the stitched loop; without the stitch every rank runs "
+                                    "free, so its max is the slowest board's own time"}
         ms, ms_e2e = float(t[0]), float(t[1])
         frames = self.num_clips * self.T * self.steps
         nbytes = self.B * self.T * 3 * self.H * self.W * 4 * self.world
@@ -394,7 +412,9 @@ class Measurement:
         return res
 
     def free(self):
-        self.host_sets = self.dev_sets = self.out_host = None
+        self.host_sets = self.dev_sets = self.out_host = self._dev_in = None
+        if hasattr(self.stitch, "close"):
+            self.stitch.close()                  # peer-memory landing buffers are cudaMalloc'd outside torch's allocator
         torch.cuda.empty_cache()
 
 
@@ -486,6 +506,9 @@ def main():
     model, sd = get_model(module)
     log(f"rank {rank}/{world}: model ready, workload={name}, host cores={host_cores()}")
     head = Measurement(name, model, dev, rank, world, B, args.steps, args.warmup)
+    stitch_kind = ("none (one GPU)" if world == 1 else
+                   "peer-memory DMA pushes + stream-memop flags (clips.PeerStitcher)" if type(head.stitch).__name__ == "PeerStitcher"
+                   else "all_gather_into_tensor (clips.ClipStitcher)")
     main_res = head.run(sample_clocks=True)
     kernels = kernel_rooflines(main_res["prof"], main_res["ms_prof"], traffic_for(name)) if rank == 0 else {}
     one_clip = head.dev_sets[0][:1].clone()
@@ -566,7 +589,7 @@ def main():
             "fps_b1_cuda_graph": None if not b1 else b1.get("cuda_graph_value"),
             "latency_b1_cuda_graph_ms": None if not b1 else b1.get("cuda_graph_ms_per_step"),
             "speedup_vs_cpu_b1": None if not (b1 and cpu and "value" in b1) else b1["value"] / cpu["value"],
-            "workloads": extra, "video_driver": video,
+            "workloads": extra, "video_driver": video, "stitch": stitch_kind, "ranks": main_res.get("ranks"),
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -55,6 +55,13 @@ SIGNATURES = {
     "e2f_spynet_pyramid": (_i, [_fp, _fp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _fp, _fp, _vp]),
     "e2f_spynet_level_input": (_i, [_fp, _fp, _vp, _vp, _fp, _i, _i, _i, _i, _i, _vp]),
     "e2f_spynet_final": (_i, [_fp, _fp, _fp, _i, _i, _i, _i, _i, _i, _vp]),
+    "e2f_peer_alloc": (_i, [_c.c_size_t, _c.POINTER(_c.c_void_p), _c.c_char_p]),
+    "e2f_peer_open": (_i, [_c.c_char_p, _c.POINTER(_c.c_void_p)]),
+    "e2f_peer_close": (_i, [_vp]),
+    "e2f_peer_free": (_i, [_vp]),
+    "e2f_peer_copy": (_i, [_vp, _vp, _c.c_size_t, _vp]),
+    "e2f_peer_signal": (_i, [_vp, _c.c_uint, _vp]),
+    "e2f_peer_wait": (_i, [_vp, _c.c_uint, _vp]),
     "e2f_video_prepare_clip": (_i, [_vp, _vp, _vp, _fp, _i, _i, _i, _i, _i, _vp]),
     "e2f_video_compose": (_i, [_fp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "e2f_video_blend": (_i, [_vp, _vp, _vp, _fp, _i, _c.c_int64, _vp]),

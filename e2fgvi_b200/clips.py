@@ -9,7 +9,12 @@ Round 2 (VERDICT r01 "Multi-GPU"):
 * the stitch is asynchronous and double-buffered (``ClipStitcher``): the all-gather of step i runs on the
   communication stream while the forward of step i+1 computes;
 * the payload can be fp32 (exact, default), fp16, or the uint8 frames test.py actually keeps
-  (``((x + 1) / 2 * 255)`` truncated, test.py:168-169) — 2x / 4x fewer bytes over NVLink.
+  (``((x + 1) / 2 * 255)`` truncated, test.py:168-169) — 2x / 4x fewer bytes over NVLink;
+* on one NVLink / NVSwitch box the payload does not go through NCCL at all (``PeerStitcher``): every rank pushes its
+  block of frames into the peers' landing buffers (CUDA IPC peer memory) with copy-engine DMA on a side stream and
+  orders the pushes with flag words driven by stream memory operations.  An NCCL kernel holds SMs for as long as it runs
+  and the persistent one-CTA-per-SM kernels of the next forward cannot place all their CTAs meanwhile: measured
+  +1.1 ms per 34 ms step at 4 GPUs (weak scaling 0.969), growing with the bytes landed per rank.
 """
 import os
 
@@ -106,6 +111,169 @@ class ClipStitcher:
             buf = self._bufs[k] = torch.empty(shape, dtype=send.dtype, device=send.device)
         work = dist.all_gather_into_tensor(buf, send, async_op=True)
         return _Pending(work, buf, n_valid, send)
+
+
+class _PendingPeer:
+    """Handle of one in-flight peer-memory stitch (same contract as ``_Pending``)."""
+
+    def __init__(self, done, out, n_valid, keep):
+        self.done, self.out, self.n_valid, self.keep = done, out, n_valid, keep
+
+    def wait(self):
+        if self.done is not None:
+            torch.cuda.current_stream().wait_event(self.done)
+            self.done = None
+        self.keep = None
+        return self.out[: self.n_valid]
+
+
+class _DevicePtr:
+    """Minimal ``__cuda_array_interface__`` carrier: lets torch view a cudaMalloc'd landing buffer it does not own."""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+
+class PeerStitcher(ClipStitcher):
+    """The stitch as copy-engine pushes into the peers' landing buffers (csrc/peer.cu); same ``start`` / ``wait``
+    contract as ``ClipStitcher``.  Every rank owns two landing buffers and one block of 32-bit flag words
+    (``may_write[r]``, ``landed[r]`` per peer r), all exported through CUDA IPC.  Step i (buffer k = i & 1), on the
+    stitcher's side stream of rank me — DMA copies and stream memory operations only, no kernel, no SM:
+
+        wait(event: pred computed and the readers of my buffer k have finished)
+        for every peer p:  p.may_write[me] := i + 1          "you may overwrite my buffer k"
+        for every peer p:  wait my.may_write[p] >= i + 1;  copy my block -> p.buffer[k][slot me];  p.landed[me] := i + 1
+        copy my block -> my buffer k;  for every peer p: wait my.landed[p] >= i + 1
+
+    Counters only grow, so a fast rank can run at most one buffer ahead of a slow one and never overwrites unread data."""
+
+    def __init__(self, num_clips, frames_per_clip, rank, world, payload="fp32", group=None):
+        super().__init__(num_clips, frames_per_clip, rank, world, payload)
+        self.group = group
+        self._stream = None
+        self._local = [None, None, None]  # raw pointers: landing buffer 0, landing buffer 1, flag block
+        self._remote = None               # [r] -> (buffer 0, buffer 1, flag block) of rank r as mapped here
+        self._shape = None
+
+    # ---- one-time (per payload shape) collective setup: allocate, exchange IPC handles, map the peers' buffers
+    def _setup(self, send):
+        import ctypes
+
+        from . import _lib
+        lib = _lib.load()
+        self.close()
+        dev = send.device
+        nbytes = self.world * send.numel() * send.element_size()
+        shape = (self.world * send.shape[0],) + tuple(send.shape[1:])
+        handles = []
+        for k, size in enumerate((nbytes, nbytes, 2 * 4 * self.world)):
+            ptr, h = ctypes.c_void_p(), ctypes.create_string_buffer(64)
+            _lib.check(lib.e2f_peer_alloc(size, ctypes.byref(ptr), h), "e2f_peer_alloc")
+            self._local[k] = ptr.value
+            if k < 2:
+                self._bufs[k] = torch.as_tensor(_DevicePtr(ptr.value, nbytes), device=dev).view(send.dtype).view(shape)
+            handles.append(bytes(h.raw))
+        everyone = [None] * self.world
+        dist.all_gather_object(everyone, handles, group=self.group)
+        self._remote = []
+        for r in range(self.world):
+            if r == self.rank:
+                self._remote.append(tuple(self._local))
+                continue
+            ptrs = []
+            for k in range(3):
+                ptr = ctypes.c_void_p()
+                _lib.check(lib.e2f_peer_open(everyone[r][k], ctypes.byref(ptr)), "e2f_peer_open")
+                ptrs.append(ptr.value)
+            self._remote.append(tuple(ptrs))
+        self._shape, self._dtype, self._device = shape, send.dtype, dev
+        self._n = 0                                          # flag words were zeroed with the allocation
+        if self._stream is None:
+            self._stream = torch.cuda.Stream(device=dev)
+        dist.barrier(group=self.group)                       # every rank has mapped every buffer before the first push
+
+    def close(self):
+        """Unmap the peers' buffers and free the local ones (collective: every rank must call it, or none)."""
+        if self._shape is None:
+            return
+        from . import _lib
+        lib = _lib.load()
+        torch.cuda.synchronize(self._device)
+        dist.barrier(group=self.group)                      # no rank is still pushing into buffers about to go away
+        for r, ptrs in enumerate(self._remote):
+            if r != self.rank:
+                for ptr in ptrs:
+                    lib.e2f_peer_close(ptr)
+        dist.barrier(group=self.group)                      # nobody frees memory a peer still has mapped
+        for k in range(3):
+            lib.e2f_peer_free(self._local[k])
+            self._local[k] = None
+        self._bufs = [None, None]
+        self._remote = None
+        self._shape = None
+
+    def start(self, local_pred):
+        from . import _lib
+        n_valid = self.num_clips * self.T
+        send = encode_payload(local_pred, self.payload)
+        if self.world == 1:
+            return _Pending(None, send, n_valid, None)
+        if send.shape[0] != self.share * self.T:
+            raise ValueError(f"local_pred has {send.shape[0]} frames, expected share*T = {self.share * self.T}")
+        shape = (self.world * send.shape[0],) + tuple(send.shape[1:])
+        if self._shape != shape or self._dtype != send.dtype or self._device != send.device:
+            self._setup(send)
+        k = self._n & 1
+        self._n += 1
+        seq = self._n & 0xFFFFFFFF                           # i + 1
+        lib, me, W = _lib.load(), self.rank, self.world
+        nbytes = send.numel() * send.element_size()
+        ready = torch.cuda.Event()
+        ready.record()                                      # pred computed; the readers of buffer k were enqueued before
+        side = self._stream
+        st = side.cuda_stream
+        peers = [(me + 1 + j) % W for j in range(W - 1)]    # every rank starts at a different destination
+        may_write = lambda owner, writer: self._remote[owner][2] + 4 * writer            # noqa: E731
+        landed = lambda owner, writer: self._remote[owner][2] + 4 * (W + writer)         # noqa: E731
+        with torch.cuda.stream(side):
+            side.wait_event(ready)
+            for p in peers:
+                _lib.check(lib.e2f_peer_signal(may_write(p, me), seq, st), "e2f_peer_signal")
+            for p in peers:
+                _lib.check(lib.e2f_peer_wait(may_write(me, p), seq, st), "e2f_peer_wait")
+                _lib.check(lib.e2f_peer_copy(self._remote[p][k] + me * nbytes, send.data_ptr(), nbytes, st), "e2f_peer_copy")
+                _lib.check(lib.e2f_peer_signal(landed(p, me), seq, st), "e2f_peer_signal")
+            _lib.check(lib.e2f_peer_copy(self._local[k] + me * nbytes, send.data_ptr(), nbytes, st), "e2f_peer_copy")
+            for p in peers:
+                _lib.check(lib.e2f_peer_wait(landed(me, p), seq, st), "e2f_peer_wait")
+            done = torch.cuda.Event()
+            done.record(side)
+        send.record_stream(side)
+        return _PendingPeer(done, self._bufs[k], n_valid, send)
+
+
+def peer_stitch_available(world, device=None):
+    """True when the stitch can use peer memory: CUDA, several ranks, all on this node with peer access to this device.
+    ``E2F_STITCH=nccl`` forces the NCCL all-gather (A/B measurements)."""
+    if os.environ.get("E2F_STITCH", "peer") == "nccl" or world <= 1 or not torch.cuda.is_available():
+        return False
+    if int(os.environ.get("LOCAL_WORLD_SIZE", str(world))) != world or torch.cuda.device_count() < world:
+        return False
+    dev = torch.cuda.current_device() if device is None else torch.device(device).index
+    return all(r == dev or torch.cuda.can_device_access_peer(dev, r) for r in range(world))
+
+
+def make_stitcher(num_clips, frames_per_clip, rank, world, payload="fp32", device=None):
+    """``PeerStitcher`` on one NVLink box, ``ClipStitcher`` (NCCL / gloo all-gather) otherwise.  The choice is made from
+    the same inputs on every rank (world size, visible devices, environment), so all ranks pick the same class."""
+    use_peer = peer_stitch_available(world, device)
+    if world > 1 and dist.is_initialized():
+        votes = [None] * world
+        dist.all_gather_object(votes, bool(use_peer))       # one rank without peer access -> everybody uses the all-gather
+        use_peer = all(votes)
+    if use_peer:
+        return PeerStitcher(num_clips, frames_per_clip, rank, world, payload)
+    return ClipStitcher(num_clips, frames_per_clip, rank, world, payload)
 
 
 def gather_outputs(local_pred, num_clips, frames_per_clip, rank, world, payload="fp32"):

@@ -15,6 +15,7 @@
 #ifndef E2FGVI_B200_H_
 #define E2FGVI_B200_H_
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -346,6 +347,26 @@ int e2f_spynet_level_input(const float* level_img, const float* prev_flow, void*
                            int b, int l_t, int hk, int wk, int lead, void* stream);
 int e2f_spynet_final(const float* flow, float* flows_forward, float* flows_backward, int b, int l_t, int h, int w, int h_up,
                      int w_up, void* stream);
+
+/* Output stitch over NVLink / NVSwitch peer memory (clips are the sharding unit, the only exchange is the
+ * all-gather of the output frames — the multi-GPU form of test.py:168-179 collecting every window's frames into one list).
+ * Each rank owns a landing buffer and PUSHES its block of frames into every peer's buffer with DMA copies (copy engines,
+ * no SMs: an NCCL all-gather kernel takes SMs from the persistent kernels of the next forward, csrc/peer.cu).
+ *   e2f_peer_alloc : cudaMalloc `bytes` (an IPC handle names a whole allocation, so no caching allocator) and export
+ *                    the 64-byte CUDA IPC handle other processes open.
+ *   e2f_peer_open  : map a peer's buffer into this process (lazily enables peer access); e2f_peer_close unmaps it.
+ *   e2f_peer_copy  : asynchronous device-to-device copy of one block on `stream` (local or peer destination).
+ *   e2f_peer_signal: 32-bit flag word (local or peer memory) := value, stream-ordered (cuStreamWriteValue32, no kernel).
+ *   e2f_peer_wait  : `stream` stalls until (int32)(*flag - value) >= 0 (cuStreamWaitValue32); flag in LOCAL memory.
+ * Protocol (e2fgvi_b200/clips.py, PeerStitcher): per step a rank tells every peer "my landing buffer k may be
+ * overwritten", waits for the same word from the peer, pushes its block, then raises the peer's "block landed" word. */
+int e2f_peer_alloc(size_t bytes, void** ptr, unsigned char* handle64);
+int e2f_peer_open(const unsigned char* handle64, void** ptr);
+int e2f_peer_close(void* ptr);
+int e2f_peer_free(void* ptr);
+int e2f_peer_copy(void* dst, const void* src, size_t bytes, void* stream);
+int e2f_peer_signal(void* flag, unsigned int value, void* stream);
+int e2f_peer_wait(void* flag, unsigned int value, void* stream);
 
 /* Video-level driver — replaces the per-window host / eager-torch code of test.py:132-179.
  * All buffers are device memory; `frames` [N][H][W][3] uint8 RGB, `masks` [N][H][W] uint8 (non-zero = hole, already

@@ -34,7 +34,8 @@ def _worker(rank, world, port, num_clips, q):
     ok = ok and out8.dtype == torch.uint8 and bool(torch.equal(out8, want8))
     # asynchronous double-buffered stitch: two stitches in flight, joined in order
     share, T = C.padded_share(num_clips, w), clips.shape[1]
-    st = C.ClipStitcher(num_clips, T, r, w)
+    st = C.make_stitcher(num_clips, T, r, w)              # no CUDA here: every rank must agree on the all-gather class
+    ok = ok and type(st) is C.ClipStitcher
     pend = []
     for k in range(3):
         mine = C.shard_clips(num_clips, r, w)
@@ -83,3 +84,60 @@ def test_shard_helpers():
     assert C.padded_share(5, 2) == 3 and C.padded_share(64, 8) == 8
     x = torch.arange(12.).view(12, 1, 1, 1)
     assert torch.equal(C.gather_outputs(x, 3, 4, 0, 1), x)
+
+
+# ---- GPU: the peer-memory stitch (csrc/peer.cu) between two PROCESSES sharing cuda:0 — CUDA IPC, DMA pushes and the
+# stream-memop flags are the real ones; only the process group (IPC-handle exchange, barriers) runs over gloo because
+# NCCL refuses two ranks on one device.  On a multi-GPU box `torchrun bench.py --gpus N` exercises the NVLink route.
+def _peer_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK="0")
+    from e2fgvi_b200 import clips as C
+    torch.cuda.set_device(0)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    dev = torch.device("cuda:0")
+    num_clips, T = 5, 4                                     # ragged: rank 1 pads its share
+    share = C.padded_share(num_clips, world)
+    g = torch.Generator().manual_seed(0)
+    clips = torch.randn(num_clips, T, 3, 20, 24, generator=g).to(dev)
+    want = lambda k: (clips + k).reshape(num_clips * T, 3, 20, 24)             # noqa: E731
+    ok = True
+    for payload in ("fp32", "uint8"):
+        st = C.PeerStitcher(num_clips, T, rank, world, payload)
+        pend = []
+        for k in range(5):                                  # both landing buffers reused twice
+            mine = C.shard_clips(num_clips, rank, world)
+            local = (clips[mine] + k).reshape(-1, 3, 20, 24)
+            if local.shape[0] < share * T:
+                local = torch.cat([local, local.new_zeros((share * T - local.shape[0],) + tuple(local.shape[1:]))])
+            if rank == 1 and k == 2:
+                torch.cuda._sleep(200_000_000)              # a slow rank: the fast one must not overwrite unread data
+            pend.append((k, st.start(local)))
+            if len(pend) == 2:
+                kk, h = pend.pop(0)
+                got = h.wait().clone()
+                ok = ok and bool(torch.equal(got, C.encode_payload(want(kk), payload)))
+        for kk, h in pend:
+            ok = ok and bool(torch.equal(h.wait().clone(), C.encode_payload(want(kk), payload)))
+        st.close()
+    q.put((rank, ok))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+import pytest  # noqa: E402
+
+
+@pytest.mark.gpu
+def test_peer_memory_stitch_two_processes_one_gpu():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_peer_worker, args=(r, 2, 29631, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(ok for _, ok in res)
