@@ -12,9 +12,10 @@ Round 2 (VERDICT r01 "Multi-GPU"):
   (``((x + 1) / 2 * 255)`` truncated, test.py:168-169) — 2x / 4x fewer bytes over NVLink;
 * on one NVLink / NVSwitch box the payload does not go through NCCL at all (``PeerStitcher``): every rank pushes its
   block of frames into the peers' landing buffers (CUDA IPC peer memory) with copy-engine DMA on a side stream and
-  orders the pushes with flag words driven by stream memory operations.  An NCCL kernel holds SMs for as long as it runs
-  and the persistent one-CTA-per-SM kernels of the next forward cannot place all their CTAs meanwhile: measured
-  +1.1 ms per 34 ms step at 4 GPUs (weak scaling 0.969), growing with the bytes landed per rank.
+  orders the pushes with flag words driven by stream memory operations — no kernel, no SM, so the persistent
+  one-CTA-per-SM kernels of the next forward keep the whole chip while the exchange runs.  Measured on 4 x B200
+  (profiles/r02/run22_*): the exchange costs ~0 ms per 35 ms step with either implementation (weak-scaling loss is the
+  slowest board under the power cap); the peer path is the default because it cannot compete for SMs as payloads grow.
 """
 import os
 
@@ -154,10 +155,14 @@ class PeerStitcher(ClipStitcher):
         self._local = [None, None, None]  # raw pointers: landing buffer 0, landing buffer 1, flag block
         self._remote = None               # [r] -> (buffer 0, buffer 1, flag block) of rank r as mapped here
         self._shape = None
+        self._fallback = None             # ClipStitcher, if the peer-memory set-up failed on any rank
 
-    # ---- one-time (per payload shape) collective setup: allocate, exchange IPC handles, map the peers' buffers
+    # ---- one-time (per payload shape) collective setup: allocate, exchange IPC handles, map the peers' buffers.
+    # Two votes (after allocating, after mapping): if ANY rank fails, every rank releases what it holds and the stitcher
+    # degrades to the all-gather of ``ClipStitcher`` for good — never a rank-dependent choice, never a hang.
     def _setup(self, send):
         import ctypes
+        import warnings
 
         from . import _lib
         lib = _lib.load()
@@ -165,27 +170,53 @@ class PeerStitcher(ClipStitcher):
         dev = send.device
         nbytes = self.world * send.numel() * send.element_size()
         shape = (self.world * send.shape[0],) + tuple(send.shape[1:])
-        handles = []
-        for k, size in enumerate((nbytes, nbytes, 2 * 4 * self.world)):
-            ptr, h = ctypes.c_void_p(), ctypes.create_string_buffer(64)
-            _lib.check(lib.e2f_peer_alloc(size, ctypes.byref(ptr), h), "e2f_peer_alloc")
-            self._local[k] = ptr.value
-            if k < 2:
-                self._bufs[k] = torch.as_tensor(_DevicePtr(ptr.value, nbytes), device=dev).view(send.dtype).view(shape)
-            handles.append(bytes(h.raw))
+        handles, err = [], None
+        try:
+            for k, size in enumerate((nbytes, nbytes, 2 * 4 * self.world)):
+                ptr, h = ctypes.c_void_p(), ctypes.create_string_buffer(64)
+                _lib.check(lib.e2f_peer_alloc(size, ctypes.byref(ptr), h), "e2f_peer_alloc")
+                self._local[k] = ptr.value
+                if k < 2:
+                    self._bufs[k] = torch.as_tensor(_DevicePtr(ptr.value, nbytes), device=dev).view(send.dtype).view(shape)
+                handles.append(bytes(h.raw))
+        except Exception as exc:  # noqa: BLE001 - any failure here is answered by the collective fallback below
+            err = repr(exc)
         everyone = [None] * self.world
-        dist.all_gather_object(everyone, handles, group=self.group)
-        self._remote = []
-        for r in range(self.world):
-            if r == self.rank:
-                self._remote.append(tuple(self._local))
-                continue
-            ptrs = []
+        dist.all_gather_object(everyone, (err, handles), group=self.group)
+        opened = []
+        if all(e is None for e, _ in everyone):
+            try:
+                self._remote = []
+                for r in range(self.world):
+                    if r == self.rank:
+                        self._remote.append(tuple(self._local))
+                        continue
+                    ptrs = []
+                    for k in range(3):
+                        ptr = ctypes.c_void_p()
+                        _lib.check(lib.e2f_peer_open(everyone[r][1][k], ctypes.byref(ptr)), "e2f_peer_open")
+                        ptrs.append(ptr.value)
+                        opened.append(ptr.value)
+                    self._remote.append(tuple(ptrs))
+            except Exception as exc:  # noqa: BLE001
+                err = repr(exc)
+        else:
+            err = err or "a peer failed to allocate its landing buffers"
+        votes = [None] * self.world
+        dist.all_gather_object(votes, err, group=self.group)
+        if any(v is not None for v in votes):
+            for ptr in opened:
+                lib.e2f_peer_close(ptr)
+            dist.barrier(group=self.group)                   # nobody frees memory a peer still has mapped
             for k in range(3):
-                ptr = ctypes.c_void_p()
-                _lib.check(lib.e2f_peer_open(everyone[r][k], ctypes.byref(ptr)), "e2f_peer_open")
-                ptrs.append(ptr.value)
-            self._remote.append(tuple(ptrs))
+                if self._local[k]:
+                    lib.e2f_peer_free(self._local[k])
+                self._local[k] = None
+            self._bufs, self._remote = [None, None], None
+            self._fallback = ClipStitcher(self.num_clips, self.T, self.rank, self.world, self.payload)
+            if self.rank == 0:
+                warnings.warn(f"PeerStitcher: peer-memory set-up failed ({[v for v in votes if v][0]}); using the all-gather")
+            return
         self._shape, self._dtype, self._device = shape, send.dtype, dev
         self._n = 0                                          # flag words were zeroed with the allocation
         if self._stream is None:
@@ -221,8 +252,10 @@ class PeerStitcher(ClipStitcher):
         if send.shape[0] != self.share * self.T:
             raise ValueError(f"local_pred has {send.shape[0]} frames, expected share*T = {self.share * self.T}")
         shape = (self.world * send.shape[0],) + tuple(send.shape[1:])
-        if self._shape != shape or self._dtype != send.dtype or self._device != send.device:
+        if self._fallback is None and (self._shape != shape or self._dtype != send.dtype or self._device != send.device):
             self._setup(send)
+        if self._fallback is not None:
+            return self._fallback.start(local_pred)
         k = self._n & 1
         self._n += 1
         seq = self._n & 0xFFFFFFFF                           # i + 1
