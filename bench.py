@@ -469,8 +469,8 @@ def video_driver_run(model, H, W):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--clips-per-gpu", type=int, default=None)
     ap.add_argument("--workload", default="base", choices=sorted(WORKLOADS))

@@ -218,7 +218,7 @@ int e2f_upsample2x_split(const float* x, void* out_hi, void* out_lo, int n, int 
   if (!x || !out_hi || !out_lo) { set_error("e2f_upsample2x_split: null pointer"); return E2F_ERR_BAD_ARG; }
   if (n < 0 || h <= 0 || w <= 0 || c <= 0) { set_error("e2f_upsample2x_split: bad shape"); return E2F_ERR_BAD_ARG; }
   if (c % 8) { set_error("e2f_upsample2x_split: C=%d must be a multiple of 8", c); return E2F_ERR_UNSUPPORTED; }
-  if (!aligned(x, 16) || !aligned(out_hi, 16) || !aligned(out_lo, 16)) { set_error("e2f_upsample2x_split: 16-byte alignment required"); return E2F_ERR_ALIGNMENT; }
+  if (!aligned(x, 32) || !aligned(out_hi, 16) || !aligned(out_lo, 16)) { set_error("e2f_upsample2x_split: x needs 32-byte, out_hi / out_lo 16-byte alignment"); return E2F_ERR_ALIGNMENT; }
   return finish(launch_upsample2x_split(x, out_hi, out_lo, n, h, w, c, static_cast<cudaStream_t>(stream)), "e2f_upsample2x_split");
 }
 

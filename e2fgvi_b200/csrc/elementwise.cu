@@ -23,6 +23,13 @@ __device__ __forceinline__ void split_store8(const float (&f)[8], __nv_bfloat16*
   *reinterpret_cast<uint4*>(lo) = make_uint4(lp[0], lp[1], lp[2], lp[3]);
 }
 
+// 256-bit read-only load of 8 consecutive, 32-byte aligned floats (sm_100+, PTX 8.8: LDG.E.256)
+__device__ __forceinline__ void ldg256_f32(const float4* p, float (&v)[8]) {
+  asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+               : "l"(p));
+}
+
 // one thread per (output pixel, 8 channels); source index arithmetic mirrors ATen's upsample_bilinear2d.
 // grid = (x blocks, output row, image): no 64-bit div / mod chain per thread (the first version decoded a flat 64-bit
 // index: ~45 % of its instructions, 3.1 TB/s)
@@ -45,15 +52,16 @@ __global__ void __launch_bounds__(256) upsample2x_split_kernel(const float* __re
   const float4* p01 = reinterpret_cast<const float4*>(base + (static_cast<long long>(y0) * W + x1) * C);
   const float4* p10 = reinterpret_cast<const float4*>(base + (static_cast<long long>(y1) * W + x0) * C);
   const float4* p11 = reinterpret_cast<const float4*>(base + (static_cast<long long>(y1) * W + x1) * C);
+  // one 256-bit request per corner (8 fp32 channels = 32 aligned bytes): ncu showed the kernel L1-bound (l1tex 94-96 %)
+  // with two LDG.128 per corner
+  float a[8], b[8], c[8], d[8];
+  ldg256_f32(p00, a);
+  ldg256_f32(p01, b);
+  ldg256_f32(p10, c);
+  ldg256_f32(p11, d);
   float f[8];
 #pragma unroll
-  for (int h = 0; h < 2; ++h) {
-    const float4 a = __ldg(p00 + h), b = __ldg(p01 + h), c = __ldg(p10 + h), d = __ldg(p11 + h);
-    f[4 * h + 0] = hy * (hx * a.x + lx * b.x) + ly * (hx * c.x + lx * d.x);
-    f[4 * h + 1] = hy * (hx * a.y + lx * b.y) + ly * (hx * c.y + lx * d.y);
-    f[4 * h + 2] = hy * (hx * a.z + lx * b.z) + ly * (hx * c.z + lx * d.z);
-    f[4 * h + 3] = hy * (hx * a.w + lx * b.w) + ly * (hx * c.w + lx * d.w);
-  }
+  for (int i = 0; i < 8; ++i) f[i] = hy * (hx * a[i] + lx * b[i]) + ly * (hx * c[i] + lx * d[i]);
   const long long o = pix * C + v * 8;
   split_store8(f, hi + o, lo + o);
 }

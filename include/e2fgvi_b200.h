@@ -168,7 +168,7 @@ int e2f_layernorm_pool_split(const float* x, const float* gamma, const float* be
 
 /* x2 bilinear upsample, align_corners=True (F.interpolate in deconv.forward, e2fgvi.py:125-129) of an NHWC fp32
  * tensor [N][H][W][C] (C % 8 == 0), written directly as the bf16 (hi, lo) split [N][2H][2W][C] consumed by
- * e2f_conv3x3_bf16x3 — the 4x larger fp32 intermediate is never materialised. */
+ * e2f_conv3x3_bf16x3 — the 4x larger fp32 intermediate is never materialised.  x must be 32-byte aligned (256-bit loads). */
 int e2f_upsample2x_split(const float* x, void* out_hi, void* out_lo, int n, int h, int w, int c, void* stream);
 
 /* nn.LayerNorm over the last dimension (tfocal_transformer.py:470 norm1, :533 norm2; C = 512):

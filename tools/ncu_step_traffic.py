@@ -41,7 +41,8 @@ for rec in per.values():
     a[2] += rec.get("dram__bytes_read.sum", 0.0) + rec.get("dram__bytes_write.sum", 0.0)
     a[3] += rec.get("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", 0.0) * us
 tot = sum(a[1] for a in agg.values())
-out = [f"# one step (8 clips 432x240 5+3), every launch measured; total {tot / 1e3:.2f} ms serialised over "
+wl = sys.argv[3] if len(sys.argv) > 3 else "base"
+out = [f"# one step of workload '{wl}' (base = 8 clips 432x240 5+3, b1 = one clip), every launch measured; total {tot / 1e3:.2f} ms serialised over "
        f"{sum(a[0] for a in agg.values())} launches"]
 traffic = {}
 for name, (n, us, b, tp) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
