@@ -26,12 +26,11 @@ _ENC = ((3, 64, 2, 1), (64, 64, 1, 1), (64, 128, 2, 1), (128, 256, 1, 1), (256, 
 
 @contextlib.contextmanager
 def library_precision(mode):
-    """Precision of the LIBRARY ops (cuDNN convs, cuBLAS linears) during forward.
-
-    "strict": TF32 disabled — full fp32 like the reference's CPU path; needed for the 1e-3 parity bar on O(1)
-              ("stress") activations, where TF32's 10-bit mantissa costs 3-5e-3 over ~60 layers (measured).
-    "tf32"  : TF32 tensor-core convs and matmuls (PyTorch's own default for convs on Ampere+).
-    The hand-written kernels (DCN, attention) always use fp16 operands with fp32 accumulation."""
+    """TF32 switch of torch's LIBRARY ops around forward.  No cuDNN / cuBLAS kernel is left on the path (every conv and
+    Linear runs on the bf16x3 tcgen05 kernels, DCN / attention on fp16 operands with fp32 accumulation), so this only
+    matters for library ops a caller wraps around the model; "strict" (default) keeps them at full fp32 like the
+    reference's CPU path — TF32 costs 3-7e-3 over ~60 layers on O(1) activations — "tf32" restores
+    PyTorch's own default."""
     if mode not in ("strict", "tf32"):
         raise ValueError("precision must be 'strict' or 'tf32'")
     old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
@@ -119,7 +118,9 @@ class deconv(nn.Module):
         self.conv = nn.Conv2d(input_channel, output_channel, kernel_size=kernel_size, stride=1, padding=padding)
 
     def forward(self, x):
-        return self.conv(F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=True))
+        """Stand-alone call (the generator's ``_decode`` fuses the following LeakyReLU and keeps the bf16 split between
+        layers): the same two kernels — x2 bilinear upsample written as the conv's split operand, then the conv."""
+        return ops.conv3x3([ops.upsample2x_split(x)], self.conv.weight, self.conv.bias)
 
 
 class InpaintGenerator(BaseNetwork):

@@ -219,17 +219,6 @@ class TemporalFocalTransformerBlock(nn.Module):
         self.norm2 = norm_layer(dim)
         self.mlp = FusionFeedForward(dim, n_vecs=n_vecs, t2t_params=t2t_params)
 
-    def _pool_windows(self, x):
-        """Linear(wh*ww -> 1) over each window's tokens, per channel (tfocal_transformer.py:508-516)."""
-        B, T, H, W, C = x.shape
-        wh, ww = self.window_size
-        if H % wh or W % ww:
-            raise ValueError(f"token grid {H}x{W} must be a multiple of the window {wh}x{ww}")
-        lin = self.pool_layers[0]
-        xw = x.view(B, T, H // wh, wh, W // ww, ww, C)
-        pooled = torch.einsum("bthrwqc,rq->bhwtc", xw, lin.weight.view(wh, ww).to(x.dtype))
-        return pooled + lin.bias.to(x.dtype)
-
     def _forward(self, x, output_size):
         shortcut = x
         B, T, H, W, C = x.shape
