@@ -50,6 +50,28 @@ def test_forward_matches_reference_golden(cuda, name):
         assert (got.cpu() - want).abs().max().item() < 2e-3 * max(1.0, want.abs().max().item())
 
 
+@pytest.mark.parametrize("hq,b,T,l_t,H,W", [(True, 1, 4, 4, 60, 108),      # no reference frames (get_ref_index returned [])
+                                            (True, 2, 3, 2, 60, 108),      # the shortest local window, two clips
+                                            (True, 1, 7, 6, 120, 216),     # l_t = 6: odd frame counts, T not a multiple of 4
+                                            (False, 1, 5, 5, 240, 432)])   # base model without reference frames
+def test_forward_edge_frame_counts_match_oracle(cuda, hq, b, T, l_t, H, W):
+    """Frame-count edge cases of test.py's window loop (short videos: ``get_ref_index`` returns no reference frames,
+    test.py:37-52; the first / last windows hold fewer neighbours) — the CUDA path against the CPU oracle on the same
+    seeded inputs (the oracle is pinned to the reference)."""
+    from oracle import restate
+    model = _model(hq, "stress", 5, cuda)
+    sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+    x = synth_frames(b, T, H, W, seed=9)
+    with torch.no_grad():
+        want, (wf, wb) = restate.inpaint_generator_forward(sd, x, l_t, hq=hq)
+        pred, (ff, fb) = model(x.to(cuda), l_t)
+    assert pred.shape == (b * T, 3, H, W) and ff.shape == (b, l_t - 1, 2, H // 4, W // 4)
+    err = (pred.cpu() - want).abs().max().item()
+    assert err < TOL, f"max abs err {err:.3e}"
+    for got, ref in ((ff, wf), (fb, wb)):
+        assert (got.cpu() - ref).abs().max().item() < 2e-3 * max(1.0, ref.abs().max().item())
+
+
 @pytest.mark.parametrize("shape", [(2, 4, 3, 120, 216), (1, 8, 5, 240, 432), (1, 3, 2, 128, 256)])
 def test_spynet_fused_glue_matches_oracle(cuda, shape):
     """SPyNet with its glue as three kernels (pyramid per frame, per-level upsample + border warp + cat as the conv

@@ -45,6 +45,25 @@ def test_host_logic_against_golden(name):
     assert (ff - g["flows_forward"]).abs().max() < 1e-3 and (fb - g["flows_backward"]).abs().max() < 1e-3
 
 
+@pytest.mark.parametrize("hq,b,T,l_t,H,W", [(True, 1, 4, 4, 60, 108), (True, 2, 3, 2, 60, 108)])
+def test_host_logic_edge_frame_counts(hq, b, T, l_t, H, W):
+    """No reference frames (T == l_t: ``get_ref_index`` returned [], test.py:37-52) and the shortest local window: the
+    model's host logic (buffer slicing, in-place propagation, flow indexing) against the oracle's restatement."""
+    from oracle import restate
+    net = importlib.import_module("model." + ("e2fgvi_hq" if hq else "e2fgvi"))
+    model = net.InpaintGenerator().eval()
+    sd = synth_state_dict(model, "stress", 5)
+    model.load_state_dict(sd, strict=True)
+    x = synth_frames(b, T, H, W, seed=9)
+    with torch.no_grad():
+        want, (wf, wb) = restate.inpaint_generator_forward(sd, x, l_t, hq=hq)
+        with oracle_ops():
+            pred, (ff, fb) = model(x, l_t)
+    assert pred.shape == (b * T, 3, H, W) and ff.shape == (b, l_t - 1, 2, H // 4, W // 4)
+    assert (pred - want).abs().max() < 5e-5
+    assert (ff - wf).abs().max() < 1e-3 and (fb - wb).abs().max() < 1e-3
+
+
 def test_reference_module_boundaries():
     """The inner operator boundaries keep the reference's call shapes."""
     from model.modules.tfocal_transformer import WindowAttention
