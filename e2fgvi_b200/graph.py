@@ -1,10 +1,12 @@
 """CUDA-graph replay of ``InpaintGenerator.forward`` for a fixed input shape.
 
-A single 432x240 5+3 clip is launch-bound (~900 kernel launches for ~7 ms of GPU work), so the whole forward —
-torch glue ops and the C-ABI kernels alike, all issued on the capture stream — is recorded once and replayed.
+A single 432x240 5+3 clip is launch-bound from Python (~195 kernel launches for ~5.5 ms of GPU work), so the whole
+forward — the C-ABI kernels and the one memset, all issued on the capture stream — is recorded once and replayed.
 Weights must not change between capture and replay (inference); inputs are copied into a static buffer.
 """
 import torch
+
+from . import ops
 
 
 class GraphedGenerator:
@@ -24,8 +26,10 @@ class GraphedGenerator:
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
+        n0 = ops.launch_count()
         with torch.no_grad(), torch.cuda.graph(self.graph):
             self.static_out, self.static_flows = self._eager(self.static_in, num_local_frames)
+        self.kernel_launches = ops.launch_count() - n0      # kernels of this library recorded in the graph
 
     @torch.no_grad()
     def __call__(self, masked_frames, num_local_frames=None):
@@ -35,4 +39,5 @@ class GraphedGenerator:
             raise ValueError(f"captured for shape {tuple(self.static_in.shape)}, got {tuple(masked_frames.shape)}")
         self.static_in.copy_(masked_frames, non_blocking=True)
         self.graph.replay()
+        ops.note_graph_replay(self.kernel_launches)
         return self.static_out, self.static_flows

@@ -1288,5 +1288,16 @@ def invalidate_weight_caches():
     _DERIVED.clear()
 
 
+_GRAPH_REPLAY_LAUNCHES = 0
+
+
+def note_graph_replay(kernel_launches):
+    """A CUDA-graph replay relaunches the kernels recorded at capture time without passing through the C ABI's launch
+    functions; ``e2fgvi_b200.graph`` reports them here so that ``launch_count`` keeps counting kernels, not host calls."""
+    global _GRAPH_REPLAY_LAUNCHES
+    _GRAPH_REPLAY_LAUNCHES += int(kernel_launches)
+
+
 def launch_count():
-    return int(_lib.load().e2f_launch_count())
+    """Kernels of this library launched so far: host-side launches (``e2f_launch_count``) + kernels replayed by graphs."""
+    return int(_lib.load().e2f_launch_count()) + _GRAPH_REPLAY_LAUNCHES

@@ -174,7 +174,13 @@ def test_cuda_graph_replay_matches_eager(cuda):
     x1 = synth_frames(1, 4, 120, 216, seed=5).to(cuda)
     x2 = synth_frames(1, 4, 120, 216, seed=6).to(cuda)
     g = GraphedGenerator(model, x1, 3)
+    from e2fgvi_b200 import ops
     with torch.no_grad():
+        n0 = ops.launch_count()
         want, _ = model(x2, 3)
+        eager_launches = ops.launch_count() - n0
+    n1 = ops.launch_count()
     got, _ = g(x2)
     assert torch.equal(got, want)          # same kernels, same order: bit-identical
+    # a replay relaunches exactly the kernels an eager forward launches, and launch_count keeps counting them
+    assert g.kernel_launches == eager_launches > 100 and ops.launch_count() - n1 == eager_launches
