@@ -12,6 +12,7 @@ process: ``workloads.b1`` (configs[1]: ONE 432x240 5+3 clip per call, eager and 
 """
 import argparse
 import importlib
+import datetime
 import json
 import math
 import os
@@ -63,12 +64,19 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md).
+
+    The process is started BEFORE the warm-up steps: nvidia-smi needs 0.1-0.5 s to attach to the driver and, while it
+    does, kernel launches of this process stall behind it — started right in front of the timed region (as this file
+    did until run 27 of round 2) that cost landed inside the measurement: 36.6-38.0 ms per step in the device-resident
+    loop against 34.2-34.9 ms in the end-to-end loop two seconds later, with only 1-3 samples returned.  Every line
+    carries nvidia-smi's own timestamp; only the samples between ``mark_start()`` and ``stop()`` are used."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         self.p = None
+        self.t0 = None
         try:
             self.p = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}",
                                        "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
@@ -76,7 +84,11 @@ class ClockSampler:
         except OSError:
             pass
 
+    def mark_start(self):
+        self.t0 = time.time()
+
     def stop(self):
+        t1 = time.time()
         if self.p is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.p.terminate()
@@ -85,20 +97,26 @@ class ClockSampler:
         except subprocess.TimeoutExpired:
             self.p.kill()
             out, _ = self.p.communicate()
-        sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        rows = []                                           # (inside the timed region?, sm, max sm, active reasons)
         for line in out.strip().splitlines():
             f = [x.strip() for x in line.split(",")]
-            if len(f) < 6:
+            if len(f) < 7:
                 continue
             try:
-                sm.append(float(f[0]))
-                mx.append(float(f[1]))
+                sm_v, mx_v = float(f[1]), float(f[2])
             except ValueError:
                 continue
-            for n, v in zip(names, f[2:6]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
+            inside = True
+            try:
+                ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                inside = self.t0 is None or (self.t0 - 0.05 <= ts <= t1 + 0.05)
+            except ValueError:
+                pass                                        # unknown timestamp format: keep the sample
+            rows.append((inside, sm_v, mx_v, [n for n, v in zip(names, f[3:7]) if v.lower().startswith("active")]))
+        used = [r for r in rows if r[0]] or rows            # a timed region shorter than one sampling period: use all
+        sm, mx = [r[1] for r in used], [r[2] for r in used]
+        reasons = {n for r in used for n in r[3]}
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "samples": len(sm), "reasons": sorted(reasons)}
 
@@ -337,12 +355,14 @@ class Measurement:
         from e2fgvi_b200 import ops
         res = {}
         with torch.no_grad():
+            sampler = ClockSampler(self.dev.index) if (sample_clocks and self.rank == 0) else None
             self._loop(self.warmup, self.dev_sets)
             self.sync()
-            sampler = ClockSampler(self.dev.index) if (sample_clocks and self.rank == 0) else None
             n0 = ops.launch_count()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             self.sync()
+            if sampler:
+                sampler.mark_start()
             e0.record()
             self._loop(self.steps, self.dev_sets)
             e1.record()
